@@ -1,0 +1,195 @@
+/*
+ * kurosiwo_b200.h — C ABI of libkurosiwo_b200.so (sm_100a only).
+ *
+ * This is the drop-in boundary beneath the reference's Python surface.  The
+ * reference (Orion-AI-Lab/KuroSiwo) has no FFI of its own: its training hot
+ * path is `model(*inputs)` -> `criterion(output, mask)` -> `backward()` ->
+ * `optimizer.step()` (training/change_detection_trainer.py:136-177), lowered
+ * to cuDNN/ATen kernels.  Every entry point below replaces one family of those
+ * library calls; the reference call site it replaces is cited per function.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers
+ *     unless the name says `host`.
+ *   - every function returns 0 on success, a negative KS_E* code on a bad
+ *     argument, or a positive cudaError_t from the launch.
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous.
+ *   - the caller owns every buffer (including workspaces).
+ *   - activations are NHWC ("pixels x channels") strided views: channel stride
+ *     is 1, the n/h/w strides are explicit so that channel slices of a concat
+ *     buffer and the 2x2-strided phases of a transposed conv are views.
+ *   - dtype: KS_F32 (parity mode, fp32 storage + fp32 FMA) or KS_BF16 (perf
+ *     mode, bf16 storage, fp32 accumulate; tcgen05 tensor cores).
+ */
+#ifndef KUROSIWO_B200_H
+#define KUROSIWO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KS_F32 0
+#define KS_BF16 1
+
+#define KS_OK 0
+#define KS_EINVAL (-1)      /* bad argument */
+#define KS_EUNSUPPORTED (-2) /* shape not handled by the requested implementation */
+#define KS_EDRIVER (-3)     /* driver entry point (TMA descriptor encode) unavailable */
+
+#define KS_IMPL_AUTO 0
+#define KS_IMPL_SIMT 1  /* CUDA-core implicit GEMM (parity mode / odd shapes) */
+#define KS_IMPL_TC 2    /* TMA + tcgen05 implicit GEMM (bf16 only) */
+
+#define KS_MAX_VIEWS 8
+
+/* Strided NHWC view; `ptr` addresses element (n=0,h=0,w=0,c=0) of the view. */
+typedef struct ks_view {
+  void *ptr;
+  int64_t sn, sh, sw; /* strides in ELEMENTS; channel stride is 1 */
+  int32_t C;          /* channels of this view */
+  int32_t _pad;
+} ks_view_t;
+
+/* ---- library ---------------------------------------------------------- */
+int ks_version(void);
+const char *ks_error_string(int code);
+/* Tuning/debug knobs: "tc_mt" (output windows per CTA), "tc_bo_mode", "tc_disable",
+ * "wgrad_tc_disable", "tc_sa", "tc_sb" (pipeline depths). Returns KS_EINVAL for unknown names. */
+int ks_set_option(const char *name, int value);
+
+/* ---- layout / precision plumbing --------------------------------------- */
+/* dst[i0][i1][i2][i3] (contiguous, dtype dst_dtype) = src[i0*s0+i1*s1+i2*s2+i3*s3]
+ * (dtype src_dtype).  Used for NCHW fp32 -> NHWC, OIHW -> [tap][Cout][Cin]
+ * weight packing and the inverse gradient unpacking.
+ * Replaces: `.to(device)` + cuDNN's internal layout transforms. */
+int ks_permute_cast(int src_dtype, const void *src, int dst_dtype, void *dst,
+                    int d0, int d1, int d2, int d3,
+                    int64_t s0, int64_t s1, int64_t s2, int64_t s3,
+                    int accumulate, void *stream);
+
+/* ---- convolution engine ------------------------------------------------ */
+/* out[n,h,w,co] (+)= bias[co] + sum_{tap,src,ci} x_src[n,h+dy,w+dx,ci] * w[tap][co][ci_global]
+ * ksize 3: taps (dy,dx) in row-major order over {-1,0,1}^2, zero padding 1.
+ * ksize 1: single tap.
+ * srcs: K-dimension concat (torch.cat along C never materialised, snunet.py:132-144).
+ * dsts: N-dimension split; dst_accumulate[i]!=0 -> read-modify-write (+=).
+ * Used as forward conv (snunet.py:15-17 nn.Conv2d), as data-gradient conv with
+ * tap-flipped/transposed weights, and for the four phases of
+ * ConvTranspose2d(k=2,s=2) (snunet.py:41) and its data gradient.
+ * weight: [taps][Cout_total][Cin_total] in `dtype`; bias fp32 [Cout_total] or NULL.
+ * stats (optional, fp64 [2][Cout_total], pre-zeroed): per-channel sum and sum
+ * of squares of the stored output (BatchNorm batch statistics, snunet.py:23,27). */
+int ks_conv2d(int dtype, int N, int H, int W, int ksize,
+              const ks_view_t *srcs, int n_src,
+              const void *weight, const float *bias,
+              const ks_view_t *dsts, int n_dst, const int *dst_accumulate,
+              double *stats, int impl, void *stream);
+
+/* dw[tap][co_global][ci_global] (+)= sum_{n,h,w} dy_j[n,h,w,co] * x_i[n,h+dy,w+dx,ci]
+ * (fp32 output).  Replaces cuDNN wgrad for nn.Conv2d / nn.ConvTranspose2d. */
+int ks_conv2d_wgrad(int dtype, int N, int H, int W, int ksize,
+                    const ks_view_t *xs, int n_x,
+                    const ks_view_t *dys, int n_dy,
+                    float *dw, int accumulate, int impl, void *stream);
+
+/* ---- BatchNorm (training mode) + ReLU + residual + pool ----------------- */
+/* sums[0][c] += sum x, sums[1][c] += sum x^2 (fp64, caller zeroes). snunet.py:23,27 */
+int ks_bn_stats(int dtype, int N, int H, int W, const ks_view_t *x, double *sums, void *stream);
+
+/* mean/var from sums; scale=gamma*rstd, shift=beta-mean*scale; running stats
+ * updated with `momentum` and the unbiased variance (nn.BatchNorm2d training). */
+int ks_bn_finalize(int C, double count, const double *sums, const float *gamma,
+                   const float *beta, float eps, float momentum,
+                   float *running_mean, float *running_var,
+                   float *scale, float *shift, float *mean, float *rstd, void *stream);
+
+/* out = act(y*scale+shift (+res)); optional 2x2/s2 max-pooled copy to `pool`
+ * (snunet.py:23-28 bn+relu(+identity), :73 MaxPool2d). H,W are y's dims. */
+int ks_bn_act(int dtype, int N, int H, int W, const ks_view_t *y,
+              const float *scale, const float *shift, const ks_view_t *res,
+              int relu, const ks_view_t *out, const ks_view_t *pool, void *stream);
+
+/* g = dout * (out>0);  sums[0][c] += sum g,  sums[1][c] += sum g*xhat. */
+int ks_bn_bwd_reduce(int dtype, int N, int H, int W, const ks_view_t *dout,
+                     const ks_view_t *out, const ks_view_t *y,
+                     const float *mean, const float *rstd, double *sums, void *stream);
+
+/* dy = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M) (+ add_dout*(add_out>0)).
+ * dgamma = sum_gx, dbeta = sum_g written as fp32 (+= if accumulate). */
+int ks_bn_bwd_apply(int dtype, int N, int H, int W, const ks_view_t *dout,
+                    const ks_view_t *out, const ks_view_t *y,
+                    const float *mean, const float *rstd, const float *gamma,
+                    const double *sums, double count,
+                    const ks_view_t *add_dout, const ks_view_t *add_out,
+                    const ks_view_t *dy, float *dgamma, float *dbeta,
+                    int accumulate_param_grads, void *stream);
+
+/* dx[n,2h+i,2w+j,c] (+)= dpool[n,h,w,c] at the first max of each 2x2 window
+ * (H,W are the POOLED dims). aten max_pool2d_with_indices_backward. */
+int ks_maxpool2x2_bwd(int dtype, int N, int H, int W, const ks_view_t *x,
+                      const ks_view_t *dpool, const ks_view_t *dx, int accumulate, void *stream);
+
+/* out[c] (+)= sum_{n,h,w} x[n,h,w,c]  (conv bias gradients). */
+int ks_channel_sum(int dtype, int N, int H, int W, const ks_view_t *x, float *out,
+                   int accumulate, void *stream);
+
+/* ---- ECAM head (snunet.py:49-62,146-151) ------------------------------- */
+/* Global avg+max pool of cat(x_0..x_{J-1}) (J*Cb channels) and of intra=sum_j x_j
+ * (Cb channels).  pooled: fp32 [N][2][(J+1)*Cb]  (avg | max; cat channels then intra);
+ * argmax: int32 [N][(J+1)*Cb] flat pixel index of the first maximum. */
+int ks_ecam_pool(int dtype, int N, int H, int W, const ks_view_t *xs, int J,
+                 float *pooled, int *argmax, unsigned long long *scratch, void *stream);
+
+/* gates: ca[N][J*Cb] = sigmoid(fc2(relu(fc1(avg))) + fc2(relu(fc1(max)))), same for ca1[N][Cb].
+ * hidden: fp32 [N][2][hid+hid1] pre-ReLU hidden activations kept for backward. */
+int ks_ecam_gates(int N, int Cb, int J, int hid, int hid1, const float *pooled,
+                  const float *w_fc1, const float *w_fc2, const float *w1_fc1, const float *w1_fc2,
+                  float *gates, float *hidden, void *stream);
+
+/* logits[n,k,h,w] = bf[k] + sum_c wf[k][c] * ca[n,c]*(x[c] + ca1[n, c%Cb])   (NCHW fp32 out) */
+int ks_ecam_final(int dtype, int N, int H, int W, const ks_view_t *xs, int J,
+                  const float *gates, const float *wf, const float *bf, int K,
+                  float *logits, void *stream);
+
+/* Pixel reductions of the head backward (callee zeroes `red`):
+ * red: fp64 [N][K*J*Cb + K] = { B[k][c] = sum_px dlogits[k]*x[c] , D[k] = sum_px dlogits[k] }. */
+int ks_ecam_bwd_reduce(int dtype, int N, int H, int W, const ks_view_t *xs, int J, int K,
+                       const float *dlogits, double *red, void *stream);
+
+/* Backward of ks_ecam_gates and of the classifier weights: dpooled fp32 [N][2][(J+1)*Cb];
+ * dwf [K][J*Cb], dbf [K] and the fc weight grads are fp32 (+= if accumulate). */
+int ks_ecam_gates_bwd(int N, int Cb, int J, int hid, int hid1, int K, const float *pooled,
+                      const float *hidden, const float *gates, const double *red, const float *wf,
+                      const float *w_fc1, const float *w_fc2, const float *w1_fc1, const float *w1_fc2,
+                      float *dpooled, float *dwf, float *dbf, float *dw_fc1, float *dw_fc2,
+                      float *dw1_fc1, float *dw1_fc2, int accumulate, void *stream);
+
+/* dx_j = ca*dO + avg/max-pool and intra gradients (assign). */
+int ks_ecam_bwd_apply(int dtype, int N, int H, int W, int J, int Cb,
+                      const float *gates, const float *wf, int K, const float *dlogits,
+                      const float *dpooled, const int *argmax, const ks_view_t *dxs, void *stream);
+
+/* ---- loss (utilities/bce_and_dice.py:18-24, utilities/dice.py:93-137) --- */
+/* Fused softmax -> weighted CE(ignore_index) + Dice, forward + gradient + argmax.
+ * logits: NCHW fp32 [N][C][HW] (C==3); labels int64 [N][HW].
+ * loss_out: fp32[3] = {total, dice, ce}; dlogits NCHW fp32 scaled by grad_scale
+ * (may be NULL: forward only); pred: uint8 [N][HW] argmax (may be NULL).
+ * workspace: ks_ce_dice_workspace_bytes(N) bytes, contents ignored. */
+int64_t ks_ce_dice_workspace_bytes(int N);
+int ks_ce_dice_fwd_bwd(const float *logits, const int64_t *labels, int N, int C, int64_t HW,
+                       const float *class_weights, int ignore_index, float grad_scale,
+                       float *loss_out, float *dlogits, uint8_t *pred,
+                       void *workspace, void *stream);
+
+/* ---- optimizer (torch.optim.Adam, change_detection_trainer.py:52-54) ---- */
+/* step_ptr: device int32 counter, incremented by the kernel (graph-capturable). */
+int ks_adam_step(float *p, const float *g, float *m, float *v, int64_t n,
+                 float lr, float beta1, float beta2, float eps, float weight_decay,
+                 float grad_scale, int *step_ptr, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KUROSIWO_B200_H */

@@ -1,0 +1,340 @@
+// TMA + tcgen05 implicit-GEMM convolution for sm_100a (bf16 NHWC, fp32 accumulate in TMEM).
+//
+//   out[pixel, co] = bias[co] + sum_{tap, src, ci} x_src[pixel + tap, ci] * w[tap][co][ci]
+//
+// Mapping: M = 128 output pixels (an 8-row x 16-column spatial window, of which 14 columns are
+// real outputs for 3x3), N = Cout tile (<=256), K = (source, 64- or 32-channel chunk, tap).
+//
+// Halo reuse: for each K chunk ONE TMA box of (8+2) x 16 pixels x BK channels lands in shared
+// memory (zero-filled outside the image = the conv padding).  Because the box pitch is exactly
+// 16 pixels, the operand of tap (r,s) is the SAME smem tile viewed from row offset r*16+s: 128
+// consecutive 128-byte rows.  So the nine taps are nine UMMA descriptors over one tile; L2->SMEM
+// activation traffic is 1.43x the input instead of 9x (im2col / per-tap loads).
+// Weights stream through a second mbarrier ring, one [BN x BK] K-major tile per (chunk, tap).
+// MT output windows share every weight tile (MT accumulators of BN TMEM columns each).
+//
+// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer,
+// warps2-5 = epilogue (TMEM -> registers -> +bias (+=dst) -> bf16 -> global).
+//
+// Replaces: cuDNN fprop/dgrad behind nn.Conv2d / nn.ConvTranspose2d (models/snunet.py:15,17,41)
+// and the torch.cat copies of models/snunet.py:132-144 (K loop walks the source views).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace ks {
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+Options g_opt = {0, 0, 0, 0, 0, 0};
+
+struct alignas(64) ConvTcParams {
+  CUtensorMap src[KS_MAX_VIEWS];
+  CUtensorMap wmap;
+  ViewList dsts;
+  const float *bias;
+  int cstart[KS_MAX_VIEWS + 1];
+  int n_src, acc_mask;
+  int N, H, W, tiles_w, tiles_h, total_tiles;
+  int BN, MT, SA, SB, TH, bo_mode;
+  uint32_t a_tile_bytes, b_stage_bytes, tmem_cols, idesc;
+};
+
+using namespace tc;
+
+template <int BK, int KS>
+__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int TW = (KS == 3) ? 14 : 16;
+  constexpr int PADK = KS / 2;
+  constexpr int BOX_ROWS = (KS == 3) ? 10 : 8;
+  constexpr uint32_t ROW_BYTES = BK * 2;
+  constexpr uint32_t A_BOX_BYTES = BOX_ROWS * 16 * ROW_BYTES;
+  constexpr uint32_t LAYOUT = (BK == 64) ? LAYOUT_SW128 : LAYOUT_SW64;
+  constexpr uint32_t SBO = 8 * ROW_BYTES;
+  constexpr int TAPS = KS * KS;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int SA = p.SA, SB = p.SB, MT = p.MT, BN = p.BN;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *sm = smem_raw + (base - raw);
+  const uint32_t a_base = base;
+  const uint32_t b_base = a_base + (uint32_t)SA * MT * p.a_tile_bytes;
+  const uint32_t bar_base = b_base + (uint32_t)SB * p.b_stage_bytes;
+  auto a_full = [&](int i) { return bar_base + 8u * i; };
+  auto a_empty = [&](int i) { return bar_base + 8u * (SA + i); };
+  auto b_full = [&](int i) { return bar_base + 8u * (2 * SA + i); };
+  auto b_empty = [&](int i) { return bar_base + 8u * (2 * SA + SB + i); };
+  const uint32_t acc_full = bar_base + 8u * (2 * SA + 2 * SB);
+  const uint32_t tmem_slot = acc_full + 8u;
+  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(sm + (tmem_slot - base));
+
+  // this CTA's output windows
+  const int t0 = blockIdx.x * MT;
+  const int nvalid = min(MT, p.total_tiles - t0);
+  const int n0 = blockIdx.y * BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.n_src; ++s) prefetch_tmap(&p.src[s]);
+    prefetch_tmap(&p.wmap);
+    for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      for (int s = 0; s < p.n_src; ++s) {
+        const int C = p.cstart[s + 1] - p.cstart[s];
+        for (int c0 = 0; c0 < C; c0 += BK) {
+          mbar_wait(a_empty(sa), pa ^ 1);
+          mbar_expect_tx(a_full(sa), (uint32_t)nvalid * A_BOX_BYTES);
+          for (int mt = 0; mt < nvalid; ++mt) {
+            const int t = t0 + mt;
+            const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, n = t / (p.tiles_w * p.tiles_h);
+            tma_load_4d(a_base + (uint32_t)(sa * MT + mt) * p.a_tile_bytes, &p.src[s], c0, tw * TW - PADK, th * p.TH - PADK, n, a_full(sa));
+          }
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+          for (int tap = 0; tap < TAPS; ++tap) {
+            mbar_wait(b_empty(sb), pb ^ 1);
+            mbar_expect_tx(b_full(sb), p.b_stage_bytes);
+            tma_load_3d(b_base + (uint32_t)sb * p.b_stage_bytes, &p.wmap, p.cstart[s] + c0, n0, tap, b_full(sb));
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      bool first = true;
+      for (int s = 0; s < p.n_src; ++s) {
+        const int C = p.cstart[s + 1] - p.cstart[s];
+        for (int c0 = 0; c0 < C; c0 += BK) {
+          mbar_wait(a_full(sa), pa);
+          for (int tap = 0; tap < TAPS; ++tap) {
+            mbar_wait(b_full(sb), pb);
+            tc_fence_after();
+            const uint32_t b_addr = b_base + (uint32_t)sb * p.b_stage_bytes;
+            const uint32_t row_off = (KS == 3) ? (uint32_t)((tap / 3) * 16 + (tap % 3)) : 0u;
+            for (int mt = 0; mt < nvalid; ++mt) {
+              const uint32_t a_addr = a_base + (uint32_t)(sa * MT + mt) * p.a_tile_bytes + row_off * ROW_BYTES;
+              const uint32_t bo = p.bo_mode ? ((a_addr >> 7) & 7u) : 0u;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, SBO, LAYOUT, bo);
+                const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, SBO, LAYOUT, 0);
+                umma_bf16(tmem_base + (uint32_t)(mt * BN), ad, bd, p.idesc, (first && k == 0) ? 0u : 1u);
+              }
+            }
+            first = false;
+            tc_commit(b_empty(sb));
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+          tc_commit(a_empty(sa));
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+        }
+      }
+      tc_commit(acc_full);
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane group = warp % 4 =====
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    const int ty = row >> 4, tx = row & 15;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    for (int mt = 0; mt < nvalid; ++mt) {
+      const int t = t0 + mt;
+      const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, n = t / (p.tiles_w * p.tiles_h);
+      const int h = th * p.TH + ty, w = tw * TW + tx;
+      const bool ok = (tx < TW) && (ty < p.TH) && (h < p.H) && (w < p.W);
+      for (int cc = 0; cc < BN; cc += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mt * BN + cc), r);
+        tmem_ld_wait();
+        if (ok) {
+          const int co = n0 + cc;
+          int d = 0;
+#pragma unroll
+          for (int i = 1; i < KS_MAX_VIEWS; ++i) if (i < p.dsts.n && co >= p.dsts.cstart[i]) d = i;
+          const View &dv = p.dsts.v[d];
+          __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(dv.ptr) +
+                              ((long long)n * dv.sn + (long long)h * dv.sh + (long long)w * dv.sw + (co - p.dsts.cstart[d]));
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + co + i) : 0.f);
+          if ((p.acc_mask >> d) & 1) {
+            float o[8];
+            ld8(op, o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += o[i];
+            ld8(op + 8, o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 + i] += o[i];
+          }
+          float a[8], b[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { a[i] = v[i]; b[i] = v[8 + i]; }
+          st8(op, a);
+          st8(op + 8, b);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
+}
+
+static bool tma_view_ok(const View &v) {
+  return (((uintptr_t)v.ptr) % 16 == 0) && ((v.sn * 2) % 16 == 0) && ((v.sh * 2) % 16 == 0) && ((v.sw * 2) % 16 == 0) &&
+         v.sw > 0 && v.sh > 0 && v.sn > 0;
+}
+
+int encode_act_map(CUtensorMap *m, const View &v, int N, int H, int W, int box_c, int box_w, int box_h, CUtensorMapSwizzle sw) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return KS_EDRIVER;
+  cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)v.ptr, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? KS_OK : KS_EDRIVER;
+}
+
+template <int BK, int KS>
+static int launch_conv_tc(const ConvTcParams &p, dim3 grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BK, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  conv_tc_kernel<BK, KS><<<grid, 192, smem, st>>>(p);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ks_bn_stats(int dtype, int N, int H, int W, const ks_view_t *x, double *sums, void *stream);
+
+int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *weight, const float *bias,
+              const ViewList &dsts, int acc_mask, double *stats, cudaStream_t st) {
+  if (g_opt.tc_disable) return KS_EUNSUPPORTED;
+  const int Cin = srcs.cstart[srcs.n], Cout = dsts.cstart[dsts.n];
+  bool all64 = true;
+  for (int s = 0; s < srcs.n; ++s) {
+    if (srcs.v[s].C % 32) return KS_EUNSUPPORTED;
+    if (srcs.v[s].C % 64) all64 = false;
+    if (!tma_view_ok(srcs.v[s])) return KS_EUNSUPPORTED;
+  }
+  for (int d = 0; d < dsts.n; ++d) {
+    if (dsts.cstart[d] % 16 || dsts.v[d].C % 16) return KS_EUNSUPPORTED;
+    if (!tma_view_ok(dsts.v[d])) return KS_EUNSUPPORTED;
+  }
+  if (((uintptr_t)weight) % 16) return KS_EUNSUPPORTED;
+  if (stats && dsts.n != 1) return KS_EUNSUPPORTED;
+  const int BK = all64 ? 64 : 32;
+  int nt = 1;
+  for (;; ++nt) {
+    if (nt > 64) return KS_EUNSUPPORTED;
+    if (Cout % nt == 0 && (Cout / nt) <= 256 && (Cout / nt) % 16 == 0) break;
+  }
+  ConvTcParams p;
+  p.BN = Cout / nt;
+  int MT = g_opt.mt > 0 ? g_opt.mt : 1;
+  while (MT > 1 && MT * p.BN > 512) MT >>= 1;
+  p.MT = MT;
+  p.TH = (ksize == 3) ? ((H % 8 == 0) ? 8 : ((H % 7 == 0) ? 7 : 8)) : 8;
+  const int TW = (ksize == 3) ? 14 : 16;
+  p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + p.TH - 1) / p.TH;
+  const long long tt = (long long)p.tiles_w * p.tiles_h * N;
+  if (tt > 0x7fffffffLL) return KS_EUNSUPPORTED;
+  p.total_tiles = (int)tt;
+  p.N = N; p.H = H; p.W = W;
+  p.n_src = srcs.n; p.acc_mask = acc_mask; p.bias = bias; p.dsts = dsts;
+  for (int i = 0; i <= KS_MAX_VIEWS; ++i) p.cstart[i] = srcs.cstart[i];
+  p.bo_mode = g_opt.bo_mode;
+  const uint32_t row_bytes = BK * 2;
+  const uint32_t a_rows = (ksize == 3) ? 162 : 128;
+  p.a_tile_bytes = ((a_rows * row_bytes + 1023) / 1024) * 1024;
+  p.b_stage_bytes = (uint32_t)p.BN * row_bytes;
+  uint32_t cols = 32; while (cols < (uint32_t)(MT * p.BN)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
+  // pipeline depth under the 227 KB budget
+  int SA = g_opt.sa > 0 ? g_opt.sa : 3, SB = g_opt.sb > 0 ? g_opt.sb : 4;
+  auto bytes = [&](int sa, int sb) { return (size_t)sa * MT * p.a_tile_bytes + (size_t)sb * p.b_stage_bytes + 1024 + 256; };
+  const size_t budget = 220 * 1024;
+  while (bytes(SA, SB) > budget && SB > 2) --SB;
+  while (bytes(SA, SB) > budget && SA > 2) --SA;
+  if (bytes(SA, SB) > budget) return KS_EUNSUPPORTED;
+  p.SA = SA; p.SB = SB;
+  const CUtensorMapSwizzle sw = (BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  for (int s = 0; s < srcs.n; ++s) {
+    int rc = encode_act_map(&p.src[s], srcs.v[s], N, H, W, BK, 16, (ksize == 3) ? 10 : 8, sw);
+    if (rc) return rc;
+  }
+  {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return KS_EDRIVER;
+    const int taps = ksize * ksize;
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * Cout * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)p.BN, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    if ((Cin * 2) % 16) return KS_EUNSUPPORTED;
+    CUresult r = enc(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)weight, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return KS_EDRIVER;
+  }
+  dim3 grid((unsigned)((p.total_tiles + MT - 1) / MT), (unsigned)nt);
+  const size_t smem = bytes(SA, SB);
+  int rc;
+  if (BK == 64 && ksize == 3) rc = launch_conv_tc<64, 3>(p, grid, smem, st);
+  else if (BK == 64 && ksize == 1) rc = launch_conv_tc<64, 1>(p, grid, smem, st);
+  else if (BK == 32 && ksize == 3) rc = launch_conv_tc<32, 3>(p, grid, smem, st);
+  else rc = launch_conv_tc<32, 1>(p, grid, smem, st);
+  if (rc) return rc;
+  if (stats) {
+    ks_view_t dv; dv.ptr = dsts.v[0].ptr; dv.sn = dsts.v[0].sn; dv.sh = dsts.v[0].sh; dv.sw = dsts.v[0].sw; dv.C = dsts.v[0].C; dv._pad = 0;
+    return ks_bn_stats(KS_BF16, N, H, W, &dv, stats, (void *)st);
+  }
+  return KS_OK;
+}
+
+}  // namespace ks
+
+extern "C" int ks_set_option(const char *name, int value) {
+  if (!name) return KS_EINVAL;
+  auto eq = [&](const char *s) { const char *a = name; while (*a && *a == *s) { ++a; ++s; } return *a == 0 && *s == 0; };
+  if (eq("tc_mt")) ks::g_opt.mt = value;
+  else if (eq("tc_bo_mode")) ks::g_opt.bo_mode = value;
+  else if (eq("tc_disable")) ks::g_opt.tc_disable = value;
+  else if (eq("wgrad_tc_disable")) ks::g_opt.wgrad_tc_disable = value;
+  else if (eq("tc_sa")) ks::g_opt.sa = value;
+  else if (eq("tc_sb")) ks::g_opt.sb = value;
+  else return KS_EINVAL;
+  return KS_OK;
+}

@@ -1,0 +1,504 @@
+// ECAM head of SNUNet (ensemble channel attention + 1x1 classifier), forward and backward.
+//
+// Reference: models/snunet.py:49-62 (ChannelAttention), :146-151
+//   out   = cat(x0_1..x0_4)                      (J*Cb channels, never materialised here)
+//   intra = x0_1 + x0_2 + x0_3 + x0_4            (Cb channels, never materialised here)
+//   ca    = CA_{J*Cb}(out), ca1 = CA_{Cb}(intra) (global avg+max pool -> fc1 -> relu -> fc2 -> sigmoid)
+//   logits = conv_final( ca * (out + ca1.repeat(1,J,1,1)) )
+// The reference runs ~14 ATen kernels and materialises `out`, `intra`, the repeat and the
+// gated tensor (4 x 128ch x 224^2 per sample).  Here: one pooling pass, one tiny gate kernel
+// and one pass that reads the four block outputs and writes the 3 logit planes.
+#include "common.cuh"
+
+namespace ks {
+
+__device__ __forceinline__ unsigned long long pack_max(float v, unsigned int idx) {
+  unsigned int b = __float_as_uint(v);
+  b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ((unsigned long long)b << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+}
+__device__ __forceinline__ float unpack_max_val(unsigned long long k) {
+  unsigned int b = (unsigned int)(k >> 32);
+  b = (b & 0x80000000u) ? (b & 0x7FFFFFFFu) : ~b;
+  return __uint_as_float(b);
+}
+
+template <typename T>
+__device__ __forceinline__ const T *vptr(const View &v, int n, int h, int w, int c) {
+  return reinterpret_cast<const T *>(v.ptr) + ((long long)n * v.sn + (long long)h * v.sh + (long long)w * v.sw + c);
+}
+
+constexpr int kMaxJ = 4;
+
+// ---- pooling: sums (fp32 atomics) and packed (max, first index) ---------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+ecam_pool_kernel(ViewList xs, int J, int Cb, int H, int W, float *pooled, unsigned long long *scratch) {
+  extern __shared__ unsigned char smem_raw[];
+  const int CT = (J + 1) * Cb;
+  unsigned long long *smax = reinterpret_cast<unsigned long long *>(smem_raw);
+  float *ssum = reinterpret_cast<float *>(smax + CT);
+  for (int i = threadIdx.x; i < CT; i += blockDim.x) { smax[i] = 0ull; ssum[i] = 0.f; }
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int CVb = Cb / 8, rows = blockDim.x / CVb;
+  const int tx = threadIdx.x % CVb, ty = threadIdx.x / CVb;
+  const int HW = H * W;
+  float sum[kMaxJ + 1][8], best[kMaxJ + 1][8]; unsigned int bidx[kMaxJ + 1][8];
+#pragma unroll
+  for (int j = 0; j <= kMaxJ; ++j)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sum[j][k] = 0.f; best[j][k] = -INFINITY; bidx[j][k] = 0u; }
+  bool any = false;
+  if (ty < rows) {
+    for (int p = blockIdx.x * rows + ty; p < HW; p += gridDim.x * rows) {
+      any = true;
+      const int h = p / W, w = p % W;
+      float it[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) it[k] = 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxJ; ++j) {
+        if (j < J) {
+          float f[8]; ld8(vptr<T>(xs.v[j], n, h, w, tx * 8), f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            sum[j][k] += f[k]; it[k] += f[k];
+            if (f[k] > best[j][k]) { best[j][k] = f[k]; bidx[j][k] = (unsigned)p; }
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        sum[kMaxJ][k] += it[k];
+        if (it[k] > best[kMaxJ][k]) { best[kMaxJ][k] = it[k]; bidx[kMaxJ][k] = (unsigned)p; }
+      }
+    }
+  }
+  if (any) {
+#pragma unroll
+    for (int j = 0; j <= kMaxJ; ++j) {
+      const int jj = (j == kMaxJ) ? J : j;
+      if (j < J || j == kMaxJ) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = jj * Cb + tx * 8 + k;
+          atomicAdd(&ssum[c], sum[j][k]);
+          atomicMax(&smax[c], pack_max(best[j][k], bidx[j][k]));
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CT; i += blockDim.x) {
+    atomicAdd(pooled + ((size_t)n * 2 + 0) * CT + i, ssum[i]);
+    atomicMax(scratch + (size_t)n * CT + i, smax[i]);
+  }
+}
+
+__global__ void ecam_pool_finalize_kernel(int N, int CT, int HW, float *pooled, const unsigned long long *scratch, int *argmax) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * CT) return;
+  const int n = i / CT, c = i % CT;
+  pooled[((size_t)n * 2 + 0) * CT + c] *= (1.0f / (float)HW);
+  const unsigned long long k = scratch[i];
+  pooled[((size_t)n * 2 + 1) * CT + c] = unpack_max_val(k);
+  argmax[i] = (int)(0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFull));
+}
+
+// ---- gates: one block per sample -----------------------------------------------------------
+__device__ __forceinline__ void ca_forward(int Cin, int hid, const float *avg, const float *mx,
+                                           const float *w1 /*[hid][Cin]*/, const float *w2 /*[Cin][hid]*/,
+                                           float *gate, float *h_avg, float *h_max, float *sh /* smem 2*hid */) {
+  for (int q = threadIdx.x; q < 2 * hid; q += blockDim.x) {
+    const int qq = q % hid; const float *src = (q < hid) ? avg : mx;
+    float s = 0.f;
+    for (int c = 0; c < Cin; ++c) s += w1[qq * Cin + c] * src[c];
+    sh[q] = s;
+    if (q < hid) h_avg[qq] = s; else h_max[qq] = s;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
+    float s = 0.f;
+    for (int q = 0; q < hid; ++q) s += w2[c * hid + q] * (fmaxf(sh[q], 0.f) + fmaxf(sh[hid + q], 0.f));
+    gate[c] = 1.0f / (1.0f + expf(-s));
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+ecam_gates_kernel(int Cb, int J, int hid, int hid1, const float *__restrict__ pooled,
+                  const float *__restrict__ w_fc1, const float *__restrict__ w_fc2,
+                  const float *__restrict__ w1_fc1, const float *__restrict__ w1_fc2,
+                  float *gates, float *hidden) {
+  __shared__ float sh[128];
+  const int n = blockIdx.x, CT = (J + 1) * Cb, CC = J * Cb, HT = hid + hid1;
+  const float *avg = pooled + ((size_t)n * 2 + 0) * CT, *mx = pooled + ((size_t)n * 2 + 1) * CT;
+  float *g = gates + (size_t)n * CT;
+  float *ha = hidden + ((size_t)n * 2 + 0) * HT, *hm = hidden + ((size_t)n * 2 + 1) * HT;
+  ca_forward(CC, hid, avg, mx, w_fc1, w_fc2, g, ha, hm, sh);
+  ca_forward(Cb, hid1, avg + CC, mx + CC, w1_fc1, w1_fc2, g + CC, ha + hid, hm + hid, sh);
+}
+
+// ---- final: gated sum + 1x1 classifier -> NCHW fp32 logits --------------------------------
+// 4 threads per pixel (one per concat source j), shuffle-reduced.
+template <typename T, int K>
+__global__ void __launch_bounds__(256)
+ecam_final_kernel(ViewList xs, int J, int Cb, int H, int W, const float *__restrict__ gates,
+                  const float *__restrict__ wf, const float *__restrict__ bf, float *logits) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.y, CC = J * Cb, CT = (J + 1) * Cb;
+  float *weff = sm;             // [K][CC]
+  float *cst = sm + K * CC;     // [K]
+  const float *g = gates + (size_t)n * CT;
+  for (int i = threadIdx.x; i < K * CC; i += blockDim.x) weff[i] = wf[i] * g[i % CC];
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float s = bf[threadIdx.x];
+    for (int c = 0; c < CC; ++c) s += weff[threadIdx.x * CC + c] * g[CC + (c % Cb)];
+    cst[threadIdx.x] = s;
+  }
+  __syncthreads();
+  const int HW = H * W;
+  const int j = threadIdx.x & 3;
+  for (int p = blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2); p < ((HW + 63) / 64) * 64; p += gridDim.x * (blockDim.x >> 2)) {
+    float acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.f;
+    const bool ok = p < HW;
+    if (ok && j < J) {
+      const int h = p / W, w = p % W;
+      for (int c0 = 0; c0 < Cb; c0 += 8) {
+        float f[8]; ld8(vptr<T>(xs.v[j], n, h, w, c0), f);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float *wk = weff + k * CC + j * Cb + c0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[k] = fmaf(f[i], wk[i], acc[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
+      acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
+    }
+    if (ok && j < K) {
+      float v = acc[0];
+#pragma unroll
+      for (int k = 1; k < K; ++k) if (j == k) v = acc[k];
+      logits[((size_t)n * K + j) * HW + p] = v + cst[j];
+    }
+  }
+}
+
+// ---- backward reductions: B[n][k][c] = sum_px dl[k]*x[c],  D[n][k] = sum_px dl[k] ---------
+template <typename T, int K>
+__global__ void __launch_bounds__(256)
+ecam_bwd_reduce_kernel(ViewList xs, int J, int Cb, int H, int W, const float *__restrict__ dlogits, double *red) {
+  extern __shared__ float sacc[];  // [K*CC + K]
+  const int n = blockIdx.y, CC = J * Cb, HW = H * W, RT = K * CC + K;
+  for (int i = threadIdx.x; i < RT; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int CVb = Cb / 8, rows = blockDim.x / CVb;
+  const int tx = threadIdx.x % CVb, ty = threadIdx.x / CVb;
+  float B[K][kMaxJ][8], D[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    D[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxJ; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) B[k][j][i] = 0.f;
+  }
+  bool any = false;
+  if (ty < rows) {
+    for (int p = blockIdx.x * rows + ty; p < HW; p += gridDim.x * rows) {
+      any = true;
+      const int h = p / W, w = p % W;
+      float dl[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) { dl[k] = __ldg(dlogits + ((size_t)n * K + k) * HW + p); D[k] += dl[k]; }
+#pragma unroll
+      for (int j = 0; j < kMaxJ; ++j) {
+        if (j < J) {
+          float f[8]; ld8(vptr<T>(xs.v[j], n, h, w, tx * 8), f);
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) B[k][j][i] = fmaf(dl[k], f[i], B[k][j][i]);
+        }
+      }
+    }
+  }
+  if (any) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int j = 0; j < kMaxJ; ++j)
+        if (j < J) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) atomicAdd(&sacc[k * CC + j * Cb + tx * 8 + i], B[k][j][i]);
+        }
+      if (tx == 0) atomicAdd(&sacc[K * CC + k], D[k]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < RT; i += blockDim.x) atomicAdd(red + (size_t)n * RT + i, (double)sacc[i]);
+}
+
+// ---- gates backward: single block, loops over samples (deterministic) ----------------------
+// smem layout helper
+__global__ void __launch_bounds__(256)
+ecam_gates_bwd_kernel(int N, int Cb, int J, int hid, int hid1, int K,
+                      const float *__restrict__ pooled, const float *__restrict__ hidden,
+                      const float *__restrict__ gates, const double *__restrict__ red,
+                      const float *__restrict__ wf, const float *__restrict__ w_fc1, const float *__restrict__ w_fc2,
+                      const float *__restrict__ w1_fc1, const float *__restrict__ w1_fc2,
+                      float *dpooled, float *dwf, float *dbf, float *dw_fc1, float *dw_fc2,
+                      float *dw1_fc1, float *dw1_fc2, int accumulate) {
+  extern __shared__ float sm[];
+  const int CC = J * Cb, CT = (J + 1) * Cb, HT = hid + hid1, RT = K * CC + K;
+  // accumulators (over n) in smem
+  float *a_wf = sm;                       // K*CC
+  float *a_bf = a_wf + K * CC;            // K
+  float *a_fc1 = a_bf + K;                // hid*CC
+  float *a_fc2 = a_fc1 + hid * CC;        // CC*hid
+  float *a1_fc1 = a_fc2 + CC * hid;       // hid1*Cb
+  float *a1_fc2 = a1_fc1 + hid1 * Cb;     // Cb*hid1
+  float *ds = a1_fc2 + Cb * hid1;         // CT   (d pre-sigmoid)
+  float *dh = ds + CT;                    // 2*HT (d hidden pre-relu: avg | max)
+  const int nacc = (int)(ds - sm);
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  for (int n = 0; n < N; ++n) {
+    const double *R = red + (size_t)n * RT;
+    const float *g = gates + (size_t)n * CT;
+    const float *avg = pooled + ((size_t)n * 2 + 0) * CT, *mx = pooled + ((size_t)n * 2 + 1) * CT;
+    const float *ha = hidden + ((size_t)n * 2 + 0) * HT, *hm = hidden + ((size_t)n * 2 + 1) * HT;
+    // d_ca, d_ca1 -> d pre-sigmoid; classifier grads
+    for (int c = threadIdx.x; c < CC; c += blockDim.x) {
+      const float ca1 = g[CC + (c % Cb)];
+      float dca = 0.f;
+      for (int k = 0; k < K; ++k) {
+        const float A = (float)R[k * CC + c] + ca1 * (float)R[K * CC + k];
+        dca += wf[k * CC + c] * A;
+        a_wf[k * CC + c] += g[c] * A;
+      }
+      ds[c] = dca * g[c] * (1.f - g[c]);
+    }
+    for (int cb = threadIdx.x; cb < Cb; cb += blockDim.x) {
+      float d = 0.f;
+      for (int j = 0; j < J; ++j) {
+        const int c = j * Cb + cb;
+        float t = 0.f;
+        for (int k = 0; k < K; ++k) t += wf[k * CC + c] * (float)R[K * CC + k];
+        d += g[c] * t;
+      }
+      const float gg = g[CC + cb];
+      ds[CC + cb] = d * gg * (1.f - gg);
+    }
+    if (threadIdx.x < K) a_bf[threadIdx.x] += (float)R[K * CC + threadIdx.x];
+    __syncthreads();
+    // hidden grads: d_relu[q] = sum_c ds[c]*w2[c][q]
+    for (int q = threadIdx.x; q < HT; q += blockDim.x) {
+      float s = 0.f;
+      if (q < hid) { for (int c = 0; c < CC; ++c) s += ds[c] * w_fc2[c * hid + q]; }
+      else { const int qq = q - hid; for (int c = 0; c < Cb; ++c) s += ds[CC + c] * w1_fc2[c * hid1 + qq]; }
+      dh[q] = (ha[q] > 0.f) ? s : 0.f;
+      dh[HT + q] = (hm[q] > 0.f) ? s : 0.f;
+    }
+    // fc2 weight grads: dW2[c][q] += ds[c]*(relu(ha[q])+relu(hm[q]))
+    for (int i = threadIdx.x; i < CC * hid; i += blockDim.x) {
+      const int c = i / hid, q = i % hid;
+      a_fc2[i] += ds[c] * (fmaxf(ha[q], 0.f) + fmaxf(hm[q], 0.f));
+    }
+    for (int i = threadIdx.x; i < Cb * hid1; i += blockDim.x) {
+      const int c = i / hid1, q = i % hid1;
+      a1_fc2[i] += ds[CC + c] * (fmaxf(ha[hid + q], 0.f) + fmaxf(hm[hid + q], 0.f));
+    }
+    __syncthreads();
+    // fc1 weight grads and pooled grads
+    for (int i = threadIdx.x; i < hid * CC; i += blockDim.x) {
+      const int q = i / CC, c = i % CC;
+      a_fc1[i] += dh[q] * avg[c] + dh[HT + q] * mx[c];
+    }
+    for (int i = threadIdx.x; i < hid1 * Cb; i += blockDim.x) {
+      const int q = i / Cb, c = i % Cb;
+      a1_fc1[i] += dh[hid + q] * avg[CC + c] + dh[HT + hid + q] * mx[CC + c];
+    }
+    for (int c = threadIdx.x; c < CT; c += blockDim.x) {
+      float da = 0.f, dm = 0.f;
+      if (c < CC) { for (int q = 0; q < hid; ++q) { da += dh[q] * w_fc1[q * CC + c]; dm += dh[HT + q] * w_fc1[q * CC + c]; } }
+      else { const int cb = c - CC; for (int q = 0; q < hid1; ++q) { da += dh[hid + q] * w1_fc1[q * Cb + cb]; dm += dh[HT + hid + q] * w1_fc1[q * Cb + cb]; } }
+      dpooled[((size_t)n * 2 + 0) * CT + c] = da;
+      dpooled[((size_t)n * 2 + 1) * CT + c] = dm;
+    }
+    __syncthreads();
+  }
+  auto flush = [&](float *dst, const float *src, int cnt) {
+    if (!dst) return;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = (accumulate ? dst[i] : 0.f) + src[i];
+  };
+  flush(dwf, a_wf, K * CC); flush(dbf, a_bf, K);
+  flush(dw_fc1, a_fc1, hid * CC); flush(dw_fc2, a_fc2, CC * hid);
+  flush(dw1_fc1, a1_fc1, hid1 * Cb); flush(dw1_fc2, a1_fc2, Cb * hid1);
+}
+
+// ---- backward apply: gradient of the four block outputs -------------------------------------
+template <typename T, int K>
+__global__ void __launch_bounds__(256)
+ecam_bwd_apply_kernel(ViewList dxs, int J, int Cb, int H, int W, const float *__restrict__ gates,
+                      const float *__restrict__ wf, const float *__restrict__ dlogits,
+                      const float *__restrict__ dpooled, const int *__restrict__ argmax) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.y, CC = J * Cb, CT = (J + 1) * Cb, HW = H * W;
+  float *weff = sm;                 // [K][CC]  ca*wf
+  float *base = weff + K * CC;      // [CC]     (d_avg_cat + d_avg_intra)/HW
+  float *dmx = base + CC;           // [CT]     d_max (cat | intra)
+  int *amx = reinterpret_cast<int *>(dmx + CT);  // [CT]
+  const float *g = gates + (size_t)n * CT;
+  const float *da = dpooled + ((size_t)n * 2 + 0) * CT, *dm = dpooled + ((size_t)n * 2 + 1) * CT;
+  const float inv = 1.0f / (float)HW;
+  for (int i = threadIdx.x; i < K * CC; i += blockDim.x) weff[i] = wf[i] * g[i % CC];
+  for (int c = threadIdx.x; c < CC; c += blockDim.x) base[c] = (da[c] + da[CC + (c % Cb)]) * inv;
+  for (int c = threadIdx.x; c < CT; c += blockDim.x) { dmx[c] = dm[c]; amx[c] = argmax[(size_t)n * CT + c]; }
+  __syncthreads();
+  const int j = threadIdx.x & 3;
+  for (int p = blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2); p < HW; p += gridDim.x * (blockDim.x >> 2)) {
+    if (j >= J) continue;
+    const int h = p / W, w = p % W;
+    float dl[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) dl[k] = __ldg(dlogits + ((size_t)n * K + k) * HW + p);
+    for (int c0 = 0; c0 < Cb; c0 += 8) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int cb = c0 + i, c = j * Cb + cb;
+        float v = base[c];
+#pragma unroll
+        for (int k = 0; k < K; ++k) v = fmaf(weff[k * CC + c], dl[k], v);
+        if (amx[c] == p) v += dmx[c];
+        if (amx[CC + cb] == p) v += dmx[CC + cb];
+        o[i] = v;
+      }
+      T *dst = reinterpret_cast<T *>(dxs.v[j].ptr) + ((long long)n * dxs.v[j].sn + (long long)h * dxs.v[j].sh + (long long)w * dxs.v[j].sw + c0);
+      st8(dst, o);
+    }
+  }
+}
+
+static int check_views(const ks_view_t *xs, int J, int &Cb, int esize) {
+  if (!xs || J < 1 || J > kMaxJ) return KS_EINVAL;
+  Cb = xs[0].C;
+  if (Cb % 8 != 0 || Cb > 64) return KS_EUNSUPPORTED;
+  for (int j = 0; j < J; ++j) {
+    if (xs[j].C != Cb || !xs[j].ptr) return KS_EINVAL;
+    if (((uintptr_t)xs[j].ptr % 16) || (xs[j].sn * esize) % 16 || (xs[j].sh * esize) % 16 || (xs[j].sw * esize) % 16) return KS_EUNSUPPORTED;
+  }
+  return KS_OK;
+}
+
+}  // namespace ks
+
+using namespace ks;
+
+extern "C" int ks_ecam_pool(int dtype, int N, int H, int W, const ks_view_t *xs, int J,
+                            float *pooled, int *argmax, unsigned long long *scratch, void *stream) {
+  KS_CHECK_ARG(pooled && argmax && scratch && N > 0 && H > 0 && W > 0);
+  int Cb; int rc = check_views(xs, J, Cb, dtype == KS_F32 ? 4 : 2); if (rc) return rc;
+  ViewList vl; rc = make_view_list(xs, J, vl); if (rc) return rc;
+  const int CT = (J + 1) * Cb;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(pooled, 0, sizeof(float) * (size_t)N * 2 * CT, st); if (e) return (int)e;
+  e = cudaMemsetAsync(scratch, 0, sizeof(unsigned long long) * (size_t)N * CT, st); if (e) return (int)e;
+  const int rows = 256 / (Cb / 8);
+  int chunks = (H * W + rows * 16 - 1) / (rows * 16); if (chunks < 1) chunks = 1;
+  const int cap = (kNumSMs * 8 + N - 1) / N; if (chunks > cap) chunks = cap;
+  const size_t smem = (size_t)CT * (sizeof(unsigned long long) + sizeof(float));
+  if (dtype == KS_F32) ecam_pool_kernel<float><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, pooled, scratch);
+  else if (dtype == KS_BF16) ecam_pool_kernel<__nv_bfloat16><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, pooled, scratch);
+  else return KS_EINVAL;
+  ecam_pool_finalize_kernel<<<(N * CT + 255) / 256, 256, 0, st>>>(N, CT, H * W, pooled, scratch, argmax);
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_ecam_gates(int N, int Cb, int J, int hid, int hid1, const float *pooled,
+                             const float *w_fc1, const float *w_fc2, const float *w1_fc1, const float *w1_fc2,
+                             float *gates, float *hidden, void *stream) {
+  KS_CHECK_ARG(N > 0 && Cb > 0 && J > 0 && hid > 0 && hid1 > 0 && 2 * hid <= 128 && 2 * hid1 <= 128);
+  KS_CHECK_ARG(pooled && w_fc1 && w_fc2 && w1_fc1 && w1_fc2 && gates && hidden);
+  ecam_gates_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(Cb, J, hid, hid1, pooled, w_fc1, w_fc2, w1_fc1, w1_fc2, gates, hidden);
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_ecam_final(int dtype, int N, int H, int W, const ks_view_t *xs, int J,
+                             const float *gates, const float *wf, const float *bf, int K,
+                             float *logits, void *stream) {
+  KS_CHECK_ARG(gates && wf && bf && logits && N > 0 && H > 0 && W > 0);
+  if (K != 3) return KS_EUNSUPPORTED;
+  int Cb; int rc = check_views(xs, J, Cb, dtype == KS_F32 ? 4 : 2); if (rc) return rc;
+  ViewList vl; rc = make_view_list(xs, J, vl); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  int chunks = (H * W + 64 * 8 - 1) / (64 * 8); if (chunks < 1) chunks = 1;
+  const int cap = (kNumSMs * 16 + N - 1) / N; if (chunks > cap) chunks = cap;
+  const size_t smem = sizeof(float) * (size_t)(3 * J * Cb + 3);
+  if (dtype == KS_F32) ecam_final_kernel<float, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, gates, wf, bf, logits);
+  else if (dtype == KS_BF16) ecam_final_kernel<__nv_bfloat16, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, gates, wf, bf, logits);
+  else return KS_EINVAL;
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_ecam_bwd_reduce(int dtype, int N, int H, int W, const ks_view_t *xs, int J, int K,
+                                  const float *dlogits, double *red, void *stream) {
+  KS_CHECK_ARG(dlogits && red && N > 0 && H > 0 && W > 0);
+  if (K != 3) return KS_EUNSUPPORTED;
+  int Cb; int rc = check_views(xs, J, Cb, dtype == KS_F32 ? 4 : 2); if (rc) return rc;
+  ViewList vl; rc = make_view_list(xs, J, vl); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int RT = K * J * Cb + K;
+  cudaError_t e = cudaMemsetAsync(red, 0, sizeof(double) * (size_t)N * RT, st); if (e) return (int)e;
+  const int rows = 256 / (Cb / 8);
+  int chunks = (H * W + rows * 16 - 1) / (rows * 16); if (chunks < 1) chunks = 1;
+  const int cap = (kNumSMs * 8 + N - 1) / N; if (chunks > cap) chunks = cap;
+  const size_t smem = sizeof(float) * (size_t)RT;
+  if (dtype == KS_F32) ecam_bwd_reduce_kernel<float, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, dlogits, red);
+  else if (dtype == KS_BF16) ecam_bwd_reduce_kernel<__nv_bfloat16, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, dlogits, red);
+  else return KS_EINVAL;
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_ecam_gates_bwd(int N, int Cb, int J, int hid, int hid1, int K, const float *pooled,
+                                 const float *hidden, const float *gates, const double *red, const float *wf,
+                                 const float *w_fc1, const float *w_fc2, const float *w1_fc1, const float *w1_fc2,
+                                 float *dpooled, float *dwf, float *dbf, float *dw_fc1, float *dw_fc2,
+                                 float *dw1_fc1, float *dw1_fc2, int accumulate, void *stream) {
+  KS_CHECK_ARG(N > 0 && Cb > 0 && J > 0 && hid > 0 && hid1 > 0 && K > 0);
+  KS_CHECK_ARG(pooled && hidden && gates && red && wf && w_fc1 && w_fc2 && w1_fc1 && w1_fc2 && dpooled);
+  const int CC = J * Cb, CT = (J + 1) * Cb, HT = hid + hid1;
+  const size_t smem = sizeof(float) * (size_t)(K * CC + K + 2 * hid * CC + 2 * hid1 * Cb + CT + 2 * HT);
+  if (smem > 48 * 1024) return KS_EUNSUPPORTED;
+  ecam_gates_bwd_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(N, Cb, J, hid, hid1, K, pooled, hidden, gates, red, wf,
+      w_fc1, w_fc2, w1_fc1, w1_fc2, dpooled, dwf, dbf, dw_fc1, dw_fc2, dw1_fc1, dw1_fc2, accumulate);
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_ecam_bwd_apply(int dtype, int N, int H, int W, int J, int Cb, const float *gates, const float *wf, int K,
+                                 const float *dlogits, const float *dpooled, const int *argmax,
+                                 const ks_view_t *dxs, void *stream) {
+  KS_CHECK_ARG(gates && wf && dlogits && dpooled && argmax && N > 0 && H > 0 && W > 0);
+  if (K != 3) return KS_EUNSUPPORTED;
+  int Cb2; int rc = check_views(dxs, J, Cb2, dtype == KS_F32 ? 4 : 2); if (rc) return rc;
+  if (Cb2 != Cb) return KS_EINVAL;
+  ViewList vl; rc = make_view_list(dxs, J, vl); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  int chunks = (H * W + 64 * 8 - 1) / (64 * 8); if (chunks < 1) chunks = 1;
+  const int cap = (kNumSMs * 16 + N - 1) / N; if (chunks > cap) chunks = cap;
+  const int CC = J * Cb, CT = (J + 1) * Cb;
+  const size_t smem = sizeof(float) * (size_t)(3 * CC + CC + CT) + sizeof(int) * (size_t)CT;
+  if (dtype == KS_F32) ecam_bwd_apply_kernel<float, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, gates, wf, dlogits, dpooled, argmax);
+  else if (dtype == KS_BF16) ecam_bwd_apply_kernel<__nv_bfloat16, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, gates, wf, dlogits, dpooled, argmax);
+  else return KS_EINVAL;
+  KS_LAUNCH_RET();
+}

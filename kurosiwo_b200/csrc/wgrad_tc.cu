@@ -1,0 +1,229 @@
+// TMA + tcgen05 weight-gradient kernel for sm_100a (bf16 NHWC activations, fp32 result).
+//
+//   dw[tap][co][ci] += sum_{pixels} dy[pixel, co] * x[pixel + tap, ci]
+//
+// GEMM view per tap: D[M = ci (128)][N = co (<=256)] = sum_{K = pixels} A[ci][k] * B[co][k].
+// Both operands are "MN-major" for the tensor core: NHWC keeps channels contiguous and the
+// contraction index (the pixel) is the strided one, so a TMA box of 128 pixels x 64 (32)
+// channels IS the canonical MN-major SWIZZLE_128B (64B) operand tile - no transposes anywhere.
+// The pixel dimension is split over CTAs (grid.y); each CTA accumulates its share in TMEM
+// (one accumulator per tap of its tap group) and adds it to dw with coalesced fp32 reductions.
+// The dy tile of a window is loaded once and reused by every tap of the group.
+//
+// Replaces: cuDNN wgrad behind nn.Conv2d / nn.ConvTranspose2d backward (models/snunet.py:15,17,41).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace ks {
+
+int encode_act_map(CUtensorMap *m, const View &v, int N, int H, int W, int box_c, int box_w, int box_h, CUtensorMapSwizzle sw);
+
+struct alignas(64) WgradTcParams {
+  CUtensorMap x[KS_MAX_VIEWS];
+  CUtensorMap dy[KS_MAX_VIEWS];
+  unsigned char xg_view[64], yg_view[64];
+  short xg_c0[64], yg_c0[64];
+  int x_cstart[KS_MAX_VIEWS + 1], y_cstart[KS_MAX_VIEWS + 1];
+  int n_xg, n_yg, GX, GY, MG, NG, BN;
+  int m_tiles, n_tiles, tap_groups, TG, taps, ksize;
+  int N, H, W, tiles_w, tiles_h, total_tiles, splits;
+  int Cin, Cout, SX, SY;
+  uint32_t x_stage_bytes, y_stage_bytes, tmem_cols, idesc;
+  float *dw;
+};
+
+using namespace tc;
+
+__global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int SX = p.SX, SY = p.SY;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *sm = smem_raw + (base - raw);
+  const uint32_t x_base = base;
+  const uint32_t y_base = x_base + (uint32_t)SX * p.x_stage_bytes;
+  const uint32_t bar_base = y_base + (uint32_t)SY * p.y_stage_bytes;
+  auto x_full = [&](int i) { return bar_base + 8u * i; };
+  auto x_empty = [&](int i) { return bar_base + 8u * (SX + i); };
+  auto y_full = [&](int i) { return bar_base + 8u * (2 * SX + i); };
+  auto y_empty = [&](int i) { return bar_base + 8u * (2 * SX + SY + i); };
+  const uint32_t acc_full = bar_base + 8u * (2 * SX + 2 * SY);
+  const uint32_t tmem_slot = acc_full + 8u;
+  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(sm + (tmem_slot - base));
+
+  // work item
+  int item = blockIdx.x;
+  const int tg = item % p.tap_groups; item /= p.tap_groups;
+  const int ntile = item % p.n_tiles; const int mtile = item / p.n_tiles;
+  const int xg0 = mtile * p.MG, nxg = min(p.MG, p.n_xg - xg0);
+  const int yg0 = ntile * p.NG, nyg = min(p.NG, p.n_yg - yg0);
+  const int tap0 = tg * p.TG, ntap = min(p.TG, p.taps - tap0);
+  const int per = (p.total_tiles + p.splits - 1) / p.splits;
+  const int tile_begin = blockIdx.y * per, tile_end = min(p.total_tiles, tile_begin + per);
+  const int pad = p.ksize / 2;
+  const uint32_t xg_bytes = 128u * p.GX * 2u, yg_bytes = 128u * p.GY * 2u;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < SX; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 1); }
+    for (int i = 0; i < SY; ++i) { mbar_init(y_full(i), 1); mbar_init(y_empty(i), 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int sx = 0, px = 0, sy = 0, py = 0;
+      for (int t = tile_begin; t < tile_end; ++t) {
+        const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, n = t / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * 16, h0 = th * 8;
+        mbar_wait(y_empty(sy), py ^ 1);
+        mbar_expect_tx(y_full(sy), (uint32_t)nyg * yg_bytes);
+        for (int g = 0; g < nyg; ++g)
+          tma_load_4d(y_base + (uint32_t)sy * p.y_stage_bytes + (uint32_t)g * yg_bytes, &p.dy[p.yg_view[yg0 + g]],
+                      p.yg_c0[yg0 + g], w0, h0, n, y_full(sy));
+        if (++sy == SY) { sy = 0; py ^= 1; }
+        for (int tp = 0; tp < ntap; ++tp) {
+          const int tap = tap0 + tp;
+          const int dyy = tap / p.ksize - pad, dxx = tap % p.ksize - pad;
+          mbar_wait(x_empty(sx), px ^ 1);
+          mbar_expect_tx(x_full(sx), (uint32_t)nxg * xg_bytes);
+          for (int g = 0; g < nxg; ++g)
+            tma_load_4d(x_base + (uint32_t)sx * p.x_stage_bytes + (uint32_t)g * xg_bytes, &p.x[p.xg_view[xg0 + g]],
+                        p.xg_c0[xg0 + g], w0 + dxx, h0 + dyy, n, x_full(sx));
+          if (++sx == SX) { sx = 0; px ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int sx = 0, px = 0, sy = 0, py = 0;
+      const uint32_t lx = (p.GX == 64) ? LAYOUT_SW128 : LAYOUT_SW64, ly = (p.GY == 64) ? LAYOUT_SW128 : LAYOUT_SW64;
+      const uint32_t x_sbo = 8u * p.GX * 2u, y_sbo = 8u * p.GY * 2u;
+      const uint32_t x_kstep = 16u * p.GX * 2u, y_kstep = 16u * p.GY * 2u;
+      for (int t = tile_begin; t < tile_end; ++t) {
+        mbar_wait(y_full(sy), py);
+        const uint32_t y_addr = y_base + (uint32_t)sy * p.y_stage_bytes;
+        for (int tp = 0; tp < ntap; ++tp) {
+          mbar_wait(x_full(sx), px);
+          tc_fence_after();
+          const uint32_t x_addr = x_base + (uint32_t)sx * p.x_stage_bytes;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t ad = make_smem_desc(x_addr + k * x_kstep, xg_bytes, x_sbo, lx, 0);
+            const uint64_t bd = make_smem_desc(y_addr + k * y_kstep, yg_bytes, y_sbo, ly, 0);
+            umma_bf16(tmem_base + (uint32_t)(tp * p.BN), ad, bd, p.idesc, (t == tile_begin && k == 0) ? 0u : 1u);
+          }
+          tc_commit(x_empty(sx));
+          if (++sx == SX) { sx = 0; px ^= 1; }
+        }
+        tc_commit(y_empty(sy));
+        if (++sy == SY) { sy = 0; py ^= 1; }
+      }
+      tc_commit(acc_full);
+    }
+  } else {
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;            // ci within the M tile
+    const int g = row / p.GX;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    if (tile_end > tile_begin) {
+      const bool row_ok = g < nxg;
+      int ci = 0;
+      if (row_ok) ci = p.x_cstart[p.xg_view[xg0 + g]] + p.xg_c0[xg0 + g] + (row % p.GX);
+      for (int tp = 0; tp < ntap; ++tp) {
+        const int tap = tap0 + tp;
+        for (int cc = 0; cc < nyg * p.GY; cc += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(tp * p.BN + cc), r);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int yg = cc / p.GY;
+            const int co = p.y_cstart[p.yg_view[yg0 + yg]] + p.yg_c0[yg0 + yg] + (cc % p.GY);
+            float *dst = p.dw + ((long long)tap * p.Cout + co) * p.Cin + ci;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(dst + (long long)i * p.Cin, __uint_as_float(r[i]));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
+}
+
+static bool tma_ok(const View &v) {
+  return (((uintptr_t)v.ptr) % 16 == 0) && ((v.sn * 2) % 16 == 0) && ((v.sh * 2) % 16 == 0) && ((v.sw * 2) % 16 == 0) &&
+         v.sw > 0 && v.sh > 0 && v.sn > 0;
+}
+
+int wgrad_tc(int N, int H, int W, int ksize, const ViewList &xs, const ViewList &dys, float *dw, cudaStream_t st) {
+  if (g_opt.tc_disable || g_opt.wgrad_tc_disable) return KS_EUNSUPPORTED;
+  WgradTcParams p;
+  p.GX = 64; p.GY = 64;
+  for (int i = 0; i < xs.n; ++i) { if (xs.v[i].C % 32 || !tma_ok(xs.v[i])) return KS_EUNSUPPORTED; if (xs.v[i].C % 64) p.GX = 32; }
+  for (int i = 0; i < dys.n; ++i) { if (dys.v[i].C % 32 || !tma_ok(dys.v[i])) return KS_EUNSUPPORTED; if (dys.v[i].C % 64) p.GY = 32; }
+  p.n_xg = 0; p.n_yg = 0;
+  for (int i = 0; i < xs.n; ++i) for (int c0 = 0; c0 < xs.v[i].C; c0 += p.GX) { if (p.n_xg >= 64) return KS_EUNSUPPORTED; p.xg_view[p.n_xg] = (unsigned char)i; p.xg_c0[p.n_xg] = (short)c0; ++p.n_xg; }
+  for (int i = 0; i < dys.n; ++i) for (int c0 = 0; c0 < dys.v[i].C; c0 += p.GY) { if (p.n_yg >= 64) return KS_EUNSUPPORTED; p.yg_view[p.n_yg] = (unsigned char)i; p.yg_c0[p.n_yg] = (short)c0; ++p.n_yg; }
+  for (int i = 0; i <= KS_MAX_VIEWS; ++i) { p.x_cstart[i] = xs.cstart[i]; p.y_cstart[i] = dys.cstart[i]; }
+  p.Cin = xs.cstart[xs.n]; p.Cout = dys.cstart[dys.n];
+  p.MG = 128 / p.GX;
+  p.m_tiles = (p.n_xg + p.MG - 1) / p.MG;
+  int ng_max = 256 / p.GY;
+  p.n_tiles = (p.n_yg + ng_max - 1) / ng_max;
+  p.NG = (p.n_yg + p.n_tiles - 1) / p.n_tiles;
+  p.BN = p.NG * p.GY;
+  p.taps = ksize * ksize; p.ksize = ksize;
+  p.TG = (p.taps == 1) ? 1 : ((9 * p.BN <= 512) ? 9 : ((3 * p.BN <= 512) ? 3 : 1));
+  p.tap_groups = (p.taps + p.TG - 1) / p.TG;
+  p.N = N; p.H = H; p.W = W;
+  p.tiles_w = (W + 15) / 16; p.tiles_h = (H + 7) / 8;
+  const long long tt = (long long)p.tiles_w * p.tiles_h * N;
+  if (tt > 0x7fffffffLL) return KS_EUNSUPPORTED;
+  p.total_tiles = (int)tt;
+  const int items = p.m_tiles * p.n_tiles * p.tap_groups;
+  int splits = (kNumSMs * 2 + items - 1) / items;
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  p.splits = splits;
+  p.x_stage_bytes = 128u * 128u * 2u;
+  p.y_stage_bytes = (uint32_t)p.BN * 256u;
+  uint32_t cols = 32; while (cols < (uint32_t)(p.TG * p.BN)) cols <<= 1;
+  if (cols > 512) return KS_EUNSUPPORTED;
+  p.tmem_cols = cols;
+  p.idesc = make_idesc_bf16(128, p.BN, 1, 1);
+  int SX = 4, SY = 2;
+  auto bytes = [&](int sx, int sy) { return (size_t)sx * p.x_stage_bytes + (size_t)sy * p.y_stage_bytes + 1024 + 256; };
+  const size_t budget = 220 * 1024;
+  while (bytes(SX, SY) > budget && SX > 2) --SX;
+  if (bytes(SX, SY) > budget) return KS_EUNSUPPORTED;
+  p.SX = SX; p.SY = SY;
+  p.dw = dw;
+  for (int i = 0; i < xs.n; ++i) {
+    int rc = encode_act_map(&p.x[i], xs.v[i], N, H, W, p.GX, 16, 8, p.GX == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < dys.n; ++i) {
+    int rc = encode_act_map(&p.dy[i], dys.v[i], N, H, W, p.GY, 16, 8, p.GY == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  wgrad_tc_kernel<<<dim3(items, splits), 192, bytes(SX, SY), st>>>(p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace ks
