@@ -1,0 +1,268 @@
+"""ctypes binding of libkurosiwo_b200.so (the C ABI in include/kurosiwo_b200.h).
+
+There is NO CPU fallback: `load()` raises if the shared library is missing, and every op
+raises `KsError` on a non-zero status.  torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Optional, Sequence
+
+import torch
+
+KS_F32, KS_BF16 = 0, 1
+IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+_LIB_PATH = Path(__file__).resolve().parent / "libkurosiwo_b200.so"
+_lib = None
+
+
+class KsError(RuntimeError):
+    pass
+
+
+class ks_view_t(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("sn", C.c_int64), ("sh", C.c_int64), ("sw", C.c_int64),
+                ("C", C.c_int32), ("_pad", C.c_int32)]
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return KS_F32
+    if dt == torch.bfloat16:
+        return KS_BF16
+    raise KsError(f"unsupported storage dtype {dt}")
+
+
+@dataclass
+class View:
+    """Strided NHWC view into a flat storage tensor (channel stride 1)."""
+    base: torch.Tensor
+    offset: int
+    N: int
+    H: int
+    W: int
+    C: int
+    sn: int
+    sh: int
+    sw: int
+
+    @staticmethod
+    def alloc(N, H, W, C, dtype, device, zero=True) -> "View":
+        t = (torch.zeros if zero else torch.empty)(N * H * W * C, dtype=dtype, device=device)
+        return View(t, 0, N, H, W, C, H * W * C, W * C, C)
+
+    def ch(self, c0: int, c: int) -> "View":
+        assert 0 <= c0 and c0 + c <= self.C
+        return View(self.base, self.offset + c0, self.N, self.H, self.W, c, self.sn, self.sh, self.sw)
+
+    def phase(self, i: int, j: int) -> "View":
+        """2x2-strided phase (i,j): pixels (2h+i, 2w+j)."""
+        return View(self.base, self.offset + i * self.sh + j * self.sw, self.N, self.H // 2, self.W // 2, self.C,
+                    self.sn, 2 * self.sh, 2 * self.sw)
+
+    def tensor(self) -> torch.Tensor:
+        return torch.as_strided(self.base, (self.N, self.H, self.W, self.C), (self.sn, self.sh, self.sw, 1), self.offset)
+
+    def c_view(self) -> ks_view_t:
+        return ks_view_t(self.base.data_ptr() + self.offset * self.base.element_size(), self.sn, self.sh, self.sw, self.C, 0)
+
+    @property
+    def dtype(self):
+        return self.base.dtype
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise KsError(f"{_LIB_PATH} is missing: run `python -m kurosiwo_b200.build` (nvcc, sm_100a). "
+                      "There is no CPU fallback.")
+    lib = C.CDLL(str(_LIB_PATH))
+    lib.ks_error_string.restype = C.c_char_p
+    lib.ks_ce_dice_workspace_bytes.restype = C.c_int64
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "ks_version", "ks_error_string", "ks_set_option", "ks_permute_cast", "ks_conv2d", "ks_conv2d_wgrad",
+    "ks_bn_stats", "ks_bn_finalize", "ks_bn_act", "ks_bn_bwd_reduce", "ks_bn_bwd_apply", "ks_maxpool2x2_bwd",
+    "ks_channel_sum", "ks_ecam_pool", "ks_ecam_gates", "ks_ecam_final", "ks_ecam_bwd_reduce", "ks_ecam_gates_bwd",
+    "ks_ecam_bwd_apply", "ks_ce_dice_workspace_bytes", "ks_ce_dice_fwd_bwd", "ks_adam_step",
+]
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _views(vs: Sequence[View]):
+    arr = (ks_view_t * len(vs))(*[v.c_view() for v in vs])
+    return arr
+
+
+def _vp(v: Optional[View]):
+    return None if v is None else C.byref(v.c_view())
+
+
+class CudaOps:
+    """The product op set: every method is one C-ABI call on torch's current CUDA stream."""
+
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = load()
+        if not torch.cuda.is_available():
+            raise KsError("kurosiwo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.launches = 0
+
+    # -- helpers -----------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _check(self, rc: int, what: str):
+        self.launches += 1
+        if rc != 0:
+            raise KsError(f"{what} failed: {self.lib.ks_error_string(C.c_int(rc)).decode()} (code {rc})")
+
+    def set_option(self, name: str, value: int):
+        rc = self.lib.ks_set_option(name.encode(), C.c_int(value))
+        if rc != 0:
+            raise KsError(f"unknown option {name}")
+
+    # -- plumbing ----------------------------------------------------------------------------
+    def permute_cast(self, src: torch.Tensor, dst: torch.Tensor, dims, strides, accumulate=False, src_offset=0):
+        d = list(dims) + [1] * (4 - len(dims))
+        s = list(strides) + [0] * (4 - len(strides))
+        sp = C.c_void_p(src.data_ptr() + src_offset * src.element_size())
+        rc = self.lib.ks_permute_cast(dtype_code(src.dtype), sp, dtype_code(dst.dtype), _p(dst),
+                                      *[C.c_int(x) for x in d], *[C.c_int64(x) for x in s],
+                                      C.c_int(int(accumulate)), self._stream())
+        self._check(rc, "ks_permute_cast")
+
+    # -- convolution -------------------------------------------------------------------------
+    def conv2d(self, N, H, W, ksize, srcs, weight, bias, dsts, acc=None, stats=None, impl=IMPL_AUTO):
+        acc = acc or [False] * len(dsts)
+        accs = (C.c_int * len(dsts))(*[int(a) for a in acc])
+        rc = self.lib.ks_conv2d(dtype_code(srcs[0].dtype), C.c_int(N), C.c_int(H), C.c_int(W), C.c_int(ksize),
+                                _views(srcs), C.c_int(len(srcs)), _p(weight), _p(bias),
+                                _views(dsts), C.c_int(len(dsts)), accs, _p(stats), C.c_int(impl), self._stream())
+        self._check(rc, "ks_conv2d")
+
+    def conv2d_wgrad(self, N, H, W, ksize, xs, dys, dw, accumulate=False, impl=IMPL_AUTO):
+        rc = self.lib.ks_conv2d_wgrad(dtype_code(xs[0].dtype), C.c_int(N), C.c_int(H), C.c_int(W), C.c_int(ksize),
+                                      _views(xs), C.c_int(len(xs)), _views(dys), C.c_int(len(dys)), _p(dw),
+                                      C.c_int(int(accumulate)), C.c_int(impl), self._stream())
+        self._check(rc, "ks_conv2d_wgrad")
+
+    # -- batch norm / pooling ----------------------------------------------------------------
+    def bn_stats(self, x: View, sums):
+        rc = self.lib.ks_bn_stats(dtype_code(x.dtype), C.c_int(x.N), C.c_int(x.H), C.c_int(x.W), _vp(x), _p(sums), self._stream())
+        self._check(rc, "ks_bn_stats")
+
+    def bn_finalize(self, Cn, count, sums, gamma, beta, eps, momentum, rmean, rvar, scale, shift, mean, rstd):
+        rc = self.lib.ks_bn_finalize(C.c_int(Cn), C.c_double(count), _p(sums), _p(gamma), _p(beta), C.c_float(eps),
+                                     C.c_float(momentum), _p(rmean), _p(rvar), _p(scale), _p(shift), _p(mean), _p(rstd),
+                                     self._stream())
+        self._check(rc, "ks_bn_finalize")
+
+    def bn_act(self, y: View, scale, shift, res: Optional[View], relu: bool, out: View, pool: Optional[View]):
+        rc = self.lib.ks_bn_act(dtype_code(y.dtype), C.c_int(y.N), C.c_int(y.H), C.c_int(y.W), _vp(y), _p(scale), _p(shift),
+                                _vp(res), C.c_int(int(relu)), _vp(out), _vp(pool), self._stream())
+        self._check(rc, "ks_bn_act")
+
+    def bn_bwd_reduce(self, dout: View, out: View, y: View, mean, rstd, sums):
+        rc = self.lib.ks_bn_bwd_reduce(dtype_code(y.dtype), C.c_int(y.N), C.c_int(y.H), C.c_int(y.W), _vp(dout), _vp(out), _vp(y),
+                                       _p(mean), _p(rstd), _p(sums), self._stream())
+        self._check(rc, "ks_bn_bwd_reduce")
+
+    def bn_bwd_apply(self, dout, out, y, mean, rstd, gamma, sums, count, add_dout, add_out, dy, dgamma, dbeta, accumulate):
+        rc = self.lib.ks_bn_bwd_apply(dtype_code(y.dtype), C.c_int(y.N), C.c_int(y.H), C.c_int(y.W), _vp(dout), _vp(out), _vp(y),
+                                      _p(mean), _p(rstd), _p(gamma), _p(sums), C.c_double(count), _vp(add_dout), _vp(add_out),
+                                      _vp(dy), _p(dgamma), _p(dbeta), C.c_int(int(accumulate)), self._stream())
+        self._check(rc, "ks_bn_bwd_apply")
+
+    def maxpool2x2_bwd(self, x: View, dpool: View, dx: View, accumulate: bool):
+        rc = self.lib.ks_maxpool2x2_bwd(dtype_code(x.dtype), C.c_int(dpool.N), C.c_int(dpool.H), C.c_int(dpool.W), _vp(x), _vp(dpool),
+                                        _vp(dx), C.c_int(int(accumulate)), self._stream())
+        self._check(rc, "ks_maxpool2x2_bwd")
+
+    def channel_sum(self, x: View, out, accumulate: bool):
+        rc = self.lib.ks_channel_sum(dtype_code(x.dtype), C.c_int(x.N), C.c_int(x.H), C.c_int(x.W), _vp(x), _p(out),
+                                     C.c_int(int(accumulate)), self._stream())
+        self._check(rc, "ks_channel_sum")
+
+    # -- ECAM head ---------------------------------------------------------------------------
+    def ecam_pool(self, xs, pooled, argmax, scratch):
+        x = xs[0]
+        rc = self.lib.ks_ecam_pool(dtype_code(x.dtype), C.c_int(x.N), C.c_int(x.H), C.c_int(x.W), _views(xs), C.c_int(len(xs)),
+                                   _p(pooled), _p(argmax), _p(scratch), self._stream())
+        self._check(rc, "ks_ecam_pool")
+
+    def ecam_gates(self, N, Cb, J, hid, hid1, pooled, w_fc1, w_fc2, w1_fc1, w1_fc2, gates, hidden):
+        rc = self.lib.ks_ecam_gates(C.c_int(N), C.c_int(Cb), C.c_int(J), C.c_int(hid), C.c_int(hid1), _p(pooled), _p(w_fc1),
+                                    _p(w_fc2), _p(w1_fc1), _p(w1_fc2), _p(gates), _p(hidden), self._stream())
+        self._check(rc, "ks_ecam_gates")
+
+    def ecam_final(self, xs, gates, wf, bf, K, logits):
+        x = xs[0]
+        rc = self.lib.ks_ecam_final(dtype_code(x.dtype), C.c_int(x.N), C.c_int(x.H), C.c_int(x.W), _views(xs), C.c_int(len(xs)),
+                                    _p(gates), _p(wf), _p(bf), C.c_int(K), _p(logits), self._stream())
+        self._check(rc, "ks_ecam_final")
+
+    def ecam_bwd_reduce(self, xs, K, dlogits, red):
+        x = xs[0]
+        rc = self.lib.ks_ecam_bwd_reduce(dtype_code(x.dtype), C.c_int(x.N), C.c_int(x.H), C.c_int(x.W), _views(xs), C.c_int(len(xs)),
+                                         C.c_int(K), _p(dlogits), _p(red), self._stream())
+        self._check(rc, "ks_ecam_bwd_reduce")
+
+    def ecam_gates_bwd(self, N, Cb, J, hid, hid1, K, pooled, hidden, gates, red, wf, w_fc1, w_fc2, w1_fc1, w1_fc2,
+                       dpooled, dwf, dbf, dw_fc1, dw_fc2, dw1_fc1, dw1_fc2, accumulate=False):
+        rc = self.lib.ks_ecam_gates_bwd(C.c_int(N), C.c_int(Cb), C.c_int(J), C.c_int(hid), C.c_int(hid1), C.c_int(K), _p(pooled),
+                                        _p(hidden), _p(gates), _p(red), _p(wf), _p(w_fc1), _p(w_fc2), _p(w1_fc1), _p(w1_fc2),
+                                        _p(dpooled), _p(dwf), _p(dbf), _p(dw_fc1), _p(dw_fc2), _p(dw1_fc1), _p(dw1_fc2),
+                                        C.c_int(int(accumulate)), self._stream())
+        self._check(rc, "ks_ecam_gates_bwd")
+
+    def ecam_bwd_apply(self, dxs, gates, wf, K, dlogits, dpooled, argmax):
+        x = dxs[0]
+        rc = self.lib.ks_ecam_bwd_apply(dtype_code(x.dtype), C.c_int(x.N), C.c_int(x.H), C.c_int(x.W), C.c_int(len(dxs)), C.c_int(x.C),
+                                        _p(gates), _p(wf), C.c_int(K), _p(dlogits), _p(dpooled), _p(argmax), _views(dxs),
+                                        self._stream())
+        self._check(rc, "ks_ecam_bwd_apply")
+
+    # -- loss --------------------------------------------------------------------------------
+    def ce_dice_workspace(self, N: int, device) -> torch.Tensor:
+        nbytes = int(self.lib.ks_ce_dice_workspace_bytes(C.c_int(N)))
+        return torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
+
+    def ce_dice(self, logits, labels, class_weights, ignore_index, grad_scale, loss_out, dlogits, pred, workspace):
+        N, K = logits.shape[0], logits.shape[1]
+        HW = logits.numel() // (N * K)
+        rc = self.lib.ks_ce_dice_fwd_bwd(_p(logits), _p(labels), C.c_int(N), C.c_int(K), C.c_int64(HW), _p(class_weights),
+                                         C.c_int(ignore_index), C.c_float(grad_scale), _p(loss_out), _p(dlogits), _p(pred),
+                                         _p(workspace), self._stream())
+        self._check(rc, "ks_ce_dice_fwd_bwd")
+
+    # -- optimizer ---------------------------------------------------------------------------
+    def adam_step(self, p, g, m, v, lr, b1, b2, eps, wd, grad_scale, step):
+        rc = self.lib.ks_adam_step(_p(p), _p(g), _p(m), _p(v), C.c_int64(p.numel()), C.c_float(lr), C.c_float(b1), C.c_float(b2),
+                                   C.c_float(eps), C.c_float(wd), C.c_float(grad_scale), _p(step), self._stream())
+        self._check(rc, "ks_adam_step")
+
+    # -- misc memory ops (plumbing through torch) ----------------------------------------------
+    def zero_(self, t: torch.Tensor):
+        t.zero_()
+
+
+_default_ops: Optional[CudaOps] = None
+
+
+def default_ops() -> CudaOps:
+    global _default_ops
+    if _default_ops is None:
+        _default_ops = CudaOps()
+    return _default_ops

@@ -1,0 +1,386 @@
+"""Host-side schedule of the SNUNet-ECAM training step over the C-ABI ops.
+
+Reference path being replaced: models/snunet.py:118-153 (SNUNet_ECAM.forward) and its autograd
+backward, training/change_detection_trainer.py:136-177 (forward, loss, backward, optimizer step).
+
+Layout in HBM (N = per-GPU batch, f_l = base*2^l, H_l = H >> l), all NHWC in the storage dtype
+(bf16 in perf mode, fp32 in parity mode):
+  X[l]    one dense "concat" buffer per pyramid level, channel slots [x_l0A | x_l0B | x_l1 | x_l2 ...]:
+          every block writes its output straight into its slot, so each `torch.cat` of
+          snunet.py:132-144 is the channel PREFIX of X[l] plus the upsampled tensor - never a copy.
+  UP[l,j] ConvTranspose2d(k2,s2) output feeding decoder block (l,j); written by four strided
+          1x1-conv phases.
+  P[l]    2x2 max-pooled encoder outputs, produced by the same pass that applies BN+residual+ReLU.
+  Y1/Hh/Y2 per block execution: pre-BN conv1 output (also the residual), post-BN/ReLU hidden,
+          pre-BN conv2 output - kept for backward.
+  dX/dUP/dP mirror the activations for gradients; producers accumulate (+=) or assign according
+          to a static first-writer analysis, so no gradient buffer is ever zero-filled.
+Parameters live in ONE flat fp32 buffer (module parameters are views into it) with a matching flat
+gradient buffer: the optimizer step and the data-parallel all-reduce are one launch / one message.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from .lib import View
+
+DEC_ORDER = [(0, 1), (1, 1), (0, 2), (2, 1), (1, 2), (0, 3), (3, 1), (2, 2), (1, 3), (0, 4)]  # snunet.py:132-144
+NSLOTS = [6, 5, 4, 3, 1]
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+
+
+def _align(n: int, a: int = 64) -> int:
+    return (n + a - 1) // a * a
+
+
+class FlatParams:
+    """All trainable parameters of a module as views into one flat fp32 buffer (+ flat grad)."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.module = module
+        self.names: List[str] = []
+        self.offsets: Dict[str, Tuple[int, torch.Size]] = {}
+        off = 0
+        for name, p in module.named_parameters():
+            self.names.append(name)
+            self.offsets[name] = (off, p.shape)
+            off += _align(p.numel(), 4)
+        self.numel = _align(off, 4)
+        self.flat: Optional[torch.Tensor] = None
+        self.grad: Optional[torch.Tensor] = None
+
+    def ensure(self, device) -> bool:
+        """(Re)flatten if the module's parameters are not views of the flat buffer (e.g. after .to())."""
+        params = dict(self.module.named_parameters())
+        ok = self.flat is not None and self.flat.device == torch.device(device)
+        if ok:
+            base = self.flat.data_ptr()
+            for name in self.names:
+                if params[name].data_ptr() != base + 4 * self.offsets[name][0]:
+                    ok = False
+                    break
+        if ok:
+            return False
+        flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
+        grad = torch.zeros(self.numel, dtype=torch.float32, device=device)
+        for name in self.names:
+            off, shape = self.offsets[name]
+            p = params[name]
+            flat[off:off + p.numel()].copy_(p.data.reshape(-1).to(device=device, dtype=torch.float32))
+            p.data = flat[off:off + p.numel()].view(shape)
+        self.flat, self.grad = flat, grad
+        return True
+
+    def p(self, name: str) -> torch.Tensor:
+        off, shape = self.offsets[name]
+        return self.flat[off:off + shape.numel()]
+
+    def g(self, name: str) -> torch.Tensor:
+        off, shape = self.offsets[name]
+        return self.grad[off:off + shape.numel()]
+
+    def grad_views(self):
+        return [self.g(n).view(self.offsets[n][1]) for n in self.names]
+
+
+class _Exec:
+    """One execution of a conv_block_nested (the shared encoder blocks execute twice)."""
+    __slots__ = ("name", "level", "srcs", "gsrcs", "out", "dout", "pool", "y1", "h", "y2", "bn", "stats", "bstats", "key")
+
+
+class SNUNetEngine:
+    def __init__(self, ops, module: torch.nn.Module, in_ch: int, num_classes: int, base: int,
+                 N: int, H: int, W: int, dtype: torch.dtype, device, conv_impl: int = 0):
+        assert H % 16 == 0 and W % 16 == 0, "SNUNet needs H, W divisible by 16 (four 2x2 poolings)"
+        assert num_classes == 3, "the fused head/loss kernels are built for num_classes == 3 (configs/config.json:13)"
+        self.ops, self.module, self.dtype, self.device = ops, module, dtype, torch.device(device)
+        self.in_ch, self.K, self.base, self.N, self.H, self.W = in_ch, num_classes, base, N, H, W
+        self.f = [base * (1 << l) for l in range(5)]
+        self.hid, self.hid1 = (4 * base) // 16, base // 4
+        self.conv_impl = conv_impl
+        self.params = FlatParams(module)
+        self._alloc()
+        self._build_schedule()
+        self.packed_version = -1
+
+    # ------------------------------------------------------------------------------------------
+    def _hw(self, l):
+        return self.H >> l, self.W >> l
+
+    def _buf(self, l, C):
+        h, w = self._hw(l)
+        return View.alloc(self.N, h, w, C, self.dtype, self.device)
+
+    def slot(self, buf: Dict[int, View], l: int, k: int) -> View:
+        f = self.f[l]
+        return buf[l].ch((k if l < 4 else 0) * f, f)
+
+    def _alloc(self):
+        N, dev, f = self.N, self.device, self.f
+        self.X = {l: self._buf(l, f[l] * NSLOTS[l]) for l in range(5)}
+        self.dX = {l: self._buf(l, f[l] * NSLOTS[l]) for l in range(5)}
+        self.P, self.dP = {}, {}
+        for l in range(1, 5):
+            for br in (0, 1):
+                if l == 4 and br == 0:
+                    continue  # conv4_0 is only run on the second image (snunet.py:124)
+                self.P[(l, br)] = self._buf(l, f[l - 1])
+                self.dP[(l, br)] = self._buf(l, f[l - 1])
+        self.UP = {(l, j): self._buf(l, f[l + 1]) for (l, j) in DEC_ORDER}
+        self.dUP = {(l, j): self._buf(l, f[l + 1]) for (l, j) in DEC_ORDER}
+        self.xin = [View.alloc(N, self.H, self.W, self.in_ch, self.dtype, dev) for _ in range(2)]
+        self.dY = {l: self._buf(l, f[l]) for l in range(5)}
+        self.dH = {l: self._buf(l, f[l]) for l in range(5)}
+        CT = 5 * f[0]
+        self.pooled = torch.zeros(N * 2 * CT, dtype=torch.float32, device=dev)
+        self.dpooled = torch.zeros(N * 2 * CT, dtype=torch.float32, device=dev)
+        self.argmax = torch.zeros(N * CT, dtype=torch.int32, device=dev)
+        self.pool_scratch = torch.zeros(N * CT, dtype=torch.int64, device=dev)
+        self.gates = torch.zeros(N * CT, dtype=torch.float32, device=dev)
+        self.hidden = torch.zeros(N * 2 * (self.hid + self.hid1), dtype=torch.float32, device=dev)
+        self.red = torch.zeros(N * (self.K * 4 * f[0] + self.K), dtype=torch.float64, device=dev)
+        self.logits = torch.zeros(N, self.K, self.H, self.W, dtype=torch.float32, device=dev)
+
+    def _build_schedule(self):
+        f = self.f
+        self.execs: List[_Exec] = []
+        self.exec_of: Dict[Tuple, _Exec] = {}
+
+        def add(name, level, srcs, gsrcs, out_key, pool_key, key):
+            e = _Exec()
+            e.name, e.level, e.srcs, e.gsrcs, e.key = name, level, srcs, gsrcs, key
+            e.out = self.slot(self.X, level, out_key)
+            e.dout = self.slot(self.dX, level, out_key)
+            e.pool = self.P.get(pool_key) if pool_key else None
+            e.y1, e.h, e.y2 = self._buf(level, f[level]), self._buf(level, f[level]), self._buf(level, f[level])
+            e.bn = torch.zeros(8 * f[level], dtype=torch.float32, device=self.device)   # scale1,shift1,mean1,rstd1,scale2,...
+            e.stats = None
+            self.execs.append(e)
+            self.exec_of[key] = e
+            return e
+
+        for br in (0, 1):  # encoder A then B, as the reference (running stats update order)
+            for l in range(5):
+                if l == 4 and br == 0:
+                    continue
+                src = self.xin[br] if l == 0 else self.P[(l, br)]
+                gsrc = None if l == 0 else self.dP[(l, br)]
+                pool_key = (l + 1, br) if (l + 1, br) in self.P else None
+                add(f"conv{l}_0", l, [src], [gsrc], br, pool_key, ("enc", l, br))
+        for (l, j) in DEC_ORDER:
+            prefix = self.X[l].ch(0, f[l] * (j + 1))
+            add(f"conv{l}_{j}", l, [prefix, self.UP[(l, j)]], None, 1 + j, None, ("dec", l, j))
+        n = len(self.execs)
+        fmax = max(self.f)
+        self.stats_all = torch.zeros(n * 2 * 2 * fmax, dtype=torch.float64, device=self.device)
+        self.bstats_all = torch.zeros(n * 2 * 2 * fmax, dtype=torch.float64, device=self.device)
+        for i, e in enumerate(self.execs):
+            fl = f[e.level]
+            o = i * 4 * fmax
+            e.stats = (self.stats_all[o:o + 2 * fl], self.stats_all[o + 2 * fmax:o + 2 * fmax + 2 * fl])
+            e.bstats = (self.bstats_all[o:o + 2 * fl], self.bstats_all[o + 2 * fmax:o + 2 * fmax + 2 * fl])
+
+        # packed weights (storage dtype) and packed weight gradients (fp32)
+        self.wp: Dict[str, torch.Tensor] = {}
+        self.gp: Dict[str, torch.Tensor] = {}
+        self.block_names = sorted({e.name for e in self.execs})
+        self.block_cin = {}
+        for e in self.execs:
+            self.block_cin[e.name] = sum(s.C for s in e.srcs)
+        for bn_ in self.block_names:
+            l = int(bn_[4])
+            cin, fl = self.block_cin[bn_], f[l]
+            for tag, (co, ci) in (("conv1", (fl, cin)), ("conv2", (fl, fl))):
+                self.wp[f"{bn_}.{tag}.fwd"] = torch.zeros(9 * co * ci, dtype=self.dtype, device=self.device)
+                self.wp[f"{bn_}.{tag}.dgrad"] = torch.zeros(9 * co * ci, dtype=self.dtype, device=self.device)
+                self.gp[f"{bn_}.{tag}"] = torch.zeros(9 * co * ci, dtype=torch.float32, device=self.device)
+        self.up_names = {}
+        for (l, j) in DEC_ORDER:
+            nm = f"Up{l + 1}_{j - 1}"
+            self.up_names[(l, j)] = nm
+            c = f[l + 1]
+            self.wp[f"{nm}.fwd"] = torch.zeros(4 * c * c, dtype=self.dtype, device=self.device)
+            self.wp[f"{nm}.dgrad"] = torch.zeros(4 * c * c, dtype=self.dtype, device=self.device)
+            self.wp[f"{nm}.bias4"] = torch.zeros(4 * c, dtype=torch.float32, device=self.device)
+            self.gp[nm] = torch.zeros(4 * c * c, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------------------------------
+    def _pack_weights(self):
+        ops, P = self.ops, self.params
+        for bn_ in self.block_names:
+            l = int(bn_[4])
+            cin, fl = self.block_cin[bn_], self.f[l]
+            for tag, (co, ci) in (("conv1", (fl, cin)), ("conv2", (fl, fl))):
+                w = P.p(f"{bn_}.{tag}.weight")  # OIHW
+                # fwd  [t][o][i] = w[o][i][t]
+                ops.permute_cast(w, self.wp[f"{bn_}.{tag}.fwd"], (9, co, ci), (1, ci * 9, 9))
+                # dgrad [t][i][o] = w[o][i][8-t]   (180-degree rotated taps, in/out swapped)
+                ops.permute_cast(w, self.wp[f"{bn_}.{tag}.dgrad"], (9, ci, co), (-1, 9, ci * 9), src_offset=8)
+        for (l, j), nm in self.up_names.items():
+            c = self.f[l + 1]
+            w = P.p(f"{nm}.up.weight")  # (Cin, Cout, 2, 2)
+            ops.permute_cast(w, self.wp[f"{nm}.fwd"], (4, c, c), (1, 4, c * 4))       # [k][co][ci]
+            ops.permute_cast(w, self.wp[f"{nm}.dgrad"], (c, 4, c), (c * 4, 1, 4))     # [ci][k][co]
+            ops.permute_cast(P.p(f"{nm}.up.bias"), self.wp[f"{nm}.bias4"], (4, c), (0, 1))
+
+    def _unpack_grads(self):
+        ops, P = self.ops, self.params
+        for bn_ in self.block_names:
+            l = int(bn_[4])
+            cin, fl = self.block_cin[bn_], self.f[l]
+            for tag, (co, ci) in (("conv1", (fl, cin)), ("conv2", (fl, fl))):
+                # grad[o][i][t] = gp[t][o][i]
+                ops.permute_cast(self.gp[f"{bn_}.{tag}"], P.g(f"{bn_}.{tag}.weight"), (co, ci, 9), (ci, 1, co * ci))
+        for (l, j), nm in self.up_names.items():
+            c = self.f[l + 1]
+            # grad[ci][co][k] = gp[k][co][ci]
+            ops.permute_cast(self.gp[nm], P.g(f"{nm}.up.weight"), (c, c, 4), (1, c, c * c))
+
+    def _buf_(self, name: str) -> torch.Tensor:
+        mod, _, leaf = name.rpartition(".")
+        return getattr(self.module.get_submodule(mod), leaf)
+
+    # ------------------------------------------------------------------------------------------
+    def _block_forward(self, e: _Exec, training: bool):
+        ops, P, N = self.ops, self.params, self.N
+        h_, w_ = self._hw(e.level)
+        fl = self.f[e.level]
+        nm = e.name
+        count = float(N * h_ * w_)
+        bn = e.bn
+        sc1, sh1, mu1, rs1, sc2, sh2, mu2, rs2 = [bn[i * fl:(i + 1) * fl] for i in range(8)]
+        for idx, (tag, bnt, srcs, y, sc, sh, mu, rs) in enumerate((("conv1", "bn1", e.srcs, e.y1, sc1, sh1, mu1, rs1),
+                                                                   ("conv2", "bn2", [e.h], e.y2, sc2, sh2, mu2, rs2))):
+            stats = e.stats[idx] if training else None
+            ops.conv2d(N, h_, w_, 3, srcs, self.wp[f"{nm}.{tag}.fwd"], P.p(f"{nm}.{tag}.bias"), [y], None, stats, self.conv_impl)
+            rm, rv = self._buf_(f"{nm}.{bnt}.running_mean"), self._buf_(f"{nm}.{bnt}.running_var")
+            if training:
+                ops.bn_finalize(fl, count, stats, P.p(f"{nm}.{bnt}.weight"), P.p(f"{nm}.{bnt}.bias"), BN_EPS, BN_MOMENTUM,
+                                rm, rv, sc, sh, mu, rs)
+                self._buf_(f"{nm}.{bnt}.num_batches_tracked").add_(1)
+            else:
+                g = P.p(f"{nm}.{bnt}.weight")
+                torch.mul(g, torch.rsqrt(rv + BN_EPS), out=sc)
+                torch.sub(P.p(f"{nm}.{bnt}.bias"), rm * sc, out=sh)
+            if idx == 0:
+                ops.bn_act(y, sc, sh, None, True, e.h, None)
+            else:
+                ops.bn_act(y, sc, sh, e.y1, True, e.out, e.pool)
+
+    def _up_forward(self, l: int, j: int):
+        nm = self.up_names[(l, j)]
+        src = self.slot(self.X, l + 1, j)
+        up = self.UP[(l, j)]
+        h_, w_ = self._hw(l + 1)
+        dsts = [up.phase(k // 2, k % 2) for k in range(4)]
+        self.ops.conv2d(self.N, h_, w_, 1, [src], self.wp[f"{nm}.fwd"], self.wp[f"{nm}.bias4"], dsts, None, None, self.conv_impl)
+
+    def forward(self, xA: torch.Tensor, xB: torch.Tensor, training: bool = True) -> torch.Tensor:
+        ops, N, H, W, Cin = self.ops, self.N, self.H, self.W, self.in_ch
+        assert tuple(xA.shape) == (N, Cin, H, W) and tuple(xB.shape) == (N, Cin, H, W), \
+            f"engine was planned for {(N, Cin, H, W)}, got {tuple(xA.shape)}"
+        self.params.ensure(self.device)
+        for br, x in enumerate((xA, xB)):
+            x = x.contiguous()
+            if x.dtype != torch.float32:
+                x = x.float()
+            ops.permute_cast(x, self.xin[br].base, (N, H, W, Cin), (Cin * H * W, W, 1, H * W))
+        self._pack_weights()
+        if training:
+            ops.zero_(self.stats_all)
+        for e in self.execs:
+            if e.key[0] == "dec":
+                self._up_forward(e.key[1], e.key[2])
+            self._block_forward(e, training)
+        xs = [self.slot(self.X, 0, 2 + i) for i in range(4)]
+        P = self.params
+        ops.ecam_pool(xs, self.pooled, self.argmax, self.pool_scratch)
+        ops.ecam_gates(N, self.f[0], 4, self.hid, self.hid1, self.pooled, P.p("ca.fc1.weight"), P.p("ca.fc2.weight"),
+                       P.p("ca1.fc1.weight"), P.p("ca1.fc2.weight"), self.gates, self.hidden)
+        ops.ecam_final(xs, self.gates, P.p("conv_final.weight"), P.p("conv_final.bias"), self.K, self.logits)
+        return self.logits
+
+    # ------------------------------------------------------------------------------------------
+    def _block_backward(self, e: _Exec, gdsts: Optional[List[View]], gacc: Optional[List[bool]], first: bool):
+        ops, P, N = self.ops, self.params, self.N
+        h_, w_ = self._hw(e.level)
+        fl = self.f[e.level]
+        nm = e.name
+        count = float(N * h_ * w_)
+        sc1, sh1, mu1, rs1, sc2, sh2, mu2, rs2 = [e.bn[i * fl:(i + 1) * fl] for i in range(8)]
+        dy, dh = self.dY[e.level], self.dH[e.level]
+        acc = not first
+        # ---- bn2 + residual + relu backward -> dy2
+        ops.bn_bwd_reduce(e.dout, e.out, e.y2, mu2, rs2, e.bstats[1])
+        ops.bn_bwd_apply(e.dout, e.out, e.y2, mu2, rs2, P.p(f"{nm}.bn2.weight"), e.bstats[1], count, None, None, dy,
+                         P.g(f"{nm}.bn2.weight"), P.g(f"{nm}.bn2.bias"), acc)
+        ops.channel_sum(dy, P.g(f"{nm}.conv2.bias"), acc)
+        ops.conv2d_wgrad(N, h_, w_, 3, [e.h], [dy], self.gp[f"{nm}.conv2"], acc, self.conv_impl)
+        ops.conv2d(N, h_, w_, 3, [dy], self.wp[f"{nm}.conv2.dgrad"], None, [dh], None, None, self.conv_impl)
+        # ---- bn1 + relu backward (+ identity path g = dout*(out>0)) -> dy1 (reuses dy)
+        ops.bn_bwd_reduce(dh, e.h, e.y1, mu1, rs1, e.bstats[0])
+        ops.bn_bwd_apply(dh, e.h, e.y1, mu1, rs1, P.p(f"{nm}.bn1.weight"), e.bstats[0], count, e.dout, e.out, dy,
+                         P.g(f"{nm}.bn1.weight"), P.g(f"{nm}.bn1.bias"), acc)
+        ops.channel_sum(dy, P.g(f"{nm}.conv1.bias"), acc)
+        ops.conv2d_wgrad(N, h_, w_, 3, e.srcs, [dy], self.gp[f"{nm}.conv1"], acc, self.conv_impl)
+        if gdsts:
+            ops.conv2d(N, h_, w_, 3, [dy], self.wp[f"{nm}.conv1.dgrad"], None, gdsts, gacc, None, self.conv_impl)
+
+    def backward(self, dlogits: torch.Tensor):
+        ops, P, N, f = self.ops, self.params, self.N, self.f
+        ops.zero_(self.bstats_all)
+        xs = [self.slot(self.X, 0, 2 + i) for i in range(4)]
+        dxs = [self.slot(self.dX, 0, 2 + i) for i in range(4)]
+        ops.ecam_bwd_reduce(xs, self.K, dlogits, self.red)
+        ops.ecam_gates_bwd(N, f[0], 4, self.hid, self.hid1, self.K, self.pooled, self.hidden, self.gates, self.red,
+                           P.p("conv_final.weight"), P.p("ca.fc1.weight"), P.p("ca.fc2.weight"), P.p("ca1.fc1.weight"),
+                           P.p("ca1.fc2.weight"), self.dpooled, P.g("conv_final.weight"), P.g("conv_final.bias"),
+                           P.g("ca.fc1.weight"), P.g("ca.fc2.weight"), P.g("ca1.fc1.weight"), P.g("ca1.fc2.weight"), False)
+        ops.ecam_bwd_apply(dxs, self.gates, P.p("conv_final.weight"), self.K, dlogits, self.dpooled, self.argmax)
+        written = {(0, 2), (0, 3), (0, 4), (0, 5)}
+        seen_blocks = set()
+        for (l, j) in reversed(DEC_ORDER):
+            e = self.exec_of[("dec", l, j)]
+            # gradient destinations: runs of prefix slots with equal first-writer status, then the up tensor
+            gd, ga = [], []
+            k = 0
+            while k <= j:
+                st = (l, k) in written
+                k2 = k
+                while k2 + 1 <= j and ((l, k2 + 1) in written) == st:
+                    k2 += 1
+                gd.append(self.dX[l].ch(k * f[l], (k2 - k + 1) * f[l]))
+                ga.append(st)
+                k = k2 + 1
+            for kk in range(j + 1):
+                written.add((l, kk))
+            gd.append(self.dUP[(l, j)])
+            ga.append(False)
+            self._block_backward(e, gd, ga, e.name not in seen_blocks)
+            seen_blocks.add(e.name)
+            # transposed-conv backward
+            nm = self.up_names[(l, j)]
+            h1, w1 = self._hw(l + 1)
+            dup = self.dUP[(l, j)]
+            phases = [dup.phase(k_ // 2, k_ % 2) for k_ in range(4)]
+            tgt = (l + 1, j)
+            ops.conv2d(N, h1, w1, 1, phases, self.wp[f"{nm}.dgrad"], None, [self.slot(self.dX, l + 1, j)],
+                       [tgt in written], None, self.conv_impl)
+            written.add(tgt)
+            ops.conv2d_wgrad(N, h1, w1, 1, [self.slot(self.X, l + 1, j)], phases, self.gp[nm], False, self.conv_impl)
+            ops.channel_sum(dup, P.g(f"{nm}.up.bias"), False)
+        for br in (1, 0):
+            for l in (4, 3, 2, 1, 0):
+                if l == 4 and br == 0:
+                    continue
+                e = self.exec_of[("enc", l, br)]
+                if (l + 1, br) in self.P:
+                    ops.maxpool2x2_bwd(e.out, self.dP[(l + 1, br)], e.dout, (l, br) in written)
+                    written.add((l, br))
+                assert (l, br) in written
+                gd = None if l == 0 else [self.dP[(l, br)]]
+                self._block_backward(e, gd, None if gd is None else [False], e.name not in seen_blocks)
+                seen_blocks.add(e.name)
+        self._unpack_grads()

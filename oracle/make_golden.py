@@ -1,0 +1,87 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference modules from /root/reference.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python -m oracle.make_golden
+The fixtures pin oracle/ (tests/test_oracle_golden.py) and, through it, the CUDA path.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+def main():
+    sys.path.insert(0, REF)
+    from models.snunet import SNUNet_ECAM as RefSNUNet          # noqa: E402  (reference, read-only)
+    from utilities.bce_and_dice import BCEandDiceLoss as RefLoss  # noqa: E402
+    from oracle.weights import make_batch, make_state
+
+    OUT.mkdir(parents=True, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+
+    # ---- loss fixtures ------------------------------------------------------------------
+    rng = np.random.Generator(np.random.PCG64(7))
+    cases = {}
+    for tag, (N, H, W, wts, all_ignored) in {
+        "small": (2, 16, 16, [1.0, 1.0, 1.0], False),
+        "weighted": (3, 12, 20, [0.3715753140309927, 14.009780283125977, 8.20405370357821], False),
+        "ragged": (1, 7, 9, [1.0, 2.0, 0.5], False),
+        "allignored": (2, 8, 8, [1.0, 1.0, 1.0], True),
+    }.items():
+        z = (3.0 * rng.standard_normal((N, 3, H, W))).astype(np.float32)
+        y = rng.choice(4, size=(N, H, W), p=[0.6, 0.1, 0.15, 0.15]).astype(np.int64)
+        if all_ignored:
+            y[:] = 3
+        zt = torch.from_numpy(z).requires_grad_(True)
+        crit = RefLoss(weights=torch.tensor(wts), ignore_index=3, use_softmax=True)
+        loss = crit(zt, torch.from_numpy(y))
+        dice = crit.dice(zt, torch.from_numpy(y))
+        loss.backward()
+        cases[tag] = dict(logits=z, labels=y, weights=np.array(wts, np.float32), loss=loss.detach().numpy(),
+                          dice=dice.detach().numpy(), dlogits=zt.grad.numpy(), argmax=zt.detach().argmax(1).numpy().astype(np.uint8))
+    np.savez_compressed(OUT / "loss_cases.npz", **{f"{t}.{k}": v for t, c in cases.items() for k, v in c.items()})
+
+    # ---- SNUNet fixtures: forward logits, loss, gradients, running stats after one step ----
+    for tag, (base, N, H, W, seed) in {"b8_n2_s32": (8, 2, 32, 32, 11), "b32_n2_s16": (32, 2, 16, 16, 12)}.items():
+        sd = make_state(seed, 2, 3, base)
+        xA, xB, mask = make_batch(seed, N, H, W)
+        model = RefSNUNet(2, 3, base_channel=base)
+        model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+        model.train()
+        crit = RefLoss(weights=torch.tensor([1.0, 1.0, 1.0]), ignore_index=3, use_softmax=True)
+        out = model(torch.from_numpy(xA), torch.from_numpy(xB))
+        loss = crit(out, torch.from_numpy(mask))
+        loss.backward()
+        fx = {"base": base, "N": N, "H": H, "W": W, "seed": seed, "logits": out.detach().numpy(), "loss": loss.detach().numpy()}
+        keep_full = {"conv0_0.conv1.weight", "conv0_0.conv1.bias", "conv0_0.bn1.weight", "conv0_0.bn2.bias", "conv0_4.conv1.weight",
+                     "conv1_2.conv2.weight", "Up1_0.up.weight", "Up2_1.up.bias", "ca.fc1.weight", "ca.fc2.weight", "ca1.fc1.weight",
+                     "ca1.fc2.weight", "conv_final.weight", "conv_final.bias", "conv3_0.bn1.weight", "conv2_1.conv1.bias"}
+        names, norms = [], []
+        for k, p in model.named_parameters():
+            names.append(k)
+            norms.append(float(p.grad.double().norm()))
+            if k in keep_full:
+                fx[f"grad.{k}"] = p.grad.numpy()
+        fx["grad_names"] = np.array(names)
+        fx["grad_norms"] = np.array(norms, np.float64)
+        st = model.state_dict()
+        for k in ("conv0_0.bn1.running_mean", "conv0_0.bn1.running_var", "conv0_0.bn1.num_batches_tracked",
+                  "conv4_0.bn2.running_var", "conv0_4.bn2.running_mean", "conv0_4.bn1.num_batches_tracked"):
+            fx[f"state.{k}"] = st[k].numpy()
+        # eval-mode forward with the updated running stats
+        model.eval()
+        with torch.no_grad():
+            fx["logits_eval"] = model(torch.from_numpy(xA), torch.from_numpy(xB)).numpy()
+        np.savez_compressed(OUT / f"snunet_{tag}.npz", **fx)
+        print(tag, "loss", float(loss.detach()), "logits", out.shape)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,255 @@
+"""Reference semantics of every C-ABI op, written with torch CPU ops.  TEST-ONLY.
+
+Two uses: (1) `-m "not gpu"` tests drive the product's host schedule (snunet_engine.py) through
+this backend to check the wiring against the oracle without a GPU; (2) `-m gpu` tests compare
+each CUDA kernel with the same contract on identical inputs.  Never imported by the product.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from kurosiwo_b200.lib import View
+
+
+def _t(v: View) -> torch.Tensor:
+    return v.tensor()
+
+
+class ShadowOps:
+    name = "shadow"
+
+    def __init__(self):
+        self.launches = 0
+
+    def set_option(self, name, value):
+        pass
+
+    def zero_(self, t):
+        t.zero_()
+
+    # -- plumbing ----------------------------------------------------------------------------
+    def permute_cast(self, src, dst, dims, strides, accumulate=False, src_offset=0):
+        d = list(dims) + [1] * (4 - len(dims))
+        s = list(strides) + [0] * (4 - len(strides))
+        idx = torch.zeros(d, dtype=torch.int64)
+        for ax in range(4):
+            shape = [1, 1, 1, 1]
+            shape[ax] = d[ax]
+            idx = idx + (torch.arange(d[ax]) * s[ax]).view(shape)
+        vals = src.reshape(-1)[(idx + src_offset).reshape(-1)].float()
+        out = dst.reshape(-1)[: vals.numel()]
+        if accumulate:
+            vals = vals + out.float()
+        out.copy_(vals.to(dst.dtype))
+
+    # -- convolution -------------------------------------------------------------------------
+    def conv2d(self, N, H, W, ksize, srcs, weight, bias, dsts, acc=None, stats=None, impl=0):
+        acc = acc or [False] * len(dsts)
+        x = torch.cat([_t(v).float() for v in srcs], dim=3).permute(0, 3, 1, 2)
+        cin = x.shape[1]
+        cout = sum(v.C for v in dsts)
+        w = weight.float().view(ksize * ksize, cout, cin).permute(1, 2, 0).reshape(cout, cin, ksize, ksize)
+        y = F.conv2d(x, w, None if bias is None else bias.float(), padding=ksize // 2).permute(0, 2, 3, 1)
+        c0 = 0
+        for v, a in zip(dsts, acc):
+            part = y[..., c0:c0 + v.C]
+            t = _t(v)
+            if a:
+                part = part + t.float()
+            t.copy_(part.to(t.dtype))
+            c0 += v.C
+        if stats is not None:
+            st = torch.cat([_t(v).float() for v in dsts], dim=3).double().reshape(-1, cout)
+            stats.view(2, cout)[0] += st.sum(0)
+            stats.view(2, cout)[1] += (st * st).sum(0)
+
+    def conv2d_wgrad(self, N, H, W, ksize, xs, dys, dw, accumulate=False, impl=0):
+        x = torch.cat([_t(v).float() for v in xs], dim=3).permute(0, 3, 1, 2)
+        dy = torch.cat([_t(v).float() for v in dys], dim=3).permute(0, 3, 1, 2)
+        cin, cout = x.shape[1], dy.shape[1]
+        g = torch.nn.grad.conv2d_weight(x, (cout, cin, ksize, ksize), dy, padding=ksize // 2)  # (co, ci, k, k)
+        g = g.reshape(cout, cin, ksize * ksize).permute(2, 0, 1).reshape(-1)
+        out = dw.reshape(-1)[: g.numel()]
+        out.copy_(g + out if accumulate else g)
+
+    # -- batch norm / pooling ----------------------------------------------------------------
+    def bn_stats(self, x, sums):
+        t = _t(x).double().reshape(-1, x.C)
+        sums.view(2, x.C)[0] += t.sum(0)
+        sums.view(2, x.C)[1] += (t * t).sum(0)
+
+    def bn_finalize(self, Cn, count, sums, gamma, beta, eps, momentum, rmean, rvar, scale, shift, mean, rstd):
+        s = sums.view(2, Cn)
+        mu = s[0] / count
+        var = (s[1] / count - mu * mu).clamp_min(0)
+        rs = (1.0 / torch.sqrt(var + eps)).float()
+        sc = gamma * rs
+        scale.copy_(sc)
+        shift.copy_(beta - mu.float() * sc)
+        mean.copy_(mu.float())
+        rstd.copy_(rs)
+        if rmean is not None:
+            rmean.mul_(1 - momentum).add_(momentum * mu.float())
+        if rvar is not None:
+            unb = var * count / (count - 1.0) if count > 1 else var
+            rvar.mul_(1 - momentum).add_(momentum * unb.float())
+
+    def bn_act(self, y, scale, shift, res, relu, out, pool):
+        v = _t(y).float() * scale + shift
+        if res is not None:
+            v = v + _t(res).float()
+        if relu:
+            v = F.relu(v)
+        o = _t(out)
+        o.copy_(v.to(o.dtype))
+        if pool is not None:
+            p = F.max_pool2d(o.float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+            _t(pool).copy_(p.to(o.dtype))
+
+    def bn_bwd_reduce(self, dout, out, y, mean, rstd, sums):
+        g = _t(dout).float() * (_t(out).float() > 0)
+        xh = (_t(y).float() - mean) * rstd
+        Cn = y.C
+        sums.view(2, Cn)[0] += g.double().reshape(-1, Cn).sum(0)
+        sums.view(2, Cn)[1] += (g * xh).double().reshape(-1, Cn).sum(0)
+
+    def bn_bwd_apply(self, dout, out, y, mean, rstd, gamma, sums, count, add_dout, add_out, dy, dgamma, dbeta, accumulate):
+        Cn = y.C
+        s = sums.view(2, Cn).float()
+        g = _t(dout).float() * (_t(out).float() > 0)
+        xh = (_t(y).float() - mean) * rstd
+        v = gamma * rstd * (g - s[0] / count - xh * (s[1] / count))
+        if add_dout is not None:
+            v = v + _t(add_dout).float() * (_t(add_out).float() > 0)
+        t = _t(dy)
+        t.copy_(v.to(t.dtype))
+        if dgamma is not None:
+            dgamma.copy_(dgamma + s[1] if accumulate else s[1])
+        if dbeta is not None:
+            dbeta.copy_(dbeta + s[0] if accumulate else s[0])
+
+    def maxpool2x2_bwd(self, x, dpool, dx, accumulate):
+        xt = _t(x).float().permute(0, 3, 1, 2)
+        _, idx = F.max_pool2d(xt, 2, 2, return_indices=True)
+        g = F.max_unpool2d(_t(dpool).float().permute(0, 3, 1, 2), idx, 2, 2, output_size=xt.shape[-2:]).permute(0, 2, 3, 1)
+        t = _t(dx)
+        t.copy_((g + t.float() if accumulate else g).to(t.dtype))
+
+    def channel_sum(self, x, out, accumulate):
+        s = _t(x).float().reshape(-1, x.C).sum(0)
+        out.copy_(out + s if accumulate else s)
+
+    # -- ECAM --------------------------------------------------------------------------------
+    def ecam_pool(self, xs, pooled, argmax, scratch):
+        N, J, Cb = xs[0].N, len(xs), xs[0].C
+        CT = (J + 1) * Cb
+        ts = [_t(v).float() for v in xs]
+        full = torch.cat(ts + [sum(ts)], dim=3).reshape(N, -1, CT)  # [N, HW, CT]
+        p = pooled.view(N, 2, CT)
+        p[:, 0] = full.mean(1)
+        mx, am = full.max(1)
+        # first occurrence of the maximum
+        first = (full == mx.unsqueeze(1)).float().argmax(1)
+        p[:, 1] = mx
+        argmax.view(N, CT).copy_(first.to(torch.int32))
+
+    def ecam_gates(self, N, Cb, J, hid, hid1, pooled, w_fc1, w_fc2, w1_fc1, w1_fc2, gates, hidden):
+        CC, CT, HT = J * Cb, (J + 1) * Cb, hid + hid1
+        p = pooled.view(N, 2, CT)
+        g = gates.view(N, CT)
+        hd = hidden.view(N, 2, HT)
+        for (c0, c1, h0, h1, w1, w2) in ((0, CC, 0, hid, w_fc1.view(hid, CC), w_fc2.view(CC, hid)),
+                                         (CC, CT, hid, HT, w1_fc1.view(hid1, Cb), w1_fc2.view(Cb, hid1))):
+            ha = p[:, 0, c0:c1] @ w1.t()
+            hm = p[:, 1, c0:c1] @ w1.t()
+            hd[:, 0, h0:h1] = ha
+            hd[:, 1, h0:h1] = hm
+            g[:, c0:c1] = torch.sigmoid((F.relu(ha) + F.relu(hm)) @ w2.t())
+
+    def ecam_final(self, xs, gates, wf, bf, K, logits):
+        N, J, Cb = xs[0].N, len(xs), xs[0].C
+        CC = J * Cb
+        g = gates.view(N, (J + 1) * Cb)
+        cat = torch.cat([_t(v).float() for v in xs], dim=3)  # N,H,W,CC
+        out = g[:, None, None, :CC] * (cat + g[:, None, None, CC:].repeat(1, 1, 1, J))
+        lg = out @ wf.view(K, CC).t() + bf
+        logits.copy_(lg.permute(0, 3, 1, 2))
+
+    def ecam_bwd_reduce(self, xs, K, dlogits, red):
+        N, J, Cb = xs[0].N, len(xs), xs[0].C
+        CC = J * Cb
+        cat = torch.cat([_t(v).float() for v in xs], dim=3).reshape(N, -1, CC).double()
+        dl = dlogits.reshape(N, K, -1).double()
+        r = red.view(N, K * CC + K)
+        r[:, :K * CC] = torch.bmm(dl, cat).reshape(N, K * CC)
+        r[:, K * CC:] = dl.sum(2)
+
+    def ecam_gates_bwd(self, N, Cb, J, hid, hid1, K, pooled, hidden, gates, red, wf, w_fc1, w_fc2, w1_fc1, w1_fc2,
+                       dpooled, dwf, dbf, dw_fc1, dw_fc2, dw1_fc1, dw1_fc2, accumulate=False):
+        CC, CT, HT = J * Cb, (J + 1) * Cb, hid + hid1
+        p, hd, g = pooled.view(N, 2, CT), hidden.view(N, 2, HT), gates.view(N, CT)
+        r = red.view(N, K * CC + K).float()
+        B, D = r[:, :K * CC].view(N, K, CC), r[:, K * CC:]
+        wfm = wf.view(K, CC)
+        ca, ca1 = g[:, :CC], g[:, CC:]
+        A = B + ca1.repeat(1, J)[:, None, :] * D[:, :, None]
+        dca = (wfm[None] * A).sum(1)
+        dca1 = (ca * (D @ wfm)).view(N, J, Cb).sum(1)
+        outs = {"dwf": (ca[:, None, :] * A).sum(0).reshape(-1), "dbf": D.sum(0)}
+        dp = dpooled.view(N, 2, CT)
+        for (c0, c1, h0, h1, w1, w2, dg, gg, n1, n2) in (
+                (0, CC, 0, hid, w_fc1.view(hid, CC), w_fc2.view(CC, hid), dca, ca, "dw_fc1", "dw_fc2"),
+                (CC, CT, hid, HT, w1_fc1.view(hid1, Cb), w1_fc2.view(Cb, hid1), dca1, ca1, "dw1_fc1", "dw1_fc2")):
+            ds = dg * gg * (1 - gg)
+            ha, hm = hd[:, 0, h0:h1], hd[:, 1, h0:h1]
+            outs[n2] = (ds.t() @ (F.relu(ha) + F.relu(hm))).reshape(-1)
+            drelu = ds @ w2
+            dha, dhm = drelu * (ha > 0), drelu * (hm > 0)
+            outs[n1] = (dha.t() @ p[:, 0, c0:c1] + dhm.t() @ p[:, 1, c0:c1]).reshape(-1)
+            dp[:, 0, c0:c1] = dha @ w1
+            dp[:, 1, c0:c1] = dhm @ w1
+        for name, dst in (("dwf", dwf), ("dbf", dbf), ("dw_fc1", dw_fc1), ("dw_fc2", dw_fc2), ("dw1_fc1", dw1_fc1), ("dw1_fc2", dw1_fc2)):
+            if dst is not None:
+                d = dst.reshape(-1)
+                d.copy_(d + outs[name] if accumulate else outs[name])
+
+    def ecam_bwd_apply(self, dxs, gates, wf, K, dlogits, dpooled, argmax):
+        N, J, Cb = dxs[0].N, len(dxs), dxs[0].C
+        H, W = dxs[0].H, dxs[0].W
+        CC, CT = J * Cb, (J + 1) * Cb
+        g = gates.view(N, CT)
+        dp = dpooled.view(N, 2, CT)
+        am = argmax.view(N, CT).long()
+        dl = dlogits.reshape(N, K, H * W)
+        dO = torch.einsum("kc,nkp->npc", wf.view(K, CC), dl)  # N,HW,CC
+        v = g[:, None, :CC] * dO + (dp[:, 0, :CC] + dp[:, 0, CC:].repeat(1, J))[:, None, :] / (H * W)
+        onehot = torch.zeros(N, H * W, CT)
+        onehot.scatter_(1, am[:, None, :], 1.0)
+        v = v + onehot[:, :, :CC] * dp[:, 1, None, :CC] + onehot[:, :, CC:].repeat(1, 1, J) * dp[:, 1, None, CC:].repeat(1, 1, J)
+        v = v.view(N, H, W, CC)
+        for j, d in enumerate(dxs):
+            t = _t(d)
+            t.copy_(v[..., j * Cb:(j + 1) * Cb].to(t.dtype))
+
+    # -- loss / optimizer --------------------------------------------------------------------
+    def ce_dice_workspace(self, N, device):
+        return torch.empty(2 * N + 16, dtype=torch.float64, device=device)
+
+    def ce_dice(self, logits, labels, class_weights, ignore_index, grad_scale, loss_out, dlogits, pred, workspace):
+        from oracle.loss_oracle import ce_dice
+        r = ce_dice(logits.numpy(), labels.numpy(), class_weights.numpy(), ignore_index)
+        loss_out.copy_(torch.tensor([r["loss"], r["dice"], r["ce"]], dtype=torch.float32))
+        if dlogits is not None:
+            dlogits.copy_(torch.from_numpy(r["dlogits"] * grad_scale).float())
+        if pred is not None:
+            pred.copy_(torch.from_numpy(r["argmax"]))
+
+    def adam_step(self, p, g, m, v, lr, b1, b2, eps, wd, grad_scale, step):
+        t = int(step.item()) + 1
+        gg = g * grad_scale + wd * p
+        m.mul_(b1).add_(gg, alpha=1 - b1)
+        v.mul_(b2).addcmul_(gg, gg, value=1 - b2)
+        bc1, bc2 = 1 - b1 ** t, 1 - b2 ** t
+        p.addcdiv_(m, v.sqrt() / (bc2 ** 0.5) + eps, value=-lr / bc1)
+        step += 1
