@@ -1,0 +1,158 @@
+"""Mirror of the reference's `training/change_detection_trainer.py` entry points for the B200 path.
+
+`train_change_detection(model, train_loader, val_loader, test_loader, configs, model_configs)` and
+`eval_change_detection(model, loader, settype, configs, model_configs)` keep the reference signatures,
+batch tuple layout (dataset/Dataset.py:826-839), checkpoint dict layout (:206-213) and return values (:791).
+The inner loop (:93-204) is replaced: pinned H2D copies, ONE fused engine step (forward, CE+Dice+argmax,
+backward, Adam) with no per-iteration host sync, metrics from one device-side confusion matrix.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+from .snunet import SNUNet_ECAM
+from .utilities import ConfusionMetrics, create_loss, init_lr_scheduler
+
+CLASS_LABELS = {0: "No water", 1: "Permanent Waters", 2: "Floods", 3: "Invalid pixels"}
+
+
+def unpack_batch(batch, configs):
+    """change_detection_trainer.py:95-106 -> dict(post_event, mask, pre_event_1, pre_event_2, dem, clz, activ)."""
+    if configs.get("scale_input") is not None:
+        if configs.get("dem"):
+            (_, _, post, mask, _, _, pre1, _, _, pre2, dem, clz, activ) = batch
+        else:
+            (_, _, post, mask, _, _, pre1, _, _, pre2, clz, activ) = batch
+            dem = None
+    else:
+        if configs.get("dem"):
+            post, mask, pre1, pre2, dem, clz, activ = batch
+        else:
+            post, mask, pre1, pre2, clz, activ = batch
+            dem = None
+    return dict(post_event=post, mask=mask, pre_event_1=pre1, pre_event_2=pre2, dem=dem, clz=clz, activ=activ)
+
+
+def select_inputs(b, configs, device):
+    """change_detection_trainer.py:117-133: the two images in `configs['inputs']` order (+DEM channel)."""
+    outs = []
+    for name in configs["inputs"]:
+        x = b[name].to(device, non_blocking=True)
+        if configs.get("dem"):
+            x = torch.cat((x, b["dem"].to(device, non_blocking=True)), dim=1)
+        outs.append(x)
+    return outs
+
+
+class FusedStepper:
+    """Owns the engine-side training state for one model/batch geometry (the public fast path)."""
+
+    def __init__(self, model: SNUNet_ECAM, configs, model_configs, process_group=None):
+        if not isinstance(model, SNUNet_ECAM):
+            raise TypeError("the fused step is implemented for kurosiwo_b200.SNUNet_ECAM")
+        if configs.get("loss_function", "ce+dice") != "ce+dice":
+            raise NotImplementedError("the fused step computes CE+Dice (utilities/bce_and_dice.py); set loss_function='ce+dice'")
+        opt = model_configs.get("optimizer", "adam")
+        if opt != "adam":
+            raise NotImplementedError(f"fused optimizer '{opt}' (only 'adam': change_detection_trainer.py:52-54)")
+        self.model, self.configs, self.model_configs, self.pg = model, configs, model_configs, process_group
+        self.engine = None
+        self.lr = float(model_configs["learning_rate"])
+
+    def _engine(self, x):
+        eng = self.model.engine(x)
+        if eng is not self.engine:
+            eng.init_training(class_weights=self.configs.get("class_weights", [1.0, 1.0, 1.0]), ignore_index=3, lr=self.lr,
+                              betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=self.pg)
+            self.engine = eng
+        return eng
+
+    def set_lr(self, lr: float):
+        self.lr = float(lr)
+        if self.engine is not None:
+            self.engine.hp["lr"] = self.lr
+
+    def step_host(self, batch):
+        """One training step from a HOST batch (pinned tensors): H2D copies + fused step. Returns device loss[3]."""
+        dev = self.configs["device"]
+        b = unpack_batch(batch, self.configs)
+        xa, xb = select_inputs(b, self.configs, dev)
+        mask = b["mask"].to(dev, non_blocking=True)
+        eng = self._engine(xa)
+        return eng.train_step(xa, xb, mask), mask
+
+
+def train_change_detection(model, train_loader, val_loader, test_loader, configs, model_configs, process_group=None):
+    assert len(configs["inputs"]) == 2, f'Model {model_configs.get("method")} requires exactly 2 input images.'
+    device = configs["device"]
+    model.to(device)
+    stepper = FusedStepper(model, configs, model_configs, process_group)
+    metrics = ConfusionMetrics(configs["num_classes"], 3, device)
+    # a torch optimizer object only to drive the reference's per-epoch LR scheduler / checkpoint layout
+    sched_opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=float(model_configs["learning_rate"]))
+    lr_scheduler = init_lr_scheduler(sched_opt, configs, model_configs, steps=len(train_loader))
+    best_val, last = 0.0, None
+    print(f'===== checkpoint_path: {configs.get("checkpoint_path")} ====')
+    for epoch in range(0, configs["epochs"]):
+        model.train()
+        train_loss = torch.zeros((), dtype=torch.float64, device=device)
+        metrics.reset()
+        index = -1
+        for index, batch in enumerate(train_loader):
+            loss3, mask = stepper.step_host(batch)
+            train_loss += loss3[0].double() * mask.shape[0]          # stays on device: no .item() in the loop
+            metrics.update(stepper.engine.pred, mask)
+            if configs.get("on_screen_prints") and index % configs.get("print_frequency", 10) == 0:
+                print(f"({epoch}) it {index} Train Loss: {train_loss.item():.4f}")
+        loss_val = float(loss3[0].item()) if index >= 0 else float("nan")
+        if configs.get("checkpoint_path") and index % configs.get("train_save_checkpoint_freq", 1) == 0:
+            torch.save({"epoch": epoch, "model_state_dict": model.state_dict(),
+                        "optimizer_state_dict": {"m": stepper.engine.adam_m, "v": stepper.engine.adam_v, "step": stepper.engine.adam_step},
+                        "lr_scheduler_state_dict": lr_scheduler.state_dict(), "loss": loss_val},
+                       Path(configs["checkpoint_path"]) / f"checkpoint_epoch={epoch}.pt")
+        acc, f1, prec, rec, iou = metrics.compute()
+        if configs.get("on_screen_prints"):
+            for c in range(3):
+                print(f"Train Accuracy ({CLASS_LABELS[c]}): {100 * acc[c].item()}  F-Score: {100 * f1[c].item()}  IoU: {100 * iou[c].item()}")
+            print(f"Train MeanIoU: {iou[:3].mean().item() * 100}")
+        lr_scheduler.step()
+        stepper.set_lr(lr_scheduler.get_last_lr()[0])
+        if val_loader is not None:
+            val_acc, val_score, miou = eval_change_detection(model, val_loader, settype="Validation", configs=configs, model_configs=model_configs)
+            if miou > best_val and configs.get("checkpoint_path"):
+                best_val = miou
+                torch.save({"epoch": epoch, "model_state_dict": model.state_dict(), "loss": loss_val},
+                           Path(configs["checkpoint_path"]) / "best_segmentation.pt")
+                (Path(configs["checkpoint_path"]) / "best_segmentation.txt").write_text(f"{epoch}\n{miou}")
+        last = dict(epoch=epoch, loss=loss_val, train_loss=float(train_loss.item()), miou=float(iou[:3].mean().item()))
+    return last
+
+
+def eval_change_detection(model, loader, settype, configs=None, model_configs=None):
+    """change_detection_trainer.py:325-791: eval-mode forward (running-stat BN), CE(+Dice) loss, metrics.
+    Returns (100*accuracy[4], 100*mean F1, 100*mIoU) like the reference (:791)."""
+    device = configs["device"]
+    metrics = ConfusionMetrics(configs["num_classes"], 3, device)
+    criterion = create_loss(configs, mode="val")
+    model.to(device)
+    model.eval()
+    total_loss = torch.zeros((), dtype=torch.float64, device=device)
+    n = 0
+    with torch.no_grad():
+        for batch in loader:
+            b = unpack_batch(batch, configs)
+            inputs = select_inputs(b, configs, device)
+            mask = b["mask"].to(device, non_blocking=True)
+            output = model(*inputs)
+            loss = criterion(output, mask)
+            pred = getattr(criterion, "last_pred", None)
+            predictions = pred if pred is not None else output.argmax(1)
+            total_loss += loss.double() * mask.shape[0]
+            n += mask.shape[0]
+            metrics.update(predictions, mask)
+    acc, f1, prec, rec, iou = metrics.compute()
+    print(f"{settype} Loss: {(total_loss / max(n, 1)).item()}  MeanIoU: {100 * iou[:3].mean().item()}")
+    return 100 * acc, 100 * f1[:3].mean(), 100 * iou[:3].mean()

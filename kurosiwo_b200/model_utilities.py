@@ -1,0 +1,23 @@
+"""Mirror of the reference's `models/model_utilities.py:initialize_cd_model` for the models on the B200 path."""
+from __future__ import annotations
+
+import torch
+
+from .snunet import SNUNet_ECAM
+
+
+def initialize_cd_model(configs, model_configs, phase="train"):
+    method = configs["method"].lower()
+    if method == "snunet":
+        precision = "bf16" if configs.get("mixed_precision", True) else "fp32"
+        precision = configs.get("precision", precision)
+        model = SNUNet_ECAM(configs["num_channels"], configs["num_classes"], base_channel=model_configs["base_channel"],
+                            precision=precision)
+    else:
+        raise NotImplementedError(f"method {configs['method']} is not on the B200 hot path yet (SURVEY.md §8: siam-conc/diff, "
+                                  "changeformer and finetune are 'next' rows)")
+    model = model.to(configs["device"])
+    if configs.get("resume_checkpoint"):
+        checkpoint = torch.load(configs["resume_checkpoint"], map_location=configs["device"])
+        model.load_state_dict(checkpoint["model_state_dict"])
+    return model

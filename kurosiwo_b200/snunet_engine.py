@@ -384,3 +384,60 @@ class SNUNetEngine:
                 self._block_backward(e, gd, None if gd is None else [False], e.name not in seen_blocks)
                 seen_blocks.add(e.name)
         self._unpack_grads()
+
+    # ------------------------------------------------------------------------------------------
+    # fused training step: forward -> CE+Dice (+argmax) -> backward -> (all-reduce) -> Adam
+    # (training/change_detection_trainer.py:136-177 without the two loss.item() host syncs)
+    # ------------------------------------------------------------------------------------------
+    def init_training(self, class_weights=(1.0, 1.0, 1.0), ignore_index: int = 3, lr: float = 1e-3,
+                      betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, process_group=None):
+        dev = self.device
+        self.params.ensure(dev)
+        self.cw = torch.tensor(class_weights, dtype=torch.float32, device=dev)
+        self.ignore_index = ignore_index
+        self.hp = dict(lr=lr, b1=betas[0], b2=betas[1], eps=eps, wd=weight_decay)
+        self.adam_m = torch.zeros_like(self.params.flat)
+        self.adam_v = torch.zeros_like(self.params.flat)
+        self.adam_step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.loss3 = torch.zeros(3, dtype=torch.float32, device=dev)
+        self.dlogits = torch.zeros_like(self.logits)
+        self.pred = torch.zeros(self.N, self.H, self.W, dtype=torch.uint8, device=dev)
+        self.loss_ws = self.ops.ce_dice_workspace(self.N, dev)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+            dist.broadcast(self.params.flat, src=dist.get_global_rank(process_group, 0) if hasattr(dist, "get_global_rank") else 0,
+                           group=process_group)
+        self.graph = None
+
+    def train_step(self, xA: torch.Tensor, xB: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+        """One optimizer step; returns the device tensor [total, dice, ce] (no host sync)."""
+        ops = self.ops
+        logits = self.forward(xA, xB, training=True)
+        ops.ce_dice(logits, mask, self.cw, self.ignore_index, 1.0, self.loss3, self.dlogits, self.pred, self.loss_ws)
+        self.backward(self.dlogits)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.params.grad, group=self.pg)   # NCCL over NVLink: ONE message = all gradients
+        hp = self.hp
+        ops.adam_step(self.params.flat, self.params.grad, self.adam_m, self.adam_v, hp["lr"], hp["b1"], hp["b2"], hp["eps"],
+                      hp["wd"], 1.0 / self.world, self.adam_step)
+        return self.loss3
+
+    def capture(self, xA: torch.Tensor, xB: torch.Tensor, mask: torch.Tensor):
+        """Capture train_step into a CUDA graph over the given STATIC input tensors (single-GPU)."""
+        assert self.world == 1, "graph capture of the NCCL step is not used; call train_step directly"
+        self.params.ensure(self.device)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self.train_step(xA, xB, mask)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.train_step(xA, xB, mask)
+        return self.graph

@@ -1,0 +1,26 @@
+"""Helpers for the -m gpu tests: mirror GPU views on the CPU and compare CUDA ops with the shadow ops."""
+import torch
+
+from kurosiwo_b200.lib import View
+
+
+def mirror(v: View) -> View:
+    return View(v.base.detach().cpu().clone(), v.offset, v.N, v.H, v.W, v.C, v.sn, v.sh, v.sw)
+
+
+def rand_view(N, H, W, C, dtype, device, ctot=None, c0=0, scale=1.0, gen=None):
+    """A view of C channels starting at channel c0 of a [N,H,W,ctot] buffer filled with N(0,scale)."""
+    ctot = ctot or C
+    base = (torch.randn(N * H * W * ctot, generator=gen, device="cpu") * scale).to(dtype).to(device)
+    full = View(base, 0, N, H, W, ctot, H * W * ctot, W * ctot, ctot)
+    return full.ch(c0, C), full
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def max_rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))

@@ -1,0 +1,137 @@
+"""Stand-alone probe of the tcgen05 conv / wgrad kernels against the CUDA-core kernels (same inputs).
+
+Run on a B200:  python tests/tc_probe.py [out.json]
+Each case is tried for every (bo_mode, MT) so that a descriptor-convention problem shows up as a
+pattern instead of a single failure.  Used by tests/test_gpu_tc.py through a subprocess + timeout so a
+hung kernel cannot hang the test session.
+"""
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+from kurosiwo_b200.lib import IMPL_SIMT, IMPL_TC, CudaOps, KsError, View  # noqa: E402
+from gpu_util import rand_view, rel_l2  # noqa: E402
+
+dev = "cuda:0"
+bf = torch.bfloat16
+
+
+def conv_case(ops, name, N, H, W, ks, src_specs, dst_specs, bias, gen):
+    """src_specs/dst_specs: list of (C, ctot, c0, kind) kind in {'plain','phases'}; returns dict of errors."""
+    srcs, dsts, dst_fulls = [], [], []
+    for (C, ctot, c0, kind) in src_specs:
+        if kind == "phases":
+            _, full = rand_view(N, 2 * H, 2 * W, C, bf, dev, gen=gen)
+            srcs += [full.phase(k // 2, k % 2) for k in range(4)]
+        else:
+            v, _ = rand_view(N, H, W, C, bf, dev, ctot, c0, gen=gen)
+            srcs.append(v)
+    accs = []
+    for (C, ctot, c0, kind, acc) in dst_specs:
+        if kind == "phases":
+            _, full = rand_view(N, 2 * H, 2 * W, C, bf, dev, gen=gen)
+            dsts += [full.phase(k // 2, k % 2) for k in range(4)]
+            accs += [acc] * 4
+            dst_fulls.append(full)
+        else:
+            v, full = rand_view(N, H, W, C, bf, dev, ctot, c0, gen=gen)
+            dsts.append(v)
+            accs.append(acc)
+            dst_fulls.append(full)
+    cin, cout = sum(v.C for v in srcs), sum(v.C for v in dsts)
+    w = (torch.randn(ks * ks * cout * cin, generator=gen) * (2.0 / (cin * ks * ks)) ** 0.5).to(bf).to(dev)
+    b = (torch.randn(cout, generator=gen) * 0.1).to(dev) if bias else None
+    init = [f.base.clone() for f in dst_fulls]
+    # reference: CUDA-core kernel
+    ops.conv2d(N, H, W, ks, srcs, w, b, dsts, accs, None, IMPL_SIMT)
+    torch.cuda.synchronize()
+    ref = [f.base.clone() for f in dst_fulls]
+    res = {}
+    for bo in (0, 1):
+        for mt in (1, 2, 4):
+            for f, i0 in zip(dst_fulls, init):
+                f.base.copy_(i0)
+            ops.set_option("tc_bo_mode", bo)
+            ops.set_option("tc_mt", mt)
+            key = f"bo{bo}_mt{mt}"
+            try:
+                ops.conv2d(N, H, W, ks, srcs, w, b, dsts, accs, None, IMPL_TC)
+                torch.cuda.synchronize()
+                err = max(rel_l2(f.base.float(), r.float()) for f, r in zip(dst_fulls, ref))
+                res[key] = err
+            except KsError as e:
+                res[key] = f"error: {e}"
+    ops.set_option("tc_bo_mode", 0)
+    ops.set_option("tc_mt", 0)
+    return res
+
+
+def wgrad_case(ops, name, N, H, W, ks, x_specs, dy_specs, gen):
+    xs, dys = [], []
+    for specs, out in ((x_specs, xs), (dy_specs, dys)):
+        for (C, ctot, c0, kind) in specs:
+            if kind == "phases":
+                _, full = rand_view(N, 2 * H, 2 * W, C, bf, dev, gen=gen)
+                out += [full.phase(k // 2, k % 2) for k in range(4)]
+            else:
+                v, _ = rand_view(N, H, W, C, bf, dev, ctot, c0, gen=gen)
+                out.append(v)
+    cin, cout = sum(v.C for v in xs), sum(v.C for v in dys)
+    ref = torch.zeros(ks * ks * cout * cin, device=dev)
+    got = torch.zeros_like(ref)
+    ops.conv2d_wgrad(N, H, W, ks, xs, dys, ref, False, IMPL_SIMT)
+    torch.cuda.synchronize()
+    try:
+        ops.conv2d_wgrad(N, H, W, ks, xs, dys, got, False, IMPL_TC)
+        torch.cuda.synchronize()
+        e1 = rel_l2(got, ref)
+        ops.conv2d_wgrad(N, H, W, ks, xs, dys, got, True, IMPL_TC)  # accumulate: 2x
+        torch.cuda.synchronize()
+        e2 = rel_l2(got, 2 * ref)
+        return {"assign": e1, "accumulate": e2}
+    except KsError as e:
+        return {"error": str(e)}
+
+
+def main():
+    out = Path(sys.argv[1]) if len(sys.argv) > 1 else None
+    ops = CudaOps()
+    gen = torch.Generator().manual_seed(1234)
+    report = {"conv": {}, "wgrad": {}}
+    P = "plain"
+    conv_cases = {
+        "A_k3_c64_n32": (2, 16, 28, 3, [(64, 64, 0, P)], [(32, 32, 0, P, False)], True),
+        "B_k3_prefix96+64_n32_bk32": (2, 16, 16, 3, [(96, 192, 0, P), (64, 64, 0, P)], [(32, 192, 64, P, False)], True),
+        "C_k3_c128_n256": (3, 8, 8, 3, [(128, 128, 0, P)], [(256, 256, 0, P, False)], True),
+        "D_k3_h14_c256_n512": (2, 14, 14, 3, [(256, 256, 0, P)], [(512, 512, 0, P, False)], True),
+        "E_k1_convT_fwd": (2, 8, 8, 1, [(64, 64, 0, P)], [(64, 64, 0, "phases", False)], True),
+        "F_k1_convT_dgrad_acc": (2, 8, 8, 1, [(64, 64, 0, "phases")], [(64, 128, 64, P, True)], False),
+        "G_k3_dgrad_multidst": (2, 16, 28, 3, [(32, 32, 0, P)], [(64, 192, 0, P, True), (32, 192, 64, P, False), (64, 64, 0, P, False)], False),
+        "H_k3_odd_hw": (1, 20, 20, 3, [(64, 64, 0, P)], [(64, 64, 0, P, False)], True),
+        "I_k3_big": (4, 56, 56, 3, [(128, 256, 0, P), (128, 128, 0, P)], [(128, 128, 0, P, False)], True),
+    }
+    for name, (N, H, W, ks, ss, ds, bias) in conv_cases.items():
+        report["conv"][name] = conv_case(ops, name, N, H, W, ks, ss, ds, bias, gen)
+        print(name, report["conv"][name], flush=True)
+    wgrad_cases = {
+        "H_k3_x96+64_dy32": (2, 16, 32, 3, [(96, 192, 0, P), (64, 64, 0, P)], [(32, 32, 0, P)]),
+        "I_k3_x128_dy128": (2, 16, 16, 3, [(128, 128, 0, P)], [(128, 128, 0, P)]),
+        "J_k3_x256_dy256": (2, 8, 8, 3, [(256, 256, 0, P)], [(256, 256, 0, P)]),
+        "K_k1_convT": (2, 8, 8, 1, [(64, 64, 0, P)], [(64, 64, 0, "phases")]),
+        "L_k3_x64_dy64_odd": (3, 20, 12, 3, [(64, 64, 0, P)], [(64, 64, 0, P)]),
+        "M_k3_big": (4, 56, 56, 3, [(192, 256, 0, P), (128, 128, 0, P)], [(64, 64, 0, P)]),
+    }
+    for name, (N, H, W, ks, xs, ys) in wgrad_cases.items():
+        report["wgrad"][name] = wgrad_case(ops, name, N, H, W, ks, xs, ys, gen)
+        print(name, report["wgrad"][name], flush=True)
+    if out:
+        out.parent.mkdir(parents=True, exist_ok=True)
+        out.write_text(json.dumps(report, indent=1))
+
+
+if __name__ == "__main__":
+    main()

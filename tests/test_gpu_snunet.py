@@ -1,0 +1,162 @@
+"""-m gpu: the SNUNet-ECAM training step on the CUDA path against reference outputs (golden fixtures)
+and the CPU oracle on identical seeded inputs.
+
+Tolerances (stated per BASELINE.json / SURVEY.md §8c):
+  fp32 parity mode : logits 1e-3 relative (max-norm), loss 1e-4, gradients 2e-3 of each tensor's max,
+                     argmax bit-exact wherever the top-2 logit margin exceeds 1e-3.
+  bf16 perf mode   : the reference's own bf16-autocast forward differs from its fp32 forward by ~1.3e-2
+                     rel-L2, so: logits rel-L2 < 5e-2, loss within 3e-2, argmax agreement > 97 %.
+"""
+import numpy as np
+import pytest
+import torch
+
+from kurosiwo_b200.snunet import SNUNet_ECAM
+from oracle import snunet_oracle, weights
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _model(sd_np, base, precision):
+    m = SNUNet_ECAM(2, 3, base_channel=base, precision=precision)
+    m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd_np.items()})
+    return m.to(DEV).train()
+
+
+def _argmax_check(logits, ref_logits, margin=1e-3):
+    top2 = torch.topk(ref_logits, 2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > margin * ref_logits.abs().amax(1).clamp_min(1.0)
+    assert torch.equal(logits.argmax(1)[safe], ref_logits.argmax(1)[safe])
+    return float(safe.float().mean())
+
+
+@pytest.mark.parametrize("tag", ["b8_n2_s32", "b32_n2_s16"])
+def test_fp32_matches_reference_golden(golden_dir, tag):
+    from kurosiwo_b200.bce_and_dice import BCEandDiceLoss
+    fx = np.load(golden_dir / f"snunet_{tag}.npz")
+    base, N, H, W, seed = (int(fx[k]) for k in ("base", "N", "H", "W", "seed"))
+    sd_np = weights.make_state(seed, 2, 3, base)
+    xA, xB, mask = (torch.from_numpy(a).to(DEV) for a in weights.make_batch(seed, N, H, W))
+    model = _model(sd_np, base, "fp32")
+    crit = BCEandDiceLoss(weights=[1.0, 1.0, 1.0], ignore_index=3, use_softmax=True).to(DEV)
+    out = model(xA, xB)                               # reference call signature: model(*inputs)
+    loss = crit(out, mask)                            # criterion(output, mask)
+    loss.backward()
+    ref = torch.from_numpy(fx["logits"])
+    err = (out.detach().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-3, err
+    _argmax_check(out.detach().cpu(), ref)
+    assert torch.equal(crit.last_pred.cpu().long(), out.detach().argmax(1).cpu())
+    np.testing.assert_allclose(loss.item(), float(fx["loss"]), rtol=1e-4)
+    grads = dict(model.named_parameters())
+    for n, ref_norm in zip([str(s) for s in fx["grad_names"]], fx["grad_norms"]):
+        got = float(grads[n].grad.double().norm())
+        assert abs(got - ref_norm) <= 2e-3 * ref_norm + 1e-6, (n, got, ref_norm)
+    for k in fx.files:
+        if k.startswith("grad."):
+            g = grads[k[5:]].grad.cpu().numpy()
+            assert np.abs(g - fx[k]).max() <= 2e-3 * np.abs(fx[k]).max() + 1e-6, k
+        if k.startswith("state."):
+            np.testing.assert_allclose(model.state_dict()[k[6:]].cpu().numpy(), fx[k], rtol=1e-3, atol=1e-5)
+    model.eval()
+    with torch.no_grad():
+        ev = model(xA, xB).cpu()
+    ref_ev = torch.from_numpy(fx["logits_eval"])
+    assert (ev - ref_ev).abs().max().item() / ref_ev.abs().max().item() < 1e-3
+
+
+def _oracle_step(seed, base, N, H, W, quant=None):
+    sd = snunet_oracle.to_torch_state(weights.make_state(seed, 2, 3, base))
+    xA, xB, mask = (torch.from_numpy(a) for a in weights.make_batch(seed, N, H, W))
+    loss, logits, grads = snunet_oracle.train_step(sd, xA, xB, mask, quant=quant)
+    return sd, (xA, xB, mask), loss, logits, grads
+
+
+@pytest.mark.parametrize("impl", ["auto", "simt"])
+def test_bf16_close_to_oracle(impl):
+    base, N, H, W, seed = 32, 2, 64, 64, 21
+    sd, (xA, xB, mask), loss_o, logits_o, grads_o = _oracle_step(seed, base, N, H, W)
+    model = _model(weights.make_state(seed, 2, 3, base), base, "bf16")
+    eng = model.engine(xA.to(DEV))
+    if impl == "simt":
+        from kurosiwo_b200.lib import IMPL_SIMT
+        eng.conv_impl = IMPL_SIMT
+    eng.init_training()
+    loss3 = eng.train_step(xA.to(DEV), xB.to(DEV), mask.to(DEV))
+    logits = eng.logits.cpu()
+    rel = float((logits - logits_o).norm() / logits_o.norm())
+    agree = float((logits.argmax(1) == logits_o.argmax(1)).float().mean())
+    print(f"bf16[{impl}] logits rel-L2 {rel:.4f}, argmax agreement {agree:.4f}, loss {loss3[0].item():.5f} vs {float(loss_o):.5f}")
+    assert rel < 5e-2 and agree > 0.97
+    assert abs(loss3[0].item() - float(loss_o)) < 3e-2 * abs(float(loss_o))
+    # gradients of the largest tensors (before the Adam update they sit in the flat gradient buffer)
+    for n in ("conv0_4.conv1.weight", "conv1_3.conv1.weight", "conv3_1.conv1.weight", "conv4_0.conv2.weight", "Up1_3.up.weight", "conv0_0.conv1.weight"):
+        off, shape = eng.params.offsets[n]
+        g = eng.params.grad[off:off + shape.numel()].view(shape).cpu()
+        r = float((g - grads_o[n]).norm() / grads_o[n].norm())
+        print(f"   grad {n}: rel-L2 {r:.4f}")
+        assert r < 0.15, (n, r)
+
+
+def test_fp32_three_adam_steps_match_oracle():
+    base, N, H, W, seed = 8, 2, 32, 32, 31
+    sd = snunet_oracle.to_torch_state(weights.make_state(seed, 2, 3, base))
+    xA, xB, mask = (torch.from_numpy(a) for a in weights.make_batch(seed, N, H, W))
+    model = _model(weights.make_state(seed, 2, 3, base), base, "fp32")
+    eng = model.engine(xA.to(DEV))
+    eng.init_training(lr=1e-3)
+    state = {}
+    for it in range(3):
+        loss_o, _, grads_o = snunet_oracle.train_step(sd, xA, xB, mask)
+        snunet_oracle.adam_step(sd, grads_o, state, lr=1e-3)
+        loss3 = eng.train_step(xA.to(DEV), xB.to(DEV), mask.to(DEV))
+        np.testing.assert_allclose(loss3[0].item(), float(loss_o), rtol=2e-3 * (it + 1))
+    # parameters after 3 steps (Adam normalises the step, so compare in units of lr)
+    for n in ("conv0_0.conv1.weight", "conv2_1.conv2.bias", "conv_final.weight", "ca.fc1.weight"):
+        p = dict(model.named_parameters())[n].detach().cpu()
+        assert (p - sd[n]).abs().max().item() < 2.5e-3, n
+
+
+def test_full_resolution_fp32_vs_oracle_and_graph_replay():
+    """BASELINE shape 224x224 (bs=2 so that the CPU oracle finishes in seconds)."""
+    base, N, H, W, seed = 32, 2, 224, 224, 41
+    sd, (xA, xB, mask), loss_o, logits_o, grads_o = _oracle_step(seed, base, N, H, W)
+    model = _model(weights.make_state(seed, 2, 3, base), base, "fp32")
+    xa, xb, mk = xA.to(DEV), xB.to(DEV), mask.to(DEV)
+    eng = model.engine(xa)
+    eng.init_training(lr=0.0)                        # lr=0: parameters stay put so that replays are comparable
+    loss3 = eng.train_step(xa, xb, mk)
+    lg = eng.logits.cpu()
+    assert (lg - logits_o).abs().max().item() / logits_o.abs().max().item() < 1e-3
+    _argmax_check(lg, logits_o)
+    np.testing.assert_allclose(loss3[0].item(), float(loss_o), rtol=1e-4)
+    g = eng.params.g("conv0_4.conv1.weight").cpu().view_as(grads_o["conv0_4.conv1.weight"])
+    assert (g - grads_o["conv0_4.conv1.weight"]).abs().max().item() <= 2e-3 * grads_o["conv0_4.conv1.weight"].abs().max().item()
+    # CUDA-graph replay of the whole step reproduces the eager launch sequence
+    first = loss3.clone()
+    eng.capture(xa, xb, mk)
+    eng.graph.replay()
+    torch.cuda.synchronize()
+    assert torch.allclose(eng.loss3, first, rtol=1e-5)
+
+
+def test_bf16_full_batch_properties():
+    """bs=8 at 224x224 in perf mode: finite, consistent with the fp32 path, idempotent under lr=0."""
+    base, N, H, W, seed = 32, 8, 224, 224, 51
+    sd_np = weights.make_state(seed, 2, 3, base)
+    xA, xB, mask = (torch.from_numpy(a).to(DEV) for a in weights.make_batch(seed, N, H, W))
+    losses = {}
+    for prec in ("fp32", "bf16"):
+        model = _model(sd_np, base, prec)
+        eng = model.engine(xA)
+        eng.init_training(lr=0.0)
+        l1 = eng.train_step(xA, xB, mask).clone()
+        l2 = eng.train_step(xA, xB, mask).clone()
+        assert torch.isfinite(l1).all()
+        assert torch.allclose(l1, l2, rtol=1e-3), (prec, l1, l2)     # same inputs, lr=0 -> same loss (atomics: not bitwise)
+        losses[prec] = l1[0].item()
+        assert torch.isfinite(eng.params.grad).all()
+        del model, eng
+        torch.cuda.empty_cache()
+    assert abs(losses["bf16"] - losses["fp32"]) < 3e-2 * abs(losses["fp32"]), losses

@@ -1,0 +1,42 @@
+"""-m gpu: tcgen05/TMA conv and wgrad kernels vs the CUDA-core kernels, run in a subprocess with a
+timeout (a mis-programmed mbarrier pipeline hangs instead of failing)."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+TOL = 5e-3   # bf16 outputs: both kernels accumulate in fp32, results differ by bf16 rounding of the sum only
+
+
+@pytest.fixture(scope="module")
+def report():
+    out = ROOT / "gpurun_out" / "tc_probe.json"
+    out.parent.mkdir(exist_ok=True)
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "tc_probe.py"), str(out)], capture_output=True, text=True, timeout=600)
+    (ROOT / "gpurun_out" / "tc_probe.log").write_text(r.stdout + "\n--- stderr ---\n" + r.stderr)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return json.loads(out.read_text())
+
+
+def test_conv_tc_default_config(report):
+    bad = {k: v["bo0_mt1"] for k, v in report["conv"].items() if not (isinstance(v["bo0_mt1"], float) and v["bo0_mt1"] < TOL)}
+    assert not bad, bad
+
+
+def test_conv_tc_multi_window(report):
+    bad = {}
+    for k, v in report["conv"].items():
+        for mt in (2, 4):
+            e = v[f"bo0_mt{mt}"]
+            if not (isinstance(e, float) and e < TOL):
+                bad[f"{k}.mt{mt}"] = e
+    assert not bad, bad
+
+
+def test_wgrad_tc(report):
+    bad = {k: v for k, v in report["wgrad"].items() if "error" in v or v["assign"] > TOL or v["accumulate"] > TOL}
+    assert not bad, bad
