@@ -217,6 +217,8 @@ def run_ours(args):
     xa, xb, mk = b0[6].to(dev), b0[2].to(dev), b0[3].to(dev)     # pre_event_1, post_event, mask
     eng = stepper._engine(xa)
     ops = eng.ops
+    if args.tc_mt:
+        ops.set_option("tc_mt", args.tc_mt)
     use_graph = (world == 1) and not args.no_graph
     for _ in range(2):
         eng.train_step(xa, xb, mk)
@@ -319,6 +321,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--tc-mt", type=int, default=0, help="output windows per CTA of the tcgen05 conv (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -94,6 +94,14 @@ int ks_conv2d_wgrad(int dtype, int N, int H, int W, int ksize,
                     const ks_view_t *dys, int n_dy,
                     float *dw, int accumulate, int impl, void *stream);
 
+/* Stem conv (models/snunet.py:75, conv0_0.conv1: Cin = 2 or 3, Cout = 32): reads the NCHW fp32 network
+ * input and the OIHW fp32 master weight directly; NHWC output in `dtype`; optional BN statistics. */
+int ks_stem_conv3x3(int dtype, int N, int Cin, int H, int W, const float *x_nchw, const float *w_oihw,
+                    const float *bias, const ks_view_t *dst, double *stats, void *stream);
+/* dw_oihw[co][ci][3][3] (+)= sum_px dy[px][co] * x[px+tap][ci]  (fp32, OIHW like the parameter). */
+int ks_stem_wgrad3x3(int dtype, int N, int Cin, int H, int W, const float *x_nchw, const ks_view_t *dy,
+                     float *dw_oihw, int accumulate, void *stream);
+
 /* ---- BatchNorm (training mode) + ReLU + residual + pool ----------------- */
 /* sums[0][c] += sum x, sums[1][c] += sum x^2 (fp64, caller zeroes). snunet.py:23,27 */
 int ks_bn_stats(int dtype, int N, int H, int W, const ks_view_t *x, double *sums, void *stream);

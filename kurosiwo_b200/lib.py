@@ -88,7 +88,7 @@ def load() -> C.CDLL:
 
 
 EXPORTED_SYMBOLS = [
-    "ks_version", "ks_error_string", "ks_set_option", "ks_permute_cast", "ks_conv2d", "ks_conv2d_wgrad",
+    "ks_version", "ks_error_string", "ks_set_option", "ks_permute_cast", "ks_conv2d", "ks_conv2d_wgrad", "ks_stem_conv3x3", "ks_stem_wgrad3x3",
     "ks_bn_stats", "ks_bn_finalize", "ks_bn_act", "ks_bn_bwd_reduce", "ks_bn_bwd_apply", "ks_maxpool2x2_bwd",
     "ks_channel_sum", "ks_ecam_pool", "ks_ecam_gates", "ks_ecam_final", "ks_ecam_bwd_reduce", "ks_ecam_gates_bwd",
     "ks_ecam_bwd_apply", "ks_ce_dice_workspace_bytes", "ks_ce_dice_fwd_bwd", "ks_adam_step",
@@ -157,6 +157,18 @@ class CudaOps:
                                       _views(xs), C.c_int(len(xs)), _views(dys), C.c_int(len(dys)), _p(dw),
                                       C.c_int(int(accumulate)), C.c_int(impl), self._stream())
         self._check(rc, "ks_conv2d_wgrad")
+
+    def stem_conv3x3(self, x_nchw: torch.Tensor, w_oihw, bias, dst: View, stats=None):
+        N, Cin, H, W = x_nchw.shape
+        rc = self.lib.ks_stem_conv3x3(dtype_code(dst.dtype), C.c_int(N), C.c_int(Cin), C.c_int(H), C.c_int(W), _p(x_nchw), _p(w_oihw),
+                                      _p(bias), _vp(dst), _p(stats), self._stream())
+        self._check(rc, "ks_stem_conv3x3")
+
+    def stem_wgrad3x3(self, x_nchw: torch.Tensor, dy: View, dw_oihw, accumulate=False):
+        N, Cin, H, W = x_nchw.shape
+        rc = self.lib.ks_stem_wgrad3x3(dtype_code(dy.dtype), C.c_int(N), C.c_int(Cin), C.c_int(H), C.c_int(W), _p(x_nchw), _vp(dy),
+                                       _p(dw_oihw), C.c_int(int(accumulate)), self._stream())
+        self._check(rc, "ks_stem_wgrad3x3")
 
     # -- batch norm / pooling ----------------------------------------------------------------
     def bn_stats(self, x: View, sums):

@@ -100,6 +100,9 @@ class SNUNetEngine:
         self.f = [base * (1 << l) for l in range(5)]
         self.hid, self.hid1 = (4 * base) // 16, base // 4
         self.conv_impl = conv_impl
+        # dedicated HBM-bound stem kernels (NCHW fp32 input read directly) when conv0_0 is Cin<=4 -> 32
+        self.use_stem = (base == 32 and in_ch <= 4)
+        self._x_in = [None, None]
         self.params = FlatParams(module)
         self._alloc()
         self._build_schedule()
@@ -213,6 +216,8 @@ class SNUNetEngine:
             l = int(bn_[4])
             cin, fl = self.block_cin[bn_], self.f[l]
             for tag, (co, ci) in (("conv1", (fl, cin)), ("conv2", (fl, fl))):
+                if self.use_stem and bn_ == "conv0_0" and tag == "conv1":
+                    continue
                 w = P.p(f"{bn_}.{tag}.weight")  # OIHW
                 # fwd  [t][o][i] = w[o][i][t]
                 ops.permute_cast(w, self.wp[f"{bn_}.{tag}.fwd"], (9, co, ci), (1, ci * 9, 9))
@@ -231,6 +236,8 @@ class SNUNetEngine:
             l = int(bn_[4])
             cin, fl = self.block_cin[bn_], self.f[l]
             for tag, (co, ci) in (("conv1", (fl, cin)), ("conv2", (fl, fl))):
+                if self.use_stem and bn_ == "conv0_0" and tag == "conv1":
+                    continue
                 # grad[o][i][t] = gp[t][o][i]
                 ops.permute_cast(self.gp[f"{bn_}.{tag}"], P.g(f"{bn_}.{tag}.weight"), (co, ci, 9), (ci, 1, co * ci))
         for (l, j), nm in self.up_names.items():
@@ -254,7 +261,10 @@ class SNUNetEngine:
         for idx, (tag, bnt, srcs, y, sc, sh, mu, rs) in enumerate((("conv1", "bn1", e.srcs, e.y1, sc1, sh1, mu1, rs1),
                                                                    ("conv2", "bn2", [e.h], e.y2, sc2, sh2, mu2, rs2))):
             stats = e.stats[idx] if training else None
-            ops.conv2d(N, h_, w_, 3, srcs, self.wp[f"{nm}.{tag}.fwd"], P.p(f"{nm}.{tag}.bias"), [y], None, stats, self.conv_impl)
+            if idx == 0 and self.use_stem and e.key[0] == "enc" and e.level == 0:
+                ops.stem_conv3x3(self._x_in[e.key[2]], P.p(f"{nm}.conv1.weight"), P.p(f"{nm}.conv1.bias"), y, stats)
+            else:
+                ops.conv2d(N, h_, w_, 3, srcs, self.wp[f"{nm}.{tag}.fwd"], P.p(f"{nm}.{tag}.bias"), [y], None, stats, self.conv_impl)
             rm, rv = self._buf_(f"{nm}.{bnt}.running_mean"), self._buf_(f"{nm}.{bnt}.running_var")
             if training:
                 ops.bn_finalize(fl, count, stats, P.p(f"{nm}.{bnt}.weight"), P.p(f"{nm}.{bnt}.bias"), BN_EPS, BN_MOMENTUM,
@@ -286,7 +296,9 @@ class SNUNetEngine:
             x = x.contiguous()
             if x.dtype != torch.float32:
                 x = x.float()
-            ops.permute_cast(x, self.xin[br].base, (N, H, W, Cin), (Cin * H * W, W, 1, H * W))
+            self._x_in[br] = x
+            if not self.use_stem:
+                ops.permute_cast(x, self.xin[br].base, (N, H, W, Cin), (Cin * H * W, W, 1, H * W))
         self._pack_weights()
         if training:
             ops.zero_(self.stats_all)
@@ -324,7 +336,10 @@ class SNUNetEngine:
         ops.bn_bwd_apply(dh, e.h, e.y1, mu1, rs1, P.p(f"{nm}.bn1.weight"), e.bstats[0], count, e.dout, e.out, dy,
                          P.g(f"{nm}.bn1.weight"), P.g(f"{nm}.bn1.bias"), acc)
         ops.channel_sum(dy, P.g(f"{nm}.conv1.bias"), acc)
-        ops.conv2d_wgrad(N, h_, w_, 3, e.srcs, [dy], self.gp[f"{nm}.conv1"], acc, self.conv_impl)
+        if self.use_stem and e.key[0] == "enc" and e.level == 0:
+            ops.stem_wgrad3x3(self._x_in[e.key[2]], dy, P.g(f"{nm}.conv1.weight"), acc)
+        else:
+            ops.conv2d_wgrad(N, h_, w_, 3, e.srcs, [dy], self.gp[f"{nm}.conv1"], acc, self.conv_impl)
         if gdsts:
             ops.conv2d(N, h_, w_, 3, [dy], self.wp[f"{nm}.conv1.dgrad"], None, gdsts, gacc, None, self.conv_impl)
 

@@ -73,6 +73,21 @@ class ShadowOps:
         out = dw.reshape(-1)[: g.numel()]
         out.copy_(g + out if accumulate else g)
 
+    def stem_conv3x3(self, x_nchw, w_oihw, bias, dst, stats=None):
+        t = _t(dst)
+        q = (lambda a: a.to(t.dtype).float())
+        y = F.conv2d(q(x_nchw.float()), q(w_oihw.view(dst.C, x_nchw.shape[1], 3, 3)), None if bias is None else bias.float(), padding=1)
+        t.copy_(y.permute(0, 2, 3, 1).to(t.dtype))
+        if stats is not None:
+            self.bn_stats(dst, stats)
+
+    def stem_wgrad3x3(self, x_nchw, dy, dw_oihw, accumulate=False):
+        t = _t(dy)
+        x = x_nchw.float().to(t.dtype).float()
+        g = torch.nn.grad.conv2d_weight(x, (dy.C, x.shape[1], 3, 3), t.float().permute(0, 3, 1, 2), padding=1).reshape(-1)
+        out = dw_oihw.reshape(-1)[: g.numel()]
+        out.copy_(g + out if accumulate else g)
+
     # -- batch norm / pooling ----------------------------------------------------------------
     def bn_stats(self, x, sums):
         t = _t(x).double().reshape(-1, x.C)

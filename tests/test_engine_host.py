@@ -29,7 +29,7 @@ def test_cpu_without_backend_fails_loudly():
         m(torch.zeros(2, 2, 32, 32), torch.zeros(2, 2, 32, 32))
 
 
-@pytest.mark.parametrize("base,N,H,W,seed", [(8, 2, 32, 32, 11), (8, 3, 48, 32, 5)])
+@pytest.mark.parametrize("base,N,H,W,seed", [(8, 2, 32, 32, 11), (8, 3, 48, 32, 5), (32, 2, 32, 32, 12)])
 def test_schedule_matches_oracle(base, N, H, W, seed):
     sd_np = weights.make_state(seed, 2, 3, base)
     xA, xB, mask = (torch.from_numpy(a) for a in weights.make_batch(seed, N, H, W))

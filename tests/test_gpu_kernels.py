@@ -78,6 +78,29 @@ def test_wgrad_simt(ops, sh, dtype, ks):
     assert rel_l2(dw, cdw) < 1e-4
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cin,H,W", [(2, 24, 40), (3, 17, 33)])
+def test_stem_kernels(ops, sh, dtype, cin, H, W):
+    g = _gen(8)
+    N = 3
+    x = torch.randn(N, cin, H, W, generator=g)
+    w = torch.randn(32 * cin * 9, generator=g) * 0.3
+    b = torch.randn(32, generator=g) * 0.1
+    dst, fd = rand_view(N, H, W, 32, dtype, DEV, 96, 32, gen=g)
+    cdst = mirror(dst)
+    stats, cstats = torch.zeros(64, dtype=torch.float64, device=DEV), torch.zeros(64, dtype=torch.float64)
+    ops.stem_conv3x3(x.to(DEV), w.to(DEV), b.to(DEV), dst, stats)
+    sh.stem_conv3x3(x, w, b, cdst, cstats)
+    assert rel_l2(fd.base.float(), cdst.base.float()) < _tol(dtype)
+    assert rel_l2(stats, cstats) < (1e-5 if dtype == torch.float32 else 1e-2)
+    dy, _ = rand_view(N, H, W, 32, dtype, DEV, gen=g)
+    dw, cdw = torch.ones(32 * cin * 9, device=DEV), torch.ones(32 * cin * 9)
+    for acc in (True, False):
+        ops.stem_wgrad3x3(x.to(DEV), dy, dw, acc)
+        sh.stem_wgrad3x3(x, mirror(dy), cdw, acc)
+        assert rel_l2(dw, cdw) < 1e-4
+
+
 def test_permute_cast(ops, sh):
     g = _gen(3)
     w = torch.randn(6 * 5 * 9, generator=g)
