@@ -37,7 +37,7 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-Options g_opt = {0, 0, 0, 0, 0, 0};
+Options g_opt = {0, 0, 0, 0, 0, 0, 0, 0};
 
 struct alignas(64) ConvTcParams {
   CUtensorMap src[KS_MAX_VIEWS];
@@ -49,6 +49,10 @@ struct alignas(64) ConvTcParams {
   int N, H, W, tiles_w, tiles_h, total_tiles;
   int BN, MT, SA, SB, TH, bo_mode;
   uint32_t a_tile_bytes, b_stage_bytes, tmem_cols, idesc;
+  // v2 (persistent) fields
+  int n_super, resident, n_acc, n_wtiles;
+  double *stats;
+  int Cout;
 };
 
 using namespace tc;
@@ -208,6 +212,237 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// v2: persistent CTAs, optional smem-RESIDENT weights, double-buffered TMEM accumulators (the epilogue
+// of super-tile i overlaps the MMAs of super-tile i+1) and BatchNorm statistics fused into the epilogue.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_reduce_scatter16(float (&v)[16], int lane) {
+  // after the call v[0] holds the 32-lane sum of channel ((lane>>1)&15) (both lanes of a pair hold it)
+  bool hi = lane & 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float send = hi ? v[i] : v[i + 8], keep = hi ? v[i + 8] : v[i]; v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+  hi = lane & 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float send = hi ? v[i] : v[i + 4], keep = hi ? v[i + 4] : v[i]; v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
+  hi = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) { const float send = hi ? v[i] : v[i + 2], keep = hi ? v[i + 2] : v[i]; v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4); }
+  hi = lane & 2;
+  { const float send = hi ? v[0] : v[1], keep = hi ? v[1] : v[0]; v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2); }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+template <int BK, int KS>
+__global__ void __launch_bounds__(192, 1) conv_tc2_kernel(const __grid_constant__ ConvTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int TW = (KS == 3) ? 14 : 16;
+  constexpr int PADK = KS / 2;
+  constexpr int BOX_ROWS = (KS == 3) ? 10 : 8;
+  constexpr uint32_t ROW_BYTES = BK * 2;
+  constexpr uint32_t A_BOX_BYTES = BOX_ROWS * 16 * ROW_BYTES;
+  constexpr uint32_t LAYOUT = (BK == 64) ? LAYOUT_SW128 : LAYOUT_SW64;
+  constexpr uint32_t SBO = 8 * ROW_BYTES;
+  constexpr int TAPS = KS * KS;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int SA = p.SA, SB = p.SB, MT = p.MT, BN = p.BN, NACC = p.n_acc;
+  const bool RES = p.resident != 0;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *sm = smem_raw + (base - raw);
+  const uint32_t a_base = base;
+  const uint32_t b_base = a_base + (uint32_t)SA * MT * p.a_tile_bytes;
+  const uint32_t n_bslots = RES ? (uint32_t)p.n_wtiles : (uint32_t)SB;
+  const uint32_t bar_base = b_base + n_bslots * p.b_stage_bytes;
+  auto a_full = [&](int i) { return bar_base + 8u * i; };
+  auto a_empty = [&](int i) { return bar_base + 8u * (SA + i); };
+  auto b_full = [&](int i) { return bar_base + 8u * (2 * SA + i); };
+  auto b_empty = [&](int i) { return bar_base + 8u * (2 * SA + SB + i); };
+  const uint32_t misc = bar_base + 8u * (2 * SA + 2 * SB);
+  auto acc_full = [&](int i) { return misc + 8u * i; };
+  auto acc_empty = [&](int i) { return misc + 8u * (2 + i); };
+  const uint32_t w_full = misc + 8u * 4;
+  const uint32_t tmem_slot = misc + 8u * 5;
+  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(sm + (tmem_slot - base));
+  float *sstat = reinterpret_cast<float *>(sm + (tmem_slot + 8u - base));   // [2][BN] when stats are requested
+
+  const int n0 = blockIdx.y * BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.n_src; ++s) prefetch_tmap(&p.src[s]);
+    prefetch_tmap(&p.wmap);
+    for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 4); }
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  if (p.stats) for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) sstat[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      if (RES) {
+        mbar_expect_tx(w_full, (uint32_t)p.n_wtiles * p.b_stage_bytes);
+        int idx = 0;
+        for (int s = 0; s < p.n_src; ++s) {
+          const int C = p.cstart[s + 1] - p.cstart[s];
+          for (int c0 = 0; c0 < C; c0 += BK)
+            for (int tap = 0; tap < TAPS; ++tap, ++idx)
+              tma_load_3d(b_base + (uint32_t)idx * p.b_stage_bytes, &p.wmap, p.cstart[s] + c0, n0, tap, w_full);
+        }
+      }
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+        const int t0 = st * MT;
+        const int nvalid = min(MT, p.total_tiles - t0);
+        for (int s = 0; s < p.n_src; ++s) {
+          const int C = p.cstart[s + 1] - p.cstart[s];
+          for (int c0 = 0; c0 < C; c0 += BK) {
+            mbar_wait(a_empty(sa), pa ^ 1);
+            mbar_expect_tx(a_full(sa), (uint32_t)nvalid * A_BOX_BYTES);
+            for (int mt = 0; mt < nvalid; ++mt) {
+              const int t = t0 + mt;
+              const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, n = t / (p.tiles_w * p.tiles_h);
+              tma_load_4d(a_base + (uint32_t)(sa * MT + mt) * p.a_tile_bytes, &p.src[s], c0, tw * TW - PADK, th * p.TH - PADK, n, a_full(sa));
+            }
+            if (++sa == SA) { sa = 0; pa ^= 1; }
+            if (!RES) {
+              for (int tap = 0; tap < TAPS; ++tap) {
+                mbar_wait(b_empty(sb), pb ^ 1);
+                mbar_expect_tx(b_full(sb), p.b_stage_bytes);
+                tma_load_3d(b_base + (uint32_t)sb * p.b_stage_bytes, &p.wmap, p.cstart[s] + c0, n0, tap, b_full(sb));
+                if (++sb == SB) { sb = 0; pb ^= 1; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      if (RES) mbar_wait(w_full, 0);
+      int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
+      for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+        const int nvalid = min(MT, p.total_tiles - st * MT);
+        mbar_wait(acc_empty(as), pacc ^ 1);
+        tc_fence_after();
+        const uint32_t acc_col = tmem_base + (uint32_t)(as * MT * BN);
+        bool first = true;
+        int widx = 0;
+        for (int s = 0; s < p.n_src; ++s) {
+          const int C = p.cstart[s + 1] - p.cstart[s];
+          for (int c0 = 0; c0 < C; c0 += BK) {
+            mbar_wait(a_full(sa), pa);
+            tc_fence_after();
+            for (int tap = 0; tap < TAPS; ++tap, ++widx) {
+              uint32_t b_addr;
+              if (RES) b_addr = b_base + (uint32_t)widx * p.b_stage_bytes;
+              else { mbar_wait(b_full(sb), pb); tc_fence_after(); b_addr = b_base + (uint32_t)sb * p.b_stage_bytes; }
+              const uint32_t row_off = (KS == 3) ? (uint32_t)((tap / 3) * 16 + (tap % 3)) : 0u;
+              for (int mt = 0; mt < nvalid; ++mt) {
+                const uint32_t a_addr = a_base + (uint32_t)(sa * MT + mt) * p.a_tile_bytes + row_off * ROW_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                  const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, SBO, LAYOUT, 0);
+                  const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, SBO, LAYOUT, 0);
+                  umma_bf16(acc_col + (uint32_t)(mt * BN), ad, bd, p.idesc, (first && k == 0) ? 0u : 1u);
+                }
+              }
+              first = false;
+              if (!RES) { tc_commit(b_empty(sb)); if (++sb == SB) { sb = 0; pb ^= 1; } }
+            }
+            tc_commit(a_empty(sa));
+            if (++sa == SA) { sa = 0; pa ^= 1; }
+          }
+        }
+        tc_commit(acc_full(as));
+        if (++as == NACC) { as = 0; pacc ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane group = warp % 4 =====
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    const int ty = row >> 4, tx = row & 15;
+    int as = 0, pacc = 0;
+    for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+      const int t0 = st * MT;
+      const int nvalid = min(MT, p.total_tiles - t0);
+      mbar_wait(acc_full(as), pacc);
+      tc_fence_after();
+      for (int mt = 0; mt < nvalid; ++mt) {
+        const int t = t0 + mt;
+        const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, n = t / (p.tiles_w * p.tiles_h);
+        const int h = th * p.TH + ty, w = tw * TW + tx;
+        const bool ok = (tx < TW) && (ty < p.TH) && (h < p.H) && (w < p.W);
+        for (int cc = 0; cc < BN; cc += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * MT * BN + mt * BN + cc), r);
+          tmem_ld_wait();
+          float v[16];
+          const int co = n0 + cc;
+          if (ok) {
+            int d = 0;
+#pragma unroll
+            for (int i = 1; i < KS_MAX_VIEWS; ++i) if (i < p.dsts.n && co >= p.dsts.cstart[i]) d = i;
+            const View &dv = p.dsts.v[d];
+            __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(dv.ptr) +
+                                ((long long)n * dv.sn + (long long)h * dv.sh + (long long)w * dv.sw + (co - p.dsts.cstart[d]));
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + co + i) : 0.f);
+            if ((p.acc_mask >> d) & 1) {
+              float o[8];
+              ld8(op, o);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += o[i];
+              ld8(op + 8, o);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[8 + i] += o[i];
+            }
+            float a[8], b[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a[i] = v[i]; b[i] = v[8 + i]; }
+            st8(op, a);
+            st8(op + 8, b);
+          }
+          if (p.stats) {
+            float s1[16], s2[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { const float q = ok ? round_as<__nv_bfloat16>(v[i]) : 0.f; s1[i] = q; s2[i] = q * q; }
+            warp_reduce_scatter16(s1, lane);
+            warp_reduce_scatter16(s2, lane);
+            if ((lane & 1) == 0) {
+              const int c = cc + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+              atomicAdd(&sstat[c], s1[0]);
+              atomicAdd(&sstat[BN + c], s2[0]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(as));
+      if (++as == NACC) { as = 0; pacc ^= 1; }
+    }
+  }
+  __syncthreads();
+  if (p.stats) {
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
+      const int r = i / BN, c = i % BN;
+      atomicAdd(p.stats + (size_t)r * p.Cout + n0 + c, (double)sstat[i]);
+    }
+  }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
+}
+
 static bool tma_view_ok(const View &v) {
   return (((uintptr_t)v.ptr) % 16 == 0) && ((v.sn * 2) % 16 == 0) && ((v.sh * 2) % 16 == 0) && ((v.sw * 2) % 16 == 0) &&
          v.sw > 0 && v.sh > 0 && v.sn > 0;
@@ -239,6 +474,18 @@ static int launch_conv_tc(const ConvTcParams &p, dim3 grid, size_t smem, cudaStr
 
 extern "C" int ks_bn_stats(int dtype, int N, int H, int W, const ks_view_t *x, double *sums, void *stream);
 
+template <int BK, int KS>
+static int launch_conv_tc2(const ConvTcParams &p, dim3 grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BK, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  conv_tc2_kernel<BK, KS><<<grid, 192, smem, st>>>(p);
+  return (int)cudaGetLastError();
+}
+
 int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *weight, const float *bias,
               const ViewList &dsts, int acc_mask, double *stats, cudaStream_t st) {
   if (g_opt.tc_disable) return KS_EUNSUPPORTED;
@@ -255,17 +502,17 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
   }
   if (((uintptr_t)weight) % 16) return KS_EUNSUPPORTED;
   if (stats && dsts.n != 1) return KS_EUNSUPPORTED;
+  if ((Cin * 2) % 16) return KS_EUNSUPPORTED;
   const int BK = all64 ? 64 : 32;
+  const int taps = ksize * ksize;
   int nt = 1;
   for (;; ++nt) {
     if (nt > 64) return KS_EUNSUPPORTED;
     if (Cout % nt == 0 && (Cout / nt) <= 256 && (Cout / nt) % 16 == 0) break;
   }
+  const bool v1 = g_opt.v1 != 0;
   ConvTcParams p;
   p.BN = Cout / nt;
-  int MT = g_opt.mt > 0 ? g_opt.mt : 1;
-  while (MT > 1 && MT * p.BN > 512) MT >>= 1;
-  p.MT = MT;
   p.TH = (ksize == 3) ? ((H % 8 == 0) ? 8 : ((H % 7 == 0) ? 7 : 8)) : 8;
   const int TW = (ksize == 3) ? 14 : 16;
   p.tiles_w = (W + TW - 1) / TW; p.tiles_h = (H + p.TH - 1) / p.TH;
@@ -276,21 +523,46 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
   p.n_src = srcs.n; p.acc_mask = acc_mask; p.bias = bias; p.dsts = dsts;
   for (int i = 0; i <= KS_MAX_VIEWS; ++i) p.cstart[i] = srcs.cstart[i];
   p.bo_mode = g_opt.bo_mode;
+  p.Cout = Cout;
+  p.stats = v1 ? nullptr : stats;
   const uint32_t row_bytes = BK * 2;
   const uint32_t a_rows = (ksize == 3) ? 162 : 128;
   p.a_tile_bytes = ((a_rows * row_bytes + 1023) / 1024) * 1024;
   p.b_stage_bytes = (uint32_t)p.BN * row_bytes;
-  uint32_t cols = 32; while (cols < (uint32_t)(MT * p.BN)) cols <<= 1;
-  p.tmem_cols = cols;
   p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
-  // pipeline depth under the 227 KB budget
-  int SA = g_opt.sa > 0 ? g_opt.sa : 3, SB = g_opt.sb > 0 ? g_opt.sb : 4;
-  auto bytes = [&](int sa, int sb) { return (size_t)sa * MT * p.a_tile_bytes + (size_t)sb * p.b_stage_bytes + 1024 + 256; };
-  const size_t budget = 220 * 1024;
-  while (bytes(SA, SB) > budget && SB > 2) --SB;
-  while (bytes(SA, SB) > budget && SA > 2) --SA;
-  if (bytes(SA, SB) > budget) return KS_EUNSUPPORTED;
-  p.SA = SA; p.SB = SB;
+  p.n_wtiles = (Cin / BK) * taps;
+  const size_t budget = 222 * 1024;
+  const size_t fixed = 1024 + 512 + (stats ? 2 * p.BN * 4 : 0);
+  // ---- resident weights? (all [BN x BK] tiles of this N tile stay in smem for the CTA's lifetime)
+  const size_t w_bytes = (size_t)p.n_wtiles * p.b_stage_bytes;
+  int MT, SA, SB;
+  p.resident = 0;
+  if (!v1 && !g_opt.no_resident && w_bytes + 2 * p.a_tile_bytes + fixed <= budget) {
+    p.resident = 1;
+    MT = g_opt.mt > 0 ? g_opt.mt : 1;
+    while (MT > 1 && (2 * MT * p.BN > 512 || w_bytes + 2 * (size_t)MT * p.a_tile_bytes + fixed > budget)) MT >>= 1;
+    SA = g_opt.sa > 0 ? g_opt.sa : 4;
+    while (SA > 2 && w_bytes + (size_t)SA * MT * p.a_tile_bytes + fixed > budget) --SA;
+    SB = 1;
+  } else {
+    // streamed weights: amortise every weight tile over MT output windows
+    MT = g_opt.mt > 0 ? g_opt.mt : (v1 ? 1 : 4);
+    while (MT > 1 && (v1 ? MT * p.BN > 512 : 2 * MT * p.BN > 512)) MT >>= 1;
+    SA = g_opt.sa > 0 ? g_opt.sa : 3; SB = g_opt.sb > 0 ? g_opt.sb : 4;
+    auto bytes = [&](int mt, int sa, int sb) { return (size_t)sa * mt * p.a_tile_bytes + (size_t)sb * p.b_stage_bytes + fixed; };
+    while (bytes(MT, SA, SB) > budget && SA > 2) --SA;
+    while (bytes(MT, SA, SB) > budget && SB > 2) --SB;
+    while (bytes(MT, SA, SB) > budget && MT > 1) MT >>= 1;
+    if (bytes(MT, SA, SB) > budget) return KS_EUNSUPPORTED;
+  }
+  p.MT = MT; p.SA = SA; p.SB = SB;
+  p.n_super = (p.total_tiles + MT - 1) / MT;
+  p.n_acc = (2 * MT * p.BN <= 512) ? 2 : 1;
+  if (v1) p.n_acc = 1;
+  uint32_t cols = 32; while (cols < (uint32_t)(p.n_acc * MT * p.BN)) cols <<= 1;
+  if (cols > 512) return KS_EUNSUPPORTED;
+  p.tmem_cols = cols;
+  const size_t smem = (size_t)SA * MT * p.a_tile_bytes + (p.resident ? w_bytes : (size_t)SB * p.b_stage_bytes) + fixed;
   const CUtensorMapSwizzle sw = (BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   for (int s = 0; s < srcs.n; ++s) {
     int rc = encode_act_map(&p.src[s], srcs.v[s], N, H, W, BK, 16, (ksize == 3) ? 10 : 8, sw);
@@ -299,29 +571,37 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
   {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return KS_EDRIVER;
-    const int taps = ksize * ksize;
     cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
     cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * Cout * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)p.BN, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    if ((Cin * 2) % 16) return KS_EUNSUPPORTED;
     CUresult r = enc(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)weight, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return KS_EDRIVER;
   }
-  dim3 grid((unsigned)((p.total_tiles + MT - 1) / MT), (unsigned)nt);
-  const size_t smem = bytes(SA, SB);
   int rc;
-  if (BK == 64 && ksize == 3) rc = launch_conv_tc<64, 3>(p, grid, smem, st);
-  else if (BK == 64 && ksize == 1) rc = launch_conv_tc<64, 1>(p, grid, smem, st);
-  else if (BK == 32 && ksize == 3) rc = launch_conv_tc<32, 3>(p, grid, smem, st);
-  else rc = launch_conv_tc<32, 1>(p, grid, smem, st);
-  if (rc) return rc;
-  if (stats) {
-    ks_view_t dv; dv.ptr = dsts.v[0].ptr; dv.sn = dsts.v[0].sn; dv.sh = dsts.v[0].sh; dv.sw = dsts.v[0].sw; dv.C = dsts.v[0].C; dv._pad = 0;
-    return ks_bn_stats(KS_BF16, N, H, W, &dv, stats, (void *)st);
+  if (v1) {
+    dim3 grid((unsigned)p.n_super, (unsigned)nt);
+    if (BK == 64 && ksize == 3) rc = launch_conv_tc<64, 3>(p, grid, smem, st);
+    else if (BK == 64 && ksize == 1) rc = launch_conv_tc<64, 1>(p, grid, smem, st);
+    else if (BK == 32 && ksize == 3) rc = launch_conv_tc<32, 3>(p, grid, smem, st);
+    else rc = launch_conv_tc<32, 1>(p, grid, smem, st);
+    if (rc) return rc;
+    if (stats) {
+      ks_view_t dv; dv.ptr = dsts.v[0].ptr; dv.sn = dsts.v[0].sn; dv.sh = dsts.v[0].sh; dv.sw = dsts.v[0].sw; dv.C = dsts.v[0].C; dv._pad = 0;
+      return ks_bn_stats(KS_BF16, N, H, W, &dv, stats, (void *)st);
+    }
+    return KS_OK;
   }
-  return KS_OK;
+  // persistent grid: CTAs per SM limited by shared memory; all N tiles of a super-tile run concurrently
+  int per_sm = (int)((227 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
+  int gx = (kNumSMs * per_sm) / nt; if (gx < 1) gx = 1; if (gx > p.n_super) gx = p.n_super;
+  dim3 grid((unsigned)gx, (unsigned)nt);
+  if (BK == 64 && ksize == 3) rc = launch_conv_tc2<64, 3>(p, grid, smem, st);
+  else if (BK == 64 && ksize == 1) rc = launch_conv_tc2<64, 1>(p, grid, smem, st);
+  else if (BK == 32 && ksize == 3) rc = launch_conv_tc2<32, 3>(p, grid, smem, st);
+  else rc = launch_conv_tc2<32, 1>(p, grid, smem, st);
+  return rc;
 }
 
 }  // namespace ks
@@ -335,6 +615,8 @@ extern "C" int ks_set_option(const char *name, int value) {
   else if (eq("wgrad_tc_disable")) ks::g_opt.wgrad_tc_disable = value;
   else if (eq("tc_sa")) ks::g_opt.sa = value;
   else if (eq("tc_sb")) ks::g_opt.sb = value;
+  else if (eq("tc_v1")) ks::g_opt.v1 = value;
+  else if (eq("tc_no_resident")) ks::g_opt.no_resident = value;
   else return KS_EINVAL;
   return KS_OK;
 }
