@@ -219,6 +219,8 @@ def run_ours(args):
     ops = eng.ops
     if args.tc_mt:
         ops.set_option("tc_mt", args.tc_mt)
+    if args.tc_v1:
+        ops.set_option("tc_v1", 1)
     use_graph = (world == 1) and not args.no_graph
     for _ in range(2):
         eng.train_step(xa, xb, mk)
@@ -321,6 +323,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--tc-v1", type=int, default=0, help="1 = non-persistent v1 conv kernel (A/B comparisons)")
     ap.add_argument("--tc-mt", type=int, default=0, help="output windows per CTA of the tcgen05 conv (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -119,20 +119,20 @@ int ks_bn_act(int dtype, int N, int H, int W, const ks_view_t *y,
               const float *scale, const float *shift, const ks_view_t *res,
               int relu, const ks_view_t *out, const ks_view_t *pool, void *stream);
 
-/* g = dout * (out>0);  sums[0][c] += sum g,  sums[1][c] += sum g*xhat. */
+/* BN backward pass 1: g = dout * mask; sums[0][c] += sum g, sums[1][c] += sum g*xhat.
+ * out != NULL: mask = (out > 0) and the masked gradient g is written back over `dout` (pass 2 and the
+ *              identity path re-use it); out == NULL: mask = (y*scale+shift > 0), nothing is written. */
 int ks_bn_bwd_reduce(int dtype, int N, int H, int W, const ks_view_t *dout,
-                     const ks_view_t *out, const ks_view_t *y,
+                     const ks_view_t *out, const ks_view_t *y, const float *scale, const float *shift,
                      const float *mean, const float *rstd, double *sums, void *stream);
 
-/* dy = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M) (+ add_dout*(add_out>0)).
- * dgamma = sum_gx, dbeta = sum_g written as fp32 (+= if accumulate). */
-int ks_bn_bwd_apply(int dtype, int N, int H, int W, const ks_view_t *dout,
-                    const ks_view_t *out, const ks_view_t *y,
-                    const float *mean, const float *rstd, const float *gamma,
-                    const double *sums, double count,
-                    const ks_view_t *add_dout, const ks_view_t *add_out,
-                    const ks_view_t *dy, float *dgamma, float *dbeta,
-                    int accumulate_param_grads, void *stream);
+/* BN backward pass 2: dy = gamma*rstd*(g' - sum_g/M - xhat*sum_gx/M) (+ add), with g' = g if `premasked`
+ * else g*(y*scale+shift > 0).  dgamma = sum_gx, dbeta = sum_g, dsum_out = sum_g (the gradient of the
+ * preceding conv bias along the identity path), all fp32 (+= if accumulate_param_grads). */
+int ks_bn_bwd_apply(int dtype, int N, int H, int W, const ks_view_t *g, int premasked, const ks_view_t *y,
+                    const float *scale, const float *shift, const float *mean, const float *rstd, const float *gamma,
+                    const double *sums, double count, const ks_view_t *add, const ks_view_t *dy,
+                    float *dgamma, float *dbeta, float *dsum_out, int accumulate_param_grads, void *stream);
 
 /* dx[n,2h+i,2w+j,c] (+)= dpool[n,h,w,c] at the first max of each 2x2 window
  * (H,W are the POOLED dims). aten max_pool2d_with_indices_backward. */

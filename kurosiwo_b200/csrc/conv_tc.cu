@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc2_kernel(const __grid_constant_
   constexpr uint32_t SBO = 8 * ROW_BYTES;
   constexpr int TAPS = KS * KS;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const int SA = p.SA, SB = p.SB, MT = p.MT, BN = p.BN, NACC = p.n_acc;
   const bool RES = p.resident != 0;
   const uint32_t raw = smem_u32(smem_raw);
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc2_kernel(const __grid_constant_
 
   const int n0 = blockIdx.y * BN;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     for (int s = 0; s < p.n_src; ++s) prefetch_tmap(&p.src[s]);
     prefetch_tmap(&p.wmap);
     for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
@@ -286,9 +286,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc2_kernel(const __grid_constant_
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      if (RES) {
+    // ===== TMA producer (whole warp runs the loops; one elected lane issues) =====
+    if (RES) {
+      if (elect_one()) {
         mbar_expect_tx(w_full, (uint32_t)p.n_wtiles * p.b_stage_bytes);
         int idx = 0;
         for (int s = 0; s < p.n_src; ++s) {
@@ -298,74 +298,112 @@ __global__ void __launch_bounds__(192, 1) conv_tc2_kernel(const __grid_constant_
               tma_load_3d(b_base + (uint32_t)idx * p.b_stage_bytes, &p.wmap, p.cstart[s] + c0, n0, tap, w_full);
         }
       }
-      int sa = 0, pa = 0, sb = 0, pb = 0;
-      for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
-        const int t0 = st * MT;
-        const int nvalid = min(MT, p.total_tiles - t0);
-        for (int s = 0; s < p.n_src; ++s) {
-          const int C = p.cstart[s + 1] - p.cstart[s];
-          for (int c0 = 0; c0 < C; c0 += BK) {
-            mbar_wait(a_empty(sa), pa ^ 1);
+      __syncwarp();
+    }
+    int sa = 0, pa = 0, sb = 0, pb = 0;
+    for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+      const int t0 = st * MT;
+      const int nvalid = min(MT, p.total_tiles - t0);
+      for (int s = 0; s < p.n_src; ++s) {
+        const int C = p.cstart[s + 1] - p.cstart[s];
+        for (int c0 = 0; c0 < C; c0 += BK) {
+          mbar_wait(a_empty(sa), pa ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(a_full(sa), (uint32_t)nvalid * A_BOX_BYTES);
             for (int mt = 0; mt < nvalid; ++mt) {
               const int t = t0 + mt;
               const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, n = t / (p.tiles_w * p.tiles_h);
               tma_load_4d(a_base + (uint32_t)(sa * MT + mt) * p.a_tile_bytes, &p.src[s], c0, tw * TW - PADK, th * p.TH - PADK, n, a_full(sa));
             }
-            if (++sa == SA) { sa = 0; pa ^= 1; }
-            if (!RES) {
-              for (int tap = 0; tap < TAPS; ++tap) {
-                mbar_wait(b_empty(sb), pb ^ 1);
+          }
+          __syncwarp();
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+          if (!RES) {
+            for (int tap = 0; tap < TAPS; ++tap) {
+              mbar_wait(b_empty(sb), pb ^ 1);
+              if (elect_one()) {
                 mbar_expect_tx(b_full(sb), p.b_stage_bytes);
                 tma_load_3d(b_base + (uint32_t)sb * p.b_stage_bytes, &p.wmap, p.cstart[s] + c0, n0, tap, b_full(sb));
-                if (++sb == SB) { sb = 0; pb ^= 1; }
               }
+              __syncwarp();
+              if (++sb == SB) { sb = 0; pb ^= 1; }
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      if (RES) mbar_wait(w_full, 0);
-      int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
-      for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
-        const int nvalid = min(MT, p.total_tiles - st * MT);
-        mbar_wait(acc_empty(as), pacc ^ 1);
-        tc_fence_after();
-        const uint32_t acc_col = tmem_base + (uint32_t)(as * MT * BN);
-        bool first = true;
-        int widx = 0;
-        for (int s = 0; s < p.n_src; ++s) {
-          const int C = p.cstart[s + 1] - p.cstart[s];
-          for (int c0 = 0; c0 < C; c0 += BK) {
-            mbar_wait(a_full(sa), pa);
-            tc_fence_after();
-            for (int tap = 0; tap < TAPS; ++tap, ++widx) {
-              uint32_t b_addr;
-              if (RES) b_addr = b_base + (uint32_t)widx * p.b_stage_bytes;
-              else { mbar_wait(b_full(sb), pb); tc_fence_after(); b_addr = b_base + (uint32_t)sb * p.b_stage_bytes; }
-              const uint32_t row_off = (KS == 3) ? (uint32_t)((tap / 3) * 16 + (tap % 3)) : 0u;
-              for (int mt = 0; mt < nvalid; ++mt) {
-                const uint32_t a_addr = a_base + (uint32_t)(sa * MT + mt) * p.a_tile_bytes + row_off * ROW_BYTES;
+    // ===== MMA issuer (whole warp waits; one elected lane issues tcgen05.mma / commit) =====
+    if (RES) mbar_wait(w_full, 0);
+    // descriptor constants: hi word = SBO | version | layout, lo word = (addr >> 4) | LBO(=1) << 16
+    const uint32_t desc_hi = (uint32_t)((SBO >> 4) & 0x3FFFu) | (1u << 14) | (LAYOUT << 29);
+    int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
+    for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+      const int nvalid = min(MT, p.total_tiles - st * MT);
+      mbar_wait(acc_empty(as), pacc ^ 1);
+      tc_fence_after();
+      const uint32_t acc_col = tmem_base + (uint32_t)(as * MT * BN);
+      uint32_t accum = 0;
+      int widx = 0;
+      for (int s = 0; s < p.n_src; ++s) {
+        const int C = p.cstart[s + 1] - p.cstart[s];
+        for (int c0 = 0; c0 < C; c0 += BK) {
+          mbar_wait(a_full(sa), pa);
+          tc_fence_after();
+          const uint32_t a_stage = a_base + (uint32_t)(sa * MT) * p.a_tile_bytes;
+          if (RES) {
+            if (elect_one()) {
+              const uint32_t b_lo0 = (((b_base + (uint32_t)widx * p.b_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+              const uint32_t b_step = p.b_stage_bytes >> 4;
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                  const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, SBO, LAYOUT, 0);
-                  const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, SBO, LAYOUT, 0);
-                  umma_bf16(acc_col + (uint32_t)(mt * BN), ad, bd, p.idesc, (first && k == 0) ? 0u : 1u);
+              for (int tap = 0; tap < TAPS; ++tap) {
+                const uint32_t row_off = (KS == 3) ? (uint32_t)((tap / 3) * 16 + (tap % 3)) : 0u;
+                for (int mt = 0; mt < nvalid; ++mt) {
+                  const uint32_t a_lo = (((a_stage + (uint32_t)mt * p.a_tile_bytes) & 0x3FFFFu) >> 4) + ((row_off * ROW_BYTES) >> 4) + (1u << 16);
+                  const uint32_t b_lo = b_lo0 + (uint32_t)tap * b_step;
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
+                    const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
+                    umma_bf16(acc_col + (uint32_t)(mt * BN), ad, bd, p.idesc, accum | (uint32_t)(tap | k));
+                  }
                 }
               }
-              first = false;
-              if (!RES) { tc_commit(b_empty(sb)); if (++sb == SB) { sb = 0; pb ^= 1; } }
+              tc_commit(a_empty(sa));
             }
-            tc_commit(a_empty(sa));
-            if (++sa == SA) { sa = 0; pa ^= 1; }
+            __syncwarp();
+            accum = 1;
+            widx += TAPS;
+          } else {
+            for (int tap = 0; tap < TAPS; ++tap) {
+              mbar_wait(b_full(sb), pb);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t row_off = (KS == 3) ? (uint32_t)((tap / 3) * 16 + (tap % 3)) : 0u;
+                const uint32_t b_lo = (((b_base + (uint32_t)sb * p.b_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+                for (int mt = 0; mt < nvalid; ++mt) {
+                  const uint32_t a_lo = (((a_stage + (uint32_t)mt * p.a_tile_bytes + row_off * ROW_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
+                    const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
+                    umma_bf16(acc_col + (uint32_t)(mt * BN), ad, bd, p.idesc, accum | (uint32_t)(tap | k));
+                  }
+                }
+                tc_commit(b_empty(sb));
+                if (tap == TAPS - 1) tc_commit(a_empty(sa));
+              }
+              __syncwarp();
+              if (++sb == SB) { sb = 0; pb ^= 1; }
+            }
+            accum = 1;
           }
+          if (++sa == SA) { sa = 0; pa ^= 1; }
         }
-        tc_commit(acc_full(as));
-        if (++as == NACC) { as = 0; pacc ^= 1; }
       }
+      if (elect_one()) tc_commit(acc_full(as));
+      __syncwarp();
+      if (++as == NACC) { as = 0; pacc ^= 1; }
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane group = warp % 4 =====
@@ -537,16 +575,20 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
   const size_t w_bytes = (size_t)p.n_wtiles * p.b_stage_bytes;
   int MT, SA, SB;
   p.resident = 0;
-  if (!v1 && !g_opt.no_resident && w_bytes + 2 * p.a_tile_bytes + fixed <= budget) {
+  // Measured on B200 (scripts/bench_layers.py): keeping the weights resident pays when the MMAs are short
+  // (BN <= 32: one [BN x BK] tile is only 2-4 KB, so per-tap barrier round trips dominate) or when K is tiny
+  // (Cin <= 32, the level-0 data-gradient convs); otherwise streamed weights with >1 CTA per SM win.
+  const bool want_res = g_opt.no_resident ? false : (g_opt.mt < 0 ? true : (p.BN <= 32 || Cin <= 32));
+  if (!v1 && want_res && w_bytes + 2 * p.a_tile_bytes + fixed <= budget) {
     p.resident = 1;
-    MT = g_opt.mt > 0 ? g_opt.mt : 1;
+    MT = g_opt.mt > 0 ? g_opt.mt : ((Cin >= 128) ? 2 : 1);
     while (MT > 1 && (2 * MT * p.BN > 512 || w_bytes + 2 * (size_t)MT * p.a_tile_bytes + fixed > budget)) MT >>= 1;
     SA = g_opt.sa > 0 ? g_opt.sa : 4;
     while (SA > 2 && w_bytes + (size_t)SA * MT * p.a_tile_bytes + fixed > budget) --SA;
     SB = 1;
   } else {
-    // streamed weights: amortise every weight tile over MT output windows
-    MT = g_opt.mt > 0 ? g_opt.mt : (v1 ? 1 : 4);
+    // streamed weights: every weight tile is shared by MT output windows
+    MT = g_opt.mt > 0 ? g_opt.mt : ((!v1 && Cin >= 512) ? 2 : 1);
     while (MT > 1 && (v1 ? MT * p.BN > 512 : 2 * MT * p.BN > 512)) MT >>= 1;
     SA = g_opt.sa > 0 ? g_opt.sa : 3; SB = g_opt.sb > 0 ? g_opt.sb : 4;
     auto bytes = [&](int mt, int sa, int sb) { return (size_t)sa * mt * p.a_tile_bytes + (size_t)sb * p.b_stage_bytes + fixed; };

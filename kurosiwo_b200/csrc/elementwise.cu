@@ -124,68 +124,80 @@ __global__ void bn_finalize_kernel(int C, double count, const double *__restrict
 }
 
 // ------------------------------------------------------------------------------------------
-// out = relu(y*scale+shift (+res)), optional fused 2x2 max-pool output
+// Pixel-lane layout shared by the BN passes: tx = channel vector (fixed per thread, so per-channel
+// coefficients live in registers), ty = pixel lane; a warp touches (32/CV) whole pixels x C channels.
+// `flat` views (pixel stride uniform: sh == W*sw, sn == H*sh) skip the n/h/w decomposition.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long pix_off(const View &v, long long p, int H, int W, bool flat) {
+  if (flat) return p * v.sw;
+  const int w = (int)(p % W); const long long r = p / W; const int h = (int)(r % H); const long long n = r / H;
+  return n * v.sn + (long long)h * v.sh + (long long)w * v.sw;
+}
+static inline bool view_flat(const ks_view_t &v, int H, int W) { return v.sh == (int64_t)W * v.sw && v.sn == (int64_t)H * v.sh; }
+
+// out = relu(y*scale+shift (+res)), optional fused 2x2 max-pool output
 template <typename T, int V, bool POOL>
 __global__ void __launch_bounds__(256)
 bn_act_kernel(View y, View res, bool has_res, View out, View pool, int N, int H, int W,
-              const float *__restrict__ scale, const float *__restrict__ shift, int relu) {
-  const int CV = y.C / V;
-  const int HH = POOL ? H / 2 : H, WW = POOL ? W / 2 : W;
-  const long long total = (long long)N * HH * WW * CV;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % CV); long long r = i / CV;
-    const int w = (int)(r % WW); r /= WW; const int h = (int)(r % HH); const int n = (int)(r / HH);
-    const int c = cv * V;
-    float sc[V], sh[V];
+              const float *__restrict__ scale, const float *__restrict__ shift, int relu, bool flat) {
+  const int CV = y.C / V, rows = blockDim.x / CV;
+  const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
+  if (ty >= rows) return;
+  const int c = tx * V;
+  float sc[V], sh[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) { sc[k] = __ldg(scale + c + k); sh[k] = __ldg(shift + c + k); }
-    if constexpr (POOL) {
-      float mx[V];
+  for (int k = 0; k < V; ++k) { sc[k] = __ldg(scale + c + k); sh[k] = __ldg(shift + c + k); }
+  const T *yp = reinterpret_cast<const T *>(y.ptr) + c;
+  const T *rp = reinterpret_cast<const T *>(res.ptr) + c;
+  T *op = reinterpret_cast<T *>(out.ptr) + c;
+  auto one = [&](long long p, float (&o)[V]) {
+    float f[V], rr[V];
+    VecIO<T, V>::ld(yp + pix_off(y, p, H, W, flat), f);
+    if (has_res) VecIO<T, V>::ld(rp + pix_off(res, p, H, W, flat), rr);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int hh = 2 * h + (q >> 1), ww = 2 * w + (q & 1);
-        float f[V]; VecIO<T, V>::ld(vaddr<T>(y, n, hh, ww, c), f);
-        float rr[V];
-        if (has_res) VecIO<T, V>::ld(vaddr<T>(res, n, hh, ww, c), rr);
-        float o[V];
+    for (int k = 0; k < V; ++k) {
+      float v = fmaf(f[k], sc[k], sh[k]);
+      if (has_res) v += rr[k];
+      if (relu) v = fmaxf(v, 0.f);
+      o[k] = v;
+    }
+    VecIO<T, V>::st(op + pix_off(out, p, H, W, flat), o);
+  };
+  if constexpr (POOL) {
+    const int HP = H / 2, WP = W / 2;
+    const long long npool = (long long)N * HP * WP;
+    T *pp = reinterpret_cast<T *>(pool.ptr) + c;
+    for (long long q = (long long)blockIdx.x * rows + ty; q < npool; q += (long long)gridDim.x * rows) {
+      const int wp = (int)(q % WP); const long long r = q / WP; const int hp = (int)(r % HP); const long long n = r / HP;
+      const long long p00 = (n * H + 2 * hp) * W + 2 * wp;
+      float mx[V], o[V];
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-          float v = fmaf(f[k], sc[k], sh[k]);
-          if (has_res) v += rr[k];
-          if (relu) v = fmaxf(v, 0.f);
-          o[k] = v;
-        }
-        VecIO<T, V>::st(vaddr<T>(out, n, hh, ww, c), o);
-        // pool over the values AS STORED (bf16-rounded in bf16 mode)
+      for (int i = 0; i < 4; ++i) {
+        one(p00 + (i >> 1) * W + (i & 1), o);
 #pragma unroll
-        for (int k = 0; k < V; ++k) { const float os = round_as<T>(o[k]); mx[k] = (q == 0) ? os : fmaxf(mx[k], os); }
+        for (int k = 0; k < V; ++k) { const float os = round_as<T>(o[k]); mx[k] = (i == 0) ? os : fmaxf(mx[k], os); }
       }
-      VecIO<T, V>::st(vaddr<T>(pool, n, h, w, c), mx);
-    } else {
-      float f[V]; VecIO<T, V>::ld(vaddr<T>(y, n, h, w, c), f);
-      float rr[V];
-      if (has_res) VecIO<T, V>::ld(vaddr<T>(res, n, h, w, c), rr);
+      VecIO<T, V>::st(pp + (n * pool.sn + (long long)hp * pool.sh + (long long)wp * pool.sw), mx);
+    }
+  } else {
+    const long long npix = (long long)N * H * W;
+    for (long long p = (long long)blockIdx.x * rows + ty; p < npix; p += (long long)gridDim.x * rows) {
       float o[V];
-#pragma unroll
-      for (int k = 0; k < V; ++k) {
-        float v = fmaf(f[k], sc[k], sh[k]);
-        if (has_res) v += rr[k];
-        if (relu) v = fmaxf(v, 0.f);
-        o[k] = v;
-      }
-      VecIO<T, V>::st(vaddr<T>(out, n, h, w, c), o);
+      one(p, o);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// BN backward: reductions, then apply
+// BN backward, pass 1: g = dout * mask;  sums[0][c] += sum g,  sums[1][c] += sum g*xhat.
+//   MASK_OUT : mask = (out > 0); the masked gradient is written back over dout (later passes re-use it)
+//   !MASK_OUT: mask = (y*scale+shift > 0)  (== (relu output > 0), recomputed instead of re-read)
 // ------------------------------------------------------------------------------------------
-template <typename T, int V>
+template <typename T, int V, bool MASK_OUT>
 __global__ void __launch_bounds__(256)
-bn_bwd_reduce_kernel(View dout, View out, View y, int N, int H, int W,
-                     const float *__restrict__ mean, const float *__restrict__ rstd, double *sums) {
+bn_bwd_reduce_kernel(View dout, View out, View y, int N, int H, int W, const float *__restrict__ scale,
+                     const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ rstd,
+                     double *sums, bool flat) {
   extern __shared__ float smem[];
   const int C = y.C, CV = C / V, rows = blockDim.x / CV;
   const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
@@ -194,61 +206,83 @@ bn_bwd_reduce_kernel(View dout, View out, View y, int N, int H, int W,
   for (int i = 0; i < V; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
   const long long npix = (long long)N * H * W;
   if (ty < rows) {
-    float mu[V], rs[V];
+    const int c = tx * V;
+    float mu[V], rs[V], sc[V], sh[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) { mu[k] = mean[tx * V + k]; rs[k] = rstd[tx * V + k]; }
+    for (int k = 0; k < V; ++k) {
+      mu[k] = mean[c + k]; rs[k] = rstd[c + k];
+      sc[k] = MASK_OUT ? 0.f : scale[c + k]; sh[k] = MASK_OUT ? 0.f : shift[c + k];
+    }
+    T *gp = reinterpret_cast<T *>(dout.ptr) + c;
+    const T *op = reinterpret_cast<const T *>(out.ptr) + c;
+    const T *yp = reinterpret_cast<const T *>(y.ptr) + c;
     for (long long p = (long long)blockIdx.x * rows + ty; p < npix; p += (long long)gridDim.x * rows) {
-      const int w = (int)(p % W); long long r = p / W; const int h = (int)(r % H); const int n = (int)(r / H);
       float g[V], o[V], f[V];
-      VecIO<T, V>::ld(vaddr<T>(dout, n, h, w, tx * V), g);
-      VecIO<T, V>::ld(vaddr<T>(out, n, h, w, tx * V), o);
-      VecIO<T, V>::ld(vaddr<T>(y, n, h, w, tx * V), f);
+      T *gptr = gp + pix_off(dout, p, H, W, flat);
+      VecIO<T, V>::ld(gptr, g);
+      VecIO<T, V>::ld(yp + pix_off(y, p, H, W, flat), f);
+      if (MASK_OUT) VecIO<T, V>::ld(op + pix_off(out, p, H, W, flat), o);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        const float gk = (o[k] > 0.f) ? g[k] : 0.f;
+        const bool on = MASK_OUT ? (o[k] > 0.f) : (fmaf(f[k], sc[k], sh[k]) > 0.f);
+        const float gk = on ? g[k] : 0.f;
+        g[k] = gk;
         acc[0][k] += gk;
         acc[1][k] += gk * ((f[k] - mu[k]) * rs[k]);
       }
+      if (MASK_OUT) VecIO<T, V>::st(gptr, g);
     }
   }
   block_channel_reduce<2, V>(acc, CV, rows, C, sums, smem);
 }
 
+// pass 2: dy = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M) (+ add);  `premasked`: g already masked by pass 1
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(View dout, View out, View y, View add_dout, View add_out, bool has_add, View dy,
-                    int N, int H, int W, const float *__restrict__ mean, const float *__restrict__ rstd,
-                    const float *__restrict__ gamma, const double *__restrict__ sums, double count,
-                    float *dgamma, float *dbeta, int accumulate) {
-  const int C = y.C, CV = C / V;
-  const long long total = (long long)N * H * W * CV;
+bn_bwd_apply_kernel(View gin, View y, View add, bool has_add, View dy, int N, int H, int W, int premasked,
+                    const float *__restrict__ scale, const float *__restrict__ shift,
+                    const float *__restrict__ mean, const float *__restrict__ rstd, const float *__restrict__ gamma,
+                    const double *__restrict__ sums, double count, float *dgamma, float *dbeta, float *dsum_out,
+                    int accumulate, bool flat) {
+  const int C = y.C, CV = C / V, rows = blockDim.x / CV;
+  const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
   if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)sums[C + c];
       if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)sums[c];
+      if (dsum_out) dsum_out[c] = (accumulate ? dsum_out[c] : 0.f) + (float)sums[c];
     }
   }
+  if (ty >= rows) return;
+  const int c = tx * V;
   const float invM = (float)(1.0 / count);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % CV); long long r = i / CV;
-    const int w = (int)(r % W); r /= W; const int h = (int)(r % H); const int n = (int)(r / H);
-    const int c = cv * V;
-    float g[V], o[V], f[V], ag[V], ao[V], d[V];
-    VecIO<T, V>::ld(vaddr<T>(dout, n, h, w, c), g);
-    VecIO<T, V>::ld(vaddr<T>(out, n, h, w, c), o);
-    VecIO<T, V>::ld(vaddr<T>(y, n, h, w, c), f);
-    if (has_add) { VecIO<T, V>::ld(vaddr<T>(add_dout, n, h, w, c), ag); VecIO<T, V>::ld(vaddr<T>(add_out, n, h, w, c), ao); }
+  float a[V], b[V], c2[V], mu[V], rs[V], sc[V], sh[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    mu[k] = mean[c + k]; rs[k] = rstd[c + k];
+    a[k] = (gamma ? gamma[c + k] : 1.f) * rs[k];
+    b[k] = (float)sums[c + k] * invM; c2[k] = (float)sums[C + c + k] * invM;
+    sc[k] = premasked ? 0.f : scale[c + k]; sh[k] = premasked ? 0.f : shift[c + k];
+  }
+  const T *gp = reinterpret_cast<const T *>(gin.ptr) + c;
+  const T *yp = reinterpret_cast<const T *>(y.ptr) + c;
+  const T *ap = reinterpret_cast<const T *>(add.ptr) + c;
+  T *dp = reinterpret_cast<T *>(dy.ptr) + c;
+  const long long npix = (long long)N * H * W;
+  for (long long p = (long long)blockIdx.x * rows + ty; p < npix; p += (long long)gridDim.x * rows) {
+    float g[V], f[V], ad[V], d[V];
+    VecIO<T, V>::ld(gp + pix_off(gin, p, H, W, flat), g);
+    VecIO<T, V>::ld(yp + pix_off(y, p, H, W, flat), f);
+    if (has_add) VecIO<T, V>::ld(ap + pix_off(add, p, H, W, flat), ad);
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-      const float mu = __ldg(mean + c + k), rs = __ldg(rstd + c + k), ga = gamma ? __ldg(gamma + c + k) : 1.f;
-      const float sg = (float)sums[c + k] * invM, sgx = (float)sums[C + c + k] * invM;
-      const float gk = (o[k] > 0.f) ? g[k] : 0.f;
-      const float xh = (f[k] - mu) * rs;
-      float v = ga * rs * (gk - sg - xh * sgx);
-      if (has_add) v += (ao[k] > 0.f) ? ag[k] : 0.f;
+      const bool on = premasked ? true : (fmaf(f[k], sc[k], sh[k]) > 0.f);
+      const float gk = on ? g[k] : 0.f;
+      float v = a[k] * (gk - b[k] - ((f[k] - mu[k]) * rs[k]) * c2[k]);
+      if (has_add) v += ad[k];
       d[k] = v;
     }
-    VecIO<T, V>::st(vaddr<T>(dy, n, h, w, c), d);
+    VecIO<T, V>::st(dp + pix_off(dy, p, H, W, flat), d);
   }
 }
 
@@ -437,6 +471,13 @@ extern "C" int ks_bn_finalize(int C, double count, const double *sums, const flo
   KS_LAUNCH_RET();
 }
 
+static inline int pl_grid(int C, int V, long long npix, int per_thread) {
+  const int CV = C / V, rows = 256 / CV;
+  long long g = (npix + (long long)rows * per_thread - 1) / ((long long)rows * per_thread);
+  const long long cap = (long long)kNumSMs * 8;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
 extern "C" int ks_bn_act(int dtype, int N, int H, int W, const ks_view_t *y, const float *scale, const float *shift,
                          const ks_view_t *res, int relu, const ks_view_t *out, const ks_view_t *pool, void *stream) {
   KS_CHECK_ARG(y && y->ptr && out && out->ptr && scale && shift && N > 0 && H > 0 && W > 0);
@@ -444,48 +485,56 @@ extern "C" int ks_bn_act(int dtype, int N, int H, int W, const ks_view_t *y, con
   if (pool) KS_CHECK_ARG(H % 2 == 0 && W % 2 == 0);
   const int es = esize_of(dtype);
   const bool vec = view_vec8_ok(*y, es) && view_vec8_ok(*out, es) && (!res || view_vec8_ok(*res, es)) && (!pool || view_vec8_ok(*pool, es));
+  if ((vec ? y->C / 8 : y->C) > 256) return KS_EUNSUPPORTED;
+  const bool flat = view_flat(*y, H, W) && view_flat(*out, H, W) && (!res || view_flat(*res, H, W));
   cudaStream_t st = (cudaStream_t)stream;
   const View vy = to_view(*y), vo = to_view(*out), vr = res ? to_view(*res) : vy, vp = pool ? to_view(*pool) : vo;
-#define CALL(T, V) { const long long total = (long long)N * (pool ? H / 2 : H) * (pool ? W / 2 : W) * (y->C / V); \
-    const int grid = ew_grid(total, 256); \
-    if (pool) bn_act_kernel<T, V, true><<<grid, 256, 0, st>>>(vy, vr, res != nullptr, vo, vp, N, H, W, scale, shift, relu); \
-    else bn_act_kernel<T, V, false><<<grid, 256, 0, st>>>(vy, vr, res != nullptr, vo, vp, N, H, W, scale, shift, relu); }
+#define CALL(T, V) { const long long np = (long long)N * (pool ? H / 2 : H) * (pool ? W / 2 : W); \
+    const int grid = pl_grid(y->C, V, np, pool ? 2 : 8); \
+    if (pool) bn_act_kernel<T, V, true><<<grid, 256, 0, st>>>(vy, vr, res != nullptr, vo, vp, N, H, W, scale, shift, relu, flat); \
+    else bn_act_kernel<T, V, false><<<grid, 256, 0, st>>>(vy, vr, res != nullptr, vo, vp, N, H, W, scale, shift, relu, flat); }
   KS_DISPATCH_TV(dtype, vec, CALL);
 #undef CALL
   KS_LAUNCH_RET();
 }
 
 extern "C" int ks_bn_bwd_reduce(int dtype, int N, int H, int W, const ks_view_t *dout, const ks_view_t *out,
-                                const ks_view_t *y, const float *mean, const float *rstd, double *sums, void *stream) {
-  KS_CHECK_ARG(dout && out && y && mean && rstd && sums && N > 0 && H > 0 && W > 0);
-  KS_CHECK_ARG(dout->C == y->C && out->C == y->C);
+                                const ks_view_t *y, const float *scale, const float *shift,
+                                const float *mean, const float *rstd, double *sums, void *stream) {
+  KS_CHECK_ARG(dout && y && mean && rstd && sums && N > 0 && H > 0 && W > 0);
+  KS_CHECK_ARG(out != nullptr || (scale != nullptr && shift != nullptr));
+  KS_CHECK_ARG(dout->C == y->C && (!out || out->C == y->C));
   const int es = esize_of(dtype);
-  const bool vec = view_vec8_ok(*y, es) && view_vec8_ok(*out, es) && view_vec8_ok(*dout, es);
+  const bool vec = view_vec8_ok(*y, es) && (!out || view_vec8_ok(*out, es)) && view_vec8_ok(*dout, es);
+  const bool flat = view_flat(*y, H, W) && view_flat(*dout, H, W) && (!out || view_flat(*out, H, W));
   const long long npix = (long long)N * H * W;
   cudaStream_t st = (cudaStream_t)stream;
+  const View vd = to_view(*dout), vy = to_view(*y), vo = out ? to_view(*out) : vy;
 #define CALL(T, V) { int grid; size_t smem; int rc = launch_reduce_cfg<T, V>(y->C, npix, grid, smem, 2); if (rc) return rc; \
-    bn_bwd_reduce_kernel<T, V><<<grid, 256, smem, st>>>(to_view(*dout), to_view(*out), to_view(*y), N, H, W, mean, rstd, sums); }
+    if (out) bn_bwd_reduce_kernel<T, V, true><<<grid, 256, smem, st>>>(vd, vo, vy, N, H, W, scale, shift, mean, rstd, sums, flat); \
+    else bn_bwd_reduce_kernel<T, V, false><<<grid, 256, smem, st>>>(vd, vo, vy, N, H, W, scale, shift, mean, rstd, sums, flat); }
   KS_DISPATCH_TV(dtype, vec, CALL);
 #undef CALL
   KS_LAUNCH_RET();
 }
 
-extern "C" int ks_bn_bwd_apply(int dtype, int N, int H, int W, const ks_view_t *dout, const ks_view_t *out,
-                               const ks_view_t *y, const float *mean, const float *rstd, const float *gamma,
-                               const double *sums, double count, const ks_view_t *add_dout, const ks_view_t *add_out,
-                               const ks_view_t *dy, float *dgamma, float *dbeta, int accumulate_param_grads, void *stream) {
-  KS_CHECK_ARG(dout && out && y && dy && mean && rstd && sums && count > 0 && N > 0 && H > 0 && W > 0);
-  KS_CHECK_ARG((add_dout == nullptr) == (add_out == nullptr));
-  KS_CHECK_ARG(dout->C == y->C && out->C == y->C && dy->C == y->C);
+extern "C" int ks_bn_bwd_apply(int dtype, int N, int H, int W, const ks_view_t *g, int premasked, const ks_view_t *y,
+                               const float *scale, const float *shift, const float *mean, const float *rstd, const float *gamma,
+                               const double *sums, double count, const ks_view_t *add, const ks_view_t *dy,
+                               float *dgamma, float *dbeta, float *dsum_out, int accumulate_param_grads, void *stream) {
+  KS_CHECK_ARG(g && y && dy && mean && rstd && sums && count > 0 && N > 0 && H > 0 && W > 0);
+  KS_CHECK_ARG(premasked || (scale && shift));
+  KS_CHECK_ARG(g->C == y->C && dy->C == y->C && (!add || add->C == y->C));
   const int es = esize_of(dtype);
-  const bool has_add = add_dout != nullptr;
-  const bool vec = view_vec8_ok(*y, es) && view_vec8_ok(*out, es) && view_vec8_ok(*dout, es) && view_vec8_ok(*dy, es) &&
-                   (!has_add || (view_vec8_ok(*add_dout, es) && view_vec8_ok(*add_out, es)));
+  const bool has_add = add != nullptr;
+  const bool vec = view_vec8_ok(*y, es) && view_vec8_ok(*g, es) && view_vec8_ok(*dy, es) && (!has_add || view_vec8_ok(*add, es));
+  if ((vec ? y->C / 8 : y->C) > 256) return KS_EUNSUPPORTED;
+  const bool flat = view_flat(*y, H, W) && view_flat(*g, H, W) && view_flat(*dy, H, W) && (!has_add || view_flat(*add, H, W));
   cudaStream_t st = (cudaStream_t)stream;
-  const View vd = to_view(*dout), vo = to_view(*out), vy = to_view(*y), vdy = to_view(*dy);
-  const View vad = has_add ? to_view(*add_dout) : vd, vao = has_add ? to_view(*add_out) : vo;
-#define CALL(T, V) { const long long total = (long long)N * H * W * (y->C / V); const int grid = ew_grid(total, 256); \
-    bn_bwd_apply_kernel<T, V><<<grid, 256, 0, st>>>(vd, vo, vy, vad, vao, has_add, vdy, N, H, W, mean, rstd, gamma, sums, count, dgamma, dbeta, accumulate_param_grads); }
+  const View vg = to_view(*g), vy = to_view(*y), vdy = to_view(*dy), va = has_add ? to_view(*add) : vg;
+#define CALL(T, V) { const int grid = pl_grid(y->C, V, (long long)N * H * W, 8); \
+    bn_bwd_apply_kernel<T, V><<<grid, 256, 0, st>>>(vg, vy, va, has_add, vdy, N, H, W, premasked, scale, shift, mean, rstd, gamma, sums, count, \
+                                                 dgamma, dbeta, dsum_out, accumulate_param_grads, flat); }
   KS_DISPATCH_TV(dtype, vec, CALL);
 #undef CALL
   KS_LAUNCH_RET();

@@ -9,6 +9,16 @@ namespace ks { namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Warp-uniform helpers.  tcgen05.mma / TMA / tcgen05.commit take uniform-register operands: issuing them under a
+// `lane == 0` branch makes ptxas wrap every instruction in a divergence ("waterfall") loop.  Role code therefore
+// runs warp-wide on a provably uniform warp index and elects one lane with elect.sync.
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier -----------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));

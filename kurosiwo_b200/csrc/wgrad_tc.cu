@@ -36,7 +36,7 @@ using namespace tc;
 
 __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const int SX = p.SX, SY = p.SY;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   const int pad = p.ksize / 2;
   const uint32_t xg_bytes = 128u * p.GX * 2u, yg_bytes = 128u * p.GY * 2u;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     for (int i = 0; i < SX; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 1); }
     for (int i = 0; i < SY; ++i) { mbar_init(y_full(i), 1); mbar_init(y_empty(i), 1); }
     mbar_init(acc_full, 1);
@@ -77,56 +77,67 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int sx = 0, px = 0, sy = 0, py = 0;
-      for (int t = tile_begin; t < tile_end; ++t) {
-        const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, n = t / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * 16, h0 = th * 8;
-        mbar_wait(y_empty(sy), py ^ 1);
+    // ===== TMA producer =====
+    int sx = 0, px = 0, sy = 0, py = 0;
+    for (int t = tile_begin; t < tile_end; ++t) {
+      const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, n = t / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * 16, h0 = th * 8;
+      mbar_wait(y_empty(sy), py ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(y_full(sy), (uint32_t)nyg * yg_bytes);
         for (int g = 0; g < nyg; ++g)
           tma_load_4d(y_base + (uint32_t)sy * p.y_stage_bytes + (uint32_t)g * yg_bytes, &p.dy[p.yg_view[yg0 + g]],
                       p.yg_c0[yg0 + g], w0, h0, n, y_full(sy));
-        if (++sy == SY) { sy = 0; py ^= 1; }
-        for (int tp = 0; tp < ntap; ++tp) {
-          const int tap = tap0 + tp;
-          const int dyy = tap / p.ksize - pad, dxx = tap % p.ksize - pad;
-          mbar_wait(x_empty(sx), px ^ 1);
+      }
+      __syncwarp();
+      if (++sy == SY) { sy = 0; py ^= 1; }
+      for (int tp = 0; tp < ntap; ++tp) {
+        const int tap = tap0 + tp;
+        const int dyy = tap / p.ksize - pad, dxx = tap % p.ksize - pad;
+        mbar_wait(x_empty(sx), px ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(x_full(sx), (uint32_t)nxg * xg_bytes);
           for (int g = 0; g < nxg; ++g)
             tma_load_4d(x_base + (uint32_t)sx * p.x_stage_bytes + (uint32_t)g * xg_bytes, &p.x[p.xg_view[xg0 + g]],
                         p.xg_c0[xg0 + g], w0 + dxx, h0 + dyy, n, x_full(sx));
-          if (++sx == SX) { sx = 0; px ^= 1; }
         }
+        __syncwarp();
+        if (++sx == SX) { sx = 0; px ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int sx = 0, px = 0, sy = 0, py = 0;
-      const uint32_t lx = (p.GX == 64) ? LAYOUT_SW128 : LAYOUT_SW64, ly = (p.GY == 64) ? LAYOUT_SW128 : LAYOUT_SW64;
-      const uint32_t x_sbo = 8u * p.GX * 2u, y_sbo = 8u * p.GY * 2u;
-      const uint32_t x_kstep = 16u * p.GX * 2u, y_kstep = 16u * p.GY * 2u;
-      for (int t = tile_begin; t < tile_end; ++t) {
-        mbar_wait(y_full(sy), py);
-        const uint32_t y_addr = y_base + (uint32_t)sy * p.y_stage_bytes;
-        for (int tp = 0; tp < ntap; ++tp) {
-          mbar_wait(x_full(sx), px);
-          tc_fence_after();
-          const uint32_t x_addr = x_base + (uint32_t)sx * p.x_stage_bytes;
+    // ===== MMA issuer =====
+    int sx = 0, px = 0, sy = 0, py = 0;
+    const uint32_t lx = (p.GX == 64) ? LAYOUT_SW128 : LAYOUT_SW64, ly = (p.GY == 64) ? LAYOUT_SW128 : LAYOUT_SW64;
+    const uint32_t x_sbo = 8u * p.GX * 2u, y_sbo = 8u * p.GY * 2u;
+    const uint32_t x_kstep = (16u * p.GX * 2u) >> 4, y_kstep = (16u * p.GY * 2u) >> 4;
+    const uint32_t x_hi = ((x_sbo >> 4) & 0x3FFFu) | (1u << 14) | (lx << 29), y_hi = ((y_sbo >> 4) & 0x3FFFu) | (1u << 14) | (ly << 29);
+    const uint32_t x_lbo = ((xg_bytes >> 4) & 0x3FFFu) << 16, y_lbo = ((yg_bytes >> 4) & 0x3FFFu) << 16;
+    for (int t = tile_begin; t < tile_end; ++t) {
+      mbar_wait(y_full(sy), py);
+      const uint32_t y_lo = (((y_base + (uint32_t)sy * p.y_stage_bytes) & 0x3FFFFu) >> 4) | y_lbo;
+      for (int tp = 0; tp < ntap; ++tp) {
+        mbar_wait(x_full(sx), px);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t x_lo = (((x_base + (uint32_t)sx * p.x_stage_bytes) & 0x3FFFFu) >> 4) | x_lbo;
+          const uint32_t first = (t == tile_begin) ? 0u : 1u;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const uint64_t ad = make_smem_desc(x_addr + k * x_kstep, xg_bytes, x_sbo, lx, 0);
-            const uint64_t bd = make_smem_desc(y_addr + k * y_kstep, yg_bytes, y_sbo, ly, 0);
-            umma_bf16(tmem_base + (uint32_t)(tp * p.BN), ad, bd, p.idesc, (t == tile_begin && k == 0) ? 0u : 1u);
+            const uint64_t ad = ((uint64_t)x_hi << 32) | (uint64_t)(x_lo + k * x_kstep);
+            const uint64_t bd = ((uint64_t)y_hi << 32) | (uint64_t)(y_lo + k * y_kstep);
+            umma_bf16(tmem_base + (uint32_t)(tp * p.BN), ad, bd, p.idesc, first | (uint32_t)k);
           }
           tc_commit(x_empty(sx));
-          if (++sx == SX) { sx = 0; px ^= 1; }
+          if (tp == ntap - 1) tc_commit(y_empty(sy));
         }
-        tc_commit(y_empty(sy));
-        if (++sy == SY) { sy = 0; py ^= 1; }
+        __syncwarp();
+        if (++sx == SX) { sx = 0; px ^= 1; }
       }
-      tc_commit(acc_full);
+      if (++sy == SY) { sy = 0; py ^= 1; }
     }
+    if (elect_one()) tc_commit(acc_full);
+    __syncwarp();
   } else {
     const int lg = warp & 3;
     const int row = lg * 32 + lane;            // ci within the M tile

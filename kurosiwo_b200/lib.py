@@ -186,15 +186,16 @@ class CudaOps:
                                 _vp(res), C.c_int(int(relu)), _vp(out), _vp(pool), self._stream())
         self._check(rc, "ks_bn_act")
 
-    def bn_bwd_reduce(self, dout: View, out: View, y: View, mean, rstd, sums):
+    def bn_bwd_reduce(self, dout: View, out: Optional[View], y: View, scale, shift, mean, rstd, sums):
         rc = self.lib.ks_bn_bwd_reduce(dtype_code(y.dtype), C.c_int(y.N), C.c_int(y.H), C.c_int(y.W), _vp(dout), _vp(out), _vp(y),
-                                       _p(mean), _p(rstd), _p(sums), self._stream())
+                                       _p(scale), _p(shift), _p(mean), _p(rstd), _p(sums), self._stream())
         self._check(rc, "ks_bn_bwd_reduce")
 
-    def bn_bwd_apply(self, dout, out, y, mean, rstd, gamma, sums, count, add_dout, add_out, dy, dgamma, dbeta, accumulate):
-        rc = self.lib.ks_bn_bwd_apply(dtype_code(y.dtype), C.c_int(y.N), C.c_int(y.H), C.c_int(y.W), _vp(dout), _vp(out), _vp(y),
-                                      _p(mean), _p(rstd), _p(gamma), _p(sums), C.c_double(count), _vp(add_dout), _vp(add_out),
-                                      _vp(dy), _p(dgamma), _p(dbeta), C.c_int(int(accumulate)), self._stream())
+    def bn_bwd_apply(self, g: View, premasked: bool, y: View, scale, shift, mean, rstd, gamma, sums, count, add: Optional[View],
+                     dy: View, dgamma, dbeta, dsum_out, accumulate: bool):
+        rc = self.lib.ks_bn_bwd_apply(dtype_code(y.dtype), C.c_int(y.N), C.c_int(y.H), C.c_int(y.W), _vp(g), C.c_int(int(premasked)), _vp(y),
+                                      _p(scale), _p(shift), _p(mean), _p(rstd), _p(gamma), _p(sums), C.c_double(count), _vp(add),
+                                      _vp(dy), _p(dgamma), _p(dbeta), _p(dsum_out), C.c_int(int(accumulate)), self._stream())
         self._check(rc, "ks_bn_bwd_apply")
 
     def maxpool2x2_bwd(self, x: View, dpool: View, dx: View, accumulate: bool):

@@ -324,18 +324,18 @@ class SNUNetEngine:
         sc1, sh1, mu1, rs1, sc2, sh2, mu2, rs2 = [e.bn[i * fl:(i + 1) * fl] for i in range(8)]
         dy, dh = self.dY[e.level], self.dH[e.level]
         acc = not first
-        # ---- bn2 + residual + relu backward -> dy2
-        ops.bn_bwd_reduce(e.dout, e.out, e.y2, mu2, rs2, e.bstats[1])
-        ops.bn_bwd_apply(e.dout, e.out, e.y2, mu2, rs2, P.p(f"{nm}.bn2.weight"), e.bstats[1], count, None, None, dy,
-                         P.g(f"{nm}.bn2.weight"), P.g(f"{nm}.bn2.bias"), acc)
-        ops.channel_sum(dy, P.g(f"{nm}.conv2.bias"), acc)
+        # ---- bn2 + residual + relu backward -> dy2.  Pass 1 masks dout IN PLACE (g = dout*(out>0)); the masked
+        # gradient is re-used by pass 2 and, below, as the identity-path gradient of conv1's output.
+        ops.bn_bwd_reduce(e.dout, e.out, e.y2, None, None, mu2, rs2, e.bstats[1])
+        ops.bn_bwd_apply(e.dout, True, e.y2, None, None, mu2, rs2, P.p(f"{nm}.bn2.weight"), e.bstats[1], count, None, dy,
+                         P.g(f"{nm}.bn2.weight"), P.g(f"{nm}.bn2.bias"), P.g(f"{nm}.conv1.bias"), acc)
+        # d(conv2.bias) = sum(dy2) == 0 identically (BatchNorm removes the mean): the flat gradient buffer keeps its 0.
         ops.conv2d_wgrad(N, h_, w_, 3, [e.h], [dy], self.gp[f"{nm}.conv2"], acc, self.conv_impl)
         ops.conv2d(N, h_, w_, 3, [dy], self.wp[f"{nm}.conv2.dgrad"], None, [dh], None, None, self.conv_impl)
-        # ---- bn1 + relu backward (+ identity path g = dout*(out>0)) -> dy1 (reuses dy)
-        ops.bn_bwd_reduce(dh, e.h, e.y1, mu1, rs1, e.bstats[0])
-        ops.bn_bwd_apply(dh, e.h, e.y1, mu1, rs1, P.p(f"{nm}.bn1.weight"), e.bstats[0], count, e.dout, e.out, dy,
-                         P.g(f"{nm}.bn1.weight"), P.g(f"{nm}.bn1.bias"), acc)
-        ops.channel_sum(dy, P.g(f"{nm}.conv1.bias"), acc)
+        # ---- bn1 + relu backward: the ReLU mask is recomputed from y1 (h is not re-read); + identity path g -> dy1
+        ops.bn_bwd_reduce(dh, None, e.y1, sc1, sh1, mu1, rs1, e.bstats[0])
+        ops.bn_bwd_apply(dh, False, e.y1, sc1, sh1, mu1, rs1, P.p(f"{nm}.bn1.weight"), e.bstats[0], count, e.dout, dy,
+                         P.g(f"{nm}.bn1.weight"), P.g(f"{nm}.bn1.bias"), None, acc)
         if self.use_stem and e.key[0] == "enc" and e.level == 0:
             ops.stem_wgrad3x3(self._x_in[e.key[2]], dy, P.g(f"{nm}.conv1.weight"), acc)
         else:

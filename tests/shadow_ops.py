@@ -122,27 +122,37 @@ class ShadowOps:
             p = F.max_pool2d(o.float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
             _t(pool).copy_(p.to(o.dtype))
 
-    def bn_bwd_reduce(self, dout, out, y, mean, rstd, sums):
-        g = _t(dout).float() * (_t(out).float() > 0)
-        xh = (_t(y).float() - mean) * rstd
+    def bn_bwd_reduce(self, dout, out, y, scale, shift, mean, rstd, sums):
+        yt = _t(y).float()
+        if out is not None:
+            mask = _t(out).float() > 0
+        else:
+            mask = torch.addcmul(shift, yt, scale) > 0
+        g = _t(dout).float() * mask
+        if out is not None:
+            d = _t(dout)
+            d.copy_(g.to(d.dtype))
+        xh = (yt - mean) * rstd
         Cn = y.C
         sums.view(2, Cn)[0] += g.double().reshape(-1, Cn).sum(0)
         sums.view(2, Cn)[1] += (g * xh).double().reshape(-1, Cn).sum(0)
 
-    def bn_bwd_apply(self, dout, out, y, mean, rstd, gamma, sums, count, add_dout, add_out, dy, dgamma, dbeta, accumulate):
+    def bn_bwd_apply(self, g, premasked, y, scale, shift, mean, rstd, gamma, sums, count, add, dy, dgamma, dbeta, dsum_out, accumulate):
         Cn = y.C
         s = sums.view(2, Cn).float()
-        g = _t(dout).float() * (_t(out).float() > 0)
-        xh = (_t(y).float() - mean) * rstd
-        v = gamma * rstd * (g - s[0] / count - xh * (s[1] / count))
-        if add_dout is not None:
-            v = v + _t(add_dout).float() * (_t(add_out).float() > 0)
+        yt = _t(y).float()
+        gg = _t(g).float()
+        if not premasked:
+            gg = gg * (torch.addcmul(shift, yt, scale) > 0)
+        xh = (yt - mean) * rstd
+        v = gamma * rstd * (gg - s[0] / count - xh * (s[1] / count))
+        if add is not None:
+            v = v + _t(add).float()
         t = _t(dy)
         t.copy_(v.to(t.dtype))
-        if dgamma is not None:
-            dgamma.copy_(dgamma + s[1] if accumulate else s[1])
-        if dbeta is not None:
-            dbeta.copy_(dbeta + s[0] if accumulate else s[0])
+        for dst, val in ((dgamma, s[1]), (dbeta, s[0]), (dsum_out, s[0])):
+            if dst is not None:
+                dst.copy_(dst + val if accumulate else val)
 
     def maxpool2x2_bwd(self, x, dpool, dx, accumulate):
         xt = _t(x).float().permute(0, 3, 1, 2)

@@ -50,23 +50,36 @@ def conv_case(ops, name, N, H, W, ks, src_specs, dst_specs, bias, gen):
     ops.conv2d(N, H, W, ks, srcs, w, b, dsts, accs, None, IMPL_SIMT)
     torch.cuda.synchronize()
     ref = [f.base.clone() for f in dst_fulls]
+    want_stats = len(dsts) == 1 and not accs[0]
+    ref_stats = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
+    if want_stats:
+        ops.bn_stats(dsts[0], ref_stats)
     res = {}
-    for bo in (0, 1):
-        for mt in (1, 2, 4):
-            for f, i0 in zip(dst_fulls, init):
-                f.base.copy_(i0)
-            ops.set_option("tc_bo_mode", bo)
-            ops.set_option("tc_mt", mt)
-            key = f"bo{bo}_mt{mt}"
-            try:
-                ops.conv2d(N, H, W, ks, srcs, w, b, dsts, accs, None, IMPL_TC)
-                torch.cuda.synchronize()
-                err = max(rel_l2(f.base.float(), r.float()) for f, r in zip(dst_fulls, ref))
-                res[key] = err
-            except KsError as e:
-                res[key] = f"error: {e}"
-    ops.set_option("tc_bo_mode", 0)
-    ops.set_option("tc_mt", 0)
+    variants = {
+        "v1_mt1": {"tc_v1": 1, "tc_mt": 1},
+        "v2_auto": {},
+        "v2_res_mt2": {"tc_mt": 2},
+        "v2_nores_mt1": {"tc_no_resident": 1, "tc_mt": 1},
+        "v2_nores_mt2": {"tc_no_resident": 1, "tc_mt": 2},
+        "v2_nores_mt4": {"tc_no_resident": 1, "tc_mt": 4},
+    }
+    for key, opts in variants.items():
+        for f, i0 in zip(dst_fulls, init):
+            f.base.copy_(i0)
+        for o in ("tc_v1", "tc_mt", "tc_no_resident"):
+            ops.set_option(o, opts.get(o, 0))
+        try:
+            st = torch.zeros(2 * cout, dtype=torch.float64, device=dev) if want_stats else None
+            ops.conv2d(N, H, W, ks, srcs, w, b, dsts, accs, st, IMPL_TC)
+            torch.cuda.synchronize()
+            err = max(rel_l2(f.base.float(), r.float()) for f, r in zip(dst_fulls, ref))
+            if want_stats:
+                err = max(err, rel_l2(st, ref_stats))
+            res[key] = err
+        except KsError as e:
+            res[key] = f"error: {e}"
+    for o in ("tc_v1", "tc_mt", "tc_no_resident"):
+        ops.set_option(o, 0)
     return res
 
 

@@ -147,20 +147,31 @@ def test_bn_forward_backward(ops, sh, dtype, C, ctot, c0):
     sh.bn_act(cy, csmall[0], csmall[1], cres, True, cout, cpool)
     assert rel_l2(fout.base.float(), cout.base.float()) < _tol(dtype)
     assert rel_l2(fpool.base.float(), cpool.base.float()) < _tol(dtype)
-    # backward
-    dout, _ = rand_view(N, H, W, C, dtype, DEV, gen=g)
+    # backward, pass 1 with the mask taken from `out` (masked gradient written back in place)
+    dout, fdo = rand_view(N, H, W, C, dtype, DEV, ctot, c0, gen=g)
     add_d, _ = rand_view(N, H, W, C, dtype, DEV, gen=g)
     dy, fdy = rand_view(N, H, W, C, dtype, DEV, gen=g)
     bs = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
     cbs = bs.cpu().clone()
     cdout, cadd, cdy = mirror(dout), mirror(add_d), mirror(dy)
-    ops.bn_bwd_reduce(dout, out, y, small[2], small[3], bs)
-    sh.bn_bwd_reduce(cdout, cout, cy, csmall[2], csmall[3], cbs)
+    cout.base.copy_(fout.base.cpu())          # identical masks on both sides
+    ops.bn_bwd_reduce(dout, out, y, None, None, small[2], small[3], bs)
+    sh.bn_bwd_reduce(cdout, cout, cy, None, None, csmall[2], csmall[3], cbs)
     assert rel_l2(bs, cbs) < (1e-5 if dtype == torch.float32 else 1e-3)
-    dg, db = torch.ones(C, device=DEV), torch.ones(C, device=DEV)
-    cdg, cdb = dg.cpu().clone(), db.cpu().clone()
-    ops.bn_bwd_apply(dout, out, y, small[2], small[3], gamma, bs, count, add_d, out, dy, dg, db, True)
-    sh.bn_bwd_apply(cdout, cout, cy, csmall[2], csmall[3], gamma.cpu(), cbs, count, cadd, cout, cdy, cdg, cdb, True)
+    assert rel_l2(fdo.base.float(), cdout.base.float()) < 1e-6
+    dg, db, ds = (torch.ones(C, device=DEV) for _ in range(3))
+    cdg, cdb, cds = dg.cpu().clone(), db.cpu().clone(), ds.cpu().clone()
+    ops.bn_bwd_apply(dout, True, y, None, None, small[2], small[3], gamma, bs, count, add_d, dy, dg, db, ds, True)
+    sh.bn_bwd_apply(cdout, True, cy, None, None, csmall[2], csmall[3], gamma.cpu(), cbs, count, cadd, cdy, cdg, cdb, cds, True)
+    assert rel_l2(fdy.base.float(), cdy.base.float()) < _tol(dtype)
+    assert max_rel(dg, cdg) < 1e-3 and max_rel(db, cdb) < 1e-3 and max_rel(ds, cds) < 1e-3
+    # pass 1 / 2 with the ReLU mask recomputed from y*scale+shift (no `out` tensor)
+    bs.zero_(); cbs.zero_()
+    ops.bn_bwd_reduce(dout, None, y, small[0], small[1], small[2], small[3], bs)
+    sh.bn_bwd_reduce(cdout, None, cy, csmall[0], csmall[1], csmall[2], csmall[3], cbs)
+    assert rel_l2(bs, cbs) < (1e-5 if dtype == torch.float32 else 1e-3)
+    ops.bn_bwd_apply(dout, False, y, small[0], small[1], small[2], small[3], gamma, bs, count, None, dy, dg, db, None, False)
+    sh.bn_bwd_apply(cdout, False, cy, csmall[0], csmall[1], csmall[2], csmall[3], gamma.cpu(), cbs, count, None, cdy, cdg, cdb, None, False)
     assert rel_l2(fdy.base.float(), cdy.base.float()) < _tol(dtype)
     assert max_rel(dg, cdg) < 1e-3 and max_rel(db, cdb) < 1e-3
     # max-pool backward (accumulate and assign) + channel sum
