@@ -234,7 +234,7 @@ __device__ __forceinline__ void warp_reduce_scatter16(float (&v)[16], int lane) 
 }
 
 template <int BK, int KS>
-__global__ void __launch_bounds__(192, 1) conv_tc2_kernel(const __grid_constant__ ConvTcParams p) {
+__global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int TW = (KS == 3) ? 14 : 16;
   constexpr int PADK = KS / 2;
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc2_kernel(const __grid_constant_
     prefetch_tmap(&p.wmap);
     for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 8); }
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
@@ -406,61 +406,94 @@ __global__ void __launch_bounds__(192, 1) conv_tc2_kernel(const __grid_constant_
       if (++as == NACC) { as = 0; pacc ^= 1; }
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane group = warp % 4 =====
+    // ===== epilogue: warps 2..9.  TMEM lane group = warp % 4; the two warps of a lane group split the
+    // (window, 32-column chunk) work items.  Per item: one 32-column TMEM load, the optional += loads are
+    // issued before the TMEM wait, then bias, bf16 pack, four 16-byte stores and the BN-statistics butterfly.
     const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = lg * 32 + lane;
     const int ty = row >> 4, tx = row & 15;
+    const int nchunk = (BN + 31) >> 5;
     int as = 0, pacc = 0;
     for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
       const int t0 = st * MT;
       const int nvalid = min(MT, p.total_tiles - t0);
       mbar_wait(acc_full(as), pacc);
       tc_fence_after();
-      for (int mt = 0; mt < nvalid; ++mt) {
+      for (int item = half; item < nvalid * nchunk; item += 2) {
+        const int mt = item / nchunk, cc = (item % nchunk) << 5;
         const int t = t0 + mt;
         const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, n = t / (p.tiles_w * p.tiles_h);
         const int h = th * p.TH + ty, w = tw * TW + tx;
         const bool ok = (tx < TW) && (ty < p.TH) && (h < p.H) && (w < p.W);
-        for (int cc = 0; cc < BN; cc += 16) {
-          uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * MT * BN + mt * BN + cc), r);
-          tmem_ld_wait();
-          float v[16];
-          const int co = n0 + cc;
-          if (ok) {
-            int d = 0;
+        const bool wide = (BN - cc) >= 32;
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * MT * BN + mt * BN + cc);
+        uint32_t r[32];
+        if (wide) tmem_ld32(taddr, r);
+        else { uint32_t r16[16]; tmem_ld16(taddr, r16);
 #pragma unroll
-            for (int i = 1; i < KS_MAX_VIEWS; ++i) if (i < p.dsts.n && co >= p.dsts.cstart[i]) d = i;
-            const View &dv = p.dsts.v[d];
-            __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(dv.ptr) +
-                                ((long long)n * dv.sn + (long long)h * dv.sh + (long long)w * dv.sw + (co - p.dsts.cstart[d]));
+          for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0u; } }
+        // destination pointers of the two 16-column halves (view boundaries are multiples of 16 channels)
+        __nv_bfloat16 *op[2]; bool accd[2];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + co + i) : 0.f);
-            if ((p.acc_mask >> d) & 1) {
-              float o[8];
-              ld8(op, o);
+        for (int hh = 0; hh < 2; ++hh) {
+          const int co = n0 + cc + 16 * hh;
+          int d = 0;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] += o[i];
-              ld8(op + 8, o);
+          for (int i = 1; i < KS_MAX_VIEWS; ++i) if (i < p.dsts.n && co >= p.dsts.cstart[i]) d = i;
+          const View &dv = p.dsts.v[d];
+          op[hh] = reinterpret_cast<__nv_bfloat16 *>(dv.ptr) +
+                   ((long long)n * dv.sn + (long long)h * dv.sh + (long long)w * dv.sw + (co - p.dsts.cstart[d]));
+          accd[hh] = ((p.acc_mask >> d) & 1) != 0;
+        }
+        const int nh = wide ? 2 : 1;
+        uint4 old[4];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[8 + i] += o[i];
+        for (int hh = 0; hh < 2; ++hh)
+          if (ok && hh < nh && accd[hh]) {
+            old[2 * hh] = *reinterpret_cast<const uint4 *>(op[hh]);
+            old[2 * hh + 1] = *reinterpret_cast<const uint4 *>(op[hh] + 8);
+          }
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (i < 16 * nh) v[i] += __ldg(p.bias + n0 + cc + i);
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          if (ok && hh < nh) {
+            if (accd[hh]) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const __nv_bfloat162 *hp = reinterpret_cast<const __nv_bfloat162 *>(&old[2 * hh + q]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const float2 f2 = __bfloat1622float2(hp[i]); v[16 * hh + 8 * q + 2 * i] += f2.x; v[16 * hh + 8 * q + 2 * i + 1] += f2.y; }
+              }
             }
             float a[8], b[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { a[i] = v[i]; b[i] = v[8 + i]; }
-            st8(op, a);
-            st8(op + 8, b);
+            for (int i = 0; i < 8; ++i) { a[i] = v[16 * hh + i]; b[i] = v[16 * hh + 8 + i]; }
+            st8(op[hh], a);
+            st8(op[hh] + 8, b);
           }
-          if (p.stats) {
-            float s1[16], s2[16];
+        }
+        if (p.stats) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { const float q = ok ? round_as<__nv_bfloat16>(v[i]) : 0.f; s1[i] = q; s2[i] = q * q; }
-            warp_reduce_scatter16(s1, lane);
-            warp_reduce_scatter16(s2, lane);
-            if ((lane & 1) == 0) {
-              const int c = cc + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-              atomicAdd(&sstat[c], s1[0]);
-              atomicAdd(&sstat[BN + c], s2[0]);
+          for (int hh = 0; hh < 2; ++hh) {
+            if (hh < nh) {
+              float s1[16], s2[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { const float q = ok ? round_as<__nv_bfloat16>(v[16 * hh + i]) : 0.f; s1[i] = q; s2[i] = q * q; }
+              warp_reduce_scatter16(s1, lane);
+              warp_reduce_scatter16(s2, lane);
+              if ((lane & 1) == 0) {
+                const int c = cc + 16 * hh + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                atomicAdd(&sstat[c], s1[0]);
+                atomicAdd(&sstat[BN + c], s2[0]);
+              }
             }
           }
         }
@@ -520,7 +553,7 @@ static int launch_conv_tc2(const ConvTcParams &p, dim3 grid, size_t smem, cudaSt
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  conv_tc2_kernel<BK, KS><<<grid, 192, smem, st>>>(p);
+  conv_tc2_kernel<BK, KS><<<grid, 320, smem, st>>>(p);
   return (int)cudaGetLastError();
 }
 

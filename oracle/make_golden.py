@@ -49,7 +49,7 @@ def main():
     np.savez_compressed(OUT / "loss_cases.npz", **{f"{t}.{k}": v for t, c in cases.items() for k, v in c.items()})
 
     # ---- SNUNet fixtures: forward logits, loss, gradients, running stats after one step ----
-    for tag, (base, N, H, W, seed) in {"b8_n2_s32": (8, 2, 32, 32, 11), "b32_n2_s32": (32, 2, 32, 32, 12)}.items():
+    for tag, (base, N, H, W, seed) in {"b8_n2_s32": (8, 2, 32, 32, 11), "b32_n4_s64": (32, 4, 64, 64, 12)}.items():
         sd = make_state(seed, 2, 3, base)
         xA, xB, mask = make_batch(seed, N, H, W)
         model = RefSNUNet(2, 3, base_channel=base)

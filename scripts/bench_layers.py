@@ -88,6 +88,15 @@ VARIANTS = {
     "nores_mt4": {"tc_no_resident": 1, "tc_mt": 4},
     "res_mt2": {"tc_mt": 2},
 }
+import os
+SEL = [x.strip() for x in os.environ.get("KS_LAYERS", "").split(",") if x.strip()]
+VSEL = [x.strip() for x in os.environ.get("KS_VARIANTS", "").split(",") if x.strip()]
+REPS = int(os.environ.get("KS_REPS", "5"))
+if SEL:
+    CONV = {k: v for k, v in CONV.items() if k in SEL}
+    WGRAD = {k: v for k, v in WGRAD.items() if k in SEL}
+if VSEL:
+    VARIANTS = {k: v for k, v in VARIANTS.items() if k in VSEL}
 out = {"conv": {}, "wgrad": {}}
 for name, (H, cins, couts, ks, stats) in CONV.items():
     row = {}
@@ -96,7 +105,7 @@ for name, (H, cins, couts, ks, stats) in CONV.items():
             ops.set_option(o, opts.get(o, 0))
         try:
             fn, fl = conv_case(H, cins, couts, ks, stats and vn != "v1")
-            ms = timeit(fn)
+            ms = timeit(fn, REPS)
             row[vn] = (round(ms, 4), round(fl / ms / 1e9, 1))
         except KsError as e:
             row[vn] = str(e)[:60]
@@ -107,7 +116,7 @@ for o in ("tc_v1", "tc_mt", "tc_no_resident"):
     ops.set_option(o, 0)
 for name, (H, cins, couts) in WGRAD.items():
     fn, fl = wgrad_case(H, cins, couts)
-    ms = timeit(fn)
+    ms = timeit(fn, REPS)
     out["wgrad"][name] = (round(ms, 4), round(fl / ms / 1e9, 1))
     print(f"{name:28s} ms={ms:.4f} TF={fl / ms / 1e9:.1f}", flush=True)
     torch.cuda.empty_cache()

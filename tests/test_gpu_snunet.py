@@ -31,7 +31,7 @@ def _argmax_check(logits, ref_logits, margin=1e-3):
     return float(safe.float().mean())
 
 
-@pytest.mark.parametrize("tag", ["b8_n2_s32", "b32_n2_s32"])
+@pytest.mark.parametrize("tag", ["b8_n2_s32", "b32_n4_s64"])
 def test_fp32_matches_reference_golden(golden_dir, tag):
     from kurosiwo_b200.bce_and_dice import BCEandDiceLoss
     fx = np.load(golden_dir / f"snunet_{tag}.npz")

@@ -20,7 +20,7 @@ def test_loss_oracle_matches_reference(golden_dir, tag):
     np.testing.assert_array_equal(r["argmax"], z[f"{tag}.argmax"])
 
 
-@pytest.mark.parametrize("tag", ["b8_n2_s32", "b32_n2_s32"])
+@pytest.mark.parametrize("tag", ["b8_n2_s32", "b32_n4_s64"])
 def test_snunet_oracle_matches_reference(golden_dir, tag):
     fx = np.load(golden_dir / f"snunet_{tag}.npz")
     base, N, H, W, seed = (int(fx[k]) for k in ("base", "N", "H", "W", "seed"))
