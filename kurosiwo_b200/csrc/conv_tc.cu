@@ -447,13 +447,10 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
           accd[hh] = ((p.acc_mask >> d) & 1) != 0;
         }
         const int nh = wide ? 2 : 1;
-        uint4 old[4];
+        uint32_t old[2][8];
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh)
-          if (ok && hh < nh && accd[hh]) {
-            old[2 * hh] = *reinterpret_cast<const uint4 *>(op[hh]);
-            old[2 * hh + 1] = *reinterpret_cast<const uint4 *>(op[hh] + 8);
-          }
+          if (ok && hh < nh && accd[hh]) ld_global_v8(op[hh], old[hh]);
         tmem_ld_wait();
         float v[32];
 #pragma unroll
@@ -467,17 +464,18 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
           if (ok && hh < nh) {
             if (accd[hh]) {
 #pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const __nv_bfloat162 *hp = reinterpret_cast<const __nv_bfloat162 *>(&old[2 * hh + q]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { const float2 f2 = __bfloat1622float2(hp[i]); v[16 * hh + 8 * q + 2 * i] += f2.x; v[16 * hh + 8 * q + 2 * i + 1] += f2.y; }
+              for (int i = 0; i < 8; ++i) {
+                const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&old[hh][i]));
+                v[16 * hh + 2 * i] += f2.x; v[16 * hh + 2 * i + 1] += f2.y;
               }
             }
-            float a[8], b[8];
+            uint32_t pk[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { a[i] = v[16 * hh + i]; b[i] = v[16 * hh + 8 + i]; }
-            st8(op[hh], a);
-            st8(op[hh] + 8, b);
+            for (int i = 0; i < 8; ++i) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[16 * hh + 2 * i], v[16 * hh + 2 * i + 1]);
+              pk[i] = *reinterpret_cast<const uint32_t *>(&h2);
+            }
+            st_global_v8(op[hh], pk);
           }
         }
         if (p.stats) {
@@ -561,6 +559,7 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
               const ViewList &dsts, int acc_mask, double *stats, cudaStream_t st) {
   if (g_opt.tc_disable) return KS_EUNSUPPORTED;
   const int Cin = srcs.cstart[srcs.n], Cout = dsts.cstart[dsts.n];
+  const bool v1_opt = g_opt.v1 != 0;
   bool all64 = true;
   for (int s = 0; s < srcs.n; ++s) {
     if (srcs.v[s].C % 32) return KS_EUNSUPPORTED;
@@ -570,6 +569,7 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
   for (int d = 0; d < dsts.n; ++d) {
     if (dsts.cstart[d] % 16 || dsts.v[d].C % 16) return KS_EUNSUPPORTED;
     if (!tma_view_ok(dsts.v[d])) return KS_EUNSUPPORTED;
+    if (!v1_opt && ((((uintptr_t)dsts.v[d].ptr) % 32) || (dsts.v[d].sw * 2) % 32 || (dsts.v[d].sh * 2) % 32 || (dsts.v[d].sn * 2) % 32)) return KS_EUNSUPPORTED;
   }
   if (((uintptr_t)weight) % 16) return KS_EUNSUPPORTED;
   if (stats && dsts.n != 1) return KS_EUNSUPPORTED;
@@ -614,7 +614,7 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
   const bool want_res = g_opt.no_resident ? false : (g_opt.mt < 0 ? true : (p.BN <= 32 || Cin <= 32));
   if (!v1 && want_res && w_bytes + 2 * p.a_tile_bytes + fixed <= budget) {
     p.resident = 1;
-    MT = g_opt.mt > 0 ? g_opt.mt : ((Cin >= 128) ? 2 : 1);
+    MT = g_opt.mt > 0 ? g_opt.mt : 2;
     while (MT > 1 && (2 * MT * p.BN > 512 || w_bytes + 2 * (size_t)MT * p.a_tile_bytes + fixed > budget)) MT >>= 1;
     SA = g_opt.sa > 0 ? g_opt.sa : 4;
     while (SA > 2 && w_bytes + (size_t)SA * MT * p.a_tile_bytes + fixed > budget) --SA;

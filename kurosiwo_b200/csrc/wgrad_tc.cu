@@ -170,13 +170,249 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
 }
 
+// ------------------------------------------------------------------------------------------------
+// v2 (3x3, W % 14 == 0): HALO REUSE.  Output windows are 8 rows x 14 columns laid out on a 16-pixel pitch.
+// The dy tile comes through a 5-D tensor map (C, 14, W/14, H, N) with a 16-wide box, so its two pad columns
+// are out-of-bounds -> zero: they contribute nothing.  The x tile is ONE halo box per window
+// ((8+2) x 16 pixels for the 9-tap mode, 8 x 16 at row h0-1+r for the 3-tap "one kernel row per CTA" mode);
+// tap (r,s) is that tile viewed from pixel offset r*16+s (resp. s) of the contraction dimension.
+// L2->SMEM traffic for x drops 7.2x (resp. 3x) against per-tap loads.
+// ------------------------------------------------------------------------------------------------
+struct alignas(64) WgradTc2Params {
+  CUtensorMap x[KS_MAX_VIEWS];
+  CUtensorMap dy[KS_MAX_VIEWS];
+  unsigned char xg_view[64], yg_view[64];
+  short xg_c0[64], yg_c0[64];
+  int x_cstart[KS_MAX_VIEWS + 1], y_cstart[KS_MAX_VIEWS + 1];
+  int n_xg, n_yg, GX, GY, MG, NG, BN;
+  int m_tiles, n_tiles, tap_groups, TG;
+  int N, H, W, tiles_w, tiles_h, total_tiles, splits;
+  int Cin, Cout, SX, SY;
+  uint32_t x_gstride, x_box_bytes, x_stage_bytes, y_stage_bytes, tmem_cols, idesc;
+  float *dw;
+};
+
+__global__ void __launch_bounds__(192, 1) wgrad_tc2_kernel(const __grid_constant__ WgradTc2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+  const int SX = p.SX, SY = p.SY;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *sm = smem_raw + (base - raw);
+  const uint32_t x_base = base;
+  const uint32_t y_base = x_base + (uint32_t)SX * p.x_stage_bytes;
+  const uint32_t bar_base = y_base + (uint32_t)SY * p.y_stage_bytes;
+  auto x_full = [&](int i) { return bar_base + 8u * i; };
+  auto x_empty = [&](int i) { return bar_base + 8u * (SX + i); };
+  auto y_full = [&](int i) { return bar_base + 8u * (2 * SX + i); };
+  auto y_empty = [&](int i) { return bar_base + 8u * (2 * SX + SY + i); };
+  const uint32_t acc_full = bar_base + 8u * (2 * SX + 2 * SY);
+  const uint32_t tmem_slot = acc_full + 8u;
+  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(sm + (tmem_slot - base));
+
+  int item = blockIdx.x;
+  const int tg = item % p.tap_groups; item /= p.tap_groups;
+  const int ntile = item % p.n_tiles; const int mtile = item / p.n_tiles;
+  const int xg0 = mtile * p.MG, nxg = min(p.MG, p.n_xg - xg0);
+  const int yg0 = ntile * p.NG, nyg = min(p.NG, p.n_yg - yg0);
+  const int per = (p.total_tiles + p.splits - 1) / p.splits;
+  const int tile_begin = blockIdx.y * per, tile_end = min(p.total_tiles, tile_begin + per);
+  const uint32_t yg_bytes = 128u * p.GY * 2u;
+  const uint32_t xrow = p.GX * 2u, yrow = p.GY * 2u;
+  const int row_shift = (p.TG == 9) ? 0 : tg;        // 3-tap mode: this CTA owns kernel row r = tg
+
+  // x stages have pad rows the TMA never writes but shifted windows read (against zero dy): make them finite
+  for (uint32_t i = threadIdx.x * 16u; i < (uint32_t)SX * p.x_stage_bytes; i += blockDim.x * 16u)
+    *reinterpret_cast<uint4 *>(sm + (x_base - base) + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 0 && elect_one()) {
+    for (int i = 0; i < SX; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 1); }
+    for (int i = 0; i < SY; ++i) { mbar_init(y_full(i), 1); mbar_init(y_empty(i), 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    int sx = 0, px = 0, sy = 0, py = 0;
+    for (int t = tile_begin; t < tile_end; ++t) {
+      const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, n = t / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * 14, h0 = th * 8;
+      mbar_wait(y_empty(sy), py ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(y_full(sy), (uint32_t)nyg * yg_bytes);
+        for (int g = 0; g < nyg; ++g)
+          tma_load_5d(y_base + (uint32_t)sy * p.y_stage_bytes + (uint32_t)g * yg_bytes, &p.dy[p.yg_view[yg0 + g]],
+                      p.yg_c0[yg0 + g], 0, tw, h0, n, y_full(sy));
+      }
+      __syncwarp();
+      if (++sy == SY) { sy = 0; py ^= 1; }
+      mbar_wait(x_empty(sx), px ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(x_full(sx), (uint32_t)nxg * p.x_box_bytes);
+        for (int g = 0; g < nxg; ++g)
+          tma_load_4d(x_base + (uint32_t)sx * p.x_stage_bytes + (uint32_t)g * p.x_gstride, &p.x[p.xg_view[xg0 + g]],
+                      p.xg_c0[xg0 + g], w0 - 1, h0 - 1 + row_shift, n, x_full(sx));
+      }
+      __syncwarp();
+      if (++sx == SX) { sx = 0; px ^= 1; }
+    }
+  } else if (warp == 1) {
+    int sx = 0, px = 0, sy = 0, py = 0;
+    const uint32_t lx = (p.GX == 64) ? LAYOUT_SW128 : LAYOUT_SW64, ly = (p.GY == 64) ? LAYOUT_SW128 : LAYOUT_SW64;
+    const uint32_t x_hi = (((8u * xrow) >> 4) & 0x3FFFu) | (1u << 14) | (lx << 29), y_hi = (((8u * yrow) >> 4) & 0x3FFFu) | (1u << 14) | (ly << 29);
+    const uint32_t x_lbo = ((p.x_gstride >> 4) & 0x3FFFu) << 16, y_lbo = ((yg_bytes >> 4) & 0x3FFFu) << 16;
+    const uint32_t x_kstep = (16u * xrow) >> 4, y_kstep = (16u * yrow) >> 4;
+    for (int t = tile_begin; t < tile_end; ++t) {
+      mbar_wait(y_full(sy), py);
+      mbar_wait(x_full(sx), px);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t y_lo = (((y_base + (uint32_t)sy * p.y_stage_bytes) & 0x3FFFFu) >> 4) | y_lbo;
+        const uint32_t x_lo = (((x_base + (uint32_t)sx * p.x_stage_bytes) & 0x3FFFFu) >> 4) | x_lbo;
+        const uint32_t first = (t == tile_begin) ? 0u : 1u;
+        for (int tp = 0; tp < p.TG; ++tp) {
+          const uint32_t off_rows = (p.TG == 9) ? (uint32_t)((tp / 3) * 16 + tp % 3) : (uint32_t)tp;
+          const uint32_t x_t = x_lo + ((off_rows * xrow) >> 4);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t ad = ((uint64_t)x_hi << 32) | (uint64_t)(x_t + k * x_kstep);
+            const uint64_t bd = ((uint64_t)y_hi << 32) | (uint64_t)(y_lo + k * y_kstep);
+            umma_bf16(tmem_base + (uint32_t)(tp * p.BN), ad, bd, p.idesc, first | (uint32_t)k);
+          }
+        }
+        tc_commit(x_empty(sx));
+        tc_commit(y_empty(sy));
+      }
+      __syncwarp();
+      if (++sx == SX) { sx = 0; px ^= 1; }
+      if (++sy == SY) { sy = 0; py ^= 1; }
+    }
+    if (elect_one()) tc_commit(acc_full);
+    __syncwarp();
+  } else {
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    const int g = row / p.GX;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    if (tile_end > tile_begin) {
+      const bool row_ok = g < nxg;
+      int ci = 0;
+      if (row_ok) ci = p.x_cstart[p.xg_view[xg0 + g]] + p.xg_c0[xg0 + g] + (row % p.GX);
+      for (int tp = 0; tp < p.TG; ++tp) {
+        const int tap = (p.TG == 9) ? tp : (tg * 3 + tp);
+        for (int cc = 0; cc < nyg * p.GY; cc += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(tp * p.BN + cc), r);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int yg = cc / p.GY;
+            const int co = p.y_cstart[p.yg_view[yg0 + yg]] + p.yg_c0[yg0 + yg] + (cc % p.GY);
+            float *dst = p.dw + ((long long)tap * p.Cout + co) * p.Cin + ci;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(dst + (long long)i * p.Cin, __uint_as_float(r[i]));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
+}
+
 static bool tma_ok(const View &v) {
   return (((uintptr_t)v.ptr) % 16 == 0) && ((v.sn * 2) % 16 == 0) && ((v.sh * 2) % 16 == 0) && ((v.sw * 2) % 16 == 0) &&
          v.sw > 0 && v.sh > 0 && v.sn > 0;
 }
 
+static int wgrad_tc2(int N, int H, int W, const ViewList &xs, const ViewList &dys, float *dw, cudaStream_t st) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return KS_EDRIVER;
+  WgradTc2Params p;
+  p.GX = 64; p.GY = 64;
+  for (int i = 0; i < xs.n; ++i) { if (xs.v[i].C % 32 || !tma_ok(xs.v[i])) return KS_EUNSUPPORTED; if (xs.v[i].C % 64) p.GX = 32; }
+  for (int i = 0; i < dys.n; ++i) { if (dys.v[i].C % 32 || !tma_ok(dys.v[i])) return KS_EUNSUPPORTED; if (dys.v[i].C % 64) p.GY = 32; }
+  p.n_xg = 0; p.n_yg = 0;
+  for (int i = 0; i < xs.n; ++i) for (int c0 = 0; c0 < xs.v[i].C; c0 += p.GX) { if (p.n_xg >= 64) return KS_EUNSUPPORTED; p.xg_view[p.n_xg] = (unsigned char)i; p.xg_c0[p.n_xg] = (short)c0; ++p.n_xg; }
+  for (int i = 0; i < dys.n; ++i) for (int c0 = 0; c0 < dys.v[i].C; c0 += p.GY) { if (p.n_yg >= 64) return KS_EUNSUPPORTED; p.yg_view[p.n_yg] = (unsigned char)i; p.yg_c0[p.n_yg] = (short)c0; ++p.n_yg; }
+  for (int i = 0; i <= KS_MAX_VIEWS; ++i) { p.x_cstart[i] = xs.cstart[i]; p.y_cstart[i] = dys.cstart[i]; }
+  p.Cin = xs.cstart[xs.n]; p.Cout = dys.cstart[dys.n];
+  p.MG = 128 / p.GX;
+  p.m_tiles = (p.n_xg + p.MG - 1) / p.MG;
+  // N tile: 9 accumulators need 9*BN <= 512 TMEM columns, 3 need 3*BN <= 512
+  int ng_max = (p.n_yg * p.GY <= 32) ? 1 : 128 / p.GY;      // BN <= 32 (all nine taps) or BN <= 128 (one kernel row per CTA)
+  if (ng_max < 1) ng_max = 1;
+  p.n_tiles = (p.n_yg + ng_max - 1) / ng_max;
+  p.NG = (p.n_yg + p.n_tiles - 1) / p.n_tiles;
+  p.BN = p.NG * p.GY;
+  p.TG = (9 * p.BN <= 512) ? 9 : 3;
+  if (p.TG * p.BN > 512) return KS_EUNSUPPORTED;
+  p.tap_groups = 9 / p.TG;
+  p.N = N; p.H = H; p.W = W;
+  p.tiles_w = W / 14; p.tiles_h = (H + 7) / 8;
+  const long long tt = (long long)p.tiles_w * p.tiles_h * N;
+  if (tt > 0x7fffffffLL) return KS_EUNSUPPORTED;
+  p.total_tiles = (int)tt;
+  const int items = p.m_tiles * p.n_tiles * p.tap_groups;
+  int splits = (kNumSMs * 2 + items - 1) / items;
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  p.splits = splits;
+  const int box_rows = (p.TG == 9) ? 10 : 8;
+  const uint32_t xrow = p.GX * 2u;
+  p.x_box_bytes = (uint32_t)box_rows * 16u * xrow;
+  p.x_gstride = (((uint32_t)(box_rows * 16 + 2) * xrow + 1023u) / 1024u) * 1024u;
+  p.x_stage_bytes = (uint32_t)p.MG * p.x_gstride;
+  p.y_stage_bytes = (uint32_t)p.BN * 256u;
+  uint32_t cols = 32; while (cols < (uint32_t)(p.TG * p.BN)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.idesc = make_idesc_bf16(128, p.BN, 1, 1);
+  int SX = 3, SY = 3;
+  auto bytes = [&](int sx, int sy) { return (size_t)sx * p.x_stage_bytes + (size_t)sy * p.y_stage_bytes + 1024 + 256; };
+  const size_t budget = 220 * 1024;
+  while (bytes(SX, SY) > budget && SY > 2) --SY;
+  while (bytes(SX, SY) > budget && SX > 2) --SX;
+  if (bytes(SX, SY) > budget) return KS_EUNSUPPORTED;
+  p.SX = SX; p.SY = SY;
+  p.dw = dw;
+  for (int i = 0; i < xs.n; ++i) {
+    int rc = encode_act_map(&p.x[i], xs.v[i], N, H, W, p.GX, 16, box_rows, p.GX == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < dys.n; ++i) {
+    const View &v = dys.v[i];
+    cuuint64_t dims[5] = {(cuuint64_t)v.C, 14, (cuuint64_t)(W / 14), (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sw * 2 * 14, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.GY, 16, 1, 8, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&p.dy[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void *)v.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     p.GY == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return KS_EDRIVER;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  wgrad_tc2_kernel<<<dim3(items, splits), 192, bytes(SX, SY), st>>>(p);
+  return (int)cudaGetLastError();
+}
+
 int wgrad_tc(int N, int H, int W, int ksize, const ViewList &xs, const ViewList &dys, float *dw, cudaStream_t st) {
   if (g_opt.tc_disable || g_opt.wgrad_tc_disable) return KS_EUNSUPPORTED;
+  if (ksize == 3 && W % 14 == 0 && !g_opt.v1) {
+    const int rc = wgrad_tc2(N, H, W, xs, dys, dw, st);
+    if (rc != KS_EUNSUPPORTED) return rc;
+  }
   WgradTcParams p;
   p.GX = 64; p.GY = 64;
   for (int i = 0; i < xs.n; ++i) { if (xs.v[i].C % 32 || !tma_ok(xs.v[i])) return KS_EUNSUPPORTED; if (xs.v[i].C % 64) p.GX = 32; }
