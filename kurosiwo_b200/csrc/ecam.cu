@@ -75,16 +75,26 @@ ecam_pool_kernel(ViewList xs, int J, int Cb, int H, int W, float *pooled, unsign
       }
     }
   }
-  if (any) {
+  // reduce over the pixel lanes of the warp first (lanes sharing tx), then one smem atomic per warp and channel
+  const int lane = threadIdx.x & 31;
+  (void)any;
 #pragma unroll
-    for (int j = 0; j <= kMaxJ; ++j) {
-      const int jj = (j == kMaxJ) ? J : j;
-      if (j < J || j == kMaxJ) {
+  for (int j = 0; j <= kMaxJ; ++j) {
+    const int jj = (j == kMaxJ) ? J : j;
+    if (j < J || j == kMaxJ) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < 8; ++k) {
+        float sv = sum[j][k];
+        unsigned long long mv = pack_max(best[j][k], bidx[j][k]);
+        for (int o = CVb; o < 32; o <<= 1) {
+          sv += __shfl_xor_sync(0xffffffffu, sv, o);
+          const unsigned long long ov = __shfl_xor_sync(0xffffffffu, mv, o);
+          mv = ov > mv ? ov : mv;
+        }
+        if (lane < CVb && ty < rows) {
           const int c = jj * Cb + tx * 8 + k;
-          atomicAdd(&ssum[c], sum[j][k]);
-          atomicMax(&smax[c], pack_max(best[j][k], bidx[j][k]));
+          atomicAdd(&ssum[c], sv);
+          atomicMax(&smax[c], mv);
         }
       }
     }
@@ -141,53 +151,51 @@ ecam_gates_kernel(int Cb, int J, int hid, int hid1, const float *__restrict__ po
 }
 
 // ---- final: gated sum + 1x1 classifier -> NCHW fp32 logits --------------------------------
-// 4 threads per pixel (one per concat source j), shuffle-reduced.
+// Thread = (pixel lane, 8-channel group g of the J*Cb concat channels): the effective weights ca*wf of the
+// group live in registers, each x access is one 16-byte load, the K partial sums are shuffle-reduced over
+// the G = J*Cb/8 lanes of a pixel.
 template <typename T, int K>
 __global__ void __launch_bounds__(256)
 ecam_final_kernel(ViewList xs, int J, int Cb, int H, int W, const float *__restrict__ gates,
                   const float *__restrict__ wf, const float *__restrict__ bf, float *logits) {
-  extern __shared__ float sm[];
-  const int n = blockIdx.y, CC = J * Cb, CT = (J + 1) * Cb;
-  float *weff = sm;             // [K][CC]
-  float *cst = sm + K * CC;     // [K]
-  const float *g = gates + (size_t)n * CT;
-  for (int i = threadIdx.x; i < K * CC; i += blockDim.x) weff[i] = wf[i] * g[i % CC];
-  __syncthreads();
-  if (threadIdx.x < K) {
-    float s = bf[threadIdx.x];
-    for (int c = 0; c < CC; ++c) s += weff[threadIdx.x * CC + c] * g[CC + (c % Cb)];
-    cst[threadIdx.x] = s;
+  const int n = blockIdx.y, CC = J * Cb, CT = (J + 1) * Cb, HW = H * W;
+  const int G = CC / 8, rows = blockDim.x / G;          // G is a power of two <= 32 (checked by the launcher)
+  const int g = threadIdx.x % G, ty = threadIdx.x / G;
+  const int c0 = g * 8, j = c0 / Cb, cb0 = c0 % Cb;
+  const float *gt = gates + (size_t)n * CT;
+  float we[K][8], cst[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { we[k][i] = wf[k * CC + c0 + i] * gt[c0 + i]; part += we[k][i] * gt[CC + cb0 + i]; }
+    for (int o = 1; o < G; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    cst[k] = part + bf[k];
   }
-  __syncthreads();
-  const int HW = H * W;
-  const int j = threadIdx.x & 3;
-  for (int p = blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2); p < ((HW + 63) / 64) * 64; p += gridDim.x * (blockDim.x >> 2)) {
+  const View &xv = xs.v[j];
+  const T *xp = reinterpret_cast<const T *>(xv.ptr) + (long long)n * xv.sn + cb0;
+  const int pmax = ((HW + rows - 1) / rows) * rows;
+  for (int p = blockIdx.x * rows + ty; p < pmax; p += gridDim.x * rows) {
     float acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.f;
     const bool ok = p < HW;
-    if (ok && j < J) {
+    if (ok) {
       const int h = p / W, w = p % W;
-      for (int c0 = 0; c0 < Cb; c0 += 8) {
-        float f[8]; ld8(vptr<T>(xs.v[j], n, h, w, c0), f);
+      float f[8]; ld8(xp + (long long)h * xv.sh + (long long)w * xv.sw, f);
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const float *wk = weff + k * CC + j * Cb + c0;
+      for (int k = 0; k < K; ++k)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[k] = fmaf(f[i], wk[i], acc[k]);
-        }
-      }
+        for (int i = 0; i < 8; ++i) acc[k] = fmaf(f[i], we[k][i], acc[k]);
     }
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
-      acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
-    }
-    if (ok && j < K) {
-      float v = acc[0];
+    for (int k = 0; k < K; ++k)
+      for (int o = 1; o < G; o <<= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    if (ok && g < K) {
+      float v = acc[0] + cst[0];
 #pragma unroll
-      for (int k = 1; k < K; ++k) if (j == k) v = acc[k];
-      logits[((size_t)n * K + j) * HW + p] = v + cst[j];
+      for (int k = 1; k < K; ++k) if (g == k) v = acc[k] + cst[k];
+      logits[((size_t)n * K + g) * HW + p] = v;
     }
   }
 }
@@ -200,55 +208,48 @@ ecam_bwd_reduce_kernel(ViewList xs, int J, int Cb, int H, int W, const float *__
   const int n = blockIdx.y, CC = J * Cb, HW = H * W, RT = K * CC + K;
   for (int i = threadIdx.x; i < RT; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
-  const int CVb = Cb / 8, rows = blockDim.x / CVb;
-  const int tx = threadIdx.x % CVb, ty = threadIdx.x / CVb;
-  float B[K][kMaxJ][8], D[K];
+  const int G = CC / 8, rows = blockDim.x / G;
+  const int g = threadIdx.x % G, ty = threadIdx.x / G;
+  const int c0 = g * 8, j = c0 / Cb, cb0 = c0 % Cb;
+  const View &xv = xs.v[j];
+  const T *xp = reinterpret_cast<const T *>(xv.ptr) + (long long)n * xv.sn + cb0;
+  float B[K][8], D[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     D[k] = 0.f;
 #pragma unroll
-    for (int j = 0; j < kMaxJ; ++j)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) B[k][j][i] = 0.f;
+    for (int i = 0; i < 8; ++i) B[k][i] = 0.f;
   }
-  bool any = false;
-  if (ty < rows) {
-    for (int p = blockIdx.x * rows + ty; p < HW; p += gridDim.x * rows) {
-      any = true;
-      const int h = p / W, w = p % W;
-      float dl[K];
+  for (int p = blockIdx.x * rows + ty; p < HW; p += gridDim.x * rows) {
+    const int h = p / W, w = p % W;
+    float dl[K];
 #pragma unroll
-      for (int k = 0; k < K; ++k) { dl[k] = __ldg(dlogits + ((size_t)n * K + k) * HW + p); D[k] += dl[k]; }
+    for (int k = 0; k < K; ++k) { dl[k] = __ldg(dlogits + ((size_t)n * K + k) * HW + p); D[k] += dl[k]; }
+    float f[8]; ld8(xp + (long long)h * xv.sh + (long long)w * xv.sw, f);
 #pragma unroll
-      for (int j = 0; j < kMaxJ; ++j) {
-        if (j < J) {
-          float f[8]; ld8(vptr<T>(xs.v[j], n, h, w, tx * 8), f);
+    for (int k = 0; k < K; ++k)
 #pragma unroll
-          for (int k = 0; k < K; ++k)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) B[k][j][i] = fmaf(dl[k], f[i], B[k][j][i]);
-        }
-      }
-    }
+      for (int i = 0; i < 8; ++i) B[k][i] = fmaf(dl[k], f[i], B[k][i]);
   }
-  if (any) {
+  // lanes of a warp that share g (pixel lanes) are combined by shuffles, then one smem atomic per warp and value
+  const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
+  for (int k = 0; k < K; ++k) {
 #pragma unroll
-      for (int j = 0; j < kMaxJ; ++j)
-        if (j < J) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) atomicAdd(&sacc[k * CC + j * Cb + tx * 8 + i], B[k][j][i]);
-        }
-      if (tx == 0) atomicAdd(&sacc[K * CC + k], D[k]);
+    for (int i = 0; i < 8; ++i) {
+      float v = B[k][i];
+      for (int o = G; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane < G) atomicAdd(&sacc[k * CC + c0 + i], v);
     }
+    float d = D[k];
+    for (int o = G; o < 32; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (lane == 0) atomicAdd(&sacc[K * CC + k], d);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < RT; i += blockDim.x) atomicAdd(red + (size_t)n * RT + i, (double)sacc[i]);
 }
 
-// ---- gates backward: single block, loops over samples (deterministic) ----------------------
-// smem layout helper
+// ---- gates backward: one block per sample; weight gradients are combined with fp32 atomics ----------
 __global__ void __launch_bounds__(256)
 ecam_gates_bwd_kernel(int N, int Cb, int J, int hid, int hid1, int K,
                       const float *__restrict__ pooled, const float *__restrict__ hidden,
@@ -256,143 +257,122 @@ ecam_gates_bwd_kernel(int N, int Cb, int J, int hid, int hid1, int K,
                       const float *__restrict__ wf, const float *__restrict__ w_fc1, const float *__restrict__ w_fc2,
                       const float *__restrict__ w1_fc1, const float *__restrict__ w1_fc2,
                       float *dpooled, float *dwf, float *dbf, float *dw_fc1, float *dw_fc2,
-                      float *dw1_fc1, float *dw1_fc2, int accumulate) {
+                      float *dw1_fc1, float *dw1_fc2) {
   extern __shared__ float sm[];
   const int CC = J * Cb, CT = (J + 1) * Cb, HT = hid + hid1, RT = K * CC + K;
-  // accumulators (over n) in smem
-  float *a_wf = sm;                       // K*CC
-  float *a_bf = a_wf + K * CC;            // K
-  float *a_fc1 = a_bf + K;                // hid*CC
-  float *a_fc2 = a_fc1 + hid * CC;        // CC*hid
-  float *a1_fc1 = a_fc2 + CC * hid;       // hid1*Cb
-  float *a1_fc2 = a1_fc1 + hid1 * Cb;     // Cb*hid1
-  float *ds = a1_fc2 + Cb * hid1;         // CT   (d pre-sigmoid)
-  float *dh = ds + CT;                    // 2*HT (d hidden pre-relu: avg | max)
-  const int nacc = (int)(ds - sm);
-  for (int i = threadIdx.x; i < nacc; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  for (int n = 0; n < N; ++n) {
-    const double *R = red + (size_t)n * RT;
-    const float *g = gates + (size_t)n * CT;
-    const float *avg = pooled + ((size_t)n * 2 + 0) * CT, *mx = pooled + ((size_t)n * 2 + 1) * CT;
-    const float *ha = hidden + ((size_t)n * 2 + 0) * HT, *hm = hidden + ((size_t)n * 2 + 1) * HT;
-    // d_ca, d_ca1 -> d pre-sigmoid; classifier grads
-    for (int c = threadIdx.x; c < CC; c += blockDim.x) {
-      const float ca1 = g[CC + (c % Cb)];
-      float dca = 0.f;
-      for (int k = 0; k < K; ++k) {
-        const float A = (float)R[k * CC + c] + ca1 * (float)R[K * CC + k];
-        dca += wf[k * CC + c] * A;
-        a_wf[k * CC + c] += g[c] * A;
-      }
-      ds[c] = dca * g[c] * (1.f - g[c]);
+  float *ds = sm;            // CT   (d pre-sigmoid)
+  float *dh = ds + CT;       // 2*HT (d hidden pre-relu: avg | max)
+  const int n = blockIdx.x;
+  const double *R = red + (size_t)n * RT;
+  const float *g = gates + (size_t)n * CT;
+  const float *avg = pooled + ((size_t)n * 2 + 0) * CT, *mx = pooled + ((size_t)n * 2 + 1) * CT;
+  const float *ha = hidden + ((size_t)n * 2 + 0) * HT, *hm = hidden + ((size_t)n * 2 + 1) * HT;
+  for (int c = threadIdx.x; c < CC; c += blockDim.x) {
+    const float ca1 = g[CC + (c % Cb)];
+    float dca = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float A = (float)R[k * CC + c] + ca1 * (float)R[K * CC + k];
+      dca += wf[k * CC + c] * A;
+      if (dwf) atomicAdd(dwf + k * CC + c, g[c] * A);
     }
-    for (int cb = threadIdx.x; cb < Cb; cb += blockDim.x) {
-      float d = 0.f;
-      for (int j = 0; j < J; ++j) {
-        const int c = j * Cb + cb;
-        float t = 0.f;
-        for (int k = 0; k < K; ++k) t += wf[k * CC + c] * (float)R[K * CC + k];
-        d += g[c] * t;
-      }
-      const float gg = g[CC + cb];
-      ds[CC + cb] = d * gg * (1.f - gg);
-    }
-    if (threadIdx.x < K) a_bf[threadIdx.x] += (float)R[K * CC + threadIdx.x];
-    __syncthreads();
-    // hidden grads: d_relu[q] = sum_c ds[c]*w2[c][q]
-    for (int q = threadIdx.x; q < HT; q += blockDim.x) {
-      float s = 0.f;
-      if (q < hid) { for (int c = 0; c < CC; ++c) s += ds[c] * w_fc2[c * hid + q]; }
-      else { const int qq = q - hid; for (int c = 0; c < Cb; ++c) s += ds[CC + c] * w1_fc2[c * hid1 + qq]; }
-      dh[q] = (ha[q] > 0.f) ? s : 0.f;
-      dh[HT + q] = (hm[q] > 0.f) ? s : 0.f;
-    }
-    // fc2 weight grads: dW2[c][q] += ds[c]*(relu(ha[q])+relu(hm[q]))
-    for (int i = threadIdx.x; i < CC * hid; i += blockDim.x) {
-      const int c = i / hid, q = i % hid;
-      a_fc2[i] += ds[c] * (fmaxf(ha[q], 0.f) + fmaxf(hm[q], 0.f));
-    }
-    for (int i = threadIdx.x; i < Cb * hid1; i += blockDim.x) {
-      const int c = i / hid1, q = i % hid1;
-      a1_fc2[i] += ds[CC + c] * (fmaxf(ha[hid + q], 0.f) + fmaxf(hm[hid + q], 0.f));
-    }
-    __syncthreads();
-    // fc1 weight grads and pooled grads
-    for (int i = threadIdx.x; i < hid * CC; i += blockDim.x) {
-      const int q = i / CC, c = i % CC;
-      a_fc1[i] += dh[q] * avg[c] + dh[HT + q] * mx[c];
-    }
-    for (int i = threadIdx.x; i < hid1 * Cb; i += blockDim.x) {
-      const int q = i / Cb, c = i % Cb;
-      a1_fc1[i] += dh[hid + q] * avg[CC + c] + dh[HT + hid + q] * mx[CC + c];
-    }
-    for (int c = threadIdx.x; c < CT; c += blockDim.x) {
-      float da = 0.f, dm = 0.f;
-      if (c < CC) { for (int q = 0; q < hid; ++q) { da += dh[q] * w_fc1[q * CC + c]; dm += dh[HT + q] * w_fc1[q * CC + c]; } }
-      else { const int cb = c - CC; for (int q = 0; q < hid1; ++q) { da += dh[hid + q] * w1_fc1[q * Cb + cb]; dm += dh[HT + hid + q] * w1_fc1[q * Cb + cb]; } }
-      dpooled[((size_t)n * 2 + 0) * CT + c] = da;
-      dpooled[((size_t)n * 2 + 1) * CT + c] = dm;
-    }
-    __syncthreads();
+    ds[c] = dca * g[c] * (1.f - g[c]);
   }
-  auto flush = [&](float *dst, const float *src, int cnt) {
-    if (!dst) return;
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = (accumulate ? dst[i] : 0.f) + src[i];
-  };
-  flush(dwf, a_wf, K * CC); flush(dbf, a_bf, K);
-  flush(dw_fc1, a_fc1, hid * CC); flush(dw_fc2, a_fc2, CC * hid);
-  flush(dw1_fc1, a1_fc1, hid1 * Cb); flush(dw1_fc2, a1_fc2, Cb * hid1);
+  for (int cb = threadIdx.x; cb < Cb; cb += blockDim.x) {
+    float d = 0.f;
+    for (int j = 0; j < J; ++j) {
+      const int c = j * Cb + cb;
+      float t = 0.f;
+      for (int k = 0; k < K; ++k) t += wf[k * CC + c] * (float)R[K * CC + k];
+      d += g[c] * t;
+    }
+    const float gg = g[CC + cb];
+    ds[CC + cb] = d * gg * (1.f - gg);
+  }
+  if (threadIdx.x < K && dbf) atomicAdd(dbf + threadIdx.x, (float)R[K * CC + threadIdx.x]);
+  __syncthreads();
+  for (int q = threadIdx.x; q < HT; q += blockDim.x) {
+    float s = 0.f;
+    if (q < hid) { for (int c = 0; c < CC; ++c) s += ds[c] * w_fc2[c * hid + q]; }
+    else { const int qq = q - hid; for (int c = 0; c < Cb; ++c) s += ds[CC + c] * w1_fc2[c * hid1 + qq]; }
+    dh[q] = (ha[q] > 0.f) ? s : 0.f;
+    dh[HT + q] = (hm[q] > 0.f) ? s : 0.f;
+  }
+  if (dw_fc2) for (int i = threadIdx.x; i < CC * hid; i += blockDim.x) {
+    const int c = i / hid, q = i % hid;
+    atomicAdd(dw_fc2 + i, ds[c] * (fmaxf(ha[q], 0.f) + fmaxf(hm[q], 0.f)));
+  }
+  if (dw1_fc2) for (int i = threadIdx.x; i < Cb * hid1; i += blockDim.x) {
+    const int c = i / hid1, q = i % hid1;
+    atomicAdd(dw1_fc2 + i, ds[CC + c] * (fmaxf(ha[hid + q], 0.f) + fmaxf(hm[hid + q], 0.f)));
+  }
+  __syncthreads();
+  if (dw_fc1) for (int i = threadIdx.x; i < hid * CC; i += blockDim.x) {
+    const int q = i / CC, c = i % CC;
+    atomicAdd(dw_fc1 + i, dh[q] * avg[c] + dh[HT + q] * mx[c]);
+  }
+  if (dw1_fc1) for (int i = threadIdx.x; i < hid1 * Cb; i += blockDim.x) {
+    const int q = i / Cb, c = i % Cb;
+    atomicAdd(dw1_fc1 + i, dh[hid + q] * avg[CC + c] + dh[HT + hid + q] * mx[CC + c]);
+  }
+  for (int c = threadIdx.x; c < CT; c += blockDim.x) {
+    float da = 0.f, dm = 0.f;
+    if (c < CC) { for (int q = 0; q < hid; ++q) { da += dh[q] * w_fc1[q * CC + c]; dm += dh[HT + q] * w_fc1[q * CC + c]; } }
+    else { const int cb = c - CC; for (int q = 0; q < hid1; ++q) { da += dh[hid + q] * w1_fc1[q * Cb + cb]; dm += dh[HT + hid + q] * w1_fc1[q * Cb + cb]; } }
+    dpooled[((size_t)n * 2 + 0) * CT + c] = da;
+    dpooled[((size_t)n * 2 + 1) * CT + c] = dm;
+  }
 }
 
 // ---- backward apply: gradient of the four block outputs -------------------------------------
+// Thread = (pixel lane, 8-channel group): all per-channel coefficients (ca*wf, pool gradients, argmax pixels) in registers.
 template <typename T, int K>
 __global__ void __launch_bounds__(256)
 ecam_bwd_apply_kernel(ViewList dxs, int J, int Cb, int H, int W, const float *__restrict__ gates,
                       const float *__restrict__ wf, const float *__restrict__ dlogits,
                       const float *__restrict__ dpooled, const int *__restrict__ argmax) {
-  extern __shared__ float sm[];
   const int n = blockIdx.y, CC = J * Cb, CT = (J + 1) * Cb, HW = H * W;
-  float *weff = sm;                 // [K][CC]  ca*wf
-  float *base = weff + K * CC;      // [CC]     (d_avg_cat + d_avg_intra)/HW
-  float *dmx = base + CC;           // [CT]     d_max (cat | intra)
-  int *amx = reinterpret_cast<int *>(dmx + CT);  // [CT]
-  const float *g = gates + (size_t)n * CT;
+  const int G = CC / 8, rows = blockDim.x / G;
+  const int g = threadIdx.x % G, ty = threadIdx.x / G;
+  const int c0 = g * 8, j = c0 / Cb, cb0 = c0 % Cb;
+  const float *gt = gates + (size_t)n * CT;
   const float *da = dpooled + ((size_t)n * 2 + 0) * CT, *dm = dpooled + ((size_t)n * 2 + 1) * CT;
+  const int *am = argmax + (size_t)n * CT;
   const float inv = 1.0f / (float)HW;
-  for (int i = threadIdx.x; i < K * CC; i += blockDim.x) weff[i] = wf[i] * g[i % CC];
-  for (int c = threadIdx.x; c < CC; c += blockDim.x) base[c] = (da[c] + da[CC + (c % Cb)]) * inv;
-  for (int c = threadIdx.x; c < CT; c += blockDim.x) { dmx[c] = dm[c]; amx[c] = argmax[(size_t)n * CT + c]; }
-  __syncthreads();
-  const int j = threadIdx.x & 3;
-  for (int p = blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2); p < HW; p += gridDim.x * (blockDim.x >> 2)) {
-    if (j >= J) continue;
+  float we[K][8], base[8], dmc[8], dmi[8]; int amc[8], ami[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) we[k][i] = wf[k * CC + c0 + i] * gt[c0 + i];
+    base[i] = (da[c0 + i] + da[CC + cb0 + i]) * inv;
+    dmc[i] = dm[c0 + i]; amc[i] = am[c0 + i];
+    dmi[i] = dm[CC + cb0 + i]; ami[i] = am[CC + cb0 + i];
+  }
+  const View &dv = dxs.v[j];
+  T *dp = reinterpret_cast<T *>(dv.ptr) + (long long)n * dv.sn + cb0;
+  for (int p = blockIdx.x * rows + ty; p < HW; p += gridDim.x * rows) {
     const int h = p / W, w = p % W;
     float dl[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) dl[k] = __ldg(dlogits + ((size_t)n * K + k) * HW + p);
-    for (int c0 = 0; c0 < Cb; c0 += 8) {
-      float o[8];
+    float o[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int cb = c0 + i, c = j * Cb + cb;
-        float v = base[c];
+    for (int i = 0; i < 8; ++i) {
+      float v = base[i];
 #pragma unroll
-        for (int k = 0; k < K; ++k) v = fmaf(weff[k * CC + c], dl[k], v);
-        if (amx[c] == p) v += dmx[c];
-        if (amx[CC + cb] == p) v += dmx[CC + cb];
-        o[i] = v;
-      }
-      T *dst = reinterpret_cast<T *>(dxs.v[j].ptr) + ((long long)n * dxs.v[j].sn + (long long)h * dxs.v[j].sh + (long long)w * dxs.v[j].sw + c0);
-      st8(dst, o);
+      for (int k = 0; k < K; ++k) v = fmaf(we[k][i], dl[k], v);
+      if (amc[i] == p) v += dmc[i];
+      if (ami[i] == p) v += dmi[i];
+      o[i] = v;
     }
+    st8(dp + (long long)h * dv.sh + (long long)w * dv.sw, o);
   }
 }
 
 static int check_views(const ks_view_t *xs, int J, int &Cb, int esize) {
   if (!xs || J < 1 || J > kMaxJ) return KS_EINVAL;
   Cb = xs[0].C;
-  if (Cb % 8 != 0 || Cb > 64) return KS_EUNSUPPORTED;
+  if (Cb % 8 != 0 || Cb > 64 || ((Cb / 8) & (Cb / 8 - 1)) != 0) return KS_EUNSUPPORTED;
+  if ((J * Cb / 8) > 32 || ((J * Cb / 8) & (J * Cb / 8 - 1)) != 0) return KS_EUNSUPPORTED;   // lanes per pixel must be a power of two
   for (int j = 0; j < J; ++j) {
     if (xs[j].C != Cb || !xs[j].ptr) return KS_EINVAL;
     if (((uintptr_t)xs[j].ptr % 16) || (xs[j].sn * esize) % 16 || (xs[j].sh * esize) % 16 || (xs[j].sw * esize) % 16) return KS_EUNSUPPORTED;
@@ -441,9 +421,10 @@ extern "C" int ks_ecam_final(int dtype, int N, int H, int W, const ks_view_t *xs
   int Cb; int rc = check_views(xs, J, Cb, dtype == KS_F32 ? 4 : 2); if (rc) return rc;
   ViewList vl; rc = make_view_list(xs, J, vl); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  int chunks = (H * W + 64 * 8 - 1) / (64 * 8); if (chunks < 1) chunks = 1;
+  const int rows_f = 256 / (J * Cb / 8);
+  int chunks = (H * W + rows_f * 32 - 1) / (rows_f * 32); if (chunks < 1) chunks = 1;
   const int cap = (kNumSMs * 16 + N - 1) / N; if (chunks > cap) chunks = cap;
-  const size_t smem = sizeof(float) * (size_t)(3 * J * Cb + 3);
+  const size_t smem = 0;
   if (dtype == KS_F32) ecam_final_kernel<float, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, gates, wf, bf, logits);
   else if (dtype == KS_BF16) ecam_final_kernel<__nv_bfloat16, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, gates, wf, bf, logits);
   else return KS_EINVAL;
@@ -459,8 +440,8 @@ extern "C" int ks_ecam_bwd_reduce(int dtype, int N, int H, int W, const ks_view_
   cudaStream_t st = (cudaStream_t)stream;
   const int RT = K * J * Cb + K;
   cudaError_t e = cudaMemsetAsync(red, 0, sizeof(double) * (size_t)N * RT, st); if (e) return (int)e;
-  const int rows = 256 / (Cb / 8);
-  int chunks = (H * W + rows * 16 - 1) / (rows * 16); if (chunks < 1) chunks = 1;
+  const int rows = 256 / (J * Cb / 8);
+  int chunks = (H * W + rows * 32 - 1) / (rows * 32); if (chunks < 1) chunks = 1;
   const int cap = (kNumSMs * 8 + N - 1) / N; if (chunks > cap) chunks = cap;
   const size_t smem = sizeof(float) * (size_t)RT;
   if (dtype == KS_F32) ecam_bwd_reduce_kernel<float, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, dlogits, red);
@@ -477,10 +458,15 @@ extern "C" int ks_ecam_gates_bwd(int N, int Cb, int J, int hid, int hid1, int K,
   KS_CHECK_ARG(N > 0 && Cb > 0 && J > 0 && hid > 0 && hid1 > 0 && K > 0);
   KS_CHECK_ARG(pooled && hidden && gates && red && wf && w_fc1 && w_fc2 && w1_fc1 && w1_fc2 && dpooled);
   const int CC = J * Cb, CT = (J + 1) * Cb, HT = hid + hid1;
-  const size_t smem = sizeof(float) * (size_t)(K * CC + K + 2 * hid * CC + 2 * hid1 * Cb + CT + 2 * HT);
-  if (smem > 48 * 1024) return KS_EUNSUPPORTED;
-  ecam_gates_bwd_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(N, Cb, J, hid, hid1, K, pooled, hidden, gates, red, wf,
-      w_fc1, w_fc2, w1_fc1, w1_fc2, dpooled, dwf, dbf, dw_fc1, dw_fc2, dw1_fc1, dw1_fc2, accumulate);
+  const size_t smem = sizeof(float) * (size_t)(CT + 2 * HT);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) {
+    struct { float *p; size_t n; } z[6] = {{dwf, (size_t)K * CC}, {dbf, (size_t)K}, {dw_fc1, (size_t)hid * CC}, {dw_fc2, (size_t)CC * hid},
+                                           {dw1_fc1, (size_t)hid1 * Cb}, {dw1_fc2, (size_t)Cb * hid1}};
+    for (auto &e : z) if (e.p) { cudaError_t er = cudaMemsetAsync(e.p, 0, sizeof(float) * e.n, st); if (er != cudaSuccess) return (int)er; }
+  }
+  ecam_gates_bwd_kernel<<<N, 256, smem, st>>>(N, Cb, J, hid, hid1, K, pooled, hidden, gates, red, wf,
+      w_fc1, w_fc2, w1_fc1, w1_fc2, dpooled, dwf, dbf, dw_fc1, dw_fc2, dw1_fc1, dw1_fc2);
   KS_LAUNCH_RET();
 }
 
@@ -493,10 +479,10 @@ extern "C" int ks_ecam_bwd_apply(int dtype, int N, int H, int W, int J, int Cb, 
   if (Cb2 != Cb) return KS_EINVAL;
   ViewList vl; rc = make_view_list(dxs, J, vl); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  int chunks = (H * W + 64 * 8 - 1) / (64 * 8); if (chunks < 1) chunks = 1;
+  const int rows_a = 256 / (J * Cb / 8);
+  int chunks = (H * W + rows_a * 32 - 1) / (rows_a * 32); if (chunks < 1) chunks = 1;
   const int cap = (kNumSMs * 16 + N - 1) / N; if (chunks > cap) chunks = cap;
-  const int CC = J * Cb, CT = (J + 1) * Cb;
-  const size_t smem = sizeof(float) * (size_t)(3 * CC + CC + CT) + sizeof(int) * (size_t)CT;
+  const size_t smem = 0;
   if (dtype == KS_F32) ecam_bwd_apply_kernel<float, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, gates, wf, dlogits, dpooled, argmax);
   else if (dtype == KS_BF16) ecam_bwd_apply_kernel<__nv_bfloat16, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, gates, wf, dlogits, dpooled, argmax);
   else return KS_EINVAL;
