@@ -69,6 +69,16 @@ int ks_permute_cast(int src_dtype, const void *src, int dst_dtype, void *dst,
                     int64_t s0, int64_t s1, int64_t s2, int64_t s3,
                     int accumulate, void *stream);
 
+/* One launch for a table of permute/cast jobs (all weight packs / gradient unpacks of a step).
+ * jobs_dev: device array; chunks_dev: device int32 pairs {job index, first dst element}, one per CTA (4096 elements each). */
+typedef struct ks_permute_job {
+  const void *src;
+  void *dst;
+  int64_t total, s0, s1, s2, s3;
+  int32_t d1, d2, d3, src_dtype, dst_dtype, accumulate;
+} ks_permute_job_t;
+int ks_permute_cast_batched(const ks_permute_job_t *jobs_dev, const int32_t *chunks_dev, int n_chunks, void *stream);
+
 /* ---- convolution engine ------------------------------------------------ */
 /* out[n,h,w,co] (+)= bias[co] + sum_{tap,src,ci} x_src[n,h+dy,w+dx,ci] * w[tap][co][ci_global]
  * ksize 3: taps (dy,dx) in row-major order over {-1,0,1}^2, zero padding 1.
@@ -121,9 +131,12 @@ int ks_bn_act(int dtype, int N, int H, int W, const ks_view_t *y,
 
 /* BN backward pass 1: g = dout * mask; sums[0][c] += sum g, sums[1][c] += sum g*xhat.
  * out != NULL: mask = (out > 0) and the masked gradient g is written back over `dout` (pass 2 and the
- *              identity path re-use it); out == NULL: mask = (y*scale+shift > 0), nothing is written. */
+ *              identity path re-use it); out == NULL: mask = (y*scale+shift > 0), nothing is written.
+ * dpool != NULL (needs out): the 2x2/s2 max-pool backward is folded in: g = (dout + dpool routed to the first
+ *              maximum of each window of `out`) * (out > 0)   (aten max_pool2d_with_indices_backward). */
 int ks_bn_bwd_reduce(int dtype, int N, int H, int W, const ks_view_t *dout,
-                     const ks_view_t *out, const ks_view_t *y, const float *scale, const float *shift,
+                     const ks_view_t *out, const ks_view_t *y, const ks_view_t *dpool,
+                     const float *scale, const float *shift,
                      const float *mean, const float *rstd, double *sums, void *stream);
 
 /* BN backward pass 2: dy = gamma*rstd*(g' - sum_g/M - xhat*sum_gx/M) (+ add), with g' = g if `premasked`

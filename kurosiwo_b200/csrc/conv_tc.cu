@@ -610,8 +610,8 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
   p.resident = 0;
   // Measured on B200 (scripts/bench_layers.py): keeping the weights resident pays when the MMAs are short
   // (BN <= 32: one [BN x BK] tile is only 2-4 KB, so per-tap barrier round trips dominate) or when K is tiny
-  // (Cin <= 32, the level-0 data-gradient convs); otherwise streamed weights with >1 CTA per SM win.
-  const bool want_res = g_opt.no_resident ? false : (g_opt.mt < 0 ? true : (p.BN <= 32 || Cin <= 32));
+  // (Cin <= 32, the level-0 data-gradient convs; 1x1 transposed-conv phases); otherwise streamed weights with >1 CTA per SM win.
+  const bool want_res = g_opt.no_resident ? false : (g_opt.mt < 0 ? true : (p.BN <= 32 || Cin <= 32 || ksize == 1));
   if (!v1 && want_res && w_bytes + 2 * p.a_tile_bytes + fixed <= budget) {
     p.resident = 1;
     MT = g_opt.mt > 0 ? g_opt.mt : 2;

@@ -28,6 +28,31 @@ __global__ void permute_cast_kernel(const TS *__restrict__ src, TD *__restrict__
   }
 }
 
+// Batched variant: one launch for a whole table of permute/cast jobs (all weight packs of a step, or all gradient
+// unpacks).  `chunks[i] = {job, first element}`; every block processes up to 4096 consecutive dst elements of one job.
+__global__ void __launch_bounds__(256)
+permute_cast_batched_kernel(const ks_permute_job_t *__restrict__ jobs, const int2 *__restrict__ chunks) {
+  const int2 ch = chunks[blockIdx.x];
+  const ks_permute_job_t j = jobs[ch.x];
+  const long long end = min((long long)j.total, (long long)ch.y + 4096);
+  for (long long i = ch.y + threadIdx.x; i < end; i += blockDim.x) {
+    long long r = i;
+    const int i3 = (int)(r % j.d3); r /= j.d3;
+    const int i2 = (int)(r % j.d2); r /= j.d2;
+    const int i1 = (int)(r % j.d1); r /= j.d1;
+    const long long so = r * j.s0 + i1 * j.s1 + i2 * j.s2 + i3 * j.s3;
+    float v = (j.src_dtype == KS_F32) ? reinterpret_cast<const float *>(j.src)[so]
+                                      : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(j.src)[so]);
+    if (j.dst_dtype == KS_F32) {
+      float *d = reinterpret_cast<float *>(j.dst) + i;
+      *d = j.accumulate ? (*d + v) : v;
+    } else {
+      __nv_bfloat16 *d = reinterpret_cast<__nv_bfloat16 *>(j.dst) + i;
+      *d = __float2bfloat16_rn(j.accumulate ? (__bfloat162float(*d) + v) : v);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // generic helpers for NHWC view kernels
 // ------------------------------------------------------------------------------------------
@@ -77,6 +102,44 @@ __device__ __forceinline__ void block_channel_reduce(float (&acc)[R][V], int CV,
     atomicAdd(out + (size_t)r * C + c, s);
   }
 }
+
+__device__ __forceinline__ long long pix_off(const View &v, long long p, int H, int W, bool flat) {
+  if (flat) return p * v.sw;
+  const int w = (int)(p % W); const long long r = p / W; const int h = (int)(r % H); const long long n = r / H;
+  return n * v.sn + (long long)h * v.sh + (long long)w * v.sw;
+}
+static inline bool view_flat(const ks_view_t &v, int H, int W) { return v.sh == (int64_t)W * v.sw && v.sn == (int64_t)H * v.sh; }
+
+// Raw register image of V elements: loads are issued for several pixels BEFORE any use so that each thread keeps
+// 4 (bf16) / 2 (fp32) x #tensors 16-byte requests in flight (ncu: 1-2 requests per thread gave ~50 % of HBM peak).
+template <typename T, int V> struct Raw {
+  T x[V];
+  __device__ __forceinline__ void ld(const T *p) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) x[i] = p[i];
+  }
+  __device__ __forceinline__ void get(float (&f)[V]) const {
+#pragma unroll
+    for (int i = 0; i < V; ++i) { T t = x[i]; f[i] = Cvt<T>::ld(&t); }
+  }
+};
+template <> struct Raw<__nv_bfloat16, 8> {
+  uint4 u;
+  __device__ __forceinline__ void ld(const __nv_bfloat16 *p) { u = *reinterpret_cast<const uint4 *>(p); }
+  __device__ __forceinline__ void get(float (&f)[8]) const {
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+};
+template <> struct Raw<float, 8> {
+  float4 a, b;
+  __device__ __forceinline__ void ld(const float *p) { a = *reinterpret_cast<const float4 *>(p); b = *reinterpret_cast<const float4 *>(p + 4); }
+  __device__ __forceinline__ void get(float (&f)[8]) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+};
+template <typename T> struct Unr { static constexpr int value = (sizeof(T) == 2) ? 4 : 2; };
 
 // ------------------------------------------------------------------------------------------
 // BatchNorm statistics: sums[0][c] += sum x, sums[1][c] += sum x^2
@@ -128,43 +191,6 @@ __global__ void bn_finalize_kernel(int C, double count, const double *__restrict
 // coefficients live in registers), ty = pixel lane; a warp touches (32/CV) whole pixels x C channels.
 // `flat` views (pixel stride uniform: sh == W*sw, sn == H*sh) skip the n/h/w decomposition.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ long long pix_off(const View &v, long long p, int H, int W, bool flat) {
-  if (flat) return p * v.sw;
-  const int w = (int)(p % W); const long long r = p / W; const int h = (int)(r % H); const long long n = r / H;
-  return n * v.sn + (long long)h * v.sh + (long long)w * v.sw;
-}
-static inline bool view_flat(const ks_view_t &v, int H, int W) { return v.sh == (int64_t)W * v.sw && v.sn == (int64_t)H * v.sh; }
-
-// Raw register image of V elements: loads are issued for several pixels BEFORE any use so that each thread keeps
-// 4 (bf16) / 2 (fp32) x #tensors 16-byte requests in flight (ncu: 1-2 requests per thread gave ~50 % of HBM peak).
-template <typename T, int V> struct Raw {
-  T x[V];
-  __device__ __forceinline__ void ld(const T *p) {
-#pragma unroll
-    for (int i = 0; i < V; ++i) x[i] = p[i];
-  }
-  __device__ __forceinline__ void get(float (&f)[V]) const {
-#pragma unroll
-    for (int i = 0; i < V; ++i) { T t = x[i]; f[i] = Cvt<T>::ld(&t); }
-  }
-};
-template <> struct Raw<__nv_bfloat16, 8> {
-  uint4 u;
-  __device__ __forceinline__ void ld(const __nv_bfloat16 *p) { u = *reinterpret_cast<const uint4 *>(p); }
-  __device__ __forceinline__ void get(float (&f)[8]) const {
-    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
-  }
-};
-template <> struct Raw<float, 8> {
-  float4 a, b;
-  __device__ __forceinline__ void ld(const float *p) { a = *reinterpret_cast<const float4 *>(p); b = *reinterpret_cast<const float4 *>(p + 4); }
-  __device__ __forceinline__ void get(float (&f)[8]) const {
-    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-  }
-};
-template <typename T> struct Unr { static constexpr int value = (sizeof(T) == 2) ? 4 : 2; };
 
 // out = relu(y*scale+shift (+res)), optional fused 2x2 max-pool output
 template <typename T, int V, bool POOL>
@@ -304,6 +330,72 @@ bn_bwd_reduce_kernel(View dout, View out, View y, int N, int H, int W, const flo
   block_channel_reduce<2, V>(acc, CV, rows, C, sums, smem);
 }
 
+// pass 1 for encoder outputs: as MASK_OUT above, with the 2x2 max-pool backward folded in.  Each thread owns whole
+// pooling windows: g = (dout + [pixel is the window's first maximum] * dpool) * (out > 0), written back over dout.
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_pool_kernel(View dout, View out, View y, View dpool, int N, int H, int W,
+                          const float *__restrict__ mean, const float *__restrict__ rstd, double *sums, bool flat) {
+  extern __shared__ float smem[];
+  const int C = y.C, CV = C / V, rows = blockDim.x / CV;
+  const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
+  float acc[2][V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { acc[0][i] = 0.f; acc[1][i] = 0.f; }
+  if (ty < rows) {
+    const int c = tx * V;
+    float mu[V], rs[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { mu[k] = mean[c + k]; rs[k] = rstd[c + k]; }
+    T *gp = reinterpret_cast<T *>(dout.ptr) + c;
+    const T *op = reinterpret_cast<const T *>(out.ptr) + c;
+    const T *yp = reinterpret_cast<const T *>(y.ptr) + c;
+    const T *pp = reinterpret_cast<const T *>(dpool.ptr) + c;
+    const int HP = H / 2, WP = W / 2;
+    const long long npool = (long long)N * HP * WP;
+    for (long long q = (long long)blockIdx.x * rows + ty; q < npool; q += (long long)gridDim.x * rows) {
+      const int wp = (int)(q % WP); const long long r = q / WP; const int hp = (int)(r % HP); const long long n = r / HP;
+      const long long p00 = (n * H + 2 * hp) * W + 2 * wp;
+      Raw<T, V> rg[4], ro[4], rf[4], rp;
+      rp.ld(pp + (n * dpool.sn + (long long)hp * dpool.sh + (long long)wp * dpool.sw));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long p = p00 + (i >> 1) * W + (i & 1);
+        rg[i].ld(gp + pix_off(dout, p, H, W, flat));
+        ro[i].ld(op + pix_off(out, p, H, W, flat));
+        rf[i].ld(yp + pix_off(y, p, H, W, flat));
+      }
+      float o[4][V], dp[V];
+      rp.get(dp);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ro[i].get(o[i]);
+      int am[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        int a = 0; float best = o[0][k];
+#pragma unroll
+        for (int i = 1; i < 4; ++i) if (o[i][k] > best) { best = o[i][k]; a = i; }
+        am[k] = a;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float g[V], f[V];
+        rg[i].get(g); rf[i].get(f);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float gk = g[k] + ((am[k] == i) ? dp[k] : 0.f);
+          gk = (o[i][k] > 0.f) ? gk : 0.f;
+          g[k] = gk;
+          acc[0][k] += gk;
+          acc[1][k] += gk * ((f[k] - mu[k]) * rs[k]);
+        }
+        VecIO<T, V>::st(gp + pix_off(dout, p00 + (i >> 1) * W + (i & 1), H, W, flat), g);
+      }
+    }
+  }
+  block_channel_reduce<2, V>(acc, CV, rows, C, sums, smem);
+}
+
 // pass 2: dy = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M) (+ add) = a*g + (k1*y + k0) (+ add);  `premasked`: g already masked by pass 1
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
@@ -415,7 +507,7 @@ maxpool_bwd_kernel(View x, View dpool, View dx, int N, int H, int W, int accumul
 // ------------------------------------------------------------------------------------------
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
-channel_sum_kernel(View x, int N, int H, int W, float *out) {
+channel_sum_kernel(View x, int N, int H, int W, float *out, bool flat) {
   extern __shared__ float smem[];
   const int C = x.C, CV = C / V, rows = blockDim.x / CV;
   const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
@@ -424,11 +516,19 @@ channel_sum_kernel(View x, int N, int H, int W, float *out) {
   for (int i = 0; i < V; ++i) acc[i] = 0.f;
   const long long npix = (long long)N * H * W;
   if (ty < rows) {
-    for (long long p = (long long)blockIdx.x * rows + ty; p < npix; p += (long long)gridDim.x * rows) {
-      const int w = (int)(p % W); long long r = p / W; const int h = (int)(r % H); const int n = (int)(r / H);
-      float f[V]; VecIO<T, V>::ld(vaddr<T>(x, n, h, w, tx * V), f);
+    const T *xp = reinterpret_cast<const T *>(x.ptr) + tx * V;
+    constexpr int U = 2 * Unr<T>::value;
+    const long long stride = (long long)gridDim.x * rows;
+    for (long long p0 = (long long)blockIdx.x * rows + ty; p0 < npix; p0 += stride * U) {
+      Raw<T, V> r[U];
 #pragma unroll
-      for (int i = 0; i < V; ++i) acc[i] += f[i];
+      for (int u = 0; u < U; ++u) if (p0 + u * stride < npix) r[u].ld(xp + pix_off(x, p0 + u * stride, H, W, flat));
+#pragma unroll
+      for (int u = 0; u < U; ++u) if (p0 + u * stride < npix) {
+        float f[V]; r[u].get(f);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] += f[i];
+      }
     }
     for (int i = 0; i < V; ++i) smem[ty * C + tx * V + i] = acc[i];
   }
@@ -535,6 +635,12 @@ extern "C" int ks_permute_cast(int src_dtype, const void *src, int dst_dtype, vo
   KS_LAUNCH_RET();
 }
 
+extern "C" int ks_permute_cast_batched(const ks_permute_job_t *jobs_dev, const int32_t *chunks_dev, int n_chunks, void *stream) {
+  KS_CHECK_ARG(jobs_dev && chunks_dev && n_chunks > 0);
+  permute_cast_batched_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(jobs_dev, reinterpret_cast<const int2 *>(chunks_dev));
+  KS_LAUNCH_RET();
+}
+
 extern "C" int ks_bn_stats(int dtype, int N, int H, int W, const ks_view_t *x, double *sums, void *stream) {
   KS_CHECK_ARG(x && x->ptr && sums && N > 0 && H > 0 && W > 0);
   const bool vec = view_vec8_ok(*x, esize_of(dtype));
@@ -584,19 +690,21 @@ extern "C" int ks_bn_act(int dtype, int N, int H, int W, const ks_view_t *y, con
 }
 
 extern "C" int ks_bn_bwd_reduce(int dtype, int N, int H, int W, const ks_view_t *dout, const ks_view_t *out,
-                                const ks_view_t *y, const float *scale, const float *shift,
+                                const ks_view_t *y, const ks_view_t *dpool, const float *scale, const float *shift,
                                 const float *mean, const float *rstd, double *sums, void *stream) {
   KS_CHECK_ARG(dout && y && mean && rstd && sums && N > 0 && H > 0 && W > 0);
   KS_CHECK_ARG(out != nullptr || (scale != nullptr && shift != nullptr));
   KS_CHECK_ARG(dout->C == y->C && (!out || out->C == y->C));
+  KS_CHECK_ARG(!dpool || (out && dpool->C == y->C && H % 2 == 0 && W % 2 == 0));
   const int es = esize_of(dtype);
-  const bool vec = view_vec8_ok(*y, es) && (!out || view_vec8_ok(*out, es)) && view_vec8_ok(*dout, es);
+  const bool vec = view_vec8_ok(*y, es) && (!out || view_vec8_ok(*out, es)) && view_vec8_ok(*dout, es) && (!dpool || view_vec8_ok(*dpool, es));
   const bool flat = view_flat(*y, H, W) && view_flat(*dout, H, W) && (!out || view_flat(*out, H, W));
   const long long npix = (long long)N * H * W;
   cudaStream_t st = (cudaStream_t)stream;
-  const View vd = to_view(*dout), vy = to_view(*y), vo = out ? to_view(*out) : vy;
-#define CALL(T, V) { int grid; size_t smem; int rc = launch_reduce_cfg<T, V>(y->C, npix, grid, smem, 2); if (rc) return rc; \
-    if (out) bn_bwd_reduce_kernel<T, V, true><<<grid, 256, smem, st>>>(vd, vo, vy, N, H, W, scale, shift, mean, rstd, sums, flat); \
+  const View vd = to_view(*dout), vy = to_view(*y), vo = out ? to_view(*out) : vy, vp = dpool ? to_view(*dpool) : vy;
+#define CALL(T, V) { int grid; size_t smem; int rc = launch_reduce_cfg<T, V>(y->C, dpool ? npix / 2 : npix, grid, smem, 2); if (rc) return rc; \
+    if (dpool) bn_bwd_reduce_pool_kernel<T, V><<<grid, 256, smem, st>>>(vd, vo, vy, vp, N, H, W, mean, rstd, sums, flat); \
+    else if (out) bn_bwd_reduce_kernel<T, V, true><<<grid, 256, smem, st>>>(vd, vo, vy, N, H, W, scale, shift, mean, rstd, sums, flat); \
     else bn_bwd_reduce_kernel<T, V, false><<<grid, 256, smem, st>>>(vd, vo, vy, N, H, W, scale, shift, mean, rstd, sums, flat); }
   KS_DISPATCH_TV(dtype, vec, CALL);
 #undef CALL
@@ -645,7 +753,7 @@ extern "C" int ks_channel_sum(int dtype, int N, int H, int W, const ks_view_t *x
   cudaStream_t st = (cudaStream_t)stream;
   if (!accumulate) { cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * x->C, st); if (e != cudaSuccess) return (int)e; }
 #define CALL(T, V) { int grid; size_t smem; int rc = launch_reduce_cfg<T, V>(x->C, npix, grid, smem, 1); if (rc) return rc; \
-    channel_sum_kernel<T, V><<<grid, 256, smem, st>>>(to_view(*x), N, H, W, out); }
+    channel_sum_kernel<T, V><<<grid, 256, smem, st>>>(to_view(*x), N, H, W, out, view_flat(*x, H, W)); }
   KS_DISPATCH_TV(dtype, vec, CALL);
 #undef CALL
   KS_LAUNCH_RET();

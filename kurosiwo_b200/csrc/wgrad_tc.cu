@@ -187,7 +187,7 @@ struct alignas(64) WgradTc2Params {
   int n_xg, n_yg, GX, GY, MG, NG, BN;
   int m_tiles, n_tiles, tap_groups, TG;
   int N, H, W, tiles_w, tiles_h, total_tiles, splits;
-  int Cin, Cout, SX, SY;
+  int Cin, Cout, SX, SY, stack3;
   uint32_t x_gstride, x_box_bytes, x_stage_bytes, y_stage_bytes, tmem_cols, idesc;
   float *dw;
 };
@@ -275,6 +275,21 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc2_kernel(const __grid_constant
         const uint32_t y_lo = (((y_base + (uint32_t)sy * p.y_stage_bytes) & 0x3FFFFu) >> 4) | y_lbo;
         const uint32_t x_lo = (((x_base + (uint32_t)sx * p.x_stage_bytes) & 0x3FFFFu) >> 4) | x_lbo;
         const uint32_t first = (t == tile_begin) ? 0u : 1u;
+        if (p.stack3) {
+          // Cin == 32: the four 32-row MN groups of the M=128 operand are the SAME halo tile shifted by 0,1,2,(3) pixels
+          // (leading-dimension byte offset = one 64-byte row), so one MMA series covers the three taps of a kernel row.
+          const uint32_t lbo1 = ((xrow >> 4) & 0x3FFFu) << 16;
+          const uint32_t x_s = (x_lo & 0xFFFFu) | lbo1;
+          for (int r = 0; r < 3; ++r) {
+            const uint32_t x_t = x_s + (((uint32_t)(r * 16) * xrow) >> 4);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint64_t ad = ((uint64_t)x_hi << 32) | (uint64_t)(x_t + k * x_kstep);
+              const uint64_t bd = ((uint64_t)y_hi << 32) | (uint64_t)(y_lo + k * y_kstep);
+              umma_bf16(tmem_base + (uint32_t)(r * p.BN), ad, bd, p.idesc, first | (uint32_t)k);
+            }
+          }
+        } else {
         for (int tp = 0; tp < p.TG; ++tp) {
           const uint32_t off_rows = (p.TG == 9) ? (uint32_t)((tp / 3) * 16 + tp % 3) : (uint32_t)tp;
           const uint32_t x_t = x_lo + ((off_rows * xrow) >> 4);
@@ -284,6 +299,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc2_kernel(const __grid_constant
             const uint64_t bd = ((uint64_t)y_hi << 32) | (uint64_t)(y_lo + k * y_kstep);
             umma_bf16(tmem_base + (uint32_t)(tp * p.BN), ad, bd, p.idesc, first | (uint32_t)k);
           }
+        }
         }
         tc_commit(x_empty(sx));
         tc_commit(y_empty(sy));
@@ -301,11 +317,13 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc2_kernel(const __grid_constant
     mbar_wait(acc_full, 0);
     tc_fence_after();
     if (tile_end > tile_begin) {
-      const bool row_ok = g < nxg;
+      const bool row_ok = p.stack3 ? (g < 3) : (g < nxg);
       int ci = 0;
-      if (row_ok) ci = p.x_cstart[p.xg_view[xg0 + g]] + p.xg_c0[xg0 + g] + (row % p.GX);
-      for (int tp = 0; tp < p.TG; ++tp) {
-        const int tap = (p.TG == 9) ? tp : (tg * 3 + tp);
+      if (row_ok) ci = p.stack3 ? (p.x_cstart[p.xg_view[xg0]] + p.xg_c0[xg0] + (row % p.GX))
+                                : (p.x_cstart[p.xg_view[xg0 + g]] + p.xg_c0[xg0 + g] + (row % p.GX));
+      const int nacc = p.stack3 ? 3 : p.TG;
+      for (int tp = 0; tp < nacc; ++tp) {
+        const int tap = p.stack3 ? (tp * 3 + g) : ((p.TG == 9) ? tp : (tg * 3 + tp));
         for (int cc = 0; cc < nyg * p.GY; cc += 16) {
           uint32_t r[16];
           tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(tp * p.BN + cc), r);
@@ -353,6 +371,7 @@ static int wgrad_tc2(int N, int H, int W, const ViewList &xs, const ViewList &dy
   p.BN = p.NG * p.GY;
   p.TG = (9 * p.BN <= 512) ? 9 : 3;
   if (p.TG * p.BN > 512) return KS_EUNSUPPORTED;
+  p.stack3 = (p.TG == 9 && p.GX == 32 && p.n_xg == 1) ? 1 : 0;
   p.tap_groups = 9 / p.TG;
   p.N = N; p.H = H; p.W = W;
   p.tiles_w = W / 14; p.tiles_h = (H + 7) / 8;

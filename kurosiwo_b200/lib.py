@@ -88,7 +88,7 @@ def load() -> C.CDLL:
 
 
 EXPORTED_SYMBOLS = [
-    "ks_version", "ks_error_string", "ks_set_option", "ks_permute_cast", "ks_conv2d", "ks_conv2d_wgrad", "ks_stem_conv3x3", "ks_stem_wgrad3x3",
+    "ks_version", "ks_error_string", "ks_set_option", "ks_permute_cast", "ks_permute_cast_batched", "ks_conv2d", "ks_conv2d_wgrad", "ks_stem_conv3x3", "ks_stem_wgrad3x3",
     "ks_bn_stats", "ks_bn_finalize", "ks_bn_act", "ks_bn_bwd_reduce", "ks_bn_bwd_apply", "ks_maxpool2x2_bwd",
     "ks_channel_sum", "ks_ecam_pool", "ks_ecam_gates", "ks_ecam_final", "ks_ecam_bwd_reduce", "ks_ecam_gates_bwd",
     "ks_ecam_bwd_apply", "ks_ce_dice_workspace_bytes", "ks_ce_dice_fwd_bwd", "ks_adam_step",
@@ -143,6 +143,28 @@ class CudaOps:
                                       C.c_int(int(accumulate)), self._stream())
         self._check(rc, "ks_permute_cast")
 
+    def make_permute_table(self, jobs, device):
+        """jobs: list of (src, dst, dims, strides, src_offset) -> opaque table for permute_cast_table (built once)."""
+        import numpy as np
+        rec = np.zeros(len(jobs), dtype=np.dtype([("src", "<u8"), ("dst", "<u8"), ("total", "<i8"), ("s", "<i8", 4),
+                                                  ("d", "<i4", 3), ("sdt", "<i4"), ("ddt", "<i4"), ("acc", "<i4")], align=True))
+        assert rec.dtype.itemsize == 80, rec.dtype.itemsize
+        chunks = []
+        for i, (src, dst, dims, strides, off) in enumerate(jobs):
+            d = list(dims) + [1] * (4 - len(dims))
+            st = list(strides) + [0] * (4 - len(strides))
+            total = d[0] * d[1] * d[2] * d[3]
+            rec[i] = (src.data_ptr() + off * src.element_size(), dst.data_ptr(), total, st, d[1:], dtype_code(src.dtype), dtype_code(dst.dtype), 0)
+            chunks += [(i, c0) for c0 in range(0, total, 4096)]
+        jobs_dev = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()).to(device)
+        chunks_dev = torch.tensor(chunks, dtype=torch.int32, device=device).reshape(-1)
+        return (jobs_dev, chunks_dev, len(chunks), [j[:2] for j in jobs])
+
+    def permute_cast_table(self, table):
+        jobs_dev, chunks_dev, n, _keep = table
+        rc = self.lib.ks_permute_cast_batched(_p(jobs_dev), _p(chunks_dev), C.c_int(n), self._stream())
+        self._check(rc, "ks_permute_cast_batched")
+
     # -- convolution -------------------------------------------------------------------------
     def conv2d(self, N, H, W, ksize, srcs, weight, bias, dsts, acc=None, stats=None, impl=IMPL_AUTO):
         acc = acc or [False] * len(dsts)
@@ -186,9 +208,9 @@ class CudaOps:
                                 _vp(res), C.c_int(int(relu)), _vp(out), _vp(pool), self._stream())
         self._check(rc, "ks_bn_act")
 
-    def bn_bwd_reduce(self, dout: View, out: Optional[View], y: View, scale, shift, mean, rstd, sums):
+    def bn_bwd_reduce(self, dout: View, out: Optional[View], y: View, scale, shift, mean, rstd, sums, dpool: Optional[View] = None):
         rc = self.lib.ks_bn_bwd_reduce(dtype_code(y.dtype), C.c_int(y.N), C.c_int(y.H), C.c_int(y.W), _vp(dout), _vp(out), _vp(y),
-                                       _p(scale), _p(shift), _p(mean), _p(rstd), _p(sums), self._stream())
+                                       _vp(dpool), _p(scale), _p(shift), _p(mean), _p(rstd), _p(sums), self._stream())
         self._check(rc, "ks_bn_bwd_reduce")
 
     def bn_bwd_apply(self, g: View, premasked: bool, y: View, scale, shift, mean, rstd, gamma, sums, count, add: Optional[View],

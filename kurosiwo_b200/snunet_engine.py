@@ -210,8 +210,8 @@ class SNUNetEngine:
             self.gp[nm] = torch.zeros(4 * c * c, dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------------------------------
-    def _pack_weights(self):
-        ops, P = self.ops, self.params
+    def _pack_jobs(self):
+        P, jobs = self.params, []
         for bn_ in self.block_names:
             l = int(bn_[4])
             cin, fl = self.block_cin[bn_], self.f[l]
@@ -220,18 +220,19 @@ class SNUNetEngine:
                     continue
                 w = P.p(f"{bn_}.{tag}.weight")  # OIHW
                 # fwd  [t][o][i] = w[o][i][t]
-                ops.permute_cast(w, self.wp[f"{bn_}.{tag}.fwd"], (9, co, ci), (1, ci * 9, 9))
+                jobs.append((w, self.wp[f"{bn_}.{tag}.fwd"], (9, co, ci), (1, ci * 9, 9), 0))
                 # dgrad [t][i][o] = w[o][i][8-t]   (180-degree rotated taps, in/out swapped)
-                ops.permute_cast(w, self.wp[f"{bn_}.{tag}.dgrad"], (9, ci, co), (-1, 9, ci * 9), src_offset=8)
+                jobs.append((w, self.wp[f"{bn_}.{tag}.dgrad"], (9, ci, co), (-1, 9, ci * 9), 8))
         for (l, j), nm in self.up_names.items():
             c = self.f[l + 1]
             w = P.p(f"{nm}.up.weight")  # (Cin, Cout, 2, 2)
-            ops.permute_cast(w, self.wp[f"{nm}.fwd"], (4, c, c), (1, 4, c * 4))       # [k][co][ci]
-            ops.permute_cast(w, self.wp[f"{nm}.dgrad"], (c, 4, c), (c * 4, 1, 4))     # [ci][k][co]
-            ops.permute_cast(P.p(f"{nm}.up.bias"), self.wp[f"{nm}.bias4"], (4, c), (0, 1))
+            jobs.append((w, self.wp[f"{nm}.fwd"], (4, c, c), (1, 4, c * 4), 0))       # [k][co][ci]
+            jobs.append((w, self.wp[f"{nm}.dgrad"], (c, 4, c), (c * 4, 1, 4), 0))     # [ci][k][co]
+            jobs.append((P.p(f"{nm}.up.bias"), self.wp[f"{nm}.bias4"], (4, c), (0, 1), 0))
+        return jobs
 
-    def _unpack_grads(self):
-        ops, P = self.ops, self.params
+    def _unpack_jobs(self):
+        P, jobs = self.params, []
         for bn_ in self.block_names:
             l = int(bn_[4])
             cin, fl = self.block_cin[bn_], self.f[l]
@@ -239,11 +240,46 @@ class SNUNetEngine:
                 if self.use_stem and bn_ == "conv0_0" and tag == "conv1":
                     continue
                 # grad[o][i][t] = gp[t][o][i]
-                ops.permute_cast(self.gp[f"{bn_}.{tag}"], P.g(f"{bn_}.{tag}.weight"), (co, ci, 9), (ci, 1, co * ci))
+                jobs.append((self.gp[f"{bn_}.{tag}"], P.g(f"{bn_}.{tag}.weight"), (co, ci, 9), (ci, 1, co * ci), 0))
         for (l, j), nm in self.up_names.items():
             c = self.f[l + 1]
             # grad[ci][co][k] = gp[k][co][ci]
-            ops.permute_cast(self.gp[nm], P.g(f"{nm}.up.weight"), (c, c, 4), (1, c, c * c))
+            jobs.append((self.gp[nm], P.g(f"{nm}.up.weight"), (c, c, 4), (1, c, c * c), 0))
+        return jobs
+
+    def _tables(self):
+        """Permute tables hold raw pointers into the flat parameter/gradient buffers: rebuild when those move."""
+        key = (self.params.flat.data_ptr(), self.params.grad.data_ptr())
+        if getattr(self, "_table_key", None) != key:
+            self._pack_table = self.ops.make_permute_table(self._pack_jobs(), self.device)
+            self._unpack_table = self.ops.make_permute_table(self._unpack_jobs(), self.device)
+            self._table_key = key
+        return self._pack_table, self._unpack_table
+
+    def _pack_weights(self):
+        self.ops.permute_cast_table(self._tables()[0])
+
+    def _unpack_grads(self):
+        self.ops.permute_cast_table(self._tables()[1])
+
+    def _ensure_nbt(self):
+        """num_batches_tracked of every BatchNorm as views into one int64 buffer (re-pointed after .to()/load)."""
+        mods = [(f"{bn_}.{t}", self.module.get_submodule(f"{bn_}.{t}")) for bn_ in self.block_names for t in ("bn1", "bn2")]
+        flat = getattr(self, "nbt_all", None)
+        ok = flat is not None and flat.device == self.device and all(
+            m.num_batches_tracked.data_ptr() == flat.data_ptr() + 8 * i for i, (_, m) in enumerate(mods))
+        if ok:
+            return
+        flat = torch.zeros(len(mods), dtype=torch.int64, device=self.device)
+        incr = torch.zeros(len(mods), dtype=torch.int64, device=self.device)
+        execs_per_block = {}
+        for e in self.execs:
+            execs_per_block[e.name] = execs_per_block.get(e.name, 0) + 1
+        for i, (name, m) in enumerate(mods):
+            flat[i] = m.num_batches_tracked.to(self.device)
+            m._buffers["num_batches_tracked"] = flat[i]
+            incr[i] = execs_per_block[name.split(".")[0]]
+        self.nbt_all, self.nbt_incr = flat, incr
 
     def _buf_(self, name: str) -> torch.Tensor:
         mod, _, leaf = name.rpartition(".")
@@ -269,7 +305,6 @@ class SNUNetEngine:
             if training:
                 ops.bn_finalize(fl, count, stats, P.p(f"{nm}.{bnt}.weight"), P.p(f"{nm}.{bnt}.bias"), BN_EPS, BN_MOMENTUM,
                                 rm, rv, sc, sh, mu, rs)
-                self._buf_(f"{nm}.{bnt}.num_batches_tracked").add_(1)
             else:
                 g = P.p(f"{nm}.{bnt}.weight")
                 torch.mul(g, torch.rsqrt(rv + BN_EPS), out=sc)
@@ -302,6 +337,8 @@ class SNUNetEngine:
         self._pack_weights()
         if training:
             ops.zero_(self.stats_all)
+            self._ensure_nbt()
+            self.nbt_all.add_(self.nbt_incr)      # one launch for the 30 num_batches_tracked counters
         for e in self.execs:
             if e.key[0] == "dec":
                 self._up_forward(e.key[1], e.key[2])
@@ -315,7 +352,8 @@ class SNUNetEngine:
         return self.logits
 
     # ------------------------------------------------------------------------------------------
-    def _block_backward(self, e: _Exec, gdsts: Optional[List[View]], gacc: Optional[List[bool]], first: bool):
+    def _block_backward(self, e: _Exec, gdsts: Optional[List[View]], gacc: Optional[List[bool]], first: bool,
+                        dpool: Optional[View] = None):
         ops, P, N = self.ops, self.params, self.N
         h_, w_ = self._hw(e.level)
         fl = self.f[e.level]
@@ -326,7 +364,7 @@ class SNUNetEngine:
         acc = not first
         # ---- bn2 + residual + relu backward -> dy2.  Pass 1 masks dout IN PLACE (g = dout*(out>0)); the masked
         # gradient is re-used by pass 2 and, below, as the identity-path gradient of conv1's output.
-        ops.bn_bwd_reduce(e.dout, e.out, e.y2, None, None, mu2, rs2, e.bstats[1])
+        ops.bn_bwd_reduce(e.dout, e.out, e.y2, None, None, mu2, rs2, e.bstats[1], dpool)
         ops.bn_bwd_apply(e.dout, True, e.y2, None, None, mu2, rs2, P.p(f"{nm}.bn2.weight"), e.bstats[1], count, None, dy,
                          P.g(f"{nm}.bn2.weight"), P.g(f"{nm}.bn2.bias"), P.g(f"{nm}.conv1.bias"), acc)
         # d(conv2.bias) = sum(dy2) == 0 identically (BatchNorm removes the mean): the flat gradient buffer keeps its 0.
@@ -391,12 +429,16 @@ class SNUNetEngine:
                 if l == 4 and br == 0:
                     continue
                 e = self.exec_of[("enc", l, br)]
+                dpool = None
                 if (l + 1, br) in self.P:
-                    ops.maxpool2x2_bwd(e.out, self.dP[(l + 1, br)], e.dout, (l, br) in written)
-                    written.add((l, br))
+                    if (l, br) in written:
+                        dpool = self.dP[(l + 1, br)]     # max-pool backward folded into the BN-backward reduce pass
+                    else:
+                        ops.maxpool2x2_bwd(e.out, self.dP[(l + 1, br)], e.dout, False)
+                        written.add((l, br))
                 assert (l, br) in written
                 gd = None if l == 0 else [self.dP[(l, br)]]
-                self._block_backward(e, gd, None if gd is None else [False], e.name not in seen_blocks)
+                self._block_backward(e, gd, None if gd is None else [False], e.name not in seen_blocks, dpool)
                 seen_blocks.add(e.name)
         self._unpack_grads()
 

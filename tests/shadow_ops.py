@@ -43,6 +43,13 @@ class ShadowOps:
             vals = vals + out.float()
         out.copy_(vals.to(dst.dtype))
 
+    def make_permute_table(self, jobs, device):
+        return list(jobs)
+
+    def permute_cast_table(self, table):
+        for (src, dst, dims, strides, off) in table:
+            self.permute_cast(src, dst, dims, strides, False, off)
+
     # -- convolution -------------------------------------------------------------------------
     def conv2d(self, N, H, W, ksize, srcs, weight, bias, dsts, acc=None, stats=None, impl=0):
         acc = acc or [False] * len(dsts)
@@ -122,7 +129,9 @@ class ShadowOps:
             p = F.max_pool2d(o.float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
             _t(pool).copy_(p.to(o.dtype))
 
-    def bn_bwd_reduce(self, dout, out, y, scale, shift, mean, rstd, sums):
+    def bn_bwd_reduce(self, dout, out, y, scale, shift, mean, rstd, sums, dpool=None):
+        if dpool is not None:
+            self.maxpool2x2_bwd(out, dpool, dout, True)
         yt = _t(y).float()
         if out is not None:
             mask = _t(out).float() > 0

@@ -118,6 +118,24 @@ def test_permute_cast(ops, sh):
     assert torch.allclose(dst.cpu().view(2, 4, 6, 3), 2 * x.permute(0, 2, 3, 1))
 
 
+def test_permute_cast_batched(ops, sh):
+    g = _gen(9)
+    srcs = [torch.randn(n, generator=g).to(DEV) for n in (9 * 40 * 24, 4 * 16 * 16, 5000)]
+    jobs, cjobs = [], []
+    specs = [((9, 24, 40), (-1, 9, 360), 8, torch.bfloat16), ((16, 4, 16), (64, 1, 4), 0, torch.float32), ((5000,), (1,), 0, torch.bfloat16)]
+    for src, (dims, strides, off, dt) in zip(srcs, specs):
+        n = 1
+        for d in dims:
+            n *= d
+        dst, cdst = torch.zeros(n, dtype=dt, device=DEV), torch.zeros(n, dtype=dt)
+        jobs.append((src, dst, dims, strides, off))
+        cjobs.append((src.cpu(), cdst, dims, strides, off))
+    ops.permute_cast_table(ops.make_permute_table(jobs, DEV))
+    sh.permute_cast_table(sh.make_permute_table(cjobs, "cpu"))
+    for (_, d, *_r), (_, cd, *_r2) in zip(jobs, cjobs):
+        assert torch.equal(d.cpu(), cd)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("C,ctot,c0", [(32, 32, 0), (64, 192, 64), (3, 3, 0), (512, 512, 0)])
 def test_bn_forward_backward(ops, sh, dtype, C, ctot, c0):
@@ -165,6 +183,15 @@ def test_bn_forward_backward(ops, sh, dtype, C, ctot, c0):
     sh.bn_bwd_apply(cdout, True, cy, None, None, csmall[2], csmall[3], gamma.cpu(), cbs, count, cadd, cdy, cdg, cdb, cds, True)
     assert rel_l2(fdy.base.float(), cdy.base.float()) < _tol(dtype)
     assert max_rel(dg, cdg) < 1e-3 and max_rel(db, cdb) < 1e-3 and max_rel(ds, cds) < 1e-3
+    # pass 1 with the max-pool backward folded in
+    dpool2, _ = rand_view(N, H // 2, W // 2, C, dtype, DEV, gen=g)
+    dout2, fdo2 = rand_view(N, H, W, C, dtype, DEV, ctot, c0, gen=g)
+    cdout2, cdpool2 = mirror(dout2), mirror(dpool2)
+    bs.zero_(); cbs.zero_()
+    ops.bn_bwd_reduce(dout2, out, y, None, None, small[2], small[3], bs, dpool2)
+    sh.bn_bwd_reduce(cdout2, cout, cy, None, None, csmall[2], csmall[3], cbs, cdpool2)
+    assert rel_l2(bs, cbs) < (1e-5 if dtype == torch.float32 else 2e-3)
+    assert rel_l2(fdo2.base.float(), cdout2.base.float()) < _tol(dtype)
     # pass 1 / 2 with the ReLU mask recomputed from y*scale+shift (no `out` tensor)
     bs.zero_(); cbs.zero_()
     ops.bn_bwd_reduce(dout, None, y, small[0], small[1], small[2], small[3], bs)
