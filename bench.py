@@ -221,7 +221,7 @@ def run_ours(args):
         ops.set_option("tc_mt", args.tc_mt)
     if args.tc_v1:
         ops.set_option("tc_v1", 1)
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph
     for _ in range(2):
         eng.train_step(xa, xb, mk)
     torch.cuda.synchronize()
@@ -229,8 +229,7 @@ def run_ours(args):
     eng.train_step(xa, xb, mk)
     calls_per_step = ops.launches - l0
     if use_graph:
-        eng.capture(xa, xb, mk)
-        step = eng.graph.replay
+        step = eng.capture(xa, xb, mk)
     else:
         step = lambda: eng.train_step(xa, xb, mk)
     for _ in range(max(args.warmup, 3)):

@@ -37,7 +37,7 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-Options g_opt = {0, 0, 0, 0, 0, 0, 0, 0};
+Options g_opt = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
 struct alignas(64) ConvTcParams {
   CUtensorMap src[KS_MAX_VIEWS];
@@ -50,9 +50,10 @@ struct alignas(64) ConvTcParams {
   int BN, MT, SA, SB, TH, bo_mode;
   uint32_t a_tile_bytes, b_stage_bytes, tmem_cols, idesc;
   // v2 (persistent) fields
-  int n_super, resident, n_acc, n_wtiles;
+  int n_super, resident, n_acc, n_wtiles, TB;
+  uint32_t b_tile_bytes;
   double *stats;
-  int Cout;
+  int Cout, debug;
 };
 
 using namespace tc;
@@ -233,8 +234,36 @@ __device__ __forceinline__ void warp_reduce_scatter16(float (&v)[16], int lane) 
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+// Issue the MMAs of NT consecutive taps for up to 4 output windows.  Every descriptor is (per-stage base + compile-time
+// immediate): no loop-carried dependency, so the single issuing lane is throughput- not latency-bound (the uniform
+// datapath has ~10-cycle ALU latency; chained descriptor arithmetic cost ~55 cycles per MMA before this).
+template <int NT, int BK>
+__device__ __forceinline__ void issue_taps(uint32_t a_lo_row, uint32_t a_tile_step, uint32_t b_lo0, uint32_t b_tile_step,
+                                           uint32_t desc_hi, uint32_t acc_col, int BN, int nvalid, uint32_t idesc,
+                                           uint32_t accum_or, bool skip) {
+  constexpr uint32_t ROW16 = (BK * 2) >> 4;
+#pragma unroll
+  for (int tl = 0; tl < NT; ++tl) {
+    const uint32_t roff = (NT == 9) ? (uint32_t)((tl / 3) * 16 + tl % 3) : (uint32_t)tl;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      if (mt < nvalid) {
+        const uint32_t a_lo = a_lo_row + (uint32_t)mt * a_tile_step + roff * ROW16;
+        const uint32_t b_lo = b_lo0 + (uint32_t)tl * b_tile_step;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
+          const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
+          if (!skip) umma_bf16(acc_col + (uint32_t)(mt * BN), ad, bd, idesc, accum_or | (uint32_t)(tl | k));
+        }
+      }
+    }
+  }
+}
+
 template <int BK, int KS>
 __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant__ ConvTcParams p) {
+#define MBW(bar, par) do { if (p.debug & 32) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int TW = (KS == 3) ? 14 : 16;
   constexpr int PADK = KS / 2;
@@ -253,8 +282,8 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
   uint8_t *sm = smem_raw + (base - raw);
   const uint32_t a_base = base;
   const uint32_t b_base = a_base + (uint32_t)SA * MT * p.a_tile_bytes;
-  const uint32_t n_bslots = RES ? (uint32_t)p.n_wtiles : (uint32_t)SB;
-  const uint32_t bar_base = b_base + n_bslots * p.b_stage_bytes;
+  const int TB = p.TB;
+  const uint32_t bar_base = b_base + (RES ? (uint32_t)p.n_wtiles * p.b_tile_bytes : (uint32_t)SB * p.b_stage_bytes);
   auto a_full = [&](int i) { return bar_base + 8u * i; };
   auto a_empty = [&](int i) { return bar_base + 8u * (SA + i); };
   auto b_full = [&](int i) { return bar_base + 8u * (2 * SA + i); };
@@ -265,7 +294,9 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
   const uint32_t w_full = misc + 8u * 4;
   const uint32_t tmem_slot = misc + 8u * 5;
   volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(sm + (tmem_slot - base));
-  float *sstat = reinterpret_cast<float *>(sm + (tmem_slot + 8u - base));   // [2][BN] when stats are requested
+  float *sstat = reinterpret_cast<float *>(sm + (tmem_slot + 8u - base));   // [2][BN] BatchNorm partial sums
+  float *sbias = sstat + 2 * BN;                                            // [BN] bias of this N tile (0 if none)
+  int2 *sdst = reinterpret_cast<int2 *>(sbias + BN);                        // [BN/16] {dst view, channel offset in view}
 
   const int n0 = blockIdx.y * BN;
 
@@ -279,7 +310,14 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
-  if (p.stats) for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) sstat[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) sstat[i] = 0.f;
+  for (int i = threadIdx.x; i < BN; i += blockDim.x) sbias[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+  for (int i = threadIdx.x; i < BN / 16; i += blockDim.x) {
+    const int co = n0 + 16 * i;
+    int d = 0;
+    for (int q = 1; q < KS_MAX_VIEWS; ++q) if (q < p.dsts.n && co >= p.dsts.cstart[q]) d = q;
+    sdst[i] = make_int2(d, co - p.dsts.cstart[d]);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -289,13 +327,13 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
     // ===== TMA producer (whole warp runs the loops; one elected lane issues) =====
     if (RES) {
       if (elect_one()) {
-        mbar_expect_tx(w_full, (uint32_t)p.n_wtiles * p.b_stage_bytes);
+        mbar_expect_tx(w_full, (uint32_t)p.n_wtiles * p.b_tile_bytes);
         int idx = 0;
         for (int s = 0; s < p.n_src; ++s) {
           const int C = p.cstart[s + 1] - p.cstart[s];
           for (int c0 = 0; c0 < C; c0 += BK)
             for (int tap = 0; tap < TAPS; ++tap, ++idx)
-              tma_load_3d(b_base + (uint32_t)idx * p.b_stage_bytes, &p.wmap, p.cstart[s] + c0, n0, tap, w_full);
+              tma_load_3d(b_base + (uint32_t)idx * p.b_tile_bytes, &p.wmap, p.cstart[s] + c0, n0, tap, w_full);
         }
       }
       __syncwarp();
@@ -307,10 +345,11 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
       for (int s = 0; s < p.n_src; ++s) {
         const int C = p.cstart[s + 1] - p.cstart[s];
         for (int c0 = 0; c0 < C; c0 += BK) {
-          mbar_wait(a_empty(sa), pa ^ 1);
+          MBW(a_empty(sa), pa ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(a_full(sa), (uint32_t)nvalid * A_BOX_BYTES);
-            for (int mt = 0; mt < nvalid; ++mt) {
+            if (p.debug & 16) mbar_arrive(a_full(sa));
+            else mbar_expect_tx(a_full(sa), (uint32_t)nvalid * A_BOX_BYTES);
+            for (int mt = 0; mt < ((p.debug & 16) ? 0 : nvalid); ++mt) {
               const int t = t0 + mt;
               const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, n = t / (p.tiles_w * p.tiles_h);
               tma_load_4d(a_base + (uint32_t)(sa * MT + mt) * p.a_tile_bytes, &p.src[s], c0, tw * TW - PADK, th * p.TH - PADK, n, a_full(sa));
@@ -319,11 +358,13 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
           __syncwarp();
           if (++sa == SA) { sa = 0; pa ^= 1; }
           if (!RES) {
-            for (int tap = 0; tap < TAPS; ++tap) {
-              mbar_wait(b_empty(sb), pb ^ 1);
+            for (int tg = 0; tg < TAPS / TB; ++tg) {       // one weight stage = TB taps (a kernel row when TB == 3)
+              MBW(b_empty(sb), pb ^ 1);
               if (elect_one()) {
                 mbar_expect_tx(b_full(sb), p.b_stage_bytes);
-                tma_load_3d(b_base + (uint32_t)sb * p.b_stage_bytes, &p.wmap, p.cstart[s] + c0, n0, tap, b_full(sb));
+                for (int tl = 0; tl < TB; ++tl)
+                  tma_load_3d(b_base + (uint32_t)sb * p.b_stage_bytes + (uint32_t)tl * p.b_tile_bytes, &p.wmap, p.cstart[s] + c0, n0,
+                              tg * TB + tl, b_full(sb));
               }
               __syncwarp();
               if (++sb == SB) { sb = 0; pb ^= 1; }
@@ -334,70 +375,54 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
     }
   } else if (warp == 1) {
     // ===== MMA issuer (whole warp waits; one elected lane issues tcgen05.mma / commit) =====
-    if (RES) mbar_wait(w_full, 0);
+    if (RES) MBW(w_full, 0);
     // descriptor constants: hi word = SBO | version | layout, lo word = (addr >> 4) | LBO(=1) << 16
     const uint32_t desc_hi = (uint32_t)((SBO >> 4) & 0x3FFFu) | (1u << 14) | (LAYOUT << 29);
+    const uint32_t a_tile_step = p.a_tile_bytes >> 4, b_tile_step = p.b_tile_bytes >> 4;
+    const bool skip = (p.debug & 4) != 0;
     int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
     for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
       const int nvalid = min(MT, p.total_tiles - st * MT);
-      mbar_wait(acc_empty(as), pacc ^ 1);
+      MBW(acc_empty(as), pacc ^ 1);
       tc_fence_after();
       const uint32_t acc_col = tmem_base + (uint32_t)(as * MT * BN);
-      uint32_t accum = 0;
-      int widx = 0;
+      uint32_t accum = 0, widx = 0;
       for (int s = 0; s < p.n_src; ++s) {
         const int C = p.cstart[s + 1] - p.cstart[s];
         for (int c0 = 0; c0 < C; c0 += BK) {
-          mbar_wait(a_full(sa), pa);
+          MBW(a_full(sa), pa);
           tc_fence_after();
-          const uint32_t a_stage = a_base + (uint32_t)(sa * MT) * p.a_tile_bytes;
+          const uint32_t a_lo0 = (((a_base + (uint32_t)(sa * MT) * p.a_tile_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
           if (RES) {
             if (elect_one()) {
-              const uint32_t b_lo0 = (((b_base + (uint32_t)widx * p.b_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-              const uint32_t b_step = p.b_stage_bytes >> 4;
-#pragma unroll
-              for (int tap = 0; tap < TAPS; ++tap) {
-                const uint32_t row_off = (KS == 3) ? (uint32_t)((tap / 3) * 16 + (tap % 3)) : 0u;
-                for (int mt = 0; mt < nvalid; ++mt) {
-                  const uint32_t a_lo = (((a_stage + (uint32_t)mt * p.a_tile_bytes) & 0x3FFFFu) >> 4) + ((row_off * ROW_BYTES) >> 4) + (1u << 16);
-                  const uint32_t b_lo = b_lo0 + (uint32_t)tap * b_step;
-#pragma unroll
-                  for (int k = 0; k < BK / 16; ++k) {
-                    const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
-                    const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
-                    umma_bf16(acc_col + (uint32_t)(mt * BN), ad, bd, p.idesc, accum | (uint32_t)(tap | k));
-                  }
-                }
-              }
+              const uint32_t b_lo0 = (((b_base + widx * p.b_tile_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+              issue_taps<TAPS, BK>(a_lo0, a_tile_step, b_lo0, b_tile_step, desc_hi, acc_col, BN, nvalid, p.idesc, accum, skip);
               tc_commit(a_empty(sa));
             }
             __syncwarp();
-            accum = 1;
             widx += TAPS;
           } else {
-            for (int tap = 0; tap < TAPS; ++tap) {
-              mbar_wait(b_full(sb), pb);
+            for (int tg = 0; tg < TAPS / TB; ++tg) {
+              MBW(b_full(sb), pb);
               tc_fence_after();
               if (elect_one()) {
-                const uint32_t row_off = (KS == 3) ? (uint32_t)((tap / 3) * 16 + (tap % 3)) : 0u;
-                const uint32_t b_lo = (((b_base + (uint32_t)sb * p.b_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-                for (int mt = 0; mt < nvalid; ++mt) {
-                  const uint32_t a_lo = (((a_stage + (uint32_t)mt * p.a_tile_bytes + row_off * ROW_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
-#pragma unroll
-                  for (int k = 0; k < BK / 16; ++k) {
-                    const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
-                    const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
-                    umma_bf16(acc_col + (uint32_t)(mt * BN), ad, bd, p.idesc, accum | (uint32_t)(tap | k));
-                  }
+                const uint32_t b_lo0 = (((b_base + (uint32_t)sb * p.b_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+                if (KS == 3 && TB == 3) {
+                  issue_taps<3, BK>(a_lo0 + (uint32_t)(tg * 16) * (ROW_BYTES >> 4), a_tile_step, b_lo0, b_tile_step, desc_hi, acc_col, BN,
+                                    nvalid, p.idesc, accum | (uint32_t)tg, skip);
+                } else {
+                  const uint32_t roff = (KS == 3) ? (uint32_t)((tg / 3) * 16 + tg % 3) : 0u;
+                  issue_taps<1, BK>(a_lo0 + roff * (ROW_BYTES >> 4), a_tile_step, b_lo0, b_tile_step, desc_hi, acc_col, BN, nvalid,
+                                    p.idesc, accum | (uint32_t)tg, skip);
                 }
                 tc_commit(b_empty(sb));
-                if (tap == TAPS - 1) tc_commit(a_empty(sa));
+                if (tg == TAPS / TB - 1) tc_commit(a_empty(sa));
               }
               __syncwarp();
               if (++sb == SB) { sb = 0; pb ^= 1; }
             }
-            accum = 1;
           }
+          accum = 1;
           if (++sa == SA) { sa = 0; pa ^= 1; }
         }
       }
@@ -418,18 +443,27 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
     for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
       const int t0 = st * MT;
       const int nvalid = min(MT, p.total_tiles - t0);
-      mbar_wait(acc_full(as), pacc);
+      MBW(acc_full(as), pacc);
       tc_fence_after();
-      for (int item = half; item < nvalid * nchunk; item += 2) {
+      int cur_mt = -1, n = 0, h = 0, w = 0;
+      bool ok = false;
+      for (int item = half; item < ((p.debug & 8) ? 0 : nvalid * nchunk); item += 2) {
         const int mt = item / nchunk, cc = (item % nchunk) << 5;
-        const int t = t0 + mt;
-        const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, n = t / (p.tiles_w * p.tiles_h);
-        const int h = th * p.TH + ty, w = tw * TW + tx;
-        const bool ok = (tx < TW) && (ty < p.TH) && (h < p.H) && (w < p.W);
+        if (mt != cur_mt) {            // window coordinates change once per MT accumulator, not per 32-column item
+          cur_mt = mt;
+          const int t = t0 + mt;
+          const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h;
+          n = t / (p.tiles_w * p.tiles_h);
+          h = th * p.TH + ty; w = tw * TW + tx;
+          ok = (tx < TW) && (ty < p.TH) && (h < p.H) && (w < p.W);
+        }
         const bool wide = (BN - cc) >= 32;
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * MT * BN + mt * BN + cc);
         uint32_t r[32];
-        if (wide) tmem_ld32(taddr, r);
+        if (p.debug & 2) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
+        } else if (wide) tmem_ld32(taddr, r);
         else { uint32_t r16[16]; tmem_ld16(taddr, r16);
 #pragma unroll
           for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0u; } }
@@ -437,14 +471,10 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
         __nv_bfloat16 *op[2]; bool accd[2];
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          const int co = n0 + cc + 16 * hh;
-          int d = 0;
-#pragma unroll
-          for (int i = 1; i < KS_MAX_VIEWS; ++i) if (i < p.dsts.n && co >= p.dsts.cstart[i]) d = i;
-          const View &dv = p.dsts.v[d];
-          op[hh] = reinterpret_cast<__nv_bfloat16 *>(dv.ptr) +
-                   ((long long)n * dv.sn + (long long)h * dv.sh + (long long)w * dv.sw + (co - p.dsts.cstart[d]));
-          accd[hh] = ((p.acc_mask >> d) & 1) != 0;
+          const int2 dd = sdst[min((cc >> 4) + hh, BN / 16 - 1)];
+          const View &dv = p.dsts.v[dd.x];
+          op[hh] = reinterpret_cast<__nv_bfloat16 *>(dv.ptr) + ((long long)n * dv.sn + (long long)h * dv.sh + (long long)w * dv.sw + dd.y);
+          accd[hh] = ((p.acc_mask >> dd.x) & 1) != 0;
         }
         const int nh = wide ? 2 : 1;
         uint32_t old[2][8];
@@ -457,7 +487,12 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
         if (p.bias) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) if (i < 16 * nh) v[i] += __ldg(p.bias + n0 + cc + i);
+          for (int q = 0; q < 8; ++q) {
+            if (q < 4 * nh) {
+              const float4 b4 = *reinterpret_cast<const float4 *>(sbias + cc + 4 * q);
+              v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+            }
+          }
         }
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -475,7 +510,7 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
               const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[16 * hh + 2 * i], v[16 * hh + 2 * i + 1]);
               pk[i] = *reinterpret_cast<const uint32_t *>(&h2);
             }
-            st_global_v8(op[hh], pk);
+            if (!(p.debug & 1)) st_global_v8(op[hh], pk);
           }
         }
         if (p.stats) {
@@ -512,6 +547,7 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
 }
 
+#undef MBW
 static bool tma_view_ok(const View &v) {
   return (((uintptr_t)v.ptr) % 16 == 0) && ((v.sn * 2) % 16 == 0) && ((v.sh * 2) % 16 == 0) && ((v.sw * 2) % 16 == 0) &&
          v.sw > 0 && v.sh > 0 && v.sn > 0;
@@ -595,17 +631,20 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
   for (int i = 0; i <= KS_MAX_VIEWS; ++i) p.cstart[i] = srcs.cstart[i];
   p.bo_mode = g_opt.bo_mode;
   p.Cout = Cout;
+  p.debug = g_opt.debug;
   p.stats = v1 ? nullptr : stats;
   const uint32_t row_bytes = BK * 2;
   const uint32_t a_rows = (ksize == 3) ? 162 : 128;
   p.a_tile_bytes = ((a_rows * row_bytes + 1023) / 1024) * 1024;
-  p.b_stage_bytes = (uint32_t)p.BN * row_bytes;
+  p.b_tile_bytes = (uint32_t)p.BN * row_bytes;
+  p.b_stage_bytes = p.b_tile_bytes;   // streamed: x TB below
+  p.TB = 1;
   p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
   p.n_wtiles = (Cin / BK) * taps;
   const size_t budget = 222 * 1024;
-  const size_t fixed = 1024 + 512 + (stats ? 2 * p.BN * 4 : 0);
+  const size_t fixed = 1024 + 512 + (size_t)p.BN * 4 * 3 + (size_t)(p.BN / 16) * 8;
   // ---- resident weights? (all [BN x BK] tiles of this N tile stay in smem for the CTA's lifetime)
-  const size_t w_bytes = (size_t)p.n_wtiles * p.b_stage_bytes;
+  const size_t w_bytes = (size_t)p.n_wtiles * p.b_tile_bytes;
   int MT, SA, SB;
   p.resident = 0;
   // Measured on B200 (scripts/bench_layers.py): keeping the weights resident pays when the MMAs are short
@@ -620,15 +659,26 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
     while (SA > 2 && w_bytes + (size_t)SA * MT * p.a_tile_bytes + fixed > budget) --SA;
     SB = 1;
   } else {
-    // streamed weights: every weight tile is shared by MT output windows
-    MT = g_opt.mt > 0 ? g_opt.mt : ((!v1 && Cin >= 512) ? 2 : 1);
+    // streamed weights.  Measured (scripts/sweep_stream.py, B200): two co-resident CTAs per SM beat deeper pipelines, and one
+    // weight stage per kernel ROW (3 taps) beats one per tap whenever it still leaves room for two CTAs.
+    MT = g_opt.mt > 0 ? g_opt.mt : 1;
     while (MT > 1 && (v1 ? MT * p.BN > 512 : 2 * MT * p.BN > 512)) MT >>= 1;
-    SA = g_opt.sa > 0 ? g_opt.sa : 3; SB = g_opt.sb > 0 ? g_opt.sb : 4;
-    auto bytes = [&](int mt, int sa, int sb) { return (size_t)sa * mt * p.a_tile_bytes + (size_t)sb * p.b_stage_bytes + fixed; };
-    while (bytes(MT, SA, SB) > budget && SA > 2) --SA;
-    while (bytes(MT, SA, SB) > budget && SB > 2) --SB;
-    while (bytes(MT, SA, SB) > budget && MT > 1) MT >>= 1;
-    if (bytes(MT, SA, SB) > budget) return KS_EUNSUPPORTED;
+    auto bytes = [&](int mt, int sa, int sb, int tb) { return (size_t)sa * mt * p.a_tile_bytes + (size_t)sb * tb * p.b_tile_bytes + fixed; };
+    const size_t half_sm = (227 * 1024) / 2 - 1024;
+    const bool can3 = !v1 && ksize == 3 && g_opt.tb != 1;
+    int TB = 1;
+    if (can3 && (g_opt.tb == 3 || bytes(MT, 2, 2, 3) <= half_sm)) { TB = 3; SA = 2; SB = 2; }
+    else if (!v1 && bytes(MT, 2, 4, 1) <= half_sm) { TB = 1; SA = 2; SB = 4; }
+    else if (can3 && bytes(MT, 3, 3, 3) <= budget) { TB = 3; SA = 3; SB = 3; }
+    else { TB = 1; SA = 3; SB = 4; }
+    if (g_opt.sa > 0) SA = g_opt.sa;
+    if (g_opt.sb > 0) SB = g_opt.sb;
+    while (bytes(MT, SA, SB, TB) > budget && SB > 2) --SB;
+    while (bytes(MT, SA, SB, TB) > budget && SA > 2) --SA;
+    while (bytes(MT, SA, SB, TB) > budget && MT > 1) MT >>= 1;
+    if (bytes(MT, SA, SB, TB) > budget) { if (TB == 3) { TB = 1; } }
+    if (bytes(MT, SA, SB, TB) > budget) return KS_EUNSUPPORTED;
+    p.TB = TB; p.b_stage_bytes = (uint32_t)TB * p.b_tile_bytes;
   }
   p.MT = MT; p.SA = SA; p.SB = SB;
   p.n_super = (p.total_tiles + MT - 1) / MT;
@@ -692,6 +742,8 @@ extern "C" int ks_set_option(const char *name, int value) {
   else if (eq("tc_sb")) ks::g_opt.sb = value;
   else if (eq("tc_v1")) ks::g_opt.v1 = value;
   else if (eq("tc_no_resident")) ks::g_opt.no_resident = value;
+  else if (eq("tc_tb")) ks::g_opt.tb = value;
+  else if (eq("tc_debug")) ks::g_opt.debug = value;   // perf experiments only: bit0 skip epilogue stores, bit1 skip TMEM loads, bit2 skip MMAs
   else return KS_EINVAL;
   return KS_OK;
 }

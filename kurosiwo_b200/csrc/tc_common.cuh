@@ -39,6 +39,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or the hint expires,
 // instead of burning issue slots in a spin loop (role warps poll a lot: ncu showed 30 % of issue slots spent spinning).
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) { }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   do {

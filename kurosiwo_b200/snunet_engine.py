@@ -469,23 +469,31 @@ class SNUNetEngine:
                            group=process_group)
         self.graph = None
 
-    def train_step(self, xA: torch.Tensor, xB: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
-        """One optimizer step; returns the device tensor [total, dice, ce] (no host sync)."""
-        ops = self.ops
+    def _fwd_loss_bwd(self, xA, xB, mask):
         logits = self.forward(xA, xB, training=True)
-        ops.ce_dice(logits, mask, self.cw, self.ignore_index, 1.0, self.loss3, self.dlogits, self.pred, self.loss_ws)
+        self.ops.ce_dice(logits, mask, self.cw, self.ignore_index, 1.0, self.loss3, self.dlogits, self.pred, self.loss_ws)
         self.backward(self.dlogits)
+
+    def _allreduce(self):
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.params.grad, group=self.pg)   # NCCL over NVLink: ONE message = all gradients
+
+    def _optimizer(self):
         hp = self.hp
-        ops.adam_step(self.params.flat, self.params.grad, self.adam_m, self.adam_v, hp["lr"], hp["b1"], hp["b2"], hp["eps"],
-                      hp["wd"], 1.0 / self.world, self.adam_step)
+        self.ops.adam_step(self.params.flat, self.params.grad, self.adam_m, self.adam_v, hp["lr"], hp["b1"], hp["b2"], hp["eps"],
+                           hp["wd"], 1.0 / self.world, self.adam_step)
+
+    def train_step(self, xA: torch.Tensor, xB: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+        """One optimizer step; returns the device tensor [total, dice, ce] (no host sync)."""
+        self._fwd_loss_bwd(xA, xB, mask)
+        self._allreduce()
+        self._optimizer()
         return self.loss3
 
     def capture(self, xA: torch.Tensor, xB: torch.Tensor, mask: torch.Tensor):
-        """Capture train_step into a CUDA graph over the given STATIC input tensors (single-GPU)."""
-        assert self.world == 1, "graph capture of the NCCL step is not used; call train_step directly"
+        """Capture the step over STATIC input tensors: one CUDA graph on a single GPU; with data parallelism two graphs
+        (forward+loss+backward | Adam) around the eager NCCL all-reduce.  Returns a callable that replays one step."""
         self.params.ensure(self.device)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -494,7 +502,22 @@ class SNUNetEngine:
                 self.train_step(xA, xB, mask)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.train_step(xA, xB, mask)
-        return self.graph
+        if self.world == 1:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.train_step(xA, xB, mask)
+            self.replay = self.graph.replay
+        else:
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                self._fwd_loss_bwd(xA, xB, mask)
+            with torch.cuda.graph(gb):
+                self._optimizer()
+            self.graph = (ga, gb)
+
+            def replay():
+                ga.replay()
+                self._allreduce()
+                gb.replay()
+            self.replay = replay
+        return self.replay

@@ -1,0 +1,10 @@
+set -x
+timeout 300 python tests/tc_probe.py gpurun_out/tc_probe12.json > gpurun_out/tc_probe12.log 2>&1; echo "probe rc=$?"; grep -c error gpurun_out/tc_probe12.log; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/tc_probe12.json'))
+bad=[(k,kk,vv) for k,v in d['conv'].items() for kk,vv in v.items() if not (isinstance(vv,float) and vv<5e-3)]
+print("conv bad:",bad); print("wgrad bad:", {k:v for k,v in d['wgrad'].items() if 'error' in v or v['assign']>5e-3})
+PY
+KS_VARIANTS=auto,nores_mt1,res_mt2 timeout 600 python scripts/bench_layers.py gpurun_out/layers12.json > gpurun_out/layers12.log 2>&1; echo "layers rc=$?"; cat gpurun_out/layers12.log
+timeout 900 python -m pytest tests -q -m gpu --timeout 600 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench12.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench12.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['by_kind'], d['roofline']['conv_ms_per_step'])"

@@ -142,8 +142,8 @@ def test_full_resolution_fp32_vs_oracle_and_graph_replay():
     assert (g - grads_o["conv0_4.conv1.weight"]).abs().max().item() <= 2e-3 * grads_o["conv0_4.conv1.weight"].abs().max().item()
     # CUDA-graph replay of the whole step reproduces the eager launch sequence
     first = loss3.clone()
-    eng.capture(xa, xb, mk)
-    eng.graph.replay()
+    replay = eng.capture(xa, xb, mk)
+    replay()
     torch.cuda.synchronize()
     assert torch.allclose(eng.loss3, first, rtol=1e-5)
 
