@@ -92,7 +92,7 @@ class _Exec:
 
 class SNUNetEngine:
     def __init__(self, ops, module: torch.nn.Module, in_ch: int, num_classes: int, base: int,
-                 N: int, H: int, W: int, dtype: torch.dtype, device, conv_impl: int = 0):
+                 N: int, H: int, W: int, dtype: torch.dtype, device, conv_impl: int = 0, planar_slots: Optional[bool] = None):
         assert H % 16 == 0 and W % 16 == 0, "SNUNet needs H, W divisible by 16 (four 2x2 poolings)"
         assert num_classes == 3, "the fused head/loss kernels are built for num_classes == 3 (configs/config.json:13)"
         self.ops, self.module, self.dtype, self.device = ops, module, dtype, torch.device(device)
@@ -100,6 +100,9 @@ class SNUNetEngine:
         self.f = [base * (1 << l) for l in range(5)]
         self.hid, self.hid1 = (4 * base) // 16, base // 4
         self.conv_impl = conv_impl
+        # slot layout of the per-level activation store: one dense concat buffer (channel slices) or one dense tensor per slot
+        import os
+        self.planar = bool(int(os.environ.get("KS_PLANAR_SLOTS", "1"))) if planar_slots is None else planar_slots
         # dedicated HBM-bound stem kernels (NCHW fp32 input read directly) when conv0_0 is Cin<=4 -> 32
         self.use_stem = (base == 32 and in_ch <= 4)
         self._x_in = [None, None]
@@ -116,14 +119,26 @@ class SNUNetEngine:
         h, w = self._hw(l)
         return View.alloc(self.N, h, w, C, self.dtype, self.device)
 
-    def slot(self, buf: Dict[int, View], l: int, k: int) -> View:
+    def slot(self, buf, l: int, k: int) -> View:
         f = self.f[l]
+        if self.planar:
+            return buf[l][k if l < 4 else 0]
         return buf[l].ch((k if l < 4 else 0) * f, f)
+
+    def prefix(self, buf, l: int, nslots: int) -> List[View]:
+        """Views covering slots 0..nslots-1 of level l (the torch.cat operand list minus the upsampled tensor)."""
+        if self.planar:
+            return [buf[l][k] for k in range(nslots)]
+        return [buf[l].ch(0, self.f[l] * nslots)]
 
     def _alloc(self):
         N, dev, f = self.N, self.device, self.f
-        self.X = {l: self._buf(l, f[l] * NSLOTS[l]) for l in range(5)}
-        self.dX = {l: self._buf(l, f[l] * NSLOTS[l]) for l in range(5)}
+        if self.planar:
+            self.X = {l: [self._buf(l, f[l]) for _ in range(NSLOTS[l])] for l in range(5)}
+            self.dX = {l: [self._buf(l, f[l]) for _ in range(NSLOTS[l])] for l in range(5)}
+        else:
+            self.X = {l: self._buf(l, f[l] * NSLOTS[l]) for l in range(5)}
+            self.dX = {l: self._buf(l, f[l] * NSLOTS[l]) for l in range(5)}
         self.P, self.dP = {}, {}
         for l in range(1, 5):
             for br in (0, 1):
@@ -173,8 +188,7 @@ class SNUNetEngine:
                 pool_key = (l + 1, br) if (l + 1, br) in self.P else None
                 add(f"conv{l}_0", l, [src], [gsrc], br, pool_key, ("enc", l, br))
         for (l, j) in DEC_ORDER:
-            prefix = self.X[l].ch(0, f[l] * (j + 1))
-            add(f"conv{l}_{j}", l, [prefix, self.UP[(l, j)]], None, 1 + j, None, ("dec", l, j))
+            add(f"conv{l}_{j}", l, self.prefix(self.X, l, j + 1) + [self.UP[(l, j)]], None, 1 + j, None, ("dec", l, j))
         n = len(self.execs)
         fmax = max(self.f)
         self.stats_all = torch.zeros(n * 2 * 2 * fmax, dtype=torch.float64, device=self.device)
@@ -404,8 +418,12 @@ class SNUNetEngine:
                 k2 = k
                 while k2 + 1 <= j and ((l, k2 + 1) in written) == st:
                     k2 += 1
-                gd.append(self.dX[l].ch(k * f[l], (k2 - k + 1) * f[l]))
-                ga.append(st)
+                if self.planar:
+                    gd += [self.dX[l][kk] for kk in range(k, k2 + 1)]
+                    ga += [st] * (k2 - k + 1)
+                else:
+                    gd.append(self.dX[l].ch(k * f[l], (k2 - k + 1) * f[l]))
+                    ga.append(st)
                 k = k2 + 1
             for kk in range(j + 1):
                 written.add((l, kk))
