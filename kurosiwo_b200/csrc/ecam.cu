@@ -31,72 +31,75 @@ __device__ __forceinline__ const T *vptr(const View &v, int n, int h, int w, int
 constexpr int kMaxJ = 4;
 
 // ---- pooling: sums (fp32 atomics) and packed (max, first index) ---------------------------
+// Thread = (pixel lane, 8-channel group g of the J*Cb concat channels): 24 registers of running state per thread, one
+// 16-byte load per pixel, UNR pixels in flight.  The intra tensor (sum over the J views) is formed with shuffles across
+// the lanes of a pixel that hold the same channels of different views; the lanes of view 0 track its pool statistics.
 template <typename T>
 __global__ void __launch_bounds__(256)
 ecam_pool_kernel(ViewList xs, int J, int Cb, int H, int W, float *pooled, unsigned long long *scratch) {
   extern __shared__ unsigned char smem_raw[];
-  const int CT = (J + 1) * Cb;
+  const int CC = J * Cb, CT = (J + 1) * Cb;
   unsigned long long *smax = reinterpret_cast<unsigned long long *>(smem_raw);
   float *ssum = reinterpret_cast<float *>(smax + CT);
   for (int i = threadIdx.x; i < CT; i += blockDim.x) { smax[i] = 0ull; ssum[i] = 0.f; }
   __syncthreads();
   const int n = blockIdx.y;
-  const int CVb = Cb / 8, rows = blockDim.x / CVb;
-  const int tx = threadIdx.x % CVb, ty = threadIdx.x / CVb;
+  const int G = CC / 8, CVb = Cb / 8, rows = blockDim.x / G;   // G lanes per pixel; lane g -> view g / CVb, vector g % CVb
+  const int g = threadIdx.x % G, ty = threadIdx.x / G;
+  const int j = g / CVb, cb0 = (g % CVb) * 8;
   const int HW = H * W;
-  float sum[kMaxJ + 1][8], best[kMaxJ + 1][8]; unsigned int bidx[kMaxJ + 1][8];
+  const View &xv = xs.v[j];
+  const T *xp = reinterpret_cast<const T *>(xv.ptr) + (long long)n * xv.sn + cb0;
+  float sum[8], best[8], isum[8], ibest[8]; unsigned int bidx[8], ibidx[8];
 #pragma unroll
-  for (int j = 0; j <= kMaxJ; ++j)
+  for (int k = 0; k < 8; ++k) { sum[k] = 0.f; best[k] = -INFINITY; bidx[k] = 0u; isum[k] = 0.f; ibest[k] = -INFINITY; ibidx[k] = 0u; }
+  constexpr int UNR = 4;
+  const int stride = gridDim.x * rows;
+  const int pmax = ((HW + rows - 1) / rows) * rows;        // uniform trip count within a warp (shuffles inside)
+  for (int p0 = blockIdx.x * rows + ty; p0 < pmax; p0 += stride * UNR) {
+    float f[UNR][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { sum[j][k] = 0.f; best[j][k] = -INFINITY; bidx[j][k] = 0u; }
-  bool any = false;
-  if (ty < rows) {
-    for (int p = blockIdx.x * rows + ty; p < HW; p += gridDim.x * rows) {
-      any = true;
-      const int h = p / W, w = p % W;
-      float it[8];
+    for (int u = 0; u < UNR; ++u) {
+      const int p = p0 + u * stride;
+      if (p < HW) ld8(xp + (long long)(p / W) * xv.sh + (long long)(p % W) * xv.sw, f[u]);
+      else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) it[k] = 0.f;
-#pragma unroll
-      for (int j = 0; j < kMaxJ; ++j) {
-        if (j < J) {
-          float f[8]; ld8(vptr<T>(xs.v[j], n, h, w, tx * 8), f);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            sum[j][k] += f[k]; it[k] += f[k];
-            if (f[k] > best[j][k]) { best[j][k] = f[k]; bidx[j][k] = (unsigned)p; }
-          }
-        }
+        for (int k = 0; k < 8; ++k) f[u][k] = 0.f;
       }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int p = p0 + u * stride;
+      const bool ok = p < HW;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        sum[kMaxJ][k] += it[k];
-        if (it[k] > best[kMaxJ][k]) { best[kMaxJ][k] = it[k]; bidx[kMaxJ][k] = (unsigned)p; }
+        float it = f[u][k];
+        for (int o = CVb; o < G; o <<= 1) it += __shfl_xor_sync(0xffffffffu, it, o);   // sum over the J views
+        if (ok) {
+          sum[k] += f[u][k];
+          if (f[u][k] > best[k]) { best[k] = f[u][k]; bidx[k] = (unsigned)p; }
+          isum[k] += it;
+          if (it > ibest[k]) { ibest[k] = it; ibidx[k] = (unsigned)p; }
+        }
       }
     }
   }
-  // reduce over the pixel lanes of the warp first (lanes sharing tx), then one smem atomic per warp and channel
+  // combine the pixel lanes of a warp (lanes sharing g), then one smem atomic per warp and channel
   const int lane = threadIdx.x & 31;
-  (void)any;
 #pragma unroll
-  for (int j = 0; j <= kMaxJ; ++j) {
-    const int jj = (j == kMaxJ) ? J : j;
-    if (j < J || j == kMaxJ) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float sv = sum[j][k];
-        unsigned long long mv = pack_max(best[j][k], bidx[j][k]);
-        for (int o = CVb; o < 32; o <<= 1) {
-          sv += __shfl_xor_sync(0xffffffffu, sv, o);
-          const unsigned long long ov = __shfl_xor_sync(0xffffffffu, mv, o);
-          mv = ov > mv ? ov : mv;
-        }
-        if (lane < CVb && ty < rows) {
-          const int c = jj * Cb + tx * 8 + k;
-          atomicAdd(&ssum[c], sv);
-          atomicMax(&smax[c], mv);
-        }
-      }
+  for (int k = 0; k < 8; ++k) {
+    float sv = sum[k], iv = isum[k];
+    unsigned long long mv = pack_max(best[k], bidx[k]), imv = pack_max(ibest[k], ibidx[k]);
+    for (int o = G; o < 32; o <<= 1) {
+      sv += __shfl_xor_sync(0xffffffffu, sv, o);
+      iv += __shfl_xor_sync(0xffffffffu, iv, o);
+      const unsigned long long ov = __shfl_xor_sync(0xffffffffu, mv, o), iov = __shfl_xor_sync(0xffffffffu, imv, o);
+      mv = ov > mv ? ov : mv; imv = iov > imv ? iov : imv;
+    }
+    if (lane < G && ty < rows) {
+      atomicAdd(&ssum[g * 8 + k], sv);
+      atomicMax(&smax[g * 8 + k], mv);
+      if (j == 0) { atomicAdd(&ssum[CC + cb0 + k], iv); atomicMax(&smax[CC + cb0 + k], imv); }
     }
   }
   __syncthreads();
@@ -175,27 +178,36 @@ ecam_final_kernel(ViewList xs, int J, int Cb, int H, int W, const float *__restr
   const View &xv = xs.v[j];
   const T *xp = reinterpret_cast<const T *>(xv.ptr) + (long long)n * xv.sn + cb0;
   const int pmax = ((HW + rows - 1) / rows) * rows;
-  for (int p = blockIdx.x * rows + ty; p < pmax; p += gridDim.x * rows) {
-    float acc[K];
+  constexpr int UNR = 4;
+  const int stride = gridDim.x * rows;
+  for (int p0 = blockIdx.x * rows + ty; p0 < pmax; p0 += stride * UNR) {
+    float f[UNR][8];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] = 0.f;
-    const bool ok = p < HW;
-    if (ok) {
-      const int h = p / W, w = p % W;
-      float f[8]; ld8(xp + (long long)h * xv.sh + (long long)w * xv.sw, f);
+    for (int u = 0; u < UNR; ++u) {
+      const int p = p0 + u * stride;
+      if (p < HW) ld8(xp + (long long)(p / W) * xv.sh + (long long)(p % W) * xv.sw, f[u]);
+      else {
 #pragma unroll
-      for (int k = 0; k < K; ++k)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[k] = fmaf(f[i], we[k][i], acc[k]);
+        for (int i = 0; i < 8; ++i) f[u][i] = 0.f;
+      }
     }
 #pragma unroll
-    for (int k = 0; k < K; ++k)
-      for (int o = 1; o < G; o <<= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    if (ok && g < K) {
-      float v = acc[0] + cst[0];
+    for (int u = 0; u < UNR; ++u) {
+      const int p = p0 + u * stride;
+      float acc[K];
 #pragma unroll
-      for (int k = 1; k < K; ++k) if (g == k) v = acc[k] + cst[k];
-      logits[((size_t)n * K + g) * HW + p] = v;
+      for (int k = 0; k < K; ++k) {
+        acc[k] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[k] = fmaf(f[u][i], we[k][i], acc[k]);
+        for (int o = 1; o < G; o <<= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+      }
+      if (p < HW && g < K) {
+        float v = acc[0] + cst[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) if (g == k) v = acc[k] + cst[k];
+        logits[((size_t)n * K + g) * HW + p] = v;
+      }
     }
   }
 }
@@ -220,16 +232,32 @@ ecam_bwd_reduce_kernel(ViewList xs, int J, int Cb, int H, int W, const float *__
 #pragma unroll
     for (int i = 0; i < 8; ++i) B[k][i] = 0.f;
   }
-  for (int p = blockIdx.x * rows + ty; p < HW; p += gridDim.x * rows) {
-    const int h = p / W, w = p % W;
-    float dl[K];
+  constexpr int UNR = 4;
+  const int stride = gridDim.x * rows;
+  for (int p0 = blockIdx.x * rows + ty; p0 < HW; p0 += stride * UNR) {
+    float f[UNR][8], dl[UNR][K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) { dl[k] = __ldg(dlogits + ((size_t)n * K + k) * HW + p); D[k] += dl[k]; }
-    float f[8]; ld8(xp + (long long)h * xv.sh + (long long)w * xv.sw, f);
+    for (int u = 0; u < UNR; ++u) {
+      const int p = p0 + u * stride;
+      if (p < HW) {
+        ld8(xp + (long long)(p / W) * xv.sh + (long long)(p % W) * xv.sw, f[u]);
 #pragma unroll
-    for (int k = 0; k < K; ++k)
+        for (int k = 0; k < K; ++k) dl[u][k] = __ldg(dlogits + ((size_t)n * K + k) * HW + p);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) B[k][i] = fmaf(dl[k], f[i], B[k][i]);
+        for (int k = 0; k < K; ++k) dl[u][k] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[u][i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        D[k] += dl[u][k];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) B[k][i] = fmaf(dl[u][k], f[u][i], B[k][i]);
+      }
   }
   // lanes of a warp that share g (pixel lanes) are combined by shuffles, then one smem atomic per warp and value
   const int lane = threadIdx.x & 31;
@@ -349,22 +377,33 @@ ecam_bwd_apply_kernel(ViewList dxs, int J, int Cb, int H, int W, const float *__
   }
   const View &dv = dxs.v[j];
   T *dp = reinterpret_cast<T *>(dv.ptr) + (long long)n * dv.sn + cb0;
-  for (int p = blockIdx.x * rows + ty; p < HW; p += gridDim.x * rows) {
-    const int h = p / W, w = p % W;
-    float dl[K];
+  constexpr int UNR = 4;
+  const int stride = gridDim.x * rows;
+  for (int p0 = blockIdx.x * rows + ty; p0 < HW; p0 += stride * UNR) {
+    float dl[UNR][K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) dl[k] = __ldg(dlogits + ((size_t)n * K + k) * HW + p);
-    float o[8];
+    for (int u = 0; u < UNR; ++u) {
+      const int p = min(p0 + u * stride, HW - 1);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float v = base[i];
-#pragma unroll
-      for (int k = 0; k < K; ++k) v = fmaf(we[k][i], dl[k], v);
-      if (amc[i] == p) v += dmc[i];
-      if (ami[i] == p) v += dmi[i];
-      o[i] = v;
+      for (int k = 0; k < K; ++k) dl[u][k] = __ldg(dlogits + ((size_t)n * K + k) * HW + p);
     }
-    st8(dp + (long long)h * dv.sh + (long long)w * dv.sw, o);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int p = p0 + u * stride;
+      if (p < HW) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float v = base[i];
+#pragma unroll
+          for (int k = 0; k < K; ++k) v = fmaf(we[k][i], dl[u][k], v);
+          if (amc[i] == p) v += dmc[i];
+          if (ami[i] == p) v += dmi[i];
+          o[i] = v;
+        }
+        st8(dp + (long long)(p / W) * dv.sh + (long long)(p % W) * dv.sw, o);
+      }
+    }
   }
 }
 
@@ -393,8 +432,8 @@ extern "C" int ks_ecam_pool(int dtype, int N, int H, int W, const ks_view_t *xs,
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(pooled, 0, sizeof(float) * (size_t)N * 2 * CT, st); if (e) return (int)e;
   e = cudaMemsetAsync(scratch, 0, sizeof(unsigned long long) * (size_t)N * CT, st); if (e) return (int)e;
-  const int rows = 256 / (Cb / 8);
-  int chunks = (H * W + rows * 16 - 1) / (rows * 16); if (chunks < 1) chunks = 1;
+  const int rows = 256 / (J * Cb / 8);
+  int chunks = (H * W + rows * 32 - 1) / (rows * 32); if (chunks < 1) chunks = 1;
   const int cap = (kNumSMs * 8 + N - 1) / N; if (chunks > cap) chunks = cap;
   const size_t smem = (size_t)CT * (sizeof(unsigned long long) + sizeof(float));
   if (dtype == KS_F32) ecam_pool_kernel<float><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, pooled, scratch);

@@ -344,6 +344,152 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc2_kernel(const __grid_constant
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
 }
 
+// ------------------------------------------------------------------------------------------------
+// v3 (3x3, W % 14 == 0): TAP STACKING ALONG N.  Rewrite dw[t][co][ci] = sum_p x[p][ci] * dy[p - t][co]: now x is the
+// unshifted operand (M = 128 ci, pad columns zeroed by the 5-D map) and dy carries the halo.  The three taps of a
+// kernel row differ by ONE pixel of shift, so they are three MN-groups of the SAME dy halo tile with a leading-
+// dimension byte offset of one row: a single UMMA computes [128 ci] x [3 taps x GY co].  N grows from 32/64 to 96/192:
+// 3x fewer MMAs and 2.3x less shared-memory operand traffic per MAC - the Cout = 32/64 levels were SMEM-read bound.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192, 1) wgrad_tc3_kernel(const __grid_constant__ WgradTc2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+  const int SX = p.SX, SY = p.SY;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *sm = smem_raw + (base - raw);
+  const uint32_t x_base = base;
+  const uint32_t y_base = x_base + (uint32_t)SX * p.x_stage_bytes;
+  const uint32_t bar_base = y_base + (uint32_t)SY * p.y_stage_bytes;
+  auto x_full = [&](int i) { return bar_base + 8u * i; };
+  auto x_empty = [&](int i) { return bar_base + 8u * (SX + i); };
+  auto y_full = [&](int i) { return bar_base + 8u * (2 * SX + i); };
+  auto y_empty = [&](int i) { return bar_base + 8u * (2 * SX + SY + i); };
+  const uint32_t acc_full = bar_base + 8u * (2 * SX + 2 * SY);
+  const uint32_t tmem_slot = acc_full + 8u;
+  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(sm + (tmem_slot - base));
+
+  int item = blockIdx.x;
+  const int tg = item % p.tap_groups; item /= p.tap_groups;      // TG == 3: all kernel rows here; TG == 1: kernel row r = tg
+  const int ntile = item % p.n_tiles; const int mtile = item / p.n_tiles;
+  const int xg0 = mtile * p.MG, nxg = min(p.MG, p.n_xg - xg0);
+  const int yg = ntile;                                           // one dy channel group per N tile
+  const int per = (p.total_tiles + p.splits - 1) / p.splits;
+  const int tile_begin = blockIdx.y * per, tile_end = min(p.total_tiles, tile_begin + per);
+  const uint32_t xg_bytes = 128u * p.GX * 2u;
+  const uint32_t xrow = p.GX * 2u, yrow = p.GY * 2u;
+  const int NR = p.TG;                                            // kernel rows accumulated by this CTA (3 or 1)
+  const int r0 = (NR == 3) ? 0 : tg;
+
+  // dy stages have pad rows the TMA never writes but shifted windows read (against zeroed x pad columns): make them finite
+  for (uint32_t i = threadIdx.x * 16u; i < (uint32_t)SY * p.y_stage_bytes; i += blockDim.x * 16u)
+    *reinterpret_cast<uint4 *>(sm + (y_base - base) + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 0 && elect_one()) {
+    for (int i = 0; i < SX; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 1); }
+    for (int i = 0; i < SY; ++i) { mbar_init(y_full(i), 1); mbar_init(y_empty(i), 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int N3 = 3 * p.GY;
+
+  if (warp == 0) {
+    int sx = 0, px = 0, sy = 0, py = 0;
+    for (int t = tile_begin; t < tile_end; ++t) {
+      const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, n = t / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * 14, h0 = th * 8;
+      mbar_wait(y_empty(sy), py ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(y_full(sy), p.x_box_bytes /* dy halo box bytes */);
+        // NR == 3: rows h0-1 .. h0+8 (10 rows);  NR == 1: rows (h0+1-r) .. +8
+        tma_load_4d(y_base + (uint32_t)sy * p.y_stage_bytes, &p.dy[p.yg_view[yg]], p.yg_c0[yg], w0 - 1,
+                    (NR == 3) ? (h0 - 1) : (h0 + 1 - r0), n, y_full(sy));
+      }
+      __syncwarp();
+      if (++sy == SY) { sy = 0; py ^= 1; }
+      mbar_wait(x_empty(sx), px ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(x_full(sx), (uint32_t)nxg * xg_bytes);
+        for (int g = 0; g < nxg; ++g)
+          tma_load_5d(x_base + (uint32_t)sx * p.x_stage_bytes + (uint32_t)g * xg_bytes, &p.x[p.xg_view[xg0 + g]],
+                      p.xg_c0[xg0 + g], 0, tw, h0, n, x_full(sx));
+      }
+      __syncwarp();
+      if (++sx == SX) { sx = 0; px ^= 1; }
+    }
+  } else if (warp == 1) {
+    int sx = 0, px = 0, sy = 0, py = 0;
+    const uint32_t lx = (p.GX == 64) ? LAYOUT_SW128 : LAYOUT_SW64, ly = (p.GY == 64) ? LAYOUT_SW128 : LAYOUT_SW64;
+    const uint32_t x_hi = (((8u * xrow) >> 4) & 0x3FFFu) | (1u << 14) | (lx << 29), y_hi = (((8u * yrow) >> 4) & 0x3FFFu) | (1u << 14) | (ly << 29);
+    const uint32_t x_lbo = ((xg_bytes >> 4) & 0x3FFFu) << 16, y_lbo = ((yrow >> 4) & 0x3FFFu) << 16;   // dy groups: one ROW apart
+    const uint32_t x_kstep = (16u * xrow) >> 4, y_kstep = (16u * yrow) >> 4;
+    for (int t = tile_begin; t < tile_end; ++t) {
+      mbar_wait(y_full(sy), py);
+      mbar_wait(x_full(sx), px);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t y_lo = (((y_base + (uint32_t)sy * p.y_stage_bytes) & 0x3FFFFu) >> 4) | y_lbo;
+        const uint32_t x_lo = (((x_base + (uint32_t)sx * p.x_stage_bytes) & 0x3FFFFu) >> 4) | x_lbo;
+        const uint32_t first = (t == tile_begin) ? 0u : 1u;
+        for (int ri = 0; ri < NR; ++ri) {
+          // window of kernel row r inside the halo tile: pixel offset (2-r)*16 for the 10-row box, 0 for the 8-row box
+          const uint32_t off_rows = (NR == 3) ? (uint32_t)((2 - ri) * 16) : 0u;
+          const uint32_t y_t = y_lo + ((off_rows * yrow) >> 4);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t ad = ((uint64_t)x_hi << 32) | (uint64_t)(x_lo + k * x_kstep);
+            const uint64_t bd = ((uint64_t)y_hi << 32) | (uint64_t)(y_t + k * y_kstep);
+            umma_bf16(tmem_base + (uint32_t)(ri * N3), ad, bd, p.idesc, first | (uint32_t)k);
+          }
+        }
+        tc_commit(x_empty(sx));
+        tc_commit(y_empty(sy));
+      }
+      __syncwarp();
+      if (++sx == SX) { sx = 0; px ^= 1; }
+      if (++sy == SY) { sy = 0; py ^= 1; }
+    }
+    if (elect_one()) tc_commit(acc_full);
+    __syncwarp();
+  } else {
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    const int g = row / p.GX;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    if (tile_end > tile_begin) {
+      const bool row_ok = g < nxg;
+      int ci = 0;
+      if (row_ok) ci = p.x_cstart[p.xg_view[xg0 + g]] + p.xg_c0[xg0 + g] + (row % p.GX);
+      const int co0 = p.y_cstart[p.yg_view[yg]] + p.yg_c0[yg];
+      for (int ri = 0; ri < NR; ++ri) {
+        const int r = r0 + ri;
+        for (int cc = 0; cc < N3; cc += 16) {
+          uint32_t rr[16];
+          tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ri * N3 + cc), rr);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int sp = cc / p.GY;                 // stacked group index: tap column s = 2 - sp
+            const int tap = r * 3 + (2 - sp);
+            const int co = co0 + (cc % p.GY);
+            float *dst = p.dw + ((long long)tap * p.Cout + co) * p.Cin + ci;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(dst + (long long)i * p.Cin, __uint_as_float(rr[i]));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
+}
+
 static bool tma_ok(const View &v) {
   return (((uintptr_t)v.ptr) % 16 == 0) && ((v.sn * 2) % 16 == 0) && ((v.sh * 2) % 16 == 0) && ((v.sw * 2) % 16 == 0) &&
          v.sw > 0 && v.sh > 0 && v.sn > 0;
@@ -426,8 +572,84 @@ static int wgrad_tc2(int N, int H, int W, const ViewList &xs, const ViewList &dy
   return (int)cudaGetLastError();
 }
 
+static int wgrad_tc3(int N, int H, int W, const ViewList &xs, const ViewList &dys, float *dw, cudaStream_t st) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return KS_EDRIVER;
+  WgradTc2Params p;
+  p.GX = 64; p.GY = 64;
+  for (int i = 0; i < xs.n; ++i) { if (xs.v[i].C % 32 || !tma_ok(xs.v[i])) return KS_EUNSUPPORTED; if (xs.v[i].C % 64) p.GX = 32; }
+  for (int i = 0; i < dys.n; ++i) { if (dys.v[i].C % 32 || !tma_ok(dys.v[i])) return KS_EUNSUPPORTED; if (dys.v[i].C % 64) p.GY = 32; }
+  p.n_xg = 0; p.n_yg = 0;
+  for (int i = 0; i < xs.n; ++i) for (int c0 = 0; c0 < xs.v[i].C; c0 += p.GX) { if (p.n_xg >= 64) return KS_EUNSUPPORTED; p.xg_view[p.n_xg] = (unsigned char)i; p.xg_c0[p.n_xg] = (short)c0; ++p.n_xg; }
+  for (int i = 0; i < dys.n; ++i) for (int c0 = 0; c0 < dys.v[i].C; c0 += p.GY) { if (p.n_yg >= 64) return KS_EUNSUPPORTED; p.yg_view[p.n_yg] = (unsigned char)i; p.yg_c0[p.n_yg] = (short)c0; ++p.n_yg; }
+  for (int i = 0; i <= KS_MAX_VIEWS; ++i) { p.x_cstart[i] = xs.cstart[i]; p.y_cstart[i] = dys.cstart[i]; }
+  p.Cin = xs.cstart[xs.n]; p.Cout = dys.cstart[dys.n];
+  p.MG = 128 / p.GX;
+  p.m_tiles = (p.n_xg + p.MG - 1) / p.MG;
+  p.n_tiles = p.n_yg; p.NG = 1; p.BN = p.GY;
+  p.TG = (p.GY == 32) ? 3 : 1;                 // kernel rows per CTA: 3 x (3*32) = 288 TMEM columns, or 1 x (3*64) = 192
+  p.tap_groups = 3 / p.TG;
+  p.N = N; p.H = H; p.W = W;
+  p.tiles_w = W / 14; p.tiles_h = (H + 7) / 8;
+  const long long tt = (long long)p.tiles_w * p.tiles_h * N;
+  if (tt > 0x7fffffffLL) return KS_EUNSUPPORTED;
+  p.total_tiles = (int)tt;
+  const int items = p.m_tiles * p.n_tiles * p.tap_groups;
+  const int ctas_per_sm = (p.TG == 3) ? 1 : 2;
+  int splits = (kNumSMs * ctas_per_sm + items - 1) / items;
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  p.splits = splits;
+  const int box_rows = (p.TG == 3) ? 10 : 8;
+  const uint32_t yrow = p.GY * 2u;
+  p.x_box_bytes = (uint32_t)box_rows * 16u * yrow;                      // dy halo box
+  p.y_stage_bytes = (((uint32_t)(box_rows * 16 + 2) * yrow + 1023u) / 1024u) * 1024u;
+  p.x_gstride = 128u * p.GX * 2u;
+  p.x_stage_bytes = 128u * 128u * 2u;
+  p.stack3 = 0;
+  uint32_t cols = 32; while (cols < (uint32_t)(p.TG * 3 * p.GY)) cols <<= 1;
+  if (cols > 512) return KS_EUNSUPPORTED;
+  p.tmem_cols = cols;
+  p.idesc = make_idesc_bf16(128, 3 * p.GY, 1, 1);
+  int SX = (p.TG == 3) ? 3 : 2, SY = (p.TG == 3) ? 3 : 2;
+  auto bytes = [&](int sx, int sy) { return (size_t)sx * p.x_stage_bytes + (size_t)sy * p.y_stage_bytes + 1024 + 256; };
+  if (bytes(SX, SY) > 220 * 1024) return KS_EUNSUPPORTED;
+  p.SX = SX; p.SY = SY;
+  p.dw = dw;
+  for (int i = 0; i < xs.n; ++i) {      // x: 5-D map (C, 14, W/14, H, N), 16-wide box -> pad columns are out of bounds = 0
+    const View &v = xs.v[i];
+    cuuint64_t dims[5] = {(cuuint64_t)v.C, 14, (cuuint64_t)(W / 14), (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sw * 2 * 14, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.GX, 16, 1, 8, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&p.x[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void *)v.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     p.GX == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return KS_EDRIVER;
+  }
+  for (int i = 0; i < dys.n; ++i) {
+    int rc = encode_act_map(&p.dy[i], dys.v[i], N, H, W, p.GY, 16, box_rows, p.GY == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  wgrad_tc3_kernel<<<dim3(items, splits), 192, bytes(SX, SY), st>>>(p);
+  return (int)cudaGetLastError();
+}
+
 int wgrad_tc(int N, int H, int W, int ksize, const ViewList &xs, const ViewList &dys, float *dw, cudaStream_t st) {
   if (g_opt.tc_disable || g_opt.wgrad_tc_disable) return KS_EUNSUPPORTED;
+  // Cin == 32 (one 32-channel group): the halo kernel stacks the three taps of a kernel row along M instead (v2, stack3)
+  const bool single32 = (xs.n == 1 && xs.v[0].C == 32);
+  if (ksize == 3 && W % 14 == 0 && !g_opt.v1 && g_opt.wgrad_mode != 2 && !(single32 && g_opt.wgrad_mode == 0)) {
+    const int rc = wgrad_tc3(N, H, W, xs, dys, dw, st);
+    if (rc != KS_EUNSUPPORTED) return rc;
+  }
   if (ksize == 3 && W % 14 == 0 && !g_opt.v1) {
     const int rc = wgrad_tc2(N, H, W, xs, dys, dw, st);
     if (rc != KS_EUNSUPPORTED) return rc;

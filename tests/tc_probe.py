@@ -98,16 +98,20 @@ def wgrad_case(ops, name, N, H, W, ks, x_specs, dy_specs, gen):
     got = torch.zeros_like(ref)
     ops.conv2d_wgrad(N, H, W, ks, xs, dys, ref, False, IMPL_SIMT)
     torch.cuda.synchronize()
-    try:
-        ops.conv2d_wgrad(N, H, W, ks, xs, dys, got, False, IMPL_TC)
-        torch.cuda.synchronize()
-        e1 = rel_l2(got, ref)
-        ops.conv2d_wgrad(N, H, W, ks, xs, dys, got, True, IMPL_TC)  # accumulate: 2x
-        torch.cuda.synchronize()
-        e2 = rel_l2(got, 2 * ref)
-        return {"assign": e1, "accumulate": e2}
-    except KsError as e:
-        return {"error": str(e)}
+    res = {}
+    for mode, tag in ((0, ""), (2, "_halo")):
+        ops.set_option("wgrad_mode", mode)
+        try:
+            ops.conv2d_wgrad(N, H, W, ks, xs, dys, got, False, IMPL_TC)
+            torch.cuda.synchronize()
+            res["assign" + tag] = rel_l2(got, ref)
+            ops.conv2d_wgrad(N, H, W, ks, xs, dys, got, True, IMPL_TC)  # accumulate: 2x
+            torch.cuda.synchronize()
+            res["accumulate" + tag] = rel_l2(got, 2 * ref)
+        except KsError as e:
+            res["error" + tag] = str(e)
+    ops.set_option("wgrad_mode", 0)
+    return res
 
 
 def main():
@@ -137,6 +141,10 @@ def main():
         "K_k1_convT": (2, 8, 8, 1, [(64, 64, 0, P)], [(64, 64, 0, "phases")]),
         "L_k3_x64_dy64_odd": (3, 20, 12, 3, [(64, 64, 0, P)], [(64, 64, 0, P)]),
         "M_k3_big": (4, 56, 56, 3, [(192, 256, 0, P), (128, 128, 0, P)], [(64, 64, 0, P)]),
+        "N_k3_x32_dy32_w28": (3, 16, 28, 3, [(32, 32, 0, P)], [(32, 32, 0, P)]),
+        "O_k3_x160_dy32_w28": (2, 24, 28, 3, [(96, 96, 0, P), (64, 64, 0, P)], [(32, 96, 32, P)]),
+        "P_k3_x128_dy128_w14": (4, 14, 14, 3, [(128, 128, 0, P)], [(128, 128, 0, P)]),
+        "Q_k3_x64_dy64_w56": (2, 56, 56, 3, [(64, 192, 64, P)], [(64, 64, 0, P)]),
     }
     for name, (N, H, W, ks, xs, ys) in wgrad_cases.items():
         report["wgrad"][name] = wgrad_case(ops, name, N, H, W, ks, xs, ys, gen)
