@@ -168,7 +168,8 @@ def conv_roofline(eng, xa, xb, mk, pk, pk_kind):
 
     ops.conv2d, ops.conv2d_wgrad = timed(orig_conv, "conv"), timed(orig_wgrad, "wgrad")
     try:
-        eng.train_step(xa, xb, mk)
+        eng._fwd_loss_bwd(xa, xb, mk)     # no all-reduce here: this leg runs on rank 0 only
+        eng._optimizer()
         torch.cuda.synchronize()
     finally:
         ops.conv2d, ops.conv2d_wgrad = orig_conv, orig_wgrad

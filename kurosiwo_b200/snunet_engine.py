@@ -527,9 +527,10 @@ class SNUNetEngine:
             self.replay = self.graph.replay
         else:
             ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ga):
+            # thread_local: NCCL's watchdog thread may issue CUDA calls while this thread captures
+            with torch.cuda.graph(ga, capture_error_mode="thread_local"):
                 self._fwd_loss_bwd(xA, xB, mask)
-            with torch.cuda.graph(gb):
+            with torch.cuda.graph(gb, capture_error_mode="thread_local"):
                 self._optimizer()
             self.graph = (ga, gb)
 
