@@ -76,6 +76,10 @@ typedef struct ks_permute_job {
   void *dst;
   int64_t total, s0, s1, s2, s3;
   int32_t d1, d2, d3, src_dtype, dst_dtype, accumulate;
+  /* dst_strided != 0: element (i0,i1,i2,i3) goes to dst[i0*t0+i1*t1+i2*t2+i3*t3] instead of the contiguous position
+   * (writes a logical sub-block into a channel-padded buffer whose padding stays zero). */
+  int64_t t0, t1, t2, t3;
+  int32_t dst_strided, _pad;
 } ks_permute_job_t;
 int ks_permute_cast_batched(const ks_permute_job_t *jobs_dev, const int32_t *chunks_dev, int n_chunks, void *stream);
 
@@ -159,7 +163,9 @@ int ks_channel_sum(int dtype, int N, int H, int W, const ks_view_t *x, float *ou
 /* ---- ECAM head (snunet.py:49-62,146-151) ------------------------------- */
 /* Global avg+max pool of cat(x_0..x_{J-1}) (J*Cb channels) and of intra=sum_j x_j
  * (Cb channels).  pooled: fp32 [N][2][(J+1)*Cb]  (avg | max; cat channels then intra);
- * argmax: int32 [N][(J+1)*Cb] flat pixel index of the first maximum. */
+ * argmax: int32 [N][(J+1)*Cb] flat pixel index of the first maximum - reset to INT_MAX here and FILLED IN by
+ * ks_ecam_final (which reads the same tensors anyway and compares against the pooled maxima).
+ * scratch: N*(J+1)*Cb 8-byte words, contents ignored. */
 int ks_ecam_pool(int dtype, int N, int H, int W, const ks_view_t *xs, int J,
                  float *pooled, int *argmax, unsigned long long *scratch, void *stream);
 
@@ -169,10 +175,12 @@ int ks_ecam_gates(int N, int Cb, int J, int hid, int hid1, const float *pooled,
                   const float *w_fc1, const float *w_fc2, const float *w1_fc1, const float *w1_fc2,
                   float *gates, float *hidden, void *stream);
 
-/* logits[n,k,h,w] = bf[k] + sum_c wf[k][c] * ca[n,c]*(x[c] + ca1[n, c%Cb])   (NCHW fp32 out) */
+/* logits[n,k,h,w] = bf[k] + sum_c wf[k][c] * ca[n,c]*(x[c] + ca1[n, c%Cb])   (NCHW fp32 out).
+ * pooled/argmax (both or neither): the buffers of ks_ecam_pool; argmax[n][c] = min(argmax, first pixel whose value
+ * equals the pooled maximum) - what aten's adaptive_max_pool2d backward routes the gradient to. */
 int ks_ecam_final(int dtype, int N, int H, int W, const ks_view_t *xs, int J,
                   const float *gates, const float *wf, const float *bf, int K,
-                  float *logits, void *stream);
+                  float *logits, const float *pooled, int *argmax, void *stream);
 
 /* Pixel reductions of the head backward (callee zeroes `red`):
  * red: fp64 [N][K*J*Cb + K] = { B[k][c] = sum_px dlogits[k]*x[c] , D[k] = sum_px dlogits[k] }. */
@@ -191,6 +199,28 @@ int ks_ecam_gates_bwd(int N, int Cb, int J, int hid, int hid1, int K, const floa
 int ks_ecam_bwd_apply(int dtype, int N, int H, int W, int J, int Cb,
                       const float *gates, const float *wf, int K, const float *dlogits,
                       const float *dpooled, const int *argmax, const ks_view_t *dxs, void *stream);
+
+/* ---- Siamese U-Net passes (models/siam_conc.py, models/siam_diff.py) ------ */
+/* nn.Softmax(dim=1) (siam_conc.py:93,177) / nn.LogSoftmax(dim=1) (siam_diff.py:93,173) over the first K channels of the
+ * NHWC view z (the conv engine pads the classifier's Cout to 16); out: NCHW fp32 [N][K][H][W]. */
+int ks_softmax_head_fwd(int dtype, int N, int H, int W, const ks_view_t *z, int K, int log_mode,
+                        float *out, void *stream);
+/* dz[.., k] = softmax / log-softmax backward from the saved output `out` and its gradient `dout` (both NCHW fp32);
+ * channels K..dz->C-1 are written as 0. */
+int ks_softmax_head_bwd(int dtype, int N, int H, int W, const float *out, const float *dout, int K,
+                        int log_mode, const ks_view_t *dz, void *stream);
+/* nn.Dropout2d masks (siam_conc.py:21...): mask[i] = 1/(1-p) with probability 1-p, else 0, i in [0, n) (n = sum over
+ * layers of N*C).  The stream is a pure function of (seed, *step_ptr, i); step_ptr is a DEVICE counter so that a
+ * captured CUDA graph draws fresh masks on every replay. */
+int ks_dropout_mask(float *mask, int64_t n, float p, uint64_t seed, const int *step_ptr, void *stream);
+/* x[n,h,w,c] *= m[n*C + c] in place: Dropout2d forward on activations, backward on gradients. */
+int ks_channel_scale(int dtype, int N, int H, int W, const ks_view_t *x, const float *m, void *stream);
+/* out = |a - b|  (siam_diff.py:141,150,158,165: torch.abs(x_1 - x_2) skip connections). */
+int ks_absdiff_fwd(int dtype, int N, int H, int W, const ks_view_t *a, const ks_view_t *b,
+                   const ks_view_t *out, void *stream);
+/* da (+)= sign(a-b)*g, db (+)= -sign(a-b)*g  (sign(0) = 0 as in aten). */
+int ks_absdiff_bwd(int dtype, int N, int H, int W, const ks_view_t *a, const ks_view_t *b, const ks_view_t *g,
+                   const ks_view_t *da, int accumulate_a, const ks_view_t *db, int accumulate_b, void *stream);
 
 /* ---- loss (utilities/bce_and_dice.py:18-24, utilities/dice.py:93-137) --- */
 /* Fused softmax -> weighted CE(ignore_index) + Dice, forward + gradient + argmax.

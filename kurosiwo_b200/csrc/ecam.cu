@@ -30,93 +30,90 @@ __device__ __forceinline__ const T *vptr(const View &v, int n, int h, int w, int
 
 constexpr int kMaxJ = 4;
 
-// ---- pooling: sums (fp32 atomics) and packed (max, first index) ---------------------------
-// Thread = (pixel lane, 8-channel group g of the J*Cb concat channels): 24 registers of running state per thread, one
-// 16-byte load per pixel, UNR pixels in flight.  The intra tensor (sum over the J views) is formed with shuffles across
-// the lanes of a pixel that hold the same channels of different views; the lanes of view 0 track its pool statistics.
+// ---- pooling: per-(n,c) sum and max of the J views and of intra = sum_j x_j -------------------------------
+// Thread = (pixel lane, 8-channel vector) and handles ALL J views of its channels, so the intra sum is thread-local
+// (no shuffles).  Only VALUES are tracked here (80 registers of state); the index of the first maximum - needed by
+// the backward pass - is recovered by ecam_final, which reads the same tensors anyway (equality test + atomicMin).
+__device__ __forceinline__ unsigned int fkey(float v) {          // order-preserving float -> uint
+  const unsigned int b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
-ecam_pool_kernel(ViewList xs, int J, int Cb, int H, int W, float *pooled, unsigned long long *scratch) {
+ecam_pool_kernel(ViewList xs, int J, int Cb, int H, int W, float *pooled, unsigned int *maxkey) {
   extern __shared__ unsigned char smem_raw[];
   const int CC = J * Cb, CT = (J + 1) * Cb;
-  unsigned long long *smax = reinterpret_cast<unsigned long long *>(smem_raw);
+  unsigned int *smax = reinterpret_cast<unsigned int *>(smem_raw);
   float *ssum = reinterpret_cast<float *>(smax + CT);
-  for (int i = threadIdx.x; i < CT; i += blockDim.x) { smax[i] = 0ull; ssum[i] = 0.f; }
+  for (int i = threadIdx.x; i < CT; i += blockDim.x) { smax[i] = 0u; ssum[i] = 0.f; }
   __syncthreads();
   const int n = blockIdx.y;
-  const int G = CC / 8, CVb = Cb / 8, rows = blockDim.x / G;   // G lanes per pixel; lane g -> view g / CVb, vector g % CVb
-  const int g = threadIdx.x % G, ty = threadIdx.x / G;
-  const int j = g / CVb, cb0 = (g % CVb) * 8;
+  const int CVb = Cb / 8, rows = blockDim.x / CVb;
+  const int tx = threadIdx.x % CVb, ty = threadIdx.x / CVb;
   const int HW = H * W;
-  const View &xv = xs.v[j];
-  const T *xp = reinterpret_cast<const T *>(xv.ptr) + (long long)n * xv.sn + cb0;
-  float sum[8], best[8], isum[8], ibest[8]; unsigned int bidx[8], ibidx[8];
+  float sum[kMaxJ][8], best[kMaxJ + 1][8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { sum[k] = 0.f; best[k] = -INFINITY; bidx[k] = 0u; isum[k] = 0.f; ibest[k] = -INFINITY; ibidx[k] = 0u; }
-  constexpr int UNR = 4;
-  const int stride = gridDim.x * rows;
-  const int pmax = ((HW + rows - 1) / rows) * rows;        // uniform trip count within a warp (shuffles inside)
-  for (int p0 = blockIdx.x * rows + ty; p0 < pmax; p0 += stride * UNR) {
-    float f[UNR][8];
+  for (int j = 0; j <= kMaxJ; ++j)
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int p = p0 + u * stride;
-      if (p < HW) ld8(xp + (long long)(p / W) * xv.sh + (long long)(p % W) * xv.sw, f[u]);
-      else {
+    for (int k = 0; k < 8; ++k) { if (j < kMaxJ) sum[j][k] = 0.f; best[j][k] = -INFINITY; }
+  for (int p = blockIdx.x * rows + ty; p < HW; p += gridDim.x * rows) {
+    const int h = p / W, w = p % W;
+    float f[kMaxJ][8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) f[u][k] = 0.f;
+    for (int j = 0; j < kMaxJ; ++j)
+      if (j < J) ld8(vptr<T>(xs.v[j], n, h, w, tx * 8), f[j]);
+    float it[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) it[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxJ; ++j)
+      if (j < J) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sum[j][k] += f[j][k]; best[j][k] = fmaxf(best[j][k], f[j][k]); it[k] += f[j][k]; }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int p = p0 + u * stride;
-      const bool ok = p < HW;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float it = f[u][k];
-        for (int o = CVb; o < G; o <<= 1) it += __shfl_xor_sync(0xffffffffu, it, o);   // sum over the J views
-        if (ok) {
-          sum[k] += f[u][k];
-          if (f[u][k] > best[k]) { best[k] = f[u][k]; bidx[k] = (unsigned)p; }
-          isum[k] += it;
-          if (it > ibest[k]) { ibest[k] = it; ibidx[k] = (unsigned)p; }
-        }
-      }
-    }
+    for (int k = 0; k < 8; ++k) best[kMaxJ][k] = fmaxf(best[kMaxJ][k], it[k]);
   }
-  // combine the pixel lanes of a warp (lanes sharing g), then one smem atomic per warp and channel
+  // combine the pixel lanes of a warp (lanes sharing tx), then one smem atomic per warp and channel
   const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float sv = sum[k], iv = isum[k];
-    unsigned long long mv = pack_max(best[k], bidx[k]), imv = pack_max(ibest[k], ibidx[k]);
-    for (int o = G; o < 32; o <<= 1) {
-      sv += __shfl_xor_sync(0xffffffffu, sv, o);
-      iv += __shfl_xor_sync(0xffffffffu, iv, o);
-      const unsigned long long ov = __shfl_xor_sync(0xffffffffu, mv, o), iov = __shfl_xor_sync(0xffffffffu, imv, o);
-      mv = ov > mv ? ov : mv; imv = iov > imv ? iov : imv;
-    }
-    if (lane < G && ty < rows) {
-      atomicAdd(&ssum[g * 8 + k], sv);
-      atomicMax(&smax[g * 8 + k], mv);
-      if (j == 0) { atomicAdd(&ssum[CC + cb0 + k], iv); atomicMax(&smax[CC + cb0 + k], imv); }
+  for (int j = 0; j <= kMaxJ; ++j) {
+    if (j < J || j == kMaxJ) {
+      const int jj = (j == kMaxJ) ? J : j;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float mv = best[j][k];
+        float sv = (j < kMaxJ) ? sum[j][k] : 0.f;
+        for (int o = CVb; o < 32; o <<= 1) {
+          mv = fmaxf(mv, __shfl_xor_sync(0xffffffffu, mv, o));
+          sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        }
+        if (lane < CVb) {
+          const int c = jj * Cb + tx * 8 + k;
+          atomicMax(&smax[c], fkey(mv));
+          if (j < kMaxJ) { atomicAdd(&ssum[c], sv); atomicAdd(&ssum[CC + tx * 8 + k], sv); }   // avg(intra) = sum_j avg_j
+        }
+      }
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < CT; i += blockDim.x) {
     atomicAdd(pooled + ((size_t)n * 2 + 0) * CT + i, ssum[i]);
-    atomicMax(scratch + (size_t)n * CT + i, smax[i]);
+    atomicMax(maxkey + (size_t)n * CT + i, smax[i]);
   }
 }
 
-__global__ void ecam_pool_finalize_kernel(int N, int CT, int HW, float *pooled, const unsigned long long *scratch, int *argmax) {
+__global__ void ecam_pool_finalize_kernel(int N, int CT, int HW, float *pooled, const unsigned int *maxkey, int *argmax) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * CT) return;
   const int n = i / CT, c = i % CT;
   pooled[((size_t)n * 2 + 0) * CT + c] *= (1.0f / (float)HW);
-  const unsigned long long k = scratch[i];
-  pooled[((size_t)n * 2 + 1) * CT + c] = unpack_max_val(k);
-  argmax[i] = (int)(0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFull));
+  pooled[((size_t)n * 2 + 1) * CT + c] = fkey_inv(maxkey[i]);
+  argmax[i] = 0x7fffffff;       // filled by ecam_final (first pixel whose value equals the maximum)
 }
 
 // ---- gates: one block per sample -----------------------------------------------------------
@@ -153,61 +150,88 @@ ecam_gates_kernel(int Cb, int J, int hid, int hid1, const float *__restrict__ po
   ca_forward(Cb, hid1, avg + CC, mx + CC, w1_fc1, w1_fc2, g + CC, ha + hid, hm + hid, sh);
 }
 
-// ---- final: gated sum + 1x1 classifier -> NCHW fp32 logits --------------------------------
-// Thread = (pixel lane, 8-channel group g of the J*Cb concat channels): the effective weights ca*wf of the
-// group live in registers, each x access is one 16-byte load, the K partial sums are shuffle-reduced over
-// the G = J*Cb/8 lanes of a pixel.
+// ---- final: gated sum + 1x1 classifier -> NCHW fp32 logits (+ arg-max discovery) -----------------------------
+// Thread = (pixel lane, 8-channel vector), all J views: 4 x 16-byte loads, effective weights ca*wf from shared memory
+// (LDS.128, conflict-free: the 4 vector lanes read 4 adjacent 32-byte runs), partial logits reduced over the CVb vector
+// lanes.  While the values are in registers, any element equal to its channel's pooled maximum records its pixel with
+// atomicMin -> argmax[n][c] = FIRST maximum (what aten adaptive_max_pool2d's backward routes to).
 template <typename T, int K>
 __global__ void __launch_bounds__(256)
 ecam_final_kernel(ViewList xs, int J, int Cb, int H, int W, const float *__restrict__ gates,
-                  const float *__restrict__ wf, const float *__restrict__ bf, float *logits) {
+                  const float *__restrict__ wf, const float *__restrict__ bf, const float *__restrict__ pooled,
+                  int *argmax, float *logits) {
+  extern __shared__ float sm[];
   const int n = blockIdx.y, CC = J * Cb, CT = (J + 1) * Cb, HW = H * W;
-  const int G = CC / 8, rows = blockDim.x / G;          // G is a power of two <= 32 (checked by the launcher)
-  const int g = threadIdx.x % G, ty = threadIdx.x / G;
-  const int c0 = g * 8, j = c0 / Cb, cb0 = c0 % Cb;
-  const float *gt = gates + (size_t)n * CT;
-  float we[K][8], cst[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    float part = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { we[k][i] = wf[k * CC + c0 + i] * gt[c0 + i]; part += we[k][i] * gt[CC + cb0 + i]; }
-    for (int o = 1; o < G; o <<= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    cst[k] = part + bf[k];
+  float *weff = sm;                 // [J][K][Cb]   ca*wf, view-major so that a thread's weights are contiguous runs
+  float *cst = weff + K * CC;       // [K]
+  float *smx = cst + 4;             // [CT] pooled maxima of this sample
+  const float *g = gates + (size_t)n * CT;
+  for (int i = threadIdx.x; i < K * CC; i += blockDim.x) {
+    const int j = i / (K * Cb), k = (i / Cb) % K, cb = i % Cb;
+    weff[i] = wf[k * CC + j * Cb + cb] * g[j * Cb + cb];
   }
-  const View &xv = xs.v[j];
-  const T *xp = reinterpret_cast<const T *>(xv.ptr) + (long long)n * xv.sn + cb0;
+  for (int i = threadIdx.x; i < CT; i += blockDim.x) smx[i] = pooled ? pooled[((size_t)n * 2 + 1) * CT + i] : 0.f;
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float s = bf[threadIdx.x];
+    for (int j = 0; j < J; ++j)
+      for (int cb = 0; cb < Cb; ++cb) s += weff[(j * K + threadIdx.x) * Cb + cb] * g[CC + cb];
+    cst[threadIdx.x] = s;
+  }
+  __syncthreads();
+  const int CVb = Cb / 8, rows = blockDim.x / CVb;
+  const int tx = threadIdx.x % CVb, ty = threadIdx.x / CVb;
+  int *am = argmax ? argmax + (size_t)n * CT : nullptr;
+  float mx[kMaxJ + 1][8];           // pooled maxima of this thread's channels (register-resident)
+#pragma unroll
+  for (int j = 0; j <= kMaxJ; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mx[j][i] = (j < J) ? smx[j * Cb + tx * 8 + i] : (j == kMaxJ ? smx[CC + tx * 8 + i] : 0.f);
   const int pmax = ((HW + rows - 1) / rows) * rows;
-  constexpr int UNR = 4;
-  const int stride = gridDim.x * rows;
-  for (int p0 = blockIdx.x * rows + ty; p0 < pmax; p0 += stride * UNR) {
-    float f[UNR][8];
+  for (int p = blockIdx.x * rows + ty; p < pmax; p += gridDim.x * rows) {
+    const bool ok = p < HW;
+    float acc[K];
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int p = p0 + u * stride;
-      if (p < HW) ld8(xp + (long long)(p / W) * xv.sh + (long long)(p % W) * xv.sw, f[u]);
-      else {
+    for (int k = 0; k < K; ++k) acc[k] = 0.f;
+    if (ok) {
+      const int h = p / W, w = p % W;
+      float f[kMaxJ][8], it[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[u][i] = 0.f;
+      for (int j = 0; j < kMaxJ; ++j)
+        if (j < J) ld8(vptr<T>(xs.v[j], n, h, w, tx * 8), f[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) it[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxJ; ++j)
+        if (j < J) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const float4 w0 = *reinterpret_cast<const float4 *>(weff + (j * K + k) * Cb + tx * 8);
+            const float4 w1 = *reinterpret_cast<const float4 *>(weff + (j * K + k) * Cb + tx * 8 + 4);
+            acc[k] = fmaf(f[j][0], w0.x, acc[k]); acc[k] = fmaf(f[j][1], w0.y, acc[k]);
+            acc[k] = fmaf(f[j][2], w0.z, acc[k]); acc[k] = fmaf(f[j][3], w0.w, acc[k]);
+            acc[k] = fmaf(f[j][4], w1.x, acc[k]); acc[k] = fmaf(f[j][5], w1.y, acc[k]);
+            acc[k] = fmaf(f[j][6], w1.z, acc[k]); acc[k] = fmaf(f[j][7], w1.w, acc[k]);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            it[i] += f[j][i];
+            if (am && f[j][i] == mx[j][i]) atomicMin(am + j * Cb + tx * 8 + i, p);
+          }
+        }
+      if (am) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (it[i] == mx[kMaxJ][i]) atomicMin(am + CC + tx * 8 + i, p);
       }
     }
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int p = p0 + u * stride;
-      float acc[K];
+    for (int k = 0; k < K; ++k)
+      for (int o = 1; o < CVb; o <<= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    if (ok) {
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        acc[k] = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[k] = fmaf(f[u][i], we[k][i], acc[k]);
-        for (int o = 1; o < G; o <<= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-      }
-      if (p < HW && g < K) {
-        float v = acc[0] + cst[0];
-#pragma unroll
-        for (int k = 1; k < K; ++k) if (g == k) v = acc[k] + cst[k];
-        logits[((size_t)n * K + g) * HW + p] = v;
-      }
+      for (int k = 0; k < K; ++k)
+        if ((k % CVb) == tx) logits[((size_t)n * K + k) * HW + p] = acc[k] + cst[k];
     }
   }
 }
@@ -220,9 +244,13 @@ ecam_bwd_reduce_kernel(ViewList xs, int J, int Cb, int H, int W, const float *__
   const int n = blockIdx.y, CC = J * Cb, HW = H * W, RT = K * CC + K;
   for (int i = threadIdx.x; i < RT; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
-  const int G = CC / 8, rows = blockDim.x / G;
-  const int g = threadIdx.x % G, ty = threadIdx.x / G;
-  const int c0 = g * 8, j = c0 / Cb, cb0 = c0 % Cb;
+  // warp -> view j (a warp load covers 32/CVb consecutive pixels of ONE view: 512 contiguous bytes at Cb = 32);
+  // lane -> (pixel lane, 8-channel vector)
+  const int CVb = Cb / 8, ppw = 32 / CVb;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = warp % J, tx = lane % CVb;
+  const int rows = (blockDim.x >> 5) / J * ppw, ty = (warp / J) * ppw + lane / CVb;
+  const int cb0 = tx * 8, c0 = j * Cb + cb0;
   const View &xv = xs.v[j];
   const T *xp = reinterpret_cast<const T *>(xv.ptr) + (long long)n * xv.sn + cb0;
   float B[K][8], D[K];
@@ -259,19 +287,18 @@ ecam_bwd_reduce_kernel(ViewList xs, int J, int Cb, int H, int W, const float *__
         for (int i = 0; i < 8; ++i) B[k][i] = fmaf(dl[u][k], f[u][i], B[k][i]);
       }
   }
-  // lanes of a warp that share g (pixel lanes) are combined by shuffles, then one smem atomic per warp and value
-  const int lane = threadIdx.x & 31;
+  // the pixel lanes of a warp (lanes sharing tx) are combined by shuffles, then one smem atomic per warp and value
 #pragma unroll
   for (int k = 0; k < K; ++k) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float v = B[k][i];
-      for (int o = G; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane < G) atomicAdd(&sacc[k * CC + c0 + i], v);
+      for (int o = CVb; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane < CVb) atomicAdd(&sacc[k * CC + c0 + i], v);
     }
     float d = D[k];
-    for (int o = G; o < 32; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-    if (lane == 0) atomicAdd(&sacc[K * CC + k], d);
+    for (int o = CVb; o < 32; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (lane == 0 && j == 0) atomicAdd(&sacc[K * CC + k], d);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < RT; i += blockDim.x) atomicAdd(red + (size_t)n * RT + i, (double)sacc[i]);
@@ -359,9 +386,11 @@ ecam_bwd_apply_kernel(ViewList dxs, int J, int Cb, int H, int W, const float *__
                       const float *__restrict__ wf, const float *__restrict__ dlogits,
                       const float *__restrict__ dpooled, const int *__restrict__ argmax) {
   const int n = blockIdx.y, CC = J * Cb, CT = (J + 1) * Cb, HW = H * W;
-  const int G = CC / 8, rows = blockDim.x / G;
-  const int g = threadIdx.x % G, ty = threadIdx.x / G;
-  const int c0 = g * 8, j = c0 / Cb, cb0 = c0 % Cb;
+  const int CVb = Cb / 8, ppw = 32 / CVb;               // warp -> view, lane -> (pixel lane, 8-channel vector)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = warp % J, tx = lane % CVb;
+  const int rows = (blockDim.x >> 5) / J * ppw, ty = (warp / J) * ppw + lane / CVb;
+  const int cb0 = tx * 8, c0 = j * Cb + cb0;
   const float *gt = gates + (size_t)n * CT;
   const float *da = dpooled + ((size_t)n * 2 + 0) * CT, *dm = dpooled + ((size_t)n * 2 + 1) * CT;
   const int *am = argmax + (size_t)n * CT;
@@ -411,7 +440,6 @@ static int check_views(const ks_view_t *xs, int J, int &Cb, int esize) {
   if (!xs || J < 1 || J > kMaxJ) return KS_EINVAL;
   Cb = xs[0].C;
   if (Cb % 8 != 0 || Cb > 64 || ((Cb / 8) & (Cb / 8 - 1)) != 0) return KS_EUNSUPPORTED;
-  if ((J * Cb / 8) > 32 || ((J * Cb / 8) & (J * Cb / 8 - 1)) != 0) return KS_EUNSUPPORTED;   // lanes per pixel must be a power of two
   for (int j = 0; j < J; ++j) {
     if (xs[j].C != Cb || !xs[j].ptr) return KS_EINVAL;
     if (((uintptr_t)xs[j].ptr % 16) || (xs[j].sn * esize) % 16 || (xs[j].sh * esize) % 16 || (xs[j].sw * esize) % 16) return KS_EUNSUPPORTED;
@@ -430,16 +458,17 @@ extern "C" int ks_ecam_pool(int dtype, int N, int H, int W, const ks_view_t *xs,
   ViewList vl; rc = make_view_list(xs, J, vl); if (rc) return rc;
   const int CT = (J + 1) * Cb;
   cudaStream_t st = (cudaStream_t)stream;
+  unsigned int *maxkey = reinterpret_cast<unsigned int *>(scratch);     // first 4 bytes of each 8-byte scratch slot pair
   cudaError_t e = cudaMemsetAsync(pooled, 0, sizeof(float) * (size_t)N * 2 * CT, st); if (e) return (int)e;
-  e = cudaMemsetAsync(scratch, 0, sizeof(unsigned long long) * (size_t)N * CT, st); if (e) return (int)e;
-  const int rows = 256 / (J * Cb / 8);
-  int chunks = (H * W + rows * 32 - 1) / (rows * 32); if (chunks < 1) chunks = 1;
-  const int cap = (kNumSMs * 8 + N - 1) / N; if (chunks > cap) chunks = cap;
-  const size_t smem = (size_t)CT * (sizeof(unsigned long long) + sizeof(float));
-  if (dtype == KS_F32) ecam_pool_kernel<float><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, pooled, scratch);
-  else if (dtype == KS_BF16) ecam_pool_kernel<__nv_bfloat16><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, pooled, scratch);
+  e = cudaMemsetAsync(maxkey, 0, sizeof(unsigned int) * (size_t)N * CT, st); if (e) return (int)e;
+  const int rows = 256 / (Cb / 8);
+  int chunks = (H * W + rows * 8 - 1) / (rows * 8); if (chunks < 1) chunks = 1;
+  const int cap = (kNumSMs * 6 + N - 1) / N; if (chunks > cap) chunks = cap;
+  const size_t smem = (size_t)CT * (sizeof(unsigned int) + sizeof(float));
+  if (dtype == KS_F32) ecam_pool_kernel<float><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, pooled, maxkey);
+  else if (dtype == KS_BF16) ecam_pool_kernel<__nv_bfloat16><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, pooled, maxkey);
   else return KS_EINVAL;
-  ecam_pool_finalize_kernel<<<(N * CT + 255) / 256, 256, 0, st>>>(N, CT, H * W, pooled, scratch, argmax);
+  ecam_pool_finalize_kernel<<<(N * CT + 255) / 256, 256, 0, st>>>(N, CT, H * W, pooled, maxkey, argmax);
   KS_LAUNCH_RET();
 }
 
@@ -454,18 +483,20 @@ extern "C" int ks_ecam_gates(int N, int Cb, int J, int hid, int hid1, const floa
 
 extern "C" int ks_ecam_final(int dtype, int N, int H, int W, const ks_view_t *xs, int J,
                              const float *gates, const float *wf, const float *bf, int K,
-                             float *logits, void *stream) {
+                             float *logits, const float *pooled, int *argmax, void *stream) {
   KS_CHECK_ARG(gates && wf && bf && logits && N > 0 && H > 0 && W > 0);
+  KS_CHECK_ARG((pooled == nullptr) == (argmax == nullptr));
   if (K != 3) return KS_EUNSUPPORTED;
   int Cb; int rc = check_views(xs, J, Cb, dtype == KS_F32 ? 4 : 2); if (rc) return rc;
   ViewList vl; rc = make_view_list(xs, J, vl); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const int rows_f = 256 / (J * Cb / 8);
-  int chunks = (H * W + rows_f * 32 - 1) / (rows_f * 32); if (chunks < 1) chunks = 1;
-  const int cap = (kNumSMs * 16 + N - 1) / N; if (chunks > cap) chunks = cap;
-  const size_t smem = 0;
-  if (dtype == KS_F32) ecam_final_kernel<float, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, gates, wf, bf, logits);
-  else if (dtype == KS_BF16) ecam_final_kernel<__nv_bfloat16, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, gates, wf, bf, logits);
+  const int rows_f = 256 / (Cb / 8);
+  int chunks = (H * W + rows_f * 8 - 1) / (rows_f * 8); if (chunks < 1) chunks = 1;
+  const int cap = (kNumSMs * 8 + N - 1) / N; if (chunks > cap) chunks = cap;
+  const int CC = J * Cb, CT = (J + 1) * Cb;
+  const size_t smem = sizeof(float) * (size_t)(K * CC + 4 + CT);
+  if (dtype == KS_F32) ecam_final_kernel<float, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, gates, wf, bf, pooled, argmax, logits);
+  else if (dtype == KS_BF16) ecam_final_kernel<__nv_bfloat16, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, gates, wf, bf, pooled, argmax, logits);
   else return KS_EINVAL;
   KS_LAUNCH_RET();
 }
@@ -479,12 +510,12 @@ extern "C" int ks_ecam_bwd_reduce(int dtype, int N, int H, int W, const ks_view_
   cudaStream_t st = (cudaStream_t)stream;
   const int RT = K * J * Cb + K;
   cudaError_t e = cudaMemsetAsync(red, 0, sizeof(double) * (size_t)N * RT, st); if (e) return (int)e;
-  const int rows = 256 / (J * Cb / 8);
-  int chunks = (H * W + rows * 32 - 1) / (rows * 32); if (chunks < 1) chunks = 1;
+  const int nthr = 32 * J * (8 / J), rows = (8 / J) * (32 / (Cb / 8));
+  int chunks = (H * W + rows * 16 - 1) / (rows * 16); if (chunks < 1) chunks = 1;
   const int cap = (kNumSMs * 8 + N - 1) / N; if (chunks > cap) chunks = cap;
   const size_t smem = sizeof(float) * (size_t)RT;
-  if (dtype == KS_F32) ecam_bwd_reduce_kernel<float, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, dlogits, red);
-  else if (dtype == KS_BF16) ecam_bwd_reduce_kernel<__nv_bfloat16, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, dlogits, red);
+  if (dtype == KS_F32) ecam_bwd_reduce_kernel<float, 3><<<dim3(chunks, N), nthr, smem, st>>>(vl, J, Cb, H, W, dlogits, red);
+  else if (dtype == KS_BF16) ecam_bwd_reduce_kernel<__nv_bfloat16, 3><<<dim3(chunks, N), nthr, smem, st>>>(vl, J, Cb, H, W, dlogits, red);
   else return KS_EINVAL;
   KS_LAUNCH_RET();
 }
@@ -518,12 +549,12 @@ extern "C" int ks_ecam_bwd_apply(int dtype, int N, int H, int W, int J, int Cb, 
   if (Cb2 != Cb) return KS_EINVAL;
   ViewList vl; rc = make_view_list(dxs, J, vl); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const int rows_a = 256 / (J * Cb / 8);
-  int chunks = (H * W + rows_a * 32 - 1) / (rows_a * 32); if (chunks < 1) chunks = 1;
+  const int nthr = 32 * J * (8 / J), rows_a = (8 / J) * (32 / (Cb / 8));
+  int chunks = (H * W + rows_a * 16 - 1) / (rows_a * 16); if (chunks < 1) chunks = 1;
   const int cap = (kNumSMs * 16 + N - 1) / N; if (chunks > cap) chunks = cap;
   const size_t smem = 0;
-  if (dtype == KS_F32) ecam_bwd_apply_kernel<float, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, gates, wf, dlogits, dpooled, argmax);
-  else if (dtype == KS_BF16) ecam_bwd_apply_kernel<__nv_bfloat16, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, gates, wf, dlogits, dpooled, argmax);
+  if (dtype == KS_F32) ecam_bwd_apply_kernel<float, 3><<<dim3(chunks, N), nthr, smem, st>>>(vl, J, Cb, H, W, gates, wf, dlogits, dpooled, argmax);
+  else if (dtype == KS_BF16) ecam_bwd_apply_kernel<__nv_bfloat16, 3><<<dim3(chunks, N), nthr, smem, st>>>(vl, J, Cb, H, W, gates, wf, dlogits, dpooled, argmax);
   else return KS_EINVAL;
   KS_LAUNCH_RET();
 }

@@ -92,6 +92,7 @@ EXPORTED_SYMBOLS = [
     "ks_bn_stats", "ks_bn_finalize", "ks_bn_act", "ks_bn_bwd_reduce", "ks_bn_bwd_apply", "ks_maxpool2x2_bwd",
     "ks_channel_sum", "ks_ecam_pool", "ks_ecam_gates", "ks_ecam_final", "ks_ecam_bwd_reduce", "ks_ecam_gates_bwd",
     "ks_ecam_bwd_apply", "ks_ce_dice_workspace_bytes", "ks_ce_dice_fwd_bwd", "ks_adam_step",
+    "ks_softmax_head_fwd", "ks_softmax_head_bwd", "ks_dropout_mask", "ks_channel_scale", "ks_absdiff_fwd", "ks_absdiff_bwd",
 ]
 
 
@@ -144,17 +145,26 @@ class CudaOps:
         self._check(rc, "ks_permute_cast")
 
     def make_permute_table(self, jobs, device):
-        """jobs: list of (src, dst, dims, strides, src_offset) -> opaque table for permute_cast_table (built once)."""
+        """jobs: list of (src, dst, dims, strides, src_offset[, dst_strides, dst_offset]) -> opaque table for
+        permute_cast_table (built once).  Without dst_strides the destination is written contiguously."""
         import numpy as np
         rec = np.zeros(len(jobs), dtype=np.dtype([("src", "<u8"), ("dst", "<u8"), ("total", "<i8"), ("s", "<i8", 4),
-                                                  ("d", "<i4", 3), ("sdt", "<i4"), ("ddt", "<i4"), ("acc", "<i4")], align=True))
-        assert rec.dtype.itemsize == 80, rec.dtype.itemsize
+                                                  ("d", "<i4", 3), ("sdt", "<i4"), ("ddt", "<i4"), ("acc", "<i4"),
+                                                  ("t", "<i8", 4), ("dstr", "<i4"), ("pad", "<i4")], align=True))
+        assert rec.dtype.itemsize == 120, rec.dtype.itemsize
         chunks = []
-        for i, (src, dst, dims, strides, off) in enumerate(jobs):
+        for i, job in enumerate(jobs):
+            src, dst, dims, strides, off = job[:5]
             d = list(dims) + [1] * (4 - len(dims))
             st = list(strides) + [0] * (4 - len(strides))
             total = d[0] * d[1] * d[2] * d[3]
-            rec[i] = (src.data_ptr() + off * src.element_size(), dst.data_ptr(), total, st, d[1:], dtype_code(src.dtype), dtype_code(dst.dtype), 0)
+            dstr, doff, strided = [0, 0, 0, 0], 0, 0
+            if len(job) > 5 and job[5] is not None:
+                dstr = list(job[5]) + [0] * (4 - len(job[5]))
+                doff = job[6] if len(job) > 6 else 0
+                strided = 1
+            rec[i] = (src.data_ptr() + off * src.element_size(), dst.data_ptr() + doff * dst.element_size(), total, st, d[1:],
+                      dtype_code(src.dtype), dtype_code(dst.dtype), 0, dstr, strided, 0)
             chunks += [(i, c0) for c0 in range(0, total, 4096)]
         jobs_dev = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()).to(device)
         chunks_dev = torch.tensor(chunks, dtype=torch.int32, device=device).reshape(-1)
@@ -242,10 +252,10 @@ class CudaOps:
                                     _p(w_fc2), _p(w1_fc1), _p(w1_fc2), _p(gates), _p(hidden), self._stream())
         self._check(rc, "ks_ecam_gates")
 
-    def ecam_final(self, xs, gates, wf, bf, K, logits):
+    def ecam_final(self, xs, gates, wf, bf, K, logits, pooled=None, argmax=None):
         x = xs[0]
         rc = self.lib.ks_ecam_final(dtype_code(x.dtype), C.c_int(x.N), C.c_int(x.H), C.c_int(x.W), _views(xs), C.c_int(len(xs)),
-                                    _p(gates), _p(wf), _p(bf), C.c_int(K), _p(logits), self._stream())
+                                    _p(gates), _p(wf), _p(bf), C.c_int(K), _p(logits), _p(pooled), _p(argmax), self._stream())
         self._check(rc, "ks_ecam_final")
 
     def ecam_bwd_reduce(self, xs, K, dlogits, red):
@@ -268,6 +278,36 @@ class CudaOps:
                                         _p(gates), _p(wf), C.c_int(K), _p(dlogits), _p(dpooled), _p(argmax), _views(dxs),
                                         self._stream())
         self._check(rc, "ks_ecam_bwd_apply")
+
+    # -- Siamese U-Net passes ------------------------------------------------------------------
+    def softmax_head_fwd(self, z: View, K: int, log_mode: bool, out: torch.Tensor):
+        rc = self.lib.ks_softmax_head_fwd(dtype_code(z.dtype), C.c_int(z.N), C.c_int(z.H), C.c_int(z.W), _vp(z), C.c_int(K),
+                                          C.c_int(int(log_mode)), _p(out), self._stream())
+        self._check(rc, "ks_softmax_head_fwd")
+
+    def softmax_head_bwd(self, out: torch.Tensor, dout: torch.Tensor, K: int, log_mode: bool, dz: View):
+        rc = self.lib.ks_softmax_head_bwd(dtype_code(dz.dtype), C.c_int(dz.N), C.c_int(dz.H), C.c_int(dz.W), _p(out), _p(dout),
+                                          C.c_int(K), C.c_int(int(log_mode)), _vp(dz), self._stream())
+        self._check(rc, "ks_softmax_head_bwd")
+
+    def dropout_mask(self, mask: torch.Tensor, p: float, seed: int, step: Optional[torch.Tensor]):
+        rc = self.lib.ks_dropout_mask(_p(mask), C.c_int64(mask.numel()), C.c_float(p), C.c_uint64(seed & (2 ** 64 - 1)), _p(step),
+                                      self._stream())
+        self._check(rc, "ks_dropout_mask")
+
+    def channel_scale(self, x: View, m: torch.Tensor):
+        rc = self.lib.ks_channel_scale(dtype_code(x.dtype), C.c_int(x.N), C.c_int(x.H), C.c_int(x.W), _vp(x), _p(m), self._stream())
+        self._check(rc, "ks_channel_scale")
+
+    def absdiff_fwd(self, a: View, b: View, out: View):
+        rc = self.lib.ks_absdiff_fwd(dtype_code(a.dtype), C.c_int(a.N), C.c_int(a.H), C.c_int(a.W), _vp(a), _vp(b), _vp(out),
+                                     self._stream())
+        self._check(rc, "ks_absdiff_fwd")
+
+    def absdiff_bwd(self, a: View, b: View, g: View, da: View, acc_a: bool, db: View, acc_b: bool):
+        rc = self.lib.ks_absdiff_bwd(dtype_code(a.dtype), C.c_int(a.N), C.c_int(a.H), C.c_int(a.W), _vp(a), _vp(b), _vp(g),
+                                     _vp(da), C.c_int(int(acc_a)), _vp(db), C.c_int(int(acc_b)), self._stream())
+        self._check(rc, "ks_absdiff_bwd")
 
     # -- loss --------------------------------------------------------------------------------
     def ce_dice_workspace(self, N: int, device) -> torch.Tensor:

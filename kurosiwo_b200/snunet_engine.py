@@ -362,7 +362,8 @@ class SNUNetEngine:
         ops.ecam_pool(xs, self.pooled, self.argmax, self.pool_scratch)
         ops.ecam_gates(N, self.f[0], 4, self.hid, self.hid1, self.pooled, P.p("ca.fc1.weight"), P.p("ca.fc2.weight"),
                        P.p("ca1.fc1.weight"), P.p("ca1.fc2.weight"), self.gates, self.hidden)
-        ops.ecam_final(xs, self.gates, P.p("conv_final.weight"), P.p("conv_final.bias"), self.K, self.logits)
+        ops.ecam_final(xs, self.gates, P.p("conv_final.weight"), P.p("conv_final.bias"), self.K, self.logits,
+                       self.pooled if training else None, self.argmax if training else None)
         return self.logits
 
     # ------------------------------------------------------------------------------------------

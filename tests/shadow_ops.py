@@ -47,8 +47,18 @@ class ShadowOps:
         return list(jobs)
 
     def permute_cast_table(self, table):
-        for (src, dst, dims, strides, off) in table:
-            self.permute_cast(src, dst, dims, strides, False, off)
+        for job in table:
+            src, dst, dims, strides, off = job[:5]
+            if len(job) > 5 and job[5] is not None:
+                d = list(dims) + [1] * (4 - len(dims))
+                tmp = torch.zeros(d[0] * d[1] * d[2] * d[3], dtype=torch.float32)
+                self.permute_cast(src, tmp, dims, strides, False, off)
+                ds = list(job[5]) + [0] * (4 - len(job[5]))
+                doff = job[6] if len(job) > 6 else 0
+                view = torch.as_strided(dst.reshape(-1), d, ds, doff)
+                view.copy_(tmp.view(d).to(dst.dtype))
+            else:
+                self.permute_cast(src, dst, dims, strides, False, off)
 
     # -- convolution -------------------------------------------------------------------------
     def conv2d(self, N, H, W, ksize, srcs, weight, bias, dsts, acc=None, stats=None, impl=0):
@@ -201,7 +211,7 @@ class ShadowOps:
             hd[:, 1, h0:h1] = hm
             g[:, c0:c1] = torch.sigmoid((F.relu(ha) + F.relu(hm)) @ w2.t())
 
-    def ecam_final(self, xs, gates, wf, bf, K, logits):
+    def ecam_final(self, xs, gates, wf, bf, K, logits, pooled=None, argmax=None):
         N, J, Cb = xs[0].N, len(xs), xs[0].C
         CC = J * Cb
         g = gates.view(N, (J + 1) * Cb)
@@ -287,3 +297,35 @@ class ShadowOps:
         bc1, bc2 = 1 - b1 ** t, 1 - b2 ** t
         p.addcdiv_(m, v.sqrt() / (bc2 ** 0.5) + eps, value=-lr / bc1)
         step += 1
+
+    # -- Siamese U-Net passes ------------------------------------------------------------------
+    def softmax_head_fwd(self, z, K, log_mode, out):
+        zz = _t(z).float()[..., :K].permute(0, 3, 1, 2)
+        out.copy_(F.log_softmax(zz, 1) if log_mode else F.softmax(zz, 1))
+
+    def softmax_head_bwd(self, out, dout, K, log_mode, dz):
+        if log_mode:
+            g = dout - out.exp() * dout.sum(1, keepdim=True)
+        else:
+            g = out * (dout - (dout * out).sum(1, keepdim=True))
+        t = _t(dz)
+        t.zero_()
+        t[..., :K].copy_(g.permute(0, 2, 3, 1).to(t.dtype))
+
+    def dropout_mask(self, mask, p, seed, step):
+        gen = torch.Generator().manual_seed(int(seed) + (0 if step is None else int(step.item())))
+        mask.copy_((torch.rand(mask.numel(), generator=gen) >= p).float() / (1.0 - p))
+
+    def channel_scale(self, x, m):
+        t = _t(x)
+        t.copy_((t.float() * m.view(x.N, 1, 1, x.C)).to(t.dtype))
+
+    def absdiff_fwd(self, a, b, out):
+        t = _t(out)
+        t.copy_((_t(a).float() - _t(b).float()).abs().to(t.dtype))
+
+    def absdiff_bwd(self, a, b, g, da, acc_a, db, acc_b):
+        s = torch.sign(_t(a).float() - _t(b).float()) * _t(g).float()
+        ta, tb = _t(da), _t(db)
+        ta.copy_((ta.float() + s if acc_a else s).to(ta.dtype))
+        tb.copy_((tb.float() - s if acc_b else -s).to(tb.dtype))

@@ -238,12 +238,11 @@ def test_ecam_forward_backward(ops, sh, dtype):
     ops.ecam_pool(xs, pooled, argmax, scratch)
     sh.ecam_pool(cxs, cpooled, cargmax, None)
     assert max_rel(pooled, cpooled) < (1e-5 if dtype == torch.float32 else 1e-2)
-    if dtype == torch.float32:
-        assert torch.equal(argmax.cpu(), cargmax)
     ops.ecam_gates(N, Cb, J, hid, hid1, pooled, *dw[:4], gates, hidden)
     sh.ecam_gates(N, Cb, J, hid, hid1, pooled.cpu(), *wts[:4], cgates, chidden)
     assert max_rel(gates, cgates) < 1e-5 and max_rel(hidden, chidden) < 1e-5
-    ops.ecam_final(xs, gates, dw[4], dw[5], K, logits)
+    ops.ecam_final(xs, gates, dw[4], dw[5], K, logits, pooled, argmax)      # also discovers the arg-max pixels
+    assert torch.equal(argmax.cpu(), cargmax)                                # both sides see the same stored values
     sh.ecam_final(cxs, gates.cpu(), wts[4], wts[5], K, clogits)
     assert rel_l2(logits, clogits) < 1e-5
     # backward
