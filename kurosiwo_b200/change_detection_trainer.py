@@ -13,6 +13,7 @@ from typing import Optional
 
 import torch
 
+from .siam_unet import _SiamUnet
 from .snunet import SNUNet_ECAM
 from .utilities import ConfusionMetrics, create_loss, init_lr_scheduler
 
@@ -50,9 +51,9 @@ def select_inputs(b, configs, device):
 class FusedStepper:
     """Owns the engine-side training state for one model/batch geometry (the public fast path)."""
 
-    def __init__(self, model: SNUNet_ECAM, configs, model_configs, process_group=None):
-        if not isinstance(model, SNUNet_ECAM):
-            raise TypeError("the fused step is implemented for kurosiwo_b200.SNUNet_ECAM")
+    def __init__(self, model, configs, model_configs, process_group=None):
+        if not isinstance(model, (SNUNet_ECAM, _SiamUnet)):
+            raise TypeError("the fused step is implemented for kurosiwo_b200's SNUNet_ECAM, SiamUnet_conc and SiamUnet_diff")
         if configs.get("loss_function", "ce+dice") != "ce+dice":
             raise NotImplementedError("the fused step computes CE+Dice (utilities/bce_and_dice.py); set loss_function='ce+dice'")
         opt = model_configs.get("optimizer", "adam")
@@ -66,7 +67,8 @@ class FusedStepper:
         eng = self.model.engine(x)
         if eng is not self.engine:
             eng.init_training(class_weights=self.configs.get("class_weights", [1.0, 1.0, 1.0]), ignore_index=3, lr=self.lr,
-                              betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=self.pg)
+                              betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,      # reference Adam gets only lr (:52-54)
+                              process_group=self.pg)
             self.engine = eng
         return eng
 

@@ -24,6 +24,7 @@ from typing import Dict, List, Optional, Tuple
 
 import torch
 
+from .engine_common import FlatParams, TrainStepMixin, _align  # noqa: F401
 from .lib import View
 
 DEC_ORDER = [(0, 1), (1, 1), (0, 2), (2, 1), (1, 2), (0, 3), (3, 1), (2, 2), (1, 3), (0, 4)]  # snunet.py:132-144
@@ -31,66 +32,12 @@ NSLOTS = [6, 5, 4, 3, 1]
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
 
 
-def _align(n: int, a: int = 64) -> int:
-    return (n + a - 1) // a * a
-
-
-class FlatParams:
-    """All trainable parameters of a module as views into one flat fp32 buffer (+ flat grad)."""
-
-    def __init__(self, module: torch.nn.Module):
-        self.module = module
-        self.names: List[str] = []
-        self.offsets: Dict[str, Tuple[int, torch.Size]] = {}
-        off = 0
-        for name, p in module.named_parameters():
-            self.names.append(name)
-            self.offsets[name] = (off, p.shape)
-            off += _align(p.numel(), 4)
-        self.numel = _align(off, 4)
-        self.flat: Optional[torch.Tensor] = None
-        self.grad: Optional[torch.Tensor] = None
-
-    def ensure(self, device) -> bool:
-        """(Re)flatten if the module's parameters are not views of the flat buffer (e.g. after .to())."""
-        params = dict(self.module.named_parameters())
-        ok = self.flat is not None and self.flat.device == torch.device(device)
-        if ok:
-            base = self.flat.data_ptr()
-            for name in self.names:
-                if params[name].data_ptr() != base + 4 * self.offsets[name][0]:
-                    ok = False
-                    break
-        if ok:
-            return False
-        flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
-        grad = torch.zeros(self.numel, dtype=torch.float32, device=device)
-        for name in self.names:
-            off, shape = self.offsets[name]
-            p = params[name]
-            flat[off:off + p.numel()].copy_(p.data.reshape(-1).to(device=device, dtype=torch.float32))
-            p.data = flat[off:off + p.numel()].view(shape)
-        self.flat, self.grad = flat, grad
-        return True
-
-    def p(self, name: str) -> torch.Tensor:
-        off, shape = self.offsets[name]
-        return self.flat[off:off + shape.numel()]
-
-    def g(self, name: str) -> torch.Tensor:
-        off, shape = self.offsets[name]
-        return self.grad[off:off + shape.numel()]
-
-    def grad_views(self):
-        return [self.g(n).view(self.offsets[n][1]) for n in self.names]
-
-
 class _Exec:
     """One execution of a conv_block_nested (the shared encoder blocks execute twice)."""
     __slots__ = ("name", "level", "srcs", "gsrcs", "out", "dout", "pool", "y1", "h", "y2", "bn", "stats", "bstats", "key")
 
 
-class SNUNetEngine:
+class SNUNetEngine(TrainStepMixin):
     def __init__(self, ops, module: torch.nn.Module, in_ch: int, num_classes: int, base: int,
                  N: int, H: int, W: int, dtype: torch.dtype, device, conv_impl: int = 0, planar_slots: Optional[bool] = None):
         assert H % 16 == 0 and W % 16 == 0, "SNUNet needs H, W divisible by 16 (four 2x2 poolings)"
@@ -460,84 +407,3 @@ class SNUNetEngine:
                 self._block_backward(e, gd, None if gd is None else [False], e.name not in seen_blocks, dpool)
                 seen_blocks.add(e.name)
         self._unpack_grads()
-
-    # ------------------------------------------------------------------------------------------
-    # fused training step: forward -> CE+Dice (+argmax) -> backward -> (all-reduce) -> Adam
-    # (training/change_detection_trainer.py:136-177 without the two loss.item() host syncs)
-    # ------------------------------------------------------------------------------------------
-    def init_training(self, class_weights=(1.0, 1.0, 1.0), ignore_index: int = 3, lr: float = 1e-3,
-                      betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, process_group=None):
-        dev = self.device
-        self.params.ensure(dev)
-        self.cw = torch.tensor(class_weights, dtype=torch.float32, device=dev)
-        self.ignore_index = ignore_index
-        self.hp = dict(lr=lr, b1=betas[0], b2=betas[1], eps=eps, wd=weight_decay)
-        self.adam_m = torch.zeros_like(self.params.flat)
-        self.adam_v = torch.zeros_like(self.params.flat)
-        self.adam_step = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.loss3 = torch.zeros(3, dtype=torch.float32, device=dev)
-        self.dlogits = torch.zeros_like(self.logits)
-        self.pred = torch.zeros(self.N, self.H, self.W, dtype=torch.uint8, device=dev)
-        self.loss_ws = self.ops.ce_dice_workspace(self.N, dev)
-        self.pg = process_group
-        self.world = 1
-        if process_group is not None:
-            import torch.distributed as dist
-            self.world = dist.get_world_size(process_group)
-            dist.broadcast(self.params.flat, src=dist.get_global_rank(process_group, 0) if hasattr(dist, "get_global_rank") else 0,
-                           group=process_group)
-        self.graph = None
-
-    def _fwd_loss_bwd(self, xA, xB, mask):
-        logits = self.forward(xA, xB, training=True)
-        self.ops.ce_dice(logits, mask, self.cw, self.ignore_index, 1.0, self.loss3, self.dlogits, self.pred, self.loss_ws)
-        self.backward(self.dlogits)
-
-    def _allreduce(self):
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.params.grad, group=self.pg)   # NCCL over NVLink: ONE message = all gradients
-
-    def _optimizer(self):
-        hp = self.hp
-        self.ops.adam_step(self.params.flat, self.params.grad, self.adam_m, self.adam_v, hp["lr"], hp["b1"], hp["b2"], hp["eps"],
-                           hp["wd"], 1.0 / self.world, self.adam_step)
-
-    def train_step(self, xA: torch.Tensor, xB: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
-        """One optimizer step; returns the device tensor [total, dice, ce] (no host sync)."""
-        self._fwd_loss_bwd(xA, xB, mask)
-        self._allreduce()
-        self._optimizer()
-        return self.loss3
-
-    def capture(self, xA: torch.Tensor, xB: torch.Tensor, mask: torch.Tensor):
-        """Capture the step over STATIC input tensors: one CUDA graph on a single GPU; with data parallelism two graphs
-        (forward+loss+backward | Adam) around the eager NCCL all-reduce.  Returns a callable that replays one step."""
-        self.params.ensure(self.device)
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            for _ in range(2):
-                self.train_step(xA, xB, mask)
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
-        if self.world == 1:
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self.train_step(xA, xB, mask)
-            self.replay = self.graph.replay
-        else:
-            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            # thread_local: NCCL's watchdog thread may issue CUDA calls while this thread captures
-            with torch.cuda.graph(ga, capture_error_mode="thread_local"):
-                self._fwd_loss_bwd(xA, xB, mask)
-            with torch.cuda.graph(gb, capture_error_mode="thread_local"):
-                self._optimizer()
-            self.graph = (ga, gb)
-
-            def replay():
-                ga.replay()
-                self._allreduce()
-                gb.replay()
-            self.replay = replay
-        return self.replay

@@ -81,7 +81,63 @@ def main():
             fx["logits_eval"] = model(torch.from_numpy(xA), torch.from_numpy(xB)).numpy()
         np.savez_compressed(OUT / f"snunet_{tag}.npz", **fx)
         print(tag, "loss", float(loss.detach()), "logits", out.shape)
+    siam_goldens()
+
+
+def siam_goldens():
+    """FC-Siam-conc / FC-Siam-diff fixtures: train-mode forward+loss+gradients with Dropout2d p=0.2 under a fixed torch
+    seed (masks re-derived by oracle.siam_oracle.draw_masks_like_torch and stored), and the eval-mode forward after it."""
+    sys.path.insert(0, REF)
+    from models.siam_conc import SiamUnet_conc as RefConc     # noqa: E402  (reference, read-only)
+    from models.siam_diff import SiamUnet_diff as RefDiff     # noqa: E402
+    from utilities.bce_and_dice import BCEandDiceLoss as RefLoss  # noqa: E402
+    from oracle import siam_oracle
+    from oracle.weights import make_batch
+
+    for kind, Ref, (N, H, W, seed, do_seed) in (("conc", RefConc, (2, 32, 32, 21, 5)), ("diff", RefDiff, (2, 48, 32, 22, 6)),
+                                                ("conc", RefConc, (4, 64, 64, 23, 7))):
+        sd = siam_oracle.make_state(seed, 2, 3, kind)
+        x1, x2, mask = make_batch(seed, N, H, W)
+        model = Ref(2, 3)
+        model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+        model.train()
+        crit = RefLoss(weights=torch.tensor([1.0, 1.0, 1.0]), ignore_index=3, use_softmax=True)
+        masks = siam_oracle.draw_masks_like_torch(do_seed, N, 0.2)
+        torch.manual_seed(do_seed)
+        out = model(torch.from_numpy(x1), torch.from_numpy(x2))
+        loss = crit(out, torch.from_numpy(mask))
+        loss.backward()
+        # the oracle with the re-derived masks must reproduce the reference (pins both the restatement and the masks)
+        osd = siam_oracle.to_torch_state(sd)
+        loss_o, out_o, grads_o = siam_oracle.train_step(osd, torch.from_numpy(x1), torch.from_numpy(x2), torch.from_numpy(mask), kind, masks=masks)
+        assert torch.allclose(out_o, out.detach(), rtol=1e-4, atol=1e-6), (kind, (out_o - out.detach()).abs().max())
+        assert abs(float(loss_o) - float(loss.detach())) < 1e-5
+        fx = {"kind": kind, "N": N, "H": H, "W": W, "seed": seed, "out": out.detach().numpy(), "loss": loss.detach().numpy()}
+        for k, m in masks.items():
+            fx[f"mask.{k}"] = m.numpy()
+        names, norms = [], []
+        keep_full = {"conv11.weight", "conv11.bias", "bn11.weight", "bn12.bias", "conv22.weight", "conv31.weight", "upconv3.weight", "upconv4.bias",
+                     "upconv1.weight", "conv33d.weight", "conv12d.weight", "conv11d.weight", "conv11d.bias", "bn33d.weight", "conv31d.weight"}
+        for k, p in model.named_parameters():
+            names.append(k)
+            norms.append(float(p.grad.double().norm()))
+            if k in keep_full:
+                fx[f"grad.{k}"] = p.grad.numpy()
+        fx["grad_names"] = np.array(names)
+        fx["grad_norms"] = np.array(norms, np.float64)
+        st = model.state_dict()
+        for k in ("bn11.running_mean", "bn11.running_var", "bn11.num_batches_tracked", "bn43.running_var", "bn12d.running_mean",
+                  "bn12d.num_batches_tracked"):
+            fx[f"state.{k}"] = st[k].numpy()
+        model.eval()
+        with torch.no_grad():
+            fx["out_eval"] = model(torch.from_numpy(x1), torch.from_numpy(x2)).numpy()
+        np.savez_compressed(OUT / f"siam_{kind}_n{N}_s{H}x{W}.npz", **fx)
+        print("siam", kind, N, H, W, "loss", float(loss.detach()))
 
 
 if __name__ == "__main__":
+    if "--siam-only" in sys.argv:
+        siam_goldens()
+        sys.exit(0)
     main()

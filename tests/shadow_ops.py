@@ -55,7 +55,7 @@ class ShadowOps:
                 self.permute_cast(src, tmp, dims, strides, False, off)
                 ds = list(job[5]) + [0] * (4 - len(job[5]))
                 doff = job[6] if len(job) > 6 else 0
-                view = torch.as_strided(dst.reshape(-1), d, ds, doff)
+                view = torch.as_strided(dst.reshape(-1), d, ds, dst.storage_offset() + doff)
                 view.copy_(tmp.view(d).to(dst.dtype))
             else:
                 self.permute_cast(src, dst, dims, strides, False, off)
