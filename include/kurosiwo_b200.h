@@ -222,6 +222,52 @@ int ks_absdiff_fwd(int dtype, int N, int H, int W, const ks_view_t *a, const ks_
 int ks_absdiff_bwd(int dtype, int N, int H, int W, const ks_view_t *a, const ks_view_t *b, const ks_view_t *g,
                    const ks_view_t *da, int accumulate_a, const ks_view_t *db, int accumulate_b, void *stream);
 
+/* ---- ViT encoder / FloodViT head passes (models/vision_transformer.py, models/model_utilities.py:36-94) ------------
+ * Token matrices are [rows = B*Tp, C] row-major in `dtype` (Tp = tokens per image padded to a multiple of 16; T valid:
+ * cls + patches); the Linear layers run on ks_conv2d / ks_conv2d_wgrad as 1x1 convolutions over the same buffers. */
+/* nn.LayerNorm over the last dim (vision_transformer.py:22,43,72,123,125): y = (x-mean)*rstd*gamma+beta, biased variance,
+ * two-pass fp32 statistics; mean/rstd (fp32 [rows], optional) are kept for the backward; copy_out (optional) receives x
+ * unchanged (the next buffer of the residual stream, which the following GEMM accumulates into).  C % 8 == 0, C <= 2048. */
+int ks_layernorm_fwd(int dtype, int64_t rows, int C, const void *x, int64_t ldx, const float *gamma, const float *beta,
+                     float eps, void *y, int64_t ldy, float *mean, float *rstd, void *copy_out, int64_t ldc, void *stream);
+/* dx (+)= rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma; dgamma += sum dy*xhat, dbeta += sum dy (fp32 atomics, caller
+ * zeroes).  dx may be NULL (parameter gradients only).  C % 8 == 0, C <= 1024. */
+int ks_layernorm_bwd(int dtype, int64_t rows, int C, const void *dy, int64_t lddy, const void *x, int64_t ldx,
+                     const float *mean, const float *rstd, const float *gamma, void *dx, int64_t lddx, int accumulate_dx,
+                     float *dgamma, float *dbeta, void *stream);
+/* Rearrange('b c (h p1) (w p2) -> b (h w) (p1 p2 c)', p=16) + LayerNorm(256*Cc) (vision_transformer.py:122-123) straight
+ * from the NCHW fp32 image: patch p of image b -> row b*Tp + 1 + p of out [B*Tp][256*Cc] (row b*Tp is the cls slot; rows the
+ * kernel does not write stay as the caller initialised them: zero).  mean/rstd: fp32 [B*Tp]. */
+int ks_patchify_ln(int dtype, int B, int Cc, int Hi, int Wi, int Tp, const float *img, const float *gamma, const float *beta,
+                   float eps, void *out, float *mean, float *rstd, void *stream);
+/* dgamma += sum_patches dy*xhat, dbeta += sum_patches dy (the image itself needs no gradient). */
+int ks_patchify_ln_bwd(int dtype, int B, int Cc, int Hi, int Wi, int Tp, const float *img, const float *mean, const float *rstd,
+                       const void *dy, float *dgamma, float *dbeta, void *stream);
+/* x0 = cat(cls_token, e[:,1:T]) + pos_embedding[:T] (vision_transformer.py:142-146); padding rows t >= T are written as 0. */
+int ks_vit_assemble(int dtype, int B, int T, int Tp, int D, const void *e, const float *cls, const float *pos, void *x0, void *stream);
+/* dpos[t] = sum_b dx0[b,t], dcls = sum_b dx0[b,0] (assigned), de[b,t] = dx0[b,t] for 1 <= t < T and 0 elsewhere. */
+int ks_vit_assemble_bwd(int dtype, int B, int T, int Tp, int D, const void *dx0, void *de, float *dcls, float *dpos, void *stream);
+/* Multi-head attention core (vision_transformer.py:56-65): qkv [B*Tp][3*heads*dh] = (q | k | v), head-major inside each third;
+ * out [B*Tp][heads*dh] = softmax(q k^T * scale) v over the T valid keys; probs [B][heads][Tp][Tp] keeps the probabilities for
+ * the backward (rows/columns >= T are 0).  dh == 64, Tp <= 256. */
+int ks_attention_fwd(int dtype, int B, int T, int Tp, int heads, int dh, const void *qkv, float scale, void *out, void *probs,
+                     void *stream);
+/* dqkv from dout: dV = P^T dO, dS = P*(dO V^T - rowsum(dO V^T * P)), dQ = scale dS K, dK = scale dS^T Q.
+ * ds_scratch: [B][heads][Tp][Tp] in `dtype`.  Padding rows of dqkv are written as 0. */
+int ks_attention_bwd(int dtype, int B, int T, int Tp, int heads, int dh, const void *qkv, const void *probs, const void *dout,
+                     float scale, void *dqkv, void *ds_scratch, void *stream);
+/* nn.GELU() (exact erf; vision_transformer.py:25): h = gelu(u); du = dh * gelu'(u).  n % 8 == 0. */
+int ks_gelu_fwd(int dtype, int64_t n, const void *u, void *h, void *stream);
+int ks_gelu_bwd(int dtype, int64_t n, const void *u, const void *dh, void *du, void *stream);
+/* nn.Upsample(size=(Ho,Wo), mode='bilinear') (align_corners=False; model_utilities.py:89-91) of the K-channel G x G token map
+ * held in rows b*Tp + row0 + gy*G + gx (channels 0..K-1 of Cs-wide rows) -> NCHW fp32 [B][K][Ho][Wo]; the linear 1x1 head
+ * commutes with the interpolation, so it runs on the G x G grid first.  _bwd is the exact adjoint (gather form): every
+ * element of dsrc [B*Tp][Cs] is written (0 outside the grid rows / channels >= K). */
+int ks_bilinear_up_fwd(int dtype, int B, int G, int Tp, int row0, int Cs, int K, int Ho, int Wo, const void *src, float *dst,
+                       void *stream);
+int ks_bilinear_up_bwd(int dtype, int B, int G, int Tp, int row0, int Cs, int K, int Ho, int Wo, const float *ddst, void *dsrc,
+                       void *stream);
+
 /* ---- loss (utilities/bce_and_dice.py:18-24, utilities/dice.py:93-137) --- */
 /* Fused softmax -> weighted CE(ignore_index) + Dice, forward + gradient + argmax.
  * logits: NCHW fp32 [N][C][HW] (C==3); labels int64 [N][HW].

@@ -1,0 +1,758 @@
+// Bandwidth-bound / small-matrix passes of the ViT encoder and the FloodViT segmentation head.
+//
+// Reference: models/vision_transformer.py (ViT.forward :139-156, Transformer.forward :84-89, Attention.forward :53-66,
+// FeedForward :19-32) and models/model_utilities.py (FinetunerSegmentation.forward :80-94).
+// The token matrix is [B*Tp, C] row-major (Tp = tokens per image padded to a multiple of 16, T valid), storage dtype
+// fp32 (parity mode) or bf16 (perf mode); the GEMMs run on the conv engine as 1x1 convolutions over the same buffers.
+//   ks_patchify_ln / _bwd   Rearrange 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' + LayerNorm(patch_dim)   (:122-123)
+//   ks_layernorm_fwd / _bwd nn.LayerNorm over the last dim (+ optional copy of x = the residual stream's next buffer)
+//   ks_vit_assemble / _bwd  cat(cls_token, x) + pos_embedding                                          (:142-146)
+//   ks_attention_fwd / _bwd softmax(q k^T * scale) v per (image, head), probabilities kept for the backward (:59-65)
+//   ks_gelu_fwd / _bwd      exact-erf GELU                                                               (:25)
+//   ks_bilinear_up_fwd/_bwd nn.Upsample(size, mode='bilinear') of the K-class token map (model_utilities.py:89-91; the
+//                           1x1 head commutes with the interpolation, so K channels are upsampled instead of `dim`)
+#include "common.cuh"
+
+namespace ks {
+
+template <typename T> __device__ __forceinline__ void ldv8(const T *p, float (&f)[8]) { ld8(p, f); }
+template <typename T> __device__ __forceinline__ void stv8(T *p, const float (&f)[8]) { st8(p, f); }
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per row, the row lives in registers (C <= 2048, C % 8 == 0).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LN_KMAX = 8;   // 8 chunks x 32 lanes x 8 elements = 2048 columns
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(long long rows, int C, const T *__restrict__ x, long long ldx, const float *__restrict__ gamma,
+                     const float *__restrict__ beta, float eps, T *__restrict__ y, long long ldy, float *__restrict__ mean,
+                     float *__restrict__ rstd, T *__restrict__ copy_out, long long ldc) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (long long r = (long long)blockIdx.x * wpb + wib; r < rows; r += (long long)gridDim.x * wpb) {
+    const T *xp = x + r * ldx;
+    float v[LN_KMAX][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_KMAX; ++k) {
+      const int c = (k * 32 + lane) * 8;
+      if (c < C) {
+        ldv8(xp + c, v[k]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[k][i];
+      }
+    }
+    const float mu = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_KMAX; ++k) {
+      const int c = (k * 32 + lane) * 8;
+      if (c < C) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[k][i] - mu; q += d * d; }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) / (float)C + eps);
+    if (lane == 0) { if (mean) mean[r] = mu; if (rstd) rstd[r] = rs; }
+#pragma unroll
+    for (int k = 0; k < LN_KMAX; ++k) {
+      const int c = (k * 32 + lane) * 8;
+      if (c < C) {
+        if (copy_out) stv8(copy_out + r * ldc + c, v[k]);
+        float g[8], b[8], o[8];
+        ld8(gamma + c, g); ld8(beta + c, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (v[k][i] - mu) * rs * g[i] + b[i];
+        stv8(y + r * ldy + c, o);
+      }
+    }
+  }
+}
+
+// LayerNorm backward (C <= 1024): dx (+)= rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma;
+// dgamma += sum_rows dy*xhat, dbeta += sum_rows dy (register accumulators -> smem -> one fp32 atomic per column per CTA).
+constexpr int LNB_KMAX = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(long long rows, int C, const T *__restrict__ dy, long long lddy, const T *__restrict__ x, long long ldx,
+                     const float *__restrict__ mean, const float *__restrict__ rstd, const float *__restrict__ gamma,
+                     T *__restrict__ dx, long long lddx, int acc_dx, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+  extern __shared__ float sred[];     // [2][C]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  float ag[LNB_KMAX][8], ab[LNB_KMAX][8], gm[LNB_KMAX][8];
+#pragma unroll
+  for (int k = 0; k < LNB_KMAX; ++k) {
+    const int c = (k * 32 + lane) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ag[k][i] = 0.f; ab[k][i] = 0.f; gm[k][i] = 0.f; }
+    if (c < C) ld8(gamma + c, gm[k]);
+  }
+  for (long long r = (long long)blockIdx.x * wpb + wib; r < rows; r += (long long)gridDim.x * wpb) {
+    const float mu = mean[r], rs = rstd[r];
+    float g[LNB_KMAX][8], xh[LNB_KMAX][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < LNB_KMAX; ++k) {
+      const int c = (k * 32 + lane) * 8;
+      if (c < C) {
+        float d[8], xv[8];
+        ldv8(dy + r * lddy + c, d); ldv8(x + r * ldx + c, xv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[k][i] = (xv[i] - mu) * rs;
+          ag[k][i] += d[i] * xh[k][i]; ab[k][i] += d[i];
+          g[k][i] = d[i] * gm[k][i];
+          s1 += g[k][i]; s2 += g[k][i] * xh[k][i];
+        }
+      }
+    }
+    if (dx) {
+      const float m1 = warp_sum(s1) / (float)C, m2 = warp_sum(s2) / (float)C;
+#pragma unroll
+      for (int k = 0; k < LNB_KMAX; ++k) {
+        const int c = (k * 32 + lane) * 8;
+        if (c < C) {
+          float o[8];
+          if (acc_dx) ldv8(dx + r * lddx + c, o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const float t = rs * (g[k][i] - m1 - xh[k][i] * m2); o[i] = acc_dx ? o[i] + t : t; }
+          stv8(dx + r * lddx + c, o);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < LNB_KMAX; ++k) {
+    const int c = (k * 32 + lane) * 8;
+    if (c < C) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { atomicAdd(&sred[c + i], ag[k][i]); atomicAdd(&sred[C + c + i], ab[k][i]); }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + i, sred[i]);
+    if (dbeta) atomicAdd(dbeta + i, sred[C + i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Patchify + LayerNorm(patch_dim).  img NCHW fp32 [B][Cc][Hi][Wi]; patch vector order (p1 p2 c), channel fastest
+// (vision_transformer.py:122).  One warp per patch; lane l owns pixel row p1 = l/2 and the 8 pixels p2 = 8*(l%2)..+7,
+// all Cc channels: 8*Cc CONTIGUOUS output elements.  Patch p of image b goes to row b*Tp + 1 + p (row 0 is the cls slot).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int PATCH = 16, PCMAX = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+patchify_ln_kernel(int B, int Cc, int Hi, int Wi, int Tp, const float *__restrict__ img, const float *__restrict__ gamma,
+                   const float *__restrict__ beta, float eps, T *__restrict__ out, float *__restrict__ mean, float *__restrict__ rstd) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int gw = Wi / PATCH, gh = Hi / PATCH, np = gw * gh, PD = PATCH * PATCH * Cc;
+  const int p1 = lane >> 1, p20 = (lane & 1) * 8;
+  for (long long pi = (long long)blockIdx.x * wpb + wib; pi < (long long)B * np; pi += (long long)gridDim.x * wpb) {
+    const int b = (int)(pi / np), pp = (int)(pi % np), gy = pp / gw, gx = pp % gw;
+    float v[PCMAX][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < PCMAX; ++c)
+      if (c < Cc) {
+        const float *ip = img + (((long long)b * Cc + c) * Hi + (gy * PATCH + p1)) * Wi + gx * PATCH + p20;
+        const float4 a = *reinterpret_cast<const float4 *>(ip), bq = *reinterpret_cast<const float4 *>(ip + 4);
+        v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w; v[c][4] = bq.x; v[c][5] = bq.y; v[c][6] = bq.z; v[c][7] = bq.w;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[c][i];
+      }
+    const float mu = warp_sum(s) / (float)PD;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < PCMAX; ++c)
+      if (c < Cc) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[c][i] - mu; q += d * d; }
+      }
+    const float rs = rsqrtf(warp_sum(q) / (float)PD + eps);
+    const long long row = (long long)b * Tp + 1 + pp;
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+    T *op = out + row * PD + (p1 * PATCH + p20) * Cc;
+    const float *gp = gamma + (p1 * PATCH + p20) * Cc, *bp = beta + (p1 * PATCH + p20) * Cc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < PCMAX; ++c)
+        if (c < Cc) Cvt<T>::st(op + i * Cc + c, (v[c][i] - mu) * rs * __ldg(gp + i * Cc + c) + __ldg(bp + i * Cc + c));
+  }
+}
+
+// dgamma[e] = sum_patches dy[row][e]*xhat[row][e], dbeta[e] = sum dy[row][e]  (the image needs no gradient)
+template <typename T>
+__global__ void __launch_bounds__(256)
+patchify_ln_bwd_kernel(int B, int Cc, int Hi, int Wi, int Tp, const float *__restrict__ img, const float *__restrict__ mean,
+                       const float *__restrict__ rstd, const T *__restrict__ dy, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+  extern __shared__ float sred[];    // [2][PD]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int gw = Wi / PATCH, gh = Hi / PATCH, np = gw * gh, PD = PATCH * PATCH * Cc;
+  for (int i = threadIdx.x; i < 2 * PD; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  const int p1 = lane >> 1, p20 = (lane & 1) * 8;
+  float ag[PCMAX][8], ab[PCMAX][8];
+#pragma unroll
+  for (int c = 0; c < PCMAX; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ag[c][i] = 0.f; ab[c][i] = 0.f; }
+  for (long long pi = (long long)blockIdx.x * wpb + wib; pi < (long long)B * np; pi += (long long)gridDim.x * wpb) {
+    const int b = (int)(pi / np), pp = (int)(pi % np), gy = pp / gw, gx = pp % gw;
+    const long long row = (long long)b * Tp + 1 + pp;
+    const float mu = mean[row], rs = rstd[row];
+    const T *dp = dy + row * PD + (p1 * PATCH + p20) * Cc;
+#pragma unroll
+    for (int c = 0; c < PCMAX; ++c)
+      if (c < Cc) {
+        const float *ip = img + (((long long)b * Cc + c) * Hi + (gy * PATCH + p1)) * Wi + gx * PATCH + p20;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = Cvt<T>::ld(dp + i * Cc + c);
+          ag[c][i] += d * (ip[i] - mu) * rs; ab[c][i] += d;
+        }
+      }
+  }
+#pragma unroll
+  for (int c = 0; c < PCMAX; ++c)
+    if (c < Cc) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int e = (p1 * PATCH + p20 + i) * Cc + c;
+        atomicAdd(&sred[e], ag[c][i]); atomicAdd(&sred[PD + e], ab[c][i]);
+      }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PD; i += blockDim.x) { atomicAdd(dgamma + i, sred[i]); atomicAdd(dbeta + i, sred[PD + i]); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// x0[b,0] = cls + pos[0]; x0[b,t] = e[b,t] + pos[t] (1 <= t < T); padding rows (t >= T) = 0.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+vit_assemble_kernel(int B, int Tt, int Tp, int D, const T *__restrict__ e, const float *__restrict__ cls, const float *__restrict__ pos,
+                    T *__restrict__ x0) {
+  const int DV = D / 8;
+  const long long total = (long long)B * Tp * DV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % DV) * 8; const long long row = i / DV; const int t = (int)(row % Tp);
+    float o[8];
+    if (t >= Tt) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = 0.f;
+    } else {
+      float a[8], pz[8];
+      if (t == 0) ld8(cls + c, a); else ldv8(e + row * D + c, a);
+      ld8(pos + (long long)t * D + c, pz);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = a[k] + pz[k];
+    }
+    stv8(x0 + row * D + c, o);
+  }
+}
+
+// dpos[t] = sum_b dx0[b,t]; dcls = sum_b dx0[b,0]; de[b,t] = dx0[b,t] for 1 <= t < T, 0 elsewhere.   grid: (Tp, D/8 chunks)
+template <typename T>
+__global__ void __launch_bounds__(128)
+vit_assemble_bwd_kernel(int B, int Tt, int Tp, int D, const T *__restrict__ dx0, T *__restrict__ de, float *__restrict__ dcls,
+                        float *__restrict__ dpos) {
+  const int t = blockIdx.x;
+  for (int c = (blockIdx.y * blockDim.x + threadIdx.x) * 8; c < D; c += gridDim.y * blockDim.x * 8) {
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const long long row = (long long)b * Tp + t;
+      float g[8], z[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) z[k] = 0.f;
+      if (t < Tt) {
+        ldv8(dx0 + row * D + c, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] += g[k];
+      }
+      if (t >= 1 && t < Tt) stv8(de + row * D + c, g); else stv8(de + row * D + c, z);
+    }
+    if (t < Tt) {
+      st8(dpos + (long long)t * D + c, s);
+      if (t == 0) st8(dcls + c, s);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Attention, exact fp32 arithmetic on CUDA cores (parity-mode engine and first bf16 path).  One CTA per (b, head, row block).
+// qkv row layout: [q (heads*dh) | k (heads*dh) | v (heads*dh)], head-major inside each third ('b n (h d) -> b h n d').
+// K and V of the head sit in shared memory as fp32 with row pitch dh+1 (conflict-free column walks).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int ATT_DH = 64, ATT_PITCH = ATT_DH + 1, ATT_WARPS = 8, ATT_JMAX = 8;   // Tp <= 256
+
+template <typename T>
+__device__ __forceinline__ void att_load_tile(float *dst, const T *src, long long ld, int rows_valid, int rows_total) {
+  for (int i = threadIdx.x; i < rows_total * (ATT_DH / 8); i += blockDim.x) {
+    const int r = i / (ATT_DH / 8), c = (i % (ATT_DH / 8)) * 8;
+    float f[8];
+    if (r < rows_valid) ldv8(src + (long long)r * ld + c, f);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dst[r * ATT_PITCH + c + k] = f[k];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attention_fwd_kernel(int Tt, int Tp, int heads, const T *__restrict__ qkv, float scale, T *__restrict__ out, T *__restrict__ probs,
+                     int rows_per_cta) {
+  extern __shared__ float sm[];
+  float *Ks = sm, *Vs = Ks + Tp * ATT_PITCH, *Pw = Vs + Tp * ATT_PITCH;       // Pw: [ATT_WARPS][Tp] probability rows, [ATT_WARPS][64] q rows
+  float *Qw = Pw + ATT_WARPS * Tp;
+  const int b = blockIdx.z, h = blockIdx.y, inner = heads * ATT_DH;
+  const long long ld = 3LL * inner;
+  const T *base = qkv + (long long)b * Tp * ld + h * ATT_DH;
+  att_load_tile(Ks, base + inner, ld, Tt, Tp);
+  att_load_tile(Vs, base + 2 * inner, ld, Tt, Tp);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float *pw = Pw + w * Tp, *qw = Qw + w * ATT_DH;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(Tp, r0 + rows_per_cta);
+  for (int i = r0 + w; i < r1; i += ATT_WARPS) {
+    T *orow = out + ((long long)b * Tp + i) * inner + h * ATT_DH;
+    T *prow = probs + (((long long)b * heads + h) * Tp + i) * Tp;
+    if (i >= Tt) {        // padding query row: defined zeros (its gradient is zero too)
+      Cvt<T>::st(orow + lane, 0.f); Cvt<T>::st(orow + 32 + lane, 0.f);
+      for (int j = lane; j < Tp; j += 32) Cvt<T>::st(prow + j, 0.f);
+      continue;
+    }
+    const T *qrow = base + (long long)i * ld;
+    qw[lane] = Cvt<T>::ld(qrow + lane); qw[32 + lane] = Cvt<T>::ld(qrow + 32 + lane);
+    __syncwarp();
+    float s[ATT_JMAX], mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < ATT_JMAX; ++jj) {
+      const int j = jj * 32 + lane;
+      s[jj] = -INFINITY;
+      if (j < Tt) {
+        float a = 0.f;
+        const float *kp = Ks + j * ATT_PITCH;
+#pragma unroll 16
+        for (int d = 0; d < ATT_DH; ++d) a = fmaf(qw[d], kp[d], a);
+        s[jj] = a * scale;
+        mx = fmaxf(mx, s[jj]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < ATT_JMAX; ++jj) {
+      const int j = jj * 32 + lane;
+      s[jj] = (j < Tt) ? expf(s[jj] - mx) : 0.f;
+      sum += s[jj];
+    }
+    const float inv = 1.f / warp_sum(sum);
+#pragma unroll
+    for (int jj = 0; jj < ATT_JMAX; ++jj) {
+      const int j = jj * 32 + lane;
+      if (j < Tp) {
+        const float pq = round_as<T>(s[jj] * inv);       // the value the backward (and P.V below) sees is the stored one
+        pw[j] = pq;
+        Cvt<T>::st(prow + j, pq);
+      }
+    }
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < Tt; ++j) {
+      const float pj = pw[j];
+      o0 = fmaf(pj, Vs[j * ATT_PITCH + lane], o0);
+      o1 = fmaf(pj, Vs[j * ATT_PITCH + 32 + lane], o1);
+    }
+    Cvt<T>::st(orow + lane, o0); Cvt<T>::st(orow + 32 + lane, o1);
+    __syncwarp();
+  }
+}
+
+// Backward, phase A (row-parallel): dP = dO V^T, dS = P*(dP - sum_j dP*P), dQ = scale * dS K; dS is written over `ds`.
+template <typename T>
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attention_bwd_rows_kernel(int Tt, int Tp, int heads, const T *__restrict__ qkv, const T *__restrict__ probs, const T *__restrict__ dout,
+                          float scale, T *__restrict__ dqkv, T *__restrict__ ds, int rows_per_cta) {
+  extern __shared__ float sm[];
+  float *Ks = sm, *Vs = Ks + Tp * ATT_PITCH, *Pw = Vs + Tp * ATT_PITCH;
+  float *Qw = Pw + ATT_WARPS * Tp;
+  const int b = blockIdx.z, h = blockIdx.y, inner = heads * ATT_DH;
+  const long long ld = 3LL * inner;
+  const T *base = qkv + (long long)b * Tp * ld + h * ATT_DH;
+  att_load_tile(Ks, base + inner, ld, Tt, Tp);
+  att_load_tile(Vs, base + 2 * inner, ld, Tt, Tp);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float *pw = Pw + w * Tp, *qw = Qw + w * ATT_DH;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(Tp, r0 + rows_per_cta);
+  for (int i = r0 + w; i < r1; i += ATT_WARPS) {
+    T *dqrow = dqkv + ((long long)b * Tp + i) * ld + h * ATT_DH;
+    T *dsrow = ds + (((long long)b * heads + h) * Tp + i) * Tp;
+    if (i >= Tt) {
+      Cvt<T>::st(dqrow + lane, 0.f); Cvt<T>::st(dqrow + 32 + lane, 0.f);
+      for (int j = lane; j < Tp; j += 32) Cvt<T>::st(dsrow + j, 0.f);
+      continue;
+    }
+    const T *dorow = dout + ((long long)b * Tp + i) * inner + h * ATT_DH;
+    const T *prow = probs + (((long long)b * heads + h) * Tp + i) * Tp;
+    qw[lane] = Cvt<T>::ld(dorow + lane); qw[32 + lane] = Cvt<T>::ld(dorow + 32 + lane);
+    __syncwarp();
+    float dp[ATT_JMAX], pv[ATT_JMAX], dot = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < ATT_JMAX; ++jj) {
+      const int j = jj * 32 + lane;
+      dp[jj] = 0.f; pv[jj] = 0.f;
+      if (j < Tt) {
+        float a = 0.f;
+        const float *vp = Vs + j * ATT_PITCH;
+#pragma unroll 16
+        for (int d = 0; d < ATT_DH; ++d) a = fmaf(qw[d], vp[d], a);
+        dp[jj] = a; pv[jj] = Cvt<T>::ld(prow + j);
+        dot += a * pv[jj];
+      }
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int jj = 0; jj < ATT_JMAX; ++jj) {
+      const int j = jj * 32 + lane;
+      if (j < Tp) {
+        const float v = round_as<T>((j < Tt) ? pv[jj] * (dp[jj] - dot) : 0.f);
+        pw[j] = v;
+        Cvt<T>::st(dsrow + j, v);
+      }
+    }
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < Tt; ++j) {
+      const float sj = pw[j];
+      o0 = fmaf(sj, Ks[j * ATT_PITCH + lane], o0);
+      o1 = fmaf(sj, Ks[j * ATT_PITCH + 32 + lane], o1);
+    }
+    Cvt<T>::st(dqrow + lane, o0 * scale); Cvt<T>::st(dqrow + 32 + lane, o1 * scale);
+    __syncwarp();
+  }
+}
+
+// Backward, phase B (key-parallel): dK[j] = scale * sum_i dS[i][j] Q[i], dV[j] = sum_i P[i][j] dO[i].
+template <typename T>
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attention_bwd_cols_kernel(int Tt, int Tp, int heads, const T *__restrict__ qkv, const T *__restrict__ probs, const T *__restrict__ ds,
+                          const T *__restrict__ dout, float scale, T *__restrict__ dqkv, int rows_per_cta) {
+  extern __shared__ float sm[];
+  float *Qs = sm, *Os = Qs + Tp * ATT_PITCH, *Cw = Os + Tp * ATT_PITCH;       // Cw: [ATT_WARPS][2][Tp] columns of dS and P
+  const int b = blockIdx.z, h = blockIdx.y, inner = heads * ATT_DH;
+  const long long ld = 3LL * inner;
+  att_load_tile(Qs, qkv + (long long)b * Tp * ld + h * ATT_DH, ld, Tt, Tp);
+  att_load_tile(Os, dout + (long long)b * Tp * inner + h * ATT_DH, (long long)inner, Tt, Tp);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float *cs = Cw + w * 2 * Tp, *cp = cs + Tp;
+  const T *pb = probs + ((long long)b * heads + h) * Tp * Tp, *sb = ds + ((long long)b * heads + h) * Tp * Tp;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(Tp, r0 + rows_per_cta);
+  for (int j = r0 + w; j < r1; j += ATT_WARPS) {
+    T *dkrow = dqkv + ((long long)b * Tp + j) * ld + inner + h * ATT_DH;
+    T *dvrow = dkrow + inner;
+    if (j >= Tt) {
+      Cvt<T>::st(dkrow + lane, 0.f); Cvt<T>::st(dkrow + 32 + lane, 0.f);
+      Cvt<T>::st(dvrow + lane, 0.f); Cvt<T>::st(dvrow + 32 + lane, 0.f);
+      continue;
+    }
+    for (int i = lane; i < Tt; i += 32) { cs[i] = Cvt<T>::ld(sb + (long long)i * Tp + j); cp[i] = Cvt<T>::ld(pb + (long long)i * Tp + j); }
+    __syncwarp();
+    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+    for (int i = 0; i < Tt; ++i) {
+      const float si = cs[i], pi = cp[i];
+      k0 = fmaf(si, Qs[i * ATT_PITCH + lane], k0); k1 = fmaf(si, Qs[i * ATT_PITCH + 32 + lane], k1);
+      v0 = fmaf(pi, Os[i * ATT_PITCH + lane], v0); v1 = fmaf(pi, Os[i * ATT_PITCH + 32 + lane], v1);
+    }
+    Cvt<T>::st(dkrow + lane, k0 * scale); Cvt<T>::st(dkrow + 32 + lane, k1 * scale);
+    Cvt<T>::st(dvrow + lane, v0); Cvt<T>::st(dvrow + 32 + lane, v1);
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GELU (exact erf, nn.GELU default)
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(long long n8, const T *__restrict__ u, T *__restrict__ hout) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    ldv8(u + i * 8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = 0.5f * f[k] * (1.f + erff(f[k] * 0.70710678118654752f));
+    stv8(hout + i * 8, f);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(long long n8, const T *__restrict__ u, const T *__restrict__ dh, T *__restrict__ du) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8], g[8];
+    ldv8(u + i * 8, f); ldv8(dh + i * 8, g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float x = f[k];
+      const float d = 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+      g[k] *= d;
+    }
+    stv8(du + i * 8, g);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Bilinear upsample (align_corners=False, aten upsample_bilinear2d) of a K-channel token map to NCHW fp32.
+// src row of grid cell (gy,gx) of image b: b*Tp + row0 + gy*G + gx, channels 0..K-1 of a Cs-wide row.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bil_src(int d, float ratio, int in, int &i0, int &i1, float &l1) {
+  float s = ratio * ((float)d + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s; if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + ((i0 < in - 1) ? 1 : 0);
+  l1 = s - (float)i0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bilinear_up_fwd_kernel(int B, int G, int Tp, int row0, int Cs, int K, int Ho, int Wo, const T *__restrict__ src, float *__restrict__ dst) {
+  const long long total = (long long)B * Ho * Wo;
+  const float ry = (float)G / (float)Ho, rx = (float)G / (float)Wo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wo), y = (int)((i / Wo) % Ho), b = (int)(i / ((long long)Wo * Ho));
+    int y0, y1, x0, x1; float ly, lx;
+    bil_src(y, ry, G, y0, y1, ly); bil_src(x, rx, G, x0, x1, lx);
+    const T *base = src + ((long long)b * Tp + row0) * Cs;
+    for (int k = 0; k < K; ++k) {
+      const float a = Cvt<T>::ld(base + (long long)(y0 * G + x0) * Cs + k), bq = Cvt<T>::ld(base + (long long)(y0 * G + x1) * Cs + k);
+      const float c = Cvt<T>::ld(base + (long long)(y1 * G + x0) * Cs + k), d = Cvt<T>::ld(base + (long long)(y1 * G + x1) * Cs + k);
+      dst[(((long long)b * K + k) * Ho + y) * Wo + x] = (1.f - ly) * ((1.f - lx) * a + lx * bq) + ly * ((1.f - lx) * c + lx * d);
+    }
+  }
+}
+
+// Adjoint, gather form (deterministic): one thread per (b, source row t in [0,Tp), channel c in [0,Cs)).
+template <typename T>
+__global__ void __launch_bounds__(128)
+bilinear_up_bwd_kernel(int B, int G, int Tp, int row0, int Cs, int K, int Ho, int Wo, const float *__restrict__ ddst, T *__restrict__ dsrc) {
+  const long long total = (long long)B * Tp * Cs;
+  const float ry = (float)G / (float)Ho, rx = (float)G / (float)Wo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cs), t = (int)((i / Cs) % Tp), b = (int)(i / ((long long)Cs * Tp));
+    float acc = 0.f;
+    const int cell = t - row0;
+    if (c < K && cell >= 0 && cell < G * G) {
+      const int gy = cell / G, gx = cell % G;
+      int ylo = (int)floorf(((float)gy - 0.5f) / ry - 0.5f) - 1, yhi = (int)ceilf(((float)gy + 1.5f) / ry - 0.5f) + 1;
+      int xlo = (int)floorf(((float)gx - 0.5f) / rx - 0.5f) - 1, xhi = (int)ceilf(((float)gx + 1.5f) / rx - 0.5f) + 1;
+      if (gy == 0) ylo = 0; if (gy == G - 1) yhi = Ho - 1;
+      if (gx == 0) xlo = 0; if (gx == G - 1) xhi = Wo - 1;
+      ylo = max(ylo, 0); yhi = min(yhi, Ho - 1); xlo = max(xlo, 0); xhi = min(xhi, Wo - 1);
+      const float *gp = ddst + ((long long)b * K + c) * Ho * Wo;
+      for (int y = ylo; y <= yhi; ++y) {
+        int y0, y1; float ly;
+        bil_src(y, ry, G, y0, y1, ly);
+        const float wy = ((y0 == gy) ? (1.f - ly) : 0.f) + ((y1 == gy) ? ly : 0.f);
+        if (wy == 0.f) continue;
+        float rowacc = 0.f;
+        for (int x = xlo; x <= xhi; ++x) {
+          int x0, x1; float lx;
+          bil_src(x, rx, G, x0, x1, lx);
+          const float wx = ((x0 == gx) ? (1.f - lx) : 0.f) + ((x1 == gx) ? lx : 0.f);
+          if (wx != 0.f) rowacc = fmaf(wx, gp[(long long)y * Wo + x], rowacc);
+        }
+        acc = fmaf(wy, rowacc, acc);
+      }
+    }
+    Cvt<T>::st(dsrc + i, acc);
+  }
+}
+
+static inline int grid_for(long long work, int per_block, int cap_mult = 8) {
+  long long g = (work + per_block - 1) / per_block;
+  const long long cap = (long long)kNumSMs * cap_mult;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace ks
+
+using namespace ks;
+
+#define KS_DISPATCH_T(dtype, CALL)                                  \
+  do {                                                              \
+    if ((dtype) == KS_F32) { CALL(float); }                         \
+    else if ((dtype) == KS_BF16) { CALL(__nv_bfloat16); }           \
+    else return KS_EINVAL;                                          \
+  } while (0)
+
+static inline bool al16(const void *p) { return ((uintptr_t)p % 16) == 0; }
+
+extern "C" int ks_layernorm_fwd(int dtype, int64_t rows, int C, const void *x, int64_t ldx, const float *gamma, const float *beta,
+                                float eps, void *y, int64_t ldy, float *mean, float *rstd, void *copy_out, int64_t ldc, void *stream) {
+  KS_CHECK_ARG(rows > 0 && C > 0 && x && y && gamma && beta);
+  if (C % 8 || C > LN_KMAX * 256 || ldx % 8 || ldy % 8 || (copy_out && ldc % 8) || !al16(x) || !al16(y) || !al16(gamma) || !al16(beta) ||
+      (copy_out && !al16(copy_out))) return KS_EUNSUPPORTED;
+  const int grid = grid_for(rows, 8);
+#define CALL(T) layernorm_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(rows, C, (const T *)x, ldx, gamma, beta, eps, (T *)y, ldy, \
+                                                                                  mean, rstd, (T *)copy_out, ldc)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_layernorm_bwd(int dtype, int64_t rows, int C, const void *dy, int64_t lddy, const void *x, int64_t ldx,
+                                const float *mean, const float *rstd, const float *gamma, void *dx, int64_t lddx, int accumulate_dx,
+                                float *dgamma, float *dbeta, void *stream) {
+  KS_CHECK_ARG(rows > 0 && C > 0 && dy && x && mean && rstd && gamma);
+  if (C % 8 || C > LNB_KMAX * 256 || lddy % 8 || ldx % 8 || (dx && lddx % 8) || !al16(dy) || !al16(x) || !al16(gamma) || (dx && !al16(dx)))
+    return KS_EUNSUPPORTED;
+  const int grid = grid_for(rows, 8 * 8, 2);     // >= 8 rows per warp so that the per-CTA column atomics amortise
+  const size_t smem = (size_t)2 * C * sizeof(float);
+#define CALL(T) layernorm_bwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(rows, C, (const T *)dy, lddy, (const T *)x, ldx, mean, rstd, \
+                                                                                     gamma, (T *)dx, lddx, accumulate_dx, dgamma, dbeta)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_patchify_ln(int dtype, int B, int Cc, int Hi, int Wi, int Tp, const float *img, const float *gamma, const float *beta,
+                              float eps, void *out, float *mean, float *rstd, void *stream) {
+  KS_CHECK_ARG(B > 0 && img && gamma && beta && out && mean && rstd);
+  if (Cc < 1 || Cc > PCMAX || Hi % PATCH || Wi % PATCH || (Hi / PATCH) * (Wi / PATCH) + 1 > Tp || !al16(img)) return KS_EUNSUPPORTED;
+  const int grid = grid_for((long long)B * (Hi / PATCH) * (Wi / PATCH), 8);
+#define CALL(T) patchify_ln_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(B, Cc, Hi, Wi, Tp, img, gamma, beta, eps, (T *)out, mean, rstd)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_patchify_ln_bwd(int dtype, int B, int Cc, int Hi, int Wi, int Tp, const float *img, const float *mean, const float *rstd,
+                                  const void *dy, float *dgamma, float *dbeta, void *stream) {
+  KS_CHECK_ARG(B > 0 && img && mean && rstd && dy && dgamma && dbeta);
+  if (Cc < 1 || Cc > PCMAX || Hi % PATCH || Wi % PATCH) return KS_EUNSUPPORTED;
+  const int grid = grid_for((long long)B * (Hi / PATCH) * (Wi / PATCH), 8 * 8, 2);
+  const size_t smem = (size_t)2 * PATCH * PATCH * Cc * sizeof(float);
+#define CALL(T) patchify_ln_bwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(B, Cc, Hi, Wi, Tp, img, mean, rstd, (const T *)dy, dgamma, dbeta)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_vit_assemble(int dtype, int B, int T, int Tp, int D, const void *e, const float *cls, const float *pos, void *x0,
+                               void *stream) {
+  KS_CHECK_ARG(B > 0 && T > 0 && Tp >= T && e && cls && pos && x0);
+  if (D % 8 || !al16(e) || !al16(x0) || !al16(cls) || !al16(pos)) return KS_EUNSUPPORTED;
+  const int grid = grid_for((long long)B * Tp * (D / 8), 256);
+#define CALL(Ty) vit_assemble_kernel<Ty><<<grid, 256, 0, (cudaStream_t)stream>>>(B, T, Tp, D, (const Ty *)e, cls, pos, (Ty *)x0)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_vit_assemble_bwd(int dtype, int B, int T, int Tp, int D, const void *dx0, void *de, float *dcls, float *dpos, void *stream) {
+  KS_CHECK_ARG(B > 0 && T > 0 && Tp >= T && dx0 && de && dcls && dpos);
+  if (D % 8 || !al16(dx0) || !al16(de) || !al16(dcls) || !al16(dpos)) return KS_EUNSUPPORTED;
+  dim3 grid((unsigned)Tp, (unsigned)((D / 8 + 127) / 128));
+#define CALL(Ty) vit_assemble_bwd_kernel<Ty><<<grid, 128, 0, (cudaStream_t)stream>>>(B, T, Tp, D, (const Ty *)dx0, (Ty *)de, dcls, dpos)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+static int att_cfg(int T, int Tp, int dh, int extra_rows, size_t &smem, int &rows_per_cta, int &nblk, int B, int heads) {
+  if (dh != ATT_DH || Tp > ATT_JMAX * 32 || T > Tp || Tp % 8) return KS_EUNSUPPORTED;
+  smem = ((size_t)2 * Tp * ATT_PITCH + (size_t)ATT_WARPS * extra_rows * Tp + (size_t)ATT_WARPS * ATT_DH) * sizeof(float);
+  if (smem > 220 * 1024) return KS_EUNSUPPORTED;
+  // enough CTAs to fill the machine: split the rows of one (b, head) when B*heads is small
+  nblk = 1;
+  while ((long long)B * heads * nblk < 2 * kNumSMs && nblk < 8) nblk <<= 1;
+  rows_per_cta = ((Tp + nblk - 1) / nblk + ATT_WARPS - 1) / ATT_WARPS * ATT_WARPS;
+  nblk = (Tp + rows_per_cta - 1) / rows_per_cta;
+  return KS_OK;
+}
+
+extern "C" int ks_attention_fwd(int dtype, int B, int T, int Tp, int heads, int dh, const void *qkv, float scale, void *out, void *probs,
+                                void *stream) {
+  KS_CHECK_ARG(B > 0 && T > 0 && heads > 0 && qkv && out && probs);
+  size_t smem; int rpc, nblk;
+  int rc = att_cfg(T, Tp, dh, 1, smem, rpc, nblk, B, heads); if (rc) return rc;
+  if (!al16(qkv) || !al16(out) || !al16(probs)) return KS_EUNSUPPORTED;
+  dim3 grid((unsigned)nblk, (unsigned)heads, (unsigned)B);
+#define CALL(Ty) { cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<Ty>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); \
+    if (e != cudaSuccess) return (int)e; \
+    attention_fwd_kernel<Ty><<<grid, ATT_WARPS * 32, smem, (cudaStream_t)stream>>>(T, Tp, heads, (const Ty *)qkv, scale, (Ty *)out, (Ty *)probs, rpc); }
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_attention_bwd(int dtype, int B, int T, int Tp, int heads, int dh, const void *qkv, const void *probs, const void *dout,
+                                float scale, void *dqkv, void *ds_scratch, void *stream) {
+  KS_CHECK_ARG(B > 0 && T > 0 && heads > 0 && qkv && probs && dout && dqkv && ds_scratch);
+  size_t smem; int rpc, nblk;
+  int rc = att_cfg(T, Tp, dh, 2, smem, rpc, nblk, B, heads); if (rc) return rc;
+  if (!al16(qkv) || !al16(dout) || !al16(probs) || !al16(dqkv) || !al16(ds_scratch)) return KS_EUNSUPPORTED;
+  dim3 grid((unsigned)nblk, (unsigned)heads, (unsigned)B);
+#define CALL(Ty) { cudaError_t e = cudaFuncSetAttribute(attention_bwd_rows_kernel<Ty>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); \
+    if (e != cudaSuccess) return (int)e; \
+    e = cudaFuncSetAttribute(attention_bwd_cols_kernel<Ty>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); \
+    if (e != cudaSuccess) return (int)e; \
+    attention_bwd_rows_kernel<Ty><<<grid, ATT_WARPS * 32, smem, (cudaStream_t)stream>>>(T, Tp, heads, (const Ty *)qkv, (const Ty *)probs, \
+        (const Ty *)dout, scale, (Ty *)dqkv, (Ty *)ds_scratch, rpc); \
+    attention_bwd_cols_kernel<Ty><<<grid, ATT_WARPS * 32, smem, (cudaStream_t)stream>>>(T, Tp, heads, (const Ty *)qkv, (const Ty *)probs, \
+        (const Ty *)ds_scratch, (const Ty *)dout, scale, (Ty *)dqkv, rpc); }
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_gelu_fwd(int dtype, int64_t n, const void *u, void *h, void *stream) {
+  KS_CHECK_ARG(n > 0 && u && h);
+  if (n % 8 || !al16(u) || !al16(h)) return KS_EUNSUPPORTED;
+  const int grid = grid_for(n / 8, 256 * 4);
+#define CALL(Ty) gelu_fwd_kernel<Ty><<<grid, 256, 0, (cudaStream_t)stream>>>(n / 8, (const Ty *)u, (Ty *)h)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_gelu_bwd(int dtype, int64_t n, const void *u, const void *dh, void *du, void *stream) {
+  KS_CHECK_ARG(n > 0 && u && dh && du);
+  if (n % 8 || !al16(u) || !al16(dh) || !al16(du)) return KS_EUNSUPPORTED;
+  const int grid = grid_for(n / 8, 256 * 4);
+#define CALL(Ty) gelu_bwd_kernel<Ty><<<grid, 256, 0, (cudaStream_t)stream>>>(n / 8, (const Ty *)u, (const Ty *)dh, (Ty *)du)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_bilinear_up_fwd(int dtype, int B, int G, int Tp, int row0, int Cs, int K, int Ho, int Wo, const void *src, float *dst,
+                                  void *stream) {
+  KS_CHECK_ARG(B > 0 && G > 0 && K > 0 && K <= Cs && row0 >= 0 && row0 + G * G <= Tp && Ho > 0 && Wo > 0 && src && dst);
+  const int grid = grid_for((long long)B * Ho * Wo, 256);
+#define CALL(Ty) bilinear_up_fwd_kernel<Ty><<<grid, 256, 0, (cudaStream_t)stream>>>(B, G, Tp, row0, Cs, K, Ho, Wo, (const Ty *)src, dst)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_bilinear_up_bwd(int dtype, int B, int G, int Tp, int row0, int Cs, int K, int Ho, int Wo, const float *ddst, void *dsrc,
+                                  void *stream) {
+  KS_CHECK_ARG(B > 0 && G > 0 && K > 0 && K <= Cs && row0 >= 0 && row0 + G * G <= Tp && Ho > 0 && Wo > 0 && ddst && dsrc);
+  const int grid = grid_for((long long)B * Tp * Cs, 128, 16);
+#define CALL(Ty) bilinear_up_bwd_kernel<Ty><<<grid, 128, 0, (cudaStream_t)stream>>>(B, G, Tp, row0, Cs, K, Ho, Wo, ddst, (Ty *)dsrc)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}

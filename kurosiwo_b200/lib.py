@@ -93,6 +93,8 @@ EXPORTED_SYMBOLS = [
     "ks_channel_sum", "ks_ecam_pool", "ks_ecam_gates", "ks_ecam_final", "ks_ecam_bwd_reduce", "ks_ecam_gates_bwd",
     "ks_ecam_bwd_apply", "ks_ce_dice_workspace_bytes", "ks_ce_dice_fwd_bwd", "ks_adam_step",
     "ks_softmax_head_fwd", "ks_softmax_head_bwd", "ks_dropout_mask", "ks_channel_scale", "ks_absdiff_fwd", "ks_absdiff_bwd",
+    "ks_layernorm_fwd", "ks_layernorm_bwd", "ks_patchify_ln", "ks_patchify_ln_bwd", "ks_vit_assemble", "ks_vit_assemble_bwd",
+    "ks_attention_fwd", "ks_attention_bwd", "ks_gelu_fwd", "ks_gelu_bwd", "ks_bilinear_up_fwd", "ks_bilinear_up_bwd",
 ]
 
 
@@ -308,6 +310,72 @@ class CudaOps:
         rc = self.lib.ks_absdiff_bwd(dtype_code(a.dtype), C.c_int(a.N), C.c_int(a.H), C.c_int(a.W), _vp(a), _vp(b), _vp(g),
                                      _vp(da), C.c_int(int(acc_a)), _vp(db), C.c_int(int(acc_b)), self._stream())
         self._check(rc, "ks_absdiff_bwd")
+
+    # -- ViT encoder / FloodViT head passes (token matrices are 2-D row-major torch tensors) ------------
+    def layernorm_fwd(self, x, gamma, beta, eps, y, mean=None, rstd=None, copy_out=None):
+        rows, Cn = x.shape
+        rc = self.lib.ks_layernorm_fwd(dtype_code(x.dtype), C.c_int64(rows), C.c_int(Cn), _p(x), C.c_int64(x.stride(0)), _p(gamma), _p(beta),
+                                       C.c_float(eps), _p(y), C.c_int64(y.stride(0)), _p(mean), _p(rstd), _p(copy_out),
+                                       C.c_int64(0 if copy_out is None else copy_out.stride(0)), self._stream())
+        self._check(rc, "ks_layernorm_fwd")
+
+    def layernorm_bwd(self, dy, x, mean, rstd, gamma, dx, accumulate_dx, dgamma, dbeta):
+        rows, Cn = x.shape
+        rc = self.lib.ks_layernorm_bwd(dtype_code(x.dtype), C.c_int64(rows), C.c_int(Cn), _p(dy), C.c_int64(dy.stride(0)), _p(x),
+                                       C.c_int64(x.stride(0)), _p(mean), _p(rstd), _p(gamma), _p(dx),
+                                       C.c_int64(0 if dx is None else dx.stride(0)), C.c_int(int(accumulate_dx)), _p(dgamma), _p(dbeta),
+                                       self._stream())
+        self._check(rc, "ks_layernorm_bwd")
+
+    def patchify_ln(self, img, Tp, gamma, beta, eps, out, mean, rstd):
+        B, Cc, Hi, Wi = img.shape
+        rc = self.lib.ks_patchify_ln(dtype_code(out.dtype), C.c_int(B), C.c_int(Cc), C.c_int(Hi), C.c_int(Wi), C.c_int(Tp), _p(img), _p(gamma),
+                                     _p(beta), C.c_float(eps), _p(out), _p(mean), _p(rstd), self._stream())
+        self._check(rc, "ks_patchify_ln")
+
+    def patchify_ln_bwd(self, img, Tp, mean, rstd, dy, dgamma, dbeta):
+        B, Cc, Hi, Wi = img.shape
+        rc = self.lib.ks_patchify_ln_bwd(dtype_code(dy.dtype), C.c_int(B), C.c_int(Cc), C.c_int(Hi), C.c_int(Wi), C.c_int(Tp), _p(img), _p(mean),
+                                         _p(rstd), _p(dy), _p(dgamma), _p(dbeta), self._stream())
+        self._check(rc, "ks_patchify_ln_bwd")
+
+    def vit_assemble(self, B, T, Tp, e, cls, pos, x0):
+        rc = self.lib.ks_vit_assemble(dtype_code(e.dtype), C.c_int(B), C.c_int(T), C.c_int(Tp), C.c_int(e.shape[1]), _p(e), _p(cls), _p(pos),
+                                      _p(x0), self._stream())
+        self._check(rc, "ks_vit_assemble")
+
+    def vit_assemble_bwd(self, B, T, Tp, dx0, de, dcls, dpos):
+        rc = self.lib.ks_vit_assemble_bwd(dtype_code(dx0.dtype), C.c_int(B), C.c_int(T), C.c_int(Tp), C.c_int(dx0.shape[1]), _p(dx0), _p(de),
+                                          _p(dcls), _p(dpos), self._stream())
+        self._check(rc, "ks_vit_assemble_bwd")
+
+    def attention_fwd(self, B, T, Tp, heads, dh, qkv, scale, out, probs):
+        rc = self.lib.ks_attention_fwd(dtype_code(qkv.dtype), C.c_int(B), C.c_int(T), C.c_int(Tp), C.c_int(heads), C.c_int(dh), _p(qkv),
+                                       C.c_float(scale), _p(out), _p(probs), self._stream())
+        self._check(rc, "ks_attention_fwd")
+
+    def attention_bwd(self, B, T, Tp, heads, dh, qkv, probs, dout, scale, dqkv, ds_scratch):
+        rc = self.lib.ks_attention_bwd(dtype_code(qkv.dtype), C.c_int(B), C.c_int(T), C.c_int(Tp), C.c_int(heads), C.c_int(dh), _p(qkv),
+                                       _p(probs), _p(dout), C.c_float(scale), _p(dqkv), _p(ds_scratch), self._stream())
+        self._check(rc, "ks_attention_bwd")
+
+    def gelu_fwd(self, u, h):
+        rc = self.lib.ks_gelu_fwd(dtype_code(u.dtype), C.c_int64(u.numel()), _p(u), _p(h), self._stream())
+        self._check(rc, "ks_gelu_fwd")
+
+    def gelu_bwd(self, u, dh, du):
+        rc = self.lib.ks_gelu_bwd(dtype_code(u.dtype), C.c_int64(u.numel()), _p(u), _p(dh), _p(du), self._stream())
+        self._check(rc, "ks_gelu_bwd")
+
+    def bilinear_up_fwd(self, B, G, Tp, row0, K, Ho, Wo, src, dst):
+        rc = self.lib.ks_bilinear_up_fwd(dtype_code(src.dtype), C.c_int(B), C.c_int(G), C.c_int(Tp), C.c_int(row0), C.c_int(src.shape[1]),
+                                         C.c_int(K), C.c_int(Ho), C.c_int(Wo), _p(src), _p(dst), self._stream())
+        self._check(rc, "ks_bilinear_up_fwd")
+
+    def bilinear_up_bwd(self, B, G, Tp, row0, K, Ho, Wo, ddst, dsrc):
+        rc = self.lib.ks_bilinear_up_bwd(dtype_code(dsrc.dtype), C.c_int(B), C.c_int(G), C.c_int(Tp), C.c_int(row0), C.c_int(dsrc.shape[1]),
+                                         C.c_int(K), C.c_int(Ho), C.c_int(Wo), _p(ddst), _p(dsrc), self._stream())
+        self._check(rc, "ks_bilinear_up_bwd")
 
     # -- loss --------------------------------------------------------------------------------
     def ce_dice_workspace(self, N: int, device) -> torch.Tensor:

@@ -329,3 +329,117 @@ class ShadowOps:
         ta, tb = _t(da), _t(db)
         ta.copy_((ta.float() + s if acc_a else s).to(ta.dtype))
         tb.copy_((tb.float() - s if acc_b else -s).to(tb.dtype))
+
+    # -- ViT encoder / FloodViT head passes ------------------------------------------------------
+    def layernorm_fwd(self, x, gamma, beta, eps, y, mean=None, rstd=None, copy_out=None):
+        xf = x.float()
+        mu = xf.mean(1)
+        var = ((xf - mu[:, None]) ** 2).mean(1)
+        rs = torch.rsqrt(var + eps)
+        y.copy_((((xf - mu[:, None]) * rs[:, None]) * gamma + beta).to(y.dtype))
+        if mean is not None:
+            mean.copy_(mu)
+        if rstd is not None:
+            rstd.copy_(rs)
+        if copy_out is not None:
+            copy_out.copy_(x)
+
+    def layernorm_bwd(self, dy, x, mean, rstd, gamma, dx, accumulate_dx, dgamma, dbeta):
+        xh = (x.float() - mean[:, None]) * rstd[:, None]
+        d = dy.float()
+        g = d * gamma
+        if dx is not None:
+            v = rstd[:, None] * (g - g.mean(1, keepdim=True) - xh * (g * xh).mean(1, keepdim=True))
+            dx.copy_((dx.float() + v if accumulate_dx else v).to(dx.dtype))
+        if dgamma is not None:
+            dgamma += (d * xh).sum(0)
+        if dbeta is not None:
+            dbeta += d.sum(0)
+
+    @staticmethod
+    def _patches(img):
+        B, Cc, Hi, Wi = img.shape
+        gh, gw = Hi // 16, Wi // 16
+        return img.view(B, Cc, gh, 16, gw, 16).permute(0, 2, 4, 3, 5, 1).reshape(B, gh * gw, 256 * Cc)   # b (h w) (p1 p2 c)
+
+    def patchify_ln(self, img, Tp, gamma, beta, eps, out, mean, rstd):
+        x = self._patches(img.float())
+        B, n, PD = x.shape
+        mu = x.mean(2)
+        rs = torch.rsqrt(((x - mu[..., None]) ** 2).mean(2) + eps)
+        y = (x - mu[..., None]) * rs[..., None] * gamma + beta
+        out.view(B, Tp, PD)[:, 1:1 + n] = y.to(out.dtype)
+        mean.view(B, Tp)[:, 1:1 + n] = mu
+        rstd.view(B, Tp)[:, 1:1 + n] = rs
+
+    def patchify_ln_bwd(self, img, Tp, mean, rstd, dy, dgamma, dbeta):
+        x = self._patches(img.float())
+        B, n, PD = x.shape
+        xh = (x - mean.view(B, Tp)[:, 1:1 + n, None]) * rstd.view(B, Tp)[:, 1:1 + n, None]
+        d = dy.view(B, Tp, PD)[:, 1:1 + n].float()
+        dgamma += (d * xh).sum((0, 1))
+        dbeta += d.sum((0, 1))
+
+    def vit_assemble(self, B, T, Tp, e, cls, pos, x0):
+        D = e.shape[1]
+        v = torch.zeros(B, Tp, D)
+        v[:, 1:T] = e.view(B, Tp, D)[:, 1:T].float()
+        v[:, 0] = cls.view(1, D)
+        v[:, :T] += pos.view(-1, D)[:T]
+        x0.copy_(v.view(B * Tp, D).to(x0.dtype))
+
+    def vit_assemble_bwd(self, B, T, Tp, dx0, de, dcls, dpos):
+        D = dx0.shape[1]
+        g = dx0.view(B, Tp, D).float()
+        dpos.view(-1, D)[:T] = g[:, :T].sum(0)
+        dcls.view(-1)[:D] = g[:, 0].sum(0)
+        o = torch.zeros(B, Tp, D)
+        o[:, 1:T] = g[:, 1:T]
+        de.copy_(o.view(B * Tp, D).to(de.dtype))
+
+    def attention_fwd(self, B, T, Tp, heads, dh, qkv, scale, out, probs):
+        inner = heads * dh
+        q, k, v = [t.view(B, Tp, heads, dh).permute(0, 2, 1, 3)[:, :, :T] for t in qkv.float().view(B, Tp, 3 * inner).split(inner, dim=2)]
+        p = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1).to(probs.dtype).float()
+        pf = torch.zeros(B, heads, Tp, Tp)
+        pf[:, :, :T, :T] = p
+        probs.copy_(pf.view(probs.shape).to(probs.dtype))
+        o = torch.zeros(B, Tp, heads, dh)
+        o[:, :T] = (p @ v).permute(0, 2, 1, 3)
+        out.copy_(o.view(B * Tp, inner).to(out.dtype))
+
+    def attention_bwd(self, B, T, Tp, heads, dh, qkv, probs, dout, scale, dqkv, ds_scratch):
+        inner = heads * dh
+        q, k, v = [t.view(B, Tp, heads, dh).permute(0, 2, 1, 3)[:, :, :T] for t in qkv.float().view(B, Tp, 3 * inner).split(inner, dim=2)]
+        p = probs.float().view(B, heads, Tp, Tp)[:, :, :T, :T]
+        do = dout.float().view(B, Tp, heads, dh).permute(0, 2, 1, 3)[:, :, :T]
+        dv = p.transpose(-1, -2) @ do
+        dp = do @ v.transpose(-1, -2)
+        ds = (p * (dp - (dp * p).sum(-1, keepdim=True))).to(dqkv.dtype).float()
+        dq = ds @ k * scale
+        dk = ds.transpose(-1, -2) @ q * scale
+        o = torch.zeros(B, Tp, 3, heads, dh)
+        for i, t in enumerate((dq, dk, dv)):
+            o[:, :T, i] = t.permute(0, 2, 1, 3)
+        dqkv.copy_(o.view(B * Tp, 3 * inner).to(dqkv.dtype))
+
+    def gelu_fwd(self, u, h):
+        h.copy_(F.gelu(u.float()).to(h.dtype))
+
+    def gelu_bwd(self, u, dh, du):
+        x = u.float()
+        d = 0.5 * (1 + torch.erf(x * 0.7071067811865476)) + x * 0.3989422804014327 * torch.exp(-0.5 * x * x)
+        du.copy_((dh.float() * d).to(du.dtype))
+
+    def bilinear_up_fwd(self, B, G, Tp, row0, K, Ho, Wo, src, dst):
+        Cs = src.shape[1]
+        m = src.float().view(B, Tp, Cs)[:, row0:row0 + G * G, :K].reshape(B, G, G, K).permute(0, 3, 1, 2)
+        dst.copy_(F.interpolate(m, size=(Ho, Wo), mode="bilinear", align_corners=False))
+
+    def bilinear_up_bwd(self, B, G, Tp, row0, K, Ho, Wo, ddst, dsrc):
+        Cs = dsrc.shape[1]
+        m = torch.zeros(B, K, G, G, requires_grad=True)
+        F.interpolate(m, size=(Ho, Wo), mode="bilinear", align_corners=False).backward(ddst.float())
+        o = torch.zeros(B, Tp, Cs)
+        o[:, row0:row0 + G * G, :K] = m.grad.permute(0, 2, 3, 1).reshape(B, G * G, K)
+        dsrc.copy_(o.view(B * Tp, Cs).to(dsrc.dtype))
