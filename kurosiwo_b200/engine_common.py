@@ -94,8 +94,10 @@ class TrainStepMixin:
                            group=process_group)
         self.graph = None
 
-    def _fwd_loss_bwd(self, xA, xB, mask):
-        logits = self.forward(xA, xB, training=True)
+    def _fwd_loss_bwd(self, *args):
+        """args = the model inputs (two dates for change detection, one stacked image for segmentation) + the mask."""
+        inputs, mask = args[:-1], args[-1]
+        logits = self.forward(*inputs, training=True)
         self.ops.ce_dice(logits, mask, self.cw, self.ignore_index, 1.0, self.loss3, self.dlogits, self.pred, self.loss_ws)
         self.backward(self.dlogits)
 
@@ -109,14 +111,14 @@ class TrainStepMixin:
         self.ops.adam_step(self.params.flat, self.params.grad, self.adam_m, self.adam_v, hp["lr"], hp["b1"], hp["b2"], hp["eps"],
                            hp["wd"], 1.0 / self.world, self.adam_step)
 
-    def train_step(self, xA: torch.Tensor, xB: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
-        """One optimizer step; returns the device tensor [total, dice, ce] (no host sync)."""
-        self._fwd_loss_bwd(xA, xB, mask)
+    def train_step(self, *args) -> torch.Tensor:
+        """One optimizer step on (inputs..., mask); returns the device tensor [total, dice, ce] (no host sync)."""
+        self._fwd_loss_bwd(*args)
         self._allreduce()
         self._optimizer()
         return self.loss3
 
-    def capture(self, xA: torch.Tensor, xB: torch.Tensor, mask: torch.Tensor):
+    def capture(self, *args):
         """Capture the step over STATIC input tensors: one CUDA graph on a single GPU; with data parallelism two graphs
         (forward+loss+backward | Adam) around the eager NCCL all-reduce.  Returns a callable that replays one step."""
         self.params.ensure(self.device)
@@ -124,19 +126,19 @@ class TrainStepMixin:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(2):
-                self.train_step(xA, xB, mask)
+                self.train_step(*args)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         if self.world == 1:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self.train_step(xA, xB, mask)
+                self.train_step(*args)
             self.replay = self.graph.replay
         else:
             ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             # thread_local: NCCL's watchdog thread may issue CUDA calls while this thread captures
             with torch.cuda.graph(ga, capture_error_mode="thread_local"):
-                self._fwd_loss_bwd(xA, xB, mask)
+                self._fwd_loss_bwd(*args)
             with torch.cuda.graph(gb, capture_error_mode="thread_local"):
                 self._optimizer()
             self.graph = (ga, gb)

@@ -5,6 +5,7 @@ import torch
 
 from .siam_unet import SiamUnet_conc, SiamUnet_diff
 from .snunet import SNUNet_ECAM
+from .vision_transformer import FinetunerSegmentation, ViT  # noqa: F401
 
 
 def initialize_cd_model(configs, model_configs, phase="train"):
@@ -26,3 +27,26 @@ def initialize_cd_model(configs, model_configs, phase="train"):
         checkpoint = torch.load(configs["resume_checkpoint"], map_location=configs["device"])
         model.load_state_dict(checkpoint["model_state_dict"])
     return model
+
+
+def initialize_segmentation_model(config, model_configs):
+    """models/model_utilities.py:97-167 for the method on the B200 path: `finetune` (FloodViT).  The reference loads a pickled
+    encoder from config["encoder"] (:159); without a checkpoint the encoder is built from the `encoder_config` block of
+    configs/method/finetune/finetune.json (the reference ships neither - SURVEY.md §8(c) "FloodViT definition gap")."""
+    if config["method"].lower() != "finetune":
+        raise NotImplementedError(f"method {config['method']} is not on the B200 hot path (SURVEY.md §8: smp U-Net family, UPerNet backbones)")
+    precision = "bf16" if config.get("mixed_precision", True) else "fp32"
+    precision = config.get("precision", precision)
+    if config.get("encoder"):
+        encoder = torch.load(config["encoder"], map_location="cpu", weights_only=False)
+        encoder.precision = precision
+    else:
+        ec = dict(model_configs.get("encoder_config") or config["encoder_config"])
+        encoder = ViT(image_size=ec.get("image_size", 224), patch_size=ec.get("patch_size", 16), num_classes=ec.get("num_classes", 1000),
+                      dim=ec["dim"], depth=ec["depth"], heads=ec["heads"], mlp_dim=ec["mlp_dim"], channels=config["num_channels"],
+                      precision=precision)
+    for param in encoder.parameters():
+        param.requires_grad = not config.get("linear_eval", False)
+    if config.get("linear_eval"):
+        raise NotImplementedError("linear_eval=true (frozen encoder) is not on the fused path: the fused step updates all parameters")
+    return FinetunerSegmentation(encoder=encoder, configs=config, precision=precision)

@@ -12,7 +12,8 @@ import torch
 
 from kurosiwo_b200 import json5lite, synthetic
 from kurosiwo_b200.change_detection_trainer import eval_change_detection, train_change_detection
-from kurosiwo_b200.model_utilities import initialize_cd_model
+from kurosiwo_b200.model_utilities import initialize_cd_model, initialize_segmentation_model
+from kurosiwo_b200.segmentation_trainer import eval_semantic_segmentation, train_semantic_segmentation
 from kurosiwo_b200.utilities import update_config
 
 parser = argparse.ArgumentParser()
@@ -30,6 +31,10 @@ def load_configs(args, root=Path(__file__).resolve().parent):
     if args.method is not None:
         configs["method"] = args.method
     m = configs["method"].lower()
+    if m == "finetune":
+        configs["task"] = "segmentation"                   # the reference selects the trainer by task (main.py:140-200)
+        if args.inputs is None:
+            configs["inputs_override"] = ["pre_event_1", "pre_event_2", "post_event"]
     model_configs = json5lite.load(open(root / f'configs/method/{m}/{m.replace("-", "_")}.json'))
     if args.backbone is not None:
         model_configs["backbone"] = args.backbone          # stored and ignored by CD models, as in the reference
@@ -38,6 +43,8 @@ def load_configs(args, root=Path(__file__).resolve().parent):
     configs.update(json5lite.load(open(root / "configs/train/train_config.json")))
     if args.inputs is not None:
         configs["inputs"] = args.inputs
+    elif "inputs_override" in configs:
+        configs["inputs"] = configs.pop("inputs_override")
     if args.dem:
         configs["dem"] = True
     configs = update_config(configs, args)
@@ -64,8 +71,15 @@ if __name__ == "__main__":
     Path(configs["checkpoint_path"]).mkdir(parents=True, exist_ok=True)
     pprint.pprint(configs)
     train_loader, val_loader, test_loader = prepare_loaders(configs)
+    if configs["task"] == "segmentation":
+        model = initialize_segmentation_model(configs, model_configs).to(configs["device"])
+        if not configs["test"]:
+            train_semantic_segmentation(model, train_loader, val_loader, test_loader, configs=configs, model_configs=model_configs)
+        test_acc, test_score, miou = eval_semantic_segmentation(model, test_loader, configs=configs, settype="Test", model_configs=model_configs)
+        print("Test Mean IOU: ", miou)
+        raise SystemExit(0)
     if configs["task"] != "cd":
-        raise NotImplementedError("only task 'cd' is on the B200 hot path in this round (SURVEY.md §8)")
+        raise NotImplementedError("tasks 'cd' and 'segmentation' are on the B200 hot path (SURVEY.md §8); 'mae' pre-training is not")
     model = initialize_cd_model(configs, model_configs)
     if not configs["test"]:
         train_change_detection(model, train_loader, val_loader, test_loader, configs=configs, model_configs=model_configs)

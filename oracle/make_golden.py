@@ -82,6 +82,7 @@ def main():
         np.savez_compressed(OUT / f"snunet_{tag}.npz", **fx)
         print(tag, "loss", float(loss.detach()), "logits", out.shape)
     siam_goldens()
+    vit_goldens()
 
 
 def siam_goldens():
@@ -136,7 +137,51 @@ def siam_goldens():
         print("siam", kind, N, H, W, "loss", float(loss.detach()))
 
 
+def vit_goldens():
+    """FloodViT fixtures (ViT encoder + linear FinetunerSegmentation head) from the unmodified reference modules."""
+    from oracle.ref_import import install_stubs
+    install_stubs()
+    from models.vision_transformer import ViT as RefViT                    # noqa: E402  (reference, read-only)
+    from models.model_utilities import FinetunerSegmentation as RefFinetuner  # noqa: E402
+    from utilities.bce_and_dice import BCEandDiceLoss as RefLoss           # noqa: E402
+    from oracle import vit_oracle
+
+    for tag, (dim, depth, heads, mlp, N, seed) in {"d128_l2_h2": (128, 2, 2, 256, 2, 61), "d192_l3_h3": (192, 3, 3, 384, 2, 62)}.items():
+        sd = vit_oracle.make_state(seed, dim, depth, heads, mlp)
+        img, mask = vit_oracle.make_batch(seed, N)
+        enc = RefViT(image_size=224, patch_size=16, num_classes=3, dim=dim, depth=depth, heads=heads, mlp_dim=mlp, channels=6)
+        model = RefFinetuner(encoder=enc, configs={"mlp": False, "decoder": False, "num_classes": 3, "finetuning_patch_size": 16})
+        model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+        model.train()
+        crit = RefLoss(weights=torch.tensor([1.0, 1.0, 1.0]), ignore_index=3, use_softmax=True)
+        out = model(torch.from_numpy(img))
+        loss = crit(out, torch.from_numpy(mask))
+        loss.backward()
+        with torch.no_grad():
+            tokens = model.model(torch.from_numpy(img))
+        fx = {"dim": dim, "depth": depth, "heads": heads, "mlp": mlp, "N": N, "seed": seed, "loss": loss.detach().numpy(),
+              "logits_sample": out.detach().numpy()[:, :, ::7, ::7].copy(),
+              "tokens": tokens.numpy()}
+        names, norms = [], []
+        keep_full = {"model.cls_token", "model.pos_embedding", "model.to_patch_embedding.1.weight", "model.to_patch_embedding.2.bias",
+                     "model.to_patch_embedding.3.weight", "model.transformer.norm.bias", "model.transformer.layers.0.0.norm.weight",
+                     "model.transformer.layers.0.0.to_qkv.weight", "model.transformer.layers.1.0.to_out.0.weight",
+                     "model.transformer.layers.1.1.net.1.bias", "model.transformer.layers.0.1.net.4.weight", "head.weight", "head.bias"}
+        for k, p in model.named_parameters():
+            names.append(k)
+            norms.append(float(p.grad.double().norm()))
+            if k in keep_full:
+                fx[f"grad.{k}"] = p.grad.numpy()
+        fx["grad_names"] = np.array(names)
+        fx["grad_norms"] = np.array(norms, np.float64)
+        np.savez_compressed(OUT / f"floodvit_{tag}.npz", **fx)
+        print("floodvit", tag, "loss", float(loss.detach()))
+
+
 if __name__ == "__main__":
+    if "--vit-only" in sys.argv:
+        vit_goldens()
+        sys.exit(0)
     if "--siam-only" in sys.argv:
         siam_goldens()
         sys.exit(0)

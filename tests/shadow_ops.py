@@ -438,8 +438,9 @@ class ShadowOps:
 
     def bilinear_up_bwd(self, B, G, Tp, row0, K, Ho, Wo, ddst, dsrc):
         Cs = dsrc.shape[1]
-        m = torch.zeros(B, K, G, G, requires_grad=True)
-        F.interpolate(m, size=(Ho, Wo), mode="bilinear", align_corners=False).backward(ddst.float())
+        with torch.enable_grad():      # called from inside autograd.Function.backward, where grad mode is off
+            m = torch.zeros(B, K, G, G, requires_grad=True)
+            F.interpolate(m, size=(Ho, Wo), mode="bilinear", align_corners=False).backward(ddst.float())
         o = torch.zeros(B, Tp, Cs)
         o[:, row0:row0 + G * G, :K] = m.grad.permute(0, 2, 3, 1).reshape(B, G * G, K)
         dsrc.copy_(o.view(B * Tp, Cs).to(dsrc.dtype))

@@ -1,0 +1,90 @@
+"""FloodViT (ViT encoder + linear FinetunerSegmentation head): oracle pinned to the reference goldens, and the product's host
+schedule (kurosiwo_b200/vit_engine.py) driven through the CPU shadow ops against the oracle.  No GPU needed."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from kurosiwo_b200.vision_transformer import FinetunerSegmentation, ViT
+from oracle import vit_oracle
+from oracle.snunet_oracle import ce_dice_torch
+from shadow_ops import ShadowOps
+
+GOLD = Path(__file__).parent / "golden"
+FIXTURES = ["floodvit_d128_l2_h2.npz", "floodvit_d192_l3_h3.npz"]
+HEAD_CFG = {"mlp": False, "decoder": False, "num_classes": 3, "finetuning_patch_size": 16}
+
+
+def _case(fx):
+    dim, depth, heads, mlp, N, seed = (int(fx[k]) for k in ("dim", "depth", "heads", "mlp", "N", "seed"))
+    sd_np = vit_oracle.make_state(seed, dim, depth, heads, mlp)
+    img, mask = (torch.from_numpy(a) for a in vit_oracle.make_batch(seed, N))
+    return dim, depth, heads, mlp, sd_np, img, mask
+
+
+@pytest.mark.parametrize("fixture", FIXTURES)
+def test_oracle_matches_reference_golden(fixture):
+    fx = np.load(GOLD / fixture)
+    dim, depth, heads, mlp, sd_np, img, mask = _case(fx)
+    sd = vit_oracle.to_torch_state(sd_np)
+    loss, logits, grads = vit_oracle.train_step(sd, img, mask, heads)
+    np.testing.assert_allclose(logits.numpy()[:, :, ::7, ::7], fx["logits_sample"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(vit_oracle.vit_tokens(sd, img, heads).numpy(), fx["tokens"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(float(loss), float(fx["loss"]), rtol=1e-5)
+    names = [str(n) for n in fx["grad_names"]]
+    assert names == list(sd_np.keys())
+    for n, ref_norm in zip(names, fx["grad_norms"]):
+        got = float(grads[n].double().norm())
+        assert abs(got - ref_norm) <= 5e-4 * ref_norm + 1e-7, (n, got, ref_norm)
+    for k in fx.files:
+        if k.startswith("grad."):
+            assert np.abs(grads[k[5:]].numpy() - fx[k]).max() <= 2e-4 * np.abs(fx[k]).max() + 1e-8, k
+
+
+def _model(dim, depth, heads, mlp, sd_np, precision="fp32"):
+    enc = ViT(image_size=224, patch_size=16, num_classes=3, dim=dim, depth=depth, heads=heads, mlp_dim=mlp, channels=6, precision=precision)
+    m = FinetunerSegmentation(encoder=enc, configs=dict(HEAD_CFG))
+    m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd_np.items()})
+    return m
+
+
+def test_state_dict_contract():
+    sd = vit_oracle.make_state(1, 128, 2, 2, 256)
+    m = _model(128, 2, 2, 256, sd)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    enc = ViT(image_size=224, patch_size=16, num_classes=3, dim=768, depth=12, heads=12, mlp_dim=3072, channels=6)
+    assert sum(p.numel() for n, p in enc.named_parameters() if not n.startswith("mlp_head")) == 86365440     # ViT-B/16, 6 channels
+
+
+def test_cpu_without_backend_fails_loudly():
+    m = _model(128, 2, 2, 256, vit_oracle.make_state(1, 128, 2, 2, 256))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 6, 224, 224))
+
+
+@pytest.mark.parametrize("fixture", FIXTURES[:1])
+def test_schedule_matches_oracle(fixture):
+    fx = np.load(GOLD / fixture)
+    dim, depth, heads, mlp, sd_np, img, mask = _case(fx)
+    sd = vit_oracle.to_torch_state(sd_np)
+    loss_o, logits_o, grads_o = vit_oracle.train_step(sd, img, mask, heads)
+    model = _model(dim, depth, heads, mlp, sd_np)
+    model.set_ops(ShadowOps())
+    model.train()
+    out = model(img)
+    loss = ce_dice_torch(out, mask, (1.0, 1.0, 1.0))
+    loss.backward()
+    np.testing.assert_allclose(out.detach().numpy(), logits_o.numpy(), rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(float(loss.detach()), float(loss_o), rtol=1e-4)
+    for name, p in model.named_parameters():
+        go = grads_o[name]
+        err, scale = (p.grad - go).abs().max().item(), go.abs().max().item()
+        assert err <= 2e-3 * scale + 1e-7, (name, err, scale)
+    # encoder-only call returns the tokens without the cls token (vision_transformer.py:152)
+    enc = model.model
+    enc.set_ops(ShadowOps())
+    tok = enc(img)
+    np.testing.assert_allclose(tok.numpy(), vit_oracle.vit_tokens(sd, img, heads).numpy(), rtol=1e-3, atol=1e-4)
