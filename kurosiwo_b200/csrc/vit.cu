@@ -12,6 +12,7 @@
 //   ks_bilinear_up_fwd/_bwd nn.Upsample(size, mode='bilinear') of the K-class token map (model_utilities.py:89-91; the
 //                           1x1 head commutes with the interpolation, so K channels are upsampled instead of `dim`)
 #include "common.cuh"
+#include <mma.h>
 
 namespace ks {
 
@@ -579,6 +580,243 @@ bilinear_up_bwd_kernel(int B, int G, int Tp, int row0, int Cs, int K, int Ho, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Attention on the tensor cores (bf16 storage, fp32 accumulate; warp-level mma through nvcuda::wmma, 16x16x16 tiles).
+// ~4 % of the ViT FLOPs; one CTA per (image, head), each warp owns 16-query (or 16-key) strips:
+//   fwd  : S = Q K^T (13x4 mma per strip), row softmax in shared memory, P -> global (kept for the backward), O = P V
+//   bwd A: dP = dO V^T, dS = P*(dP - rowsum(dP*P)) -> global scratch, dQ = scale * dS K
+//   bwd B: dK = scale * dS^T Q, dV = P^T dO   (A operands read column-major straight from the L2-resident P / dS)
+// ---------------------------------------------------------------------------------------------------------
+namespace wm = nvcuda::wmma;
+constexpr int ATC_WARPS = 7, ATC_KP = ATT_DH + 8;      // 72-element bf16 row pitch: 16-byte aligned rows, conflict-light ldmatrix
+
+__device__ __forceinline__ void atc_load_tile(__nv_bfloat16 *dst, const __nv_bfloat16 *src, long long ld, int rows_valid, int rows_total) {
+  for (int i = threadIdx.x; i < rows_total * (ATT_DH / 8); i += blockDim.x) {
+    const int r = i / (ATT_DH / 8), c = (i % (ATT_DH / 8)) * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows_valid) v = *reinterpret_cast<const uint4 *>(src + (long long)r * ld + c);
+    *reinterpret_cast<uint4 *>(dst + r * ATC_KP + c) = v;
+  }
+}
+
+// write a 16 x 64 fp32 tile staged in shared memory (pitch sp) as bf16 rows to global (row pitch ld); lane pair per row
+__device__ __forceinline__ void atc_store_rows(const float *sw, int sp, __nv_bfloat16 *dst, long long ld, int lane, int row0, int rows_valid,
+                                               float mul) {
+  const int r = lane >> 1, c0 = (lane & 1) * 32;
+  const bool ok = (row0 + r) < rows_valid;
+#pragma unroll
+  for (int c = 0; c < 32; c += 8) {
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = ok ? sw[r * sp + c0 + c + k] * mul : 0.f;
+    st8(dst + (long long)r * ld + c0 + c, f);
+  }
+}
+
+__global__ void __launch_bounds__(ATC_WARPS * 32)
+attention_fwd_tc_kernel(int Tt, int Tp, int heads, const __nv_bfloat16 *__restrict__ qkv, float scale, __nv_bfloat16 *__restrict__ out,
+                        __nv_bfloat16 *__restrict__ probs) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int SP = (Tp > 64 ? Tp : 64) + 4, SPB = Tp + 8, NT = Tp / 16;     // SP >= 64: the strip buffer also stages 16 x 64 outputs
+  __nv_bfloat16 *Ks = reinterpret_cast<__nv_bfloat16 *>(smraw), *Vs = Ks + Tp * ATC_KP;
+  float *Sall = reinterpret_cast<float *>(Vs + Tp * ATC_KP);
+  __nv_bfloat16 *Pall = reinterpret_cast<__nv_bfloat16 *>(Sall + ATC_WARPS * 16 * SP);
+  const int b = blockIdx.y, h = blockIdx.x, inner = heads * ATT_DH;
+  const long long ld = 3LL * inner;
+  const __nv_bfloat16 *base = qkv + (long long)b * Tp * ld + h * ATT_DH;
+  atc_load_tile(Ks, base + inner, ld, Tt, Tp);
+  atc_load_tile(Vs, base + 2 * inner, ld, Tt, Tp);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float *Sw = Sall + w * 16 * SP;
+  __nv_bfloat16 *Pw = Pall + w * 16 * SPB;
+  for (int strip = w; strip < NT; strip += ATC_WARPS) {
+    const int i0 = strip * 16;
+    wm::fragment<wm::matrix_a, 16, 16, 16, __nv_bfloat16, wm::row_major> qa[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wm::load_matrix_sync(qa[k], base + (long long)i0 * ld + k * 16, (unsigned)ld);
+    for (int jt = 0; jt < NT; ++jt) {
+      wm::fragment<wm::accumulator, 16, 16, 16, float> acc;
+      wm::fill_fragment(acc, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        wm::fragment<wm::matrix_b, 16, 16, 16, __nv_bfloat16, wm::col_major> kb;
+        wm::load_matrix_sync(kb, Ks + jt * 16 * ATC_KP + k * 16, ATC_KP);
+        wm::mma_sync(acc, qa[k], kb, acc);
+      }
+      wm::store_matrix_sync(Sw + jt * 16, acc, SP, wm::mem_row_major);
+    }
+    __syncwarp();
+    {   // row softmax: lane pair per row, interleaved columns
+      const int r = lane >> 1, hf = lane & 1;
+      const bool rok = (i0 + r) < Tt;
+      float *sr = Sw + r * SP;
+      float mx = -INFINITY;
+      for (int j = hf; j < Tt; j += 2) mx = fmaxf(mx, sr[j] * scale);
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      float sum = 0.f;
+      for (int j = hf; j < Tt; j += 2) { const float e = expf(sr[j] * scale - mx); sr[j] = e; sum += e; }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      const float inv = 1.f / sum;
+      __nv_bfloat16 *pr = Pw + r * SPB;
+      __nv_bfloat16 *gr = probs + (((long long)b * heads + h) * Tp + i0 + r) * Tp;
+      for (int j = hf; j < Tp; j += 2) {
+        const __nv_bfloat16 pv = __float2bfloat16_rn((rok && j < Tt) ? sr[j] * inv : 0.f);
+        pr[j] = pv; gr[j] = pv;
+      }
+    }
+    __syncwarp();
+    wm::fragment<wm::accumulator, 16, 16, 16, float> oacc[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) wm::fill_fragment(oacc[d], 0.f);
+    for (int jt = 0; jt < NT; ++jt) {
+      wm::fragment<wm::matrix_a, 16, 16, 16, __nv_bfloat16, wm::row_major> pa;
+      wm::load_matrix_sync(pa, Pw + jt * 16, SPB);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        wm::fragment<wm::matrix_b, 16, 16, 16, __nv_bfloat16, wm::row_major> vb;
+        wm::load_matrix_sync(vb, Vs + jt * 16 * ATC_KP + d * 16, ATC_KP);
+        wm::mma_sync(oacc[d], pa, vb, oacc[d]);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) wm::store_matrix_sync(Sw + d * 16, oacc[d], SP, wm::mem_row_major);
+    __syncwarp();
+    atc_store_rows(Sw, SP, out + ((long long)b * Tp + i0) * inner + h * ATT_DH, inner, lane, i0, Tt, 1.f);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(ATC_WARPS * 32)
+attention_bwd_rows_tc_kernel(int Tt, int Tp, int heads, const __nv_bfloat16 *__restrict__ qkv, const __nv_bfloat16 *__restrict__ probs,
+                             const __nv_bfloat16 *__restrict__ dout, float scale, __nv_bfloat16 *__restrict__ dqkv,
+                             __nv_bfloat16 *__restrict__ ds) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int SP = (Tp > 64 ? Tp : 64) + 4, SPB = Tp + 8, NT = Tp / 16;     // SP >= 64: the strip buffer also stages 16 x 64 outputs
+  __nv_bfloat16 *Ks = reinterpret_cast<__nv_bfloat16 *>(smraw), *Vs = Ks + Tp * ATC_KP;
+  float *Sall = reinterpret_cast<float *>(Vs + Tp * ATC_KP);
+  __nv_bfloat16 *Pall = reinterpret_cast<__nv_bfloat16 *>(Sall + ATC_WARPS * 16 * SP);
+  const int b = blockIdx.y, h = blockIdx.x, inner = heads * ATT_DH;
+  const long long ld = 3LL * inner;
+  const __nv_bfloat16 *base = qkv + (long long)b * Tp * ld + h * ATT_DH;
+  atc_load_tile(Ks, base + inner, ld, Tt, Tp);
+  atc_load_tile(Vs, base + 2 * inner, ld, Tt, Tp);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float *Sw = Sall + w * 16 * SP;
+  __nv_bfloat16 *Pw = Pall + w * 16 * SPB;
+  const __nv_bfloat16 *dob = dout + (long long)b * Tp * inner + h * ATT_DH;
+  for (int strip = w; strip < NT; strip += ATC_WARPS) {
+    const int i0 = strip * 16;
+    wm::fragment<wm::matrix_a, 16, 16, 16, __nv_bfloat16, wm::row_major> da[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wm::load_matrix_sync(da[k], dob + (long long)i0 * inner + k * 16, (unsigned)inner);
+    for (int jt = 0; jt < NT; ++jt) {            // dP = dO V^T
+      wm::fragment<wm::accumulator, 16, 16, 16, float> acc;
+      wm::fill_fragment(acc, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        wm::fragment<wm::matrix_b, 16, 16, 16, __nv_bfloat16, wm::col_major> vb;
+        wm::load_matrix_sync(vb, Vs + jt * 16 * ATC_KP + k * 16, ATC_KP);
+        wm::mma_sync(acc, da[k], vb, acc);
+      }
+      wm::store_matrix_sync(Sw + jt * 16, acc, SP, wm::mem_row_major);
+    }
+    __syncwarp();
+    {
+      const int r = lane >> 1, hf = lane & 1;
+      const bool rok = (i0 + r) < Tt;
+      const float *sr = Sw + r * SP;
+      const __nv_bfloat16 *pg = probs + (((long long)b * heads + h) * Tp + i0 + r) * Tp;
+      float dot = 0.f;
+      for (int j = hf; j < Tt; j += 2) dot += sr[j] * __bfloat162float(pg[j]);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      __nv_bfloat16 *pr = Pw + r * SPB;
+      __nv_bfloat16 *gr = ds + (((long long)b * heads + h) * Tp + i0 + r) * Tp;
+      for (int j = hf; j < Tp; j += 2) {
+        const __nv_bfloat16 v = __float2bfloat16_rn((rok && j < Tt) ? __bfloat162float(pg[j]) * (sr[j] - dot) : 0.f);
+        pr[j] = v; gr[j] = v;
+      }
+    }
+    __syncwarp();
+    wm::fragment<wm::accumulator, 16, 16, 16, float> qacc[4];     // dQ = dS K
+#pragma unroll
+    for (int d = 0; d < 4; ++d) wm::fill_fragment(qacc[d], 0.f);
+    for (int jt = 0; jt < NT; ++jt) {
+      wm::fragment<wm::matrix_a, 16, 16, 16, __nv_bfloat16, wm::row_major> sa;
+      wm::load_matrix_sync(sa, Pw + jt * 16, SPB);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        wm::fragment<wm::matrix_b, 16, 16, 16, __nv_bfloat16, wm::row_major> kb;
+        wm::load_matrix_sync(kb, Ks + jt * 16 * ATC_KP + d * 16, ATC_KP);
+        wm::mma_sync(qacc[d], sa, kb, qacc[d]);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) wm::store_matrix_sync(Sw + d * 16, qacc[d], SP, wm::mem_row_major);
+    __syncwarp();
+    atc_store_rows(Sw, SP, dqkv + ((long long)b * Tp + i0) * ld + h * ATT_DH, ld, lane, i0, Tt, scale);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(ATC_WARPS * 32)
+attention_bwd_cols_tc_kernel(int Tt, int Tp, int heads, const __nv_bfloat16 *__restrict__ qkv, const __nv_bfloat16 *__restrict__ probs,
+                             const __nv_bfloat16 *__restrict__ ds, const __nv_bfloat16 *__restrict__ dout, float scale,
+                             __nv_bfloat16 *__restrict__ dqkv) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int NT = Tp / 16, SP = 68;
+  __nv_bfloat16 *Qs = reinterpret_cast<__nv_bfloat16 *>(smraw), *Os = Qs + Tp * ATC_KP;
+  float *Sall = reinterpret_cast<float *>(Os + Tp * ATC_KP);
+  const int b = blockIdx.y, h = blockIdx.x, inner = heads * ATT_DH;
+  const long long ld = 3LL * inner;
+  atc_load_tile(Qs, qkv + (long long)b * Tp * ld + h * ATT_DH, ld, Tt, Tp);
+  atc_load_tile(Os, dout + (long long)b * Tp * inner + h * ATT_DH, (long long)inner, Tt, Tp);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float *Sw = Sall + w * 16 * SP;
+  const __nv_bfloat16 *pb = probs + ((long long)b * heads + h) * Tp * Tp, *sb = ds + ((long long)b * heads + h) * Tp * Tp;
+  for (int strip = w; strip < NT; strip += ATC_WARPS) {
+    const int j0 = strip * 16;
+    wm::fragment<wm::accumulator, 16, 16, 16, float> kacc[4], vacc[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) { wm::fill_fragment(kacc[d], 0.f); wm::fill_fragment(vacc[d], 0.f); }
+    for (int it = 0; it < NT; ++it) {
+      wm::fragment<wm::matrix_a, 16, 16, 16, __nv_bfloat16, wm::col_major> sa, pa;     // (dS^T)[j][i], (P^T)[j][i]
+      wm::load_matrix_sync(sa, sb + (long long)it * 16 * Tp + j0, (unsigned)Tp);
+      wm::load_matrix_sync(pa, pb + (long long)it * 16 * Tp + j0, (unsigned)Tp);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        wm::fragment<wm::matrix_b, 16, 16, 16, __nv_bfloat16, wm::row_major> qb, ob;
+        wm::load_matrix_sync(qb, Qs + it * 16 * ATC_KP + d * 16, ATC_KP);
+        wm::load_matrix_sync(ob, Os + it * 16 * ATC_KP + d * 16, ATC_KP);
+        wm::mma_sync(kacc[d], sa, qb, kacc[d]);
+        wm::mma_sync(vacc[d], pa, ob, vacc[d]);
+      }
+    }
+    __nv_bfloat16 *dk = dqkv + ((long long)b * Tp + j0) * ld + inner + h * ATT_DH;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) wm::store_matrix_sync(Sw + d * 16, kacc[d], SP, wm::mem_row_major);
+    __syncwarp();
+    atc_store_rows(Sw, SP, dk, ld, lane, j0, Tt, scale);
+    __syncwarp();
+#pragma unroll
+    for (int d = 0; d < 4; ++d) wm::store_matrix_sync(Sw + d * 16, vacc[d], SP, wm::mem_row_major);
+    __syncwarp();
+    atc_store_rows(Sw, SP, dk + inner, ld, lane, j0, Tt, 1.f);
+    __syncwarp();
+  }
+}
+
+static inline size_t atc_smem_rows(int Tp) {
+  return (size_t)2 * Tp * ATC_KP * 2 + (size_t)ATC_WARPS * 16 * ((Tp > 64 ? Tp : 64) + 4) * 4 + (size_t)ATC_WARPS * 16 * (Tp + 8) * 2 + 128;
+}
+static inline size_t atc_smem_cols(int Tp) { return (size_t)2 * Tp * ATC_KP * 2 + (size_t)ATC_WARPS * 16 * 68 * 4 + 128; }
+static inline bool atc_ok(int dtype, int T, int Tp, int dh, int heads) {
+  return dtype == KS_BF16 && !g_opt.att_simt && dh == ATT_DH && Tp % 16 == 0 && T <= Tp && atc_smem_rows(Tp) <= 220 * 1024 &&
+         (Tp * 2) % 16 == 0 && ((3LL * heads * dh) % 8) == 0;
+}
+
 static inline int grid_for(long long work, int per_block, int cap_mult = 8) {
   long long g = (work + per_block - 1) / per_block;
   const long long cap = (long long)kNumSMs * cap_mult;
@@ -685,9 +923,17 @@ static int att_cfg(int T, int Tp, int dh, int extra_rows, size_t &smem, int &row
 extern "C" int ks_attention_fwd(int dtype, int B, int T, int Tp, int heads, int dh, const void *qkv, float scale, void *out, void *probs,
                                 void *stream) {
   KS_CHECK_ARG(B > 0 && T > 0 && heads > 0 && qkv && out && probs);
+  if (!al16(qkv) || !al16(out) || !al16(probs)) return KS_EUNSUPPORTED;
+  if (atc_ok(dtype, T, Tp, dh, heads)) {
+    static bool attr = false;
+    if (!attr) { cudaError_t e = cudaFuncSetAttribute(attention_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+                 if (e != cudaSuccess) return (int)e; attr = true; }
+    attention_fwd_tc_kernel<<<dim3((unsigned)heads, (unsigned)B), ATC_WARPS * 32, atc_smem_rows(Tp), (cudaStream_t)stream>>>(
+        T, Tp, heads, (const __nv_bfloat16 *)qkv, scale, (__nv_bfloat16 *)out, (__nv_bfloat16 *)probs);
+    KS_LAUNCH_RET();
+  }
   size_t smem; int rpc, nblk;
   int rc = att_cfg(T, Tp, dh, 1, smem, rpc, nblk, B, heads); if (rc) return rc;
-  if (!al16(qkv) || !al16(out) || !al16(probs)) return KS_EUNSUPPORTED;
   dim3 grid((unsigned)nblk, (unsigned)heads, (unsigned)B);
 #define CALL(Ty) { cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<Ty>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); \
     if (e != cudaSuccess) return (int)e; \
@@ -700,9 +946,27 @@ extern "C" int ks_attention_fwd(int dtype, int B, int T, int Tp, int heads, int 
 extern "C" int ks_attention_bwd(int dtype, int B, int T, int Tp, int heads, int dh, const void *qkv, const void *probs, const void *dout,
                                 float scale, void *dqkv, void *ds_scratch, void *stream) {
   KS_CHECK_ARG(B > 0 && T > 0 && heads > 0 && qkv && probs && dout && dqkv && ds_scratch);
+  if (!al16(qkv) || !al16(dout) || !al16(probs) || !al16(dqkv) || !al16(ds_scratch)) return KS_EUNSUPPORTED;
+  if (atc_ok(dtype, T, Tp, dh, heads)) {
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(attention_bwd_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(attention_bwd_cols_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      if (e != cudaSuccess) return (int)e;
+      attr = true;
+    }
+    const dim3 g((unsigned)heads, (unsigned)B);
+    attention_bwd_rows_tc_kernel<<<g, ATC_WARPS * 32, atc_smem_rows(Tp), (cudaStream_t)stream>>>(
+        T, Tp, heads, (const __nv_bfloat16 *)qkv, (const __nv_bfloat16 *)probs, (const __nv_bfloat16 *)dout, scale, (__nv_bfloat16 *)dqkv,
+        (__nv_bfloat16 *)ds_scratch);
+    attention_bwd_cols_tc_kernel<<<g, ATC_WARPS * 32, atc_smem_cols(Tp), (cudaStream_t)stream>>>(
+        T, Tp, heads, (const __nv_bfloat16 *)qkv, (const __nv_bfloat16 *)probs, (const __nv_bfloat16 *)ds_scratch, (const __nv_bfloat16 *)dout,
+        scale, (__nv_bfloat16 *)dqkv);
+    KS_LAUNCH_RET();
+  }
   size_t smem; int rpc, nblk;
   int rc = att_cfg(T, Tp, dh, 2, smem, rpc, nblk, B, heads); if (rc) return rc;
-  if (!al16(qkv) || !al16(dout) || !al16(probs) || !al16(dqkv) || !al16(ds_scratch)) return KS_EUNSUPPORTED;
   dim3 grid((unsigned)nblk, (unsigned)heads, (unsigned)B);
 #define CALL(Ty) { cudaError_t e = cudaFuncSetAttribute(attention_bwd_rows_kernel<Ty>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); \
     if (e != cudaSuccess) return (int)e; \
