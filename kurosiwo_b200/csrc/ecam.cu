@@ -436,6 +436,345 @@ ecam_bwd_apply_kernel(ViewList dxs, int J, int Cb, int H, int W, const float *__
   }
 }
 
+
+// =====================================================================================================================
+// Bulk-staged variants (default when every view is pixel-dense: sw == Cb, sh == W*Cb, the planar slot layout).
+// The register-resident formulations above run at 2 CTAs x 8 warps per SM with 4 x 16-byte loads in flight per thread:
+// ~32 KB per SM, i.e. latency-bound at ~1.1-1.6 TB/s (ncu: 80 % of the samples in long-scoreboard stalls).  Here one thread per CTA
+// issues cp.async.bulk copies of whole pixel chunks (P pixels x Cb channels of all J views = up to 32 KB) into a 3-stage shared-memory
+// ring guarded by mbarriers, so ~64-96 KB per CTA are in flight regardless of register pressure; the arithmetic is unchanged.
+// =====================================================================================================================
+constexpr int BULK_STAGES = 3;
+
+__device__ __forceinline__ uint32_t bk_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bk_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bk_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bk_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bk_copy(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Stage layout: [J][P][Cb] elements of T, then (optionally) [K][P] floats of dlogits.
+struct BulkPipe {
+  uint32_t bars;        // smem address of BULK_STAGES mbarriers
+  uint32_t stage0;      // smem address of stage 0
+  uint32_t stage_bytes;
+  __device__ __forceinline__ void init(unsigned char *barmem, unsigned char *stagemem, uint32_t sb) {
+    bars = bk_smem_u32(barmem); stage0 = bk_smem_u32(stagemem); stage_bytes = sb;
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < BULK_STAGES; ++i) bk_mbar_init(bars + 8u * i, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ void bulk_issue(const BulkPipe &bp, int stage, const ViewList &xs, int J, int Cb, int n, int P, int p0, int npx,
+                                           const float *dl, int K, long long HW) {
+  // one thread: expect the bytes, then one copy per view (+ one per logit plane)
+  const uint32_t bar = bp.bars + 8u * stage, dst0 = bp.stage0 + (uint32_t)stage * bp.stage_bytes;
+  const uint32_t vb = (uint32_t)npx * Cb * sizeof(T);
+  const uint32_t lb = dl ? (uint32_t)npx * 4u : 0u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  bk_expect_tx(bar, vb * J + lb * K);
+  for (int j = 0; j < J; ++j) {
+    const View &v = xs.v[j];
+    bk_copy(dst0 + (uint32_t)j * P * Cb * sizeof(T), reinterpret_cast<const T *>(v.ptr) + ((long long)n * v.sn + (long long)p0 * Cb), vb, bar);
+  }
+  if (dl)
+    for (int k = 0; k < K; ++k)
+      bk_copy(dst0 + (uint32_t)J * P * Cb * sizeof(T) + (uint32_t)k * P * 4u, dl + ((long long)n * K + k) * HW + p0, lb, bar);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+ecam_pool_bulk_kernel(ViewList xs, int J, int Cb, int HW, int P, float *pooled, unsigned int *maxkey) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int CC = J * Cb, CT = (J + 1) * Cb;
+  const uint32_t stage_bytes = (uint32_t)J * P * Cb * sizeof(T);
+  unsigned char *stages = smraw;
+  unsigned char *barmem = smraw + BULK_STAGES * stage_bytes;
+  unsigned int *smax = reinterpret_cast<unsigned int *>(barmem + 64);
+  float *ssum = reinterpret_cast<float *>(smax + CT);
+  BulkPipe bp; bp.init(barmem, stages, stage_bytes);
+  for (int i = threadIdx.x; i < CT; i += blockDim.x) { smax[i] = 0u; ssum[i] = 0.f; }
+  __syncthreads();
+  const int n = blockIdx.y, CVb = Cb / 8, tx = threadIdx.x % CVb;
+  const int nchunks = (HW + P - 1) / P;
+  float sum[kMaxJ][8], best[kMaxJ + 1][8];
+#pragma unroll
+  for (int j = 0; j <= kMaxJ; ++j)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { if (j < kMaxJ) sum[j][k] = 0.f; best[j][k] = -INFINITY; }
+  if (threadIdx.x == 0)
+    for (int s = 0; s < BULK_STAGES - 1; ++s) {
+      const int c = blockIdx.x + s * gridDim.x;
+      if (c < nchunks) bulk_issue<T>(bp, s, xs, J, Cb, n, P, c * P, min(P, HW - c * P), nullptr, 0, HW);
+    }
+  int it = 0;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+    const int s = it % BULK_STAGES;
+    if (threadIdx.x == 0) {
+      const int cn = c + (BULK_STAGES - 1) * gridDim.x;
+      if (cn < nchunks) bulk_issue<T>(bp, (it + BULK_STAGES - 1) % BULK_STAGES, xs, J, Cb, n, P, cn * P, min(P, HW - cn * P), nullptr, 0, HW);
+    }
+    bk_wait(bp.bars + 8u * s, (uint32_t)((it / BULK_STAGES) & 1));
+    const T *st = reinterpret_cast<const T *>(stages + (size_t)s * stage_bytes);
+    const int npx = min(P, HW - c * P);
+    for (int i = threadIdx.x; i < npx * CVb; i += blockDim.x) {
+      const int px = i / CVb;
+      float f[kMaxJ][8], itv[8];
+#pragma unroll
+      for (int j = 0; j < kMaxJ; ++j)
+        if (j < J) ld8(st + ((size_t)j * P + px) * Cb + tx * 8, f[j]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) itv[k] = 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxJ; ++j)
+        if (j < J) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { sum[j][k] += f[j][k]; best[j][k] = fmaxf(best[j][k], f[j][k]); itv[k] += f[j][k]; }
+        }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) best[kMaxJ][k] = fmaxf(best[kMaxJ][k], itv[k]);
+    }
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j <= kMaxJ; ++j) {
+    if (j < J || j == kMaxJ) {
+      const int jj = (j == kMaxJ) ? J : j;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float mv = best[j][k];
+        float sv = (j < kMaxJ) ? sum[j][k] : 0.f;
+        for (int o = CVb; o < 32; o <<= 1) {
+          mv = fmaxf(mv, __shfl_xor_sync(0xffffffffu, mv, o));
+          sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        }
+        if (lane < CVb) {
+          const int c = jj * Cb + tx * 8 + k;
+          atomicMax(&smax[c], fkey(mv));
+          if (j < kMaxJ) { atomicAdd(&ssum[c], sv); atomicAdd(&ssum[CC + tx * 8 + k], sv); }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CT; i += blockDim.x) {
+    atomicAdd(pooled + ((size_t)n * 2 + 0) * CT + i, ssum[i]);
+    atomicMax(maxkey + (size_t)n * CT + i, smax[i]);
+  }
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(256, 2)
+ecam_final_bulk_kernel(ViewList xs, int J, int Cb, int HW, int P, const float *__restrict__ gates, const float *__restrict__ wf,
+                       const float *__restrict__ bf, const float *__restrict__ pooled, int *argmax, float *logits) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int n = blockIdx.y, CC = J * Cb, CT = (J + 1) * Cb;
+  const uint32_t stage_bytes = (uint32_t)J * P * Cb * sizeof(T);
+  unsigned char *stages = smraw;
+  unsigned char *barmem = smraw + BULK_STAGES * stage_bytes;
+  float *weff = reinterpret_cast<float *>(barmem + 64);   // [J][K][Cb]
+  float *cst = weff + K * CC;                              // [K] (+1 pad)
+  float *smx = cst + 4;                                    // [CT]
+  float *slog = smx + CT;                                  // [K][P] logits of the chunk (coalesced plane stores)
+  BulkPipe bp; bp.init(barmem, stages, stage_bytes);
+  const float *g = gates + (size_t)n * CT;
+  for (int i = threadIdx.x; i < K * CC; i += blockDim.x) {
+    const int j = i / (K * Cb), k = (i / Cb) % K, cb = i % Cb;
+    weff[i] = wf[k * CC + j * Cb + cb] * g[j * Cb + cb];
+  }
+  for (int i = threadIdx.x; i < CT; i += blockDim.x) smx[i] = pooled ? pooled[((size_t)n * 2 + 1) * CT + i] : 0.f;
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float s = bf[threadIdx.x];
+    for (int j = 0; j < J; ++j)
+      for (int cb = 0; cb < Cb; ++cb) s += weff[(j * K + threadIdx.x) * Cb + cb] * g[CC + cb];
+    cst[threadIdx.x] = s;
+  }
+  __syncthreads();
+  const int CVb = Cb / 8, tx = threadIdx.x % CVb;
+  int *am = argmax ? argmax + (size_t)n * CT : nullptr;
+  float mx[kMaxJ + 1][8];
+#pragma unroll
+  for (int j = 0; j <= kMaxJ; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mx[j][i] = (j < J) ? smx[j * Cb + tx * 8 + i] : (j == kMaxJ ? smx[CC + tx * 8 + i] : 0.f);
+  const int nchunks = (HW + P - 1) / P;
+  if (threadIdx.x == 0)
+    for (int s = 0; s < BULK_STAGES - 1; ++s) {
+      const int c = blockIdx.x + s * gridDim.x;
+      if (c < nchunks) bulk_issue<T>(bp, s, xs, J, Cb, n, P, c * P, min(P, HW - c * P), nullptr, 0, HW);
+    }
+  int it = 0;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+    const int s = it % BULK_STAGES;
+    if (threadIdx.x == 0) {
+      const int cn = c + (BULK_STAGES - 1) * gridDim.x;
+      if (cn < nchunks) bulk_issue<T>(bp, (it + BULK_STAGES - 1) % BULK_STAGES, xs, J, Cb, n, P, cn * P, min(P, HW - cn * P), nullptr, 0, HW);
+    }
+    bk_wait(bp.bars + 8u * s, (uint32_t)((it / BULK_STAGES) & 1));
+    const T *st = reinterpret_cast<const T *>(stages + (size_t)s * stage_bytes);
+    const int p0 = c * P, npx = min(P, HW - p0);
+    const int nitems = ((npx * CVb + 31) / 32) * 32;           // whole warps run the shuffles
+    for (int i = threadIdx.x; i < nitems; i += blockDim.x) {
+      const int px = i / CVb;
+      const bool ok = px < npx;
+      const int p = p0 + px;
+      float acc[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] = 0.f;
+      if (ok) {
+        float f[kMaxJ][8], itv[8];
+#pragma unroll
+        for (int j = 0; j < kMaxJ; ++j)
+          if (j < J) ld8(st + ((size_t)j * P + px) * Cb + tx * 8, f[j]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) itv[q] = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxJ; ++j)
+          if (j < J) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+              const float4 w0 = *reinterpret_cast<const float4 *>(weff + (j * K + k) * Cb + tx * 8);
+              const float4 w1 = *reinterpret_cast<const float4 *>(weff + (j * K + k) * Cb + tx * 8 + 4);
+              acc[k] = fmaf(f[j][0], w0.x, acc[k]); acc[k] = fmaf(f[j][1], w0.y, acc[k]);
+              acc[k] = fmaf(f[j][2], w0.z, acc[k]); acc[k] = fmaf(f[j][3], w0.w, acc[k]);
+              acc[k] = fmaf(f[j][4], w1.x, acc[k]); acc[k] = fmaf(f[j][5], w1.y, acc[k]);
+              acc[k] = fmaf(f[j][6], w1.z, acc[k]); acc[k] = fmaf(f[j][7], w1.w, acc[k]);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              itv[q] += f[j][q];
+              if (am && f[j][q] == mx[j][q]) atomicMin(am + j * Cb + tx * 8 + q, p);
+            }
+          }
+        if (am) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (itv[q] == mx[kMaxJ][q]) atomicMin(am + CC + tx * 8 + q, p);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        for (int o = 1; o < CVb; o <<= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+      if (ok && tx == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) slog[k * P + px] = acc[k] + cst[k];
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * npx; i += blockDim.x) {
+      const int k = i / npx, px = i % npx;
+      logits[((size_t)n * K + k) * HW + p0 + px] = slog[k * P + px];
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(256, 2)
+ecam_bwd_reduce_bulk_kernel(ViewList xs, int J, int Cb, int HW, int P, const float *__restrict__ dlogits, double *red) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int n = blockIdx.y, CC = J * Cb, RT = K * CC + K;
+  const uint32_t stage_bytes = (uint32_t)J * P * Cb * sizeof(T) + (uint32_t)K * P * 4u;
+  unsigned char *stages = smraw;
+  unsigned char *barmem = smraw + BULK_STAGES * stage_bytes;
+  float *sacc = reinterpret_cast<float *>(barmem + 64);
+  BulkPipe bp; bp.init(barmem, stages, stage_bytes);
+  for (int i = threadIdx.x; i < RT; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  // warp -> view j; lane -> (pixel lane, 8-channel vector)
+  const int CVb = Cb / 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwj = (blockDim.x >> 5) / J;                      // warps per view
+  const int j = warp % J, tx = lane % CVb;
+  const int cb0 = tx * 8, c0 = j * Cb + cb0;
+  float B[K][8], D[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    D[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) B[k][i] = 0.f;
+  }
+  const int nchunks = (HW + P - 1) / P;
+  if (threadIdx.x == 0)
+    for (int s = 0; s < BULK_STAGES - 1; ++s) {
+      const int c = blockIdx.x + s * gridDim.x;
+      if (c < nchunks) bulk_issue<T>(bp, s, xs, J, Cb, n, P, c * P, min(P, HW - c * P), dlogits, K, HW);
+    }
+  int it = 0;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+    const int s = it % BULK_STAGES;
+    if (threadIdx.x == 0) {
+      const int cn = c + (BULK_STAGES - 1) * gridDim.x;
+      if (cn < nchunks) bulk_issue<T>(bp, (it + BULK_STAGES - 1) % BULK_STAGES, xs, J, Cb, n, P, cn * P, min(P, HW - cn * P), dlogits, K, HW);
+    }
+    bk_wait(bp.bars + 8u * s, (uint32_t)((it / BULK_STAGES) & 1));
+    const T *st = reinterpret_cast<const T *>(stages + (size_t)s * stage_bytes) + (size_t)j * P * Cb;
+    const float *sdl = reinterpret_cast<const float *>(stages + (size_t)s * stage_bytes + (size_t)J * P * Cb * sizeof(T));
+    const int npx = min(P, HW - c * P);
+    for (int i = (warp / J) * 32 + lane; i < npx * CVb; i += nwj * 32) {
+      const int px = i / CVb;
+      float f[8], dl[K];
+      ld8(st + (size_t)px * Cb + cb0, f);
+#pragma unroll
+      for (int k = 0; k < K; ++k) dl[k] = sdl[k * P + px];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        D[k] += dl[k];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) B[k][q] = fmaf(dl[k], f[q], B[k][q]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = B[k][i];
+      for (int o = CVb; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane < CVb) atomicAdd(&sacc[k * CC + c0 + i], v);
+    }
+    float d = D[k];
+    for (int o = CVb; o < 32; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (lane == 0 && j == 0) atomicAdd(&sacc[K * CC + k], d);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < RT; i += blockDim.x) atomicAdd(red + (size_t)n * RT + i, (double)sacc[i]);
+}
+
+// host-side: can the bulk path run?  (pixel-dense views, 16-byte multiples everywhere)
+static bool bulk_views_ok(const ks_view_t *xs, int J, int Cb, int W, long long HW, int esize) {
+  if (g_opt.debug & 64) return false;
+  if (HW % 4) return false;
+  for (int j = 0; j < J; ++j)
+    if (xs[j].sw != Cb || xs[j].sh != (long long)W * Cb || (xs[j].sn * esize) % 16) return false;
+  return true;
+}
+static int bulk_chunk_px(int J, int Cb, int esize) {
+  int P = 128;
+  while (P > 16 && (size_t)J * P * Cb * esize > 32 * 1024) P >>= 1;
+  return P;
+}
+
 static int check_views(const ks_view_t *xs, int J, int &Cb, int esize) {
   if (!xs || J < 1 || J > kMaxJ) return KS_EINVAL;
   Cb = xs[0].C;
@@ -461,6 +800,22 @@ extern "C" int ks_ecam_pool(int dtype, int N, int H, int W, const ks_view_t *xs,
   unsigned int *maxkey = reinterpret_cast<unsigned int *>(scratch);     // first 4 bytes of each 8-byte scratch slot pair
   cudaError_t e = cudaMemsetAsync(pooled, 0, sizeof(float) * (size_t)N * 2 * CT, st); if (e) return (int)e;
   e = cudaMemsetAsync(maxkey, 0, sizeof(unsigned int) * (size_t)N * CT, st); if (e) return (int)e;
+  const int es = dtype == KS_F32 ? 4 : 2;
+  if (bulk_views_ok(xs, J, Cb, W, (long long)H * W, es) && (dtype == KS_F32 || dtype == KS_BF16)) {
+    const int P = bulk_chunk_px(J, Cb, es);
+    const int nch = (H * W + P - 1) / P;
+    int gx = (kNumSMs * 2) / N; if (gx > nch) gx = nch; if (gx < 1) gx = 1;
+    const size_t smem = (size_t)BULK_STAGES * J * P * Cb * es + 64 + (size_t)CT * 8;
+    if (dtype == KS_F32) {
+      static bool a = false; if (!a) { cudaFuncSetAttribute(ecam_pool_bulk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); a = true; }
+      ecam_pool_bulk_kernel<float><<<dim3(gx, N), 256, smem, st>>>(vl, J, Cb, H * W, P, pooled, maxkey);
+    } else {
+      static bool a = false; if (!a) { cudaFuncSetAttribute(ecam_pool_bulk_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); a = true; }
+      ecam_pool_bulk_kernel<__nv_bfloat16><<<dim3(gx, N), 256, smem, st>>>(vl, J, Cb, H * W, P, pooled, maxkey);
+    }
+    ecam_pool_finalize_kernel<<<(N * CT + 255) / 256, 256, 0, st>>>(N, CT, H * W, pooled, maxkey, argmax);
+    KS_LAUNCH_RET();
+  }
   const int rows = 256 / (Cb / 8);
   int chunks = (H * W + rows * 8 - 1) / (rows * 8); if (chunks < 1) chunks = 1;
   const int cap = (kNumSMs * 6 + N - 1) / N; if (chunks > cap) chunks = cap;
@@ -490,10 +845,25 @@ extern "C" int ks_ecam_final(int dtype, int N, int H, int W, const ks_view_t *xs
   int Cb; int rc = check_views(xs, J, Cb, dtype == KS_F32 ? 4 : 2); if (rc) return rc;
   ViewList vl; rc = make_view_list(xs, J, vl); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  const int CC = J * Cb, CT = (J + 1) * Cb;
+  const int es = dtype == KS_F32 ? 4 : 2;
+  if (bulk_views_ok(xs, J, Cb, W, (long long)H * W, es) && (dtype == KS_F32 || dtype == KS_BF16)) {
+    const int P = bulk_chunk_px(J, Cb, es);
+    const int nch = (H * W + P - 1) / P;
+    int gx = (kNumSMs * 2) / N; if (gx > nch) gx = nch; if (gx < 1) gx = 1;
+    const size_t smem = (size_t)BULK_STAGES * J * P * Cb * es + 64 + sizeof(float) * (size_t)(K * CC + 4 + CT + K * P);
+    if (dtype == KS_F32) {
+      static bool a = false; if (!a) { cudaFuncSetAttribute(ecam_final_bulk_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); a = true; }
+      ecam_final_bulk_kernel<float, 3><<<dim3(gx, N), 256, smem, st>>>(vl, J, Cb, H * W, P, gates, wf, bf, pooled, argmax, logits);
+    } else {
+      static bool a = false; if (!a) { cudaFuncSetAttribute(ecam_final_bulk_kernel<__nv_bfloat16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); a = true; }
+      ecam_final_bulk_kernel<__nv_bfloat16, 3><<<dim3(gx, N), 256, smem, st>>>(vl, J, Cb, H * W, P, gates, wf, bf, pooled, argmax, logits);
+    }
+    KS_LAUNCH_RET();
+  }
   const int rows_f = 256 / (Cb / 8);
   int chunks = (H * W + rows_f * 8 - 1) / (rows_f * 8); if (chunks < 1) chunks = 1;
   const int cap = (kNumSMs * 8 + N - 1) / N; if (chunks > cap) chunks = cap;
-  const int CC = J * Cb, CT = (J + 1) * Cb;
   const size_t smem = sizeof(float) * (size_t)(K * CC + 4 + CT);
   if (dtype == KS_F32) ecam_final_kernel<float, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, gates, wf, bf, pooled, argmax, logits);
   else if (dtype == KS_BF16) ecam_final_kernel<__nv_bfloat16, 3><<<dim3(chunks, N), 256, smem, st>>>(vl, J, Cb, H, W, gates, wf, bf, pooled, argmax, logits);
@@ -510,6 +880,21 @@ extern "C" int ks_ecam_bwd_reduce(int dtype, int N, int H, int W, const ks_view_
   cudaStream_t st = (cudaStream_t)stream;
   const int RT = K * J * Cb + K;
   cudaError_t e = cudaMemsetAsync(red, 0, sizeof(double) * (size_t)N * RT, st); if (e) return (int)e;
+  const int es = dtype == KS_F32 ? 4 : 2;
+  if (bulk_views_ok(xs, J, Cb, W, (long long)H * W, es) && (dtype == KS_F32 || dtype == KS_BF16) && 8 % J == 0 && (((uintptr_t)dlogits) % 16) == 0) {
+    const int P = bulk_chunk_px(J, Cb, es);
+    const int nch = (H * W + P - 1) / P;
+    int gx = (kNumSMs * 2) / N; if (gx > nch) gx = nch; if (gx < 1) gx = 1;
+    const size_t smem = (size_t)BULK_STAGES * ((size_t)J * P * Cb * es + (size_t)K * P * 4) + 64 + sizeof(float) * (size_t)RT;
+    if (dtype == KS_F32) {
+      static bool a = false; if (!a) { cudaFuncSetAttribute(ecam_bwd_reduce_bulk_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); a = true; }
+      ecam_bwd_reduce_bulk_kernel<float, 3><<<dim3(gx, N), 256, smem, st>>>(vl, J, Cb, H * W, P, dlogits, red);
+    } else {
+      static bool a = false; if (!a) { cudaFuncSetAttribute(ecam_bwd_reduce_bulk_kernel<__nv_bfloat16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); a = true; }
+      ecam_bwd_reduce_bulk_kernel<__nv_bfloat16, 3><<<dim3(gx, N), 256, smem, st>>>(vl, J, Cb, H * W, P, dlogits, red);
+    }
+    KS_LAUNCH_RET();
+  }
   const int nthr = 32 * J * (8 / J), rows = (8 / J) * (32 / (Cb / 8));
   int chunks = (H * W + rows * 16 - 1) / (rows * 16); if (chunks < 1) chunks = 1;
   const int cap = (kNumSMs * 8 + N - 1) / N; if (chunks > cap) chunks = cap;

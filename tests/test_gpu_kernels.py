@@ -217,15 +217,22 @@ def test_bn_forward_backward(ops, sh, dtype, C, ctot, c0):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_ecam_forward_backward(ops, sh, dtype):
+@pytest.mark.parametrize("layout,N,H,W", [("sliced", 3, 12, 20), ("planar", 3, 12, 20), ("planar", 5, 52, 36)])
+def test_ecam_forward_backward(ops, sh, dtype, layout, N, H, W):
+    """sliced = channel slices of one concat buffer (register-resident kernels); planar = one dense tensor per view
+    (the engine's default slot layout -> cp.async.bulk-staged kernels; 52x36 spans many 128-pixel chunks + a ragged tail)."""
     g = _gen(5)
-    N, H, W, Cb, J, K = 3, 12, 20, 32, 4, 3
+    Cb, J, K = 32, 4, 3
     hid, hid1 = 8, 8
     CC, CT = J * Cb, (J + 1) * Cb
-    _, full = rand_view(N, H, W, 6 * Cb, dtype, DEV, gen=g)
-    xs = [full.ch((2 + j) * Cb, Cb) for j in range(J)]
-    cfull = mirror(full)
-    cxs = [cfull.ch((2 + j) * Cb, Cb) for j in range(J)]
+    if layout == "sliced":
+        _, full = rand_view(N, H, W, 6 * Cb, dtype, DEV, gen=g)
+        xs = [full.ch((2 + j) * Cb, Cb) for j in range(J)]
+        cfull = mirror(full)
+        cxs = [cfull.ch((2 + j) * Cb, Cb) for j in range(J)]
+    else:
+        xs = [rand_view(N, H, W, Cb, dtype, DEV, gen=g)[0] for _ in range(J)]
+        cxs = [mirror(v) for v in xs]
     wts = [torch.randn(n, generator=g) * s for n, s in ((hid * CC, 0.2), (CC * hid, 0.3), (hid1 * Cb, 0.3), (Cb * hid1, 0.3), (K * CC, 0.2), (K, 0.1))]
     dw = [w.to(DEV) for w in wts]
     mk = lambda n, dt=torch.float32: (torch.zeros(n, dtype=dt, device=DEV), torch.zeros(n, dtype=dt))
