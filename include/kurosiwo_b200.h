@@ -280,6 +280,20 @@ int ks_ce_dice_fwd_bwd(const float *logits, const int64_t *labels, int N, int C,
                        float *loss_out, float *dlogits, uint8_t *pred,
                        void *workspace, void *stream);
 
+/* Same kernel with the Dice term weighted by dice_weight: loss = dice_weight*Dice + CE.  dice_weight = 0 is exactly
+ * nn.CrossEntropyLoss(weight=class_weights, ignore_index) - the reference's DEFAULT criterion (configs/train/train_config.json:11,
+ * utilities/utilities.py:308-321); loss_out[1] still reports the Dice value. */
+int ks_ce_dice_fwd_bwd_ex(const float *logits, const int64_t *labels, int N, int C, int64_t HW,
+                          const float *class_weights, int ignore_index, float grad_scale, float dice_weight,
+                          float *loss_out, float *dlogits, uint8_t *pred,
+                          void *workspace, void *stream);
+
+/* In-loop metrics: mat[target][pred] += 1 (int64 [4][4], row-major) over the n pixels whose target != ignore_index; replaces
+ * the 5 torchmetrics objects of utilities/utilities.py:228-265 updated at change_detection_trainer.py:184-199 (accuracy, F1,
+ * precision, recall, IoU per class all derive from the confusion matrix).  pred: the uint8 argmax map of ks_ce_dice_fwd_bwd. */
+int ks_confusion_update(const uint8_t *pred, const int64_t *labels, int64_t n, int num_classes_with_ignore, int ignore_index,
+                        int64_t *mat, void *stream);
+
 /* ---- optimizer (torch.optim.Adam, change_detection_trainer.py:52-54) ---- */
 /* step_ptr: device int32 counter, incremented by the kernel (graph-capturable). */
 int ks_adam_step(float *p, const float *g, float *m, float *v, int64_t n,

@@ -15,7 +15,7 @@ import torch.nn as nn
 
 class _CeDiceFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, preds, lbl, weights, ignore_index, state):
+    def forward(ctx, preds, lbl, weights, ignore_index, state, dice_weight=1.0):
         from .lib import default_ops
         ops = state.get("ops") or default_ops()
         logits = preds.detach()
@@ -32,7 +32,7 @@ class _CeDiceFunction(torch.autograd.Function):
             state["dlogits"] = torch.empty_like(logits)
             state["pred"] = torch.empty((N,) + tuple(logits.shape[2:]), dtype=torch.uint8, device=logits.device)
         ops.ce_dice(logits, lbl.contiguous(), weights, ignore_index, 1.0, state["loss3"],
-                    state["dlogits"] if need_grad else None, state["pred"], state["ws"])
+                    state["dlogits"] if need_grad else None, state["pred"], state["ws"], dice_weight)
         ctx.dlogits = state["dlogits"] if need_grad else None
         ctx.in_dtype = preds.dtype
         return state["loss3"][0].clone()
@@ -42,7 +42,7 @@ class _CeDiceFunction(torch.autograd.Function):
         g = ctx.dlogits * gout
         if g.dtype != ctx.in_dtype:
             g = g.to(ctx.in_dtype)
-        return g, None, None, None, None
+        return g, None, None, None, None, None
 
 
 class DiceLoss(nn.Module):
@@ -56,6 +56,8 @@ class DiceLoss(nn.Module):
 
 
 class BCEandDiceLoss(nn.Module):
+    dice_weight = 1.0
+
     def __init__(self, weights=None, ignore_index=None, use_softmax=False):
         super().__init__()
         if not use_softmax:
@@ -94,9 +96,19 @@ class BCEandDiceLoss(nn.Module):
             raise RuntimeError("kurosiwo_b200.BCEandDiceLoss runs on a CUDA device only (no CPU fallback)")
         if self.weight.device != preds.device:
             self.weight = self.weight.to(preds.device)
-        return _CeDiceFunction.apply(preds, lbl, self.weight, self.ignore_index, self._state)
+        return _CeDiceFunction.apply(preds, lbl, self.weight, self.ignore_index, self._state, float(self.dice_weight))
 
     def __getstate__(self):
         d = dict(self.__dict__)
         d["_state"] = {}
         return d
+
+
+class FusedCrossEntropyLoss(BCEandDiceLoss):
+    """nn.CrossEntropyLoss(weight=w, ignore_index=i) - the reference's default criterion (utilities/utilities.py:308-321) - on the
+    same fused kernel with the Dice term switched off (dice_weight = 0): value, gradient and the argmax map in one pass."""
+    dice_weight = 0.0
+
+    def __init__(self, weight=None, ignore_index=-100, num_classes=3):
+        w = torch.ones(num_classes) if weight is None else weight
+        super().__init__(weights=w, ignore_index=ignore_index, use_softmax=True)

@@ -54,8 +54,9 @@ class FusedStepper:
     def __init__(self, model, configs, model_configs, process_group=None):
         if not isinstance(model, (SNUNet_ECAM, _SiamUnet)):
             raise TypeError("the fused step is implemented for kurosiwo_b200's SNUNet_ECAM, SiamUnet_conc and SiamUnet_diff")
-        if configs.get("loss_function", "ce+dice") != "ce+dice":
-            raise NotImplementedError("the fused step computes CE+Dice (utilities/bce_and_dice.py); set loss_function='ce+dice'")
+        if configs.get("loss_function", "ce+dice") not in ("ce+dice", "cross_entropy"):
+            raise NotImplementedError("the fused step computes CE+Dice (utilities/bce_and_dice.py) or plain cross-entropy "
+                                      "(utilities/utilities.py:308-321); other losses are outside the B200 hot path")
         opt = model_configs.get("optimizer", "adam")
         if opt != "adam":
             raise NotImplementedError(f"fused optimizer '{opt}' (only 'adam': change_detection_trainer.py:52-54)")
@@ -68,7 +69,8 @@ class FusedStepper:
         if eng is not self.engine:
             eng.init_training(class_weights=self.configs.get("class_weights", [1.0, 1.0, 1.0]), ignore_index=3, lr=self.lr,
                               betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,      # reference Adam gets only lr (:52-54)
-                              process_group=self.pg)
+                              process_group=self.pg,
+                              dice_weight=0.0 if self.configs.get("loss_function") == "cross_entropy" else 1.0)
             self.engine = eng
         return eng
 

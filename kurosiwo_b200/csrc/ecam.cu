@@ -642,6 +642,7 @@ ecam_final_bulk_kernel(ViewList xs, int J, int Cb, int HW, int P, const float *_
       for (int k = 0; k < K; ++k) acc[k] = 0.f;
       if (ok) {
         float f[kMaxJ][8], itv[8];
+        bool hit = false;
 #pragma unroll
         for (int j = 0; j < kMaxJ; ++j)
           if (j < J) ld8(st + ((size_t)j * P + px) * Cb + tx * 8, f[j]);
@@ -660,12 +661,18 @@ ecam_final_bulk_kernel(ViewList xs, int J, int Cb, int HW, int P, const float *_
               acc[k] = fmaf(f[j][6], w1.z, acc[k]); acc[k] = fmaf(f[j][7], w1.w, acc[k]);
             }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              itv[q] += f[j][q];
-              if (am && f[j][q] == mx[j][q]) atomicMin(am + j * Cb + tx * 8 + q, p);
-            }
+            for (int q = 0; q < 8; ++q) { itv[q] += f[j][q]; hit |= (f[j][q] == mx[j][q]); }
           }
-        if (am) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) hit |= (itv[q] == mx[kMaxJ][q]);
+        if (am && hit) {      // rare: some element equals its channel's pooled maximum -> record the FIRST such pixel
+#pragma unroll
+          for (int j = 0; j < kMaxJ; ++j)
+            if (j < J) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (f[j][q] == mx[j][q]) atomicMin(am + j * Cb + tx * 8 + q, p);
+            }
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             if (itv[q] == mx[kMaxJ][q]) atomicMin(am + CC + tx * 8 + q, p);

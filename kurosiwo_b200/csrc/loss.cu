@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256)
 ce_dice_kernel(const float *__restrict__ logits, const long long *__restrict__ labels,
                int N, long long HW, const float *__restrict__ cw, int ignore_index,
                float grad_scale, float *__restrict__ loss_out, float *__restrict__ dlogits,
-               unsigned char *__restrict__ pred, double *acc, double *ce, unsigned int *counter) {
+               unsigned char *__restrict__ pred, double *acc, double *ce, unsigned int *counter, float dice_weight) {
   const int n = blockIdx.y;
   const long long chunk = (((HW + gridDim.x - 1) / gridDim.x) + VEC - 1) / VEC * VEC;
   const long long p0 = (long long)blockIdx.x * chunk;
@@ -145,14 +145,14 @@ ce_dice_kernel(const float *__restrict__ logits, const long long *__restrict__ l
     }
     dice /= (double)N;
     const double cel = __ldcg(ce) / __ldcg(ce + 1);  // NaN when every pixel is ignored (as torch)
-    loss_out[0] = (float)(dice + cel); loss_out[1] = (float)dice; loss_out[2] = (float)cel;
+    loss_out[0] = (float)((double)dice_weight * dice + cel); loss_out[1] = (float)dice; loss_out[2] = (float)cel;
   }
   if (dlogits == nullptr) return;
 
   // ---------------- phase 2: gradient ----------------
   const double In = __ldcg(acc + 2 * n), Sn = __ldcg(acc + 2 * n + 1) + 1e-6;
-  const float a_n = (float)(-2.0 / ((double)N * Sn)) * grad_scale;      // dL/dp = a_n*t + b_n
-  const float b_n = (float)(2.0 * In / ((double)N * Sn * Sn)) * grad_scale;
+  const float a_n = (float)(-2.0 / ((double)N * Sn)) * grad_scale * dice_weight;      // dL/dp = a_n*t + b_n
+  const float b_n = (float)(2.0 * In / ((double)N * Sn * Sn)) * grad_scale * dice_weight;
   const float inv_den = (float)(1.0 / __ldcg(ce + 1)) * grad_scale;
   float *gb = dlogits + (long long)n * C * HW;
   for (long long px = p0 + (long long)threadIdx.x * VEC; px < p1; px += (long long)blockDim.x * VEC) {
@@ -215,7 +215,7 @@ ce_dice_kernel(const float *__restrict__ logits, const long long *__restrict__ l
 template <int C, int VEC>
 static int launch_ce_dice(const float *logits, const int64_t *labels, int N, int64_t HW,
                           const float *cw, int ignore_index, float grad_scale, float *loss_out,
-                          float *dlogits, uint8_t *pred, void *workspace, cudaStream_t st) {
+                          float *dlogits, uint8_t *pred, void *workspace, cudaStream_t st, float dice_weight) {
   auto kern = ce_dice_kernel<C, VEC>;
   static int max_blocks = 0;  // co-resident CTA capacity of this device for this kernel
   if (max_blocks == 0) {
@@ -240,7 +240,7 @@ static int launch_ce_dice(const float *logits, const int64_t *labels, int N, int
   const long long *lab = (const long long *)labels; long long hw = HW; unsigned char *pr = pred;
   void *args[] = {(void *)&logits, (void *)&lab, (void *)&N, (void *)&hw, (void *)&cw, (void *)&ignore_index,
                   (void *)&grad_scale, (void *)&loss_out, (void *)&dlogits, (void *)&pr,
-                  (void *)&acc, (void *)&ce, (void *)&counter};
+                  (void *)&acc, (void *)&ce, (void *)&counter, (void *)&dice_weight};
   e = cudaLaunchCooperativeKernel((const void *)kern, dim3(chunks, N), dim3(256), args, 0, st);
   return (int)e;
 }
@@ -251,16 +251,75 @@ extern "C" int64_t ks_ce_dice_workspace_bytes(int N) {
   return (int64_t)((2 * (int64_t)N + 2) * 8 + 64);
 }
 
+extern "C" int ks_ce_dice_fwd_bwd_ex(const float *logits, const int64_t *labels, int N, int C, int64_t HW,
+                                     const float *class_weights, int ignore_index, float grad_scale, float dice_weight,
+                                     float *loss_out, float *dlogits, uint8_t *pred, void *workspace, void *stream);
+
 extern "C" int ks_ce_dice_fwd_bwd(const float *logits, const int64_t *labels, int N, int C, int64_t HW,
                                   const float *class_weights, int ignore_index, float grad_scale,
                                   float *loss_out, float *dlogits, uint8_t *pred,
                                   void *workspace, void *stream) {
+  return ks_ce_dice_fwd_bwd_ex(logits, labels, N, C, HW, class_weights, ignore_index, grad_scale, 1.0f, loss_out, dlogits, pred,
+                               workspace, stream);
+}
+
+extern "C" int ks_ce_dice_fwd_bwd_ex(const float *logits, const int64_t *labels, int N, int C, int64_t HW,
+                                     const float *class_weights, int ignore_index, float grad_scale, float dice_weight,
+                                     float *loss_out, float *dlogits, uint8_t *pred, void *workspace, void *stream) {
   KS_CHECK_ARG(logits && labels && class_weights && loss_out && workspace);
   KS_CHECK_ARG(N > 0 && HW > 0);
   if (C != 3) return KS_EUNSUPPORTED;  // num_classes is 3 on every reference config (configs/config.json:13)
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (HW % 4 == 0) && (((uintptr_t)logits & 15) == 0) && (((uintptr_t)labels & 15) == 0) &&
                    (dlogits == nullptr || ((uintptr_t)dlogits & 15) == 0) && (pred == nullptr || ((uintptr_t)pred & 3) == 0);
-  if (vec) return ks::launch_ce_dice<3, 4>(logits, labels, N, HW, class_weights, ignore_index, grad_scale, loss_out, dlogits, pred, workspace, st);
-  return ks::launch_ce_dice<3, 1>(logits, labels, N, HW, class_weights, ignore_index, grad_scale, loss_out, dlogits, pred, workspace, st);
+  if (vec) return ks::launch_ce_dice<3, 4>(logits, labels, N, HW, class_weights, ignore_index, grad_scale, loss_out, dlogits, pred, workspace, st, dice_weight);
+  return ks::launch_ce_dice<3, 1>(logits, labels, N, HW, class_weights, ignore_index, grad_scale, loss_out, dlogits, pred, workspace, st, dice_weight);
+}
+
+// ---- in-loop metrics ----------------------------------------------------------------------
+// The reference keeps 5 torchmetrics objects (multiclass, num_classes 4, ignore_index 3, average 'none'; utilities/utilities.py:
+// 228-265) and updates each one every iteration (training/change_detection_trainer.py:184-199): ~25 small kernels per step.
+// Everything they report derives from ONE KxK confusion matrix: mat[target][pred] += 1 over the pixels whose target is not ignored.
+namespace ks {
+template <int K>
+__global__ void __launch_bounds__(256)
+confusion_kernel(const unsigned char *__restrict__ pred, const long long *__restrict__ labels, long long n, int ignore_index,
+                 unsigned long long *mat) {
+  __shared__ unsigned int sm[K * K];
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x) sm[i] = 0u;
+  __syncthreads();
+  unsigned int cnt[K * K];
+#pragma unroll
+  for (int i = 0; i < K * K; ++i) cnt[i] = 0u;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long t = labels[i];
+    const int p = pred[i];
+    if (t != ignore_index && t >= 0 && t < K && p < K) {
+      const int idx = (int)t * K + p;
+#pragma unroll
+      for (int q = 0; q < K * K; ++q) cnt[q] += (q == idx) ? 1u : 0u;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < K * K; ++q) {
+    unsigned int v = cnt[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sm[q], v);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x)
+    if (sm[i]) atomicAdd(mat + i, (unsigned long long)sm[i]);
+}
+}  // namespace ks
+
+extern "C" int ks_confusion_update(const uint8_t *pred, const int64_t *labels, int64_t n, int num_classes_with_ignore, int ignore_index,
+                                   int64_t *mat, void *stream) {
+  KS_CHECK_ARG(pred && labels && mat && n > 0);
+  if (num_classes_with_ignore != 4) return KS_EUNSUPPORTED;
+  long long g = (n + 256 * 16 - 1) / (256 * 16);
+  if (g > ks::kNumSMs * 8) g = ks::kNumSMs * 8;
+  if (g < 1) g = 1;
+  ks::confusion_kernel<4><<<(int)g, 256, 0, (cudaStream_t)stream>>>(pred, (const long long *)labels, n, ignore_index, (unsigned long long *)mat);
+  KS_LAUNCH_RET();
 }

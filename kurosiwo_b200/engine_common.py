@@ -72,11 +72,13 @@ class TrainStepMixin:
     # (training/change_detection_trainer.py:136-177 without the two loss.item() host syncs)
     # ------------------------------------------------------------------------------------------
     def init_training(self, class_weights=(1.0, 1.0, 1.0), ignore_index: int = 3, lr: float = 1e-3,
-                      betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, process_group=None):
+                      betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, process_group=None,
+                      dice_weight: float = 1.0):
         dev = self.device
         self.params.ensure(dev)
         self.cw = torch.tensor(class_weights, dtype=torch.float32, device=dev)
         self.ignore_index = ignore_index
+        self.dice_weight = float(dice_weight)     # 1: CE+Dice (utilities/bce_and_dice.py), 0: plain cross-entropy (the reference default)
         self.hp = dict(lr=lr, b1=betas[0], b2=betas[1], eps=eps, wd=weight_decay)
         self.adam_m = torch.zeros_like(self.params.flat)
         self.adam_v = torch.zeros_like(self.params.flat)
@@ -98,7 +100,7 @@ class TrainStepMixin:
         """args = the model inputs (two dates for change detection, one stacked image for segmentation) + the mask."""
         inputs, mask = args[:-1], args[-1]
         logits = self.forward(*inputs, training=True)
-        self.ops.ce_dice(logits, mask, self.cw, self.ignore_index, 1.0, self.loss3, self.dlogits, self.pred, self.loss_ws)
+        self.ops.ce_dice(logits, mask, self.cw, self.ignore_index, 1.0, self.loss3, self.dlogits, self.pred, self.loss_ws, self.dice_weight)
         self.backward(self.dlogits)
 
     def _allreduce(self):

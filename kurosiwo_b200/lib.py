@@ -91,10 +91,10 @@ EXPORTED_SYMBOLS = [
     "ks_version", "ks_error_string", "ks_set_option", "ks_permute_cast", "ks_permute_cast_batched", "ks_conv2d", "ks_conv2d_wgrad", "ks_stem_conv3x3", "ks_stem_wgrad3x3",
     "ks_bn_stats", "ks_bn_finalize", "ks_bn_act", "ks_bn_bwd_reduce", "ks_bn_bwd_apply", "ks_maxpool2x2_bwd",
     "ks_channel_sum", "ks_ecam_pool", "ks_ecam_gates", "ks_ecam_final", "ks_ecam_bwd_reduce", "ks_ecam_gates_bwd",
-    "ks_ecam_bwd_apply", "ks_ce_dice_workspace_bytes", "ks_ce_dice_fwd_bwd", "ks_adam_step",
+    "ks_ecam_bwd_apply", "ks_ce_dice_workspace_bytes", "ks_ce_dice_fwd_bwd", "ks_ce_dice_fwd_bwd_ex", "ks_adam_step",
     "ks_softmax_head_fwd", "ks_softmax_head_bwd", "ks_dropout_mask", "ks_channel_scale", "ks_absdiff_fwd", "ks_absdiff_bwd",
     "ks_layernorm_fwd", "ks_layernorm_bwd", "ks_patchify_ln", "ks_patchify_ln_bwd", "ks_vit_assemble", "ks_vit_assemble_bwd",
-    "ks_attention_fwd", "ks_attention_bwd", "ks_gelu_fwd", "ks_gelu_bwd", "ks_bilinear_up_fwd", "ks_bilinear_up_bwd",
+    "ks_confusion_update", "ks_attention_fwd", "ks_attention_bwd", "ks_gelu_fwd", "ks_gelu_bwd", "ks_bilinear_up_fwd", "ks_bilinear_up_bwd",
 ]
 
 
@@ -382,13 +382,18 @@ class CudaOps:
         nbytes = int(self.lib.ks_ce_dice_workspace_bytes(C.c_int(N)))
         return torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
 
-    def ce_dice(self, logits, labels, class_weights, ignore_index, grad_scale, loss_out, dlogits, pred, workspace):
+    def ce_dice(self, logits, labels, class_weights, ignore_index, grad_scale, loss_out, dlogits, pred, workspace, dice_weight=1.0):
         N, K = logits.shape[0], logits.shape[1]
         HW = logits.numel() // (N * K)
-        rc = self.lib.ks_ce_dice_fwd_bwd(_p(logits), _p(labels), C.c_int(N), C.c_int(K), C.c_int64(HW), _p(class_weights),
-                                         C.c_int(ignore_index), C.c_float(grad_scale), _p(loss_out), _p(dlogits), _p(pred),
-                                         _p(workspace), self._stream())
-        self._check(rc, "ks_ce_dice_fwd_bwd")
+        rc = self.lib.ks_ce_dice_fwd_bwd_ex(_p(logits), _p(labels), C.c_int(N), C.c_int(K), C.c_int64(HW), _p(class_weights),
+                                            C.c_int(ignore_index), C.c_float(grad_scale), C.c_float(dice_weight), _p(loss_out),
+                                            _p(dlogits), _p(pred), _p(workspace), self._stream())
+        self._check(rc, "ks_ce_dice_fwd_bwd_ex")
+
+    def confusion_update(self, pred: torch.Tensor, labels: torch.Tensor, K: int, ignore_index: int, mat: torch.Tensor):
+        rc = self.lib.ks_confusion_update(_p(pred), _p(labels), C.c_int64(labels.numel()), C.c_int(K), C.c_int(ignore_index), _p(mat),
+                                          self._stream())
+        self._check(rc, "ks_confusion_update")
 
     # -- optimizer ---------------------------------------------------------------------------
     def adam_step(self, p, g, m, v, lr, b1, b2, eps, wd, grad_scale, step):

@@ -42,8 +42,9 @@ class FusedSegStepper:
     def __init__(self, model, configs, model_configs, process_group=None):
         if not isinstance(model, FinetunerSegmentation):
             raise TypeError("the fused segmentation step is implemented for kurosiwo_b200.FinetunerSegmentation (FloodViT)")
-        if configs.get("loss_function", "ce+dice") != "ce+dice":
-            raise NotImplementedError("the fused step computes CE+Dice (utilities/bce_and_dice.py); set loss_function='ce+dice'")
+        if configs.get("loss_function", "ce+dice") not in ("ce+dice", "cross_entropy"):
+            raise NotImplementedError("the fused step computes CE+Dice (utilities/bce_and_dice.py) or plain cross-entropy "
+                                      "(utilities/utilities.py:308-321); other losses are outside the B200 hot path")
         self.model, self.configs, self.model_configs, self.pg = model, configs, model_configs, process_group
         self.engine = None
         self.lr = float(model_configs["learning_rate"])
@@ -52,7 +53,8 @@ class FusedSegStepper:
         eng = self.model.engine(x)
         if eng is not self.engine:
             eng.init_training(class_weights=self.configs.get("class_weights", [1.0, 1.0, 1.0]), ignore_index=3, lr=self.lr,
-                              betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=self.pg)   # torch.optim.Adam(lr) (:36)
+                              betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=self.pg,
+                              dice_weight=0.0 if self.configs.get("loss_function") == "cross_entropy" else 1.0)   # torch.optim.Adam(lr) (:36)
             self.engine = eng
         return eng
 

@@ -6,7 +6,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .bce_and_dice import BCEandDiceLoss
+from .bce_and_dice import BCEandDiceLoss, FusedCrossEntropyLoss
 
 RANDOM_EVENTS_CLASS_WEIGHTS = [0.3715753140309927, 14.009780283125977, 8.20405370357821]  # utilities.py:393-397
 
@@ -28,14 +28,15 @@ def update_config(config, args=None):
 
 
 def create_loss(configs, mode="val"):
-    """utilities/utilities.py:307-347.  'ce+dice' is the fused sm_100a kernel; plain CE stays torch's."""
+    """utilities/utilities.py:307-347.  'ce+dice' and 'cross_entropy' both run on the fused sm_100a loss kernel."""
     weights = configs.get("class_weights", [1.0, 1.0, 1.0])
     if configs["loss_function"] == "ce+dice":
         return BCEandDiceLoss(weights=torch.tensor(weights), ignore_index=3, use_softmax=True).to(configs["device"])
-    if configs["loss_function"] == "cross_entropy":
-        if mode == "train":
-            return nn.CrossEntropyLoss(weight=torch.tensor(weights), ignore_index=3).to(configs["device"])
-        return nn.CrossEntropyLoss(ignore_index=3).to(configs["device"])
+    if configs["loss_function"] == "cross_entropy":           # class weights only in train mode, as the reference (:316-321)
+        w = torch.tensor(weights) if mode == "train" else None
+        if str(configs["device"]).startswith("cuda"):
+            return FusedCrossEntropyLoss(weight=w, ignore_index=3, num_classes=configs.get("num_classes", 3)).to(configs["device"])
+        return nn.CrossEntropyLoss(weight=w, ignore_index=3).to(configs["device"])
     raise NotImplementedError(f'loss_function {configs["loss_function"]} is outside the B200 hot path (SURVEY.md §8)')
 
 
@@ -51,6 +52,11 @@ class ConfusionMetrics:
         self.mat.zero_()
 
     def update(self, preds: torch.Tensor, target: torch.Tensor):
+        if preds.is_cuda and preds.dtype == torch.uint8 and target.dtype == torch.int64 and self.K == 4 and preds.is_contiguous() \
+                and target.is_contiguous():
+            from .lib import default_ops        # one kernel, no host sync (the uint8 argmax map comes from the loss kernel)
+            default_ops().confusion_update(preds, target, self.K, self.ignore, self.mat)
+            return
         t = target.reshape(-1)
         p = preds.reshape(-1).to(torch.int64)
         keep = t != self.ignore

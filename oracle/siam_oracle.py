@@ -105,15 +105,24 @@ def _do(x, masks, key):
 
 
 def siam_forward(sd: Dict[str, torch.Tensor], x1, x2, kind: str = "conc", training: bool = True,
-                 masks: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
-    """Returns the model output: probabilities (conc) or log-probabilities (diff), [N,K,H,W]."""
+                 masks: Optional[Dict[str, torch.Tensor]] = None, tap: Optional[dict] = None,
+                 relu_masks: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+    """Returns the model output: probabilities (conc) or log-probabilities (diff), [N,K,H,W].
+    relu_masks (tests only): per-execution boolean masks that REPLACE the ReLU sign test (v * mask instead of relu(v)); with the
+    masks of another implementation's activations this makes gradient comparisons immune to sign flips of pre-activations
+    that are zero to rounding error (a ReLU mask flip changes the gradient by a finite amount)."""
+    def act(v, key):
+        return v * relu_masks[key].to(v.dtype) if relu_masks is not None else F.relu(v)
+
     skips = {}
     pooled_last = None
     for br, x in ((1, x1), (2, x2)):
         h = x
         for n, _ in ENC:                                   # siam_conc.py:99-144
-            h = _do(F.relu(_bn(sd, f"bn{n}", F.conv2d(h, sd[f"conv{n}.weight"], sd[f"conv{n}.bias"], padding=1), training)),
+            h = _do(act(_bn(sd, f"bn{n}", F.conv2d(h, sd[f"conv{n}.weight"], sd[f"conv{n}.bias"], padding=1), training), f"{n}_{br}"),
                     masks, f"{n}_{br}")
+            if tap is not None:
+                tap[f"{n}_{br}"] = h
             if n in STAGE_LAST:
                 skips[(n, br)] = h
                 h = F.max_pool2d(h, 2, 2)
@@ -126,13 +135,15 @@ def siam_forward(sd: Dict[str, torch.Tensor], x1, x2, kind: str = "conc", traini
             s1, s2 = skips[(SKIP_OF[n], 1)], skips[(SKIP_OF[n], 2)]
             h = F.pad(h, (0, s1.shape[3] - h.shape[3], 0, s1.shape[2] - h.shape[2]), mode="replicate")
             h = torch.cat((h, s1, s2), 1) if kind == "conc" else torch.cat((h, torch.abs(s1 - s2)), 1)
-        h = _do(F.relu(_bn(sd, f"bn{n}", F.conv_transpose2d(h, sd[f"conv{n}.weight"], sd[f"conv{n}.bias"], padding=1), training)),
+        h = _do(act(_bn(sd, f"bn{n}", F.conv_transpose2d(h, sd[f"conv{n}.weight"], sd[f"conv{n}.bias"], padding=1), training), n),
                 masks, n)
+        if tap is not None:
+            tap[n] = h
     z = F.conv_transpose2d(h, sd["conv11d.weight"], sd["conv11d.bias"], padding=1)
     return F.softmax(z, 1) if kind == "conc" else F.log_softmax(z, 1)
 
 
-def train_step(sd, x1, x2, mask, kind="conc", class_weights=(1.0, 1.0, 1.0), masks=None):
+def train_step(sd, x1, x2, mask, kind="conc", class_weights=(1.0, 1.0, 1.0), masks=None, relu_masks=None):
     """forward (train-mode BN) + CE+Dice on the model OUTPUT (the reference applies the criterion to the softmax /
     log-softmax output: change_detection_trainer.py:136-170, utilities.py:342-347) + autograd backward."""
     from .snunet_oracle import ce_dice_torch
@@ -140,7 +151,7 @@ def train_step(sd, x1, x2, mask, kind="conc", class_weights=(1.0, 1.0, 1.0), mas
     leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in names}
     work = dict(sd)
     work.update(leaves)
-    out = siam_forward(work, x1, x2, kind, True, masks)
+    out = siam_forward(work, x1, x2, kind, True, masks, None, relu_masks)
     # running stats / num_batches_tracked were updated in place: `work` shares those tensor objects with `sd`
     loss = ce_dice_torch(out, mask, class_weights)
     grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)

@@ -280,9 +280,15 @@ class ShadowOps:
     def ce_dice_workspace(self, N, device):
         return torch.empty(2 * N + 16, dtype=torch.float64, device=device)
 
-    def ce_dice(self, logits, labels, class_weights, ignore_index, grad_scale, loss_out, dlogits, pred, workspace):
+    def ce_dice(self, logits, labels, class_weights, ignore_index, grad_scale, loss_out, dlogits, pred, workspace, dice_weight=1.0):
         from oracle.loss_oracle import ce_dice
         r = ce_dice(logits.numpy(), labels.numpy(), class_weights.numpy(), ignore_index)
+        if dice_weight != 1.0:       # loss = dice_weight*Dice + CE: the CE part alone comes from torch's own cross_entropy
+            z = logits.detach().clone().requires_grad_(True)
+            ce = F.cross_entropy(z, labels, weight=class_weights, ignore_index=ignore_index)
+            ce.backward()
+            d_only = r["dlogits"] - z.grad.numpy()
+            r = dict(r, loss=dice_weight * r["dice"] + r["ce"], dlogits=dice_weight * d_only + z.grad.numpy())
         loss_out.copy_(torch.tensor([r["loss"], r["dice"], r["ce"]], dtype=torch.float32))
         if dlogits is not None:
             dlogits.copy_(torch.from_numpy(r["dlogits"] * grad_scale).float())
@@ -444,3 +450,8 @@ class ShadowOps:
         o = torch.zeros(B, Tp, Cs)
         o[:, row0:row0 + G * G, :K] = m.grad.permute(0, 2, 3, 1).reshape(B, G * G, K)
         dsrc.copy_(o.view(B * Tp, Cs).to(dsrc.dtype))
+
+    def confusion_update(self, pred, labels, K, ignore_index, mat):
+        t, p = labels.reshape(-1), pred.reshape(-1).long()
+        keep = t != ignore_index
+        mat.view(-1).add_(torch.bincount(t[keep] * K + p[keep], minlength=K * K))

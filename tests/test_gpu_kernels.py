@@ -340,3 +340,45 @@ def test_adam(ops, sh):
         ops.adam_step(dp, dg * (it + 1), dm, dv, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, step)
     assert int(step.item()) == 3
     assert max_rel(dp, ref.data) < 1e-6
+
+
+def test_confusion_update(ops, sh):
+    """Bit-exact integer work: the fused confusion-matrix kernel against torch.bincount, incl. accumulation over two calls."""
+    g = _gen(9)
+    n = 3 * 224 * 224 + 5
+    pred = torch.randint(0, 3, (n,), generator=g, dtype=torch.uint8)
+    lab = torch.randint(0, 4, (n,), generator=g, dtype=torch.int64)
+    mat, cmat = torch.zeros(4, 4, dtype=torch.int64, device=DEV), torch.zeros(4, 4, dtype=torch.int64)
+    for _ in range(2):
+        ops.confusion_update(pred.to(DEV), lab.to(DEV), 4, 3, mat)
+        sh.confusion_update(pred, lab, 4, 3, cmat)
+    assert torch.equal(mat.cpu(), cmat) and int(cmat[3].sum()) == 0
+    from kurosiwo_b200.utilities import ConfusionMetrics
+    m = ConfusionMetrics(3, 3, DEV)
+    m.update(pred.to(DEV), lab.to(DEV))
+    m2 = ConfusionMetrics(3, 3, "cpu")
+    m2.update(pred, lab)
+    for a, b in zip(m.compute(), m2.compute()):
+        assert torch.allclose(a.cpu(), b)
+
+
+@pytest.mark.parametrize("weights", [[1.0, 1.0, 1.0], [0.3715753140309927, 14.009780283125977, 8.20405370357821]])
+def test_cross_entropy_mode_matches_torch(ops, weights):
+    """dice_weight = 0: the fused loss kernel is exactly nn.CrossEntropyLoss(weight, ignore_index=3) (the reference's default
+    criterion, utilities/utilities.py:308-321): value 1e-5, gradient 1e-5 rel-L2, argmax bit-exact."""
+    import torch.nn.functional as F
+    from kurosiwo_b200.bce_and_dice import FusedCrossEntropyLoss
+    g = _gen(11)
+    N, H, W = 3, 28, 36
+    z = (3.0 * torch.randn(N, 3, H, W, generator=g)).requires_grad_(True)
+    y = torch.randint(0, 4, (N, H, W), generator=g)
+    w = torch.tensor(weights)
+    ref = F.cross_entropy(z, y, weight=w, ignore_index=3)
+    ref.backward()
+    zd = z.detach().to(DEV).requires_grad_(True)
+    crit = FusedCrossEntropyLoss(weight=w, ignore_index=3).to(DEV)
+    loss = crit(zd, y.to(DEV))
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), ref.item(), rtol=1e-5)
+    assert rel_l2(zd.grad, z.grad) < 1e-5
+    assert torch.equal(crit.last_pred.cpu().long(), z.detach().argmax(1))
