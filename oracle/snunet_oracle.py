@@ -29,7 +29,10 @@ def to_torch_state(sd_np: Dict[str, np.ndarray], dtype=torch.float32) -> Dict[st
     return out
 
 
-def _block(sd, name, x, training, q):
+def _block(sd, name, x, training, q, rm=None):
+    """rm (tests only): (mask_h, mask_out) boolean tensors that REPLACE the two ReLU sign tests (see snunet_forward)."""
+    def act(v, i):
+        return v * rm[i].to(v.dtype) if rm is not None else F.relu(v)
     def bn(t, tag):
         return F.batch_norm(t, sd[f"{name}.{tag}.running_mean"], sd[f"{name}.{tag}.running_var"],
                             sd[f"{name}.{tag}.weight"], sd[f"{name}.{tag}.bias"], training, 0.1, 1e-5)
@@ -37,9 +40,9 @@ def _block(sd, name, x, training, q):
     if training:
         sd[f"{name}.bn1.num_batches_tracked"] += 1
         sd[f"{name}.bn2.num_batches_tracked"] += 1
-    h = q(F.relu(bn(y1, "bn1")))
+    h = q(act(bn(y1, "bn1"), 0))
     y2 = q(F.conv2d(h, q(sd[f"{name}.conv2.weight"]), sd[f"{name}.conv2.bias"], padding=1))
-    return q(F.relu(bn(y2, "bn2") + y1))
+    return q(act(bn(y2, "bn2") + y1, 1))
 
 
 def _up(sd, name, x, q):
@@ -55,8 +58,12 @@ def _ca(sd, name, x):
 
 
 def snunet_forward(sd: Dict[str, torch.Tensor], xA: torch.Tensor, xB: torch.Tensor, training: bool = True,
-                   quant: Optional[Callable] = None) -> torch.Tensor:
-    """`quant` (optional) rounds stored activations / conv weights, to emulate bf16 storage."""
+                   quant: Optional[Callable] = None, relu_masks: Optional[dict] = None, tap: Optional[dict] = None) -> torch.Tensor:
+    """`quant` (optional) rounds stored activations / conv weights, to emulate bf16 storage.
+    relu_masks (tests only): {("enc", l, 0|1) / ("dec", l, j): (mask_h, mask_out)} replaces the ReLU sign tests by given masks, so
+    that gradient comparisons with another implementation are immune to sign flips of pre-activations that are zero to rounding
+    error; tap (tests only) collects each block's (h-less) output under the same keys."""
+    rmk = (lambda key: relu_masks[key]) if relu_masks is not None else (lambda key: None)
     q = quant or (lambda t: t)
     X = {}
     for br, x in (("A", q(xA)), ("B", q(xB))):           # snunet.py:120-130 (A first: running-stat order)
@@ -64,11 +71,15 @@ def snunet_forward(sd: Dict[str, torch.Tensor], xA: torch.Tensor, xB: torch.Tens
             if l == 4 and br == "A":
                 continue                                 # snunet.py:124 (commented out)
             inp = x if l == 0 else F.max_pool2d(X[(l - 1, br)], 2, 2)
-            X[(l, br)] = _block(sd, f"conv{l}_0", inp, training, q)
+            X[(l, br)] = _block(sd, f"conv{l}_0", inp, training, q, rmk(("enc", l, 0 if br == "A" else 1)))
+            if tap is not None:
+                tap[("enc", l, 0 if br == "A" else 1)] = X[(l, br)]
     for (l, j) in DEC_ORDER:                             # snunet.py:132-144
         below = X[(l + 1, "B")] if j == 1 else X[(l + 1, j - 1)]
         cat = [X[(l, "A")], X[(l, "B")]] + [X[(l, k)] for k in range(1, j)] + [_up(sd, f"Up{l + 1}_{j - 1}", below, q)]
-        X[(l, j)] = _block(sd, f"conv{l}_{j}", torch.cat(cat, 1), training, q)
+        X[(l, j)] = _block(sd, f"conv{l}_{j}", torch.cat(cat, 1), training, q, rmk(("dec", l, j)))
+        if tap is not None:
+            tap[("dec", l, j)] = X[(l, j)]
     outs = [X[(0, j)] for j in range(1, 5)]
     out = torch.cat(outs, 1)                             # :146
     intra = torch.sum(torch.stack(outs), dim=0)          # :148
@@ -98,13 +109,13 @@ def param_names(sd) -> list:
     return [k for k in sd if k.endswith(PARAM_SUFFIXES)]
 
 
-def train_step(sd: Dict[str, torch.Tensor], xA, xB, mask, weights=(1.0, 1.0, 1.0), quant=None):
+def train_step(sd: Dict[str, torch.Tensor], xA, xB, mask, weights=(1.0, 1.0, 1.0), quant=None, relu_masks=None):
     """One forward + loss + backward. Returns (loss, logits, grads dict). Updates BN running stats in sd."""
     names = param_names(sd)
     for k in names:
         sd[k].requires_grad_(True)
         sd[k].grad = None
-    logits = snunet_forward(sd, xA, xB, True, quant)
+    logits = snunet_forward(sd, xA, xB, True, quant, relu_masks)
     loss = ce_dice_torch(logits.float(), mask, weights)
     loss.backward()
     grads = {k: sd[k].grad.detach().clone() for k in names}
