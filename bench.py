@@ -27,6 +27,20 @@ METRIC = "SAR patches/sec (224x224x6ch, bs=64) SNUNet-ECAM train step"
 UNIT = "patches/s"
 H = W = 224
 SNUNET_TRAIN_GFLOP_PER_PATCH = 213.9   # 3 x 71.32 GF forward
+# --workload: the headline (default) is BASELINE.json configs[1]; the others are the remaining model families on the path
+# (secondary lines, same JSON contract): configs[0] shape (siam-conc, bs=4) and configs[3]'s encoder (FloodViT-B, bs=64).
+WORKLOADS = {
+    "snunet": dict(metric=METRIC, batch=64, gflop=SNUNET_TRAIN_GFLOP_PER_PATCH, task="cd", method="snunet", lr=1e-3,
+                   desc="snunet-ecam (base 32, 12.03M params) train step: fwd + CE+Dice(+argmax) + bwd + allreduce + Adam; "
+                        "inputs pre_event_1,post_event of the 3-date x 2-pol 224x224 batch (reference SNUNet takes 2 dates)"),
+    "siam-conc": dict(metric="SAR patches/sec (224x224x6ch, bs=4) FC-Siam-conc train step", batch=4, gflop=22.2, task="cd", method="siam-conc",
+                      lr=1e-5, desc="siam-conc (1.55M params, Dropout2d p=0.2 on) train step: fwd + CE+Dice(+argmax) + bwd + allreduce + Adam; "
+                                    "inputs pre_event_1,post_event (BASELINE.json configs[0] shape)"),
+    "floodvit": dict(metric="SAR patches/sec (224x224x6ch, bs=64) FloodViT-B train step", batch=64, gflop=106.1, task="segmentation",
+                     method="finetune", lr=1e-4,
+                     desc="FloodViT: ViT-B/16 encoder (6 channels, 86.4M params) + linear FinetunerSegmentation head, train step: fwd + "
+                          "CE+Dice(+argmax) + bwd + allreduce + Adam; image = cat(post_event, pre_event_1, pre_event_2)"),
+}
 
 
 def peaks():
@@ -142,7 +156,7 @@ def cpu_baseline_leg(seconds_budget: float = 25.0):
             "sample": f"oracle port of the reference SNUNet train step, fp32, bs={bs} (of 64), 1 warm-up + {len(times)} timed steps"}
 
 
-def conv_roofline(eng, xa, xb, mk, pk, pk_kind):
+def conv_roofline(eng, dev_inputs, pk, pk_kind):
     """Per-launch CUDA-event timing of the dominant kernel family (tcgen05 implicit-GEMM conv: fwd + dgrad + wgrad)
     inside one eager training step; achieved = algorithmic FLOPs / summed launch time."""
     import torch
@@ -168,7 +182,7 @@ def conv_roofline(eng, xa, xb, mk, pk, pk_kind):
 
     ops.conv2d, ops.conv2d_wgrad = timed(orig_conv, "conv"), timed(orig_wgrad, "wgrad")
     try:
-        eng._fwd_loss_bwd(xa, xb, mk)     # no all-reduce here: this leg runs on rank 0 only
+        eng._fwd_loss_bwd(*dev_inputs)     # no all-reduce here: this leg runs on rank 0 only
         eng._optimizer()
         torch.cuda.synchronize()
     finally:
@@ -194,7 +208,6 @@ def run_ours(args):
     import torch.distributed as dist
     from kurosiwo_b200 import synthetic
     from kurosiwo_b200.change_detection_trainer import FusedStepper
-    from kurosiwo_b200.snunet import SNUNet_ECAM
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -205,18 +218,33 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
         pg = dist.group.WORLD
-    bs = args.batch
+    wl = WORKLOADS[args.workload]
+    bs = args.batch or wl["batch"]
     torch.manual_seed(999)
-    model = SNUNet_ECAM(2, 3, base_channel=32, precision=args.precision).to(dev).train()
     configs = {"device": dev, "inputs": ["pre_event_1", "post_event"], "dem": False, "scale_input": "normalize", "num_classes": 3,
-               "loss_function": "ce+dice", "class_weights": [1.0, 1.0, 1.0], "method": "snunet", "epochs": 1}
-    model_configs = {"method": "snunet", "optimizer": "adam", "learning_rate": 1e-3, "lr_schedule": None, "base_channel": 32}
-    stepper = FusedStepper(model, configs, model_configs, process_group=pg)
+               "num_channels": 2, "loss_function": "ce+dice", "class_weights": [1.0, 1.0, 1.0], "method": wl["method"], "epochs": 1,
+               "precision": args.precision, "task": wl["task"], "resume_checkpoint": False}
+    model_configs = {"method": wl["method"], "optimizer": "adam", "learning_rate": wl["lr"], "lr_schedule": None, "base_channel": 32}
     host_batches = [synthetic.make_batch(999 + rank + 1000 * i, bs, H, W, pin=True) for i in range(2)]
-    # ---- device-resident arm -------------------------------------------------------------------
     b0 = host_batches[0]
-    xa, xb, mk = b0[6].to(dev), b0[2].to(dev), b0[3].to(dev)     # pre_event_1, post_event, mask
-    eng = stepper._engine(xa)
+    if wl["task"] == "cd":
+        from kurosiwo_b200.model_utilities import initialize_cd_model
+        model = initialize_cd_model(configs, model_configs).train()
+        stepper = FusedStepper(model, configs, model_configs, process_group=pg)
+        dev_inputs = (b0[6].to(dev), b0[2].to(dev), b0[3].to(dev))     # pre_event_1, post_event, mask
+        h2d = 2 * bs * 2 * H * W * 4 + bs * H * W * 8
+    else:
+        from kurosiwo_b200.model_utilities import initialize_segmentation_model
+        from kurosiwo_b200.segmentation_trainer import FusedSegStepper
+        configs.update({"inputs": ["pre_event_1", "pre_event_2", "post_event"], "num_channels": 6, "mlp": False, "decoder": False,
+                        "finetuning_patch_size": 16, "linear_eval": False, "encoder": None})
+        model_configs["encoder_config"] = {"image_size": 224, "patch_size": 16, "dim": 768, "depth": 12, "heads": 12, "mlp_dim": 3072}
+        model = initialize_segmentation_model(configs, model_configs).to(dev).train()
+        stepper = FusedSegStepper(model, configs, model_configs, process_group=pg)
+        dev_inputs = (torch.cat((b0[2], b0[6], b0[9]), 1).to(dev), b0[3].to(dev))   # cat(post, pre1, pre2), mask
+        h2d = 3 * bs * 2 * H * W * 4 + bs * H * W * 8
+    # ---- device-resident arm -------------------------------------------------------------------
+    eng = stepper._engine(dev_inputs[0])
     ops = eng.ops
     if args.tc_mt:
         ops.set_option("tc_mt", args.tc_mt)
@@ -224,15 +252,15 @@ def run_ours(args):
         ops.set_option("tc_v1", 1)
     use_graph = not args.no_graph
     for _ in range(2):
-        eng.train_step(xa, xb, mk)
+        eng.train_step(*dev_inputs)
     torch.cuda.synchronize()
     l0 = ops.launches
-    eng.train_step(xa, xb, mk)
+    eng.train_step(*dev_inputs)
     calls_per_step = ops.launches - l0
     if use_graph:
-        step = eng.capture(xa, xb, mk)
+        step = eng.capture(*dev_inputs)
     else:
-        step = lambda: eng.train_step(xa, xb, mk)
+        step = lambda: eng.train_step(*dev_inputs)
     for _ in range(max(args.warmup, 3)):
         step()
     sampler = ClockSampler(local)
@@ -276,13 +304,12 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * bs / (t.item() / args.steps * 1e-3)
-    h2d = 2 * bs * 2 * H * W * 4 + bs * H * W * 8
     # ---- roofline + CPU baseline (rank 0, N==1 only) --------------------------------------------
     pk, pk_kind = peaks()
     roof, layers, cpu = None, None, None
     if rank == 0:
-        roof, layers = conv_roofline(eng, xa, xb, mk, pk, pk_kind)
-        if world == 1 and not args.no_cpu_baseline:
+        roof, layers = conv_roofline(eng, dev_inputs, pk, pk_kind)
+        if world == 1 and not args.no_cpu_baseline and args.workload == "snunet":
             cpu = cpu_baseline_leg()
         out_dir = ROOT / "gpurun_out"
         try:
@@ -295,16 +322,15 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank != 0:
         return
-    step_tflops = world * bs * SNUNET_TRAIN_GFLOP_PER_PATCH / (ms_per_step * 1e-3) / 1e3 / world
+    step_tflops = world * bs * wl["gflop"] / (ms_per_step * 1e-3) / 1e3 / world
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": "snunet-ecam (base 32, 12.03M params) train step: fwd + CE+Dice(+argmax) + bwd + allreduce + Adam; "
-                               "inputs pre_event_1,post_event of the 3-date x 2-pol 224x224 batch (reference SNUNet takes 2 dates)",
+        "config": {"workload": wl["desc"],
                    "per_gpu_batch": bs, "global_batch": bs * world, "parallelism": f"dp{world}", "cuda_graph": use_graph,
-                   "l2": "working set per step (>30 GB of activations at bs=64) exceeds the 126 MB L2; no explicit flush",
-                   "step_tflops_per_gpu_vs_213.9GF_per_patch": step_tflops, "final_loss": loss_val},
+                   "l2": "per-step working set (activations kept for the backward: GBs at the BASELINE batch) exceeds the 126 MB L2; no explicit flush",
+                   "step_tflops_per_gpu": step_tflops, "gflop_per_patch": wl["gflop"], "final_loss": loss_val},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
         "gpu_launches": calls_per_step * args.steps,
@@ -320,7 +346,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (0 = the workload's BASELINE.json batch)")
+    ap.add_argument("--workload", default="snunet", choices=sorted(WORKLOADS), help="snunet = the headline (BASELINE.json configs[1])")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--tc-v1", type=int, default=0, help="1 = non-persistent v1 conv kernel (A/B comparisons)")
