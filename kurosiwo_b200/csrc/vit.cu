@@ -613,150 +613,201 @@ __device__ __forceinline__ void atc_store_rows(const float *sw, int sp, __nv_bfl
   }
 }
 
-__global__ void __launch_bounds__(ATC_WARPS * 32)
+// ---- register-resident ("flash"-style) strips on mma.sync.m16n8k16 ------------------------------------------------------
+// One warp owns a 16-query strip; the whole score row block S[16 x Tp] lives in the accumulator fragments (Tp <= 256: 128
+// registers), so the softmax is a per-lane pass plus two quad shuffles, and the bf16 probabilities are re-used IN REGISTERS as the
+// A operand of P.V (accumulator layout of two adjacent n8 tiles == A layout of one k16 step).  K and V sit in shared memory
+// (72-element pitch) and are read with ldmatrix (.trans for the [key][d] -> (k = key, n = d) operands).
+constexpr int AM_WARPS = 8, AM_T8 = 32;       // up to 32 n8 tiles = 256 keys
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void *p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void *p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t *>(&h2);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u));
+}
+// A fragments (4 k16 steps over d = 64) of a 16-row strip read straight from global rows (pitch ld elements)
+__device__ __forceinline__ void am_load_a(uint32_t (&a)[4][4], const __nv_bfloat16 *rows, long long ld, int g, int t) {
+  const __nv_bfloat16 *r0 = rows + (long long)g * ld + 2 * t, *r1 = r0 + 8 * ld;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    a[kk][0] = *reinterpret_cast<const uint32_t *>(r0 + kk * 16);
+    a[kk][1] = *reinterpret_cast<const uint32_t *>(r1 + kk * 16);
+    a[kk][2] = *reinterpret_cast<const uint32_t *>(r0 + kk * 16 + 8);
+    a[kk][3] = *reinterpret_cast<const uint32_t *>(r1 + kk * 16 + 8);
+  }
+}
+// acc[jt] (+)= A[16 x 64] . M^T where M = [Tp][64] in shared memory (scores against K, or dO against V)
+__device__ __forceinline__ void am_scores(float (&acc)[AM_T8][4], const uint32_t (&a)[4][4], const __nv_bfloat16 *Ms, int NT8, int lane) {
+#pragma unroll
+  for (int jt = 0; jt < AM_T8; ++jt) {
+    if (jt < NT8) {
+      acc[jt][0] = acc[jt][1] = acc[jt][2] = acc[jt][3] = 0.f;
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        uint32_t r[4];
+        ldsm_x4(r, Ms + (jt * 8 + (lane & 7)) * ATC_KP + h2 * 32 + (lane >> 3) * 8);
+        mma16816(acc[jt], a[2 * h2], r[0], r[1]);
+        mma16816(acc[jt], a[2 * h2 + 1], r[2], r[3]);
+      }
+    }
+  }
+}
+// o[dt] += P[16 x Tp] . M where the bf16 P comes packed per n8 tile: pk[jt][0] = row g, pk[jt][1] = row g+8
+__device__ __forceinline__ void am_apply(float (&o)[8][4], const uint32_t (&pk)[AM_T8][2], const __nv_bfloat16 *Ms, int NT16, int lane) {
+#pragma unroll
+  for (int kk = 0; kk < AM_T8 / 2; ++kk) {
+    if (kk < NT16) {
+      const uint32_t a[4] = {pk[2 * kk][0], pk[2 * kk][1], pk[2 * kk + 1][0], pk[2 * kk + 1][1]};
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t r[4];
+        ldsm_x4_t(r, Ms + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATC_KP + (dp * 2 + (lane >> 4)) * 8);
+        mma16816(o[2 * dp], a, r[0], r[1]);
+        mma16816(o[2 * dp + 1], a, r[2], r[3]);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void am_store_o(const float (&o)[8][4], __nv_bfloat16 *rows, long long ld, int g, int t, bool ok0, bool ok1, float mul) {
+  __nv_bfloat16 *r0 = rows + (long long)g * ld + 2 * t, *r1 = r0 + 8 * ld;
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt) {
+    *reinterpret_cast<uint32_t *>(r0 + dt * 8) = ok0 ? pack_bf16(o[dt][0] * mul, o[dt][1] * mul) : 0u;
+    *reinterpret_cast<uint32_t *>(r1 + dt * 8) = ok1 ? pack_bf16(o[dt][2] * mul, o[dt][3] * mul) : 0u;
+  }
+}
+
+__global__ void __launch_bounds__(AM_WARPS * 32, 1)
 attention_fwd_tc_kernel(int Tt, int Tp, int heads, const __nv_bfloat16 *__restrict__ qkv, float scale, __nv_bfloat16 *__restrict__ out,
                         __nv_bfloat16 *__restrict__ probs) {
   extern __shared__ __align__(128) unsigned char smraw[];
-  const int SP = (Tp > 64 ? Tp : 64) + 4, SPB = Tp + 8, NT = Tp / 16;     // SP >= 64: the strip buffer also stages 16 x 64 outputs
   __nv_bfloat16 *Ks = reinterpret_cast<__nv_bfloat16 *>(smraw), *Vs = Ks + Tp * ATC_KP;
-  float *Sall = reinterpret_cast<float *>(Vs + Tp * ATC_KP);
-  __nv_bfloat16 *Pall = reinterpret_cast<__nv_bfloat16 *>(Sall + ATC_WARPS * 16 * SP);
-  const int b = blockIdx.y, h = blockIdx.x, inner = heads * ATT_DH;
+  const int b = blockIdx.y, h = blockIdx.x, inner = heads * ATT_DH, NT8 = Tp / 8, NT16 = Tp / 16;
   const long long ld = 3LL * inner;
   const __nv_bfloat16 *base = qkv + (long long)b * Tp * ld + h * ATT_DH;
   atc_load_tile(Ks, base + inner, ld, Tt, Tp);
   atc_load_tile(Vs, base + 2 * inner, ld, Tt, Tp);
   __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float *Sw = Sall + w * 16 * SP;
-  __nv_bfloat16 *Pw = Pall + w * 16 * SPB;
-  for (int strip = w; strip < NT; strip += ATC_WARPS) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  for (int strip = w; strip < NT16; strip += AM_WARPS) {
     const int i0 = strip * 16;
-    wm::fragment<wm::matrix_a, 16, 16, 16, __nv_bfloat16, wm::row_major> qa[4];
+    const bool ok0 = (i0 + g) < Tt, ok1 = (i0 + g + 8) < Tt;
+    uint32_t qa[4][4];
+    am_load_a(qa, base + (long long)i0 * ld, ld, g, t);
+    float s[AM_T8][4];
+    am_scores(s, qa, Ks, NT8, lane);
+    float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) wm::load_matrix_sync(qa[k], base + (long long)i0 * ld + k * 16, (unsigned)ld);
-    for (int jt = 0; jt < NT; ++jt) {
-      wm::fragment<wm::accumulator, 16, 16, 16, float> acc;
-      wm::fill_fragment(acc, 0.f);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        wm::fragment<wm::matrix_b, 16, 16, 16, __nv_bfloat16, wm::col_major> kb;
-        wm::load_matrix_sync(kb, Ks + jt * 16 * ATC_KP + k * 16, ATC_KP);
-        wm::mma_sync(acc, qa[k], kb, acc);
-      }
-      wm::store_matrix_sync(Sw + jt * 16, acc, SP, wm::mem_row_major);
-    }
-    __syncwarp();
-    {   // row softmax: lane pair per row, interleaved columns
-      const int r = lane >> 1, hf = lane & 1;
-      const bool rok = (i0 + r) < Tt;
-      float *sr = Sw + r * SP;
-      float mx = -INFINITY;
-      for (int j = hf; j < Tt; j += 2) mx = fmaxf(mx, sr[j] * scale);
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      float sum = 0.f;
-      for (int j = hf; j < Tt; j += 2) { const float e = expf(sr[j] * scale - mx); sr[j] = e; sum += e; }
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      const float inv = 1.f / sum;
-      __nv_bfloat16 *pr = Pw + r * SPB;
-      __nv_bfloat16 *gr = probs + (((long long)b * heads + h) * Tp + i0 + r) * Tp;
-      for (int j = hf; j < Tp; j += 2) {
-        const __nv_bfloat16 pv = __float2bfloat16_rn((rok && j < Tt) ? sr[j] * inv : 0.f);
-        pr[j] = pv; gr[j] = pv;
+    for (int jt = 0; jt < AM_T8; ++jt) {
+      if (jt < NT8) {
+        const int c = jt * 8 + 2 * t;
+        if (c < Tt) { m0 = fmaxf(m0, s[jt][0]); m1 = fmaxf(m1, s[jt][2]); }
+        if (c + 1 < Tt) { m0 = fmaxf(m0, s[jt][1]); m1 = fmaxf(m1, s[jt][3]); }
       }
     }
-    __syncwarp();
-    wm::fragment<wm::accumulator, 16, 16, 16, float> oacc[4];
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-    for (int d = 0; d < 4; ++d) wm::fill_fragment(oacc[d], 0.f);
-    for (int jt = 0; jt < NT; ++jt) {
-      wm::fragment<wm::matrix_a, 16, 16, 16, __nv_bfloat16, wm::row_major> pa;
-      wm::load_matrix_sync(pa, Pw + jt * 16, SPB);
-#pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        wm::fragment<wm::matrix_b, 16, 16, 16, __nv_bfloat16, wm::row_major> vb;
-        wm::load_matrix_sync(vb, Vs + jt * 16 * ATC_KP + d * 16, ATC_KP);
-        wm::mma_sync(oacc[d], pa, vb, oacc[d]);
+    for (int jt = 0; jt < AM_T8; ++jt) {
+      if (jt < NT8) {
+        const int c = jt * 8 + 2 * t;
+        s[jt][0] = (c < Tt) ? expf((s[jt][0] - m0) * scale) : 0.f;
+        s[jt][1] = (c + 1 < Tt) ? expf((s[jt][1] - m0) * scale) : 0.f;
+        s[jt][2] = (c < Tt) ? expf((s[jt][2] - m1) * scale) : 0.f;
+        s[jt][3] = (c + 1 < Tt) ? expf((s[jt][3] - m1) * scale) : 0.f;
+        l0 += s[jt][0] + s[jt][1]; l1 += s[jt][2] + s[jt][3];
       }
     }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = ok0 ? 1.f / l0 : 0.f, inv1 = ok1 ? 1.f / l1 : 0.f;
+    uint32_t pk[AM_T8][2];
+    __nv_bfloat16 *pr0 = probs + (((long long)b * heads + h) * Tp + i0 + g) * Tp + 2 * t, *pr1 = pr0 + 8LL * Tp;
 #pragma unroll
-    for (int d = 0; d < 4; ++d) wm::store_matrix_sync(Sw + d * 16, oacc[d], SP, wm::mem_row_major);
-    __syncwarp();
-    atc_store_rows(Sw, SP, out + ((long long)b * Tp + i0) * inner + h * ATT_DH, inner, lane, i0, Tt, 1.f);
-    __syncwarp();
+    for (int jt = 0; jt < AM_T8; ++jt) {
+      if (jt < NT8) {
+        pk[jt][0] = pack_bf16(s[jt][0] * inv0, s[jt][1] * inv0);
+        pk[jt][1] = pack_bf16(s[jt][2] * inv1, s[jt][3] * inv1);
+        *reinterpret_cast<uint32_t *>(pr0 + jt * 8) = pk[jt][0];
+        *reinterpret_cast<uint32_t *>(pr1 + jt * 8) = pk[jt][1];
+      }
+    }
+    float o[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+    am_apply(o, pk, Vs, NT16, lane);
+    am_store_o(o, out + ((long long)b * Tp + i0) * inner + h * ATT_DH, inner, g, t, ok0, ok1, 1.f);
   }
 }
 
-__global__ void __launch_bounds__(ATC_WARPS * 32)
+__global__ void __launch_bounds__(AM_WARPS * 32, 1)
 attention_bwd_rows_tc_kernel(int Tt, int Tp, int heads, const __nv_bfloat16 *__restrict__ qkv, const __nv_bfloat16 *__restrict__ probs,
                              const __nv_bfloat16 *__restrict__ dout, float scale, __nv_bfloat16 *__restrict__ dqkv,
                              __nv_bfloat16 *__restrict__ ds) {
   extern __shared__ __align__(128) unsigned char smraw[];
-  const int SP = (Tp > 64 ? Tp : 64) + 4, SPB = Tp + 8, NT = Tp / 16;     // SP >= 64: the strip buffer also stages 16 x 64 outputs
   __nv_bfloat16 *Ks = reinterpret_cast<__nv_bfloat16 *>(smraw), *Vs = Ks + Tp * ATC_KP;
-  float *Sall = reinterpret_cast<float *>(Vs + Tp * ATC_KP);
-  __nv_bfloat16 *Pall = reinterpret_cast<__nv_bfloat16 *>(Sall + ATC_WARPS * 16 * SP);
-  const int b = blockIdx.y, h = blockIdx.x, inner = heads * ATT_DH;
+  const int b = blockIdx.y, h = blockIdx.x, inner = heads * ATT_DH, NT8 = Tp / 8, NT16 = Tp / 16;
   const long long ld = 3LL * inner;
   const __nv_bfloat16 *base = qkv + (long long)b * Tp * ld + h * ATT_DH;
   atc_load_tile(Ks, base + inner, ld, Tt, Tp);
   atc_load_tile(Vs, base + 2 * inner, ld, Tt, Tp);
   __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float *Sw = Sall + w * 16 * SP;
-  __nv_bfloat16 *Pw = Pall + w * 16 * SPB;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const __nv_bfloat16 *dob = dout + (long long)b * Tp * inner + h * ATT_DH;
-  for (int strip = w; strip < NT; strip += ATC_WARPS) {
+  for (int strip = w; strip < NT16; strip += AM_WARPS) {
     const int i0 = strip * 16;
-    wm::fragment<wm::matrix_a, 16, 16, 16, __nv_bfloat16, wm::row_major> da[4];
+    const bool ok0 = (i0 + g) < Tt, ok1 = (i0 + g + 8) < Tt;
+    uint32_t da[4][4];
+    am_load_a(da, dob + (long long)i0 * inner, inner, g, t);
+    float dp[AM_T8][4];
+    am_scores(dp, da, Vs, NT8, lane);                          // dP = dO V^T
+    const __nv_bfloat16 *pr0 = probs + (((long long)b * heads + h) * Tp + i0 + g) * Tp + 2 * t, *pr1 = pr0 + 8LL * Tp;
+    float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) wm::load_matrix_sync(da[k], dob + (long long)i0 * inner + k * 16, (unsigned)inner);
-    for (int jt = 0; jt < NT; ++jt) {            // dP = dO V^T
-      wm::fragment<wm::accumulator, 16, 16, 16, float> acc;
-      wm::fill_fragment(acc, 0.f);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        wm::fragment<wm::matrix_b, 16, 16, 16, __nv_bfloat16, wm::col_major> vb;
-        wm::load_matrix_sync(vb, Vs + jt * 16 * ATC_KP + k * 16, ATC_KP);
-        wm::mma_sync(acc, da[k], vb, acc);
-      }
-      wm::store_matrix_sync(Sw + jt * 16, acc, SP, wm::mem_row_major);
-    }
-    __syncwarp();
-    {
-      const int r = lane >> 1, hf = lane & 1;
-      const bool rok = (i0 + r) < Tt;
-      const float *sr = Sw + r * SP;
-      const __nv_bfloat16 *pg = probs + (((long long)b * heads + h) * Tp + i0 + r) * Tp;
-      float dot = 0.f;
-      for (int j = hf; j < Tt; j += 2) dot += sr[j] * __bfloat162float(pg[j]);
-      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-      __nv_bfloat16 *pr = Pw + r * SPB;
-      __nv_bfloat16 *gr = ds + (((long long)b * heads + h) * Tp + i0 + r) * Tp;
-      for (int j = hf; j < Tp; j += 2) {
-        const __nv_bfloat16 v = __float2bfloat16_rn((rok && j < Tt) ? __bfloat162float(pg[j]) * (sr[j] - dot) : 0.f);
-        pr[j] = v; gr[j] = v;
+    for (int jt = 0; jt < AM_T8; ++jt) {
+      if (jt < NT8) {
+        const float2 p0 = unpack_bf16(*reinterpret_cast<const uint32_t *>(pr0 + jt * 8));
+        const float2 p1 = unpack_bf16(*reinterpret_cast<const uint32_t *>(pr1 + jt * 8));
+        d0 += dp[jt][0] * p0.x + dp[jt][1] * p0.y;
+        d1 += dp[jt][2] * p1.x + dp[jt][3] * p1.y;
       }
     }
-    __syncwarp();
-    wm::fragment<wm::accumulator, 16, 16, 16, float> qacc[4];     // dQ = dS K
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+    uint32_t pk[AM_T8][2];
+    __nv_bfloat16 *sr0 = ds + (((long long)b * heads + h) * Tp + i0 + g) * Tp + 2 * t, *sr1 = sr0 + 8LL * Tp;
 #pragma unroll
-    for (int d = 0; d < 4; ++d) wm::fill_fragment(qacc[d], 0.f);
-    for (int jt = 0; jt < NT; ++jt) {
-      wm::fragment<wm::matrix_a, 16, 16, 16, __nv_bfloat16, wm::row_major> sa;
-      wm::load_matrix_sync(sa, Pw + jt * 16, SPB);
-#pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        wm::fragment<wm::matrix_b, 16, 16, 16, __nv_bfloat16, wm::row_major> kb;
-        wm::load_matrix_sync(kb, Ks + jt * 16 * ATC_KP + d * 16, ATC_KP);
-        wm::mma_sync(qacc[d], sa, kb, qacc[d]);
+    for (int jt = 0; jt < AM_T8; ++jt) {
+      if (jt < NT8) {
+        const float2 p0 = unpack_bf16(*reinterpret_cast<const uint32_t *>(pr0 + jt * 8));
+        const float2 p1 = unpack_bf16(*reinterpret_cast<const uint32_t *>(pr1 + jt * 8));
+        pk[jt][0] = ok0 ? pack_bf16(p0.x * (dp[jt][0] - d0), p0.y * (dp[jt][1] - d0)) : 0u;     // P is 0 for keys >= T
+        pk[jt][1] = ok1 ? pack_bf16(p1.x * (dp[jt][2] - d1), p1.y * (dp[jt][3] - d1)) : 0u;
+        *reinterpret_cast<uint32_t *>(sr0 + jt * 8) = pk[jt][0];
+        *reinterpret_cast<uint32_t *>(sr1 + jt * 8) = pk[jt][1];
       }
     }
+    float o[8][4];
 #pragma unroll
-    for (int d = 0; d < 4; ++d) wm::store_matrix_sync(Sw + d * 16, qacc[d], SP, wm::mem_row_major);
-    __syncwarp();
-    atc_store_rows(Sw, SP, dqkv + ((long long)b * Tp + i0) * ld + h * ATT_DH, ld, lane, i0, Tt, scale);
-    __syncwarp();
+    for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+    am_apply(o, pk, Ks, NT16, lane);                           // dQ = dS K
+    am_store_o(o, dqkv + ((long long)b * Tp + i0) * ld + h * ATT_DH, ld, g, t, ok0, ok1, scale);
   }
 }
 
@@ -808,9 +859,7 @@ attention_bwd_cols_tc_kernel(int Tt, int Tp, int heads, const __nv_bfloat16 *__r
   }
 }
 
-static inline size_t atc_smem_rows(int Tp) {
-  return (size_t)2 * Tp * ATC_KP * 2 + (size_t)ATC_WARPS * 16 * ((Tp > 64 ? Tp : 64) + 4) * 4 + (size_t)ATC_WARPS * 16 * (Tp + 8) * 2 + 128;
-}
+static inline size_t atc_smem_rows(int Tp) { return (size_t)2 * Tp * ATC_KP * 2 + 128; }
 static inline size_t atc_smem_cols(int Tp) { return (size_t)2 * Tp * ATC_KP * 2 + (size_t)ATC_WARPS * 16 * 68 * 4 + 128; }
 static inline bool atc_ok(int dtype, int T, int Tp, int dh, int heads) {
   return dtype == KS_BF16 && !g_opt.att_simt && dh == ATT_DH && Tp % 16 == 0 && T <= Tp && atc_smem_rows(Tp) <= 220 * 1024 &&
@@ -855,7 +904,7 @@ extern "C" int ks_layernorm_bwd(int dtype, int64_t rows, int C, const void *dy, 
   KS_CHECK_ARG(rows > 0 && C > 0 && dy && x && mean && rstd && gamma);
   if (C % 8 || C > LNB_KMAX * 256 || lddy % 8 || ldx % 8 || (dx && lddx % 8) || !al16(dy) || !al16(x) || !al16(gamma) || (dx && !al16(dx)))
     return KS_EUNSUPPORTED;
-  const int grid = grid_for(rows, 8 * 8, 2);     // >= 8 rows per warp so that the per-CTA column atomics amortise
+  const int grid = grid_for(rows, 8 * 8, 2);     // >= 8 rows per warp so that the per-CTA column atomics amortise (more, smaller CTAs measured slower)
   const size_t smem = (size_t)2 * C * sizeof(float);
 #define CALL(T) layernorm_bwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(rows, C, (const T *)dy, lddy, (const T *)x, ldx, mean, rstd, \
                                                                                      gamma, (T *)dx, lddx, accumulate_dx, dgamma, dbeta)
@@ -928,7 +977,7 @@ extern "C" int ks_attention_fwd(int dtype, int B, int T, int Tp, int heads, int 
     static bool attr = false;
     if (!attr) { cudaError_t e = cudaFuncSetAttribute(attention_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
                  if (e != cudaSuccess) return (int)e; attr = true; }
-    attention_fwd_tc_kernel<<<dim3((unsigned)heads, (unsigned)B), ATC_WARPS * 32, atc_smem_rows(Tp), (cudaStream_t)stream>>>(
+    attention_fwd_tc_kernel<<<dim3((unsigned)heads, (unsigned)B), AM_WARPS * 32, atc_smem_rows(Tp), (cudaStream_t)stream>>>(
         T, Tp, heads, (const __nv_bfloat16 *)qkv, scale, (__nv_bfloat16 *)out, (__nv_bfloat16 *)probs);
     KS_LAUNCH_RET();
   }
@@ -957,7 +1006,7 @@ extern "C" int ks_attention_bwd(int dtype, int B, int T, int Tp, int heads, int 
       attr = true;
     }
     const dim3 g((unsigned)heads, (unsigned)B);
-    attention_bwd_rows_tc_kernel<<<g, ATC_WARPS * 32, atc_smem_rows(Tp), (cudaStream_t)stream>>>(
+    attention_bwd_rows_tc_kernel<<<g, AM_WARPS * 32, atc_smem_rows(Tp), (cudaStream_t)stream>>>(
         T, Tp, heads, (const __nv_bfloat16 *)qkv, (const __nv_bfloat16 *)probs, (const __nv_bfloat16 *)dout, scale, (__nv_bfloat16 *)dqkv,
         (__nv_bfloat16 *)ds_scratch);
     attention_bwd_cols_tc_kernel<<<g, ATC_WARPS * 32, atc_smem_cols(Tp), (cudaStream_t)stream>>>(
