@@ -83,6 +83,7 @@ def main():
         print(tag, "loss", float(loss.detach()), "logits", out.shape)
     siam_goldens()
     vit_goldens()
+    changeformer_goldens()
 
 
 def siam_goldens():
@@ -178,7 +179,65 @@ def vit_goldens():
         print("floodvit", tag, "loss", float(loss.detach()))
 
 
+def changeformer_goldens():
+    """ChangeFormerV6 fixtures from the unmodified reference (timm stubbed: DropPath / trunc_normal_ / to_2tuple only); the stochastic
+    layers run with p = 0 (train-mode BatchNorm statistics kept), see oracle/changeformer_oracle.py."""
+    from oracle.ref_import import install_stubs
+    install_stubs()
+    from models.changeformer import ChangeFormerV6 as RefCF                # noqa: E402  (reference, read-only)
+    from utilities.bce_and_dice import BCEandDiceLoss as RefLoss           # noqa: E402
+    from oracle import changeformer_oracle as co
+    from oracle.weights import make_batch
+
+    for tag, (N, HW, seed) in {"n2_s64": (2, 64, 81), "n2_s224": (2, 224, 82)}.items():
+        sd = co.make_state(seed)
+        x1, x2, mask = make_batch(seed, N, HW, HW)
+        model = RefCF(embed_dim=256, input_nc=2, output_nc=3, decoder_softmax=True)
+        assert list(model.state_dict().keys()) == list(sd.keys())
+        model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+            if type(mod).__name__ == "DropPath":
+                mod.drop_prob = 0.0
+        model.train()
+        crit = RefLoss(weights=torch.tensor([1.0, 1.0, 1.0]), ignore_index=3, use_softmax=True)
+        outs = model(torch.from_numpy(x1), torch.from_numpy(x2))
+        loss = crit(outs[-1], torch.from_numpy(mask))          # change_detection_trainer.py:166-170 (no multi_scale_train)
+        loss.backward()
+        st = max(1, HW // 32)
+        fx = {"N": N, "HW": HW, "seed": seed, "loss": loss.detach().numpy(), "out_sample": outs[-1].detach().numpy()[:, :, ::st, ::st].copy()}
+        for i in range(4):
+            fx[f"side{i}"] = outs[i].detach().numpy()
+        names, norms = [], []
+        keep_full = {"Tenc_x2.patch_embed1.proj.weight", "Tenc_x2.patch_embed1.norm.bias", "Tenc_x2.block1.0.attn.sr.weight",
+                     "Tenc_x2.block1.0.attn.q.bias", "Tenc_x2.block2.1.attn.kv.weight", "Tenc_x2.block1.2.mlp.dwconv.dwconv.weight",
+                     "Tenc_x2.block3.0.norm1.weight", "Tenc_x2.block4.2.mlp.fc2.bias", "Tenc_x2.norm4.weight", "TDec_x2.linear_c1.proj.weight",
+                     "TDec_x2.diff_c3.2.weight", "TDec_x2.diff_c4.0.bias", "TDec_x2.linear_fuse.1.bias", "TDec_x2.convd1x.conv2d.bias",
+                     "TDec_x2.change_probability.conv2d.weight", "TDec_x2.change_probability.conv2d.bias"}
+        for k, p in model.named_parameters():
+            names.append(k)
+            g = p.grad if p.grad is not None else torch.zeros_like(p)
+            norms.append(float(g.double().norm()))
+            if k in keep_full:
+                fx[f"grad.{k}"] = g.numpy()
+        fx["grad_names"] = np.array(names)
+        fx["grad_norms"] = np.array(norms, np.float64)
+        stt = model.state_dict()
+        for k in ("TDec_x2.diff_c1.2.running_mean", "TDec_x2.diff_c4.2.running_var", "TDec_x2.linear_fuse.1.running_mean",
+                  "TDec_x2.make_pred_c2.2.running_var", "TDec_x2.linear_fuse.1.num_batches_tracked"):
+            fx[f"state.{k}"] = stt[k].numpy()
+        model.eval()
+        with torch.no_grad():
+            fx["out_eval_sample"] = model(torch.from_numpy(x1), torch.from_numpy(x2))[-1].numpy()[:, :, ::st, ::st].copy()
+        np.savez_compressed(OUT / f"changeformer_{tag}.npz", **fx)
+        print("changeformer", tag, "loss", float(loss.detach()))
+
+
 if __name__ == "__main__":
+    if "--cf-only" in sys.argv:
+        changeformer_goldens()
+        sys.exit(0)
     if "--vit-only" in sys.argv:
         vit_goldens()
         sys.exit(0)
