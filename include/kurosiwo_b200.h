@@ -79,7 +79,8 @@ typedef struct ks_permute_job {
   /* dst_strided != 0: element (i0,i1,i2,i3) goes to dst[i0*t0+i1*t1+i2*t2+i3*t3] instead of the contiguous position
    * (writes a logical sub-block into a channel-padded buffer whose padding stays zero). */
   int64_t t0, t1, t2, t3;
-  int32_t dst_strided, _pad;
+  int32_t dst_strided;
+  float scale;   /* value multiplier; 0 means 1 (ResidualBlock's `* 0.1`, changeformer.py:481, is folded into packed weights) */
 } ks_permute_job_t;
 int ks_permute_cast_batched(const ks_permute_job_t *jobs_dev, const int32_t *chunks_dev, int n_chunks, void *stream);
 
@@ -267,6 +268,43 @@ int ks_bilinear_up_fwd(int dtype, int B, int G, int Tp, int row0, int Cs, int K,
                        void *stream);
 int ks_bilinear_up_bwd(int dtype, int B, int G, int Tp, int row0, int Cs, int K, int Ho, int Wo, const float *ddst, void *dsrc,
                        void *stream);
+
+/* ---- ChangeFormerV6 passes (models/changeformer.py) ---------------------------------------------------------------
+ * Token matrices [B*N, C] are NHWC images [B, H, W, C]; LayerNorm / GELU / Linear reuse the ViT entry points above, the decoder's
+ * 3x3 / 1x1 / transposed convolutions and BatchNorm reuse ks_conv2d / ks_conv2d_wgrad / ks_bn_*. */
+/* Generic strided convolution (OverlapPatchEmbed.proj 7x7 s4|s2 p3, changeformer.py:281; Attention.sr k = s = sr, :166):
+ * out[n,ho,wo,co] = bias[co] + sum x[n, ho*s-p+ky, wo*s-p+kx, ci] * w[ky*k+kx][co][ci]; weight in `dtype`, k <= 8. */
+int ks_conv2d_strided(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int ksize, int stride, int pad, const ks_view_t *src,
+                      const void *weight, const float *bias, const ks_view_t *dst, void *stream);
+/* dx (+)= its data gradient (same weight layout); dw[ky*k+kx][co][ci] (+)= its weight gradient (fp32). */
+int ks_conv2d_strided_dgrad(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int ksize, int stride, int pad, const ks_view_t *dy,
+                            const void *weight, const ks_view_t *dx, int accumulate, void *stream);
+int ks_conv2d_strided_wgrad(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int ksize, int stride, int pad, const ks_view_t *x,
+                            const ks_view_t *dy, float *dw, int accumulate, void *stream);
+/* Spatial-reduction attention core (changeformer.py:186-208): q [B*Nq][ldq] (head h at columns h*dh..), kv [B*Nk][ldkv] with k at
+ * columns h*dh.. and v at heads*dh + h*dh..; out = softmax(q k^T * scale) v; probs [B][heads][Nq][Nk] kept for the backward.
+ * Nk <= 64, dh <= 96.  _bwd writes dq and ACCUMULATES dk|dv into the fp32 buffer dkv [B*Nk][2*heads*dh] (zeroed by the call). */
+int ks_xattention_fwd(int dtype, int B, int Nq, int Nk, int heads, int dh, const void *q, int64_t ldq, const void *kv, int64_t ldkv,
+                      float scale, void *out, int64_t ldo, void *probs, void *stream);
+int ks_xattention_bwd(int dtype, int B, int Nq, int Nk, int heads, int dh, const void *q, int64_t ldq, const void *kv, int64_t ldkv,
+                      const void *probs, const void *dout, int64_t ldo, float scale, void *dq, int64_t lddq, float *dkv, void *stream);
+/* Depth-wise 3x3 conv, padding 1 (DWConv, changeformer.py:84-96) on dense NHWC; w9: fp32 [9][C] (tap-major), bias fp32 [C].
+ * _bwd: dx = data gradient; dw9 += weight gradient, dbias += bias gradient (fp32 atomics, caller zeroes). */
+int ks_dwconv3x3_fwd(int dtype, int N, int H, int W, int C, const void *x, const float *w9, const float *bias, void *y, void *stream);
+int ks_dwconv3x3_bwd(int dtype, int N, int H, int W, int C, const void *x, const void *dy, const float *w9, void *dx, float *dw9,
+                     float *dbias, void *stream);
+/* F.interpolate(mode='bilinear', align_corners=False) of dense NHWC maps (changeformer.py:587,592,600,608): dst (+)= resize(src);
+ * _bwd is the exact adjoint in gather form: dsrc (+)= resize^T(ddst). */
+int ks_bilinear_nhwc_fwd(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int C, const void *src, void *dst, int accumulate, void *stream);
+int ks_bilinear_nhwc_bwd(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int C, const void *ddst, void *dsrc, int accumulate, void *stream);
+/* ReLU outside a BatchNorm pass (conv_diff / ResidualBlock, changeformer.py:31-38,471-483): y = max(x, 0) (y may alias x);
+ * dx = g * (r > 0) with r the ReLU OUTPUT (dx may alias g). */
+int ks_relu_fwd(int dtype, int64_t n, const void *x, void *y, void *stream);
+int ks_relu_bwd(int dtype, int64_t n, const void *r, const void *g, void *dx, void *stream);
+/* nn.Sigmoid on the K-class map (changeformer.py:635-639): NHWC view z (Cout padded to 16) -> NCHW fp32; _bwd writes every
+ * channel of dz (0 for channels >= K). */
+int ks_sigmoid_head_fwd(int dtype, int N, int H, int W, const ks_view_t *z, int K, float *out, void *stream);
+int ks_sigmoid_head_bwd(int dtype, int N, int H, int W, const float *out, const float *dout, int K, const ks_view_t *dz, void *stream);
 
 /* ---- loss (utilities/bce_and_dice.py:18-24, utilities/dice.py:93-137) --- */
 /* Fused softmax -> weighted CE(ignore_index) + Dice, forward + gradient + argmax.

@@ -1,0 +1,700 @@
+// Passes of ChangeFormerV6 (models/changeformer.py) that are not a stride-1 3x3 / 1x1 convolution, LayerNorm, GELU or BatchNorm
+// (those run on the engines in conv_*.cu, vit.cu, elementwise.cu):
+//   ks_conv2d_strided / _dgrad / _wgrad   OverlapPatchEmbed.proj 7x7 s4|s2 p3 (:281,288) and Attention.sr k = s = sr (:166,193)
+//   ks_xattention_fwd / _bwd              spatial-reduction attention: N queries x (<= 64) reduced keys (:186-208)
+//   ks_dwconv3x3_fwd / _bwd               Mix-FFN depth-wise 3x3 conv (:84-96)
+//   ks_bilinear_nhwc_fwd / _bwd           F.interpolate(..., mode='bilinear', align_corners=False) of NHWC maps (:585-608)
+//   ks_relu_fwd / _bwd, ks_sigmoid_head_fwd / _bwd   ReLU outside a BatchNorm pass (:31-38,471-483), final Sigmoid (:635-639)
+// Token matrices [B*N, C] ARE NHWC images [B, H, W, C] (N = H*W row-major), so no transposes exist on this path.
+// First correct path: the strided convolutions and the attention are exact-fp32 CUDA-core kernels for both storage dtypes
+// (6 % of the model's FLOPs, models/changeformer.py encoder); the 94 % in the decoder's 256-channel 3x3 convs run on tcgen05.
+#include "common.cuh"
+
+namespace ks {
+
+// ---------------------------------------------------------------------------------------------------------
+// Generic strided convolution, implicit GEMM 64x64x16 on CUDA cores.
+//   MODE 0 (forward):  out[n,ho,wo,co] = bias[co] + sum_{ky,kx,ci} x[n, ho*s-p+ky, wo*s-p+kx, ci] * w[ky*k+kx][co][ci]
+//   MODE 1 (data grad): dx[n,h,w,ci] (+)= sum_{ky,kx,co} dy[n, (h+p-ky)/s, (w+p-kx)/s, co] * w[ky*k+kx][co][ci]   (divisible only)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int GBM = 64, GBN = 64, GBK = 16;
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+conv_gen_kernel(View src, View dst, int N, int Hs, int Ws, int Hd, int Wd, int ksize, int stride, int pad, int Cin, int Cout,
+                const T *__restrict__ weight, const float *__restrict__ bias, int accumulate) {
+  // src/dst: MODE 0 src = x [N,Hs,Ws,Cin], dst = out [N,Hd,Wd,Cout];  MODE 1 src = dy [N,Hs,Ws,Cout], dst = dx [N,Hd,Wd,Cin]
+  __shared__ float As[GBK][GBM + 4];
+  __shared__ float Bs[GBK][GBN + 4];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const long long M = (long long)N * Hd * Wd;
+  const long long m0 = (long long)blockIdx.x * GBM;
+  const int n0 = blockIdx.y * GBN;
+  const int CK = (MODE == 0) ? Cin : Cout;      // reduction channels
+  const int CN = (MODE == 0) ? Cout : Cin;      // output channels
+  const int lrow = tid / 4, lk = (tid % 4) * 4;
+  const long long lm = m0 + lrow;
+  const bool lm_ok = lm < M;
+  int ln = 0, lh = 0, lw = 0;
+  if (lm_ok) { lw = (int)(lm % Wd); long long r = lm / Wd; lh = (int)(r % Hd); ln = (int)(r / Hd); }
+  const int lcn = n0 + lrow;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int tap = 0; tap < ksize * ksize; ++tap) {
+    const int ky = tap / ksize, kx = tap % ksize;
+    int hh, ww; bool pix_ok = lm_ok;
+    if (MODE == 0) { hh = lh * stride - pad + ky; ww = lw * stride - pad + kx; }
+    else {
+      const int th = lh + pad - ky, tw = lw + pad - kx;
+      pix_ok = pix_ok && th >= 0 && tw >= 0 && (th % stride) == 0 && (tw % stride) == 0;
+      hh = th / stride; ww = tw / stride;
+    }
+    pix_ok = pix_ok && hh >= 0 && hh < Hs && ww >= 0 && ww < Ws;
+    const T *xp = reinterpret_cast<const T *>(src.ptr) + ((long long)ln * src.sn + (long long)hh * src.sh + (long long)ww * src.sw);
+    const T *wt = weight + (long long)tap * Cout * Cin;
+    for (int c0 = 0; c0 < CK; c0 += GBK) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + lk + i;
+        float a = 0.f, b = 0.f;
+        if (c < CK) {
+          if (pix_ok) a = Cvt<T>::ld(xp + c);
+          if (lcn < CN) b = Cvt<T>::ld(MODE == 0 ? (wt + (long long)lcn * Cin + c) : (wt + (long long)c * Cin + lcn));
+        }
+        As[lk + i][lrow] = a;
+        Bs[lk + i][lrow] = b;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < GBK; ++k) {
+        const float4 a4 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+        const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int w = (int)(m % Wd); long long r = m / Wd; const int h = (int)(r % Hd); const int n = (int)(r / Hd);
+    T *op = reinterpret_cast<T *>(dst.ptr) + ((long long)n * dst.sn + (long long)h * dst.sh + (long long)w * dst.sw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cn = n0 + tx * 4 + j;
+      if (cn >= CN) continue;
+      float v = acc[i][j] + ((MODE == 0 && bias) ? __ldg(bias + cn) : 0.f);
+      if (accumulate) v += Cvt<T>::ld(op + cn);
+      Cvt<T>::st(op + cn, v);
+    }
+  }
+}
+
+// dw[tap][co][ci] (+)= sum_{n,ho,wo} dy[n,ho,wo,co] * x[n, ho*s-p+ky, wo*s-p+kx, ci];  grid (ci blocks, co blocks, taps*splits)
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_gen_wgrad_kernel(View x, View dy, int N, int Hi, int Wi, int Ho, int Wo, int ksize, int stride, int pad, int Cin, int Cout,
+                      int splits, float *dw) {
+  __shared__ float As[GBK][GBM + 4];  // dY tile [px][co]
+  __shared__ float Bs[GBK][GBN + 4];  // X tile  [px][ci]
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int tap = blockIdx.z / splits, split = blockIdx.z % splits;
+  const int ky = tap / ksize, kx = tap % ksize;
+  const int ci0 = blockIdx.x * 64, co0 = blockIdx.y * 64;
+  const long long M = (long long)N * Ho * Wo;
+  const long long per = ((M + splits - 1) / splits + GBK - 1) / GBK * GBK;
+  const long long p0 = (long long)split * per, p1 = min(M, p0 + per);
+  const int lp = tid / 16, lc = (tid % 16) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long long pb = p0; pb < p1; pb += GBK) {
+    const long long p = pb + lp;
+    float a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+    if (p < p1) {
+      const int wo = (int)(p % Wo); long long r = p / Wo; const int ho = (int)(r % Ho); const int n = (int)(r / Ho);
+      const T *yp = reinterpret_cast<const T *>(dy.ptr) + ((long long)n * dy.sn + (long long)ho * dy.sh + (long long)wo * dy.sw + co0 + lc);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) if (co0 + lc + i < Cout) a[i] = Cvt<T>::ld(yp + i);
+      const int hh = ho * stride - pad + ky, ww = wo * stride - pad + kx;
+      if (hh >= 0 && hh < Hi && ww >= 0 && ww < Wi) {
+        const T *xp = reinterpret_cast<const T *>(x.ptr) + ((long long)n * x.sn + (long long)hh * x.sh + (long long)ww * x.sw + ci0 + lc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (ci0 + lc + i < Cin) b[i] = Cvt<T>::ld(xp + i);
+      }
+    }
+    *reinterpret_cast<float4 *>(&As[lp][lc]) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4 *>(&Bs[lp][lc]) = make_float4(b[0], b[1], b[2], b[3]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GBK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+      const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = ci0 + tx * 4 + j;
+      if (ci >= Cin) continue;
+      atomicAdd(dw + ((long long)tap * Cout + co) * Cin + ci, acc[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Spatial-reduction attention (exact fp32 arithmetic).  q: [B*Nq, ldq] (head h at columns h*dh..), kv: [B*Nk, ldkv] with
+// k at columns h*dh.. and v at heads*dh + h*dh.. ('reshape(B,-1,2,heads,d)', :195-198); Nk <= 64, dh <= 96.
+// One CTA per (row chunk, head, image); K/V of the head in shared memory (pitch dh+1); one warp per query row.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int XA_WARPS = 8, XA_DMAX = 96, XA_KMAX = 64;
+
+template <typename T>
+__device__ __forceinline__ void xa_load(float *dst, const T *src, long long ld, int rows, int dh) {
+  for (int i = threadIdx.x; i < rows * dh; i += blockDim.x) {
+    const int r = i / dh, c = i % dh;
+    dst[r * (dh + 1) + c] = Cvt<T>::ld(src + (long long)r * ld + c);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(XA_WARPS * 32)
+xattention_fwd_kernel(int Nq, int Nk, int heads, int dh, const T *__restrict__ q, long long ldq, const T *__restrict__ kv, long long ldkv,
+                      float scale, T *__restrict__ out, long long ldo, T *__restrict__ probs, int rows_per_cta) {
+  extern __shared__ float sm[];
+  const int P = dh + 1;
+  float *Ks = sm, *Vs = Ks + Nk * P, *Qw = Vs + Nk * P, *Pw = Qw + XA_WARPS * XA_DMAX;
+  const int b = blockIdx.z, h = blockIdx.y, inner = heads * dh;
+  const T *kvb = kv + (long long)b * Nk * ldkv + h * dh;
+  xa_load(Ks, kvb, ldkv, Nk, dh);
+  xa_load(Vs, kvb + inner, ldkv, Nk, dh);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float *qw = Qw + w * XA_DMAX, *pw = Pw + w * XA_KMAX;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(Nq, r0 + rows_per_cta);
+  for (int i = r0 + w; i < r1; i += XA_WARPS) {
+    const T *qrow = q + ((long long)b * Nq + i) * ldq + h * dh;
+    for (int d = lane; d < dh; d += 32) qw[d] = Cvt<T>::ld(qrow + d);
+    __syncwarp();
+    float s[2], mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = jj * 32 + lane;
+      s[jj] = -INFINITY;
+      if (j < Nk) {
+        float a = 0.f;
+        const float *kp = Ks + j * P;
+        for (int d = 0; d < dh; ++d) a = fmaf(qw[d], kp[d], a);
+        s[jj] = a * scale; mx = fmaxf(mx, s[jj]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) { s[jj] = (jj * 32 + lane < Nk) ? expf(s[jj] - mx) : 0.f; sum += s[jj]; }
+    const float inv = 1.f / warp_sum(sum);
+    T *prow = probs + (((long long)b * heads + h) * Nq + i) * Nk;
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = jj * 32 + lane;
+      if (j < Nk) { const float pq = round_as<T>(s[jj] * inv); pw[j] = pq; Cvt<T>::st(prow + j, pq); }
+    }
+    __syncwarp();
+    T *orow = out + ((long long)b * Nq + i) * ldo + h * dh;
+    for (int d = lane; d < dh; d += 32) {
+      float o = 0.f;
+      for (int j = 0; j < Nk; ++j) o = fmaf(pw[j], Vs[j * P + d], o);
+      Cvt<T>::st(orow + d, o);
+    }
+    __syncwarp();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(XA_WARPS * 32)
+xattention_bwd_kernel(int Nq, int Nk, int heads, int dh, const T *__restrict__ q, long long ldq, const T *__restrict__ kv, long long ldkv,
+                      const T *__restrict__ probs, const T *__restrict__ dout, long long ldo, float scale, T *__restrict__ dq, long long lddq,
+                      float *__restrict__ dkv, int rows_per_cta) {
+  extern __shared__ float sm[];
+  const int P = dh + 1;
+  float *Ks = sm, *Vs = Ks + Nk * P, *dKs = Vs + Nk * P, *dVs = dKs + Nk * P, *Qw = dVs + Nk * P, *Ow = Qw + XA_WARPS * XA_DMAX,
+        *Pw = Ow + XA_WARPS * XA_DMAX, *Sw = Pw + XA_WARPS * XA_KMAX;
+  const int b = blockIdx.z, h = blockIdx.y, inner = heads * dh;
+  const T *kvb = kv + (long long)b * Nk * ldkv + h * dh;
+  xa_load(Ks, kvb, ldkv, Nk, dh);
+  xa_load(Vs, kvb + inner, ldkv, Nk, dh);
+  for (int i = threadIdx.x; i < 2 * Nk * P; i += blockDim.x) dKs[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float *qw = Qw + w * XA_DMAX, *ow = Ow + w * XA_DMAX, *pw = Pw + w * XA_KMAX, *sw = Sw + w * XA_KMAX;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(Nq, r0 + rows_per_cta);
+  for (int i = r0 + w; i < r1; i += XA_WARPS) {
+    const T *qrow = q + ((long long)b * Nq + i) * ldq + h * dh;
+    const T *dorow = dout + ((long long)b * Nq + i) * ldo + h * dh;
+    const T *prow = probs + (((long long)b * heads + h) * Nq + i) * Nk;
+    for (int d = lane; d < dh; d += 32) { qw[d] = Cvt<T>::ld(qrow + d); ow[d] = Cvt<T>::ld(dorow + d); }
+    __syncwarp();
+    float dp[2], pv[2], dot = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = jj * 32 + lane;
+      dp[jj] = 0.f; pv[jj] = 0.f;
+      if (j < Nk) {
+        float a = 0.f;
+        const float *vp = Vs + j * P;
+        for (int d = 0; d < dh; ++d) a = fmaf(ow[d], vp[d], a);
+        dp[jj] = a; pv[jj] = Cvt<T>::ld(prow + j);
+        dot += a * pv[jj];
+      }
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = jj * 32 + lane;
+      if (j < Nk) { pw[j] = pv[jj]; sw[j] = pv[jj] * (dp[jj] - dot) * scale; }
+    }
+    __syncwarp();
+    T *dqrow = dq + ((long long)b * Nq + i) * lddq + h * dh;
+    for (int d = lane; d < dh; d += 32) {
+      float o = 0.f;
+      const float qd = qw[d], od = ow[d];
+      for (int j = 0; j < Nk; ++j) {
+        o = fmaf(sw[j], Ks[j * P + d], o);
+        atomicAdd(&dKs[j * P + d], sw[j] * qd);
+        atomicAdd(&dVs[j * P + d], pw[j] * od);
+      }
+      Cvt<T>::st(dqrow + d, o);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  float *dkvb = dkv + (long long)b * Nk * (2 * inner) + h * dh;
+  for (int i = threadIdx.x; i < Nk * dh; i += blockDim.x) {
+    const int j = i / dh, d = i % dh;
+    atomicAdd(dkvb + (long long)j * (2 * inner) + d, dKs[j * P + d]);
+    atomicAdd(dkvb + (long long)j * (2 * inner) + inner + d, dVs[j * P + d]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Depth-wise 3x3 convolution (padding 1) on dense NHWC [N,H,W,C]; weights [9][C] fp32 (tap-major), bias [C].
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, bool FLIP>
+__global__ void __launch_bounds__(256)
+dwconv_kernel(int N, int H, int W, int C, const T *__restrict__ x, const float *__restrict__ w9, const float *__restrict__ bias, T *__restrict__ y) {
+  const int CV = C / 8;
+  const long long total = (long long)N * H * W * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * 8; const long long p = i / CV;
+    const int w = (int)(p % W), h = (int)((p / W) % H); const long long n = p / ((long long)W * H);
+    float acc[8];
+    if (bias) ld8(bias + c, acc); else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int dy = t / 3 - 1, dx = t % 3 - 1;
+      const int hh = FLIP ? h - dy : h + dy, ww = FLIP ? w - dx : w + dx;
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+      float f[8], wv[8];
+      ld8(x + ((n * H + hh) * W + ww) * C + c, f);
+      ld8(w9 + (long long)t * C + c, wv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[k], wv[k], acc[k]);
+    }
+    st8(y + p * C + c, acc);
+  }
+}
+
+// dw9[t][c] += sum_px dy[px][c] * x[px+t][c];  dbias[c] += sum_px dy[px][c].   grid (pixel chunks, C/256)
+template <typename T>
+__global__ void __launch_bounds__(256)
+dwconv_wgrad_kernel(int N, int H, int W, int C, const T *__restrict__ x, const T *__restrict__ dy, float *__restrict__ dw9, float *__restrict__ dbias) {
+  __shared__ float red[10][256];
+  for (int i = threadIdx.x; i < 10 * 256; i += blockDim.x) (&red[0][0])[i] = 0.f;
+  __syncthreads();
+  const int cbase = blockIdx.y * 256, cw = min(256, C - cbase), CV = cw / 8;
+  const int tx = threadIdx.x % CV, ty = threadIdx.x / CV, rows = blockDim.x / CV;
+  const int c = cbase + tx * 8;
+  float acc[10][8];
+#pragma unroll
+  for (int t = 0; t < 10; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
+  const long long npix = (long long)N * H * W;
+  if (ty < rows) {
+    for (long long p = (long long)blockIdx.x * rows + ty; p < npix; p += (long long)gridDim.x * rows) {
+      const int w = (int)(p % W), h = (int)((p / W) % H); const long long n = p / ((long long)W * H);
+      float g[8];
+      ld8(dy + p * C + c, g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[9][k] += g[k];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
+        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+        float f[8];
+        ld8(x + ((n * H + hh) * W + ww) * C + c, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(g[k], f[k], acc[t][k]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 10; ++t)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&red[t][tx * 8 + k], acc[t][k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 10 * cw; i += blockDim.x) {
+    const int t = i / cw, cc = i % cw;
+    if (t < 9) atomicAdd(dw9 + (long long)t * C + cbase + cc, red[t][cc]);
+    else if (dbias) atomicAdd(dbias + cbase + cc, red[9][cc]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Bilinear resize of dense NHWC maps, align_corners=False (aten upsample_bilinear2d).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bl_src(int d, float ratio, int in, int &i0, int &i1, float &l1) {
+  float s = ratio * ((float)d + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s; if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + ((i0 < in - 1) ? 1 : 0);
+  l1 = s - (float)i0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bilinear_nhwc_fwd_kernel(int N, int Hi, int Wi, int Ho, int Wo, int C, const T *__restrict__ src, T *__restrict__ dst, int accumulate) {
+  const int CV = C / 8;
+  const long long total = (long long)N * Ho * Wo * CV;
+  const float ry = (float)Hi / (float)Ho, rx = (float)Wi / (float)Wo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * 8; const long long p = i / CV;
+    const int x = (int)(p % Wo), y = (int)((p / Wo) % Ho); const long long n = p / ((long long)Wo * Ho);
+    int y0, y1, x0, x1; float ly, lx;
+    bl_src(y, ry, Hi, y0, y1, ly); bl_src(x, rx, Wi, x0, x1, lx);
+    float a[8], b[8], cc[8], d[8], o[8];
+    const T *base = src + n * Hi * Wi * C + c;
+    ld8(base + ((long long)y0 * Wi + x0) * C, a); ld8(base + ((long long)y0 * Wi + x1) * C, b);
+    ld8(base + ((long long)y1 * Wi + x0) * C, cc); ld8(base + ((long long)y1 * Wi + x1) * C, d);
+    if (accumulate) ld8(dst + p * C + c, o); else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] += (1.f - ly) * ((1.f - lx) * a[k] + lx * b[k]) + ly * ((1.f - lx) * cc[k] + lx * d[k]);
+    st8(dst + p * C + c, o);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bilinear_nhwc_bwd_kernel(int N, int Hi, int Wi, int Ho, int Wo, int C, const T *__restrict__ ddst, T *__restrict__ dsrc, int accumulate) {
+  const int CV = C / 8;
+  const long long total = (long long)N * Hi * Wi * CV;
+  const float ry = (float)Hi / (float)Ho, rx = (float)Wi / (float)Wo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * 8; const long long p = i / CV;
+    const int gx = (int)(p % Wi), gy = (int)((p / Wi) % Hi); const long long n = p / ((long long)Wi * Hi);
+    int ylo = (int)floorf(((float)gy - 0.5f) / ry - 0.5f) - 1, yhi = (int)ceilf(((float)gy + 1.5f) / ry - 0.5f) + 1;
+    int xlo = (int)floorf(((float)gx - 0.5f) / rx - 0.5f) - 1, xhi = (int)ceilf(((float)gx + 1.5f) / rx - 0.5f) + 1;
+    if (gy == 0) ylo = 0;
+    if (gy == Hi - 1) yhi = Ho - 1;
+    if (gx == 0) xlo = 0;
+    if (gx == Wi - 1) xhi = Wo - 1;
+    ylo = max(ylo, 0); yhi = min(yhi, Ho - 1); xlo = max(xlo, 0); xhi = min(xhi, Wo - 1);
+    float acc[8];
+    if (accumulate) ld8(dsrc + p * C + c, acc); else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    }
+    const T *gp = ddst + n * Ho * Wo * C + c;
+    for (int y = ylo; y <= yhi; ++y) {
+      int y0, y1; float ly;
+      bl_src(y, ry, Hi, y0, y1, ly);
+      const float wy = ((y0 == gy) ? (1.f - ly) : 0.f) + ((y1 == gy) ? ly : 0.f);
+      if (wy == 0.f) continue;
+      for (int x = xlo; x <= xhi; ++x) {
+        int x0, x1; float lx;
+        bl_src(x, rx, Wi, x0, x1, lx);
+        const float wx = ((x0 == gx) ? (1.f - lx) : 0.f) + ((x1 == gx) ? lx : 0.f);
+        if (wx == 0.f) continue;
+        float g[8];
+        ld8(gp + ((long long)y * Wo + x) * C, g);
+        const float ww = wy * wx;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(ww, g[k], acc[k]);
+      }
+    }
+    st8(dsrc + p * C + c, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ReLU outside a BatchNorm pass, Sigmoid head
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) relu_fwd_kernel(long long n8, const T *__restrict__ x, T *__restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    ld8(x + i * 8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+    st8(y + i * 8, f);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) relu_bwd_kernel(long long n8, const T *__restrict__ r, const T *__restrict__ g, T *__restrict__ dx) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8], gg[8];
+    ld8(r + i * 8, f); ld8(g + i * 8, gg);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gg[k] = (f[k] > 0.f) ? gg[k] : 0.f;
+    st8(dx + i * 8, gg);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T *cvp(const View &v, long long p, int H, int W, int c) {
+  const int w = (int)(p % W); const long long r = p / W; const int h = (int)(r % H); const long long n = r / H;
+  return reinterpret_cast<T *>(v.ptr) + (n * v.sn + (long long)h * v.sh + (long long)w * v.sw + c);
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+sigmoid_head_fwd_kernel(View z, int H, int W, long long NP, int K, float *__restrict__ out) {
+  const long long HW = (long long)H * W;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < NP; p += (long long)gridDim.x * blockDim.x) {
+    const T *zp = cvp<T>(z, p, H, W, 0);
+    const long long n = p / HW, q = p % HW;
+    for (int k = 0; k < K; ++k) out[(n * K + k) * HW + q] = 1.f / (1.f + expf(-Cvt<T>::ld(zp + k)));
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+sigmoid_head_bwd_kernel(View dz, int H, int W, long long NP, int K, const float *__restrict__ out, const float *__restrict__ dout) {
+  const long long HW = (long long)H * W;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < NP; p += (long long)gridDim.x * blockDim.x) {
+    T *dp = cvp<T>(dz, p, H, W, 0);
+    const long long n = p / HW, q = p % HW;
+    for (int c = 0; c < dz.C; ++c) {
+      float v = 0.f;
+      if (c < K) { const float y = out[(n * K + c) * HW + q]; v = dout[(n * K + c) * HW + q] * y * (1.f - y); }
+      Cvt<T>::st(dp + c, v);
+    }
+  }
+}
+
+static inline int cgrid(long long work, int per_block, int cap_mult = 8) {
+  long long g = (work + per_block - 1) / per_block;
+  const long long cap = (long long)kNumSMs * cap_mult;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace ks
+
+using namespace ks;
+
+#define KS_DISPATCH_T(dtype, CALL)                                  \
+  do {                                                              \
+    if ((dtype) == KS_F32) { CALL(float); }                         \
+    else if ((dtype) == KS_BF16) { CALL(__nv_bfloat16); }           \
+    else return KS_EINVAL;                                          \
+  } while (0)
+
+static inline bool a16(const void *p) { return ((uintptr_t)p % 16) == 0; }
+
+extern "C" int ks_conv2d_strided(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int ksize, int stride, int pad, const ks_view_t *src,
+                                 const void *weight, const float *bias, const ks_view_t *dst, void *stream) {
+  KS_CHECK_ARG(src && dst && weight && N > 0 && ksize >= 1 && ksize <= 8 && stride >= 1 && pad >= 0);
+  KS_CHECK_ARG(Ho == (Hi + 2 * pad - ksize) / stride + 1 && Wo == (Wi + 2 * pad - ksize) / stride + 1);
+  const long long M = (long long)N * Ho * Wo;
+  dim3 grid((unsigned)((M + GBM - 1) / GBM), (unsigned)((dst->C + GBN - 1) / GBN));
+#define CALL(T) conv_gen_kernel<T, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(to_view(*src), to_view(*dst), N, Hi, Wi, Ho, Wo, ksize, stride, pad, \
+                                                                             src->C, dst->C, (const T *)weight, bias, 0)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_conv2d_strided_dgrad(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int ksize, int stride, int pad, const ks_view_t *dy,
+                                       const void *weight, const ks_view_t *dx, int accumulate, void *stream) {
+  KS_CHECK_ARG(dy && dx && weight && N > 0 && ksize >= 1 && ksize <= 8 && stride >= 1 && pad >= 0);
+  const long long M = (long long)N * Hi * Wi;
+  dim3 grid((unsigned)((M + GBM - 1) / GBM), (unsigned)((dx->C + GBN - 1) / GBN));
+#define CALL(T) conv_gen_kernel<T, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(to_view(*dy), to_view(*dx), N, Ho, Wo, Hi, Wi, ksize, stride, pad, \
+                                                                             dx->C, dy->C, (const T *)weight, nullptr, accumulate)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_conv2d_strided_wgrad(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int ksize, int stride, int pad, const ks_view_t *x,
+                                       const ks_view_t *dy, float *dw, int accumulate, void *stream) {
+  KS_CHECK_ARG(x && dy && dw && N > 0 && ksize >= 1 && ksize <= 8 && stride >= 1 && pad >= 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int taps = ksize * ksize, Cin = x->C, Cout = dy->C;
+  if (!accumulate) { cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)taps * Cin * Cout, st); if (e != cudaSuccess) return (int)e; }
+  const int bx = (Cin + 63) / 64, by = (Cout + 63) / 64;
+  const long long M = (long long)N * Ho * Wo, tiles = (long long)bx * by * taps;
+  long long splits = (kNumSMs * 6 + tiles - 1) / tiles;
+  const long long maxs = (M + 255) / 256;
+  if (splits > maxs) splits = maxs;
+  if (splits < 1) splits = 1;
+  if (splits * taps > 65535) splits = 65535 / taps;
+  dim3 grid(bx, by, (unsigned)(taps * splits));
+#define CALL(T) conv_gen_wgrad_kernel<T><<<grid, 256, 0, st>>>(to_view(*x), to_view(*dy), N, Hi, Wi, Ho, Wo, ksize, stride, pad, Cin, Cout, (int)splits, dw)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+static int xa_cfg(int B, int Nq, int Nk, int heads, int dh, int nbuf, size_t &smem, int &rpc, int &nblk) {
+  if (Nk < 1 || Nk > XA_KMAX || dh < 1 || dh > XA_DMAX) return KS_EUNSUPPORTED;
+  smem = ((size_t)nbuf * Nk * (dh + 1) + (size_t)2 * XA_WARPS * XA_DMAX + (size_t)2 * XA_WARPS * XA_KMAX) * sizeof(float);
+  nblk = 1;
+  while ((long long)B * heads * nblk < 4 * kNumSMs && nblk * 64 < Nq) nblk <<= 1;
+  rpc = ((Nq + nblk - 1) / nblk + XA_WARPS - 1) / XA_WARPS * XA_WARPS;
+  nblk = (Nq + rpc - 1) / rpc;
+  return KS_OK;
+}
+
+extern "C" int ks_xattention_fwd(int dtype, int B, int Nq, int Nk, int heads, int dh, const void *q, int64_t ldq, const void *kv, int64_t ldkv,
+                                 float scale, void *out, int64_t ldo, void *probs, void *stream) {
+  KS_CHECK_ARG(B > 0 && Nq > 0 && heads > 0 && q && kv && out && probs);
+  size_t smem; int rpc, nblk;
+  int rc = xa_cfg(B, Nq, Nk, heads, dh, 2, smem, rpc, nblk); if (rc) return rc;
+  dim3 grid((unsigned)nblk, (unsigned)heads, (unsigned)B);
+#define CALL(T) { cudaError_t e = cudaFuncSetAttribute(xattention_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); \
+    if (e != cudaSuccess) return (int)e; \
+    xattention_fwd_kernel<T><<<grid, XA_WARPS * 32, smem, (cudaStream_t)stream>>>(Nq, Nk, heads, dh, (const T *)q, ldq, (const T *)kv, ldkv, scale, \
+                                                                                   (T *)out, ldo, (T *)probs, rpc); }
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_xattention_bwd(int dtype, int B, int Nq, int Nk, int heads, int dh, const void *q, int64_t ldq, const void *kv, int64_t ldkv,
+                                 const void *probs, const void *dout, int64_t ldo, float scale, void *dq, int64_t lddq, float *dkv, void *stream) {
+  KS_CHECK_ARG(B > 0 && Nq > 0 && heads > 0 && q && kv && probs && dout && dq && dkv);
+  size_t smem; int rpc, nblk;
+  int rc = xa_cfg(B, Nq, Nk, heads, dh, 4, smem, rpc, nblk); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e0 = cudaMemsetAsync(dkv, 0, sizeof(float) * (size_t)B * Nk * 2 * heads * dh, st); if (e0 != cudaSuccess) return (int)e0;
+  dim3 grid((unsigned)nblk, (unsigned)heads, (unsigned)B);
+#define CALL(T) { cudaError_t e = cudaFuncSetAttribute(xattention_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); \
+    if (e != cudaSuccess) return (int)e; \
+    xattention_bwd_kernel<T><<<grid, XA_WARPS * 32, smem, st>>>(Nq, Nk, heads, dh, (const T *)q, ldq, (const T *)kv, ldkv, (const T *)probs, \
+                                                                 (const T *)dout, ldo, scale, (T *)dq, lddq, dkv, rpc); }
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_dwconv3x3_fwd(int dtype, int N, int H, int W, int C, const void *x, const float *w9, const float *bias, void *y, void *stream) {
+  KS_CHECK_ARG(N > 0 && H > 0 && W > 0 && x && w9 && y);
+  if (C % 8 || !a16(x) || !a16(y) || !a16(w9) || (bias && !a16(bias))) return KS_EUNSUPPORTED;
+  const int grid = cgrid((long long)N * H * W * (C / 8), 256);
+#define CALL(T) dwconv_kernel<T, false><<<grid, 256, 0, (cudaStream_t)stream>>>(N, H, W, C, (const T *)x, w9, bias, (T *)y)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_dwconv3x3_bwd(int dtype, int N, int H, int W, int C, const void *x, const void *dy, const float *w9, void *dx, float *dw9,
+                                float *dbias, void *stream) {
+  KS_CHECK_ARG(N > 0 && H > 0 && W > 0 && x && dy && w9 && dx && dw9);
+  if (C % 8 || !a16(x) || !a16(dy) || !a16(dx) || !a16(w9)) return KS_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = cgrid((long long)N * H * W * (C / 8), 256);
+  const int gy = (C + 255) / 256;
+  int gx = (kNumSMs * 4) / gy; if (gx < 1) gx = 1;
+  const long long npix = (long long)N * H * W;
+  if (gx > (npix + 7) / 8) gx = (int)((npix + 7) / 8);
+#define CALL(T) { dwconv_kernel<T, true><<<grid, 256, 0, st>>>(N, H, W, C, (const T *)dy, w9, nullptr, (T *)dx); \
+    dwconv_wgrad_kernel<T><<<dim3(gx, gy), 256, 0, st>>>(N, H, W, C, (const T *)x, (const T *)dy, dw9, dbias); }
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_bilinear_nhwc_fwd(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int C, const void *src, void *dst, int accumulate, void *stream) {
+  KS_CHECK_ARG(N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && src && dst);
+  if (C % 8 || !a16(src) || !a16(dst)) return KS_EUNSUPPORTED;
+  const int grid = cgrid((long long)N * Ho * Wo * (C / 8), 256);
+#define CALL(T) bilinear_nhwc_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, C, (const T *)src, (T *)dst, accumulate)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_bilinear_nhwc_bwd(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int C, const void *ddst, void *dsrc, int accumulate, void *stream) {
+  KS_CHECK_ARG(N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && ddst && dsrc);
+  if (C % 8 || !a16(ddst) || !a16(dsrc)) return KS_EUNSUPPORTED;
+  const int grid = cgrid((long long)N * Hi * Wi * (C / 8), 256, 16);
+#define CALL(T) bilinear_nhwc_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, C, (const T *)ddst, (T *)dsrc, accumulate)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_relu_fwd(int dtype, int64_t n, const void *x, void *y, void *stream) {
+  KS_CHECK_ARG(n > 0 && x && y);
+  if (n % 8 || !a16(x) || !a16(y)) return KS_EUNSUPPORTED;
+  const int grid = cgrid(n / 8, 256 * 4);
+#define CALL(T) relu_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(n / 8, (const T *)x, (T *)y)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_relu_bwd(int dtype, int64_t n, const void *r, const void *g, void *dx, void *stream) {
+  KS_CHECK_ARG(n > 0 && r && g && dx);
+  if (n % 8 || !a16(r) || !a16(g) || !a16(dx)) return KS_EUNSUPPORTED;
+  const int grid = cgrid(n / 8, 256 * 4);
+#define CALL(T) relu_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(n / 8, (const T *)r, (const T *)g, (T *)dx)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_sigmoid_head_fwd(int dtype, int N, int H, int W, const ks_view_t *z, int K, float *out, void *stream) {
+  KS_CHECK_ARG(N > 0 && H > 0 && W > 0 && z && z->ptr && out && K > 0 && K <= z->C);
+  const long long NP = (long long)N * H * W;
+  const int grid = cgrid(NP, 256);
+#define CALL(T) sigmoid_head_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(to_view(*z), H, W, NP, K, out)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_sigmoid_head_bwd(int dtype, int N, int H, int W, const float *out, const float *dout, int K, const ks_view_t *dz, void *stream) {
+  KS_CHECK_ARG(N > 0 && H > 0 && W > 0 && dz && dz->ptr && out && dout && K > 0 && K <= dz->C);
+  const long long NP = (long long)N * H * W;
+  const int grid = cgrid(NP, 256);
+#define CALL(T) sigmoid_head_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(to_view(*dz), H, W, NP, K, out, dout)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}

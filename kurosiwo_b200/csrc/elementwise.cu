@@ -43,6 +43,7 @@ permute_cast_batched_kernel(const ks_permute_job_t *__restrict__ jobs, const int
     const long long so = r * j.s0 + i1 * j.s1 + i2 * j.s2 + i3 * j.s3;
     float v = (j.src_dtype == KS_F32) ? reinterpret_cast<const float *>(j.src)[so]
                                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(j.src)[so]);
+    if (j.scale != 0.f) v *= j.scale;
     const long long di = j.dst_strided ? (r * j.t0 + i1 * j.t1 + i2 * j.t2 + i3 * j.t3) : i;
     if (j.dst_dtype == KS_F32) {
       float *d = reinterpret_cast<float *>(j.dst) + di;

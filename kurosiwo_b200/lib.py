@@ -94,7 +94,9 @@ EXPORTED_SYMBOLS = [
     "ks_ecam_bwd_apply", "ks_ce_dice_workspace_bytes", "ks_ce_dice_fwd_bwd", "ks_ce_dice_fwd_bwd_ex", "ks_adam_step",
     "ks_softmax_head_fwd", "ks_softmax_head_bwd", "ks_dropout_mask", "ks_channel_scale", "ks_absdiff_fwd", "ks_absdiff_bwd",
     "ks_layernorm_fwd", "ks_layernorm_bwd", "ks_patchify_ln", "ks_patchify_ln_bwd", "ks_vit_assemble", "ks_vit_assemble_bwd",
-    "ks_confusion_update", "ks_attention_fwd", "ks_attention_bwd", "ks_gelu_fwd", "ks_gelu_bwd", "ks_bilinear_up_fwd", "ks_bilinear_up_bwd",
+    "ks_confusion_update", "ks_attention_fwd", "ks_attention_bwd", "ks_conv2d_strided", "ks_conv2d_strided_dgrad", "ks_conv2d_strided_wgrad",
+    "ks_xattention_fwd", "ks_xattention_bwd", "ks_dwconv3x3_fwd", "ks_dwconv3x3_bwd", "ks_bilinear_nhwc_fwd", "ks_bilinear_nhwc_bwd",
+    "ks_relu_fwd", "ks_relu_bwd", "ks_sigmoid_head_fwd", "ks_sigmoid_head_bwd", "ks_gelu_fwd", "ks_gelu_bwd", "ks_bilinear_up_fwd", "ks_bilinear_up_bwd",
 ]
 
 
@@ -147,12 +149,12 @@ class CudaOps:
         self._check(rc, "ks_permute_cast")
 
     def make_permute_table(self, jobs, device):
-        """jobs: list of (src, dst, dims, strides, src_offset[, dst_strides, dst_offset]) -> opaque table for
+        """jobs: list of (src, dst, dims, strides, src_offset[, dst_strides, dst_offset[, scale]]) -> opaque table for
         permute_cast_table (built once).  Without dst_strides the destination is written contiguously."""
         import numpy as np
         rec = np.zeros(len(jobs), dtype=np.dtype([("src", "<u8"), ("dst", "<u8"), ("total", "<i8"), ("s", "<i8", 4),
                                                   ("d", "<i4", 3), ("sdt", "<i4"), ("ddt", "<i4"), ("acc", "<i4"),
-                                                  ("t", "<i8", 4), ("dstr", "<i4"), ("pad", "<i4")], align=True))
+                                                  ("t", "<i8", 4), ("dstr", "<i4"), ("scale", "<f4")], align=True))
         assert rec.dtype.itemsize == 120, rec.dtype.itemsize
         chunks = []
         for i, job in enumerate(jobs):
@@ -165,8 +167,9 @@ class CudaOps:
                 dstr = list(job[5]) + [0] * (4 - len(job[5]))
                 doff = job[6] if len(job) > 6 else 0
                 strided = 1
+            scale = float(job[7]) if len(job) > 7 and job[7] is not None else 0.0          # 0 = no scaling
             rec[i] = (src.data_ptr() + off * src.element_size(), dst.data_ptr() + doff * dst.element_size(), total, st, d[1:],
-                      dtype_code(src.dtype), dtype_code(dst.dtype), 0, dstr, strided, 0)
+                      dtype_code(src.dtype), dtype_code(dst.dtype), 0, dstr, strided, scale)
             chunks += [(i, c0) for c0 in range(0, total, 4096)]
         jobs_dev = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()).to(device)
         chunks_dev = torch.tensor(chunks, dtype=torch.int32, device=device).reshape(-1)
@@ -376,6 +379,70 @@ class CudaOps:
         rc = self.lib.ks_bilinear_up_bwd(dtype_code(dsrc.dtype), C.c_int(B), C.c_int(G), C.c_int(Tp), C.c_int(row0), C.c_int(dsrc.shape[1]),
                                          C.c_int(K), C.c_int(Ho), C.c_int(Wo), _p(ddst), _p(dsrc), self._stream())
         self._check(rc, "ks_bilinear_up_bwd")
+
+    # -- ChangeFormer passes ---------------------------------------------------------------------
+    def conv2d_strided(self, N, Hi, Wi, Ho, Wo, ksize, stride, pad, src: View, weight, bias, dst: View):
+        rc = self.lib.ks_conv2d_strided(dtype_code(src.dtype), *[C.c_int(v) for v in (N, Hi, Wi, Ho, Wo, ksize, stride, pad)], _vp(src), _p(weight),
+                                        _p(bias), _vp(dst), self._stream())
+        self._check(rc, "ks_conv2d_strided")
+
+    def conv2d_strided_dgrad(self, N, Hi, Wi, Ho, Wo, ksize, stride, pad, dy: View, weight, dx: View, accumulate=False):
+        rc = self.lib.ks_conv2d_strided_dgrad(dtype_code(dy.dtype), *[C.c_int(v) for v in (N, Hi, Wi, Ho, Wo, ksize, stride, pad)], _vp(dy),
+                                              _p(weight), _vp(dx), C.c_int(int(accumulate)), self._stream())
+        self._check(rc, "ks_conv2d_strided_dgrad")
+
+    def conv2d_strided_wgrad(self, N, Hi, Wi, Ho, Wo, ksize, stride, pad, x: View, dy: View, dw, accumulate=False):
+        rc = self.lib.ks_conv2d_strided_wgrad(dtype_code(x.dtype), *[C.c_int(v) for v in (N, Hi, Wi, Ho, Wo, ksize, stride, pad)], _vp(x), _vp(dy),
+                                              _p(dw), C.c_int(int(accumulate)), self._stream())
+        self._check(rc, "ks_conv2d_strided_wgrad")
+
+    def xattention_fwd(self, B, Nq, Nk, heads, dh, q, kv, scale, out, probs):
+        rc = self.lib.ks_xattention_fwd(dtype_code(q.dtype), *[C.c_int(v) for v in (B, Nq, Nk, heads, dh)], _p(q), C.c_int64(q.stride(0)), _p(kv),
+                                        C.c_int64(kv.stride(0)), C.c_float(scale), _p(out), C.c_int64(out.stride(0)), _p(probs), self._stream())
+        self._check(rc, "ks_xattention_fwd")
+
+    def xattention_bwd(self, B, Nq, Nk, heads, dh, q, kv, probs, dout, scale, dq, dkv_f32):
+        rc = self.lib.ks_xattention_bwd(dtype_code(q.dtype), *[C.c_int(v) for v in (B, Nq, Nk, heads, dh)], _p(q), C.c_int64(q.stride(0)), _p(kv),
+                                        C.c_int64(kv.stride(0)), _p(probs), _p(dout), C.c_int64(dout.stride(0)), C.c_float(scale), _p(dq),
+                                        C.c_int64(dq.stride(0)), _p(dkv_f32), self._stream())
+        self._check(rc, "ks_xattention_bwd")
+
+    def dwconv3x3_fwd(self, N, H, W, x, w9, bias, y):
+        rc = self.lib.ks_dwconv3x3_fwd(dtype_code(x.dtype), C.c_int(N), C.c_int(H), C.c_int(W), C.c_int(x.shape[-1]), _p(x), _p(w9), _p(bias), _p(y),
+                                       self._stream())
+        self._check(rc, "ks_dwconv3x3_fwd")
+
+    def dwconv3x3_bwd(self, N, H, W, x, dy, w9, dx, dw9, dbias):
+        rc = self.lib.ks_dwconv3x3_bwd(dtype_code(x.dtype), C.c_int(N), C.c_int(H), C.c_int(W), C.c_int(x.shape[-1]), _p(x), _p(dy), _p(w9), _p(dx),
+                                       _p(dw9), _p(dbias), self._stream())
+        self._check(rc, "ks_dwconv3x3_bwd")
+
+    def bilinear_nhwc_fwd(self, N, Hi, Wi, Ho, Wo, src, dst, accumulate=False):
+        rc = self.lib.ks_bilinear_nhwc_fwd(dtype_code(src.dtype), *[C.c_int(v) for v in (N, Hi, Wi, Ho, Wo, src.shape[-1])], _p(src), _p(dst),
+                                           C.c_int(int(accumulate)), self._stream())
+        self._check(rc, "ks_bilinear_nhwc_fwd")
+
+    def bilinear_nhwc_bwd(self, N, Hi, Wi, Ho, Wo, ddst, dsrc, accumulate=False):
+        rc = self.lib.ks_bilinear_nhwc_bwd(dtype_code(ddst.dtype), *[C.c_int(v) for v in (N, Hi, Wi, Ho, Wo, ddst.shape[-1])], _p(ddst), _p(dsrc),
+                                           C.c_int(int(accumulate)), self._stream())
+        self._check(rc, "ks_bilinear_nhwc_bwd")
+
+    def relu_fwd(self, x, y):
+        rc = self.lib.ks_relu_fwd(dtype_code(x.dtype), C.c_int64(x.numel()), _p(x), _p(y), self._stream())
+        self._check(rc, "ks_relu_fwd")
+
+    def relu_bwd(self, r, g, dx):
+        rc = self.lib.ks_relu_bwd(dtype_code(r.dtype), C.c_int64(r.numel()), _p(r), _p(g), _p(dx), self._stream())
+        self._check(rc, "ks_relu_bwd")
+
+    def sigmoid_head_fwd(self, z: View, K: int, out: torch.Tensor):
+        rc = self.lib.ks_sigmoid_head_fwd(dtype_code(z.dtype), C.c_int(z.N), C.c_int(z.H), C.c_int(z.W), _vp(z), C.c_int(K), _p(out), self._stream())
+        self._check(rc, "ks_sigmoid_head_fwd")
+
+    def sigmoid_head_bwd(self, out: torch.Tensor, dout: torch.Tensor, K: int, dz: View):
+        rc = self.lib.ks_sigmoid_head_bwd(dtype_code(dz.dtype), C.c_int(dz.N), C.c_int(dz.H), C.c_int(dz.W), _p(out), _p(dout), C.c_int(K), _vp(dz),
+                                          self._stream())
+        self._check(rc, "ks_sigmoid_head_bwd")
 
     # -- loss --------------------------------------------------------------------------------
     def ce_dice_workspace(self, N: int, device) -> torch.Tensor:

@@ -49,6 +49,8 @@ class ShadowOps:
     def permute_cast_table(self, table):
         for job in table:
             src, dst, dims, strides, off = job[:5]
+            if len(job) > 7 and job[7] is not None:          # value multiplier
+                src = src.float() * float(job[7])
             if len(job) > 5 and job[5] is not None:
                 d = list(dims) + [1] * (4 - len(dims))
                 tmp = torch.zeros(d[0] * d[1] * d[2] * d[3], dtype=torch.float32)
@@ -455,3 +457,101 @@ class ShadowOps:
         t, p = labels.reshape(-1), pred.reshape(-1).long()
         keep = t != ignore_index
         mat.view(-1).add_(torch.bincount(t[keep] * K + p[keep], minlength=K * K))
+
+    # -- ChangeFormer passes ---------------------------------------------------------------------
+    @staticmethod
+    def _w_oihw(weight, k, cout, cin):
+        return weight.float().view(k * k, cout, cin).permute(1, 2, 0).reshape(cout, cin, k, k)
+
+    def conv2d_strided(self, N, Hi, Wi, Ho, Wo, ksize, stride, pad, src, weight, bias, dst):
+        x = _t(src).float().permute(0, 3, 1, 2)
+        y = F.conv2d(x, self._w_oihw(weight, ksize, dst.C, src.C), None if bias is None else bias.float(), stride=stride, padding=pad)
+        t = _t(dst)
+        t.copy_(y.permute(0, 2, 3, 1).to(t.dtype))
+
+    def conv2d_strided_dgrad(self, N, Hi, Wi, Ho, Wo, ksize, stride, pad, dy, weight, dx, accumulate=False):
+        g = _t(dy).float().permute(0, 3, 1, 2)
+        v = torch.nn.grad.conv2d_input((N, dx.C, Hi, Wi), self._w_oihw(weight, ksize, dy.C, dx.C), g, stride=stride, padding=pad).permute(0, 2, 3, 1)
+        t = _t(dx)
+        t.copy_((t.float() + v if accumulate else v).to(t.dtype))
+
+    def conv2d_strided_wgrad(self, N, Hi, Wi, Ho, Wo, ksize, stride, pad, x, dy, dw, accumulate=False):
+        xx, g = _t(x).float().permute(0, 3, 1, 2), _t(dy).float().permute(0, 3, 1, 2)
+        gw = torch.nn.grad.conv2d_weight(xx, (dy.C, x.C, ksize, ksize), g, stride=stride, padding=pad)
+        gw = gw.reshape(dy.C, x.C, ksize * ksize).permute(2, 0, 1).reshape(-1)
+        out = dw.reshape(-1)[: gw.numel()]
+        out.copy_(gw + out if accumulate else gw)
+
+    @staticmethod
+    def _xa_split(B, Nq, Nk, heads, dh, q, kv):
+        inner = heads * dh
+        qq = q.float()[:, :inner].reshape(B, Nq, heads, dh).permute(0, 2, 1, 3)
+        k = kv.float()[:, :inner].reshape(B, Nk, heads, dh).permute(0, 2, 1, 3)
+        v = kv.float()[:, inner:2 * inner].reshape(B, Nk, heads, dh).permute(0, 2, 1, 3)
+        return qq, k, v
+
+    def xattention_fwd(self, B, Nq, Nk, heads, dh, q, kv, scale, out, probs):
+        qq, k, v = self._xa_split(B, Nq, Nk, heads, dh, q, kv)
+        p = torch.softmax(qq @ k.transpose(-1, -2) * scale, dim=-1).to(probs.dtype)
+        probs.copy_(p.reshape(probs.shape))
+        out[:, :heads * dh] = (p.float() @ v).permute(0, 2, 1, 3).reshape(B * Nq, heads * dh).to(out.dtype)
+
+    def xattention_bwd(self, B, Nq, Nk, heads, dh, q, kv, probs, dout, scale, dq, dkv_f32):
+        inner = heads * dh
+        qq, k, v = self._xa_split(B, Nq, Nk, heads, dh, q, kv)
+        p = probs.float().view(B, heads, Nq, Nk)
+        do = dout.float()[:, :inner].reshape(B, Nq, heads, dh).permute(0, 2, 1, 3)
+        dv = p.transpose(-1, -2) @ do
+        dp = do @ v.transpose(-1, -2)
+        ds = p * (dp - (dp * p).sum(-1, keepdim=True)) * scale
+        dq[:, :inner] = (ds @ k).permute(0, 2, 1, 3).reshape(B * Nq, inner).to(dq.dtype)
+        dk = ds.transpose(-1, -2) @ qq
+        dkv_f32.view(B * Nk, 2 * inner)[:, :inner] = dk.permute(0, 2, 1, 3).reshape(B * Nk, inner)
+        dkv_f32.view(B * Nk, 2 * inner)[:, inner:] = dv.permute(0, 2, 1, 3).reshape(B * Nk, inner)
+
+    def dwconv3x3_fwd(self, N, H, W, x, w9, bias, y):
+        Cn = x.shape[-1]
+        xx = x.float().view(N, H, W, Cn).permute(0, 3, 1, 2)
+        w = w9.float().view(9, Cn).t().reshape(Cn, 1, 3, 3)
+        o = F.conv2d(xx, w, None if bias is None else bias.float(), padding=1, groups=Cn).permute(0, 2, 3, 1)
+        y.copy_(o.reshape(y.shape).to(y.dtype))
+
+    def dwconv3x3_bwd(self, N, H, W, x, dy, w9, dx, dw9, dbias):
+        Cn = x.shape[-1]
+        with torch.enable_grad():
+            xx = x.float().view(N, H, W, Cn).permute(0, 3, 1, 2).detach().requires_grad_(True)
+            w = w9.float().view(9, Cn).t().reshape(Cn, 1, 3, 3).detach().requires_grad_(True)
+            o = F.conv2d(xx, w, None, padding=1, groups=Cn)
+            gx, gw = torch.autograd.grad(o, (xx, w), dy.float().view(N, H, W, Cn).permute(0, 3, 1, 2))
+        dx.copy_(gx.permute(0, 2, 3, 1).reshape(dx.shape).to(dx.dtype))
+        dw9.view(9, Cn).add_(gw.reshape(Cn, 9).t())
+        if dbias is not None:
+            dbias.add_(dy.float().reshape(-1, Cn).sum(0))
+
+    def bilinear_nhwc_fwd(self, N, Hi, Wi, Ho, Wo, src, dst, accumulate=False):
+        Cn = src.shape[-1]
+        v = F.interpolate(src.float().view(N, Hi, Wi, Cn).permute(0, 3, 1, 2), size=(Ho, Wo), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+        v = v.reshape(dst.shape)
+        dst.copy_((dst.float() + v if accumulate else v).to(dst.dtype))
+
+    def bilinear_nhwc_bwd(self, N, Hi, Wi, Ho, Wo, ddst, dsrc, accumulate=False):
+        Cn = ddst.shape[-1]
+        with torch.enable_grad():
+            m = torch.zeros(N, Cn, Hi, Wi, requires_grad=True)
+            F.interpolate(m, size=(Ho, Wo), mode="bilinear", align_corners=False).backward(ddst.float().view(N, Ho, Wo, Cn).permute(0, 3, 1, 2))
+        v = m.grad.permute(0, 2, 3, 1).reshape(dsrc.shape)
+        dsrc.copy_((dsrc.float() + v if accumulate else v).to(dsrc.dtype))
+
+    def relu_fwd(self, x, y):
+        y.copy_(F.relu(x.float()).to(y.dtype))
+
+    def relu_bwd(self, r, g, dx):
+        dx.copy_((g.float() * (r.float() > 0)).to(dx.dtype))
+
+    def sigmoid_head_fwd(self, z, K, out):
+        out.copy_(torch.sigmoid(_t(z).float()[..., :K].permute(0, 3, 1, 2)))
+
+    def sigmoid_head_bwd(self, out, dout, K, dz):
+        t = _t(dz)
+        t.zero_()
+        t[..., :K].copy_((dout * out * (1 - out)).permute(0, 2, 3, 1).to(t.dtype))
