@@ -36,6 +36,10 @@ WORKLOADS = {
     "siam-conc": dict(metric="SAR patches/sec (224x224x6ch, bs=4) FC-Siam-conc train step", batch=4, gflop=22.2, task="cd", method="siam-conc",
                       lr=1e-5, desc="siam-conc (1.55M params, Dropout2d p=0.2 on) train step: fwd + CE+Dice(+argmax) + bwd + allreduce + Adam; "
                                     "inputs pre_event_1,post_event (BASELINE.json configs[0] shape)"),
+    "changeformer": dict(metric="SAR patches/sec (224x224x6ch, bs=32) ChangeFormerV6 train step", batch=32, gflop=636.0, task="cd",
+                         method="changeformer", lr=6e-4,
+                         desc="ChangeFormerV6 (embed 256, 41.0M params; stochastic layers p=0) train step: fwd + CE+Dice(+argmax) on the last "
+                              "sigmoid output + bwd + allreduce + SGD(momentum 0.99); inputs pre_event_1,post_event (BASELINE.json configs[2] shape)"),
     "floodvit": dict(metric="SAR patches/sec (224x224x6ch, bs=64) FloodViT-B train step", batch=64, gflop=106.1, task="segmentation",
                      method="finetune", lr=1e-4,
                      desc="FloodViT: ViT-B/16 encoder (6 channels, 86.4M params) + linear FinetunerSegmentation head, train step: fwd + "
@@ -225,6 +229,8 @@ def run_ours(args):
                "num_channels": 2, "loss_function": "ce+dice", "class_weights": [1.0, 1.0, 1.0], "method": wl["method"], "epochs": 1,
                "precision": args.precision, "task": wl["task"], "resume_checkpoint": False}
     model_configs = {"method": wl["method"], "optimizer": "adam", "learning_rate": wl["lr"], "lr_schedule": None, "base_channel": 32}
+    if wl["method"] == "changeformer":
+        model_configs.update({"optimizer": "sgd", "momentum": 0.99, "weight_decay": 1e-5, "embed_dim": 256, "decoder_softmax": True})
     host_batches = [synthetic.make_batch(999 + rank + 1000 * i, bs, H, W, pin=True) for i in range(2)]
     b0 = host_batches[0]
     if wl["task"] == "cd":

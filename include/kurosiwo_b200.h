@@ -338,6 +338,11 @@ int ks_adam_step(float *p, const float *g, float *m, float *v, int64_t n,
                  float lr, float beta1, float beta2, float eps, float weight_decay,
                  float grad_scale, int *step_ptr, void *stream);
 
+/* torch.optim.SGD(lr, momentum, weight_decay) (change_detection_trainer.py:61-66; ChangeFormer: momentum 0.99, wd 1e-5,
+ * configs/method/changeformer/changeformer.json): g = grad_scale*g + wd*p; buf = momentum*buf + g; p -= lr*buf. */
+int ks_sgd_step(float *p, const float *g, float *buf, int64_t n, float lr, float momentum, float weight_decay, float grad_scale,
+                void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@ from typing import Optional
 
 import torch
 
+from .changeformer import ChangeFormerV6
 from .siam_unet import _SiamUnet
 from .snunet import SNUNet_ECAM
 from .utilities import ConfusionMetrics, create_loss, init_lr_scheduler
@@ -52,14 +53,15 @@ class FusedStepper:
     """Owns the engine-side training state for one model/batch geometry (the public fast path)."""
 
     def __init__(self, model, configs, model_configs, process_group=None):
-        if not isinstance(model, (SNUNet_ECAM, _SiamUnet)):
-            raise TypeError("the fused step is implemented for kurosiwo_b200's SNUNet_ECAM, SiamUnet_conc and SiamUnet_diff")
+        if not isinstance(model, (SNUNet_ECAM, _SiamUnet, ChangeFormerV6)):
+            raise TypeError("the fused step is implemented for kurosiwo_b200's SNUNet_ECAM, SiamUnet_conc/diff and ChangeFormerV6")
         if configs.get("loss_function", "ce+dice") not in ("ce+dice", "cross_entropy"):
             raise NotImplementedError("the fused step computes CE+Dice (utilities/bce_and_dice.py) or plain cross-entropy "
                                       "(utilities/utilities.py:308-321); other losses are outside the B200 hot path")
         opt = model_configs.get("optimizer", "adam")
-        if opt != "adam":
-            raise NotImplementedError(f"fused optimizer '{opt}' (only 'adam': change_detection_trainer.py:52-54)")
+        if opt not in ("adam", "sgd"):
+            raise NotImplementedError(f"fused optimizer '{opt}' ('adam': change_detection_trainer.py:52-54, 'sgd': :61-66)")
+        self.opt = opt
         self.model, self.configs, self.model_configs, self.pg = model, configs, model_configs, process_group
         self.engine = None
         self.lr = float(model_configs["learning_rate"])
@@ -68,7 +70,10 @@ class FusedStepper:
         eng = self.model.engine(x)
         if eng is not self.engine:
             eng.init_training(class_weights=self.configs.get("class_weights", [1.0, 1.0, 1.0]), ignore_index=3, lr=self.lr,
-                              betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,      # reference Adam gets only lr (:52-54)
+                              betas=(0.9, 0.999), eps=1e-8,
+                              # the reference's Adam gets only lr (:52-54); its SGD gets momentum and weight_decay (:61-66)
+                              weight_decay=float(self.model_configs.get("weight_decay", 0.0)) if self.opt == "sgd" else 0.0,
+                              optimizer=self.opt, momentum=float(self.model_configs.get("momentum", 0.0)),
                               process_group=self.pg,
                               dice_weight=0.0 if self.configs.get("loss_function") == "cross_entropy" else 1.0)
             self.engine = eng
@@ -151,6 +156,8 @@ def eval_change_detection(model, loader, settype, configs=None, model_configs=No
             inputs = select_inputs(b, configs, device)
             mask = b["mask"].to(device, non_blocking=True)
             output = model(*inputs)
+            if isinstance(output, (list, tuple)):       # ChangeFormer returns [p_c4, p_c3, p_c2, p_c1, cp]; the last is used (:396)
+                output = output[-1]
             loss = criterion(output, mask)
             pred = getattr(criterion, "last_pred", None)
             predictions = pred if pred is not None else output.argmax(1)

@@ -761,6 +761,29 @@ extern "C" int ks_channel_sum(int dtype, int N, int H, int W, const ks_view_t *x
   KS_LAUNCH_RET();
 }
 
+namespace ks {
+// torch.optim.SGD (dampening 0, no nesterov): g += wd*p; buf = momentum*buf + g (buf starts at 0 == torch's first-step clone); p -= lr*buf
+__global__ void __launch_bounds__(256)
+sgd_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ buf, long long n, float lr, float momentum, float wd, float gscale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float pv = p[i];
+    const float gk = g[i] * gscale + wd * pv;
+    const float b = momentum * buf[i] + gk;
+    buf[i] = b;
+    p[i] = pv - lr * b;
+  }
+}
+}  // namespace ks
+
+extern "C" int ks_sgd_step(float *p, const float *g, float *buf, int64_t n, float lr, float momentum, float weight_decay, float grad_scale,
+                           void *stream) {
+  KS_CHECK_ARG(p && g && buf && n > 0);
+  long long grid = (n + 256 * 4 - 1) / (256 * 4);
+  if (grid > ks::kNumSMs * 8) grid = ks::kNumSMs * 8;
+  ks::sgd_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(p, g, buf, n, lr, momentum, weight_decay, grad_scale);
+  KS_LAUNCH_RET();
+}
+
 extern "C" int ks_adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2,
                             float eps, float weight_decay, float grad_scale, int *step_ptr, void *stream) {
   KS_CHECK_ARG(p && g && m && v && step_ptr && n > 0);

@@ -73,13 +73,16 @@ class TrainStepMixin:
     # ------------------------------------------------------------------------------------------
     def init_training(self, class_weights=(1.0, 1.0, 1.0), ignore_index: int = 3, lr: float = 1e-3,
                       betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, process_group=None,
-                      dice_weight: float = 1.0):
+                      dice_weight: float = 1.0, optimizer: str = "adam", momentum: float = 0.0):
         dev = self.device
         self.params.ensure(dev)
         self.cw = torch.tensor(class_weights, dtype=torch.float32, device=dev)
         self.ignore_index = ignore_index
         self.dice_weight = float(dice_weight)     # 1: CE+Dice (utilities/bce_and_dice.py), 0: plain cross-entropy (the reference default)
-        self.hp = dict(lr=lr, b1=betas[0], b2=betas[1], eps=eps, wd=weight_decay)
+        self.hp = dict(lr=lr, b1=betas[0], b2=betas[1], eps=eps, wd=weight_decay, momentum=momentum)
+        if optimizer not in ("adam", "sgd"):
+            raise NotImplementedError(f"fused optimizer '{optimizer}' (adam: change_detection_trainer.py:52-54, sgd: :61-66)")
+        self.optimizer = optimizer
         self.adam_m = torch.zeros_like(self.params.flat)
         self.adam_v = torch.zeros_like(self.params.flat)
         self.adam_step = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -110,6 +113,9 @@ class TrainStepMixin:
 
     def _optimizer(self):
         hp = self.hp
+        if self.optimizer == "sgd":
+            self.ops.sgd_step(self.params.flat, self.params.grad, self.adam_m, hp["lr"], hp["momentum"], hp["wd"], 1.0 / self.world)
+            return
         self.ops.adam_step(self.params.flat, self.params.grad, self.adam_m, self.adam_v, hp["lr"], hp["b1"], hp["b2"], hp["eps"],
                            hp["wd"], 1.0 / self.world, self.adam_step)
 

@@ -91,7 +91,7 @@ EXPORTED_SYMBOLS = [
     "ks_version", "ks_error_string", "ks_set_option", "ks_permute_cast", "ks_permute_cast_batched", "ks_conv2d", "ks_conv2d_wgrad", "ks_stem_conv3x3", "ks_stem_wgrad3x3",
     "ks_bn_stats", "ks_bn_finalize", "ks_bn_act", "ks_bn_bwd_reduce", "ks_bn_bwd_apply", "ks_maxpool2x2_bwd",
     "ks_channel_sum", "ks_ecam_pool", "ks_ecam_gates", "ks_ecam_final", "ks_ecam_bwd_reduce", "ks_ecam_gates_bwd",
-    "ks_ecam_bwd_apply", "ks_ce_dice_workspace_bytes", "ks_ce_dice_fwd_bwd", "ks_ce_dice_fwd_bwd_ex", "ks_adam_step",
+    "ks_ecam_bwd_apply", "ks_ce_dice_workspace_bytes", "ks_ce_dice_fwd_bwd", "ks_ce_dice_fwd_bwd_ex", "ks_adam_step", "ks_sgd_step",
     "ks_softmax_head_fwd", "ks_softmax_head_bwd", "ks_dropout_mask", "ks_channel_scale", "ks_absdiff_fwd", "ks_absdiff_bwd",
     "ks_layernorm_fwd", "ks_layernorm_bwd", "ks_patchify_ln", "ks_patchify_ln_bwd", "ks_vit_assemble", "ks_vit_assemble_bwd",
     "ks_confusion_update", "ks_attention_fwd", "ks_attention_bwd", "ks_conv2d_strided", "ks_conv2d_strided_dgrad", "ks_conv2d_strided_wgrad",
@@ -467,6 +467,11 @@ class CudaOps:
         rc = self.lib.ks_adam_step(_p(p), _p(g), _p(m), _p(v), C.c_int64(p.numel()), C.c_float(lr), C.c_float(b1), C.c_float(b2),
                                    C.c_float(eps), C.c_float(wd), C.c_float(grad_scale), _p(step), self._stream())
         self._check(rc, "ks_adam_step")
+
+    def sgd_step(self, p, g, buf, lr, momentum, wd, grad_scale):
+        rc = self.lib.ks_sgd_step(_p(p), _p(g), _p(buf), C.c_int64(p.numel()), C.c_float(lr), C.c_float(momentum), C.c_float(wd),
+                                  C.c_float(grad_scale), self._stream())
+        self._check(rc, "ks_sgd_step")
 
     # -- misc memory ops (plumbing through torch) ----------------------------------------------
     def zero_(self, t: torch.Tensor):

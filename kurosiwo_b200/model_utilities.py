@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import torch
 
+from .changeformer import ChangeFormerV6
 from .siam_unet import SiamUnet_conc, SiamUnet_diff
 from .snunet import SNUNet_ECAM
 from .vision_transformer import FinetunerSegmentation, ViT  # noqa: F401
@@ -16,12 +17,15 @@ def initialize_cd_model(configs, model_configs, phase="train"):
         model = SiamUnet_conc(input_nbr=configs["num_channels"], label_nbr=configs["num_classes"], precision=precision)
     elif method == "siam-diff":                            # model_utilities.py:187-190
         model = SiamUnet_diff(input_nbr=configs["num_channels"], label_nbr=configs["num_classes"], precision=precision)
+    elif method == "changeformer":                         # model_utilities.py:199-205
+        model = ChangeFormerV6(embed_dim=model_configs["embed_dim"], input_nc=configs["num_channels"], output_nc=configs["num_classes"],
+                               decoder_softmax=model_configs["decoder_softmax"], precision=precision)
     elif method == "snunet":
         model = SNUNet_ECAM(configs["num_channels"], configs["num_classes"], base_channel=model_configs["base_channel"],
                             precision=precision)
     else:
         raise NotImplementedError(f"method {configs['method']} is not on the B200 hot path yet (SURVEY.md §8: "
-                                  "changeformer and finetune are 'next' rows)")
+                                  "bit-cd, hfa-net, adhr-cdnet and transunet-cd are outside it)")
     model = model.to(configs["device"])
     if configs.get("resume_checkpoint"):
         checkpoint = torch.load(configs["resume_checkpoint"], map_location=configs["device"])

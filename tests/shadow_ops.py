@@ -555,3 +555,8 @@ class ShadowOps:
         t = _t(dz)
         t.zero_()
         t[..., :K].copy_((dout * out * (1 - out)).permute(0, 2, 3, 1).to(t.dtype))
+
+    def sgd_step(self, p, g, buf, lr, momentum, wd, grad_scale):
+        gg = g * grad_scale + wd * p
+        buf.mul_(momentum).add_(gg)
+        p.add_(buf, alpha=-lr)
