@@ -24,11 +24,16 @@ __global__ void __launch_bounds__(256)
 conv_gen_kernel(View src, View dst, int N, int Hs, int Ws, int Hd, int Wd, int ksize, int stride, int pad, int Cin, int Cout,
                 const T *__restrict__ weight, const float *__restrict__ bias, int accumulate) {
   // src/dst: MODE 0 src = x [N,Hs,Ws,Cin], dst = out [N,Hd,Wd,Cout];  MODE 1 src = dy [N,Hs,Ws,Cout], dst = dx [N,Hd,Wd,Cin]
+  // MODE 1 runs one grid.z slice per input-pixel PHASE (h % stride, w % stride): all pixels of a slice share the set of taps that
+  // divide evenly, (ky, kx) = (ky0 + i*stride, kx0 + j*stride), so only those k^2/stride^2 taps are visited (1 tap when k == stride).
   __shared__ float As[GBK][GBM + 4];
   __shared__ float Bs[GBK][GBN + 4];
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
-  const long long M = (long long)N * Hd * Wd;
+  const int ph = (MODE == 1) ? (int)blockIdx.z / stride : 0, pw = (MODE == 1) ? (int)blockIdx.z % stride : 0;
+  const int Hp = (MODE == 1) ? (Hd - ph + stride - 1) / stride : Hd, Wp = (MODE == 1) ? (Wd - pw + stride - 1) / stride : Wd;
+  const long long M = (long long)N * Hp * Wp;
   const long long m0 = (long long)blockIdx.x * GBM;
+  if (m0 >= M) return;
   const int n0 = blockIdx.y * GBN;
   const int CK = (MODE == 0) ? Cin : Cout;      // reduction channels
   const int CN = (MODE == 0) ? Cout : Cin;      // output channels
@@ -36,56 +41,58 @@ conv_gen_kernel(View src, View dst, int N, int Hs, int Ws, int Hd, int Wd, int k
   const long long lm = m0 + lrow;
   const bool lm_ok = lm < M;
   int ln = 0, lh = 0, lw = 0;
-  if (lm_ok) { lw = (int)(lm % Wd); long long r = lm / Wd; lh = (int)(r % Hd); ln = (int)(r / Hd); }
+  if (lm_ok) { lw = (int)(lm % Wp); long long r = lm / Wp; lh = (int)(r % Hp); ln = (int)(r / Hp); }
+  if (MODE == 1) { lh = lh * stride + ph; lw = lw * stride + pw; }
   const int lcn = n0 + lrow;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int tap = 0; tap < ksize * ksize; ++tap) {
-    const int ky = tap / ksize, kx = tap % ksize;
-    int hh, ww; bool pix_ok = lm_ok;
-    if (MODE == 0) { hh = lh * stride - pad + ky; ww = lw * stride - pad + kx; }
-    else {
-      const int th = lh + pad - ky, tw = lw + pad - kx;
-      pix_ok = pix_ok && th >= 0 && tw >= 0 && (th % stride) == 0 && (tw % stride) == 0;
-      hh = th / stride; ww = tw / stride;
-    }
-    pix_ok = pix_ok && hh >= 0 && hh < Hs && ww >= 0 && ww < Ws;
-    const T *xp = reinterpret_cast<const T *>(src.ptr) + ((long long)ln * src.sn + (long long)hh * src.sh + (long long)ww * src.sw);
-    const T *wt = weight + (long long)tap * Cout * Cin;
-    for (int c0 = 0; c0 < CK; c0 += GBK) {
+  const int ky0 = (MODE == 1) ? (ph + pad) % stride : 0, kx0 = (MODE == 1) ? (pw + pad) % stride : 0;
+  const int kstep = (MODE == 1) ? stride : 1;
+  for (int ky = ky0; ky < ksize; ky += kstep) {
+    for (int kx = kx0; kx < ksize; kx += kstep) {
+      const int tap = ky * ksize + kx;
+      int hh, ww;
+      if (MODE == 0) { hh = lh * stride - pad + ky; ww = lw * stride - pad + kx; }
+      else { hh = (lh + pad - ky) / stride; ww = (lw + pad - kx) / stride; }       // exact by construction; may be negative -> masked
+      const bool pix_ok = lm_ok && (MODE == 0 || (lh + pad - ky >= 0 && lw + pad - kx >= 0)) && hh >= 0 && hh < Hs && ww >= 0 && ww < Ws;
+      const T *xp = reinterpret_cast<const T *>(src.ptr) + ((long long)ln * src.sn + (long long)hh * src.sh + (long long)ww * src.sw);
+      const T *wt = weight + (long long)tap * Cout * Cin;
+      for (int c0 = 0; c0 < CK; c0 += GBK) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = c0 + lk + i;
-        float a = 0.f, b = 0.f;
-        if (c < CK) {
-          if (pix_ok) a = Cvt<T>::ld(xp + c);
-          if (lcn < CN) b = Cvt<T>::ld(MODE == 0 ? (wt + (long long)lcn * Cin + c) : (wt + (long long)c * Cin + lcn));
+        for (int i = 0; i < 4; ++i) {
+          const int c = c0 + lk + i;
+          float a = 0.f, b = 0.f;
+          if (c < CK) {
+            if (pix_ok) a = Cvt<T>::ld(xp + c);
+            if (lcn < CN) b = Cvt<T>::ld(MODE == 0 ? (wt + (long long)lcn * Cin + c) : (wt + (long long)c * Cin + lcn));
+          }
+          As[lk + i][lrow] = a;
+          Bs[lk + i][lrow] = b;
         }
-        As[lk + i][lrow] = a;
-        Bs[lk + i][lrow] = b;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GBK; ++k) {
+          const float4 a4 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+          const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+          const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
       }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < GBK; ++k) {
-        const float4 a4 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
-        const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
-        const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-      }
-      __syncthreads();
     }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const long long m = m0 + ty * 4 + i;
     if (m >= M) continue;
-    const int w = (int)(m % Wd); long long r = m / Wd; const int h = (int)(r % Hd); const int n = (int)(r / Hd);
+    int w = (int)(m % Wp); long long r = m / Wp; int h = (int)(r % Hp); const int n = (int)(r / Hp);
+    if (MODE == 1) { h = h * stride + ph; w = w * stride + pw; }
     T *op = reinterpret_cast<T *>(dst.ptr) + ((long long)n * dst.sn + (long long)h * dst.sh + (long long)w * dst.sw);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -541,8 +548,8 @@ extern "C" int ks_conv2d_strided(int dtype, int N, int Hi, int Wi, int Ho, int W
 extern "C" int ks_conv2d_strided_dgrad(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int ksize, int stride, int pad, const ks_view_t *dy,
                                        const void *weight, const ks_view_t *dx, int accumulate, void *stream) {
   KS_CHECK_ARG(dy && dx && weight && N > 0 && ksize >= 1 && ksize <= 8 && stride >= 1 && pad >= 0);
-  const long long M = (long long)N * Hi * Wi;
-  dim3 grid((unsigned)((M + GBM - 1) / GBM), (unsigned)((dx->C + GBN - 1) / GBN));
+  const long long M = (long long)N * ((Hi + stride - 1) / stride) * ((Wi + stride - 1) / stride);        // pixels of the largest phase
+  dim3 grid((unsigned)((M + GBM - 1) / GBM), (unsigned)((dx->C + GBN - 1) / GBN), (unsigned)(stride * stride));
 #define CALL(T) conv_gen_kernel<T, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(to_view(*dy), to_view(*dx), N, Ho, Wo, Hi, Wi, ksize, stride, pad, \
                                                                              dx->C, dy->C, (const T *)weight, nullptr, accumulate)
   KS_DISPATCH_T(dtype, CALL);
