@@ -30,7 +30,7 @@ from .lib import IMPL_SIMT, View
 
 EMBED_DIMS, DEPTHS, HEADS, SR = [64, 128, 320, 512], [3, 3, 4, 3], [1, 2, 4, 8], [8, 4, 2, 1]
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
-HEAD_PAD = 16
+HEAD_PAD = 32          # classifier Cout padded to 32: both its data- and weight-gradient convs then take the tcgen05 path (C % 32 == 0)
 # (output phase a, input offset di, kernel index ky) per axis of ConvTranspose2d(k4, s2, p1)
 UP4_TERMS = [(0, 0, 1), (0, -1, 3), (1, 0, 2), (1, 1, 0)]
 
