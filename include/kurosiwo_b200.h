@@ -285,9 +285,23 @@ int ks_conv2d_strided_wgrad(int dtype, int N, int Hi, int Wi, int Ho, int Wo, in
  * columns h*dh.. and v at heads*dh + h*dh..; out = softmax(q k^T * scale) v; probs [B][heads][Nq][Nk] kept for the backward.
  * Nk <= 64, dh <= 96.  _bwd writes dq and ACCUMULATES dk|dv into the fp32 buffer dkv [B*Nk][2*heads*dh] (zeroed by the call). */
 int ks_xattention_fwd(int dtype, int B, int Nq, int Nk, int heads, int dh, const void *q, int64_t ldq, const void *kv, int64_t ldkv,
-                      float scale, void *out, int64_t ldo, void *probs, void *stream);
+                      float scale, void *out, int64_t ldo, void *probs, float pdrop, uint64_t seed, const int *step_ptr, int site,
+                      void *stream);
 int ks_xattention_bwd(int dtype, int B, int Nq, int Nk, int heads, int dh, const void *q, int64_t ldq, const void *kv, int64_t ldkv,
-                      const void *probs, const void *dout, int64_t ldo, float scale, void *dq, int64_t lddq, float *dkv, void *stream);
+                      const void *probs, const void *dout, int64_t ldo, float scale, void *dq, int64_t lddq, float *dkv,
+                      float pdrop, uint64_t seed, const int *step_ptr, int site, void *stream);
+/* Stochastic regularisers of the ChangeFormer encoder (changeformer.py:652-654).  Every mask is a pure function of
+ * (seed, *step_ptr, site, element index) - nothing is stored, the backward regenerates it; step_ptr is a DEVICE counter so a
+ * captured CUDA graph draws fresh masks per replay.  pdrop of ks_xattention_* is attn_drop (:203) on the probabilities used for P.V.
+ * ks_dropout_apply: y = x * keep/(1-p)                                   nn.Dropout after GELU (:129-130) and its backward
+ * ks_branch_add:    x += droppath[sample] * keep/(1-p) * t               x = x + drop_path(dropout(branch)) (:246-247; :131-132,206)
+ * ks_branch_scale:  dt = droppath[sample] * keep/(1-p) * dx              its backward (gradient of the branch output)
+ * droppath: fp32 [samples] factors 0 or 1/(1-p_path) from ks_dropout_mask (may be NULL); per_sample = elements per sample. */
+int ks_dropout_apply(int dtype, int64_t n, const void *x, void *y, float p, uint64_t seed, const int *step_ptr, int site, void *stream);
+int ks_branch_add(int dtype, int64_t n, int64_t per_sample, void *x, const void *t, float p, const float *droppath, uint64_t seed,
+                  const int *step_ptr, int site, void *stream);
+int ks_branch_scale(int dtype, int64_t n, int64_t per_sample, const void *dx, void *dt, float p, const float *droppath, uint64_t seed,
+                    const int *step_ptr, int site, void *stream);
 /* Depth-wise 3x3 conv, padding 1 (DWConv, changeformer.py:84-96) on dense NHWC; w9: fp32 [9][C] (tap-major), bias fp32 [C].
  * _bwd: dx = data gradient; dw9 += weight gradient, dbias += bias gradient (fp32 atomics, caller zeroes). */
 int ks_dwconv3x3_fwd(int dtype, int N, int H, int W, int C, const void *x, const float *w9, const float *bias, void *y, void *stream);

@@ -7,7 +7,8 @@ convd1x,dense_1x,change_probability}`), same initialisation rules (changeformer.
 `model(x1, x2)` returns the LIST [p_c4, p_c3, p_c2, p_c1, cp] of post-Sigmoid maps whose last element the trainer uses
 (change_detection_trainer.py:148,166).  The sub-modules are parameter containers; the arithmetic runs in the sm_100a kernels
 behind `ChangeFormerEngine` (cformer_engine.py).  There is no eager/CPU fallback.
-Round-1 restriction: Dropout / attention dropout / DropPath (0.1 each in the reference, :652-654) run with p = 0.
+Dropout / attention dropout / DropPath (0.1 each, :652-654) are active in train mode with a device-side stateless RNG
+(`model.drop_rate`, `model.attn_drop`, `model.drop_path_rate`; set them to 0 for deterministic parity runs).
 """
 from __future__ import annotations
 
@@ -198,7 +199,7 @@ class ChangeFormerV6(nn.Module):
     def __init__(self, input_nc=3, output_nc=2, decoder_softmax=False, embed_dim=256, precision="bf16"):
         super().__init__()
         self.embed_dims, self.depths, self.embedding_dim = list(EMBED_DIMS), list(DEPTHS), embed_dim
-        self.drop_rate, self.attn_drop, self.drop_path_rate = 0.1, 0.1, 0.1       # reference values (:652-654); run with p = 0 here
+        self.drop_rate, self.attn_drop, self.drop_path_rate = 0.1, 0.1, 0.1       # reference values (:652-654)
         self.input_nc, self.output_nc, self.decoder_softmax, self.precision = input_nc, output_nc, decoder_softmax, precision
         self.Tenc_x2 = EncoderTransformer_v3(img_size=256, patch_size=7, in_chans=input_nc, num_classes=output_nc, embed_dims=self.embed_dims,
                                              num_heads=HEADS, mlp_ratios=[4, 4, 4, 4], qkv_bias=True, drop_rate=self.drop_rate,

@@ -12,6 +12,23 @@
 
 namespace ks {
 
+// stateless RNG of the stochastic regularisers (see the dropout section below)
+__device__ __forceinline__ unsigned long long cf_mix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ unsigned long long cf_key(unsigned long long seed, const int *step_ptr, int site) {
+  const unsigned long long step = step_ptr ? (unsigned long long)(unsigned int)*step_ptr : 0ull;
+  return cf_mix64(seed ^ (step << 32) ^ ((unsigned long long)(unsigned int)site * 0x632BE59BD9B4E019ull));
+}
+// keep/(1-p) factor of element idx: 0 with probability p, 1/(1-p) otherwise
+__device__ __forceinline__ float cf_keep(unsigned long long key, unsigned long long idx, float p, float inv_keep) {
+  const unsigned long long r = cf_mix64(key + idx);
+  return ((float)(r >> 40) * (1.0f / 16777216.0f) >= p) ? inv_keep : 0.f;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Generic strided convolution, implicit GEMM 64x64x16 on CUDA cores.
 //   MODE 0 (forward):  out[n,ho,wo,co] = bias[co] + sum_{ky,kx,ci} x[n, ho*s-p+ky, wo*s-p+kx, ci] * w[ky*k+kx][co][ci]
@@ -186,9 +203,12 @@ __device__ __forceinline__ void xa_load(float *dst, const T *src, long long ld, 
 template <typename T>
 __global__ void __launch_bounds__(XA_WARPS * 32)
 xattention_fwd_kernel(int Nq, int Nk, int heads, int dh, const T *__restrict__ q, long long ldq, const T *__restrict__ kv, long long ldkv,
-                      float scale, T *__restrict__ out, long long ldo, T *__restrict__ probs, int rows_per_cta) {
+                      float scale, T *__restrict__ out, long long ldo, T *__restrict__ probs, int rows_per_cta,
+                      float pdrop, unsigned long long seed, const int *step_ptr, int site) {
   extern __shared__ float sm[];
   const int P = dh + 1;
+  const unsigned long long dkey = cf_key(seed, step_ptr, site);
+  const float ikeep = 1.f / (1.f - pdrop);
   float *Ks = sm, *Vs = Ks + Nk * P, *Qw = Vs + Nk * P, *Pw = Qw + XA_WARPS * XA_DMAX;
   const int b = blockIdx.z, h = blockIdx.y, inner = heads * dh;
   const T *kvb = kv + (long long)b * Nk * ldkv + h * dh;
@@ -224,7 +244,11 @@ xattention_fwd_kernel(int Nq, int Nk, int heads, int dh, const T *__restrict__ q
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {
       const int j = jj * 32 + lane;
-      if (j < Nk) { const float pq = round_as<T>(s[jj] * inv); pw[j] = pq; Cvt<T>::st(prow + j, pq); }
+      if (j < Nk) {
+        const float pq = round_as<T>(s[jj] * inv);
+        Cvt<T>::st(prow + j, pq);                  // the softmax output is kept; attn_drop (:203) acts on the copy used for P.V
+        pw[j] = (pdrop > 0.f) ? pq * cf_keep(dkey, (unsigned long long)((((long long)b * heads + h) * Nq + i) * Nk + j), pdrop, ikeep) : pq;
+      }
     }
     __syncwarp();
     T *orow = out + ((long long)b * Nq + i) * ldo + h * dh;
@@ -241,9 +265,11 @@ template <typename T>
 __global__ void __launch_bounds__(XA_WARPS * 32)
 xattention_bwd_kernel(int Nq, int Nk, int heads, int dh, const T *__restrict__ q, long long ldq, const T *__restrict__ kv, long long ldkv,
                       const T *__restrict__ probs, const T *__restrict__ dout, long long ldo, float scale, T *__restrict__ dq, long long lddq,
-                      float *__restrict__ dkv, int rows_per_cta) {
+                      float *__restrict__ dkv, int rows_per_cta, float pdrop, unsigned long long seed, const int *step_ptr, int site) {
   extern __shared__ float sm[];
   const int P = dh + 1;
+  const unsigned long long dkey = cf_key(seed, step_ptr, site);
+  const float ikeep = 1.f / (1.f - pdrop);
   float *Ks = sm, *Vs = Ks + Nk * P, *dKs = Vs + Nk * P, *dVs = dKs + Nk * P, *Qw = dVs + Nk * P, *Ow = Qw + XA_WARPS * XA_DMAX,
         *Pw = Ow + XA_WARPS * XA_DMAX, *Sw = Pw + XA_WARPS * XA_KMAX;
   const int b = blockIdx.z, h = blockIdx.y, inner = heads * dh;
@@ -261,24 +287,25 @@ xattention_bwd_kernel(int Nq, int Nk, int heads, int dh, const T *__restrict__ q
     const T *prow = probs + (((long long)b * heads + h) * Nq + i) * Nk;
     for (int d = lane; d < dh; d += 32) { qw[d] = Cvt<T>::ld(qrow + d); ow[d] = Cvt<T>::ld(dorow + d); }
     __syncwarp();
-    float dp[2], pv[2], dot = 0.f;
+    float dp[2], pv[2], kf[2], dot = 0.f;
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {
       const int j = jj * 32 + lane;
-      dp[jj] = 0.f; pv[jj] = 0.f;
+      dp[jj] = 0.f; pv[jj] = 0.f; kf[jj] = 1.f;
       if (j < Nk) {
         float a = 0.f;
         const float *vp = Vs + j * P;
         for (int d = 0; d < dh; ++d) a = fmaf(ow[d], vp[d], a);
-        dp[jj] = a; pv[jj] = Cvt<T>::ld(prow + j);
-        dot += a * pv[jj];
+        if (pdrop > 0.f) kf[jj] = cf_keep(dkey, (unsigned long long)((((long long)b * heads + h) * Nq + i) * Nk + j), pdrop, ikeep);
+        dp[jj] = a * kf[jj]; pv[jj] = Cvt<T>::ld(prow + j);         // d(softmax output) = d(dropped copy) * keep/(1-p)
+        dot += dp[jj] * pv[jj];
       }
     }
     dot = warp_sum(dot);
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {
       const int j = jj * 32 + lane;
-      if (j < Nk) { pw[j] = pv[jj]; sw[j] = pv[jj] * (dp[jj] - dot) * scale; }
+      if (j < Nk) { pw[j] = pv[jj] * kf[jj]; sw[j] = pv[jj] * (dp[jj] - dot) * scale; }     // pw: the dropped probabilities (dV = Pdrop^T dO)
     }
     __syncwarp();
     T *dqrow = dq + ((long long)b * Nq + i) * lddq + h * dh;
@@ -513,6 +540,37 @@ sigmoid_head_bwd_kernel(View dz, int H, int W, long long NP, int K, const float 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Stochastic regularisers of the encoder (changeformer.py:652-654: Dropout 0.1, attention dropout 0.1, DropPath 0.1).
+// Masks are a pure function of (seed, *step_ptr, site, element index): nothing is stored, the backward regenerates them,
+// and a captured CUDA graph draws fresh masks on every replay (the step counter lives in device memory).
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+dropout_apply_kernel(long long n, const T *__restrict__ x, T *__restrict__ y, float p, unsigned long long seed, const int *step_ptr, int site) {
+  const unsigned long long key = cf_key(seed, step_ptr, site);
+  const float ik = 1.f / (1.f - p);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    Cvt<T>::st(y + i, Cvt<T>::ld(x + i) * cf_keep(key, (unsigned long long)i, p, ik));
+}
+
+// MODE 0: x[i] += f(i) * t[i]   (x = x + drop_path(dropout(t)), Block.forward :246-247)
+// MODE 1: t[i]  = f(i) * x[i]   (its backward: gradient of the branch output)
+// f(i) = dp[sample(i)] * keep(i)/(1-p);  dp may be NULL (no DropPath)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+branch_kernel(long long n, long long per_sample, T *__restrict__ x, T *__restrict__ t, float p, const float *__restrict__ dp,
+              unsigned long long seed, const int *step_ptr, int site) {
+  const unsigned long long key = cf_key(seed, step_ptr, site);
+  const float ik = 1.f / (1.f - p);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float f = (p > 0.f) ? cf_keep(key, (unsigned long long)i, p, ik) : 1.f;
+    if (dp) f *= dp[i / per_sample];
+    if (MODE == 0) Cvt<T>::st(x + i, Cvt<T>::ld(x + i) + f * Cvt<T>::ld(t + i));
+    else Cvt<T>::st(t + i, f * Cvt<T>::ld(x + i));
+  }
+}
+
 static inline int cgrid(long long work, int per_block, int cap_mult = 8) {
   long long g = (work + per_block - 1) / per_block;
   const long long cap = (long long)kNumSMs * cap_mult;
@@ -588,7 +646,9 @@ static int xa_cfg(int B, int Nq, int Nk, int heads, int dh, int nbuf, size_t &sm
 }
 
 extern "C" int ks_xattention_fwd(int dtype, int B, int Nq, int Nk, int heads, int dh, const void *q, int64_t ldq, const void *kv, int64_t ldkv,
-                                 float scale, void *out, int64_t ldo, void *probs, void *stream) {
+                                 float scale, void *out, int64_t ldo, void *probs, float pdrop, uint64_t seed, const int *step_ptr, int site,
+                                 void *stream) {
+  KS_CHECK_ARG(pdrop >= 0.f && pdrop < 1.f);
   KS_CHECK_ARG(B > 0 && Nq > 0 && heads > 0 && q && kv && out && probs);
   size_t smem; int rpc, nblk;
   int rc = xa_cfg(B, Nq, Nk, heads, dh, 2, smem, rpc, nblk); if (rc) return rc;
@@ -596,14 +656,16 @@ extern "C" int ks_xattention_fwd(int dtype, int B, int Nq, int Nk, int heads, in
 #define CALL(T) { cudaError_t e = cudaFuncSetAttribute(xattention_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); \
     if (e != cudaSuccess) return (int)e; \
     xattention_fwd_kernel<T><<<grid, XA_WARPS * 32, smem, (cudaStream_t)stream>>>(Nq, Nk, heads, dh, (const T *)q, ldq, (const T *)kv, ldkv, scale, \
-                                                                                   (T *)out, ldo, (T *)probs, rpc); }
+                                                                                   (T *)out, ldo, (T *)probs, rpc, pdrop, seed, step_ptr, site); }
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();
 }
 
 extern "C" int ks_xattention_bwd(int dtype, int B, int Nq, int Nk, int heads, int dh, const void *q, int64_t ldq, const void *kv, int64_t ldkv,
-                                 const void *probs, const void *dout, int64_t ldo, float scale, void *dq, int64_t lddq, float *dkv, void *stream) {
+                                 const void *probs, const void *dout, int64_t ldo, float scale, void *dq, int64_t lddq, float *dkv,
+                                 float pdrop, uint64_t seed, const int *step_ptr, int site, void *stream) {
+  KS_CHECK_ARG(pdrop >= 0.f && pdrop < 1.f);
   KS_CHECK_ARG(B > 0 && Nq > 0 && heads > 0 && q && kv && probs && dout && dq && dkv);
   size_t smem; int rpc, nblk;
   int rc = xa_cfg(B, Nq, Nk, heads, dh, 4, smem, rpc, nblk); if (rc) return rc;
@@ -613,7 +675,7 @@ extern "C" int ks_xattention_bwd(int dtype, int B, int Nq, int Nk, int heads, in
 #define CALL(T) { cudaError_t e = cudaFuncSetAttribute(xattention_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); \
     if (e != cudaSuccess) return (int)e; \
     xattention_bwd_kernel<T><<<grid, XA_WARPS * 32, smem, st>>>(Nq, Nk, heads, dh, (const T *)q, ldq, (const T *)kv, ldkv, (const T *)probs, \
-                                                                 (const T *)dout, ldo, scale, (T *)dq, lddq, dkv, rpc); }
+                                                                 (const T *)dout, ldo, scale, (T *)dq, lddq, dkv, rpc, pdrop, seed, step_ptr, site); }
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();
@@ -701,6 +763,35 @@ extern "C" int ks_sigmoid_head_bwd(int dtype, int N, int H, int W, const float *
   const long long NP = (long long)N * H * W;
   const int grid = cgrid(NP, 256);
 #define CALL(T) sigmoid_head_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(to_view(*dz), H, W, NP, K, out, dout)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_dropout_apply(int dtype, int64_t n, const void *x, void *y, float p, uint64_t seed, const int *step_ptr, int site, void *stream) {
+  KS_CHECK_ARG(n > 0 && x && y && p >= 0.f && p < 1.f);
+  const int grid = cgrid(n, 256 * 8);
+#define CALL(T) dropout_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(n, (const T *)x, (T *)y, p, seed, step_ptr, site)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_branch_add(int dtype, int64_t n, int64_t per_sample, void *x, const void *t, float p, const float *droppath, uint64_t seed,
+                             const int *step_ptr, int site, void *stream) {
+  KS_CHECK_ARG(n > 0 && per_sample > 0 && x && t && p >= 0.f && p < 1.f);
+  const int grid = cgrid(n, 256 * 8);
+#define CALL(T) branch_kernel<T, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(n, per_sample, (T *)x, (T *)t, p, droppath, seed, step_ptr, site)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_branch_scale(int dtype, int64_t n, int64_t per_sample, const void *dx, void *dt, float p, const float *droppath, uint64_t seed,
+                               const int *step_ptr, int site, void *stream) {
+  KS_CHECK_ARG(n > 0 && per_sample > 0 && dx && dt && p >= 0.f && p < 1.f);
+  const int grid = cgrid(n, 256 * 8);
+#define CALL(T) branch_kernel<T, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(n, per_sample, (T *)dx, (T *)dt, p, droppath, seed, step_ptr, site)
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();

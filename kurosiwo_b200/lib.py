@@ -96,7 +96,7 @@ EXPORTED_SYMBOLS = [
     "ks_layernorm_fwd", "ks_layernorm_bwd", "ks_patchify_ln", "ks_patchify_ln_bwd", "ks_vit_assemble", "ks_vit_assemble_bwd",
     "ks_confusion_update", "ks_attention_fwd", "ks_attention_bwd", "ks_conv2d_strided", "ks_conv2d_strided_dgrad", "ks_conv2d_strided_wgrad",
     "ks_xattention_fwd", "ks_xattention_bwd", "ks_dwconv3x3_fwd", "ks_dwconv3x3_bwd", "ks_bilinear_nhwc_fwd", "ks_bilinear_nhwc_bwd",
-    "ks_relu_fwd", "ks_relu_bwd", "ks_sigmoid_head_fwd", "ks_sigmoid_head_bwd", "ks_gelu_fwd", "ks_gelu_bwd", "ks_bilinear_up_fwd", "ks_bilinear_up_bwd",
+    "ks_relu_fwd", "ks_relu_bwd", "ks_sigmoid_head_fwd", "ks_sigmoid_head_bwd", "ks_dropout_apply", "ks_branch_add", "ks_branch_scale", "ks_gelu_fwd", "ks_gelu_bwd", "ks_bilinear_up_fwd", "ks_bilinear_up_bwd",
 ]
 
 
@@ -396,16 +396,33 @@ class CudaOps:
                                               _p(dw), C.c_int(int(accumulate)), self._stream())
         self._check(rc, "ks_conv2d_strided_wgrad")
 
-    def xattention_fwd(self, B, Nq, Nk, heads, dh, q, kv, scale, out, probs):
+    def xattention_fwd(self, B, Nq, Nk, heads, dh, q, kv, scale, out, probs, pdrop=0.0, seed=0, step=None, site=0):
         rc = self.lib.ks_xattention_fwd(dtype_code(q.dtype), *[C.c_int(v) for v in (B, Nq, Nk, heads, dh)], _p(q), C.c_int64(q.stride(0)), _p(kv),
-                                        C.c_int64(kv.stride(0)), C.c_float(scale), _p(out), C.c_int64(out.stride(0)), _p(probs), self._stream())
+                                        C.c_int64(kv.stride(0)), C.c_float(scale), _p(out), C.c_int64(out.stride(0)), _p(probs),
+                                        C.c_float(pdrop), C.c_uint64(seed), _p(step), C.c_int(site), self._stream())
         self._check(rc, "ks_xattention_fwd")
 
-    def xattention_bwd(self, B, Nq, Nk, heads, dh, q, kv, probs, dout, scale, dq, dkv_f32):
+    def xattention_bwd(self, B, Nq, Nk, heads, dh, q, kv, probs, dout, scale, dq, dkv_f32, pdrop=0.0, seed=0, step=None, site=0):
         rc = self.lib.ks_xattention_bwd(dtype_code(q.dtype), *[C.c_int(v) for v in (B, Nq, Nk, heads, dh)], _p(q), C.c_int64(q.stride(0)), _p(kv),
                                         C.c_int64(kv.stride(0)), _p(probs), _p(dout), C.c_int64(dout.stride(0)), C.c_float(scale), _p(dq),
-                                        C.c_int64(dq.stride(0)), _p(dkv_f32), self._stream())
+                                        C.c_int64(dq.stride(0)), _p(dkv_f32), C.c_float(pdrop), C.c_uint64(seed), _p(step), C.c_int(site),
+                                        self._stream())
         self._check(rc, "ks_xattention_bwd")
+
+    def dropout_apply(self, x, y, p, seed, step, site):
+        rc = self.lib.ks_dropout_apply(dtype_code(x.dtype), C.c_int64(x.numel()), _p(x), _p(y), C.c_float(p), C.c_uint64(seed), _p(step),
+                                       C.c_int(site), self._stream())
+        self._check(rc, "ks_dropout_apply")
+
+    def branch_add(self, x, t, per_sample, p, droppath, seed, step, site):
+        rc = self.lib.ks_branch_add(dtype_code(x.dtype), C.c_int64(x.numel()), C.c_int64(per_sample), _p(x), _p(t), C.c_float(p), _p(droppath),
+                                    C.c_uint64(seed), _p(step), C.c_int(site), self._stream())
+        self._check(rc, "ks_branch_add")
+
+    def branch_scale(self, dx, dt, per_sample, p, droppath, seed, step, site):
+        rc = self.lib.ks_branch_scale(dtype_code(dx.dtype), C.c_int64(dx.numel()), C.c_int64(per_sample), _p(dx), _p(dt), C.c_float(p),
+                                      _p(droppath), C.c_uint64(seed), _p(step), C.c_int(site), self._stream())
+        self._check(rc, "ks_branch_scale")
 
     def dwconv3x3_fwd(self, N, H, W, x, w9, bias, y):
         rc = self.lib.ks_dwconv3x3_fwd(dtype_code(x.dtype), C.c_int(N), C.c_int(H), C.c_int(W), C.c_int(x.shape[-1]), _p(x), _p(w9), _p(bias), _p(y),

@@ -26,6 +26,35 @@ import torch.nn.functional as F
 EMBED_DIMS, DEPTHS, HEADS, SR = [64, 128, 320, 512], [3, 3, 4, 3], [1, 2, 4, 8], [8, 4, 2, 1]
 
 
+# ---- stateless RNG of the product's stochastic layers, restated (bit for bit: csrc/cformer.cu cf_mix64 / cf_key / cf_keep) ------------
+def _mix64(x):
+    x = x + np.uint64(0x9E3779B97F4A7C15)
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def keep_factors(n: int, p: float, seed: int, step: int, site: int) -> torch.Tensor:
+    """fp32 [n]: 0 with probability p, 1/(1-p) otherwise - the factor the product applies to element i at (seed, step, site)."""
+    with np.errstate(over="ignore"):
+        k0 = (int(seed) ^ ((int(step) & 0xFFFFFFFF) << 32) ^ ((int(site) & 0xFFFFFFFF) * 0x632BE59BD9B4E019)) & ((1 << 64) - 1)
+        key = _mix64(np.array([k0], dtype=np.uint64))[0]
+        r = _mix64(key + np.arange(n, dtype=np.uint64))
+    u = (r >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return torch.from_numpy(np.where(u >= np.float32(p), np.float32(1.0) / (np.float32(1.0) - np.float32(p)), np.float32(0.0)).astype(np.float32))
+
+
+class Stoch:
+    """Explicit stochastic-layer masks for parity runs against the product: the product's own RNG (keep_factors) for the element
+    dropouts, its DropPath factors `dp` [blocks][2][2B] as drawn on the device.  Needs the two dates batched as cat(x1, x2)."""
+
+    def __init__(self, seed, step, p_drop, p_attn, dp):
+        self.seed, self.step, self.p_drop, self.p_attn, self.dp = seed, step, p_drop, p_attn, dp
+
+    def elem(self, t, p, site):
+        return t if p <= 0 else t * keep_factors(t.numel(), p, self.seed, self.step, site).view(t.shape)
+
+
 def make_state(seed: int, in_ch: int = 2, n_cls: int = 3, embed_dim: int = 256, embed_dims=None, depths=None) -> "OrderedDict[str, np.ndarray]":
     """Deterministic state dict in the reference's key order / shapes (373 entries for the default config)."""
     dims, dep = embed_dims or EMBED_DIMS, depths or DEPTHS
@@ -110,7 +139,7 @@ def _bn(sd, name, x, training):
     return out
 
 
-def _attention(sd, p, x, H, W, heads, sr):                       # :186-208
+def _attention(sd, p, x, H, W, heads, sr, st=None, g=0):          # :186-208
     B, N, C = x.shape
     d = C // heads
     q = _lin(sd, f"{p}.q", x).reshape(B, N, heads, d).permute(0, 2, 1, 3)
@@ -123,22 +152,29 @@ def _attention(sd, p, x, H, W, heads, sr):                       # :186-208
     kv = _lin(sd, f"{p}.kv", x_).reshape(B, -1, 2, heads, d).permute(2, 0, 3, 1, 4)
     k, v = kv[0], kv[1]
     attn = ((q @ k.transpose(-2, -1)) * d ** -0.5).softmax(dim=-1)
-    return _lin(sd, f"{p}.proj", (attn @ v).transpose(1, 2).reshape(B, N, C))
+    if st is not None:
+        attn = st.elem(attn, st.p_attn, g * 8)                    # attn_drop (:203)
+    out = _lin(sd, f"{p}.proj", (attn @ v).transpose(1, 2).reshape(B, N, C))
+    return out if st is None else st.elem(out, st.p_drop, g * 8 + 1)   # proj_drop (:206)
 
 
-def _mlp(sd, p, x, H, W):                                       # :126-133, :90-96
+def _mlp(sd, p, x, H, W, st=None, g=0):                         # :126-133, :90-96
     B, N, _ = x.shape
     h = _lin(sd, f"{p}.fc1", x)
     Ch = h.shape[-1]
     h = F.conv2d(h.transpose(1, 2).reshape(B, Ch, H, W), sd[f"{p}.dwconv.dwconv.weight"], sd[f"{p}.dwconv.dwconv.bias"], padding=1, groups=Ch)
-    h = h.flatten(2).transpose(1, 2)
-    return _lin(sd, f"{p}.fc2", F.gelu(h))
+    h = F.gelu(h.flatten(2).transpose(1, 2))
+    if st is not None:
+        h = st.elem(h, st.p_drop, g * 8 + 2)                      # drop after the activation (:130)
+    out = _lin(sd, f"{p}.fc2", h)
+    return out if st is None else st.elem(out, st.p_drop, g * 8 + 3)   # drop after fc2 (:132)
 
 
-def encoder(sd, x, dims=None, depths=None) -> List[torch.Tensor]:   # :430-465
+def encoder(sd, x, dims=None, depths=None, st=None) -> List[torch.Tensor]:   # :430-465
     dims, dep = dims or EMBED_DIMS, depths or DEPTHS
     outs = []
     B = x.shape[0]
+    g = 0
     for s in range(4):
         pe = f"Tenc_x2.patch_embed{s + 1}"
         x = F.conv2d(x, sd[f"{pe}.proj.weight"], sd[f"{pe}.proj.bias"], stride=4 if s == 0 else 2, padding=3)
@@ -146,8 +182,11 @@ def encoder(sd, x, dims=None, depths=None) -> List[torch.Tensor]:   # :430-465
         t = _ln(sd, f"{pe}.norm", x.flatten(2).transpose(1, 2), 1e-5)   # OverlapPatchEmbed.norm: default eps (:266)
         for i in range(dep[s]):
             p = f"Tenc_x2.block{s + 1}.{i}"
-            t = t + _attention(sd, f"{p}.attn", _ln(sd, f"{p}.norm1", t, 1e-6), H, W, HEADS[s], SR[s])
-            t = t + _mlp(sd, f"{p}.mlp", _ln(sd, f"{p}.norm2", t, 1e-6), H, W)
+            dp1 = 1.0 if st is None else st.dp[g, 0].view(B, 1, 1)          # drop_path (:246-247)
+            dp2 = 1.0 if st is None else st.dp[g, 1].view(B, 1, 1)
+            t = t + dp1 * _attention(sd, f"{p}.attn", _ln(sd, f"{p}.norm1", t, 1e-6), H, W, HEADS[s], SR[s], st, g)
+            t = t + dp2 * _mlp(sd, f"{p}.mlp", _ln(sd, f"{p}.norm2", t, 1e-6), H, W, st, g)
+            g += 1
         t = _ln(sd, f"Tenc_x2.norm{s + 1}", t, 1e-6)
         x = t.reshape(B, H, W, -1).permute(0, 3, 1, 2).contiguous()
         outs.append(x)
@@ -183,11 +222,15 @@ def decoder(sd, f1, f2, training=True, decoder_softmax=True) -> List[torch.Tenso
     return [torch.sigmoid(o) for o in outs] if decoder_softmax else outs
 
 
-def changeformer_forward(sd, x1, x2, training=True, decoder_softmax=True) -> List[torch.Tensor]:
-    return decoder(sd, encoder(sd, x1), encoder(sd, x2), training, decoder_softmax)
+def changeformer_forward(sd, x1, x2, training=True, decoder_softmax=True, stoch: "Stoch" = None) -> List[torch.Tensor]:
+    if stoch is None:
+        return decoder(sd, encoder(sd, x1), encoder(sd, x2), training, decoder_softmax)
+    n = x1.shape[0]                  # the encoder has no cross-sample coupling: cat(x1, x2) through it == two separate passes
+    f = encoder(sd, torch.cat((x1, x2), 0), st=stoch)
+    return decoder(sd, [t[:n] for t in f], [t[n:] for t in f], training, decoder_softmax)
 
 
-def train_step(sd, x1, x2, mask, class_weights=(1.0, 1.0, 1.0), decoder_softmax=True):
+def train_step(sd, x1, x2, mask, class_weights=(1.0, 1.0, 1.0), decoder_softmax=True, stoch=None):
     """Reference training step without multi_scale_train: the criterion sees only the last output (change_detection_trainer.py:
     166-170), so the make_pred_c* heads receive no gradient (returned as zeros)."""
     from .snunet_oracle import ce_dice_torch
@@ -195,7 +238,7 @@ def train_step(sd, x1, x2, mask, class_weights=(1.0, 1.0, 1.0), decoder_softmax=
     leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in names}
     work = dict(sd)
     work.update(leaves)
-    outs = changeformer_forward(work, x1, x2, True, decoder_softmax)
+    outs = changeformer_forward(work, x1, x2, True, decoder_softmax, stoch)
     loss = ce_dice_torch(outs[-1], mask, class_weights)
     grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
     return loss.detach(), [o.detach() for o in outs], {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(names, grads)}

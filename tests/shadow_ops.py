@@ -490,19 +490,44 @@ class ShadowOps:
         v = kv.float()[:, inner:2 * inner].reshape(B, Nk, heads, dh).permute(0, 2, 1, 3)
         return qq, k, v
 
-    def xattention_fwd(self, B, Nq, Nk, heads, dh, q, kv, scale, out, probs):
+    # stateless RNG of the stochastic regularisers: the numpy restatement lives in oracle/changeformer_oracle.py
+    def keep_factors(self, n, p, seed, step, site):
+        from oracle.changeformer_oracle import keep_factors
+        return keep_factors(n, p, seed, 0 if step is None else int(step.item()), site)
+
+    def dropout_apply(self, x, y, p, seed, step, site):
+        f = self.keep_factors(x.numel(), p, seed, step, site).view(x.shape)
+        y.copy_((x.float() * f).to(y.dtype))
+
+    def _branch_f(self, t, per_sample, p, droppath, seed, step, site):
+        f = self.keep_factors(t.numel(), p, seed, step, site) if p > 0 else torch.ones(t.numel())
+        if droppath is not None:
+            f = f * droppath.reshape(-1)[torch.arange(t.numel()) // per_sample]
+        return f.view(t.shape)
+
+    def branch_add(self, x, t, per_sample, p, droppath, seed, step, site):
+        x.copy_((x.float() + self._branch_f(t, per_sample, p, droppath, seed, step, site) * t.float()).to(x.dtype))
+
+    def branch_scale(self, dx, dt, per_sample, p, droppath, seed, step, site):
+        dt.copy_((self._branch_f(dx, per_sample, p, droppath, seed, step, site) * dx.float()).to(dt.dtype))
+
+    def xattention_fwd(self, B, Nq, Nk, heads, dh, q, kv, scale, out, probs, pdrop=0.0, seed=0, step=None, site=0):
         qq, k, v = self._xa_split(B, Nq, Nk, heads, dh, q, kv)
         p = torch.softmax(qq @ k.transpose(-1, -2) * scale, dim=-1).to(probs.dtype)
         probs.copy_(p.reshape(probs.shape))
-        out[:, :heads * dh] = (p.float() @ v).permute(0, 2, 1, 3).reshape(B * Nq, heads * dh).to(out.dtype)
+        pd = p.float()
+        if pdrop > 0:
+            pd = pd * self.keep_factors(pd.numel(), pdrop, seed, step, site).view(pd.shape)
+        out[:, :heads * dh] = (pd @ v).permute(0, 2, 1, 3).reshape(B * Nq, heads * dh).to(out.dtype)
 
-    def xattention_bwd(self, B, Nq, Nk, heads, dh, q, kv, probs, dout, scale, dq, dkv_f32):
+    def xattention_bwd(self, B, Nq, Nk, heads, dh, q, kv, probs, dout, scale, dq, dkv_f32, pdrop=0.0, seed=0, step=None, site=0):
         inner = heads * dh
         qq, k, v = self._xa_split(B, Nq, Nk, heads, dh, q, kv)
         p = probs.float().view(B, heads, Nq, Nk)
         do = dout.float()[:, :inner].reshape(B, Nq, heads, dh).permute(0, 2, 1, 3)
-        dv = p.transpose(-1, -2) @ do
-        dp = do @ v.transpose(-1, -2)
+        kf = self.keep_factors(p.numel(), pdrop, seed, step, site).view(p.shape) if pdrop > 0 else torch.ones_like(p)
+        dv = (p * kf).transpose(-1, -2) @ do
+        dp = (do @ v.transpose(-1, -2)) * kf
         ds = p * (dp - (dp * p).sum(-1, keepdim=True)) * scale
         dq[:, :inner] = (ds @ k).permute(0, 2, 1, 3).reshape(B * Nq, inner).to(dq.dtype)
         dk = ds.transpose(-1, -2) @ qq
