@@ -202,7 +202,14 @@ def conv_roofline(eng, dev_inputs, pk, pk_kind):
     detail = {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12, "ms": v[1], "launches": v[2]} for k, v in by_kind.items()}
     layers = [{"kind": r[0], "cin": r[1], "cout": r[2], "h": r[3], "k": r[4], "ms": r[6].elapsed_time(r[7]),
                "tflops": r[5] / (r[6].elapsed_time(r[7]) * 1e-3) / 1e12} for r in recs]
-    return ({"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+    traffic = None      # DRAM bytes per launch of this kernel family from the committed ncu launch list (SNUNet bs=64 only)
+    tp = ROOT / "profiles" / "r1_conv_traffic.json"
+    if tp.exists() and getattr(eng, "f", None) is not None and getattr(eng, "N", 0) == 64:
+        try:
+            traffic = json.loads(tp.read_text())["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
+    return ({"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
              "kernel": "conv_tc_kernel + wgrad_tc_kernel (tcgen05 implicit GEMM; CUDA-core stem included in the time)",
              "peak_source": f"{pk_kind} bf16_tflops_sustained", "conv_ms_per_step": tot_ms, "by_kind": detail}, layers)
 

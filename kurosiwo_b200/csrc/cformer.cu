@@ -5,6 +5,7 @@
 //   ks_dwconv3x3_fwd / _bwd               Mix-FFN depth-wise 3x3 conv (:84-96)
 //   ks_bilinear_nhwc_fwd / _bwd           F.interpolate(..., mode='bilinear', align_corners=False) of NHWC maps (:585-608)
 //   ks_relu_fwd / _bwd, ks_sigmoid_head_fwd / _bwd   ReLU outside a BatchNorm pass (:31-38,471-483), final Sigmoid (:635-639)
+//   ks_dropout_apply, ks_branch_add / _scale         Dropout / DropPath with a stateless RNG (:129-132,206,246-247,652-654)
 // Token matrices [B*N, C] ARE NHWC images [B, H, W, C] (N = H*W row-major), so no transposes exist on this path.
 // First correct path: the strided convolutions and the attention are exact-fp32 CUDA-core kernels for both storage dtypes
 // (6 % of the model's FLOPs, models/changeformer.py encoder); the 94 % in the decoder's 256-channel 3x3 convs run on tcgen05.
