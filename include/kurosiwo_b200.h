@@ -269,6 +269,12 @@ int ks_bilinear_up_fwd(int dtype, int B, int G, int Tp, int row0, int Cs, int K,
 int ks_bilinear_up_bwd(int dtype, int B, int G, int Tp, int row0, int Cs, int K, int Ho, int Wo, const float *ddst, void *dsrc,
                        void *stream);
 
+/* nn.AdaptiveAvgPool2d(S) of an NHWC view -> dense [N][S][S][C] (UPerNet pyramid pooling; HF transformers modeling_upernet.py
+ * UperNetPyramidPoolingBlock, called through models/upernet.py:80): bin (i,j) = mean over rows [floor(i*H/S), ceil((i+1)*H/S)) x
+ * cols [floor(j*W/S), ceil((j+1)*W/S)).  _bwd: dsrc (+)= adjoint(ddst). */
+int ks_adaptive_avgpool_fwd(int dtype, int N, int H, int W, int S, const ks_view_t *src, void *dst, void *stream);
+int ks_adaptive_avgpool_bwd(int dtype, int N, int H, int W, int S, const void *ddst, const ks_view_t *dsrc, int accumulate, void *stream);
+
 /* ---- ChangeFormerV6 passes (models/changeformer.py) ---------------------------------------------------------------
  * Token matrices [B*N, C] are NHWC images [B, H, W, C]; LayerNorm / GELU / Linear reuse the ViT entry points above, the decoder's
  * 3x3 / 1x1 / transposed convolutions and BatchNorm reuse ks_conv2d / ks_conv2d_wgrad / ks_bn_*. */

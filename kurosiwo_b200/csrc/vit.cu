@@ -866,6 +866,50 @@ static inline bool atc_ok(int dtype, int T, int Tp, int dh, int heads) {
          (Tp * 2) % 16 == 0 && ((3LL * heads * dh) % 8) == 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// nn.AdaptiveAvgPool2d(S) on NHWC views (UPerNet pyramid pooling, HF modeling_upernet.py UperNetPyramidPoolingBlock):
+// bin (i, j) averages rows [floor(i*H/S), ceil((i+1)*H/S)) x cols [floor(j*W/S), ceil((j+1)*W/S)).  _bwd is the adjoint.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+adaptive_pool_fwd_kernel(View src, int N, int H, int W, int S, T *__restrict__ dst) {
+  const int C = src.C;
+  const long long total = (long long)N * S * S * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C); long long r = i / C;
+    const int j = (int)(r % S); r /= S; const int bi = (int)(r % S); const long long n = r / S;
+    const int h0 = (bi * H) / S, h1 = ((bi + 1) * H + S - 1) / S, w0 = (j * W) / S, w1 = ((j + 1) * W + S - 1) / S;
+    float a = 0.f;
+    for (int h = h0; h < h1; ++h)
+      for (int w = w0; w < w1; ++w)
+        a += Cvt<T>::ld(reinterpret_cast<const T *>(src.ptr) + (n * src.sn + (long long)h * src.sh + (long long)w * src.sw + c));
+    Cvt<T>::st(dst + i, a / (float)((h1 - h0) * (w1 - w0)));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+adaptive_pool_bwd_kernel(View dsrc, int N, int H, int W, int S, const T *__restrict__ ddst, int accumulate) {
+  const int C = dsrc.C;
+  const long long total = (long long)N * H * W * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C); long long r = i / C;
+    const int w = (int)(r % W); r /= W; const int h = (int)(r % H); const long long n = r / H;
+    float a = 0.f;
+    for (int bi = 0; bi < S; ++bi) {
+      const int h0 = (bi * H) / S, h1 = ((bi + 1) * H + S - 1) / S;
+      if (h < h0 || h >= h1) continue;
+      for (int j = 0; j < S; ++j) {
+        const int w0 = (j * W) / S, w1 = ((j + 1) * W + S - 1) / S;
+        if (w < w0 || w >= w1) continue;
+        a += Cvt<T>::ld(ddst + ((n * S + bi) * S + j) * C + c) / (float)((h1 - h0) * (w1 - w0));
+      }
+    }
+    T *p = reinterpret_cast<T *>(dsrc.ptr) + (n * dsrc.sn + (long long)h * dsrc.sh + (long long)w * dsrc.sw + c);
+    Cvt<T>::st(p, accumulate ? Cvt<T>::ld(p) + a : a);
+  }
+}
+
 static inline int grid_for(long long work, int per_block, int cap_mult = 8) {
   long long g = (work + per_block - 1) / per_block;
   const long long cap = (long long)kNumSMs * cap_mult;
@@ -1065,6 +1109,24 @@ extern "C" int ks_bilinear_up_bwd(int dtype, int B, int G, int Tp, int row0, int
   KS_CHECK_ARG(B > 0 && G > 0 && K > 0 && K <= Cs && row0 >= 0 && row0 + G * G <= Tp && Ho > 0 && Wo > 0 && ddst && dsrc);
   const int grid = grid_for((long long)B * Tp * Cs, 128, 16);
 #define CALL(Ty) bilinear_up_bwd_kernel<Ty><<<grid, 128, 0, (cudaStream_t)stream>>>(B, G, Tp, row0, Cs, K, Ho, Wo, ddst, (Ty *)dsrc)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_adaptive_avgpool_fwd(int dtype, int N, int H, int W, int S, const ks_view_t *src, void *dst, void *stream) {
+  KS_CHECK_ARG(N > 0 && H > 0 && W > 0 && S > 0 && S <= H && S <= W && src && src->ptr && dst);
+  const int grid = grid_for((long long)N * S * S * src->C, 256);
+#define CALL(Ty) adaptive_pool_fwd_kernel<Ty><<<grid, 256, 0, (cudaStream_t)stream>>>(to_view(*src), N, H, W, S, (Ty *)dst)
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_adaptive_avgpool_bwd(int dtype, int N, int H, int W, int S, const void *ddst, const ks_view_t *dsrc, int accumulate, void *stream) {
+  KS_CHECK_ARG(N > 0 && H > 0 && W > 0 && S > 0 && S <= H && S <= W && dsrc && dsrc->ptr && ddst);
+  const int grid = grid_for((long long)N * H * W * dsrc->C, 256);
+#define CALL(Ty) adaptive_pool_bwd_kernel<Ty><<<grid, 256, 0, (cudaStream_t)stream>>>(to_view(*dsrc), N, H, W, S, (const Ty *)ddst, accumulate)
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();

@@ -96,7 +96,7 @@ EXPORTED_SYMBOLS = [
     "ks_layernorm_fwd", "ks_layernorm_bwd", "ks_patchify_ln", "ks_patchify_ln_bwd", "ks_vit_assemble", "ks_vit_assemble_bwd",
     "ks_confusion_update", "ks_attention_fwd", "ks_attention_bwd", "ks_conv2d_strided", "ks_conv2d_strided_dgrad", "ks_conv2d_strided_wgrad",
     "ks_xattention_fwd", "ks_xattention_bwd", "ks_dwconv3x3_fwd", "ks_dwconv3x3_bwd", "ks_bilinear_nhwc_fwd", "ks_bilinear_nhwc_bwd",
-    "ks_relu_fwd", "ks_relu_bwd", "ks_sigmoid_head_fwd", "ks_sigmoid_head_bwd", "ks_dropout_apply", "ks_branch_add", "ks_branch_scale", "ks_gelu_fwd", "ks_gelu_bwd", "ks_bilinear_up_fwd", "ks_bilinear_up_bwd",
+    "ks_relu_fwd", "ks_relu_bwd", "ks_sigmoid_head_fwd", "ks_sigmoid_head_bwd", "ks_dropout_apply", "ks_branch_add", "ks_branch_scale", "ks_gelu_fwd", "ks_gelu_bwd", "ks_bilinear_up_fwd", "ks_bilinear_up_bwd", "ks_adaptive_avgpool_fwd", "ks_adaptive_avgpool_bwd",
 ]
 
 
@@ -379,6 +379,16 @@ class CudaOps:
         rc = self.lib.ks_bilinear_up_bwd(dtype_code(dsrc.dtype), C.c_int(B), C.c_int(G), C.c_int(Tp), C.c_int(row0), C.c_int(dsrc.shape[1]),
                                          C.c_int(K), C.c_int(Ho), C.c_int(Wo), _p(ddst), _p(dsrc), self._stream())
         self._check(rc, "ks_bilinear_up_bwd")
+
+    def adaptive_avgpool_fwd(self, src: View, S: int, dst: torch.Tensor):
+        rc = self.lib.ks_adaptive_avgpool_fwd(dtype_code(src.dtype), C.c_int(src.N), C.c_int(src.H), C.c_int(src.W), C.c_int(S), _vp(src), _p(dst),
+                                              self._stream())
+        self._check(rc, "ks_adaptive_avgpool_fwd")
+
+    def adaptive_avgpool_bwd(self, ddst: torch.Tensor, S: int, dsrc: View, accumulate=False):
+        rc = self.lib.ks_adaptive_avgpool_bwd(dtype_code(dsrc.dtype), C.c_int(dsrc.N), C.c_int(dsrc.H), C.c_int(dsrc.W), C.c_int(S), _p(ddst),
+                                              _vp(dsrc), C.c_int(int(accumulate)), self._stream())
+        self._check(rc, "ks_adaptive_avgpool_bwd")
 
     # -- ChangeFormer passes ---------------------------------------------------------------------
     def conv2d_strided(self, N, Hi, Wi, Ho, Wo, ksize, stride, pad, src: View, weight, bias, dst: View):

@@ -194,3 +194,83 @@ class FinetunerSegmentation(_EngineHost):
             return _FinetuneFunction.apply(self, x, *[p for _, p in self.named_parameters()])
         eng = self._engine_for(x)
         return eng.forward(x, training=self.training).detach().clone()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# FloodViT + UPerNet head (BASELINE.json configs[3]).  Head modules mirror HF transformers' UperNetHead state-dict keys.
+# ---------------------------------------------------------------------------------------------------------------------
+class UperNetConvModule(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, padding=0):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, padding=padding, bias=False)
+        self.batch_norm = nn.BatchNorm2d(out_channels)
+        self.activation = nn.ReLU()
+
+
+class UperNetPyramidPoolingBlock(nn.Module):
+    def __init__(self, pool_scale, in_channels, channels):
+        super().__init__()
+        self.add_module("0", nn.AdaptiveAvgPool2d(pool_scale))
+        self.add_module("1", UperNetConvModule(in_channels, channels, kernel_size=1))
+
+
+class UperNetPyramidPoolingModule(nn.Module):
+    def __init__(self, pool_scales, in_channels, channels):
+        super().__init__()
+        for i, s in enumerate(pool_scales):
+            self.add_module(str(i), UperNetPyramidPoolingBlock(s, in_channels, channels))
+
+
+class UperNetHead(nn.Module):
+    """Parameter container with the key names / shapes of transformers.models.upernet.modeling_upernet.UperNetHead."""
+
+    def __init__(self, in_channels, hidden_size=512, num_labels=3, pool_scales=(1, 2, 3, 6)):
+        super().__init__()
+        if tuple(pool_scales) != (1, 2, 3, 6):
+            raise NotImplementedError("the fused head is built for pool_scales (1, 2, 3, 6) (UperNetConfig default)")
+        self.classifier = nn.Conv2d(hidden_size, num_labels, kernel_size=1)
+        self.psp_modules = UperNetPyramidPoolingModule(pool_scales, in_channels[-1], hidden_size)
+        self.bottleneck = UperNetConvModule(in_channels[-1] + len(pool_scales) * hidden_size, hidden_size, kernel_size=3, padding=1)
+        self.lateral_convs = nn.ModuleList([UperNetConvModule(c, hidden_size, kernel_size=1) for c in in_channels[:-1]])
+        self.fpn_convs = nn.ModuleList([UperNetConvModule(hidden_size, hidden_size, kernel_size=3, padding=1) for _ in in_channels[:-1]])
+        self.fpn_bottleneck = UperNetConvModule(len(in_channels) * hidden_size, hidden_size, kernel_size=3, padding=1)
+
+
+class FloodViTUperNet(_EngineHost):
+    """ViT encoder (`model`) + UPerNet head (`decode_head`): model(img[B,6,224,224]) -> logits [B, num_classes, 224, 224]."""
+
+    def __init__(self, encoder: ViT, num_classes=3, hidden_size=512, out_indices=None, precision=None):
+        super().__init__()
+        self.model = encoder
+        self.model.mlp_head = nn.Identity()
+        D = encoder.cfg["dim"]
+        self.decode_head = UperNetHead([D] * 4, hidden_size, num_classes)
+        self.num_classes, self.hidden_size, self.out_indices = num_classes, hidden_size, out_indices
+        self.precision = precision or encoder.precision
+        self._engines, self._ops = {}, None
+
+    def _engine_for(self, x):
+        from .upernet_engine import ViTUperNetEngine
+        ops = self._get_ops(x)
+        key = (x.shape[0], x.shape[2], x.shape[3], self._storage_dtype(), str(x.device))
+        eng = self._engines.get(key)
+        if eng is None:
+            self._engines = {}
+            eng = ViTUperNetEngine(ops, self, "model.", self.model.cfg, self.num_classes, x.shape[0], x.shape[2], x.shape[3],
+                                   self._storage_dtype(), x.device, self.out_indices, self.hidden_size)
+            self._engines[key] = eng
+        return eng
+
+    def engine(self, x):
+        return self._engine_for(x)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        cfg = self.model.cfg
+        if x.dim() != 4 or x.shape[1] != cfg["channels"] or x.shape[2] != cfg["image_size"] or x.shape[3] != cfg["image_size"]:
+            raise ValueError(f"expected [B,{cfg['channels']},{cfg['image_size']},{cfg['image_size']}], got {tuple(x.shape)}")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            eng = self._engine_for(x)
+            eng.params.ensure(x.device)
+            return _FinetuneFunction.apply(self, x, *[p for _, p in self.named_parameters()])
+        eng = self._engine_for(x)
+        return eng.forward(x, training=self.training).detach().clone()

@@ -41,7 +41,8 @@ class ViTSegEngine(TrainStepMixin):
     def __init__(self, ops, module: torch.nn.Module, enc_prefix: str, cfg: dict, head: str, num_classes: int,
                  B: int, H: int, W: int, dtype: torch.dtype, device, conv_impl: int = 0):
         assert num_classes == 3, "the fused head/loss kernels are built for num_classes == 3 (configs/config.json:13)"
-        assert head == "linear", "only the linear (1x1 conv) FinetunerSegmentation head is on the fused path"
+        assert head in ("linear", "upernet"), "heads on the fused path: linear (FinetunerSegmentation), upernet (HF UperNetHead)"
+        self.head_kind = head
         self.ops, self.module, self.dtype, self.device = ops, module, dtype, torch.device(device)
         self.pre = enc_prefix
         self.B, self.N, self.H, self.W, self.K = B, B, H, W, num_classes
@@ -161,6 +162,10 @@ class ViTSegEngine(TrainStepMixin):
 
     # ------------------------------------------------------------------------------------------
     def forward(self, img: torch.Tensor, training: bool = True) -> torch.Tensor:
+        self._encoder_forward(img)
+        return self._head_forward(training)
+
+    def _encoder_forward(self, img: torch.Tensor):
         ops, P, pre, B = self.ops, self.params, self.pre, self.B
         assert tuple(img.shape) == (B, self.Cc, self.H, self.W), f"engine was planned for {(B, self.Cc, self.H, self.W)}, got {tuple(img.shape)}"
         P.ensure(self.device)
@@ -185,6 +190,9 @@ class ViTSegEngine(TrainStepMixin):
             ops.gelu_fwd(b.u, b.h)
             self._linear(b.h, f"{b.pf}.4", nxt, P.p(f"{b.pf}.4.bias"), accumulate=True)                          # x = ff(x) + x
         ops.layernorm_fwd(self.xL, P.p(f"{pre}transformer.norm.weight"), P.p(f"{pre}transformer.norm.bias"), LN_EPS, self.tok, self.mf, self.rf, None)
+
+    def _head_forward(self, training: bool) -> torch.Tensor:
+        ops, B = self.ops, self.B
         # head: the 1x1 conv commutes with the bilinear interpolation -> classify the G x G grid, upsample K planes
         ops.conv2d(1, self.R // 16, 16, 1, [tok_view(self.tok)], self.wp["head.fwd"], self.wp["head.bias"], [tok_view(self.z)], [False], None, self.conv_impl)
         ops.bilinear_up_fwd(B, self.G, self.Tp, 1, self.K, self.H, self.W, self.z, self.logits)
@@ -196,15 +204,27 @@ class ViTSegEngine(TrainStepMixin):
 
     # ------------------------------------------------------------------------------------------
     def backward(self, dlogits: torch.Tensor):
+        self.ops.zero_(self.params.grad)        # LayerNorm / attention parameter gradients are accumulated with atomics
+        self._head_backward(dlogits)            # leaves d(tokens) in self.dxn (all rows; 0 for the cls / padding rows)
+        self._encoder_backward()
+
+    def _inject(self, bi: int):
+        """Hook: add gradients that enter the residual stream AFTER block `bi` (multi-level heads); none for the linear head."""
+
+    def _head_backward(self, dlogits: torch.Tensor):
         ops, P, pre, B = self.ops, self.params, self.pre, self.B
-        ops.zero_(P.grad)                       # LayerNorm / attention parameter gradients are accumulated with atomics
         ops.bilinear_up_bwd(B, self.G, self.Tp, 1, self.K, self.H, self.W, dlogits, self.dz)
         ops.conv2d_wgrad(1, self.R // 16, 16, 1, [tok_view(self.tok)], [tok_view(self.dz)], self.gp_head, False, self.conv_impl)
         ops.channel_sum(tok_view(self.dz), self.gp_head_bias, False)
         ops.conv2d(1, self.R // 16, 16, 1, [tok_view(self.dz)], self.wp["head.dgrad"], None, [tok_view(self.dxn)], [False], None, self.conv_impl)
+
+    def _encoder_backward(self):
+        ops, P, pre, B = self.ops, self.params, self.pre, self.B
         ops.layernorm_bwd(self.dxn, self.xL, self.mf, self.rf, P.p(f"{pre}transformer.norm.weight"), self.dx, False,
                           P.g(f"{pre}transformer.norm.weight"), P.g(f"{pre}transformer.norm.bias"))
-        for b in reversed(self.blocks):
+        for bi in reversed(range(self.depth)):
+            b = self.blocks[bi]
+            self._inject(bi)
             # x_out = xm + W2 gelu(W1 LN2(xm) + b1) + b2
             self._linear_bwd(b.h, f"{b.pf}.4", self.dx, self.dh_, True)
             ops.gelu_bwd(b.u, self.dh_, self.dh_)
@@ -221,3 +241,8 @@ class ViTSegEngine(TrainStepMixin):
         self._linear_bwd(self.a0, f"{pe}.2", self.de1, self.da0, True)
         ops.patchify_ln_bwd(self._img, self.Tp, self.mp, self.rp, self.da0, P.g(f"{pe}.1.weight"), P.g(f"{pe}.1.bias"))
         ops.permute_cast_table(self._tables()[1])
+
+    def grid_view(self, t: torch.Tensor) -> View:
+        """The patch tokens (cls dropped) of a [R, C] token matrix as the NHWC map [B, G, G, C] - a strided view, no copy."""
+        Cn = t.shape[1]
+        return View(t.view(-1), Cn, self.B, self.G, self.G, Cn, self.Tp * Cn, self.G * Cn, Cn)

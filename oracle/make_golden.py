@@ -84,6 +84,7 @@ def main():
     siam_goldens()
     vit_goldens()
     changeformer_goldens()
+    upernet_goldens()
 
 
 def siam_goldens():
@@ -234,7 +235,67 @@ def changeformer_goldens():
         print("changeformer", tag, "loss", float(loss.detach()))
 
 
+def upernet_goldens():
+    """FloodViT + UPerNet: the reference's ViT modules (driven layer by layer to tap the residual stream) + the installed HF
+    UperNetHead class (the third-party code models/upernet.py:80 reaches), logits resized like UperNetForSemanticSegmentation."""
+    from oracle.ref_import import install_stubs
+    install_stubs()
+    from models.vision_transformer import ViT as RefViT                    # noqa: E402  (reference, read-only)
+    from utilities.bce_and_dice import BCEandDiceLoss as RefLoss           # noqa: E402
+    from transformers import UperNetConfig
+    from transformers.models.upernet.modeling_upernet import UperNetHead
+    from einops import repeat
+    from oracle import upernet_oracle as uo
+    from oracle import vit_oracle
+    import torch.nn.functional as F
+
+    dim, depth, heads, mlp, N, seed, out_idx = 128, 4, 2, 256, 2, 71, [1, 2, 3, 4]
+    sd = uo.make_state(seed, dim, depth, heads, mlp)
+    img, mask = vit_oracle.make_batch(seed, N)
+    enc = RefViT(image_size=224, patch_size=16, num_classes=3, dim=dim, depth=depth, heads=heads, mlp_dim=mlp, channels=6)
+    enc.mlp_head = torch.nn.Identity()
+    head = UperNetHead(UperNetConfig(hidden_size=512, pool_scales=[1, 2, 3, 6], num_labels=3), in_channels=[dim] * 4)
+    enc.load_state_dict({k[len("model."):]: torch.from_numpy(np.array(v)) for k, v in sd.items() if k.startswith("model.")})
+    head.load_state_dict({k[len("decode_head."):]: torch.from_numpy(np.array(v)) for k, v in sd.items() if k.startswith("decode_head.")})
+    enc.train(); head.train()
+    x = enc.to_patch_embedding(torch.from_numpy(img))
+    b, n, _ = x.shape
+    x = torch.cat((repeat(enc.cls_token, "1 1 d -> b 1 d", b=b), x), dim=1) + enc.pos_embedding[:, : n + 1]
+    taps = {}
+    for l, (attn, ff) in enumerate(enc.transformer.layers):
+        x = attn(x) + x
+        x = ff(x) + x
+        taps[l + 1] = x[:, 1:]
+    taps[depth] = enc.transformer.norm(x)[:, 1:]
+    feats = [taps[i].reshape(b, 14, 14, dim).permute(0, 3, 1, 2) for i in out_idx]
+    logits = F.interpolate(head(feats), size=(224, 224), mode="bilinear", align_corners=False)
+    crit = RefLoss(weights=torch.tensor([1.0, 1.0, 1.0]), ignore_index=3, use_softmax=True)
+    loss = crit(logits, torch.from_numpy(mask))
+    loss.backward()
+    fx = {"dim": dim, "depth": depth, "heads": heads, "mlp": mlp, "N": N, "seed": seed, "out_indices": np.array(out_idx),
+          "loss": loss.detach().numpy(), "logits_sample": logits.detach().numpy()[:, :, ::7, ::7].copy()}
+    names, norms = [], []
+    keep_full = {"model.cls_token", "model.transformer.layers.0.0.to_qkv.weight", "model.transformer.layers.2.1.net.4.weight",
+                 "decode_head.classifier.weight", "decode_head.psp_modules.0.1.conv.weight", "decode_head.psp_modules.2.1.batch_norm.weight",
+                 "decode_head.lateral_convs.1.conv.weight", "decode_head.fpn_convs.0.batch_norm.bias", "decode_head.fpn_bottleneck.batch_norm.weight"}
+    for pre, mod in (("model.", enc), ("decode_head.", head)):
+        for k, p in mod.named_parameters():
+            names.append(pre + k)
+            norms.append(float(p.grad.double().norm()))
+            if pre + k in keep_full:
+                fx[f"grad.{pre + k}"] = p.grad.numpy()
+    fx["grad_names"] = np.array(names)
+    fx["grad_norms"] = np.array(norms, np.float64)
+    for k in ("bottleneck.batch_norm.running_mean", "psp_modules.3.1.batch_norm.running_var", "fpn_bottleneck.batch_norm.running_var"):
+        fx[f"state.decode_head.{k}"] = head.state_dict()[k].numpy()
+    np.savez_compressed(OUT / "floodvit_upernet_d128_l4.npz", **fx)
+    print("floodvit+upernet loss", float(loss.detach()))
+
+
 if __name__ == "__main__":
+    if "--upernet-only" in sys.argv:
+        upernet_goldens()
+        sys.exit(0)
     if "--cf-only" in sys.argv:
         changeformer_goldens()
         sys.exit(0)

@@ -70,7 +70,9 @@ def _ln(sd, name, x):
     return F.layer_norm(x, (x.shape[-1],), sd[f"{name}.weight"], sd[f"{name}.bias"], 1e-5)
 
 
-def vit_tokens(sd, img, heads: int, dim_head: int = 64, pre: str = "model.") -> torch.Tensor:
+def vit_tokens(sd, img, heads: int, dim_head: int = 64, pre: str = "model.", out_indices=None):
+    """out_indices (optional): also return the residual stream (cls token dropped) after those block counts; an index equal to
+    the depth yields the final-norm output."""
     B, C, H, W = img.shape
     gh, gw = H // 16, W // 16
     x = img.view(B, C, gh, 16, gw, 16).permute(0, 2, 4, 3, 5, 1).reshape(B, gh * gw, 256 * C)       # :122
@@ -81,6 +83,7 @@ def vit_tokens(sd, img, heads: int, dim_head: int = 64, pre: str = "model.") -> 
     x = x + sd[f"{pre}pos_embedding"][:, : n + 1]                                              # :144
     depth = 1 + max(int(k.split(".")[3 if pre else 2]) for k in sd if k.startswith(f"{pre}transformer.layers."))
     inner = heads * dim_head
+    taps = {}
     for l in range(depth):
         pa, pf = f"{pre}transformer.layers.{l}.0", f"{pre}transformer.layers.{l}.1.net"
         y = _ln(sd, f"{pa}.norm", x)                                                           # :54
@@ -91,7 +94,11 @@ def vit_tokens(sd, img, heads: int, dim_head: int = 64, pre: str = "model.") -> 
         y = _ln(sd, f"{pf}.0", x)
         y = F.linear(F.gelu(F.linear(y, sd[f"{pf}.1.weight"], sd[f"{pf}.1.bias"])), sd[f"{pf}.4.weight"], sd[f"{pf}.4.bias"])
         x = y + x                                                                              # :87
+        taps[l + 1] = x[:, 1:]
     x = _ln(sd, f"{pre}transformer.norm", x)                                                   # :89
+    if out_indices is not None:
+        taps[depth] = x[:, 1:]
+        return [taps[i] for i in out_indices]
     return x[:, 1:]                                                                            # :152
 
 

@@ -585,3 +585,15 @@ class ShadowOps:
         gg = g * grad_scale + wd * p
         buf.mul_(momentum).add_(gg)
         p.add_(buf, alpha=-lr)
+
+    def adaptive_avgpool_fwd(self, src, S, dst):
+        x = _t(src).float().permute(0, 3, 1, 2)
+        dst.copy_(F.adaptive_avg_pool2d(x, S).permute(0, 2, 3, 1).reshape(dst.shape).to(dst.dtype))
+
+    def adaptive_avgpool_bwd(self, ddst, S, dsrc, accumulate=False):
+        t = _t(dsrc)
+        with torch.enable_grad():
+            m = torch.zeros(dsrc.N, dsrc.C, dsrc.H, dsrc.W, requires_grad=True)
+            F.adaptive_avg_pool2d(m, S).backward(ddst.float().view(dsrc.N, S, S, dsrc.C).permute(0, 3, 1, 2))
+        v = m.grad.permute(0, 2, 3, 1)
+        t.copy_((t.float() + v if accumulate else v).to(t.dtype))
