@@ -44,6 +44,10 @@ WORKLOADS = {
                      method="finetune", lr=1e-4,
                      desc="FloodViT: ViT-B/16 encoder (6 channels, 86.4M params) + linear FinetunerSegmentation head, train step: fwd + "
                           "CE+Dice(+argmax) + bwd + allreduce + Adam; image = cat(post_event, pre_event_1, pre_event_2)"),
+    "floodvit-upernet": dict(metric="SAR patches/sec (224x224x6ch, bs=64) FloodViT-B + UPerNet head train step", batch=64, gflop=118.0,
+                             task="segmentation", method="finetune", lr=1e-4,
+                             desc="FloodViT (BASELINE.json configs[3]): ViT-B/16 encoder (6 channels) + HF-UperNetHead semantics (hidden 512, pool "
+                                  "scales 1/2/3/6, features after blocks 3/6/9/12), train step: fwd + CE+Dice(+argmax) + bwd + allreduce + Adam"),
 }
 
 
@@ -252,6 +256,8 @@ def run_ours(args):
         configs.update({"inputs": ["pre_event_1", "pre_event_2", "post_event"], "num_channels": 6, "mlp": False, "decoder": False,
                         "finetuning_patch_size": 16, "linear_eval": False, "encoder": None})
         model_configs["encoder_config"] = {"image_size": 224, "patch_size": 16, "dim": 768, "depth": 12, "heads": 12, "mlp_dim": 3072}
+        if args.workload == "floodvit-upernet":
+            configs["head"] = "upernet"
         model = initialize_segmentation_model(configs, model_configs).to(dev).train()
         stepper = FusedSegStepper(model, configs, model_configs, process_group=pg)
         dev_inputs = (torch.cat((b0[2], b0[6], b0[9]), 1).to(dev), b0[3].to(dev))   # cat(post, pre1, pre2), mask

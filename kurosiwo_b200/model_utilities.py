@@ -6,7 +6,7 @@ import torch
 from .changeformer import ChangeFormerV6
 from .siam_unet import SiamUnet_conc, SiamUnet_diff
 from .snunet import SNUNet_ECAM
-from .vision_transformer import FinetunerSegmentation, ViT  # noqa: F401
+from .vision_transformer import FinetunerSegmentation, FloodViTUperNet, ViT  # noqa: F401
 
 
 def initialize_cd_model(configs, model_configs, phase="train"):
@@ -53,4 +53,7 @@ def initialize_segmentation_model(config, model_configs):
         param.requires_grad = not config.get("linear_eval", False)
     if config.get("linear_eval"):
         raise NotImplementedError("linear_eval=true (frozen encoder) is not on the fused path: the fused step updates all parameters")
+    if config.get("head", model_configs.get("head", "linear")) == "upernet":      # BASELINE.json configs[3]: MAE-ViT encoder + UPerNet head
+        return FloodViTUperNet(encoder, num_classes=config["num_classes"], hidden_size=int(model_configs.get("upernet_hidden", 512)),
+                               out_indices=model_configs.get("out_indices"), precision=precision)
     return FinetunerSegmentation(encoder=encoder, configs=config, precision=precision)

@@ -14,7 +14,7 @@ import torch
 
 from .change_detection_trainer import CLASS_LABELS, unpack_batch
 from .utilities import ConfusionMetrics, create_loss, init_lr_scheduler
-from .vision_transformer import FinetunerSegmentation
+from .vision_transformer import FinetunerSegmentation, FloodViTUperNet
 
 
 def stack_inputs(b, configs, device):
@@ -40,8 +40,8 @@ class FusedSegStepper:
     """Owns the engine-side training state of a segmentation model (the public fast path)."""
 
     def __init__(self, model, configs, model_configs, process_group=None):
-        if not isinstance(model, FinetunerSegmentation):
-            raise TypeError("the fused segmentation step is implemented for kurosiwo_b200.FinetunerSegmentation (FloodViT)")
+        if not isinstance(model, (FinetunerSegmentation, FloodViTUperNet)):
+            raise TypeError("the fused segmentation step is implemented for kurosiwo_b200's FinetunerSegmentation / FloodViTUperNet")
         if configs.get("loss_function", "ce+dice") not in ("ce+dice", "cross_entropy"):
             raise NotImplementedError("the fused step computes CE+Dice (utilities/bce_and_dice.py) or plain cross-entropy "
                                       "(utilities/utilities.py:308-321); other losses are outside the B200 hot path")

@@ -249,7 +249,7 @@ def upernet_goldens():
     from oracle import vit_oracle
     import torch.nn.functional as F
 
-    dim, depth, heads, mlp, N, seed, out_idx = 128, 4, 2, 256, 2, 71, [1, 2, 3, 4]
+    dim, depth, heads, mlp, N, seed, out_idx = 128, 4, 2, 256, 8, 71, [1, 2, 3, 4]   # N=8: the pool-scale-1 module normalises over N samples; N=2 makes its 1/sqrt(var+eps) reach 316 and the case ill-conditioned
     sd = uo.make_state(seed, dim, depth, heads, mlp)
     img, mask = vit_oracle.make_batch(seed, N)
     enc = RefViT(image_size=224, patch_size=16, num_classes=3, dim=dim, depth=depth, heads=heads, mlp_dim=mlp, channels=6)

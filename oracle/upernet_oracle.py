@@ -51,18 +51,26 @@ def make_head_state(seed: int, in_channels, hidden: int = 512, n_cls: int = 3, p
     return sd
 
 
-def _cbr(sd, name, x, training, pad):
+def _conv_module(sd, name, x, training, pad, relu_masks=None, tap=None):
     y = F.conv2d(x, sd[f"{name}.conv.weight"], None, padding=pad)
     y = F.batch_norm(y, sd[f"{name}.batch_norm.running_mean"], sd[f"{name}.batch_norm.running_var"], sd[f"{name}.batch_norm.weight"],
                      sd[f"{name}.batch_norm.bias"], training, 0.1, 1e-5)
     if training:
         sd[f"{name}.batch_norm.num_batches_tracked"] += 1
-    return F.relu(y)
+    if tap is not None:
+        tap[name] = y.detach()
+    return y * relu_masks[name].to(y.dtype) if relu_masks is not None else F.relu(y)
 
 
-def upernet_head(sd: Dict[str, torch.Tensor], feats: List[torch.Tensor], training: bool = True, prefix: str = "decode_head.") -> torch.Tensor:
-    """feats: NCHW maps, coarsest last.  Returns the logits at the resolution of feats[0]."""
+def upernet_head(sd: Dict[str, torch.Tensor], feats: List[torch.Tensor], training: bool = True, prefix: str = "decode_head.",
+                 relu_masks=None, tap=None) -> torch.Tensor:
+    """feats: NCHW maps, coarsest last.  Returns the logits at the resolution of feats[0].
+    relu_masks (tests only): per-module boolean masks that REPLACE the ReLU sign test (see oracle/siam_oracle.py:siam_forward);
+    tap: receives every module's pre-ReLU map."""
     p = prefix
+
+    def _cbr(sd, name, x, training, pad):
+        return _conv_module(sd, name, x, training, pad, relu_masks, tap)
     laterals = [_cbr(sd, f"{p}lateral_convs.{i}", feats[i], training, 0) for i in range(len(feats) - 1)]
     x = feats[-1]
     psp = [x]
@@ -87,22 +95,22 @@ def make_state(seed: int, dim: int, depth: int, heads: int, mlp_dim: int, hidden
     return sd
 
 
-def forward(sd, img, heads: int, out_indices, training: bool = True) -> torch.Tensor:
+def forward(sd, img, heads: int, out_indices, training: bool = True, relu_masks=None, tap=None) -> torch.Tensor:
     taps = vit_oracle.vit_tokens(sd, img, heads, out_indices=list(out_indices))
     B, n, D = taps[0].shape
     G = int(round(n ** 0.5))
     feats = [t.reshape(B, G, G, D).permute(0, 3, 1, 2) for t in taps]
-    logits = upernet_head(sd, feats, training)
+    logits = upernet_head(sd, feats, training, relu_masks=relu_masks, tap=tap)
     return F.interpolate(logits, size=img.shape[2:], mode="bilinear", align_corners=False)
 
 
-def train_step(sd, img, mask, heads: int, out_indices, class_weights=(1.0, 1.0, 1.0)):
+def train_step(sd, img, mask, heads: int, out_indices, class_weights=(1.0, 1.0, 1.0), relu_masks=None, tap=None):
     from .snunet_oracle import ce_dice_torch
     names = [k for k in sd if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
     leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in names}
     work = dict(sd)
     work.update(leaves)
-    logits = forward(work, img, heads, out_indices, True)
+    logits = forward(work, img, heads, out_indices, True, relu_masks, tap)
     loss = ce_dice_torch(logits, mask, class_weights)
     grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
     return loss.detach(), logits.detach(), {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(names, grads)}

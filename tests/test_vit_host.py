@@ -116,6 +116,36 @@ def test_upernet_oracle_matches_golden():
             np.testing.assert_allclose(sd[k[6:]].numpy(), fx[k], rtol=1e-5, atol=1e-7)
 
 
+def upernet_grad_check(model, eng, grads_o, uo, sd_np, img, mask, heads, out_idx, tol=2e-3):
+    """13 BatchNorm+ReLU modules on 2x14x14 maps: a pre-activation that is zero to rounding error can take different ReLU signs in two
+    implementations (see tests/test_gpu_snunet.py); one flip in the last module moves its own conv-weight gradient by ~15 % and
+    everything upstream by ~2 %.  So: compare directly; if that fails, (a) the oracle equals the golden on the CPU
+    (test_upernet_oracle_matches_golden), (b) the gradients equal the oracle's when the oracle uses THIS path's ReLU masks, and
+    (c) the two sides' masks differ in a handful of elements only, all with |pre-activation| < 1e-5."""
+    def compare(ref, t):
+        return [(n, float((p.grad.cpu() - ref[n]).abs().max()), float(ref[n].abs().max())) for n, p in model.named_parameters()
+                if float((p.grad.cpu() - ref[n]).abs().max()) > t * float(ref[n].abs().max()) + 1e-8]
+    bad = compare(grads_o, tol)
+    if not bad:
+        return 0
+    nchw = lambda L, t: t.float().view(L.n, L.h, L.w, L.cout).permute(0, 3, 1, 2).cpu()
+    relu_masks = {L.name: nchw(L, L.out) > 0 for L in eng.cbrs}
+    tap = {}
+    _, _, grads_m = uo.train_step(vit_oracle.to_torch_state(sd_np), img.cpu(), mask.cpu(), heads, out_idx, relu_masks=relu_masks, tap=tap)
+    flips = 0
+    for L in eng.cbrs:
+        diff = relu_masks[L.name] != (tap[L.name] > 0)      # tap holds the oracle's pre-ReLU maps computed under this path's masks
+        flips += int(diff.sum())
+        if diff.any():
+            sc, sh = L.bn[:L.cout].cpu().view(1, -1, 1, 1), L.bn[L.cout:2 * L.cout].cpu().view(1, -1, 1, 1)
+            mine = nchw(L, L.y) * sc + sh
+            assert float(tap[L.name][diff].abs().max()) < 1e-5 and float(mine[diff].abs().max()) < 1e-5, L.name
+    assert 0 < flips <= 8, (flips, bad[:5])
+    bad2 = compare(grads_m, tol)
+    assert not bad2, (flips, bad2[:10])
+    return flips
+
+
 def test_upernet_schedule_matches_oracle():
     from kurosiwo_b200.vision_transformer import FloodViTUperNet
     fx, uo, dim, depth, heads, mlp, out_idx, sd_np, img, mask = _upernet_case()
@@ -132,17 +162,6 @@ def test_upernet_schedule_matches_oracle():
     loss.backward()
     np.testing.assert_allclose(out.detach().numpy(), logits_o.numpy(), rtol=1e-3, atol=1e-4)
     np.testing.assert_allclose(float(loss.detach()), float(loss_o), rtol=1e-4)
-    # 13 BatchNorm+ReLU modules on 2x14x14 maps: ONE pre-activation that is zero to rounding error can flip its ReLU sign between two
-    # implementations (see tests/test_gpu_snunet.py); that moves the flipped module's own weight/bias gradient by a few % and everything
-    # upstream by ~0.2 %.  Bars: every tensor within 5e-3 of its max, except at most 3 tensors within 1e-1.
-    bad, loose = [], []
-    for name, p in model.named_parameters():
-        go = grads_o[name]
-        err, scale = (p.grad - go).abs().max().item(), go.abs().max().item()
-        if err > 1e-1 * scale + 1e-8:
-            bad.append((name, err, scale))
-        elif err > 5e-3 * scale + 1e-8:
-            loose.append((name, err, scale))
-    assert not bad and len(loose) <= 3, (bad[:10], loose)
+    upernet_grad_check(model, model.engine(img), grads_o, uo, sd_np, img, mask, heads, out_idx)
     for k in ("decode_head.bottleneck.batch_norm.running_mean", "decode_head.psp_modules.3.1.batch_norm.running_var"):
         np.testing.assert_allclose(model.state_dict()[k].numpy(), sd[k].numpy(), rtol=1e-4, atol=1e-6)
