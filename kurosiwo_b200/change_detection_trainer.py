@@ -16,6 +16,7 @@ import torch
 from .changeformer import ChangeFormerV6
 from .siam_unet import _SiamUnet
 from .snunet import SNUNet_ECAM
+from .host_pipeline import HostPipelineMixin, lookahead
 from .utilities import ConfusionMetrics, create_loss, init_lr_scheduler
 
 CLASS_LABELS = {0: "No water", 1: "Permanent Waters", 2: "Floods", 3: "Invalid pixels"}
@@ -49,7 +50,7 @@ def select_inputs(b, configs, device):
     return outs
 
 
-class FusedStepper:
+class FusedStepper(HostPipelineMixin):
     """Owns the engine-side training state for one model/batch geometry (the public fast path)."""
 
     def __init__(self, model, configs, model_configs, process_group=None):
@@ -84,14 +85,11 @@ class FusedStepper:
         if self.engine is not None:
             self.engine.hp["lr"] = self.lr
 
-    def step_host(self, batch):
-        """One training step from a HOST batch (pinned tensors): H2D copies + fused step. Returns device loss[3]."""
+    def _to_device(self, batch):
         dev = self.configs["device"]
         b = unpack_batch(batch, self.configs)
         xa, xb = select_inputs(b, self.configs, dev)
-        mask = b["mask"].to(dev, non_blocking=True)
-        eng = self._engine(xa)
-        return eng.train_step(xa, xb, mask), mask
+        return [xa, xb, b["mask"].to(dev, non_blocking=True)]
 
 
 def train_change_detection(model, train_loader, val_loader, test_loader, configs, model_configs, process_group=None):
@@ -110,7 +108,9 @@ def train_change_detection(model, train_loader, val_loader, test_loader, configs
         train_loss = torch.zeros((), dtype=torch.float64, device=device)
         metrics.reset()
         index = -1
-        for index, batch in enumerate(train_loader):
+        for index, (batch, nxt) in enumerate(lookahead(train_loader)):
+            if nxt is not None:
+                stepper.prefetch(nxt)                                # H2D of the next batch overlaps this step
             loss3, mask = stepper.step_host(batch)
             train_loss += loss3[0].double() * mask.shape[0]          # stays on device: no .item() in the loop
             metrics.update(stepper.engine.pred, mask)

@@ -126,22 +126,47 @@ class TrainStepMixin:
         self._optimizer()
         return self.loss3
 
-    def capture(self, *args):
+    def capture(self, *args, warmup: int = 2, optimizer_in_graph: bool = True):
         """Capture the step over STATIC input tensors: one CUDA graph on a single GPU; with data parallelism two graphs
-        (forward+loss+backward | Adam) around the eager NCCL all-reduce.  Returns a callable that replays one step."""
+        (forward+loss+backward | optimizer) around the eager NCCL all-reduce.  Returns a callable that replays one step.
+        warmup: real training steps run on `args` before capturing (0 when the caller has already stepped this engine eagerly);
+        optimizer_in_graph=False keeps the optimizer launch eager, so a learning-rate change (hp["lr"], a by-value kernel argument)
+        takes effect without re-capturing."""
         self.params.ensure(self.device)
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            for _ in range(2):
-                self.train_step(*args)
-        torch.cuda.current_stream().wait_stream(s)
+        if warmup > 0:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(warmup):
+                    self.train_step(*args)
+            torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        if self.world == 1:
+        if self.world == 1 and optimizer_in_graph:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.train_step(*args)
             self.replay = self.graph.replay
+        elif self.world == 1:
+            ga = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                self._fwd_loss_bwd(*args)
+            self.graph = ga
+
+            def replay():
+                ga.replay()
+                self._optimizer()
+            self.replay = replay
+        elif not optimizer_in_graph:
+            ga = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga, capture_error_mode="thread_local"):
+                self._fwd_loss_bwd(*args)
+            self.graph = ga
+
+            def replay():
+                ga.replay()
+                self._allreduce()
+                self._optimizer()
+            self.replay = replay
         else:
             ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             # thread_local: NCCL's watchdog thread may issue CUDA calls while this thread captures

@@ -13,6 +13,7 @@ from pathlib import Path
 import torch
 
 from .change_detection_trainer import CLASS_LABELS, unpack_batch
+from .host_pipeline import HostPipelineMixin, lookahead
 from .utilities import ConfusionMetrics, create_loss, init_lr_scheduler
 from .vision_transformer import FinetunerSegmentation, FloodViTUperNet
 
@@ -36,7 +37,7 @@ def stack_inputs(b, configs, device):
     raise SystemExit(1)
 
 
-class FusedSegStepper:
+class FusedSegStepper(HostPipelineMixin):
     """Owns the engine-side training state of a segmentation model (the public fast path)."""
 
     def __init__(self, model, configs, model_configs, process_group=None):
@@ -63,13 +64,10 @@ class FusedSegStepper:
         if self.engine is not None:
             self.engine.hp["lr"] = self.lr
 
-    def step_host(self, batch):
+    def _to_device(self, batch):
         dev = self.configs["device"]
         b = unpack_batch(batch, self.configs)
-        image = stack_inputs(b, self.configs, dev)
-        mask = b["mask"].to(dev, non_blocking=True)
-        eng = self._engine(image)
-        return eng.train_step(image, mask), mask
+        return [stack_inputs(b, self.configs, dev), b["mask"].to(dev, non_blocking=True)]
 
 
 def train_semantic_segmentation(model, train_loader, val_loader, test_loader, configs, model_configs, process_group=None):
@@ -85,7 +83,9 @@ def train_semantic_segmentation(model, train_loader, val_loader, test_loader, co
         train_loss = torch.zeros((), dtype=torch.float64, device=device)
         metrics.reset()
         index, loss3 = -1, None
-        for index, batch in enumerate(train_loader):
+        for index, (batch, nxt) in enumerate(lookahead(train_loader)):
+            if nxt is not None:
+                stepper.prefetch(nxt)
             loss3, mask = stepper.step_host(batch)
             train_loss += loss3[0].double() * mask.shape[0]
             metrics.update(stepper.engine.pred, mask)

@@ -196,3 +196,42 @@ def test_bf16_full_batch_properties():
         del model, eng
         torch.cuda.empty_cache()
     assert abs(losses["bf16"] - losses["fp32"]) < 3e-2 * abs(losses["fp32"]), losses
+
+
+def test_step_host_pipeline_equals_eager_steps():
+    """FusedStepper.step_host (H2D of the next batch on a copy stream, two eager steps, then a CUDA-graph replay per step over static
+    inputs, optimizer launch outside the graph so set_lr takes effect) == the same steps run eagerly on resident tensors."""
+    from kurosiwo_b200 import synthetic
+    from kurosiwo_b200.change_detection_trainer import FusedStepper, select_inputs, unpack_batch
+    base, seed = 8, 41
+    configs = {"device": DEV, "inputs": ["pre_event_1", "post_event"], "dem": False, "scale_input": "normalize", "num_classes": 3,
+               "loss_function": "ce+dice", "class_weights": [1.0, 1.0, 1.0], "method": "snunet"}
+    model_configs = {"method": "snunet", "optimizer": "adam", "learning_rate": 1e-3, "base_channel": base}
+    batches = list(synthetic.SyntheticLoader(2, 6, seed=5, H=64, W=64, pin=True, distinct=6))
+    lrs = [1e-3, 1e-3, 1e-3, 1e-3, 5e-4, 5e-4]
+    ma, mb = (_model(weights.make_state(seed, 2, 3, base), base, "fp32") for _ in range(2))
+    stepper = FusedStepper(ma, configs, model_configs)
+    losses_a = []
+    stepper.prefetch(batches[0])
+    for i, b in enumerate(batches):
+        stepper.set_lr(lrs[i])
+        if i + 1 < len(batches):
+            stepper.prefetch(batches[i + 1])
+        l3, mask = stepper.step_host(b)
+        losses_a.append(l3.clone())
+    assert stepper._pl["replay"] is not None                      # steps 3.. ran as graph replays
+    eng = None
+    losses_b = []
+    for i, b in enumerate(batches):
+        ub = unpack_batch(b, configs)
+        xa, xb = select_inputs(ub, configs, DEV)
+        if eng is None:
+            eng = mb.engine(xa)
+            eng.init_training(lr=1e-3)
+        eng.hp["lr"] = lrs[i]
+        losses_b.append(eng.train_step(xa, xb, ub["mask"].to(DEV)).clone())
+    torch.cuda.synchronize()
+    for la, lb in zip(losses_a, losses_b):
+        np.testing.assert_allclose(la.cpu().numpy(), lb.cpu().numpy(), rtol=1e-4)
+    for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert (pa - pb).abs().max().item() < 2e-4, n          # 6 Adam steps of <= 1e-3 each; fp32 atomics order differs between runs
