@@ -308,6 +308,15 @@ int ks_branch_add(int dtype, int64_t n, int64_t per_sample, void *x, const void 
                   const int *step_ptr, int site, void *stream);
 int ks_branch_scale(int dtype, int64_t n, int64_t per_sample, const void *dx, void *dt, float p, const float *droppath, uint64_t seed,
                     const int *step_ptr, int site, void *stream);
+/* The strided convolutions as GEMMs on the tensor-core conv engine (OverlapPatchEmbed.proj, changeformer.py:281-290; Attention.sr, :166,193):
+ * ks_im2col: col[(n,ho,wo)][(u*k+v)*C + c] = x[n, ho*s-p+u, wo*s-p+v, c] (0 outside the image); col is a dense [N*Ho*Wo, Kp] matrix,
+ * Kp >= k*k*C, columns >= k*k*C are left untouched (the caller zeroes them once).  ks_col2im is the adjoint in gather form:
+ * dx[n,h,w,c] (+)= sum of dcol over the windows containing (h,w).  Then forward = 1x1 ks_conv2d(col, W[Cout][Kp]), weight gradient =
+ * 1x1 ks_conv2d_wgrad(col, dy), data gradient = ks_col2im(1x1 ks_conv2d(dy, W^T)). */
+int ks_im2col(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int ksize, int stride, int pad, const ks_view_t *x, void *col, int Kp,
+              void *stream);
+int ks_col2im(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int ksize, int stride, int pad, const void *dcol, int Kp, const ks_view_t *dx,
+              int accumulate, void *stream);
 /* Depth-wise 3x3 conv, padding 1 (DWConv, changeformer.py:84-96) on dense NHWC; w9: fp32 [9][C] (tap-major), bias fp32 [C].
  * _bwd: dx = data gradient; dw9 += weight gradient, dbias += bias gradient (fp32 atomics, caller zeroes). */
 int ks_dwconv3x3_fwd(int dtype, int N, int H, int W, int C, const void *x, const float *w9, const float *bias, void *y, void *stream);

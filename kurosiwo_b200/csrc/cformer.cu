@@ -578,6 +578,68 @@ static inline int cgrid(long long work, int per_block, int cap_mult = 8) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// im2col / col2im: the strided convolutions (OverlapPatchEmbed.proj 7x7 s4|s2 p3, Attention.sr k = s) as GEMMs on the tensor-core
+// conv engine:  col[(n,ho,wo)][(u*k+v)*C + c] = x[n, ho*s-p+u, wo*s-p+v, c]  (zero outside the image; columns >= k*k*C untouched),
+// forward = col x W^T (1x1 ks_conv2d), weight gradient = 1x1 ks_conv2d_wgrad(col, dy), data gradient = col2im(dy x W).
+// Pure data movement (HBM-bound): one 16-byte (bf16) / 32-byte (fp32) vector per thread.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+im2col_kernel(int N, int Hi, int Wi, int Ho, int Wo, int k, int s, int p, View x, T *__restrict__ col, int Kp) {
+  const int C = x.C, CV = C / VEC, taps = k * k;
+  const long long total = (long long)N * Ho * Wo * taps * CV;
+  const T *xp = reinterpret_cast<const T *>(x.ptr);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV); const int t = (int)((i / CV) % taps); const long long row = i / ((long long)CV * taps);
+    const int wo = (int)(row % Wo), ho = (int)((row / Wo) % Ho); const long long n = row / ((long long)Wo * Ho);
+    const int h = ho * s - p + t / k, w = wo * s - p + t % k;
+    const bool in = h >= 0 && h < Hi && w >= 0 && w < Wi;
+    const T *src = xp + n * x.sn + (long long)h * x.sh + (long long)w * x.sw + cv * VEC;
+    T *dst = col + row * Kp + (long long)t * C + cv * VEC;
+    if (VEC == 1) dst[0] = in ? src[0] : T(0.f);
+    else {
+      constexpr int NV = (VEC * (int)sizeof(T)) / 16;
+#pragma unroll
+      for (int q = 0; q < NV; ++q)
+        reinterpret_cast<uint4 *>(dst)[q] = in ? reinterpret_cast<const uint4 *>(src)[q] : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+// dx[n,h,w,c] (+)= sum over the windows (ho,wo) that contain (h,w) of dcol[(n,ho,wo)][(u*k+v)*C + c], u = h+p-ho*s, v = w+p-wo*s
+template <typename T>
+__global__ void __launch_bounds__(256)
+col2im_kernel(int N, int Hi, int Wi, int Ho, int Wo, int k, int s, int p, const T *__restrict__ dcol, int Kp, View dx, int accumulate) {
+  const int C = dx.C, CV = C / 8;
+  const long long total = (long long)N * Hi * Wi * CV;
+  T *dp = reinterpret_cast<T *>(dx.ptr);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * 8; const long long px = i / CV;
+    const int w = (int)(px % Wi), h = (int)((px / Wi) % Hi); const long long n = px / ((long long)Wi * Hi);
+    float acc[8];
+    T *out = dp + n * dx.sn + (long long)h * dx.sh + (long long)w * dx.sw + c;
+    if (accumulate) ld8(out, acc); else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    }
+    const int ho_lo = max(0, (h + p - k + s) / s), ho_hi = min(Ho - 1, (h + p) / s);      // ho*s <= h+p <= ho*s + k-1
+    const int wo_lo = max(0, (w + p - k + s) / s), wo_hi = min(Wo - 1, (w + p) / s);
+    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+      const int u = h + p - ho * s;
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        const int v = w + p - wo * s;
+        float f[8];
+        ld8(dcol + ((n * Ho + ho) * Wo + wo) * Kp + (long long)(u * k + v) * C + c, f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += f[q];
+      }
+    }
+    st8(out, acc);
+  }
+}
+
 }  // namespace ks
 
 using namespace ks;
@@ -677,6 +739,38 @@ extern "C" int ks_xattention_bwd(int dtype, int B, int Nq, int Nk, int heads, in
     if (e != cudaSuccess) return (int)e; \
     xattention_bwd_kernel<T><<<grid, XA_WARPS * 32, smem, st>>>(Nq, Nk, heads, dh, (const T *)q, ldq, (const T *)kv, ldkv, (const T *)probs, \
                                                                  (const T *)dout, ldo, scale, (T *)dq, lddq, dkv, rpc, pdrop, seed, step_ptr, site); }
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_im2col(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int ksize, int stride, int pad, const ks_view_t *x, void *col,
+                         int Kp, void *stream) {
+  KS_CHECK_ARG(N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && ksize > 0 && stride > 0 && pad >= 0 && x && x->ptr && col);
+  KS_CHECK_ARG(Kp >= ksize * ksize * x->C && (Ho - 1) * stride - pad + ksize - 1 < Hi + pad && (Wo - 1) * stride - pad + ksize - 1 < Wi + pad);
+  const View xv = to_view(*x);
+  const int es = (dtype == KS_F32) ? 4 : 2;
+  const bool vec = xv.C % 8 == 0 && a16(xv.ptr) && a16(col) && (xv.sn * es) % 16 == 0 && (xv.sh * es) % 16 == 0 && (xv.sw * es) % 16 == 0 &&
+                   ((long long)Kp * es) % 16 == 0;
+  const long long items = (long long)N * Ho * Wo * ksize * ksize * (vec ? xv.C / 8 : xv.C);
+  const int grid = cgrid(items, 256);
+#define CALL(T) { if (vec) im2col_kernel<T, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, ksize, stride, pad, xv, (T *)col, Kp); \
+                  else im2col_kernel<T, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, ksize, stride, pad, xv, (T *)col, Kp); }
+  KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_col2im(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int ksize, int stride, int pad, const void *dcol, int Kp,
+                         const ks_view_t *dx, int accumulate, void *stream) {
+  KS_CHECK_ARG(N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && ksize > 0 && stride > 0 && pad >= 0 && dx && dx->ptr && dcol);
+  KS_CHECK_ARG(Kp >= ksize * ksize * dx->C);
+  const View dv = to_view(*dx);
+  const int es = (dtype == KS_F32) ? 4 : 2;
+  if (dv.C % 8 || !a16(dv.ptr) || !a16(dcol) || (dv.sn * es) % 16 || (dv.sh * es) % 16 || (dv.sw * es) % 16 || ((long long)Kp * es) % 16)
+    return KS_EUNSUPPORTED;
+  const int grid = cgrid((long long)N * Hi * Wi * (dv.C / 8), 256);
+#define CALL(T) col2im_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, ksize, stride, pad, (const T *)dcol, Kp, dv, accumulate)
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();

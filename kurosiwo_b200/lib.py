@@ -94,7 +94,7 @@ EXPORTED_SYMBOLS = [
     "ks_ecam_bwd_apply", "ks_ce_dice_workspace_bytes", "ks_ce_dice_fwd_bwd", "ks_ce_dice_fwd_bwd_ex", "ks_adam_step", "ks_sgd_step",
     "ks_softmax_head_fwd", "ks_softmax_head_bwd", "ks_dropout_mask", "ks_channel_scale", "ks_absdiff_fwd", "ks_absdiff_bwd",
     "ks_layernorm_fwd", "ks_layernorm_bwd", "ks_patchify_ln", "ks_patchify_ln_bwd", "ks_vit_assemble", "ks_vit_assemble_bwd",
-    "ks_confusion_update", "ks_attention_fwd", "ks_attention_bwd", "ks_conv2d_strided", "ks_conv2d_strided_dgrad", "ks_conv2d_strided_wgrad",
+    "ks_confusion_update", "ks_attention_fwd", "ks_attention_bwd", "ks_conv2d_strided", "ks_conv2d_strided_dgrad", "ks_conv2d_strided_wgrad", "ks_im2col", "ks_col2im",
     "ks_xattention_fwd", "ks_xattention_bwd", "ks_dwconv3x3_fwd", "ks_dwconv3x3_bwd", "ks_bilinear_nhwc_fwd", "ks_bilinear_nhwc_bwd",
     "ks_relu_fwd", "ks_relu_bwd", "ks_sigmoid_head_fwd", "ks_sigmoid_head_bwd", "ks_dropout_apply", "ks_branch_add", "ks_branch_scale", "ks_gelu_fwd", "ks_gelu_bwd", "ks_bilinear_up_fwd", "ks_bilinear_up_bwd", "ks_adaptive_avgpool_fwd", "ks_adaptive_avgpool_bwd",
 ]
@@ -405,6 +405,16 @@ class CudaOps:
         rc = self.lib.ks_conv2d_strided_wgrad(dtype_code(x.dtype), *[C.c_int(v) for v in (N, Hi, Wi, Ho, Wo, ksize, stride, pad)], _vp(x), _vp(dy),
                                               _p(dw), C.c_int(int(accumulate)), self._stream())
         self._check(rc, "ks_conv2d_strided_wgrad")
+
+    def im2col(self, N, Hi, Wi, Ho, Wo, ksize, stride, pad, x: View, col, Kp):
+        rc = self.lib.ks_im2col(dtype_code(x.dtype), *[C.c_int(v) for v in (N, Hi, Wi, Ho, Wo, ksize, stride, pad)], _vp(x), _p(col), C.c_int(Kp),
+                                self._stream())
+        self._check(rc, "ks_im2col")
+
+    def col2im(self, N, Hi, Wi, Ho, Wo, ksize, stride, pad, dcol, Kp, dx: View, accumulate=False):
+        rc = self.lib.ks_col2im(dtype_code(dx.dtype), *[C.c_int(v) for v in (N, Hi, Wi, Ho, Wo, ksize, stride, pad)], _p(dcol), C.c_int(Kp), _vp(dx),
+                                C.c_int(int(accumulate)), self._stream())
+        self._check(rc, "ks_col2im")
 
     def xattention_fwd(self, B, Nq, Nk, heads, dh, q, kv, scale, out, probs, pdrop=0.0, seed=0, step=None, site=0):
         rc = self.lib.ks_xattention_fwd(dtype_code(q.dtype), *[C.c_int(v) for v in (B, Nq, Nk, heads, dh)], _p(q), C.c_int64(q.stride(0)), _p(kv),

@@ -23,6 +23,9 @@ cases = {
   "L0 dgrad 32->224 acc": (224, [32], [64, 96, 64], 3, False, True),
   "L0 fwd 224->32": (224, [160, 64], [32], 3, True, False),
   "L1 fwd 64->64": (112, [64], [64], 3, True, False),
+  "L0 fwd 32->32": (224, [32], [32], 3, True, False),
+  "L0 dgrad 32->32": (224, [32], [32], 3, False, False),
+  "L1 dgrad 64->384": (112, [64], [256, 128], 3, False, False),
 }
 for name, (H, cins, couts, ks, bias, acc) in cases.items():
     srcs = [buf(H, c) for c in cins]; dsts = [buf(H, c) for c in couts]
@@ -30,9 +33,9 @@ for name, (H, cins, couts, ks, bias, acc) in cases.items():
     w = torch.randn(ks * ks * cout * cin, device=dev).mul_(0.05).to(bf)
     b = torch.zeros(cout, device=dev) if bias else None
     row = {}
-    for dbg in (0, 32, 8, 8 + 4, 16, 16 + 8, 16 + 8 + 4, 16 + 8 + 4 + 32):
+    for dbg in (0, 1, 2, 3, 32, 8, 8 + 4, 16, 16 + 8, 16 + 8 + 4, 16 + 8 + 4 + 32):
         ops.set_option("tc_debug", dbg)
         row[dbg] = round(timeit(lambda: ops.conv2d(N, H, H, ks, srcs, w, b, dsts, [acc] * len(dsts), None, IMPL_TC)), 4)
     ops.set_option("tc_debug", 0)
-    print(f"{name:24s} full={row[0]} spin={row[32]} noepi={row[8]} noepi+nomma={row[12]} notma={row[16]} notma+noepi={row[24]} onlybarriers={row[28]} onlybarriers+spin={row[60]}", flush=True)
+    print(f"{name:24s} full={row[0]} nostore={row[1]} notmemld={row[2]} nostore+notmemld={row[3]} spin={row[32]} noepi={row[8]} noepi+nomma={row[12]} notma={row[16]} notma+noepi={row[24]} onlybarriers={row[28]} onlybarriers+spin={row[60]}", flush=True)
     del srcs, dsts; torch.cuda.empty_cache()

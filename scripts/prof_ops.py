@@ -27,7 +27,7 @@ def wrap(name):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); r = f(*a, **k); e1.record()
         key = name
-        if name in ("conv2d", "conv2d_wgrad"): key = f"{name}[k{a[3]}]"
+        if name in ("conv2d", "conv2d_wgrad"): key = f"{name}[k{a[3]}]" + ("[K>=1024]" if a[3] == 1 and sum(v.C for v in a[4]) >= 1024 else "")
         if name.startswith("conv2d_strided"): key = f"{name}[k{a[5]}s{a[6]}]"
         times.setdefault(key, []).append((e0, e1)); return r
     orig[name] = f; setattr(ops, name, g)

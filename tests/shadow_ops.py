@@ -482,6 +482,27 @@ class ShadowOps:
         out = dw.reshape(-1)[: gw.numel()]
         out.copy_(gw + out if accumulate else gw)
 
+    def im2col(self, N, Hi, Wi, Ho, Wo, ksize, stride, pad, x, col, Kp):
+        xx = F.pad(_t(x).float(), (0, 0, pad, pad, pad, pad))                       # [N, Hi+2p, Wi+2p, C]
+        c = col.view(N, Ho, Wo, Kp)
+        Cn = x.C
+        for u in range(ksize):
+            for v in range(ksize):
+                t = u * ksize + v
+                c[..., t * Cn:(t + 1) * Cn] = xx[:, u:u + (Ho - 1) * stride + 1:stride, v:v + (Wo - 1) * stride + 1:stride, :].to(col.dtype)
+
+    def col2im(self, N, Hi, Wi, Ho, Wo, ksize, stride, pad, dcol, Kp, dx, accumulate=False):
+        Cn = dx.C
+        acc = torch.zeros(N, Hi + 2 * pad + ksize, Wi + 2 * pad + ksize, Cn)
+        c = dcol.view(N, Ho, Wo, Kp).float()
+        for u in range(ksize):
+            for v in range(ksize):
+                t = u * ksize + v
+                acc[:, u:u + (Ho - 1) * stride + 1:stride, v:v + (Wo - 1) * stride + 1:stride, :] += c[..., t * Cn:(t + 1) * Cn]
+        g = acc[:, pad:pad + Hi, pad:pad + Wi, :]
+        t_ = _t(dx)
+        t_.copy_((t_.float() + g if accumulate else g).to(t_.dtype))
+
     @staticmethod
     def _xa_split(B, Nq, Nk, heads, dh, q, kv):
         inner = heads * dh

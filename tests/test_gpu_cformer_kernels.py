@@ -149,3 +149,28 @@ def test_permute_table_scale(ops):
     table = ops.make_permute_table([(src, dst, (4, 6), (1, 4), 0, None, 0, 0.1)], DEV)
     ops.permute_cast_table(table)
     assert torch.allclose(dst.view(4, 6), 0.1 * src.view(6, 4).t())
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("k,s,p,cin,H", [(7, 4, 3, 2, 32), (7, 2, 3, 64, 16), (8, 8, 0, 64, 16), (2, 2, 0, 40, 14), (3, 1, 1, 16, 9)])
+def test_im2col_col2im(ops, sh, dtype, k, s, p, cin, H):
+    """ks_im2col is pure data movement (bit-exact, also on a strided source view); ks_col2im is its adjoint in gather form."""
+    g = torch.Generator().manual_seed(4)
+    N, W = 2, H + 4
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    Kp = (k * k * cin + 63) // 64 * 64
+    x, _ = rand_view(N, H, W, cin, dtype, DEV, ctot=cin + (8 if cin % 8 == 0 else 0), c0=8 if cin % 8 == 0 else 0, gen=g)
+    cx = mirror(x)
+    col_c = _r((N * Ho * Wo, Kp), dtype, g)
+    col_d = col_c.to(DEV)
+    ops.im2col(N, H, W, Ho, Wo, k, s, p, x, col_d, Kp)
+    sh.im2col(N, H, W, Ho, Wo, k, s, p, cx, col_c, Kp)
+    assert torch.equal(col_d.cpu(), col_c)                             # incl. the untouched pad columns
+    if cin % 8 == 0:
+        dcol = _r((N * Ho * Wo, Kp), dtype, g)
+        dx, _ = rand_view(N, H, W, cin, dtype, DEV, ctot=cin + 8, c0=8, gen=g)
+        cdx = mirror(dx)
+        for acc in (False, True):
+            ops.col2im(N, H, W, Ho, Wo, k, s, p, dcol.to(DEV), Kp, dx, acc)
+            sh.col2im(N, H, W, Ho, Wo, k, s, p, dcol, Kp, cdx, acc)
+            assert rel_l2(dx.base.float(), cdx.base.float()) < _tol(dtype)
