@@ -196,7 +196,7 @@ __global__ void bn_finalize_kernel(int C, double count, const double *__restrict
 
 // out = relu(y*scale+shift (+res)), optional fused 2x2 max-pool output
 template <typename T, int V, bool POOL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_act_kernel(View y, View res, bool has_res, View out, View pool, int N, int H, int W,
               const float *__restrict__ scale, const float *__restrict__ shift, int relu, bool flat) {
   const int CV = y.C / V, rows = blockDim.x / CV;
@@ -274,7 +274,7 @@ bn_act_kernel(View y, View res, bool has_res, View out, View pool, int N, int H,
 //   !MASK_OUT: mask = (y*scale+shift > 0)  (== (relu output > 0), recomputed instead of re-read)
 // ------------------------------------------------------------------------------------------
 template <typename T, int V, bool MASK_OUT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce_kernel(View dout, View out, View y, int N, int H, int W, const float *__restrict__ scale,
                      const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ rstd,
                      double *sums, bool flat) {
@@ -400,7 +400,7 @@ bn_bwd_reduce_pool_kernel(View dout, View out, View y, View dpool, int N, int H,
 
 // pass 2: dy = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M) (+ add) = a*g + (k1*y + k0) (+ add);  `premasked`: g already masked by pass 1
 template <typename T, int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_kernel(View gin, View y, View add, bool has_add, View dy, int N, int H, int W, int premasked,
                     const float *__restrict__ scale, const float *__restrict__ shift,
                     const float *__restrict__ mean, const float *__restrict__ rstd, const float *__restrict__ gamma,
@@ -667,7 +667,9 @@ extern "C" int ks_bn_finalize(int C, double count, const double *sums, const flo
 static inline int pl_grid(int C, int V, long long npix, int per_thread) {
   const int CV = C / V, rows = 256 / CV;
   long long g = (npix + (long long)rows * per_thread - 1) / ((long long)rows * per_thread);
-  const long long cap = (long long)kNumSMs * 8;
+  // the vector kernels hold 2 CTAs per SM (98-128 registers): a grid of exactly the resident CTAs, each looping over more pixels,
+  // measured 4-6 % faster than 8 CTAs per SM in 4 waves (scripts/bench_bn.py)
+  const long long cap = (long long)kNumSMs * (g_opt.ew_cap > 0 ? g_opt.ew_cap : 2);
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 

@@ -621,7 +621,7 @@ __device__ __forceinline__ void atc_store_rows(const float *sw, int sp, __nv_bfl
 constexpr int AM_WARPS = 8, AM_T8 = 32;       // up to 32 n8 tiles = 256 keys
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -632,6 +632,11 @@ __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void *p) {
 __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void *p) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   const __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
@@ -653,16 +658,23 @@ __device__ __forceinline__ void am_load_a(uint32_t (&a)[4][4], const __nv_bfloat
 }
 // acc[jt] (+)= A[16 x 64] . M^T where M = [Tp][64] in shared memory (scores against K, or dO against V)
 __device__ __forceinline__ void am_scores(float (&acc)[AM_T8][4], const uint32_t (&a)[4][4], const __nv_bfloat16 *Ms, int NT8, int lane) {
+  // k-outer / tile-inner, two key tiles per step: consecutive MMAs hit different accumulators (the 4 k-steps of one tile are a
+  // dependent chain; issued back to back they left the warp waiting on the MMA latency - ncu: IPC 0.19, "wait" the top stall)
 #pragma unroll
-  for (int jt = 0; jt < AM_T8; ++jt) {
-    if (jt < NT8) {
-      acc[jt][0] = acc[jt][1] = acc[jt][2] = acc[jt][3] = 0.f;
+  for (int jt = 0; jt < AM_T8; ++jt) acc[jt][0] = acc[jt][1] = acc[jt][2] = acc[jt][3] = 0.f;
+  const __nv_bfloat16 *row = Ms + (lane & 7) * ATC_KP + (lane >> 3) * 8;
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        uint32_t r[4];
-        ldsm_x4(r, Ms + (jt * 8 + (lane & 7)) * ATC_KP + h2 * 32 + (lane >> 3) * 8);
-        mma16816(acc[jt], a[2 * h2], r[0], r[1]);
-        mma16816(acc[jt], a[2 * h2 + 1], r[2], r[3]);
+  for (int h2 = 0; h2 < 2; ++h2) {
+#pragma unroll
+    for (int jt = 0; jt < AM_T8; jt += 2) {
+      if (jt < NT8) {                                            // NT8 is even (Tp % 16 == 0)
+        uint32_t r0[4], r1[4];
+        ldsm_x4(r0, row + jt * 8 * ATC_KP + h2 * 32);
+        ldsm_x4(r1, row + (jt + 1) * 8 * ATC_KP + h2 * 32);
+        mma16816(acc[jt], a[2 * h2], r0[0], r0[1]);
+        mma16816(acc[jt + 1], a[2 * h2], r1[0], r1[1]);
+        mma16816(acc[jt], a[2 * h2 + 1], r0[2], r0[3]);
+        mma16816(acc[jt + 1], a[2 * h2 + 1], r1[2], r1[3]);
       }
     }
   }
@@ -723,14 +735,15 @@ attention_fwd_tc_kernel(int Tt, int Tp, int heads, const __nv_bfloat16 *__restri
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
     float l0 = 0.f, l1 = 0.f;
+    const float sl2 = scale * 1.4426950408889634f, m0s = m0 * sl2, m1s = m1 * sl2;
 #pragma unroll
     for (int jt = 0; jt < AM_T8; ++jt) {
       if (jt < NT8) {
         const int c = jt * 8 + 2 * t;
-        s[jt][0] = (c < Tt) ? expf((s[jt][0] - m0) * scale) : 0.f;
-        s[jt][1] = (c + 1 < Tt) ? expf((s[jt][1] - m0) * scale) : 0.f;
-        s[jt][2] = (c < Tt) ? expf((s[jt][2] - m1) * scale) : 0.f;
-        s[jt][3] = (c + 1 < Tt) ? expf((s[jt][3] - m1) * scale) : 0.f;
+        s[jt][0] = (c < Tt) ? ex2_approx(fmaf(s[jt][0], sl2, -m0s)) : 0.f;      // exp((s - m) * scale) as one FFMA + MUFU.EX2
+        s[jt][1] = (c + 1 < Tt) ? ex2_approx(fmaf(s[jt][1], sl2, -m0s)) : 0.f;
+        s[jt][2] = (c < Tt) ? ex2_approx(fmaf(s[jt][2], sl2, -m1s)) : 0.f;
+        s[jt][3] = (c + 1 < Tt) ? ex2_approx(fmaf(s[jt][3], sl2, -m1s)) : 0.f;
         l0 += s[jt][0] + s[jt][1]; l1 += s[jt][2] + s[jt][3];
       }
     }

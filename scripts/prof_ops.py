@@ -11,12 +11,26 @@ torch.manual_seed(0)
 configs = {"device": dev, "inputs": ["pre_event_1", "post_event"], "dem": False, "scale_input": "normalize", "num_classes": 3, "num_channels": 2,
            "loss_function": "ce+dice", "class_weights": [1.0, 1.0, 1.0], "method": wl["method"], "epochs": 1, "precision": "bf16", "resume_checkpoint": False}
 mc = {"method": wl["method"], "optimizer": "adam", "learning_rate": wl["lr"], "lr_schedule": None, "base_channel": 32, "embed_dim": 256, "decoder_softmax": True}
-from kurosiwo_b200.model_utilities import initialize_cd_model
-from kurosiwo_b200.change_detection_trainer import FusedStepper
-model = initialize_cd_model(configs, mc).train()
-stepper = FusedStepper(model, configs, mc)
 b = synthetic.make_batch(999, bs)
-inputs = (b[6].to(dev), b[2].to(dev), b[3].to(dev))
+if wl["task"] == "cd":
+    from kurosiwo_b200.model_utilities import initialize_cd_model
+    from kurosiwo_b200.change_detection_trainer import FusedStepper
+    if wl["method"] == "changeformer":
+        mc.update({"optimizer": "sgd", "momentum": 0.99, "weight_decay": 1e-5})
+    model = initialize_cd_model(configs, mc).train()
+    stepper = FusedStepper(model, configs, mc)
+    inputs = (b[6].to(dev), b[2].to(dev), b[3].to(dev))
+else:
+    from kurosiwo_b200.model_utilities import initialize_segmentation_model
+    from kurosiwo_b200.segmentation_trainer import FusedSegStepper
+    configs.update({"inputs": ["pre_event_1", "pre_event_2", "post_event"], "num_channels": 6, "mlp": False, "decoder": False, "task": "segmentation",
+                    "finetuning_patch_size": 16, "linear_eval": False, "encoder": None})
+    mc["encoder_config"] = {"image_size": 224, "patch_size": 16, "dim": 768, "depth": 12, "heads": 12, "mlp_dim": 3072}
+    if wl_name == "floodvit-upernet":
+        configs["head"] = "upernet"
+    model = initialize_segmentation_model(configs, mc).to(dev).train()
+    stepper = FusedSegStepper(model, configs, mc)
+    inputs = (torch.cat((b[2], b[6], b[9]), 1).to(dev), b[3].to(dev))
 eng = stepper._engine(inputs[0]); ops = eng.ops
 for _ in range(2): eng.train_step(*inputs)
 torch.cuda.synchronize()
