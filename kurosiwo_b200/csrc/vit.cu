@@ -588,7 +588,7 @@ bilinear_up_bwd_kernel(int B, int G, int Tp, int row0, int Cs, int K, int Ho, in
 //   bwd B: dK = scale * dS^T Q, dV = P^T dO   (A operands read column-major straight from the L2-resident P / dS)
 // ---------------------------------------------------------------------------------------------------------
 namespace wm = nvcuda::wmma;
-constexpr int ATC_WARPS = 7, ATC_KP = ATT_DH + 8;      // 72-element bf16 row pitch: 16-byte aligned rows, conflict-light ldmatrix
+constexpr int ATC_WARPS = 7, ATC_SLAB = 24, ATC_KP = ATT_DH + 8;      // 72-element bf16 row pitch: 16-byte aligned rows, conflict-light ldmatrix
 
 __device__ __forceinline__ void atc_load_tile(__nv_bfloat16 *dst, const __nv_bfloat16 *src, long long ld, int rows_valid, int rows_total) {
   for (int i = threadIdx.x; i < rows_total * (ATT_DH / 8); i += blockDim.x) {
@@ -824,58 +824,96 @@ attention_bwd_rows_tc_kernel(int Tt, int Tp, int heads, const __nv_bfloat16 *__r
   }
 }
 
-__global__ void __launch_bounds__(ATC_WARPS * 32)
+// dK = scale * dS^T Q and dV = P^T dO for one (batch, head): one warp owns a 16-KEY strip.  Its 16 columns of P and dS for all
+// queries are staged once in a per-warp shared-memory slab ([Tp][ATC_SLAB], every load in flight together); ldmatrix.trans then hands
+// out the transposed A fragments (A[key][query] = S[query][key]) and the [query][d] B fragments of Q / dO, and the strip's two
+// 16 x 64 results stay in mma.sync accumulators until they are stored.
+__global__ void __launch_bounds__(AM_WARPS * 32, 2)
 attention_bwd_cols_tc_kernel(int Tt, int Tp, int heads, const __nv_bfloat16 *__restrict__ qkv, const __nv_bfloat16 *__restrict__ probs,
                              const __nv_bfloat16 *__restrict__ ds, const __nv_bfloat16 *__restrict__ dout, float scale,
                              __nv_bfloat16 *__restrict__ dqkv) {
   extern __shared__ __align__(128) unsigned char smraw[];
-  const int NT = Tp / 16, SP = 68;
-  __nv_bfloat16 *Qs = reinterpret_cast<__nv_bfloat16 *>(smraw), *Os = Qs + Tp * ATC_KP;
-  float *Sall = reinterpret_cast<float *>(Os + Tp * ATC_KP);
+  const int NT = Tp / 16;
+  __nv_bfloat16 *Qs = reinterpret_cast<__nv_bfloat16 *>(smraw), *Os = Qs + Tp * ATC_KP, *slabs = Os + Tp * ATC_KP;
   const int b = blockIdx.y, h = blockIdx.x, inner = heads * ATT_DH;
   const long long ld = 3LL * inner;
   atc_load_tile(Qs, qkv + (long long)b * Tp * ld + h * ATT_DH, ld, Tt, Tp);
   atc_load_tile(Os, dout + (long long)b * Tp * inner + h * ATT_DH, (long long)inner, Tt, Tp);
   __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float *Sw = Sall + w * 16 * SP;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  // per-warp double-buffered slab: [2 buffers][P, dS][32 queries][ATC_SLAB]
+  __nv_bfloat16 *Ww = slabs + (size_t)w * 2 * 2 * 32 * ATC_SLAB;
   const __nv_bfloat16 *pb = probs + ((long long)b * heads + h) * Tp * Tp, *sb = ds + ((long long)b * heads + h) * Tp * Tp;
-  for (int strip = w; strip < NT; strip += ATC_WARPS) {
+  // ldmatrix.x4.trans source rows: matrices 0..3 = (queries 0-7, keys 0-7), (q 0-7, k 8-15), (q 8-15, k 0-7), (q 8-15, k 8-15)
+  const int a_off = ((lane & 7) + (lane >> 4) * 8) * ATC_SLAB + ((lane >> 3) & 1) * 8;
+  const int lr = lane >> 1, lh = (lane & 1) * 8;               // this lane's slab rows lr, lr + 16 and 8-key half
+  const int NC = (Tp + 31) / 32;                               // 32-query chunks (the last one may hold 16)
+  for (int strip = w; strip < NT; strip += (int)(blockDim.x >> 5)) {
     const int j0 = strip * 16;
-    wm::fragment<wm::accumulator, 16, 16, 16, float> kacc[4], vacc[4];
+    float ok[8][4], ov[8][4];
 #pragma unroll
-    for (int d = 0; d < 4; ++d) { wm::fill_fragment(kacc[d], 0.f); wm::fill_fragment(vacc[d], 0.f); }
-    for (int it = 0; it < NT; ++it) {
-      wm::fragment<wm::matrix_a, 16, 16, 16, __nv_bfloat16, wm::col_major> sa, pa;     // (dS^T)[j][i], (P^T)[j][i]
-      wm::load_matrix_sync(sa, sb + (long long)it * 16 * Tp + j0, (unsigned)Tp);
-      wm::load_matrix_sync(pa, pb + (long long)it * 16 * Tp + j0, (unsigned)Tp);
+    for (int dt = 0; dt < 8; ++dt) { ok[dt][0] = ok[dt][1] = ok[dt][2] = ok[dt][3] = 0.f; ov[dt][0] = ov[dt][1] = ov[dt][2] = ov[dt][3] = 0.f; }
+    uint4 vp[2], vs[2];
+    auto fetch = [&](int c) {
 #pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        wm::fragment<wm::matrix_b, 16, 16, 16, __nv_bfloat16, wm::row_major> qb, ob;
-        wm::load_matrix_sync(qb, Qs + it * 16 * ATC_KP + d * 16, ATC_KP);
-        wm::load_matrix_sync(ob, Os + it * 16 * ATC_KP + d * 16, ATC_KP);
-        wm::mma_sync(kacc[d], sa, qb, kacc[d]);
-        wm::mma_sync(vacc[d], pa, ob, vacc[d]);
+      for (int q = 0; q < 2; ++q) {
+        const int r = c * 32 + q * 16 + lr;
+        if (r < Tp) {
+          vp[q] = *reinterpret_cast<const uint4 *>(pb + (long long)r * Tp + j0 + lh);
+          vs[q] = *reinterpret_cast<const uint4 *>(sb + (long long)r * Tp + j0 + lh);
+        }
       }
+    };
+    fetch(0);
+    for (int c = 0; c < NC; ++c) {
+      __nv_bfloat16 *Pw = Ww + (c & 1) * 2 * 32 * ATC_SLAB, *Dw = Pw + 32 * ATC_SLAB;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        *reinterpret_cast<uint4 *>(Pw + (q * 16 + lr) * ATC_SLAB + lh) = vp[q];
+        *reinterpret_cast<uint4 *>(Dw + (q * 16 + lr) * ATC_SLAB + lh) = vs[q];
+      }
+      __syncwarp();
+      if (c + 1 < NC) fetch(c + 1);                            // the next chunk's loads fly while this chunk's MMAs run
+#pragma unroll
+      for (int k2 = 0; k2 < 2; ++k2) {
+        const int kk = c * 2 + k2;                             // 16 queries per step
+        if (kk < NT) {
+          uint32_t as[4], ap[4];
+          ldsm_x4_t(as, Dw + k2 * 16 * ATC_SLAB + a_off);
+          ldsm_x4_t(ap, Pw + k2 * 16 * ATC_SLAB + a_off);
+          const int brow = (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATC_KP + (lane >> 4) * 8;
+#pragma unroll
+          for (int dp = 0; dp < 4; ++dp) {
+            uint32_t rq[4], ro[4];
+            ldsm_x4_t(rq, Qs + brow + dp * 16);
+            ldsm_x4_t(ro, Os + brow + dp * 16);
+            mma16816(ok[2 * dp], as, rq[0], rq[1]);
+            mma16816(ov[2 * dp], ap, ro[0], ro[1]);
+            mma16816(ok[2 * dp + 1], as, rq[2], rq[3]);
+            mma16816(ov[2 * dp + 1], ap, ro[2], ro[3]);
+          }
+        }
+      }
+      // buffer (c & 1) is rewritten at chunk c + 2; the __syncwarp() of chunk c + 1 orders these ldmatrix reads before that store
     }
+    __syncwarp();
+    const bool ok0 = (j0 + g) < Tt, ok1 = (j0 + g + 8) < Tt;
     __nv_bfloat16 *dk = dqkv + ((long long)b * Tp + j0) * ld + inner + h * ATT_DH;
-#pragma unroll
-    for (int d = 0; d < 4; ++d) wm::store_matrix_sync(Sw + d * 16, kacc[d], SP, wm::mem_row_major);
-    __syncwarp();
-    atc_store_rows(Sw, SP, dk, ld, lane, j0, Tt, scale);
-    __syncwarp();
-#pragma unroll
-    for (int d = 0; d < 4; ++d) wm::store_matrix_sync(Sw + d * 16, vacc[d], SP, wm::mem_row_major);
-    __syncwarp();
-    atc_store_rows(Sw, SP, dk + inner, ld, lane, j0, Tt, 1.f);
-    __syncwarp();
+    am_store_o(ok, dk, ld, g, t, ok0, ok1, scale);
+    am_store_o(ov, dk + inner, ld, g, t, ok0, ok1, 1.f);
   }
 }
 
 static inline size_t atc_smem_rows(int Tp) { return (size_t)2 * Tp * ATC_KP * 2 + 128; }
-static inline size_t atc_smem_cols(int Tp) { return (size_t)2 * Tp * ATC_KP * 2 + (size_t)ATC_WARPS * 16 * 68 * 4 + 128; }
+static inline size_t atc_smem_cols(int Tp, int warps) { return (size_t)2 * Tp * ATC_KP * 2 + (size_t)warps * 2 * 2 * 32 * ATC_SLAB * 2 + 128; }   // Q, dO + per-warp slabs
+static inline int atc_cols_warps(int Tp) {
+  int w = AM_WARPS;
+  while (w > 1 && atc_smem_cols(Tp, w) > 220 * 1024) --w;
+  return w;
+}
 static inline bool atc_ok(int dtype, int T, int Tp, int dh, int heads) {
   return dtype == KS_BF16 && !g_opt.att_simt && dh == ATT_DH && Tp % 16 == 0 && T <= Tp && atc_smem_rows(Tp) <= 220 * 1024 &&
+         atc_smem_cols(Tp, atc_cols_warps(Tp)) <= 220 * 1024 &&
          (Tp * 2) % 16 == 0 && ((3LL * heads * dh) % 8) == 0;
 }
 
@@ -1066,7 +1104,7 @@ extern "C" int ks_attention_bwd(int dtype, int B, int T, int Tp, int heads, int 
     attention_bwd_rows_tc_kernel<<<g, AM_WARPS * 32, atc_smem_rows(Tp), (cudaStream_t)stream>>>(
         T, Tp, heads, (const __nv_bfloat16 *)qkv, (const __nv_bfloat16 *)probs, (const __nv_bfloat16 *)dout, scale, (__nv_bfloat16 *)dqkv,
         (__nv_bfloat16 *)ds_scratch);
-    attention_bwd_cols_tc_kernel<<<g, ATC_WARPS * 32, atc_smem_cols(Tp), (cudaStream_t)stream>>>(
+    attention_bwd_cols_tc_kernel<<<g, atc_cols_warps(Tp) * 32, atc_smem_cols(Tp, atc_cols_warps(Tp)), (cudaStream_t)stream>>>(
         T, Tp, heads, (const __nv_bfloat16 *)qkv, (const __nv_bfloat16 *)probs, (const __nv_bfloat16 *)ds_scratch, (const __nv_bfloat16 *)dout,
         scale, (__nv_bfloat16 *)dqkv);
     KS_LAUNCH_RET();
