@@ -70,67 +70,101 @@ layernorm_fwd_kernel(long long rows, int C, const T *__restrict__ x, long long l
   }
 }
 
-// LayerNorm backward (C <= 1024): dx (+)= rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma;
-// dgamma += sum_rows dy*xhat, dbeta += sum_rows dy (register accumulators -> smem -> one fp32 atomic per column per CTA).
+// LayerNorm backward (C <= 1024), two kernels:
+//   rows: dx (+)= rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma.  L = min(32, pow2 >= C/8) lanes own one row (32/L rows per warp,
+//         so narrow rows - the 64-channel ChangeFormer stage - keep every lane busy), K = ceil(C / (8 L)) vectors per lane.
+//   cols: dgamma += sum_rows dy*xhat, dbeta += sum_rows dy, thread = 8 channels x a row lane (coalesced over C, no cross-lane traffic
+//         per row); dy and x are re-read, for the ViT / ChangeFormer sizes out of L2.
+// (One fused kernel with register column accumulators needed 218 registers: 8 warps per SM and 1.1-1.5 TB/s.)
 constexpr int LNB_KMAX = 4;
 
-template <typename T>
-__global__ void __launch_bounds__(256)
-layernorm_bwd_kernel(long long rows, int C, const T *__restrict__ dy, long long lddy, const T *__restrict__ x, long long ldx,
-                     const float *__restrict__ mean, const float *__restrict__ rstd, const float *__restrict__ gamma,
-                     T *__restrict__ dx, long long lddx, int acc_dx, float *__restrict__ dgamma, float *__restrict__ dbeta) {
-  extern __shared__ float sred[];     // [2][C]
+template <typename T, int K>
+__global__ void __launch_bounds__(256, 2)
+layernorm_bwd_rows_kernel(long long rows, int C, int L, const T *__restrict__ dy, long long lddy, const T *__restrict__ x, long long ldx,
+                          const float *__restrict__ mean, const float *__restrict__ rstd, const float *__restrict__ gamma,
+                          T *__restrict__ dx, long long lddx, int acc_dx) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
-  __syncthreads();
-  float ag[LNB_KMAX][8], ab[LNB_KMAX][8], gm[LNB_KMAX][8];
+  const int rpw = 32 / L, sub = lane / L, sl = lane % L;
+  float gm[K][8];
 #pragma unroll
-  for (int k = 0; k < LNB_KMAX; ++k) {
-    const int c = (k * 32 + lane) * 8;
+  for (int k = 0; k < K; ++k) {
+    const int c = (k * L + sl) * 8;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { ag[k][i] = 0.f; ab[k][i] = 0.f; gm[k][i] = 0.f; }
+    for (int i = 0; i < 8; ++i) gm[k][i] = 0.f;
     if (c < C) ld8(gamma + c, gm[k]);
   }
-  for (long long r = (long long)blockIdx.x * wpb + wib; r < rows; r += (long long)gridDim.x * wpb) {
-    const float mu = mean[r], rs = rstd[r];
-    float g[LNB_KMAX][8], xh[LNB_KMAX][8];
+  const float invC = 1.f / (float)C;
+  for (long long r0 = ((long long)blockIdx.x * wpb + wib) * rpw; r0 < rows; r0 += (long long)gridDim.x * wpb * rpw) {
+    const long long r = r0 + sub;
+    const bool live = r < rows;
+    const float mu = live ? mean[r] : 0.f, rs = live ? rstd[r] : 0.f;
+    float g[K][8], xh[K][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < LNB_KMAX; ++k) {
-      const int c = (k * 32 + lane) * 8;
-      if (c < C) {
+    for (int k = 0; k < K; ++k) {
+      const int c = (k * L + sl) * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { g[k][i] = 0.f; xh[k][i] = 0.f; }
+      if (live && c < C) {
         float d[8], xv[8];
         ldv8(dy + r * lddy + c, d); ldv8(x + r * ldx + c, xv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           xh[k][i] = (xv[i] - mu) * rs;
-          ag[k][i] += d[i] * xh[k][i]; ab[k][i] += d[i];
           g[k][i] = d[i] * gm[k][i];
           s1 += g[k][i]; s2 += g[k][i] * xh[k][i];
         }
       }
     }
-    if (dx) {
-      const float m1 = warp_sum(s1) / (float)C, m2 = warp_sum(s2) / (float)C;
+    for (int o = L >> 1; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    const float m1 = s1 * invC, m2 = s2 * invC;
 #pragma unroll
-      for (int k = 0; k < LNB_KMAX; ++k) {
-        const int c = (k * 32 + lane) * 8;
-        if (c < C) {
-          float o[8];
-          if (acc_dx) ldv8(dx + r * lddx + c, o);
+    for (int k = 0; k < K; ++k) {
+      const int c = (k * L + sl) * 8;
+      if (live && c < C) {
+        float o[8];
+        if (acc_dx) ldv8(dx + r * lddx + c, o);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { const float t = rs * (g[k][i] - m1 - xh[k][i] * m2); o[i] = acc_dx ? o[i] + t : t; }
-          stv8(dx + r * lddx + c, o);
-        }
+        for (int i = 0; i < 8; ++i) { const float t = rs * (g[k][i] - m1 - xh[k][i] * m2); o[i] = acc_dx ? o[i] + t : t; }
+        stv8(dx + r * lddx + c, o);
       }
     }
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_cols_kernel(long long rows, int C, const T *__restrict__ dy, long long lddy, const T *__restrict__ x, long long ldx,
+                          const float *__restrict__ mean, const float *__restrict__ rstd, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+  extern __shared__ float sred[];     // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  const int CV = C / 8, cvb = min(CV, 256), rl = 256 / cvb;           // channel vectors per pass, row lanes
+  const int tx = threadIdx.x % cvb, ty = threadIdx.x / cvb;
+  if (ty < rl) {
+    for (int cv = tx; cv < CV; cv += cvb) {
+      const int c = cv * 8;
+      float ag[8], ab[8];
 #pragma unroll
-  for (int k = 0; k < LNB_KMAX; ++k) {
-    const int c = (k * 32 + lane) * 8;
-    if (c < C) {
+      for (int i = 0; i < 8; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+      const long long stride = (long long)gridDim.x * rl;
+      for (long long r0 = (long long)blockIdx.x * rl + ty; r0 < rows; r0 += 4 * stride) {
+        float d[4][8], xv[4][8], mu[4], rs[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { atomicAdd(&sred[c + i], ag[k][i]); atomicAdd(&sred[C + c + i], ab[k][i]); }
+        for (int u = 0; u < 4; ++u) {
+          const long long r = r0 + u * stride;
+          if (r < rows) { ldv8(dy + r * lddy + c, d[u]); ldv8(x + r * ldx + c, xv[u]); mu[u] = mean[r]; rs[u] = rstd[r]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (r0 + u * stride < rows) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ag[i] = fmaf(d[u][i], (xv[u][i] - mu[u]) * rs[u], ag[i]); ab[i] += d[u][i]; }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { atomicAdd(&sred[c + i], ag[i]); atomicAdd(&sred[C + c + i], ab[i]); }
     }
   }
   __syncthreads();
@@ -486,15 +520,36 @@ attention_bwd_cols_kernel(int Tt, int Tp, int heads, const T *__restrict__ qkv, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// GELU (exact erf, nn.GELU default)
+// GELU (exact-erf form, nn.GELU default).  fp32 storage (parity mode): erff / expf.  bf16 storage: erf by Abramowitz-Stegun 7.1.26
+// (|error| < 2e-7 + the MUFU approximations, three orders below bf16 resolution) - with erff the kernels were instruction-bound
+// (~40 instructions per element) at half the HBM rate; the backward shares the one exponential between erf and the Gaussian.
 // ---------------------------------------------------------------------------------------------------------
+template <typename T> struct GeluMath {
+  static __device__ __forceinline__ void eval(float x, float &cdf, float &pdf_x) {          // Phi(x), x * phi(x)
+    cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+    pdf_x = x * 0.3989422804014327f * expf(-0.5f * x * x);
+  }
+};
+template <> struct GeluMath<__nv_bfloat16> {
+  static __device__ __forceinline__ void eval(float x, float &cdf, float &pdf_x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    float e, t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));     // exp(-x^2/2)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f); p = fmaf(p, t, -0.284496736f); p = fmaf(p, t, 0.254829592f);
+    const float erfc_z = p * t * e;                                                          // 1 - erf(z), z >= 0
+    cdf = (x >= 0.f) ? 1.f - 0.5f * erfc_z : 0.5f * erfc_z;
+    pdf_x = x * 0.3989422804014327f * e;
+  }
+};
 template <typename T>
 __global__ void __launch_bounds__(256) gelu_fwd_kernel(long long n8, const T *__restrict__ u, T *__restrict__ hout) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float f[8];
     ldv8(u + i * 8, f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = 0.5f * f[k] * (1.f + erff(f[k] * 0.70710678118654752f));
+    for (int k = 0; k < 8; ++k) { float c, px; GeluMath<T>::eval(f[k], c, px); f[k] *= c; }
     stv8(hout + i * 8, f);
   }
 }
@@ -504,11 +559,7 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(long long n8, const T *__
     float f[8], g[8];
     ldv8(u + i * 8, f); ldv8(dh + i * 8, g);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float x = f[k];
-      const float d = 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
-      g[k] *= d;
-    }
+    for (int k = 0; k < 8; ++k) { float c, px; GeluMath<T>::eval(f[k], c, px); g[k] *= c + px; }
     stv8(du + i * 8, g);
   }
 }
@@ -999,12 +1050,28 @@ extern "C" int ks_layernorm_bwd(int dtype, int64_t rows, int C, const void *dy, 
   KS_CHECK_ARG(rows > 0 && C > 0 && dy && x && mean && rstd && gamma);
   if (C % 8 || C > LNB_KMAX * 256 || lddy % 8 || ldx % 8 || (dx && lddx % 8) || !al16(dy) || !al16(x) || !al16(gamma) || (dx && !al16(dx)))
     return KS_EUNSUPPORTED;
-  const int grid = grid_for(rows, 8 * 8, 2);     // >= 8 rows per warp so that the per-CTA column atomics amortise (more, smaller CTAs measured slower)
-  const size_t smem = (size_t)2 * C * sizeof(float);
-#define CALL(T) layernorm_bwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(rows, C, (const T *)dy, lddy, (const T *)x, ldx, mean, rstd, \
-                                                                                     gamma, (T *)dx, lddx, accumulate_dx, dgamma, dbeta)
-  KS_DISPATCH_T(dtype, CALL);
+  cudaStream_t st = (cudaStream_t)stream;
+  int L = 1;
+  while (L < 32 && L * 8 < C) L <<= 1;
+  const int K = (C + 8 * L - 1) / (8 * L);
+  if (dx) {
+    const int grid = grid_for(rows, 8 * (32 / L) * 2, 4);
+#define CALL(T) { \
+    if (K == 1) layernorm_bwd_rows_kernel<T, 1><<<grid, 256, 0, st>>>(rows, C, L, (const T *)dy, lddy, (const T *)x, ldx, mean, rstd, gamma, (T *)dx, lddx, accumulate_dx); \
+    else if (K == 2) layernorm_bwd_rows_kernel<T, 2><<<grid, 256, 0, st>>>(rows, C, L, (const T *)dy, lddy, (const T *)x, ldx, mean, rstd, gamma, (T *)dx, lddx, accumulate_dx); \
+    else if (K == 3) layernorm_bwd_rows_kernel<T, 3><<<grid, 256, 0, st>>>(rows, C, L, (const T *)dy, lddy, (const T *)x, ldx, mean, rstd, gamma, (T *)dx, lddx, accumulate_dx); \
+    else layernorm_bwd_rows_kernel<T, 4><<<grid, 256, 0, st>>>(rows, C, L, (const T *)dy, lddy, (const T *)x, ldx, mean, rstd, gamma, (T *)dx, lddx, accumulate_dx); }
+    KS_DISPATCH_T(dtype, CALL);
 #undef CALL
+  }
+  if (dgamma || dbeta) {
+    const int cvb = (C / 8) < 256 ? (C / 8) : 256, rl = 256 / cvb;
+    const int grid = grid_for(rows, rl * 16, 4);        // >= 16 rows per thread so that the per-CTA column atomics amortise
+    const size_t smem = (size_t)2 * C * sizeof(float);
+#define CALL(T) layernorm_bwd_cols_kernel<T><<<grid, 256, smem, st>>>(rows, C, (const T *)dy, lddy, (const T *)x, ldx, mean, rstd, dgamma, dbeta)
+    KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+  }
   KS_LAUNCH_RET();
 }
 

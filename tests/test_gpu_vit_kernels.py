@@ -48,7 +48,7 @@ def test_layernorm_fwd(ops, sh, dtype, rows, C):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("rows,C,acc", [(37, 64, False), (416, 768, True), (100, 1024, False)])
+@pytest.mark.parametrize("rows,C,acc", [(37, 64, False), (1001, 64, True), (130, 128, False), (77, 320, True), (300, 512, False), (416, 768, True), (100, 1024, False), (5, 8, False)])
 def test_layernorm_bwd(ops, sh, dtype, rows, C, acc):
     g = torch.Generator().manual_seed(2)
     x, dy = _r((rows, C), dtype, g, 2.0, 0.5), _r((rows, C), dtype, g)
