@@ -331,6 +331,107 @@ xattention_bwd_kernel(int Nq, int Nk, int heads, int dh, const T *__restrict__ q
   }
 }
 
+// dh == 64 variant: the same per-row pass (one warp per query row: dP, softmax backward, dQ) writes the row's q, dO, dropped P and
+// dS into a 32-row shared-memory batch; then ALL threads fold the batch into register accumulators - thread = (16 keys, one d):
+// dK[j][d] += sum_r dS[r][j] q[r][d], dV[j][d] += sum_r Pdrop[r][j] dO[r][d] - with float4 broadcast reads.  (The generic kernel above
+// issues 4 shared-memory atomics per (row, key, d): 9 ms of the 60 ms ChangeFormer step.)
+constexpr int XB_ROWS = 32, XB_D = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(XA_WARPS * 32)
+xattention_bwd64_kernel(int Nq, int Nk, int heads, const T *__restrict__ q, long long ldq, const T *__restrict__ kv, long long ldkv,
+                        const T *__restrict__ probs, const T *__restrict__ dout, long long ldo, float scale, T *__restrict__ dq, long long lddq,
+                        float *__restrict__ dkv, int rows_per_cta, float pdrop, unsigned long long seed, const int *step_ptr, int site) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int dh = XB_D, P = XB_D + 1;
+  const unsigned long long dkey = cf_key(seed, step_ptr, site);
+  const float ikeep = 1.f / (1.f - pdrop);
+  float *Sb = sm, *Pb = Sb + XB_ROWS * XA_KMAX, *Qb = Pb + XB_ROWS * XA_KMAX, *Ob = Qb + XB_ROWS * XB_D, *Ks = Ob + XB_ROWS * XB_D,
+        *Vs = Ks + Nk * P;
+  const int b = blockIdx.z, h = blockIdx.y, inner = heads * dh;
+  const T *kvb = kv + (long long)b * Nk * ldkv + h * dh;
+  xa_load(Ks, kvb, ldkv, Nk, dh);
+  xa_load(Vs, kvb + inner, ldkv, Nk, dh);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int td = threadIdx.x & 63, tj = (threadIdx.x >> 6) * 16;          // phase 2: this thread's d and its 16-key block
+  float aK[16], aV[16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) { aK[m] = 0.f; aV[m] = 0.f; }
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(Nq, r0 + rows_per_cta);
+  for (int rb = r0; rb < r1; rb += XB_ROWS) {
+    __syncthreads();                                   // K/V loaded (first batch); phase 2 of the previous batch done
+    for (int slot = w; slot < XB_ROWS; slot += XA_WARPS) {
+      const int i = rb + slot;
+      float *qw = Qb + slot * XB_D, *ow = Ob + slot * XB_D, *pw = Pb + slot * XA_KMAX, *sw = Sb + slot * XA_KMAX;
+      if (i >= r1) {                                   // ragged tail: an all-zero row adds nothing in phase 2
+        for (int j = lane; j < XA_KMAX; j += 32) { pw[j] = 0.f; sw[j] = 0.f; }
+        for (int d = lane; d < dh; d += 32) { qw[d] = 0.f; ow[d] = 0.f; }
+        continue;
+      }
+      const T *qrow = q + ((long long)b * Nq + i) * ldq + h * dh;
+      const T *dorow = dout + ((long long)b * Nq + i) * ldo + h * dh;
+      const T *prow = probs + (((long long)b * heads + h) * Nq + i) * Nk;
+      for (int d = lane; d < dh; d += 32) { qw[d] = Cvt<T>::ld(qrow + d); ow[d] = Cvt<T>::ld(dorow + d); }
+      __syncwarp();
+      float dp[2], pv[2], kf[2], dot = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = jj * 32 + lane;
+        dp[jj] = 0.f; pv[jj] = 0.f; kf[jj] = 1.f;
+        if (j < Nk) {
+          float a = 0.f;
+          const float *vp = Vs + j * P;
+#pragma unroll 16
+          for (int d = 0; d < dh; ++d) a = fmaf(ow[d], vp[d], a);
+          if (pdrop > 0.f) kf[jj] = cf_keep(dkey, (unsigned long long)((((long long)b * heads + h) * Nq + i) * Nk + j), pdrop, ikeep);
+          dp[jj] = a * kf[jj]; pv[jj] = Cvt<T>::ld(prow + j);
+          dot += dp[jj] * pv[jj];
+        }
+      }
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = jj * 32 + lane;
+        const bool in = j < Nk;
+        pw[j] = in ? pv[jj] * kf[jj] : 0.f;
+        sw[j] = in ? pv[jj] * (dp[jj] - dot) * scale : 0.f;
+      }
+      __syncwarp();
+      T *dqrow = dq + ((long long)b * Nq + i) * lddq + h * dh;
+      for (int d = lane; d < dh; d += 32) {
+        float o = 0.f;
+        for (int j = 0; j < Nk; ++j) o = fmaf(sw[j], Ks[j * P + d], o);
+        Cvt<T>::st(dqrow + d, o);
+      }
+    }
+    __syncthreads();
+    if (tj < Nk) {
+#pragma unroll 4
+      for (int r = 0; r < XB_ROWS; ++r) {
+        const float qd = Qb[r * XB_D + td], od = Ob[r * XB_D + td];
+        const float4 *s4 = reinterpret_cast<const float4 *>(Sb + r * XA_KMAX + tj), *p4 = reinterpret_cast<const float4 *>(Pb + r * XA_KMAX + tj);
+#pragma unroll
+        for (int m4 = 0; m4 < 4; ++m4) {
+          const float4 sv = s4[m4], pv4 = p4[m4];
+          aK[4 * m4] = fmaf(sv.x, qd, aK[4 * m4]); aK[4 * m4 + 1] = fmaf(sv.y, qd, aK[4 * m4 + 1]);
+          aK[4 * m4 + 2] = fmaf(sv.z, qd, aK[4 * m4 + 2]); aK[4 * m4 + 3] = fmaf(sv.w, qd, aK[4 * m4 + 3]);
+          aV[4 * m4] = fmaf(pv4.x, od, aV[4 * m4]); aV[4 * m4 + 1] = fmaf(pv4.y, od, aV[4 * m4 + 1]);
+          aV[4 * m4 + 2] = fmaf(pv4.z, od, aV[4 * m4 + 2]); aV[4 * m4 + 3] = fmaf(pv4.w, od, aV[4 * m4 + 3]);
+        }
+      }
+    }
+  }
+  float *dkvb = dkv + (long long)b * Nk * (2 * inner) + h * dh;
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    const int j = tj + m;
+    if (j < Nk) {
+      atomicAdd(dkvb + (long long)j * (2 * inner) + td, aK[m]);
+      atomicAdd(dkvb + (long long)j * (2 * inner) + inner + td, aV[m]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Depth-wise 3x3 convolution (padding 1) on dense NHWC [N,H,W,C]; weights [9][C] fp32 (tap-major), bias [C].
 // ---------------------------------------------------------------------------------------------------------
@@ -735,6 +836,16 @@ extern "C" int ks_xattention_bwd(int dtype, int B, int Nq, int Nk, int heads, in
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e0 = cudaMemsetAsync(dkv, 0, sizeof(float) * (size_t)B * Nk * 2 * heads * dh, st); if (e0 != cudaSuccess) return (int)e0;
   dim3 grid((unsigned)nblk, (unsigned)heads, (unsigned)B);
+  if (dh == XB_D && XA_WARPS * 32 == 4 * XB_D) {
+    const size_t smem64 = ((size_t)2 * XB_ROWS * XA_KMAX + (size_t)2 * XB_ROWS * XB_D + (size_t)2 * Nk * (XB_D + 1)) * sizeof(float);
+#define CALL(T) { cudaError_t e = cudaFuncSetAttribute(xattention_bwd64_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); \
+    if (e != cudaSuccess) return (int)e; \
+    xattention_bwd64_kernel<T><<<grid, XA_WARPS * 32, smem64, st>>>(Nq, Nk, heads, (const T *)q, ldq, (const T *)kv, ldkv, (const T *)probs, \
+                                                                    (const T *)dout, ldo, scale, (T *)dq, lddq, dkv, rpc, pdrop, seed, step_ptr, site); }
+    KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+    KS_LAUNCH_RET();
+  }
 #define CALL(T) { cudaError_t e = cudaFuncSetAttribute(xattention_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); \
     if (e != cudaSuccess) return (int)e; \
     xattention_bwd_kernel<T><<<grid, XA_WARPS * 32, smem, st>>>(Nq, Nk, heads, dh, (const T *)q, ldq, (const T *)kv, ldkv, (const T *)probs, \
