@@ -34,7 +34,56 @@ __global__ void __launch_bounds__(256)
 permute_cast_batched_kernel(const ks_permute_job_t *__restrict__ jobs, const int2 *__restrict__ chunks) {
   const int2 ch = chunks[blockIdx.x];
   const ks_permute_job_t j = jobs[ch.x];
+  if (j.dst_strided == 2) {
+    // 2-D transpose job (dst[a][b] = src[a + b*s1], contiguous dst [d0][d1]): chunk = one 64 x 64 tile through shared memory, so
+    // that BOTH the reads (along a) and the writes (along b) are coalesced - the packed data-gradient copies of every Linear weight
+    __shared__ float tile[64][65];
+    const int A = (int)(j.total / j.d1), B = j.d1;
+    const int tiles_b = (B + 63) / 64;
+    const int a0 = (ch.y / tiles_b) * 64, b0 = (ch.y % tiles_b) * 64;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    for (int k = ty; k < 64; k += 4) {
+      const int a = a0 + tx, b = b0 + k;
+      if (a < A && b < B) {
+        const long long so = (long long)a * j.s0 + (long long)b * j.s1;
+        tile[k][tx] = (j.src_dtype == KS_F32) ? reinterpret_cast<const float *>(j.src)[so]
+                                              : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(j.src)[so]);
+      }
+    }
+    __syncthreads();
+    for (int k = ty; k < 64; k += 4) {
+      const int a = a0 + k, b = b0 + tx;
+      if (a < A && b < B) {
+        float v = tile[tx][k];
+        if (j.scale != 0.f) v *= j.scale;
+        const long long di = (long long)a * B + b;
+        if (j.dst_dtype == KS_F32) reinterpret_cast<float *>(j.dst)[di] = v;
+        else reinterpret_cast<__nv_bfloat16 *>(j.dst)[di] = __float2bfloat16_rn(v);
+      }
+    }
+    return;
+  }
   const long long end = min((long long)j.total, (long long)ch.y + 4096);
+  if (j.d1 == 1 && j.d2 == 1 && j.d3 == 1 && j.s0 == 1 && !j.dst_strided && !j.accumulate && j.src_dtype == KS_F32 && j.dst_dtype == KS_BF16 &&
+      (ch.y & 7) == 0 && (((uintptr_t)j.src) & 31) == 0 && (((uintptr_t)j.dst) & 15) == 0) {
+    // contiguous fp32 -> bf16 cast (the forward copies of the Linear weights): 8 elements per thread and pass
+    const float *sp = reinterpret_cast<const float *>(j.src);
+    __nv_bfloat16 *dp = reinterpret_cast<__nv_bfloat16 *>(j.dst);
+    for (long long i = ch.y + 8LL * threadIdx.x; i < end; i += 8LL * blockDim.x) {
+      if (i + 8 <= end) {
+        float f[8];
+        ld8(sp + i, f);
+        if (j.scale != 0.f) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] *= j.scale;
+        }
+        st8(dp + i, f);
+      } else {
+        for (long long q = i; q < end; ++q) dp[q] = __float2bfloat16_rn(j.scale != 0.f ? sp[q] * j.scale : sp[q]);
+      }
+    }
+    return;
+  }
   for (long long i = ch.y + threadIdx.x; i < end; i += blockDim.x) {
     long long r = i;
     const int i3 = (int)(r % j.d3); r /= j.d3;

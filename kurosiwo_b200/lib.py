@@ -168,9 +168,17 @@ class CudaOps:
                 doff = job[6] if len(job) > 6 else 0
                 strided = 1
             scale = float(job[7]) if len(job) > 7 and job[7] is not None else 0.0          # 0 = no scaling
+            # 2-D transposes with a unit source stride along the SLOW destination dimension (the [in][out] data-gradient copies of
+            # Linear weights): tiled through shared memory (dst_strided = 2, chunk = 64 x 64 tile index)
+            tiled = (not strided and d[2] == 1 and d[3] == 1 and st[0] == 1 and st[1] >= d[0] and d[0] >= 64 and d[1] >= 64)
+            if tiled:
+                strided = 2
             rec[i] = (src.data_ptr() + off * src.element_size(), dst.data_ptr() + doff * dst.element_size(), total, st, d[1:],
                       dtype_code(src.dtype), dtype_code(dst.dtype), 0, dstr, strided, scale)
-            chunks += [(i, c0) for c0 in range(0, total, 4096)]
+            if tiled:
+                chunks += [(i, t) for t in range(((d[0] + 63) // 64) * ((d[1] + 63) // 64))]
+            else:
+                chunks += [(i, c0) for c0 in range(0, total, 4096)]
         jobs_dev = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()).to(device)
         chunks_dev = torch.tensor(chunks, dtype=torch.int32, device=device).reshape(-1)
         return (jobs_dev, chunks_dev, len(chunks), [j[:2] for j in jobs])

@@ -120,9 +120,12 @@ def test_permute_cast(ops, sh):
 
 def test_permute_cast_batched(ops, sh):
     g = _gen(9)
-    srcs = [torch.randn(n, generator=g).to(DEV) for n in (9 * 40 * 24, 4 * 16 * 16, 5000)]
+    srcs = [torch.randn(n, generator=g).to(DEV) for n in (9 * 40 * 24, 4 * 16 * 16, 5000, 200 * 136, 72 * 100, 8200)]
     jobs, cjobs = [], []
-    specs = [((9, 24, 40), (-1, 9, 216), 8, torch.bfloat16), ((16, 4, 16), (64, 1, 4), 0, torch.float32), ((5000,), (1,), 0, torch.bfloat16)]
+    specs = [((9, 24, 40), (-1, 9, 216), 8, torch.bfloat16), ((16, 4, 16), (64, 1, 4), 0, torch.float32), ((5000,), (1,), 0, torch.bfloat16),
+             ((136, 200), (1, 136), 0, torch.bfloat16),        # [out=200][in=136] -> [in][out]: the tiled-transpose path (ragged tiles)
+             ((72, 100), (1, 72), 0, torch.float32),           # the same, fp32 destination
+             ((8192,), (1,), 8, torch.bfloat16)]               # vectorised contiguous cast (32-byte aligned source offset)
     for src, (dims, strides, off, dt) in zip(srcs, specs):
         n = 1
         for d in dims:
