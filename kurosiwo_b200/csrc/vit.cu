@@ -594,40 +594,48 @@ bilinear_up_fwd_kernel(int B, int G, int Tp, int row0, int Cs, int K, int Ho, in
   }
 }
 
-// Adjoint, gather form (deterministic): one thread per (b, source row t in [0,Tp), channel c in [0,Cs)).
+// Adjoint, gather form (deterministic): one WARP per (b, source row t in [0,Tp)); the lanes split the columns of the cell's
+// footprint in the output image (coalesced row reads of the K gradient planes), the Cs outputs of the row are written by lanes 0..Cs-1.
+// (One thread per (row, channel) left 3 of every Cs threads looping over a ~36 x 36 footprint: 0.3-0.5 ms per step.)
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 bilinear_up_bwd_kernel(int B, int G, int Tp, int row0, int Cs, int K, int Ho, int Wo, const float *__restrict__ ddst, T *__restrict__ dsrc) {
-  const long long total = (long long)B * Tp * Cs;
+  const int lane = threadIdx.x & 31;
+  const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5, total = (long long)B * Tp;
   const float ry = (float)G / (float)Ho, rx = (float)G / (float)Wo;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % Cs), t = (int)((i / Cs) % Tp), b = (int)(i / ((long long)Cs * Tp));
-    float acc = 0.f;
+  for (long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += nwarp) {
+    const int t = (int)(item % Tp), b = (int)(item / Tp);
     const int cell = t - row0;
-    if (c < K && cell >= 0 && cell < G * G) {
+    float mine = 0.f;                                   // lane c keeps channel c's result
+    if (cell >= 0 && cell < G * G) {
       const int gy = cell / G, gx = cell % G;
       int ylo = (int)floorf(((float)gy - 0.5f) / ry - 0.5f) - 1, yhi = (int)ceilf(((float)gy + 1.5f) / ry - 0.5f) + 1;
       int xlo = (int)floorf(((float)gx - 0.5f) / rx - 0.5f) - 1, xhi = (int)ceilf(((float)gx + 1.5f) / rx - 0.5f) + 1;
       if (gy == 0) ylo = 0; if (gy == G - 1) yhi = Ho - 1;
       if (gx == 0) xlo = 0; if (gx == G - 1) xhi = Wo - 1;
       ylo = max(ylo, 0); yhi = min(yhi, Ho - 1); xlo = max(xlo, 0); xhi = min(xhi, Wo - 1);
-      const float *gp = ddst + ((long long)b * K + c) * Ho * Wo;
-      for (int y = ylo; y <= yhi; ++y) {
-        int y0, y1; float ly;
-        bil_src(y, ry, G, y0, y1, ly);
-        const float wy = ((y0 == gy) ? (1.f - ly) : 0.f) + ((y1 == gy) ? ly : 0.f);
-        if (wy == 0.f) continue;
-        float rowacc = 0.f;
-        for (int x = xlo; x <= xhi; ++x) {
+      for (int c = 0; c < K; ++c) {
+        const float *gp = ddst + ((long long)b * K + c) * Ho * Wo;
+        float acc = 0.f;
+        for (int x = xlo + lane; x <= xhi; x += 32) {
           int x0, x1; float lx;
           bil_src(x, rx, G, x0, x1, lx);
           const float wx = ((x0 == gx) ? (1.f - lx) : 0.f) + ((x1 == gx) ? lx : 0.f);
-          if (wx != 0.f) rowacc = fmaf(wx, gp[(long long)y * Wo + x], rowacc);
+          if (wx == 0.f) continue;
+          float col = 0.f;
+          for (int y = ylo; y <= yhi; ++y) {
+            int y0, y1; float ly;
+            bil_src(y, ry, G, y0, y1, ly);
+            const float wy = ((y0 == gy) ? (1.f - ly) : 0.f) + ((y1 == gy) ? ly : 0.f);
+            if (wy != 0.f) col = fmaf(wy, gp[(long long)y * Wo + x], col);
+          }
+          acc = fmaf(wx, col, acc);
         }
-        acc = fmaf(wy, rowacc, acc);
+        acc = warp_sum(acc);
+        if (lane == c) mine = acc;
       }
     }
-    Cvt<T>::st(dsrc + i, acc);
+    for (int c = lane; c < Cs; c += 32) Cvt<T>::st(dsrc + item * Cs + c, (c < K && c < 32) ? mine : 0.f);
   }
 }
 
@@ -1012,6 +1020,38 @@ adaptive_pool_bwd_kernel(View dsrc, int N, int H, int W, int S, const T *__restr
   }
 }
 
+// the same, 8 channels per thread (16-byte accesses)
+template <typename T>
+__global__ void __launch_bounds__(256)
+adaptive_pool_bwd_vec_kernel(View dsrc, int N, int H, int W, int S, const T *__restrict__ ddst, int accumulate) {
+  const int C = dsrc.C, CV = C / 8;
+  const long long total = (long long)N * H * W * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * 8; long long r = i / CV;
+    const int w = (int)(r % W); r /= W; const int h = (int)(r % H); const long long n = r / H;
+    T *p = reinterpret_cast<T *>(dsrc.ptr) + (n * dsrc.sn + (long long)h * dsrc.sh + (long long)w * dsrc.sw + c);
+    float a[8];
+    if (accumulate) ldv8(p, a); else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = 0.f;
+    }
+    for (int bi = 0; bi < S; ++bi) {
+      const int h0 = (bi * H) / S, h1 = ((bi + 1) * H + S - 1) / S;
+      if (h < h0 || h >= h1) continue;
+      for (int j = 0; j < S; ++j) {
+        const int w0 = (j * W) / S, w1 = ((j + 1) * W + S - 1) / S;
+        if (w < w0 || w >= w1) continue;
+        float g[8];
+        ldv8(ddst + ((n * S + bi) * S + j) * C + c, g);
+        const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = fmaf(g[k], inv, a[k]);
+      }
+    }
+    stv8(p, a);
+  }
+}
+
 static inline int grid_for(long long work, int per_block, int cap_mult = 8) {
   long long g = (work + per_block - 1) / per_block;
   const long long cap = (long long)kNumSMs * cap_mult;
@@ -1225,8 +1265,9 @@ extern "C" int ks_bilinear_up_fwd(int dtype, int B, int G, int Tp, int row0, int
 extern "C" int ks_bilinear_up_bwd(int dtype, int B, int G, int Tp, int row0, int Cs, int K, int Ho, int Wo, const float *ddst, void *dsrc,
                                   void *stream) {
   KS_CHECK_ARG(B > 0 && G > 0 && K > 0 && K <= Cs && row0 >= 0 && row0 + G * G <= Tp && Ho > 0 && Wo > 0 && ddst && dsrc);
-  const int grid = grid_for((long long)B * Tp * Cs, 128, 16);
-#define CALL(Ty) bilinear_up_bwd_kernel<Ty><<<grid, 128, 0, (cudaStream_t)stream>>>(B, G, Tp, row0, Cs, K, Ho, Wo, ddst, (Ty *)dsrc)
+  if (K > 32) return KS_EUNSUPPORTED;
+  const int grid = grid_for((long long)B * Tp, 8, 16);
+#define CALL(Ty) bilinear_up_bwd_kernel<Ty><<<grid, 256, 0, (cudaStream_t)stream>>>(B, G, Tp, row0, Cs, K, Ho, Wo, ddst, (Ty *)dsrc)
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();
@@ -1243,8 +1284,11 @@ extern "C" int ks_adaptive_avgpool_fwd(int dtype, int N, int H, int W, int S, co
 
 extern "C" int ks_adaptive_avgpool_bwd(int dtype, int N, int H, int W, int S, const void *ddst, const ks_view_t *dsrc, int accumulate, void *stream) {
   KS_CHECK_ARG(N > 0 && H > 0 && W > 0 && S > 0 && S <= H && S <= W && dsrc && dsrc->ptr && ddst);
-  const int grid = grid_for((long long)N * H * W * dsrc->C, 256);
-#define CALL(Ty) adaptive_pool_bwd_kernel<Ty><<<grid, 256, 0, (cudaStream_t)stream>>>(to_view(*dsrc), N, H, W, S, (const Ty *)ddst, accumulate)
+  const int es = (dtype == KS_F32) ? 4 : 2;
+  const bool vec = dsrc->C % 8 == 0 && al16(dsrc->ptr) && al16(ddst) && (dsrc->sn * es) % 16 == 0 && (dsrc->sh * es) % 16 == 0 && (dsrc->sw * es) % 16 == 0;
+  const int grid = grid_for((long long)N * H * W * (vec ? dsrc->C / 8 : dsrc->C), 256);
+#define CALL(Ty) { if (vec) adaptive_pool_bwd_vec_kernel<Ty><<<grid, 256, 0, (cudaStream_t)stream>>>(to_view(*dsrc), N, H, W, S, (const Ty *)ddst, accumulate); \
+    else adaptive_pool_bwd_kernel<Ty><<<grid, 256, 0, (cudaStream_t)stream>>>(to_view(*dsrc), N, H, W, S, (const Ty *)ddst, accumulate); }
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();
