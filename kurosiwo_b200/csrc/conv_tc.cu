@@ -667,7 +667,10 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
     const size_t half_sm = (227 * 1024) / 2 - 1024;
     const bool can3 = !v1 && ksize == 3 && g_opt.tb != 1;
     int TB = 1;
-    if (can3 && (g_opt.tb == 3 || bytes(MT, 2, 2, 3) <= half_sm)) { TB = 3; SA = 2; SB = 2; }
+    // 1x1 (plain GEMM: the ViT / ChangeFormer Linear layers): a stage holds only BK/16 = 4 UMMAs, so two-deep rings expose the
+    // TMA round trip; measured (scripts/dbg_gemm2.py, 13312 x 768 x 3072): SA=SB=2 677, 3 924, 4 999, 5 1000 TFLOP/s
+    if (!v1 && ksize == 1 && bytes(MT, 4, 4, 1) <= budget) { TB = 1; SA = 4; SB = 4; }
+    else if (can3 && (g_opt.tb == 3 || bytes(MT, 2, 2, 3) <= half_sm)) { TB = 3; SA = 2; SB = 2; }
     else if (!v1 && bytes(MT, 2, 4, 1) <= half_sm) { TB = 1; SA = 2; SB = 4; }
     else if (can3 && bytes(MT, 3, 3, 3) <= budget) { TB = 3; SA = 3; SB = 3; }
     else { TB = 1; SA = 3; SB = 4; }
