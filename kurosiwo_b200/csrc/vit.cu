@@ -764,18 +764,23 @@ __device__ __forceinline__ void am_store_o(const float (&o)[8][4], __nv_bfloat16
 }
 
 __global__ void __launch_bounds__(AM_WARPS * 32, 1)
-attention_fwd_tc_kernel(int Tt, int Tp, int heads, const __nv_bfloat16 *__restrict__ qkv, float scale, __nv_bfloat16 *__restrict__ out,
+attention_fwd_tc_kernel(int Tt, int Tp, int heads, int hpc, const __nv_bfloat16 *__restrict__ qkv, float scale, __nv_bfloat16 *__restrict__ out,
                         __nv_bfloat16 *__restrict__ probs) {
   extern __shared__ __align__(128) unsigned char smraw[];
-  __nv_bfloat16 *Ks = reinterpret_cast<__nv_bfloat16 *>(smraw), *Vs = Ks + Tp * ATC_KP;
-  const int b = blockIdx.y, h = blockIdx.x, inner = heads * ATT_DH, NT8 = Tp / 8, NT16 = Tp / 16;
+  // hpc heads of one image per CTA: 13 strips over 8 warps leave 3 of 16 warp slots idle, 3 heads = 39 strips leave 1 of 40
+  const int b = blockIdx.y, inner = heads * ATT_DH, NT8 = Tp / 8, NT16 = Tp / 16;
   const long long ld = 3LL * inner;
-  const __nv_bfloat16 *base = qkv + (long long)b * Tp * ld + h * ATT_DH;
-  atc_load_tile(Ks, base + inner, ld, Tt, Tp);
-  atc_load_tile(Vs, base + 2 * inner, ld, Tt, Tp);
+  for (int hl = 0; hl < hpc; ++hl) {
+    const __nv_bfloat16 *hb = qkv + (long long)b * Tp * ld + (blockIdx.x * hpc + hl) * ATT_DH;
+    atc_load_tile(reinterpret_cast<__nv_bfloat16 *>(smraw) + (size_t)hl * 2 * Tp * ATC_KP, hb + inner, ld, Tt, Tp);
+    atc_load_tile(reinterpret_cast<__nv_bfloat16 *>(smraw) + (size_t)(hl * 2 + 1) * Tp * ATC_KP, hb + 2 * inner, ld, Tt, Tp);
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  for (int strip = w; strip < NT16; strip += AM_WARPS) {
+  for (int item = w; item < hpc * NT16; item += AM_WARPS) {
+    const int hl = item / NT16, strip = item - hl * NT16, h = blockIdx.x * hpc + hl;
+    const __nv_bfloat16 *Ks = reinterpret_cast<__nv_bfloat16 *>(smraw) + (size_t)hl * 2 * Tp * ATC_KP, *Vs = Ks + Tp * ATC_KP;
+    const __nv_bfloat16 *base = qkv + (long long)b * Tp * ld + h * ATT_DH;
     const int i0 = strip * 16;
     const bool ok0 = (i0 + g) < Tt, ok1 = (i0 + g + 8) < Tt;
     uint32_t qa[4][4];
@@ -829,20 +834,23 @@ attention_fwd_tc_kernel(int Tt, int Tp, int heads, const __nv_bfloat16 *__restri
 }
 
 __global__ void __launch_bounds__(AM_WARPS * 32, 1)
-attention_bwd_rows_tc_kernel(int Tt, int Tp, int heads, const __nv_bfloat16 *__restrict__ qkv, const __nv_bfloat16 *__restrict__ probs,
+attention_bwd_rows_tc_kernel(int Tt, int Tp, int heads, int hpc, const __nv_bfloat16 *__restrict__ qkv, const __nv_bfloat16 *__restrict__ probs,
                              const __nv_bfloat16 *__restrict__ dout, float scale, __nv_bfloat16 *__restrict__ dqkv,
                              __nv_bfloat16 *__restrict__ ds) {
   extern __shared__ __align__(128) unsigned char smraw[];
-  __nv_bfloat16 *Ks = reinterpret_cast<__nv_bfloat16 *>(smraw), *Vs = Ks + Tp * ATC_KP;
-  const int b = blockIdx.y, h = blockIdx.x, inner = heads * ATT_DH, NT8 = Tp / 8, NT16 = Tp / 16;
+  const int b = blockIdx.y, inner = heads * ATT_DH, NT8 = Tp / 8, NT16 = Tp / 16;
   const long long ld = 3LL * inner;
-  const __nv_bfloat16 *base = qkv + (long long)b * Tp * ld + h * ATT_DH;
-  atc_load_tile(Ks, base + inner, ld, Tt, Tp);
-  atc_load_tile(Vs, base + 2 * inner, ld, Tt, Tp);
+  for (int hl = 0; hl < hpc; ++hl) {
+    const __nv_bfloat16 *hb = qkv + (long long)b * Tp * ld + (blockIdx.x * hpc + hl) * ATT_DH;
+    atc_load_tile(reinterpret_cast<__nv_bfloat16 *>(smraw) + (size_t)hl * 2 * Tp * ATC_KP, hb + inner, ld, Tt, Tp);
+    atc_load_tile(reinterpret_cast<__nv_bfloat16 *>(smraw) + (size_t)(hl * 2 + 1) * Tp * ATC_KP, hb + 2 * inner, ld, Tt, Tp);
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const __nv_bfloat16 *dob = dout + (long long)b * Tp * inner + h * ATT_DH;
-  for (int strip = w; strip < NT16; strip += AM_WARPS) {
+  for (int item = w; item < hpc * NT16; item += AM_WARPS) {
+    const int hl = item / NT16, strip = item - hl * NT16, h = blockIdx.x * hpc + hl;
+    const __nv_bfloat16 *Ks = reinterpret_cast<__nv_bfloat16 *>(smraw) + (size_t)hl * 2 * Tp * ATC_KP, *Vs = Ks + Tp * ATC_KP;
+    const __nv_bfloat16 *dob = dout + (long long)b * Tp * inner + h * ATT_DH;
     const int i0 = strip * 16;
     const bool ok0 = (i0 + g) < Tt, ok1 = (i0 + g + 8) < Tt;
     uint32_t da[4][4];
@@ -964,6 +972,18 @@ attention_bwd_cols_tc_kernel(int Tt, int Tp, int heads, const __nv_bfloat16 *__r
 }
 
 static inline size_t atc_smem_rows(int Tp) { return (size_t)2 * Tp * ATC_KP * 2 + 128; }
+// heads of one image per CTA for the row kernels: the count (dividing `heads`, fitting shared memory) whose strips fill the 8 warps' rounds best
+static inline int atc_heads_per_cta(int Tp, int heads) {
+  const int nt = Tp / 16;
+  int best = 1; double beff = -1.0;
+  for (int c = 1; c <= heads && (size_t)c * atc_smem_rows(Tp) <= 220 * 1024; ++c) {
+    if (heads % c) continue;
+    const int rounds = (c * nt + AM_WARPS - 1) / AM_WARPS;
+    const double eff = (double)(c * nt) / (double)(rounds * AM_WARPS);
+    if (eff > beff + 1e-9) { beff = eff; best = c; }
+  }
+  return best;
+}
 static inline size_t atc_smem_cols(int Tp, int warps) { return (size_t)2 * Tp * ATC_KP * 2 + (size_t)warps * 2 * 2 * 32 * ATC_SLAB * 2 + 128; }   // Q, dO + per-warp slabs
 static inline int atc_cols_warps(int Tp) {
   int w = AM_WARPS;
@@ -1179,8 +1199,9 @@ extern "C" int ks_attention_fwd(int dtype, int B, int T, int Tp, int heads, int 
     static bool attr = false;
     if (!attr) { cudaError_t e = cudaFuncSetAttribute(attention_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
                  if (e != cudaSuccess) return (int)e; attr = true; }
-    attention_fwd_tc_kernel<<<dim3((unsigned)heads, (unsigned)B), AM_WARPS * 32, atc_smem_rows(Tp), (cudaStream_t)stream>>>(
-        T, Tp, heads, (const __nv_bfloat16 *)qkv, scale, (__nv_bfloat16 *)out, (__nv_bfloat16 *)probs);
+    const int hpc = atc_heads_per_cta(Tp, heads);
+    attention_fwd_tc_kernel<<<dim3((unsigned)(heads / hpc), (unsigned)B), AM_WARPS * 32, hpc * atc_smem_rows(Tp), (cudaStream_t)stream>>>(
+        T, Tp, heads, hpc, (const __nv_bfloat16 *)qkv, scale, (__nv_bfloat16 *)out, (__nv_bfloat16 *)probs);
     KS_LAUNCH_RET();
   }
   size_t smem; int rpc, nblk;
@@ -1208,8 +1229,9 @@ extern "C" int ks_attention_bwd(int dtype, int B, int T, int Tp, int heads, int 
       attr = true;
     }
     const dim3 g((unsigned)heads, (unsigned)B);
-    attention_bwd_rows_tc_kernel<<<g, AM_WARPS * 32, atc_smem_rows(Tp), (cudaStream_t)stream>>>(
-        T, Tp, heads, (const __nv_bfloat16 *)qkv, (const __nv_bfloat16 *)probs, (const __nv_bfloat16 *)dout, scale, (__nv_bfloat16 *)dqkv,
+    const int hpc = 1;        // several heads per CTA measured slower here (3.33 -> 3.69 ms): the 180 KB of shared memory leave too little L1 for the re-read P rows
+    attention_bwd_rows_tc_kernel<<<dim3((unsigned)(heads / hpc), (unsigned)B), AM_WARPS * 32, hpc * atc_smem_rows(Tp), (cudaStream_t)stream>>>(
+        T, Tp, heads, hpc, (const __nv_bfloat16 *)qkv, (const __nv_bfloat16 *)probs, (const __nv_bfloat16 *)dout, scale, (__nv_bfloat16 *)dqkv,
         (__nv_bfloat16 *)ds_scratch);
     attention_bwd_cols_tc_kernel<<<g, atc_cols_warps(Tp) * 32, atc_smem_cols(Tp, atc_cols_warps(Tp)), (cudaStream_t)stream>>>(
         T, Tp, heads, (const __nv_bfloat16 *)qkv, (const __nv_bfloat16 *)probs, (const __nv_bfloat16 *)ds_scratch, (const __nv_bfloat16 *)dout,
