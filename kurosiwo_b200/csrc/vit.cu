@@ -70,6 +70,51 @@ layernorm_fwd_kernel(long long rows, int C, const T *__restrict__ x, long long l
   }
 }
 
+// Narrow rows (C <= 256, e.g. the 64-channel ChangeFormer stage with 200 k rows): L = pow2 >= C/8 lanes per row, 32/L rows per warp -
+// with a whole warp per row 24 of 32 lanes idled at C = 64.
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_narrow_kernel(long long rows, int C, int L, const T *__restrict__ x, long long ldx, const float *__restrict__ gamma,
+                            const float *__restrict__ beta, float eps, T *__restrict__ y, long long ldy, float *__restrict__ mean,
+                            float *__restrict__ rstd, T *__restrict__ copy_out, long long ldc) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int rpw = 32 / L, sub = lane / L, c = (lane % L) * 8;
+  const bool cl = c < C;
+  float g[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { g[i] = 0.f; b[i] = 0.f; }
+  if (cl) { ld8(gamma + c, g); ld8(beta + c, b); }
+  const float invC = 1.f / (float)C;
+  for (long long r0 = ((long long)blockIdx.x * wpb + wib) * rpw; r0 < rows; r0 += (long long)gridDim.x * wpb * rpw) {
+    const long long r = r0 + sub;
+    const bool live = cl && r < rows;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (live) ldv8(x + r * ldx + c, v);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    for (int o = L >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mu = s * invC;
+    float q = 0.f;
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = v[i] - mu; q += d * d; }
+    }
+    for (int o = L >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rs = rsqrtf(q * invC + eps);
+    if (live) {
+      if (c == 0) { if (mean) mean[r] = mu; if (rstd) rstd[r] = rs; }
+      if (copy_out) stv8(copy_out + r * ldc + c, v);
+      float o8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o8[i] = (v[i] - mu) * rs * g[i] + b[i];
+      stv8(y + r * ldy + c, o8);
+    }
+  }
+}
+
 // LayerNorm backward (C <= 1024), two kernels:
 //   rows: dx (+)= rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma.  L = min(32, pow2 >= C/8) lanes own one row (32/L rows per warp,
 //         so narrow rows - the 64-channel ChangeFormer stage - keep every lane busy), K = ceil(C / (8 L)) vectors per lane.
@@ -1096,6 +1141,16 @@ extern "C" int ks_layernorm_fwd(int dtype, int64_t rows, int C, const void *x, i
   KS_CHECK_ARG(rows > 0 && C > 0 && x && y && gamma && beta);
   if (C % 8 || C > LN_KMAX * 256 || ldx % 8 || ldy % 8 || (copy_out && ldc % 8) || !al16(x) || !al16(y) || !al16(gamma) || !al16(beta) ||
       (copy_out && !al16(copy_out))) return KS_EUNSUPPORTED;
+  if (C <= 256) {
+    int L = 1;
+    while (L * 8 < C) L <<= 1;
+    const int grid = grid_for(rows, 8 * (32 / L) * 2, 8);
+#define CALL(T) layernorm_fwd_narrow_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(rows, C, L, (const T *)x, ldx, gamma, beta, eps, (T *)y, ldy, \
+                                                                                         mean, rstd, (T *)copy_out, ldc)
+    KS_DISPATCH_T(dtype, CALL);
+#undef CALL
+    KS_LAUNCH_RET();
+  }
   const int grid = grid_for(rows, 8);
 #define CALL(T) layernorm_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(rows, C, (const T *)x, ldx, gamma, beta, eps, (T *)y, ldy, \
                                                                                   mean, rstd, (T *)copy_out, ldc)

@@ -31,7 +31,7 @@ def _r(shape, dtype, g, scale=1.0, shift=0.0):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("rows,C", [(37, 64), (416, 768), (50, 1536), (9, 2048)])
+@pytest.mark.parametrize("rows,C", [(37, 64), (1003, 64), (130, 128), (75, 200), (64, 256), (77, 320), (416, 768), (50, 1536), (9, 2048), (5, 8)])
 def test_layernorm_fwd(ops, sh, dtype, rows, C):
     g = torch.Generator().manual_seed(1)
     x = _r((rows, C), dtype, g, 2.0, 0.5)
