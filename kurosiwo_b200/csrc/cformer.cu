@@ -439,10 +439,10 @@ template <typename T, bool FLIP>
 __global__ void __launch_bounds__(256)
 dwconv_kernel(int N, int H, int W, int C, const T *__restrict__ x, const float *__restrict__ w9, const float *__restrict__ bias, T *__restrict__ y) {
   const int CV = C / 8;
-  const long long total = (long long)N * H * W * CV;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % CV) * 8; const long long p = i / CV;
-    const int w = (int)(p % W), h = (int)((p / W) % H); const long long n = p / ((long long)W * H);
+  const unsigned total = (unsigned)N * H * W * CV;            // < 2^31 (checked by the launcher): 32-bit index arithmetic - with
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {   // 64-bit div/mod the kernel was issue-bound
+    const int c = (int)(i % CV) * 8; const unsigned p = i / CV;
+    const int w = (int)(p % W), h = (int)((p / W) % H); const long long n = p / ((unsigned)W * H);
     float acc[8];
     if (bias) ld8(bias + c, acc); else {
 #pragma unroll
@@ -459,7 +459,7 @@ dwconv_kernel(int N, int H, int W, int C, const T *__restrict__ x, const float *
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[k], wv[k], acc[k]);
     }
-    st8(y + p * C + c, acc);
+    st8(y + (long long)p * C + c, acc);
   }
 }
 
@@ -480,10 +480,10 @@ dwconv_wgrad_kernel(int N, int H, int W, int C, const T *__restrict__ x, const T
     for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
   const long long npix = (long long)N * H * W;
   if (ty < rows) {
-    for (long long p = (long long)blockIdx.x * rows + ty; p < npix; p += (long long)gridDim.x * rows) {
-      const int w = (int)(p % W), h = (int)((p / W) % H); const long long n = p / ((long long)W * H);
+    for (unsigned p = blockIdx.x * rows + ty; p < (unsigned)npix; p += gridDim.x * rows) {
+      const int w = (int)(p % W), h = (int)((p / W) % H); const long long n = p / ((unsigned)W * H);
       float g[8];
-      ld8(dy + p * C + c, g);
+      ld8(dy + (long long)p * C + c, g);
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[9][k] += g[k];
 #pragma unroll
@@ -890,6 +890,7 @@ extern "C" int ks_col2im(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int k
 extern "C" int ks_dwconv3x3_fwd(int dtype, int N, int H, int W, int C, const void *x, const float *w9, const float *bias, void *y, void *stream) {
   KS_CHECK_ARG(N > 0 && H > 0 && W > 0 && x && w9 && y);
   if (C % 8 || !a16(x) || !a16(y) || !a16(w9) || (bias && !a16(bias))) return KS_EUNSUPPORTED;
+  if ((long long)N * H * W * (C / 8) >= (1LL << 31)) return KS_EUNSUPPORTED;
   const int grid = cgrid((long long)N * H * W * (C / 8), 256);
 #define CALL(T) dwconv_kernel<T, false><<<grid, 256, 0, (cudaStream_t)stream>>>(N, H, W, C, (const T *)x, w9, bias, (T *)y)
   KS_DISPATCH_T(dtype, CALL);
@@ -901,6 +902,7 @@ extern "C" int ks_dwconv3x3_bwd(int dtype, int N, int H, int W, int C, const voi
                                 float *dbias, void *stream) {
   KS_CHECK_ARG(N > 0 && H > 0 && W > 0 && x && dy && w9 && dx && dw9);
   if (C % 8 || !a16(x) || !a16(dy) || !a16(dx) || !a16(w9)) return KS_EUNSUPPORTED;
+  if ((long long)N * H * W * (C / 8) >= (1LL << 31)) return KS_EUNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = cgrid((long long)N * H * W * (C / 8), 256);
   const int gy = (C + 255) / 256;
