@@ -331,6 +331,154 @@ xattention_bwd_kernel(int Nq, int Nk, int heads, int dh, const T *__restrict__ q
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// bf16, dh == 64, Nk <= 64: the forward on mma.sync.m16n8k16 (same scheme as the ViT kernels in vit.cu): K and V of the (batch, head)
+// in shared memory as bf16 [64][72] (rows >= Nk zero), one warp per 16-query strip, the 16 x 64 score block in accumulator fragments,
+// softmax in registers (MUFU exp), P (bf16, pre-dropout) stored for the backward, dropped P re-used in registers as the A operand of
+// P.V.  The CUDA-core kernel above stays the fp32 / generic path.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int XT_KP = 72;
+__device__ __forceinline__ void xt_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void xt_ldsm(uint32_t (&r)[4], const void *p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void xt_ldsm_t(uint32_t (&r)[4], const void *p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ uint32_t xt_pack(float lo, float hi) {
+  const __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t *>(&h2);
+}
+__device__ __forceinline__ void xt_load_kv(__nv_bfloat16 *dst, const __nv_bfloat16 *src, long long ld, int rows) {
+  for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows) v = *reinterpret_cast<const uint4 *>(src + (long long)r * ld + c);
+    *reinterpret_cast<uint4 *>(dst + r * XT_KP + c) = v;
+  }
+}
+
+__global__ void __launch_bounds__(XA_WARPS * 32)
+xattention_fwd_tc_kernel(int Nq, int Nk, int heads, const __nv_bfloat16 *__restrict__ q, long long ldq, const __nv_bfloat16 *__restrict__ kv,
+                         long long ldkv, float scale, __nv_bfloat16 *__restrict__ out, long long ldo, __nv_bfloat16 *__restrict__ probs,
+                         int rows_per_cta, float pdrop, unsigned long long seed, const int *step_ptr, int site) {
+  __shared__ __align__(16) __nv_bfloat16 Ks[64 * XT_KP], Vs[64 * XT_KP];
+  const unsigned long long dkey = cf_key(seed, step_ptr, site);
+  const float ikeep = 1.f / (1.f - pdrop);
+  const int b = blockIdx.z, h = blockIdx.y, inner = heads * 64;
+  const __nv_bfloat16 *kvb = kv + (long long)b * Nk * ldkv + h * 64;
+  xt_load_kv(Ks, kvb, ldkv, Nk);
+  xt_load_kv(Vs, kvb + inner, ldkv, Nk);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(Nq, r0 + rows_per_cta);
+  const float sl2 = scale * 1.4426950408889634f;
+  for (int i0 = r0 + w * 16; i0 < r1; i0 += XA_WARPS * 16) {
+    const int ia = i0 + g, ib = i0 + g + 8;
+    const bool ok0 = ia < r1, ok1 = ib < r1;
+    // A fragments of the 16 query rows (rows past the range are clamped for the load and never stored)
+    const __nv_bfloat16 *qa0 = q + ((long long)b * Nq + min(ia, Nq - 1)) * ldq + h * 64 + 2 * t;
+    const __nv_bfloat16 *qa1 = q + ((long long)b * Nq + min(ib, Nq - 1)) * ldq + h * 64 + 2 * t;
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      qa[kk][0] = *reinterpret_cast<const uint32_t *>(qa0 + kk * 16);
+      qa[kk][1] = *reinterpret_cast<const uint32_t *>(qa1 + kk * 16);
+      qa[kk][2] = *reinterpret_cast<const uint32_t *>(qa0 + kk * 16 + 8);
+      qa[kk][3] = *reinterpret_cast<const uint32_t *>(qa1 + kk * 16 + 8);
+    }
+    float s[8][4];
+#pragma unroll
+    for (int jt = 0; jt < 8; ++jt) s[jt][0] = s[jt][1] = s[jt][2] = s[jt][3] = 0.f;
+    const __nv_bfloat16 *krow = Ks + (lane & 7) * XT_KP + (lane >> 3) * 8;
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+#pragma unroll
+      for (int jt = 0; jt < 8; jt += 2) {
+        uint32_t ra[4], rb[4];
+        xt_ldsm(ra, krow + jt * 8 * XT_KP + h2 * 32);
+        xt_ldsm(rb, krow + (jt + 1) * 8 * XT_KP + h2 * 32);
+        xt_mma(s[jt], qa[2 * h2], ra[0], ra[1]);
+        xt_mma(s[jt + 1], qa[2 * h2], rb[0], rb[1]);
+        xt_mma(s[jt], qa[2 * h2 + 1], ra[2], ra[3]);
+        xt_mma(s[jt + 1], qa[2 * h2 + 1], rb[2], rb[3]);
+      }
+    }
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int jt = 0; jt < 8; ++jt) {
+      const int c = jt * 8 + 2 * t;
+      if (c < Nk) { m0 = fmaxf(m0, s[jt][0]); m1 = fmaxf(m1, s[jt][2]); }
+      if (c + 1 < Nk) { m0 = fmaxf(m0, s[jt][1]); m1 = fmaxf(m1, s[jt][3]); }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    const float m0s = m0 * sl2, m1s = m1 * sl2;
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int jt = 0; jt < 8; ++jt) {
+      const int c = jt * 8 + 2 * t;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool in = (c + (e & 1)) < Nk;
+        float y;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaf(s[jt][e], sl2, (e < 2) ? -m0s : -m1s)));
+        s[jt][e] = in ? y : 0.f;
+      }
+      l0 += s[jt][0] + s[jt][1]; l1 += s[jt][2] + s[jt][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    uint32_t pk[8][2];
+    const long long pbase0 = (((long long)b * heads + h) * Nq + ia) * Nk, pbase1 = (((long long)b * heads + h) * Nq + ib) * Nk;
+#pragma unroll
+    for (int jt = 0; jt < 8; ++jt) {
+      const int c = jt * 8 + 2 * t;
+      float pq[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) pq[e] = round_as<__nv_bfloat16>(s[jt][e] * ((e < 2) ? inv0 : inv1));
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int cc = c + (e & 1);
+        const bool rowok = (e < 2) ? ok0 : ok1;
+        if (rowok && cc < Nk) {
+          const long long idx = ((e < 2) ? pbase0 : pbase1) + cc;
+          probs[idx] = __float2bfloat16_rn(pq[e]);                 // Nk is odd in general: 2-byte stores
+          if (pdrop > 0.f) pq[e] *= cf_keep(dkey, (unsigned long long)idx, pdrop, ikeep);
+        } else pq[e] = 0.f;
+      }
+      pk[jt][0] = xt_pack(pq[0], pq[1]);
+      pk[jt][1] = xt_pack(pq[2], pq[3]);
+    }
+    float o[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const uint32_t a[4] = {pk[2 * kk][0], pk[2 * kk][1], pk[2 * kk + 1][0], pk[2 * kk + 1][1]};
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t r[4];
+        xt_ldsm_t(r, Vs + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * XT_KP + (dp * 2 + (lane >> 4)) * 8);
+        xt_mma(o[2 * dp], a, r[0], r[1]);
+        xt_mma(o[2 * dp + 1], a, r[2], r[3]);
+      }
+    }
+    __nv_bfloat16 *o0 = out + ((long long)b * Nq + ia) * ldo + h * 64 + 2 * t, *o1 = out + ((long long)b * Nq + ib) * ldo + h * 64 + 2 * t;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      if (ok0) *reinterpret_cast<uint32_t *>(o0 + dt * 8) = xt_pack(o[dt][0], o[dt][1]);
+      if (ok1) *reinterpret_cast<uint32_t *>(o1 + dt * 8) = xt_pack(o[dt][2], o[dt][3]);
+    }
+  }
+}
+
 // dh == 64 variant: the same per-row pass (one warp per query row: dP, softmax backward, dQ) writes the row's q, dO, dropped P and
 // dS into a 32-row shared-memory batch; then ALL threads fold the batch into register accumulators - thread = (16 keys, one d):
 // dK[j][d] += sum_r dS[r][j] q[r][d], dV[j][d] += sum_r Pdrop[r][j] dO[r][d] - with float4 broadcast reads.  (The generic kernel above
@@ -814,6 +962,17 @@ extern "C" int ks_xattention_fwd(int dtype, int B, int Nq, int Nk, int heads, in
                                  void *stream) {
   KS_CHECK_ARG(pdrop >= 0.f && pdrop < 1.f);
   KS_CHECK_ARG(B > 0 && Nq > 0 && heads > 0 && q && kv && out && probs);
+  if (dtype == KS_BF16 && dh == 64 && Nk >= 1 && Nk <= 64 && !g_opt.att_simt && a16(kv) && (ldkv * 2) % 16 == 0 && ((uintptr_t)q % 4) == 0 &&
+      (ldq % 2) == 0 && ((uintptr_t)out % 4) == 0 && (ldo % 2) == 0) {
+    int nb = 1;
+    while ((long long)B * heads * nb < 4 * kNumSMs && nb * 128 < Nq) nb <<= 1;
+    const int rpc_t = ((Nq + nb - 1) / nb + 15) / 16 * 16;
+    nb = (Nq + rpc_t - 1) / rpc_t;
+    xattention_fwd_tc_kernel<<<dim3((unsigned)nb, (unsigned)heads, (unsigned)B), XA_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        Nq, Nk, heads, (const __nv_bfloat16 *)q, ldq, (const __nv_bfloat16 *)kv, ldkv, scale, (__nv_bfloat16 *)out, ldo, (__nv_bfloat16 *)probs,
+        rpc_t, pdrop, seed, step_ptr, site);
+    KS_LAUNCH_RET();
+  }
   size_t smem; int rpc, nblk;
   int rc = xa_cfg(B, Nq, Nk, heads, dh, 2, smem, rpc, nblk); if (rc) return rc;
   dim3 grid((unsigned)nblk, (unsigned)heads, (unsigned)B);
