@@ -479,6 +479,170 @@ xattention_fwd_tc_kernel(int Nq, int Nk, int heads, const __nv_bfloat16 *__restr
   }
 }
 
+// Backward of the same (bf16, dh == 64, Nk <= 64), all four products on mma.sync.  Per batch of 128 query rows of the CTA's range:
+//   stage  Q and dO rows in shared memory ([128][72] bf16);
+//   pass A (a warp per 16 rows): dP = dO V^T, dS = P*(dP*keep - rowsum)*scale and Pdrop = P*keep in registers, dQ = dS K -> global,
+//          dS and Pdrop -> shared memory ([128][72] bf16);
+//   pass B (warp = 16 keys x 32 d): dK += dS^T Q, dV += Pdrop^T dO with ldmatrix.trans operands, accumulators live in registers over
+//          all batches and are added to the fp32 dkv buffer once at the end.
+constexpr int XT_ROWS = 128;
+
+__global__ void __launch_bounds__(XA_WARPS * 32, 2)
+xattention_bwd_tc_kernel(int Nq, int Nk, int heads, const __nv_bfloat16 *__restrict__ q, long long ldq, const __nv_bfloat16 *__restrict__ kv,
+                         long long ldkv, const __nv_bfloat16 *__restrict__ probs, const __nv_bfloat16 *__restrict__ dout, long long ldo,
+                         float scale, __nv_bfloat16 *__restrict__ dq, long long lddq, float *__restrict__ dkv, int rows_per_cta, float pdrop,
+                         unsigned long long seed, const int *step_ptr, int site) {
+  extern __shared__ __align__(16) unsigned char xsm[];
+  __nv_bfloat16 *Ks = reinterpret_cast<__nv_bfloat16 *>(xsm), *Vs = Ks + 64 * XT_KP, *Qb = Vs + 64 * XT_KP, *Ob = Qb + XT_ROWS * XT_KP,
+                *Sb = Ob + XT_ROWS * XT_KP, *Pb = Sb + XT_ROWS * XT_KP;
+  const unsigned long long dkey = cf_key(seed, step_ptr, site);
+  const float ikeep = 1.f / (1.f - pdrop);
+  const int b = blockIdx.z, h = blockIdx.y, inner = heads * 64;
+  const __nv_bfloat16 *kvb = kv + (long long)b * Nk * ldkv + h * 64;
+  xt_load_kv(Ks, kvb, ldkv, Nk);
+  xt_load_kv(Vs, kvb + inner, ldkv, Nk);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int mt = w & 3, dhalf = w >> 2;                         // pass B ownership
+  float aK[4][4], aV[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { aK[i][0] = aK[i][1] = aK[i][2] = aK[i][3] = 0.f; aV[i][0] = aV[i][1] = aV[i][2] = aV[i][3] = 0.f; }
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(Nq, r0 + rows_per_cta);
+  for (int rb = r0; rb < r1; rb += XT_ROWS) {
+    __syncthreads();                                            // K/V staged (first batch); pass B of the previous batch done
+    for (int i = threadIdx.x; i < XT_ROWS * 8; i += blockDim.x) {
+      const int r = i >> 3, c = (i & 7) * 8, row = rb + r;
+      uint4 vq = make_uint4(0u, 0u, 0u, 0u), vo = vq;
+      if (row < r1) {
+        vq = *reinterpret_cast<const uint4 *>(q + ((long long)b * Nq + row) * ldq + h * 64 + c);
+        vo = *reinterpret_cast<const uint4 *>(dout + ((long long)b * Nq + row) * ldo + h * 64 + c);
+      }
+      *reinterpret_cast<uint4 *>(Qb + r * XT_KP + c) = vq;
+      *reinterpret_cast<uint4 *>(Ob + r * XT_KP + c) = vo;
+    }
+    __syncthreads();
+    {   // ---------------- pass A: this warp's 16 rows ----------------
+      const int sr = w * 16, ia = rb + sr + g, ib = ia + 8;
+      const bool ok0 = ia < r1, ok1 = ib < r1;
+      uint32_t da[4][4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) xt_ldsm(da[kk], Ob + (sr + (lane & 7) + ((lane >> 3) & 1) * 8) * XT_KP + kk * 16 + (lane >> 4) * 8);
+      float dp[8][4];
+#pragma unroll
+      for (int jt = 0; jt < 8; ++jt) dp[jt][0] = dp[jt][1] = dp[jt][2] = dp[jt][3] = 0.f;
+      const __nv_bfloat16 *vrow = Vs + (lane & 7) * XT_KP + (lane >> 3) * 8;
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+#pragma unroll
+        for (int jt = 0; jt < 8; jt += 2) {
+          uint32_t ra[4], rb4[4];
+          xt_ldsm(ra, vrow + jt * 8 * XT_KP + h2 * 32);
+          xt_ldsm(rb4, vrow + (jt + 1) * 8 * XT_KP + h2 * 32);
+          xt_mma(dp[jt], da[2 * h2], ra[0], ra[1]);
+          xt_mma(dp[jt + 1], da[2 * h2], rb4[0], rb4[1]);
+          xt_mma(dp[jt], da[2 * h2 + 1], ra[2], ra[3]);
+          xt_mma(dp[jt + 1], da[2 * h2 + 1], rb4[2], rb4[3]);
+        }
+      }
+      const long long pbase0 = (((long long)b * heads + h) * Nq + ia) * Nk, pbase1 = (((long long)b * heads + h) * Nq + ib) * Nk;
+      float pd[8][4];                                            // P * keep
+      float dot0 = 0.f, dot1 = 0.f;
+#pragma unroll
+      for (int jt = 0; jt < 8; ++jt) {
+        const int c = jt * 8 + 2 * t;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int cc = c + (e & 1);
+          const bool ok = ((e < 2) ? ok0 : ok1) && cc < Nk;
+          float pv = 0.f, kf = 1.f;
+          if (ok) {
+            const long long idx = ((e < 2) ? pbase0 : pbase1) + cc;
+            pv = __bfloat162float(probs[idx]);
+            if (pdrop > 0.f) kf = cf_keep(dkey, (unsigned long long)idx, pdrop, ikeep);
+          }
+          pd[jt][e] = pv * kf;                                   // dropped probability; d(softmax out) = dP * keep
+          if (e < 2) dot0 = fmaf(dp[jt][e], pd[jt][e], dot0); else dot1 = fmaf(dp[jt][e], pd[jt][e], dot1);
+          dp[jt][e] = ok ? dp[jt][e] * kf : 0.f;                 // dP wrt the softmax output
+          pd[jt][e] = ok ? pd[jt][e] : 0.f;
+        }
+      }
+      dot0 += __shfl_xor_sync(0xffffffffu, dot0, 1); dot0 += __shfl_xor_sync(0xffffffffu, dot0, 2);
+      dot1 += __shfl_xor_sync(0xffffffffu, dot1, 1); dot1 += __shfl_xor_sync(0xffffffffu, dot1, 2);
+      uint32_t sk[8][2];
+#pragma unroll
+      for (int jt = 0; jt < 8; ++jt) {
+        const int c = jt * 8 + 2 * t;
+        // P itself = pd / keep where kept; where dropped (kf = 0) dS is 0 anyway... but P*(dP - dot) needs the UNdropped P: reload
+        float ds[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int cc = c + (e & 1);
+          const bool ok = ((e < 2) ? ok0 : ok1) && cc < Nk;
+          const float pv = ok ? __bfloat162float(probs[((e < 2) ? pbase0 : pbase1) + cc]) : 0.f;
+          ds[e] = pv * (dp[jt][e] - ((e < 2) ? dot0 : dot1)) * scale;
+        }
+        sk[jt][0] = xt_pack(ds[0], ds[1]); sk[jt][1] = xt_pack(ds[2], ds[3]);
+        *reinterpret_cast<uint32_t *>(Sb + (sr + g) * XT_KP + c) = sk[jt][0];
+        *reinterpret_cast<uint32_t *>(Sb + (sr + g + 8) * XT_KP + c) = sk[jt][1];
+        *reinterpret_cast<uint32_t *>(Pb + (sr + g) * XT_KP + c) = xt_pack(pd[jt][0], pd[jt][1]);
+        *reinterpret_cast<uint32_t *>(Pb + (sr + g + 8) * XT_KP + c) = xt_pack(pd[jt][2], pd[jt][3]);
+      }
+      float o[8][4];
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {                           // dQ = dS K
+        const uint32_t a[4] = {sk[2 * kk][0], sk[2 * kk][1], sk[2 * kk + 1][0], sk[2 * kk + 1][1]};
+#pragma unroll
+        for (int dp2 = 0; dp2 < 4; ++dp2) {
+          uint32_t r[4];
+          xt_ldsm_t(r, Ks + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * XT_KP + (dp2 * 2 + (lane >> 4)) * 8);
+          xt_mma(o[2 * dp2], a, r[0], r[1]);
+          xt_mma(o[2 * dp2 + 1], a, r[2], r[3]);
+        }
+      }
+      __nv_bfloat16 *o0 = dq + ((long long)b * Nq + ia) * lddq + h * 64 + 2 * t, *o1 = dq + ((long long)b * Nq + ib) * lddq + h * 64 + 2 * t;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        if (ok0) *reinterpret_cast<uint32_t *>(o0 + dt * 8) = xt_pack(o[dt][0], o[dt][1]);
+        if (ok1) *reinterpret_cast<uint32_t *>(o1 + dt * 8) = xt_pack(o[dt][2], o[dt][3]);
+      }
+    }
+    __syncthreads();
+    // ---------------- pass B: dK / dV tile of this warp over the batch's 128 rows ----------------
+#pragma unroll 2
+    for (int kk = 0; kk < XT_ROWS / 16; ++kk) {
+      uint32_t as[4], ap[4];
+      const int aoff = (kk * 16 + (lane & 7) + (lane >> 4) * 8) * XT_KP + mt * 16 + ((lane >> 3) & 1) * 8;
+      xt_ldsm_t(as, Sb + aoff);
+      xt_ldsm_t(ap, Pb + aoff);
+      const int boff = (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * XT_KP + dhalf * 32 + (lane >> 4) * 8;
+#pragma unroll
+      for (int dp2 = 0; dp2 < 2; ++dp2) {
+        uint32_t rq[4], ro[4];
+        xt_ldsm_t(rq, Qb + boff + dp2 * 16);
+        xt_ldsm_t(ro, Ob + boff + dp2 * 16);
+        xt_mma(aK[2 * dp2], as, rq[0], rq[1]);
+        xt_mma(aV[2 * dp2], ap, ro[0], ro[1]);
+        xt_mma(aK[2 * dp2 + 1], as, rq[2], rq[3]);
+        xt_mma(aV[2 * dp2 + 1], ap, ro[2], ro[3]);
+      }
+    }
+  }
+  float *dkvb = dkv + (long long)b * Nk * (2 * inner) + h * 64;
+#pragma unroll
+  for (int nt8 = 0; nt8 < 4; ++nt8) {
+    const int d = dhalf * 32 + nt8 * 8 + 2 * t;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int key = mt * 16 + g + ((e >> 1) ? 8 : 0);
+      if (key < Nk) {
+        atomicAdd(dkvb + (long long)key * (2 * inner) + d + (e & 1), aK[nt8][e]);
+        atomicAdd(dkvb + (long long)key * (2 * inner) + inner + d + (e & 1), aV[nt8][e]);
+      }
+    }
+  }
+}
+
 // dh == 64 variant: the same per-row pass (one warp per query row: dP, softmax backward, dQ) writes the row's q, dO, dropped P and
 // dS into a 32-row shared-memory batch; then ALL threads fold the batch into register accumulators - thread = (16 keys, one d):
 // dK[j][d] += sum_r dS[r][j] q[r][d], dV[j][d] += sum_r Pdrop[r][j] dO[r][d] - with float4 broadcast reads.  (The generic kernel above
@@ -995,6 +1159,21 @@ extern "C" int ks_xattention_bwd(int dtype, int B, int Nq, int Nk, int heads, in
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e0 = cudaMemsetAsync(dkv, 0, sizeof(float) * (size_t)B * Nk * 2 * heads * dh, st); if (e0 != cudaSuccess) return (int)e0;
   dim3 grid((unsigned)nblk, (unsigned)heads, (unsigned)B);
+  if (dtype == KS_BF16 && dh == 64 && Nk >= 1 && Nk <= 64 && !g_opt.att_simt && a16(kv) && (ldkv * 2) % 16 == 0 && a16(q) && (ldq * 2) % 16 == 0 &&
+      a16(dout) && (ldo * 2) % 16 == 0 && ((uintptr_t)dq % 4) == 0 && (lddq % 2) == 0) {
+    int nb = 1;
+    while ((long long)B * heads * nb < 2 * kNumSMs && nb * XT_ROWS < Nq) nb <<= 1;
+    const int rpc_t = ((Nq + nb - 1) / nb + 15) / 16 * 16;
+    nb = (Nq + rpc_t - 1) / rpc_t;
+    const size_t smem_t = (size_t)(2 * 64 + 4 * XT_ROWS) * XT_KP * sizeof(__nv_bfloat16);
+    static bool attr = false;
+    if (!attr) { cudaError_t e = cudaFuncSetAttribute(xattention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+                 if (e != cudaSuccess) return (int)e; attr = true; }
+    xattention_bwd_tc_kernel<<<dim3((unsigned)nb, (unsigned)heads, (unsigned)B), XA_WARPS * 32, smem_t, st>>>(
+        Nq, Nk, heads, (const __nv_bfloat16 *)q, ldq, (const __nv_bfloat16 *)kv, ldkv, (const __nv_bfloat16 *)probs, (const __nv_bfloat16 *)dout, ldo,
+        scale, (__nv_bfloat16 *)dq, lddq, dkv, rpc_t, pdrop, seed, step_ptr, site);
+    KS_LAUNCH_RET();
+  }
   if (dh == XB_D && XA_WARPS * 32 == 4 * XB_D) {
     const size_t smem64 = ((size_t)2 * XB_ROWS * XA_KMAX + (size_t)2 * XB_ROWS * XB_D + (size_t)2 * Nk * (XB_D + 1)) * sizeof(float);
 #define CALL(T) { cudaError_t e = cudaFuncSetAttribute(xattention_bwd64_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); \

@@ -79,7 +79,9 @@ def test_xattention_fwd_bwd(ops, sh, dtype, B, Nq, Nk, heads, dh):
     dqd, dkvd = torch.ones_like(q, device=DEV), torch.ones(B * Nk * 2 * inner, device=DEV)
     ops.xattention_bwd(B, Nq, Nk, heads, dh, q.to(DEV), kv.to(DEV), probs.to(DEV), dout.to(DEV), scale, dqd, dkvd)
     assert rel_l2(dqd.float(), dq.float()) < _tol(dtype)
-    assert rel_l2(dkvd, dkv) < 1e-4
+    # fp32 storage: CUDA-core kernels, fp32 operands.  bf16 storage with dh = 64: the mma.sync kernel feeds dS and the dropped P to the
+    # tensor cores as bf16 (as every bf16 attention backward does), so dK / dV carry bf16 operand rounding (measured 1.1e-3)
+    assert rel_l2(dkvd, dkv) < (1e-4 if dtype == torch.float32 or dh != 64 else 4e-3)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
