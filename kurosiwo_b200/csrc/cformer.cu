@@ -609,8 +609,9 @@ xattention_bwd_tc_kernel(int Nq, int Nk, int heads, const __nv_bfloat16 *__restr
     }
     __syncthreads();
     // ---------------- pass B: dK / dV tile of this warp over the batch's 128 rows ----------------
+    const int nk16 = (min(r1 - rb, XT_ROWS) + 15) >> 4;          // 16-row steps that hold rows of this batch (the rest is zero)
 #pragma unroll 2
-    for (int kk = 0; kk < XT_ROWS / 16; ++kk) {
+    for (int kk = 0; kk < nk16; ++kk) {
       uint32_t as[4], ap[4];
       const int aoff = (kk * 16 + (lane & 7) + (lane >> 4) * 8) * XT_KP + mt * 16 + ((lane >> 3) & 1) * 8;
       xt_ldsm_t(as, Sb + aoff);
@@ -1163,7 +1164,8 @@ extern "C" int ks_xattention_bwd(int dtype, int B, int Nq, int Nk, int heads, in
       a16(dout) && (ldo * 2) % 16 == 0 && ((uintptr_t)dq % 4) == 0 && (lddq % 2) == 0) {
     int nb = 1;
     while ((long long)B * heads * nb < 2 * kNumSMs && nb * XT_ROWS < Nq) nb <<= 1;
-    const int rpc_t = ((Nq + nb - 1) / nb + 15) / 16 * 16;
+    int rpc_t = ((Nq + nb - 1) / nb + 15) / 16 * 16;
+    if (rpc_t >= XT_ROWS) rpc_t = rpc_t / XT_ROWS * XT_ROWS;        // whole 128-row batches per CTA (392 rows would run a 4th batch of 8 rows)
     nb = (Nq + rpc_t - 1) / rpc_t;
     const size_t smem_t = (size_t)(2 * 64 + 4 * XT_ROWS) * XT_KP * sizeof(__nv_bfloat16);
     static bool attr = false;
