@@ -161,9 +161,14 @@ class FinetunerSegmentation(_EngineHost):
         self.pool = pool
         if pool:
             raise NotImplementedError("pool=True (one Linear over the cls token) is outside the fused path")
-        if configs.get("mlp") or configs.get("decoder"):
-            raise NotImplementedError("only the linear 1x1 head (mlp=false, decoder=false) is on the fused path in this round")
-        self.head = nn.Conv2d(encoder.mlp_head.in_features, configs["num_classes"], kernel_size=1)
+        if configs.get("decoder"):
+            raise NotImplementedError("the deconvolution `Decoder` head (model_utilities.py:21-48, hard-wired to a 1024-wide encoder) is not on "
+                                      "the fused path; heads built: linear (mlp=false) and mlp (mlp=true)")
+        if configs.get("mlp"):                                    # model_utilities.py:60-65
+            self.head = nn.Sequential(nn.Conv2d(encoder.mlp_head.in_features, 512, kernel_size=1), nn.ReLU(),
+                                      nn.Conv2d(512, configs["num_classes"], kernel_size=1))
+        else:
+            self.head = nn.Conv2d(encoder.mlp_head.in_features, configs["num_classes"], kernel_size=1)
         self.model.mlp_head = nn.Identity()
         self.precision = precision or encoder.precision
         self._engines, self._ops = {}, None
@@ -176,8 +181,13 @@ class FinetunerSegmentation(_EngineHost):
             self._engines = {}
             if self.configs.get("finetuning_patch_size", 16) != 16:
                 raise NotImplementedError("finetuning_patch_size must equal the encoder's 16x16 patches")
-            eng = ViTSegEngine(ops, self, "model.", self.model.cfg, "linear", self.configs["num_classes"], x.shape[0], x.shape[2], x.shape[3],
-                               self._storage_dtype(), x.device)
+            if self.configs.get("mlp"):
+                from .mlp_head_engine import ViTMlpHeadEngine
+                eng = ViTMlpHeadEngine(ops, self, "model.", self.model.cfg, self.configs["num_classes"], x.shape[0], x.shape[2], x.shape[3],
+                                       self._storage_dtype(), x.device)
+            else:
+                eng = ViTSegEngine(ops, self, "model.", self.model.cfg, "linear", self.configs["num_classes"], x.shape[0], x.shape[2],
+                                   x.shape[3], self._storage_dtype(), x.device)
             self._engines[key] = eng
         return eng
 

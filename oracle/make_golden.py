@@ -83,6 +83,7 @@ def main():
         print(tag, "loss", float(loss.detach()), "logits", out.shape)
     siam_goldens()
     vit_goldens()
+    vit_mlp_goldens()
     changeformer_goldens()
     upernet_goldens()
 
@@ -178,6 +179,42 @@ def vit_goldens():
         fx["grad_norms"] = np.array(norms, np.float64)
         np.savez_compressed(OUT / f"floodvit_{tag}.npz", **fx)
         print("floodvit", tag, "loss", float(loss.detach()))
+
+
+def vit_mlp_goldens():
+    """FloodViT with the `mlp` head (FinetunerSegmentation configs mlp=True) from the unmodified reference modules."""
+    from oracle.ref_import import install_stubs
+    install_stubs()
+    from models.vision_transformer import ViT as RefViT                    # noqa: E402  (reference, read-only)
+    from models.model_utilities import FinetunerSegmentation as RefFinetuner  # noqa: E402
+    from utilities.bce_and_dice import BCEandDiceLoss as RefLoss           # noqa: E402
+    from oracle import vit_oracle
+    dim, depth, heads, mlp, N, seed = 128, 2, 2, 256, 2, 63
+    sd = vit_oracle.make_state_mlp(seed, dim, depth, heads, mlp)
+    img, mask = vit_oracle.make_batch(seed, N)
+    enc = RefViT(image_size=224, patch_size=16, num_classes=3, dim=dim, depth=depth, heads=heads, mlp_dim=mlp, channels=6)
+    model = RefFinetuner(encoder=enc, configs={"mlp": True, "decoder": False, "num_classes": 3, "finetuning_patch_size": 16})
+    assert list(model.state_dict().keys()) == list(sd.keys())
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    model.train()
+    crit = RefLoss(weights=torch.tensor([1.0, 1.0, 1.0]), ignore_index=3, use_softmax=True)
+    out = model(torch.from_numpy(img))
+    loss = crit(out, torch.from_numpy(mask))
+    loss.backward()
+    fx = {"dim": dim, "depth": depth, "heads": heads, "mlp": mlp, "N": N, "seed": seed, "loss": loss.detach().numpy(),
+          "logits_sample": out.detach().numpy()[:, :, ::7, ::7].copy()}
+    names, norms = [], []
+    keep_full = {"head.0.weight", "head.0.bias", "head.2.weight", "head.2.bias", "model.transformer.norm.weight",
+                 "model.transformer.layers.1.1.net.4.weight", "model.pos_embedding"}
+    for k, p in model.named_parameters():
+        names.append(k)
+        norms.append(float(p.grad.double().norm()))
+        if k in keep_full:
+            fx[f"grad.{k}"] = p.grad.numpy()
+    fx["grad_names"] = np.array(names)
+    fx["grad_norms"] = np.array(norms, np.float64)
+    np.savez_compressed(OUT / "floodvit_mlp_d128_l2.npz", **fx)
+    print("floodvit mlp head loss", float(loss.detach()))
 
 
 def changeformer_goldens():
@@ -301,6 +338,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--vit-only" in sys.argv:
         vit_goldens()
+        sys.exit(0)
+    if "--vit-mlp-only" in sys.argv:
+        vit_mlp_goldens()
         sys.exit(0)
     if "--siam-only" in sys.argv:
         siam_goldens()

@@ -108,7 +108,22 @@ def floodvit_forward(sd, img, heads: int, dim_head: int = 64, out_size: int = 22
     G = int(round(n ** 0.5))
     x = tok.view(B, G, G, D).permute(0, 3, 1, 2)                                               # model_utilities.py:87
     x = F.interpolate(x, size=(out_size, out_size), mode="bilinear", align_corners=False)      # :89-91
+    if "head.0.weight" in sd:                                                                  # configs["mlp"]: Conv1x1 -> ReLU -> Conv1x1 (:60-65)
+        x = F.relu(F.conv2d(x, sd["head.0.weight"], sd["head.0.bias"]))
+        return F.conv2d(x, sd["head.2.weight"], sd["head.2.bias"])
     return F.conv2d(x, sd["head.weight"], sd["head.bias"])                                     # :93
+
+
+def make_state_mlp(seed: int, dim: int, depth: int, heads: int, mlp_dim: int, hidden: int = 512, n_cls: int = 3):
+    """State dict of FinetunerSegmentation(configs mlp=True): head = Sequential(Conv2d(dim, 512, 1), ReLU, Conv2d(512, n_cls, 1))."""
+    sd = make_state(seed, dim, depth, heads, mlp_dim)
+    del sd["head.weight"], sd["head.bias"]
+    rng = np.random.Generator(np.random.PCG64(seed + 17))
+    sd["head.0.weight"] = (rng.standard_normal((hidden, dim, 1, 1)) * np.sqrt(2.0 / dim)).astype(np.float32)
+    sd["head.0.bias"] = (0.1 * rng.standard_normal(hidden)).astype(np.float32)
+    sd["head.2.weight"] = (rng.standard_normal((n_cls, hidden, 1, 1)) * np.sqrt(1.0 / hidden)).astype(np.float32)
+    sd["head.2.bias"] = (0.1 * rng.standard_normal(n_cls)).astype(np.float32)
+    return sd
 
 
 def train_step(sd, img, mask, heads: int, class_weights=(1.0, 1.0, 1.0)):
