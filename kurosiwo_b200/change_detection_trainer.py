@@ -77,6 +77,11 @@ class FusedStepper(HostPipelineMixin):
                               optimizer=self.opt, momentum=float(self.model_configs.get("momentum", 0.0)),
                               process_group=self.pg,
                               dice_weight=0.0 if self.configs.get("loss_function") == "cross_entropy" else 1.0)
+            if self.engine is not None and self.engine.adam_m.numel() == eng.adam_m.numel():
+                # another batch geometry (e.g. the ragged last batch of an epoch): the optimizer state moves to the new engine
+                eng.adam_m.copy_(self.engine.adam_m)
+                eng.adam_v.copy_(self.engine.adam_v)
+                eng.adam_step.copy_(self.engine.adam_step)
             self.engine = eng
         return eng
 

@@ -61,8 +61,9 @@ class HostPipelineMixin:
             st["eager"][id(eng)] = n_eager + 1
             return eng.train_step(*tensors), tensors[-1]
         if st["engine"] is not eng:
-            if st["engine"] is not None:                                   # another batch geometry (e.g. a ragged last batch): stay eager
-                return eng.train_step(*tensors), tensors[-1]
+            # first capture, or another batch geometry took over (e.g. after a ragged last batch the model builds a new engine for the
+            # full-size batches): the old graph and its static inputs are dropped and this engine is captured instead
+            st["replay"], st["static"] = None, None
             st["static"] = [torch.empty_like(t) for t in tensors]
             st["replay"] = eng.capture(*st["static"], warmup=0, optimizer_in_graph=False)
             st["engine"] = eng

@@ -56,6 +56,11 @@ class FusedSegStepper(HostPipelineMixin):
             eng.init_training(class_weights=self.configs.get("class_weights", [1.0, 1.0, 1.0]), ignore_index=3, lr=self.lr,
                               betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=self.pg,
                               dice_weight=0.0 if self.configs.get("loss_function") == "cross_entropy" else 1.0)   # torch.optim.Adam(lr) (:36)
+            if self.engine is not None and self.engine.adam_m.numel() == eng.adam_m.numel():
+                # another batch geometry (e.g. the ragged last batch of an epoch): the optimizer state moves to the new engine
+                eng.adam_m.copy_(self.engine.adam_m)
+                eng.adam_v.copy_(self.engine.adam_v)
+                eng.adam_step.copy_(self.engine.adam_step)
             self.engine = eng
         return eng
 

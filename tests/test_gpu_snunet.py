@@ -235,3 +235,28 @@ def test_step_host_pipeline_equals_eager_steps():
         np.testing.assert_allclose(la.cpu().numpy(), lb.cpu().numpy(), rtol=1e-4)
     for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         assert (pa - pb).abs().max().item() < 2e-4, n          # 6 Adam steps of <= 1e-3 each; fp32 atomics order differs between runs
+
+
+def test_step_host_recaptures_after_a_ragged_batch():
+    """Full batches replay a graph; a ragged batch runs eagerly on a new engine (optimizer state carried over); when the full-size
+    batches come back they are captured again - and the whole sequence equals the same steps run eagerly on one optimizer state."""
+    from kurosiwo_b200 import synthetic
+    from kurosiwo_b200.change_detection_trainer import FusedStepper, select_inputs, unpack_batch
+    base, seed = 8, 43
+    configs = {"device": DEV, "inputs": ["pre_event_1", "post_event"], "dem": False, "scale_input": "normalize", "num_classes": 3,
+               "loss_function": "ce+dice", "class_weights": [1.0, 1.0, 1.0], "method": "snunet"}
+    model_configs = {"method": "snunet", "optimizer": "adam", "learning_rate": 1e-3, "base_channel": base}
+    full = [synthetic.make_batch(100 + i, 2, 32, 32, True) for i in range(7)]
+    ragged = synthetic.make_batch(200, 1, 32, 32, True)
+    seq = full[:4] + [ragged] + full[4:]
+    ma, mb = (_model(weights.make_state(seed, 2, 3, base), base, "fp32") for _ in range(2))
+    stepper = FusedStepper(ma, configs, model_configs)
+    la = [stepper.step_host(b)[0].clone() for b in seq]
+    assert stepper._pl["replay"] is not None and int(stepper.engine.adam_step.item()) == len(seq)
+    ref = FusedStepper(mb, dict(configs, cuda_graph=False), model_configs)
+    lb = [ref.step_host(b)[0].clone() for b in seq]
+    torch.cuda.synchronize()
+    for a, b in zip(la, lb):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-4)
+    for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert (pa - pb).abs().max().item() < 3e-4, n

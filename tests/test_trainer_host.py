@@ -131,3 +131,24 @@ def test_data_parallel_step_gloo_world2():
         off, shape = fp.offsets[n]
         got = g0[off:off + shape.numel()].view(shape)
         assert (got - tot[n]).abs().max().item() <= 2e-3 * tot[n].abs().max().item() + 1e-6, n
+
+
+def test_optimizer_state_survives_a_ragged_batch():
+    """A batch of another size builds a new engine (new activation buffers); the Adam moments and step count must carry over."""
+    configs, model_configs = _cfg()
+    model = SNUNet_ECAM(2, 3, base_channel=8, precision="fp32")
+    model.set_ops(ShadowOps())
+    stepper = cdt.FusedStepper(model, configs, model_configs)
+    full = synthetic.make_batch(11, 2, 32, 32, False)
+    ragged = synthetic.make_batch(12, 1, 32, 32, False)
+    stepper.step_host(full); stepper.step_host(full)
+    e1 = stepper.engine
+    m_before = e1.adam_m.clone()
+    assert int(e1.adam_step.item()) == 2 and float(m_before.abs().sum()) > 0
+    stepper.step_host(ragged)
+    e2 = stepper.engine
+    assert e2 is not e1 and int(e2.adam_step.item()) == 3
+    # after one more step the first moment is 0.9 * old + 0.1 * g: it cannot be the fresh-state value 0.1 * g
+    g = e2.params.grad
+    assert not torch.allclose(e2.adam_m, 0.1 * g, rtol=1e-3, atol=1e-9)
+    assert torch.allclose(e2.adam_m, 0.9 * m_before + 0.1 * g, rtol=1e-4, atol=1e-8)
