@@ -152,3 +152,10 @@ def test_optimizer_state_survives_a_ragged_batch():
     g = e2.params.grad
     assert not torch.allclose(e2.adam_m, 0.1 * g, rtol=1e-3, atol=1e-9)
     assert torch.allclose(e2.adam_m, 0.9 * m_before + 0.1 * g, rtol=1e-4, atol=1e-8)
+
+
+def test_lookahead_pairs():
+    from kurosiwo_b200.host_pipeline import lookahead
+    assert list(lookahead([])) == []
+    assert list(lookahead([1])) == [(1, None)]
+    assert list(lookahead("abc")) == [("a", "b"), ("b", "c"), ("c", None)]
