@@ -150,6 +150,18 @@ class _FinetuneFunction(torch.autograd.Function):
         return (None, None, *grads)
 
 
+class Decoder(nn.Module):
+    """models/model_utilities.py:21-48 (parameters only: the arithmetic runs in mlp_head_engine.ViTDecoderHeadEngine)."""
+
+    def __init__(self, input_size, output_channels):
+        super().__init__()
+        self.deconv1 = nn.ConvTranspose2d(1024, 128, kernel_size=4, stride=2, padding=1)
+        self.relu = nn.ReLU()
+        self.up = nn.Upsample(scale_factor=2)
+        self.deconv2 = nn.ConvTranspose2d(128, 64, kernel_size=4, stride=2, padding=1)
+        self.deconv3 = nn.ConvTranspose2d(64, output_channels, kernel_size=4, stride=2, padding=1)
+
+
 class FinetunerSegmentation(_EngineHost):
     """models/model_utilities.py:51-94.  configs keys: mlp, decoder, num_classes, finetuning_patch_size (as the reference)."""
 
@@ -161,12 +173,11 @@ class FinetunerSegmentation(_EngineHost):
         self.pool = pool
         if pool:
             raise NotImplementedError("pool=True (one Linear over the cls token) is outside the fused path")
-        if configs.get("decoder"):
-            raise NotImplementedError("the deconvolution `Decoder` head (model_utilities.py:21-48, hard-wired to a 1024-wide encoder) is not on "
-                                      "the fused path; heads built: linear (mlp=false) and mlp (mlp=true)")
-        if configs.get("mlp"):                                    # model_utilities.py:60-65
+        if configs.get("mlp"):                                    # model_utilities.py:60-65 (mlp wins over decoder, as in the reference)
             self.head = nn.Sequential(nn.Conv2d(encoder.mlp_head.in_features, 512, kernel_size=1), nn.ReLU(),
                                       nn.Conv2d(512, configs["num_classes"], kernel_size=1))
+        elif configs.get("decoder"):                              # model_utilities.py:66-69
+            self.head = Decoder(encoder.mlp_head.in_features, configs["num_classes"])
         else:
             self.head = nn.Conv2d(encoder.mlp_head.in_features, configs["num_classes"], kernel_size=1)
         self.model.mlp_head = nn.Identity()
@@ -181,7 +192,11 @@ class FinetunerSegmentation(_EngineHost):
             self._engines = {}
             if self.configs.get("finetuning_patch_size", 16) != 16:
                 raise NotImplementedError("finetuning_patch_size must equal the encoder's 16x16 patches")
-            if self.configs.get("mlp"):
+            if self.configs.get("decoder") and not self.configs.get("mlp"):
+                from .mlp_head_engine import ViTDecoderHeadEngine
+                eng = ViTDecoderHeadEngine(ops, self, "model.", self.model.cfg, self.configs["num_classes"], x.shape[0], x.shape[2], x.shape[3],
+                                           self._storage_dtype(), x.device)
+            elif self.configs.get("mlp"):
                 from .mlp_head_engine import ViTMlpHeadEngine
                 eng = ViTMlpHeadEngine(ops, self, "model.", self.model.cfg, self.configs["num_classes"], x.shape[0], x.shape[2], x.shape[3],
                                        self._storage_dtype(), x.device)

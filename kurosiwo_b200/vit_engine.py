@@ -41,7 +41,7 @@ class ViTSegEngine(TrainStepMixin):
     def __init__(self, ops, module: torch.nn.Module, enc_prefix: str, cfg: dict, head: str, num_classes: int,
                  B: int, H: int, W: int, dtype: torch.dtype, device, conv_impl: int = 0):
         assert num_classes == 3, "the fused head/loss kernels are built for num_classes == 3 (configs/config.json:13)"
-        assert head in ("linear", "mlp", "upernet"), "heads on the fused path: linear / mlp (FinetunerSegmentation), upernet (HF UperNetHead)"
+        assert head in ("linear", "mlp", "decoder", "upernet"), "heads on the fused path: linear / mlp / decoder (FinetunerSegmentation), upernet (HF UperNetHead)"
         self.head_kind = head
         self.ops, self.module, self.dtype, self.device = ops, module, dtype, torch.device(device)
         self.pre = enc_prefix

@@ -84,6 +84,7 @@ def main():
     siam_goldens()
     vit_goldens()
     vit_mlp_goldens()
+    vit_decoder_goldens()
     changeformer_goldens()
     upernet_goldens()
 
@@ -217,6 +218,43 @@ def vit_mlp_goldens():
     print("floodvit mlp head loss", float(loss.detach()))
 
 
+def vit_decoder_goldens():
+    """FloodViT with the deconvolution `Decoder` head (FinetunerSegmentation configs decoder=True; encoder width 1024 as the reference
+    hard-wires) from the unmodified reference modules."""
+    from oracle.ref_import import install_stubs
+    install_stubs()
+    from models.vision_transformer import ViT as RefViT                    # noqa: E402  (reference, read-only)
+    from models.model_utilities import FinetunerSegmentation as RefFinetuner  # noqa: E402
+    from utilities.bce_and_dice import BCEandDiceLoss as RefLoss           # noqa: E402
+    from oracle import vit_oracle
+    depth, heads, mlp, N, seed = 1, 2, 128, 2, 64
+    sd = vit_oracle.make_state_decoder(seed, depth, heads, mlp)
+    img, mask = vit_oracle.make_batch(seed, N)
+    enc = RefViT(image_size=224, patch_size=16, num_classes=3, dim=1024, depth=depth, heads=heads, mlp_dim=mlp, channels=6)
+    model = RefFinetuner(encoder=enc, configs={"mlp": False, "decoder": True, "num_classes": 3, "finetuning_patch_size": 16})
+    assert list(model.state_dict().keys()) == list(sd.keys())
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    model.train()
+    crit = RefLoss(weights=torch.tensor([1.0, 1.0, 1.0]), ignore_index=3, use_softmax=True)
+    out = model(torch.from_numpy(img))
+    loss = crit(out, torch.from_numpy(mask))
+    loss.backward()
+    fx = {"depth": depth, "heads": heads, "mlp": mlp, "N": N, "seed": seed, "loss": loss.detach().numpy(),
+          "logits_sample": out.detach().numpy()[:, :, ::7, ::7].copy()}
+    names, norms = [], []
+    keep_full = {"head.deconv1.bias", "head.deconv2.weight", "head.deconv2.bias", "head.deconv3.weight", "head.deconv3.bias",
+                 "model.transformer.norm.weight"}
+    for k, p in model.named_parameters():
+        names.append(k)
+        norms.append(float(p.grad.double().norm()))
+        if k in keep_full:
+            fx[f"grad.{k}"] = p.grad.numpy()
+    fx["grad_names"] = np.array(names)
+    fx["grad_norms"] = np.array(norms, np.float64)
+    np.savez_compressed(OUT / "floodvit_decoder_d1024_l1.npz", **fx)
+    print("floodvit decoder head loss", float(loss.detach()))
+
+
 def changeformer_goldens():
     """ChangeFormerV6 fixtures from the unmodified reference (timm stubbed: DropPath / trunc_normal_ / to_2tuple only); the stochastic
     layers run with p = 0 (train-mode BatchNorm statistics kept), see oracle/changeformer_oracle.py."""
@@ -338,6 +376,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--vit-only" in sys.argv:
         vit_goldens()
+        sys.exit(0)
+    if "--vit-decoder-only" in sys.argv:
+        vit_decoder_goldens()
         sys.exit(0)
     if "--vit-mlp-only" in sys.argv:
         vit_mlp_goldens()

@@ -107,6 +107,11 @@ def floodvit_forward(sd, img, heads: int, dim_head: int = 64, out_size: int = 22
     B, n, D = tok.shape
     G = int(round(n ** 0.5))
     x = tok.view(B, G, G, D).permute(0, 3, 1, 2)                                               # model_utilities.py:87
+    if "head.deconv1.weight" in sd:                                                            # configs["decoder"]: no interpolation (:88), Decoder.forward (:36-48)
+        x = F.relu(F.conv_transpose2d(x, sd["head.deconv1.weight"], sd["head.deconv1.bias"], stride=2, padding=1))
+        x = F.interpolate(x, scale_factor=2)                                                   # nn.Upsample(scale_factor=2): nearest
+        x = F.relu(F.conv_transpose2d(x, sd["head.deconv2.weight"], sd["head.deconv2.bias"], stride=2, padding=1))
+        return F.conv_transpose2d(x, sd["head.deconv3.weight"], sd["head.deconv3.bias"], stride=2, padding=1)
     x = F.interpolate(x, size=(out_size, out_size), mode="bilinear", align_corners=False)      # :89-91
     if "head.0.weight" in sd:                                                                  # configs["mlp"]: Conv1x1 -> ReLU -> Conv1x1 (:60-65)
         x = F.relu(F.conv2d(x, sd["head.0.weight"], sd["head.0.bias"]))
@@ -123,6 +128,19 @@ def make_state_mlp(seed: int, dim: int, depth: int, heads: int, mlp_dim: int, hi
     sd["head.0.bias"] = (0.1 * rng.standard_normal(hidden)).astype(np.float32)
     sd["head.2.weight"] = (rng.standard_normal((n_cls, hidden, 1, 1)) * np.sqrt(1.0 / hidden)).astype(np.float32)
     sd["head.2.bias"] = (0.1 * rng.standard_normal(n_cls)).astype(np.float32)
+    return sd
+
+
+def make_state_decoder(seed: int, depth: int, heads: int, mlp_dim: int, n_cls: int = 3):
+    """State dict of FinetunerSegmentation(configs decoder=True): head = Decoder (deconv 1024->128->64->n_cls, all k4 s2 p1); the
+    reference hard-wires the first deconvolution to 1024 input channels, so the encoder width is 1024."""
+    dim = 1024
+    sd = make_state(seed, dim, depth, heads, mlp_dim)
+    del sd["head.weight"], sd["head.bias"]
+    rng = np.random.Generator(np.random.PCG64(seed + 23))
+    for name, ci, co in (("deconv1", 1024, 128), ("deconv2", 128, 64), ("deconv3", 64, n_cls)):
+        sd[f"head.{name}.weight"] = (rng.standard_normal((ci, co, 4, 4)) * np.sqrt(2.0 / (ci * 4))).astype(np.float32)
+        sd[f"head.{name}.bias"] = (0.1 * rng.standard_normal(co)).astype(np.float32)
     return sd
 
 

@@ -206,3 +206,45 @@ def test_mlp_head_schedule_matches_oracle():
     for name, p in model.named_parameters():
         go = grads_o[name]
         assert (p.grad - go).abs().max().item() <= 2e-3 * go.abs().max().item() + 1e-8, name
+
+
+def _decoder_case():
+    fx = np.load(GOLD / "floodvit_decoder_d1024_l1.npz")
+    depth, heads, mlp, N, seed = (int(fx[k]) for k in ("depth", "heads", "mlp", "N", "seed"))
+    sd_np = vit_oracle.make_state_decoder(seed, depth, heads, mlp)
+    img, mask = (torch.from_numpy(a) for a in vit_oracle.make_batch(seed, N))
+    return fx, depth, heads, mlp, sd_np, img, mask
+
+
+def test_decoder_head_oracle_matches_golden():
+    """FinetunerSegmentation(configs decoder=True) (Decoder, models/model_utilities.py:21-48): the oracle against the UNMODIFIED reference."""
+    fx, depth, heads, mlp, sd_np, img, mask = _decoder_case()
+    loss, logits, grads = vit_oracle.train_step(vit_oracle.to_torch_state(sd_np), img, mask, heads)
+    np.testing.assert_allclose(logits.numpy()[:, :, ::7, ::7], fx["logits_sample"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(float(loss), float(fx["loss"]), rtol=1e-5)
+    for n, ref_norm in zip([str(n) for n in fx["grad_names"]], fx["grad_norms"]):
+        assert abs(float(grads[n].double().norm()) - ref_norm) <= 5e-4 * ref_norm + 1e-8, n
+    for k in fx.files:
+        if k.startswith("grad."):
+            np.testing.assert_allclose(grads[k[5:]].numpy(), fx[k], rtol=2e-3, atol=1e-6 + 2e-4 * np.abs(fx[k]).max())
+
+
+def test_decoder_head_schedule_matches_oracle():
+    """The Decoder-head host schedule (mlp_head_engine.ViTDecoderHeadEngine: every ConvTranspose2d(k4,s2,p1) as one 4-phase 3x3 conv,
+    nearest x2 as strided copies) on the CPU shadow ops."""
+    fx, depth, heads, mlp, sd_np, img, mask = _decoder_case()
+    loss_o, logits_o, grads_o = vit_oracle.train_step(vit_oracle.to_torch_state(sd_np), img, mask, heads)
+    enc = ViT(image_size=224, patch_size=16, num_classes=3, dim=1024, depth=depth, heads=heads, mlp_dim=mlp, channels=6, precision="fp32")
+    model = FinetunerSegmentation(encoder=enc, configs={"mlp": False, "decoder": True, "num_classes": 3, "finetuning_patch_size": 16})
+    assert list(model.state_dict().keys()) == list(sd_np.keys())
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd_np.items()})
+    model.set_ops(ShadowOps())
+    model.train()
+    out = model(img)
+    loss = ce_dice_torch(out, mask, (1.0, 1.0, 1.0))
+    loss.backward()
+    np.testing.assert_allclose(out.detach().numpy(), logits_o.numpy(), rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(float(loss.detach()), float(loss_o), rtol=1e-4)
+    for name, p in model.named_parameters():
+        go = grads_o[name]
+        assert (p.grad - go).abs().max().item() <= 2e-3 * go.abs().max().item() + 1e-8, name
