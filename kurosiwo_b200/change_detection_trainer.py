@@ -97,6 +97,21 @@ class FusedStepper(HostPipelineMixin):
         return [xa, xb, b["mask"].to(dev, non_blocking=True)]
 
 
+def _train_predictions(engine, model_configs):
+    """The class map the training metrics see.  Default: the argmax the loss kernel emitted.  ChangeFormer with
+    `multi_scale_infer` (change_detection_trainer.py:139-148): argmax of the mean of the five outputs, the coarser ones resized with
+    mode='nearest' - a metrics-only side computation on the outputs the engine already holds (off by default in the reference)."""
+    if model_configs.get("multi_scale_infer") and hasattr(engine, "outputs"):
+        outs = engine.outputs()
+        size = outs[-1].shape[2]
+        final = torch.zeros_like(outs[-1], dtype=torch.float32)
+        for o in outs:
+            o = o.float()
+            final += torch.nn.functional.interpolate(o, size=size, mode="nearest") if o.shape[2] != size else o
+        return (final / len(outs)).argmax(1)
+    return engine.pred
+
+
 def train_change_detection(model, train_loader, val_loader, test_loader, configs, model_configs, process_group=None):
     assert len(configs["inputs"]) == 2, f'Model {model_configs.get("method")} requires exactly 2 input images.'
     device = configs["device"]
@@ -118,7 +133,7 @@ def train_change_detection(model, train_loader, val_loader, test_loader, configs
                 stepper.prefetch(nxt)                                # H2D of the next batch overlaps this step
             loss3, mask = stepper.step_host(batch)
             train_loss += loss3[0].double() * mask.shape[0]          # stays on device: no .item() in the loop
-            metrics.update(stepper.engine.pred, mask)
+            metrics.update(_train_predictions(stepper.engine, model_configs), mask)
             if configs.get("on_screen_prints") and index % configs.get("print_frequency", 10) == 0:
                 print(f"({epoch}) it {index} Train Loss: {train_loss.item():.4f}")
         loss_val = float(loss3[0].item()) if index >= 0 else float("nan")
