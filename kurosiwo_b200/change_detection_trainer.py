@@ -62,6 +62,9 @@ class FusedStepper(HostPipelineMixin):
         opt = model_configs.get("optimizer", "adam")
         if opt not in ("adam", "sgd"):
             raise NotImplementedError(f"fused optimizer '{opt}' ('adam': change_detection_trainer.py:52-54, 'sgd': :61-66)")
+        if model_configs.get("multi_scale_train"):
+            raise NotImplementedError("multi_scale_train (weighted loss over ChangeFormer's five outputs, change_detection_trainer.py:155-164) "
+                                      "is not on the fused path: the side heads run forward-only (see DESIGN.md section 7)")
         self.opt = opt
         self.model, self.configs, self.model_configs, self.pg = model, configs, model_configs, process_group
         self.engine = None
