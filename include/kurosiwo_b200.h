@@ -361,11 +361,25 @@ int ks_ce_dice_fwd_bwd_ex(const float *logits, const int64_t *labels, int N, int
 int ks_confusion_update(const uint8_t *pred, const int64_t *labels, int64_t n, int num_classes_with_ignore, int ignore_index,
                         int64_t *mat, void *stream);
 
+/* Same counts routed additionally by per-sample keys (one launch for the global, the per-activation/AOI and the per-climate-zone
+ * metric sets of change_detection_trainer.py:184-199, :445-472 and segmentation_trainer.py:407-512): sample s adds its KxK counts
+ * to mat, to mat_a[key_a[s]] and to mat_b[key_b[s]] (keys outside [0, n) are skipped; any of mat / mat_a / mat_b may be NULL).
+ * The water-only F-score (evaluate_water, :408-413) is the same matrix with classes 1 and 2 merged. */
+int ks_confusion_update_grouped(const uint8_t *pred, const int64_t *labels, int n_samples, int64_t per_sample,
+                                int num_classes_with_ignore, int ignore_index, const int32_t *key_a, int n_a,
+                                const int32_t *key_b, int n_b, int64_t *mat, int64_t *mat_a, int64_t *mat_b, void *stream);
+
 /* ---- optimizer (torch.optim.Adam, change_detection_trainer.py:52-54) ---- */
 /* step_ptr: device int32 counter, incremented by the kernel (graph-capturable). */
 int ks_adam_step(float *p, const float *g, float *m, float *v, int64_t n,
                  float lr, float beta1, float beta2, float eps, float weight_decay,
                  float grad_scale, int *step_ptr, void *stream);
+
+/* torch.optim.AdamW(lr, betas, weight_decay) (change_detection_trainer.py:55-60): decoupled decay p *= 1 - lr*wd, then the Adam
+ * update on grad_scale*g. Same state layout as ks_adam_step. */
+int ks_adamw_step(float *p, const float *g, float *m, float *v, int64_t n,
+                  float lr, float beta1, float beta2, float eps, float weight_decay,
+                  float grad_scale, int *step_ptr, void *stream);
 
 /* torch.optim.SGD(lr, momentum, weight_decay) (change_detection_trainer.py:61-66; ChangeFormer: momentum 0.99, wd 1e-5,
  * configs/method/changeformer/changeformer.json): g = grad_scale*g + wd*p; buf = momentum*buf + g; p -= lr*buf. */

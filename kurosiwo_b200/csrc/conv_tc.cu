@@ -37,7 +37,7 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-Options g_opt = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+Options g_opt = {};
 
 struct alignas(64) ConvTcParams {
   CUtensorMap src[KS_MAX_VIEWS];
@@ -54,6 +54,7 @@ struct alignas(64) ConvTcParams {
   uint32_t b_tile_bytes;
   double *stats;
   int Cout, debug;
+  int BNA;   // TMEM columns per accumulator: BN, or 3*BN when the three column taps are stacked along N
 };
 
 using namespace tc;
@@ -237,31 +238,55 @@ __device__ __forceinline__ void warp_reduce_scatter16(float (&v)[16], int lane) 
 // Issue the MMAs of NT consecutive taps for up to 4 output windows.  Every descriptor is (per-stage base + compile-time
 // immediate): no loop-carried dependency, so the single issuing lane is throughput- not latency-bound (the uniform
 // datapath has ~10-cycle ALU latency; chained descriptor arithmetic cost ~55 cycles per MMA before this).
-template <int NT, int BK>
+template <int NT, int BK, bool NS3>
 __device__ __forceinline__ void issue_taps(uint32_t a_lo_row, uint32_t a_tile_step, uint32_t b_lo0, uint32_t b_tile_step,
-                                           uint32_t desc_hi, uint32_t acc_col, int BN, int nvalid, uint32_t idesc,
+                                           uint32_t desc_hi, uint32_t acc_col, int BNA, int nvalid, uint32_t idesc,
                                            uint32_t accum_or, bool skip) {
   constexpr uint32_t ROW16 = (BK * 2) >> 4;
+  if constexpr (NS3) {
+    // Column taps stacked along N: ONE UMMA per (kernel row, k step) multiplies the halo tile viewed from row offset
+    // r*16 (column offset 0) with the [3*BN x BK] tile {W[r][0]; W[r][1]; W[r][2]} (three consecutive weight tiles), so
+    // accumulator column block s holds sum_r x[q + 16 r] W[r][s]; the epilogue adds the blocks with a lane shift of s.
+    // A 128 x 3BN x 16 UMMA reads 4 KB + 3 BN * 32 B of shared memory per 1.5 BN tensor cycles instead of per BN / 2.
+    static_assert(NT % 3 == 0, "row groups");
 #pragma unroll
-  for (int tl = 0; tl < NT; ++tl) {
-    const uint32_t roff = (NT == 9) ? (uint32_t)((tl / 3) * 16 + tl % 3) : (uint32_t)tl;
+    for (int rr = 0; rr < NT / 3; ++rr) {
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-      if (mt < nvalid) {
-        const uint32_t a_lo = a_lo_row + (uint32_t)mt * a_tile_step + roff * ROW16;
-        const uint32_t b_lo = b_lo0 + (uint32_t)tl * b_tile_step;
+      for (int mt = 0; mt < 4; ++mt) {
+        if (mt < nvalid) {
+          const uint32_t a_lo = a_lo_row + (uint32_t)mt * a_tile_step + (uint32_t)(rr * 16) * ROW16;
+          const uint32_t b_lo = b_lo0 + (uint32_t)(3 * rr) * b_tile_step;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
-          const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
-          if (!skip) umma_bf16(acc_col + (uint32_t)(mt * BN), ad, bd, idesc, accum_or | (uint32_t)(tl | k));
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
+            const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
+            if (!skip) umma_bf16(acc_col + (uint32_t)(mt * BNA), ad, bd, idesc, accum_or | (uint32_t)(rr | k));
+          }
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int tl = 0; tl < NT; ++tl) {
+      const uint32_t roff = (NT == 9) ? (uint32_t)((tl / 3) * 16 + tl % 3) : (uint32_t)tl;
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        if (mt < nvalid) {
+          const uint32_t a_lo = a_lo_row + (uint32_t)mt * a_tile_step + roff * ROW16;
+          const uint32_t b_lo = b_lo0 + (uint32_t)tl * b_tile_step;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2u * k);
+            const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2u * k);
+            if (!skip) umma_bf16(acc_col + (uint32_t)(mt * BNA), ad, bd, idesc, accum_or | (uint32_t)(tl | k));
+          }
         }
       }
     }
   }
 }
 
-template <int BK, int KS>
+template <int BK, int KS, bool NS3>
 __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant__ ConvTcParams p) {
 #define MBW(bar, par) do { if (p.debug & 32) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -275,7 +300,7 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
   constexpr int TAPS = KS * KS;
 
   const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
-  const int SA = p.SA, SB = p.SB, MT = p.MT, BN = p.BN, NACC = p.n_acc;
+  const int SA = p.SA, SB = p.SB, MT = p.MT, BN = p.BN, NACC = p.n_acc, BNA = p.BNA;
   const bool RES = p.resident != 0;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -385,7 +410,7 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
       const int nvalid = min(MT, p.total_tiles - st * MT);
       MBW(acc_empty(as), pacc ^ 1);
       tc_fence_after();
-      const uint32_t acc_col = tmem_base + (uint32_t)(as * MT * BN);
+      const uint32_t acc_col = tmem_base + (uint32_t)(as * MT * BNA);
       uint32_t accum = 0, widx = 0;
       for (int s = 0; s < p.n_src; ++s) {
         const int C = p.cstart[s + 1] - p.cstart[s];
@@ -396,7 +421,7 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
           if (RES) {
             if (elect_one()) {
               const uint32_t b_lo0 = (((b_base + widx * p.b_tile_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-              issue_taps<TAPS, BK>(a_lo0, a_tile_step, b_lo0, b_tile_step, desc_hi, acc_col, BN, nvalid, p.idesc, accum, skip);
+              issue_taps<TAPS, BK, NS3>(a_lo0, a_tile_step, b_lo0, b_tile_step, desc_hi, acc_col, BNA, nvalid, p.idesc, accum, skip);
               tc_commit(a_empty(sa));
             }
             __syncwarp();
@@ -408,12 +433,12 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
               if (elect_one()) {
                 const uint32_t b_lo0 = (((b_base + (uint32_t)sb * p.b_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
                 if (KS == 3 && TB == 3) {
-                  issue_taps<3, BK>(a_lo0 + (uint32_t)(tg * 16) * (ROW_BYTES >> 4), a_tile_step, b_lo0, b_tile_step, desc_hi, acc_col, BN,
-                                    nvalid, p.idesc, accum | (uint32_t)tg, skip);
+                  issue_taps<3, BK, NS3>(a_lo0 + (uint32_t)(tg * 16) * (ROW_BYTES >> 4), a_tile_step, b_lo0, b_tile_step, desc_hi, acc_col, BNA,
+                                         nvalid, p.idesc, accum | (uint32_t)tg, skip);
                 } else {
                   const uint32_t roff = (KS == 3) ? (uint32_t)((tg / 3) * 16 + tg % 3) : 0u;
-                  issue_taps<1, BK>(a_lo0 + roff * (ROW_BYTES >> 4), a_tile_step, b_lo0, b_tile_step, desc_hi, acc_col, BN, nvalid,
-                                    p.idesc, accum | (uint32_t)tg, skip);
+                  issue_taps<1, BK, false>(a_lo0 + roff * (ROW_BYTES >> 4), a_tile_step, b_lo0, b_tile_step, desc_hi, acc_col, BNA, nvalid,
+                                           p.idesc, accum | (uint32_t)tg, skip);
                 }
                 tc_commit(b_empty(sb));
                 if (tg == TAPS / TB - 1) tc_commit(a_empty(sa));
@@ -458,15 +483,17 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
           ok = (tx < TW) && (ty < p.TH) && (h < p.H) && (w < p.W);
         }
         const bool wide = (BN - cc) >= 32;
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * MT * BN + mt * BN + cc);
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * MT * BNA + mt * BNA + cc);
         uint32_t r[32];
-        if (p.debug & 2) {
+        if constexpr (!NS3) {
+          if (p.debug & 2) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = 0u;
-        } else if (wide) tmem_ld32(taddr, r);
-        else { uint32_t r16[16]; tmem_ld16(taddr, r16);
+            for (int i = 0; i < 32; ++i) r[i] = 0u;
+          } else if (wide) tmem_ld32(taddr, r);
+          else { uint32_t r16[16]; tmem_ld16(taddr, r16);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0u; } }
+            for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0u; } }
+        }
         // destination pointers of the two 16-column halves (view boundaries are multiples of 16 channels)
         __nv_bfloat16 *op[2]; bool accd[2];
 #pragma unroll
@@ -481,10 +508,32 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh)
           if (ok && hh < nh && accd[hh]) ld_global_v8(op[hh], old[hh]);
-        tmem_ld_wait();
         float v[32];
+        if constexpr (NS3) {
+          // out[lane] = D0[lane] + D1[lane + 1] + D2[lane + 2]: column-tap block s sits BN columns further and belongs to the
+          // pixel s columns to the right, i.e. lane + s of the same 16-pixel row (real outputs have tx <= 13, so tx + s <= 15).
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          for (int hh = 0; hh < 2; ++hh) {
+            if (hh < nh) {
+              uint32_t d0[16], d1[16], d2[16];
+              tmem_ld16(taddr + 16 * hh, d0);
+              tmem_ld16(taddr + BN + 16 * hh, d1);
+              tmem_ld16(taddr + 2 * BN + 16 * hh, d2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                v[16 * hh + i] = __uint_as_float(d0[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(d1[i]), 1) +
+                                 __shfl_down_sync(0xffffffffu, __uint_as_float(d2[i]), 2);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[16 * hh + i] = 0.f;
+            }
+          }
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        }
         if (p.bias) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -579,15 +628,15 @@ static int launch_conv_tc(const ConvTcParams &p, dim3 grid, size_t smem, cudaStr
 
 extern "C" int ks_bn_stats(int dtype, int N, int H, int W, const ks_view_t *x, double *sums, void *stream);
 
-template <int BK, int KS>
+template <int BK, int KS, bool NS3>
 static int launch_conv_tc2(const ConvTcParams &p, dim3 grid, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BK, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BK, KS, NS3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  conv_tc2_kernel<BK, KS><<<grid, 320, smem, st>>>(p);
+  conv_tc2_kernel<BK, KS, NS3><<<grid, 320, smem, st>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -639,7 +688,18 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
   p.b_tile_bytes = (uint32_t)p.BN * row_bytes;
   p.b_stage_bytes = p.b_tile_bytes;   // streamed: x TB below
   p.TB = 1;
-  p.idesc = make_idesc_bf16(128, p.BN, 0, 0);
+  // column taps stacked along N (see issue_taps): 3x3 convs with narrow N tiles, where a 128 x BN x 16 UMMA is bound by its
+  // 4 KB shared-memory read of the pixel operand (BN <= 64: at most 40 % / 67 % of the tensor rate)
+  // Measured (scripts/bench_layers.py, KS_DEBUG ablations, B200): a 128 x N x 16 UMMA costs max(N / 2, (4096 + 32 N) / 128) cycles
+  // (N = 32: 40, N = 96: 56), so stacking lifts the N = 32 layers from 40 % to 86 % of the tensor rate.  It also triples the
+  // epilogue's TMEM reads and adds 2 shuffles per output, so it only pays when the K loop is long (Cin >= ~96); for N tiles of
+  // 64 (N = 192) it measured no gain (977 vs 978 TFLOP/s on 384->64@112), so the default applies it to N tiles <= 32 only.
+  const int ns3_min_cin = g_opt.ns3_min_cin > 0 ? g_opt.ns3_min_cin : 96;
+  const int ns3_max_bn = g_opt.ns3_min_cin > 0 ? 80 : 32;
+  bool ns3 = !v1 && ksize == 3 && p.BN <= ns3_max_bn && 3 * p.BN <= 256 && (3 * p.BN) % 16 == 0 && !g_opt.no_ns3 && Cin >= ns3_min_cin;
+  int ns3_one_cta = 0;
+  p.BNA = ns3 ? 3 * p.BN : p.BN;
+  p.idesc = make_idesc_bf16(128, p.BNA, 0, 0);
   p.n_wtiles = (Cin / BK) * taps;
   const size_t budget = 222 * 1024;
   const size_t fixed = 1024 + 512 + (size_t)p.BN * 4 * 3 + (size_t)(p.BN / 16) * 8;
@@ -654,7 +714,7 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
   if (!v1 && want_res && w_bytes + 2 * p.a_tile_bytes + fixed <= budget) {
     p.resident = 1;
     MT = g_opt.mt > 0 ? g_opt.mt : 2;
-    while (MT > 1 && (2 * MT * p.BN > 512 || w_bytes + 2 * (size_t)MT * p.a_tile_bytes + fixed > budget)) MT >>= 1;
+    while (MT > 1 && (2 * MT * p.BNA > 512 || w_bytes + 2 * (size_t)MT * p.a_tile_bytes + fixed > budget)) MT >>= 1;
     SA = g_opt.sa > 0 ? g_opt.sa : 4;
     while (SA > 2 && w_bytes + (size_t)SA * MT * p.a_tile_bytes + fixed > budget) --SA;
     SB = 1;
@@ -662,11 +722,23 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
     // streamed weights.  Measured (scripts/sweep_stream.py, B200): two co-resident CTAs per SM beat deeper pipelines, and one
     // weight stage per kernel ROW (3 taps) beats one per tap whenever it still leaves room for two CTAs.
     MT = g_opt.mt > 0 ? g_opt.mt : 1;
-    while (MT > 1 && (v1 ? MT * p.BN > 512 : 2 * MT * p.BN > 512)) MT >>= 1;
+    while (MT > 1 && (v1 ? MT * p.BN > 512 : 2 * MT * p.BNA > 512)) MT >>= 1;
     auto bytes = [&](int mt, int sa, int sb, int tb) { return (size_t)sa * mt * p.a_tile_bytes + (size_t)sb * tb * p.b_tile_bytes + fixed; };
     const size_t half_sm = (227 * 1024) / 2 - 1024;
     const bool can3 = !v1 && ksize == 3 && g_opt.tb != 1;
     int TB = 1;
+    if (ns3) {
+      // a 512-column TMEM allocation allows ONE CTA per SM (two accumulators of 3*BN columns, deep rings); 256 columns allow two
+      // co-resident CTAs (BN = 64: a single accumulator each, the other CTA's MMAs cover the epilogue)
+      ns3_one_cta = g_opt.ns3_mode ? (g_opt.ns3_mode == 2) : 1;
+      if (ns3_one_cta) {
+        MT = (g_opt.mt > 0 ? g_opt.mt : 1); while (MT > 1 && 2 * MT * p.BNA > 512) MT >>= 1;
+        TB = 3; SA = 4; SB = 4;
+        while (bytes(MT, SA, SB, TB) > budget && (SA > 2 || SB > 2)) { if (SB >= SA && SB > 2) --SB; else --SA; }
+      } else {
+        MT = 1; TB = 3; SA = 2; SB = 2;
+      }
+    } else
     // 1x1 (plain GEMM: the ViT / ChangeFormer Linear layers): a stage holds only BK/16 = 4 UMMAs, so two-deep rings expose the
     // TMA round trip; measured (scripts/dbg_gemm2.py, 13312 x 768 x 3072): SA=SB=2 677, 3 924, 4 999, 5 1000 TFLOP/s
     if (!v1 && ksize == 1 && bytes(MT, 4, 4, 1) <= budget) { TB = 1; SA = 4; SB = 4; }
@@ -681,13 +753,16 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
     while (bytes(MT, SA, SB, TB) > budget && MT > 1) MT >>= 1;
     if (bytes(MT, SA, SB, TB) > budget) { if (TB == 3) { TB = 1; } }
     if (bytes(MT, SA, SB, TB) > budget) return KS_EUNSUPPORTED;
+    if (ns3 && TB != 3) { ns3 = false; p.BNA = p.BN; p.idesc = make_idesc_bf16(128, p.BN, 0, 0); }   // stacking needs a kernel row per weight stage
     p.TB = TB; p.b_stage_bytes = (uint32_t)TB * p.b_tile_bytes;
   }
   p.MT = MT; p.SA = SA; p.SB = SB;
   p.n_super = (p.total_tiles + MT - 1) / MT;
-  p.n_acc = (2 * MT * p.BN <= 512) ? 2 : 1;
+  p.n_acc = (2 * MT * p.BNA <= 512) ? 2 : 1;
+  if (ns3 && !p.resident && !ns3_one_cta && 2 * MT * p.BNA > 256) p.n_acc = 1;
+  if (g_opt.nacc > 0) p.n_acc = g_opt.nacc;
   if (v1) p.n_acc = 1;
-  uint32_t cols = 32; while (cols < (uint32_t)(p.n_acc * MT * p.BN)) cols <<= 1;
+  uint32_t cols = 32; while (cols < (uint32_t)(p.n_acc * MT * p.BNA)) cols <<= 1;
   if (cols > 512) return KS_EUNSUPPORTED;
   p.tmem_cols = cols;
   const size_t smem = (size_t)SA * MT * p.a_tile_bytes + (p.resident ? w_bytes : (size_t)SB * p.b_stage_bytes) + fixed;
@@ -723,12 +798,13 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
   }
   // persistent grid: CTAs per SM limited by shared memory; all N tiles of a super-tile run concurrently
   int per_sm = (int)((227 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
+  if (per_sm > (int)(512 / cols)) per_sm = (int)(512 / cols);   // tcgen05.alloc of a further CTA would block until TMEM columns free up
   int gx = (kNumSMs * per_sm) / nt; if (gx < 1) gx = 1; if (gx > p.n_super) gx = p.n_super;
   dim3 grid((unsigned)gx, (unsigned)nt);
-  if (BK == 64 && ksize == 3) rc = launch_conv_tc2<64, 3>(p, grid, smem, st);
-  else if (BK == 64 && ksize == 1) rc = launch_conv_tc2<64, 1>(p, grid, smem, st);
-  else if (BK == 32 && ksize == 3) rc = launch_conv_tc2<32, 3>(p, grid, smem, st);
-  else rc = launch_conv_tc2<32, 1>(p, grid, smem, st);
+  if (BK == 64 && ksize == 3) rc = ns3 ? launch_conv_tc2<64, 3, true>(p, grid, smem, st) : launch_conv_tc2<64, 3, false>(p, grid, smem, st);
+  else if (BK == 64 && ksize == 1) rc = launch_conv_tc2<64, 1, false>(p, grid, smem, st);
+  else if (BK == 32 && ksize == 3) rc = ns3 ? launch_conv_tc2<32, 3, true>(p, grid, smem, st) : launch_conv_tc2<32, 3, false>(p, grid, smem, st);
+  else rc = launch_conv_tc2<32, 1, false>(p, grid, smem, st);
   return rc;
 }
 
@@ -746,6 +822,10 @@ extern "C" int ks_set_option(const char *name, int value) {
   else if (eq("tc_v1")) ks::g_opt.v1 = value;
   else if (eq("tc_no_resident")) ks::g_opt.no_resident = value;
   else if (eq("tc_tb")) ks::g_opt.tb = value;
+  else if (eq("tc_ns3_min_cin")) ks::g_opt.ns3_min_cin = value;   // > 0: stack column taps from this many input channels (default 96) and for N tiles up to 80
+  else if (eq("tc_ns3_mode")) ks::g_opt.ns3_mode = value;         // streamed + stacked: 1 = two CTAs per SM (256 TMEM columns), 2 = one CTA per SM
+  else if (eq("tc_nacc")) ks::g_opt.nacc = value;
+  else if (eq("tc_no_ns3")) ks::g_opt.no_ns3 = value;   // 1 = one UMMA per tap also for narrow N tiles (A/B comparisons)
   else if (eq("wgrad_mode")) ks::g_opt.wgrad_mode = value;   // 0 auto (tap stacking along N), 2 = halo kernel v2
   else if (eq("ew_cap")) ks::g_opt.ew_cap = value;       // perf experiments: CTAs per SM of the BatchNorm passes' grids (0 = default 8)
   else if (eq("att_simt")) ks::g_opt.att_simt = value;   // 1 = CUDA-core attention kernels also for bf16 (A/B comparisons)

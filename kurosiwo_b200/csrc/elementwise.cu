@@ -592,8 +592,10 @@ channel_sum_kernel(View x, int N, int H, int W, float *out, bool flat) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Adam (torch.optim.Adam semantics, L2 weight decay folded into the gradient)
+// Adam (torch.optim.Adam semantics, L2 weight decay folded into the gradient) and, with DECOUPLED, AdamW
+// (torch.optim.AdamW: p *= 1 - lr*wd before the Adam update; the gradient carries no decay term)
 // ------------------------------------------------------------------------------------------
+template <bool DECOUPLED>
 __global__ void __launch_bounds__(256)
 adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
             long long n, float lr, float b1, float b2, float eps, float wd, float gscale, const int *step_ptr) {
@@ -601,6 +603,7 @@ adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restric
   const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
   const float step_size = (float)((double)lr / bc1);
   const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  const float decay = 1.f - lr * wd;
   const long long n4 = n / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4 *>(p)[i], gg = reinterpret_cast<const float4 *>(g)[i];
@@ -608,7 +611,8 @@ adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restric
     float *P = &pp.x, *G = &gg.x, *M = &mm.x, *Vv = &vv.x;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float gk = G[k] * gscale + wd * P[k];
+      float gk = G[k] * gscale;
+      if (DECOUPLED) P[k] *= decay; else gk += wd * P[k];
       M[k] = b1 * M[k] + (1.f - b1) * gk;
       Vv[k] = b2 * Vv[k] + (1.f - b2) * gk * gk;
       P[k] -= step_size * (M[k] / (sqrtf(Vv[k]) * inv_bc2_sqrt + eps));
@@ -617,10 +621,12 @@ adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restric
   }
   if (blockIdx.x == 0) {
     for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
-      float gk = g[i] * gscale + wd * p[i];
+      float gk = g[i] * gscale;
+      float pi = p[i];
+      if (DECOUPLED) pi *= decay; else gk += wd * pi;
       m[i] = b1 * m[i] + (1.f - b1) * gk;
       v[i] = b2 * v[i] + (1.f - b2) * gk * gk;
-      p[i] -= step_size * (m[i] / (sqrtf(v[i]) * inv_bc2_sqrt + eps));
+      p[i] = pi - step_size * (m[i] / (sqrtf(v[i]) * inv_bc2_sqrt + eps));
     }
   }
 }
@@ -841,7 +847,18 @@ extern "C" int ks_adam_step(float *p, const float *g, float *m, float *v, int64_
   KS_CHECK_ARG(((uintptr_t)p % 16) == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)m % 16) == 0 && ((uintptr_t)v % 16) == 0);
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ew_grid(n / 4 + 1, 256);
-  adam_kernel<<<grid, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step_ptr);
+  adam_kernel<false><<<grid, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step_ptr);
   incr_kernel<<<1, 1, 0, st>>>(step_ptr);
+  KS_LAUNCH_RET();
+}
+
+extern "C" int ks_adamw_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, float grad_scale, int *step_ptr, void *stream) {
+  KS_CHECK_ARG(p && g && m && v && step_ptr && n > 0);
+  KS_CHECK_ARG(((uintptr_t)p % 16) == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)m % 16) == 0 && ((uintptr_t)v % 16) == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ks::ew_grid(n / 4 + 1, 256);
+  ks::adam_kernel<true><<<grid, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step_ptr);
+  ks::incr_kernel<<<1, 1, 0, st>>>(step_ptr);
   KS_LAUNCH_RET();
 }

@@ -331,6 +331,67 @@ confusion_kernel(const unsigned char *__restrict__ pred, const long long *__rest
 }
 }  // namespace ks
 
+namespace ks {
+// Grouped variant: the batch's per-sample keys route every sample's counts to up to two extra families of matrices (per
+// activation / AOI and per climate zone: change_detection_trainer.py:184-199, :445-472) next to the global one - ONE launch
+// instead of 5 torchmetrics updates per (family, key present in the batch).  grid = (chunks, samples): a block sees one sample.
+template <int K>
+__global__ void __launch_bounds__(256)
+confusion_grouped_kernel(const unsigned char *__restrict__ pred, const long long *__restrict__ labels, long long per_sample,
+                         int ignore_index, const int *__restrict__ key_a, int n_a, const int *__restrict__ key_b, int n_b,
+                         unsigned long long *mat, unsigned long long *mat_a, unsigned long long *mat_b) {
+  __shared__ unsigned int sm[K * K];
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x) sm[i] = 0u;
+  __syncthreads();
+  const long long base = (long long)blockIdx.y * per_sample;
+  unsigned int cnt[K * K];
+#pragma unroll
+  for (int i = 0; i < K * K; ++i) cnt[i] = 0u;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x) {
+    const long long t = labels[base + i];
+    const int p = pred[base + i];
+    if (t != ignore_index && t >= 0 && t < K && p < K) {
+      const int idx = (int)t * K + p;
+#pragma unroll
+      for (int q = 0; q < K * K; ++q) cnt[q] += (q == idx) ? 1u : 0u;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < K * K; ++q) {
+    unsigned int v = cnt[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sm[q], v);
+  }
+  __syncthreads();
+  const int ka = key_a ? key_a[blockIdx.y] : -1, kb = key_b ? key_b[blockIdx.y] : -1;
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x) {
+    const unsigned long long v = sm[i];
+    if (!v) continue;
+    if (mat) atomicAdd(mat + i, v);
+    if (mat_a && ka >= 0 && ka < n_a) atomicAdd(mat_a + (size_t)ka * K * K + i, v);
+    if (mat_b && kb >= 0 && kb < n_b) atomicAdd(mat_b + (size_t)kb * K * K + i, v);
+  }
+}
+}  // namespace ks
+
+extern "C" int ks_confusion_update_grouped(const uint8_t *pred, const int64_t *labels, int n_samples, int64_t per_sample,
+                                           int num_classes_with_ignore, int ignore_index, const int32_t *key_a, int n_a,
+                                           const int32_t *key_b, int n_b, int64_t *mat, int64_t *mat_a, int64_t *mat_b, void *stream) {
+  KS_CHECK_ARG(pred && labels && n_samples > 0 && per_sample > 0 && (mat || mat_a || mat_b));
+  KS_CHECK_ARG((!mat_a || (key_a && n_a > 0)) && (!mat_b || (key_b && n_b > 0)));
+  if (num_classes_with_ignore != 4) return KS_EUNSUPPORTED;
+  long long g = (per_sample + 256 * 16 - 1) / (256 * 16);
+  const long long cap = (ks::kNumSMs * 8 + n_samples - 1) / n_samples;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  dim3 grid((unsigned)g, (unsigned)n_samples);
+  ks::confusion_grouped_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(pred, (const long long *)labels, per_sample, ignore_index, key_a, n_a,
+                                                                            key_b, n_b, (unsigned long long *)mat, (unsigned long long *)mat_a,
+                                                                            (unsigned long long *)mat_b);
+  KS_LAUNCH_RET();
+}
+
 extern "C" int ks_confusion_update(const uint8_t *pred, const int64_t *labels, int64_t n, int num_classes_with_ignore, int ignore_index,
                                    int64_t *mat, void *stream) {
   KS_CHECK_ARG(pred && labels && mat && n > 0);

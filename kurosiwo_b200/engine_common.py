@@ -80,8 +80,8 @@ class TrainStepMixin:
         self.ignore_index = ignore_index
         self.dice_weight = float(dice_weight)     # 1: CE+Dice (utilities/bce_and_dice.py), 0: plain cross-entropy (the reference default)
         self.hp = dict(lr=lr, b1=betas[0], b2=betas[1], eps=eps, wd=weight_decay, momentum=momentum)
-        if optimizer not in ("adam", "sgd"):
-            raise NotImplementedError(f"fused optimizer '{optimizer}' (adam: change_detection_trainer.py:52-54, sgd: :61-66)")
+        if optimizer not in ("adam", "adamw", "sgd"):
+            raise NotImplementedError(f"fused optimizer '{optimizer}' (adam: change_detection_trainer.py:52-54, adamw: :55-60, sgd: :61-66)")
         self.optimizer = optimizer
         self.adam_m = torch.zeros_like(self.params.flat)
         self.adam_v = torch.zeros_like(self.params.flat)
@@ -116,8 +116,9 @@ class TrainStepMixin:
         if self.optimizer == "sgd":
             self.ops.sgd_step(self.params.flat, self.params.grad, self.adam_m, hp["lr"], hp["momentum"], hp["wd"], 1.0 / self.world)
             return
-        self.ops.adam_step(self.params.flat, self.params.grad, self.adam_m, self.adam_v, hp["lr"], hp["b1"], hp["b2"], hp["eps"],
-                           hp["wd"], 1.0 / self.world, self.adam_step)
+        step = self.ops.adamw_step if self.optimizer == "adamw" else self.ops.adam_step
+        step(self.params.flat, self.params.grad, self.adam_m, self.adam_v, hp["lr"], hp["b1"], hp["b2"], hp["eps"],
+             hp["wd"], 1.0 / self.world, self.adam_step)
 
     def train_step(self, *args) -> torch.Tensor:
         """One optimizer step on (inputs..., mask); returns the device tensor [total, dice, ce] (no host sync)."""
@@ -143,12 +144,13 @@ class TrainStepMixin:
         torch.cuda.synchronize()
         if self.world == 1 and optimizer_in_graph:
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            # thread_local everywhere: a DataLoader pin-memory thread (or NCCL's watchdog) may issue CUDA calls during the capture
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.train_step(*args)
             self.replay = self.graph.replay
         elif self.world == 1:
             ga = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ga):
+            with torch.cuda.graph(ga, capture_error_mode="thread_local"):
                 self._fwd_loss_bwd(*args)
             self.graph = ga
 

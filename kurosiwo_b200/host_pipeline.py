@@ -19,7 +19,7 @@ class HostPipelineMixin:
     def _pipeline_state(self):
         st = self.__dict__.get("_pl")
         if st is None:
-            st = self.__dict__["_pl"] = dict(copy_stream=None, staged=[], static=None, replay=None, engine=None, eager={})
+            st = self.__dict__["_pl"] = dict(copy_stream=None, staged=[], static=None, replay=None, engine=None)
         return st
 
     def _stage(self, batch):
@@ -56,9 +56,10 @@ class HostPipelineMixin:
         for t in tensors:
             t.record_stream(main)
         eng = self._engine(tensors[0])
-        n_eager = st["eager"].get(id(eng), 0)
+        # the warm-up count lives ON the engine object: engines are rebuilt per batch geometry and freed, and CPython reuses ids
+        n_eager = getattr(eng, "_eager_steps", 0)
         if not self.configs.get("cuda_graph", True) or n_eager < EAGER_STEPS:
-            st["eager"][id(eng)] = n_eager + 1
+            eng._eager_steps = n_eager + 1
             return eng.train_step(*tensors), tensors[-1]
         if st["engine"] is not eng:
             # first capture, or another batch geometry took over (e.g. after a ragged last batch the model builds a new engine for the

@@ -91,10 +91,10 @@ EXPORTED_SYMBOLS = [
     "ks_version", "ks_error_string", "ks_set_option", "ks_permute_cast", "ks_permute_cast_batched", "ks_conv2d", "ks_conv2d_wgrad", "ks_stem_conv3x3", "ks_stem_wgrad3x3",
     "ks_bn_stats", "ks_bn_finalize", "ks_bn_act", "ks_bn_bwd_reduce", "ks_bn_bwd_apply", "ks_maxpool2x2_bwd",
     "ks_channel_sum", "ks_ecam_pool", "ks_ecam_gates", "ks_ecam_final", "ks_ecam_bwd_reduce", "ks_ecam_gates_bwd",
-    "ks_ecam_bwd_apply", "ks_ce_dice_workspace_bytes", "ks_ce_dice_fwd_bwd", "ks_ce_dice_fwd_bwd_ex", "ks_adam_step", "ks_sgd_step",
+    "ks_ecam_bwd_apply", "ks_ce_dice_workspace_bytes", "ks_ce_dice_fwd_bwd", "ks_ce_dice_fwd_bwd_ex", "ks_adam_step", "ks_adamw_step", "ks_sgd_step",
     "ks_softmax_head_fwd", "ks_softmax_head_bwd", "ks_dropout_mask", "ks_channel_scale", "ks_absdiff_fwd", "ks_absdiff_bwd",
     "ks_layernorm_fwd", "ks_layernorm_bwd", "ks_patchify_ln", "ks_patchify_ln_bwd", "ks_vit_assemble", "ks_vit_assemble_bwd",
-    "ks_confusion_update", "ks_attention_fwd", "ks_attention_bwd", "ks_conv2d_strided", "ks_conv2d_strided_dgrad", "ks_conv2d_strided_wgrad", "ks_im2col", "ks_col2im",
+    "ks_confusion_update", "ks_confusion_update_grouped", "ks_attention_fwd", "ks_attention_bwd", "ks_conv2d_strided", "ks_conv2d_strided_dgrad", "ks_conv2d_strided_wgrad", "ks_im2col", "ks_col2im",
     "ks_xattention_fwd", "ks_xattention_bwd", "ks_dwconv3x3_fwd", "ks_dwconv3x3_bwd", "ks_bilinear_nhwc_fwd", "ks_bilinear_nhwc_bwd",
     "ks_relu_fwd", "ks_relu_bwd", "ks_sigmoid_head_fwd", "ks_sigmoid_head_bwd", "ks_dropout_apply", "ks_branch_add", "ks_branch_scale", "ks_gelu_fwd", "ks_gelu_bwd", "ks_bilinear_up_fwd", "ks_bilinear_up_bwd", "ks_adaptive_avgpool_fwd", "ks_adaptive_avgpool_bwd",
 ]
@@ -507,11 +507,25 @@ class CudaOps:
                                           self._stream())
         self._check(rc, "ks_confusion_update")
 
+    def confusion_update_grouped(self, pred, labels, K, ignore_index, mat, key_a=None, mat_a=None, key_b=None, mat_b=None):
+        """pred uint8 [B,H,W], labels int64 [B,H,W]; key_*: int32 [B] device tensors; mat_*: int64 [n_keys, K, K]."""
+        B = labels.shape[0]
+        rc = self.lib.ks_confusion_update_grouped(_p(pred), _p(labels), C.c_int(B), C.c_int64(labels.numel() // B), C.c_int(K),
+                                                  C.c_int(ignore_index), _p(key_a), C.c_int(0 if mat_a is None else mat_a.shape[0]),
+                                                  _p(key_b), C.c_int(0 if mat_b is None else mat_b.shape[0]), _p(mat), _p(mat_a), _p(mat_b),
+                                                  self._stream())
+        self._check(rc, "ks_confusion_update_grouped")
+
     # -- optimizer ---------------------------------------------------------------------------
     def adam_step(self, p, g, m, v, lr, b1, b2, eps, wd, grad_scale, step):
         rc = self.lib.ks_adam_step(_p(p), _p(g), _p(m), _p(v), C.c_int64(p.numel()), C.c_float(lr), C.c_float(b1), C.c_float(b2),
                                    C.c_float(eps), C.c_float(wd), C.c_float(grad_scale), _p(step), self._stream())
         self._check(rc, "ks_adam_step")
+
+    def adamw_step(self, p, g, m, v, lr, b1, b2, eps, wd, grad_scale, step):
+        rc = self.lib.ks_adamw_step(_p(p), _p(g), _p(m), _p(v), C.c_int64(p.numel()), C.c_float(lr), C.c_float(b1), C.c_float(b2),
+                                    C.c_float(eps), C.c_float(wd), C.c_float(grad_scale), _p(step), self._stream())
+        self._check(rc, "ks_adamw_step")
 
     def sgd_step(self, p, g, buf, lr, momentum, wd, grad_scale):
         rc = self.lib.ks_sgd_step(_p(p), _p(g), _p(buf), C.c_int64(p.numel()), C.c_float(lr), C.c_float(momentum), C.c_float(wd),

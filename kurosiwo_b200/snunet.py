@@ -60,7 +60,8 @@ class _SNUNetFunction(torch.autograd.Function):
     def forward(ctx, model, xA, xB, *params):
         eng = model._engine_for(xA)
         ctx.engine = eng
-        return eng.forward(xA, xB, training=model.training).detach()
+        # a private copy: the engine's logits buffer is overwritten by the next forward
+        return eng.forward(xA, xB, training=model.training).detach().clone()
 
     @staticmethod
     def backward(ctx, dlogits):
@@ -147,7 +148,7 @@ class SNUNet_ECAM(nn.Module):
             eng.params.ensure(xA.device)
             return _SNUNetFunction.apply(self, xA, xB, *[p for _, p in self.named_parameters()])
         eng = self._engine_for(xA)
-        return eng.forward(xA, xB, training=self.training).detach()
+        return eng.forward(xA, xB, training=self.training).detach().clone()   # the fused trainer reads engine.logits directly
 
     def __getstate__(self):  # torch.save(model) must not pickle device plans (segmentation_trainer.py:255 style)
         d = dict(self.__dict__)

@@ -64,7 +64,11 @@ CONV = {
     "L0 dgrad 32->224": (224, [32], [64, 96, 64], 3, False),
     "L0 dgrad 32->32": (224, [32], [32], 3, False),
     "L1 fwd 64->64": (112, [64], [64], 3, True),
+    "L1 dgrad 64->64": (112, [64], [64], 3, False),
+    "L1 fwd 32->64": (112, [32], [64], 3, True),
     "L1 fwd 384->64 (256+128)": (112, [256, 128], [64], 3, True),
+    "L1 fwd 256->64 (128+128)": (112, [128, 128], [64], 3, True),
+    "L2 fwd 256->128 as 2x64": (56, [256], [128], 3, True),
     "L1 dgrad 64->384": (112, [64], [256, 128], 3, False),
     "L2 fwd 640->128": (56, [384, 256], [128], 3, True),
     "L2 fwd 128->128": (56, [128], [128], 3, True),
@@ -87,11 +91,19 @@ VARIANTS = {
     "nores_mt2": {"tc_no_resident": 1, "tc_mt": 2},
     "nores_mt4": {"tc_no_resident": 1, "tc_mt": 4},
     "res_mt2": {"tc_mt": 2},
+    "no_ns3": {"tc_no_ns3": 1},
+    "ns3_all": {"tc_ns3_min_cin": 1},
+    "ns3_two": {"tc_ns3_min_cin": 1, "tc_ns3_mode": 1},
+    "ns3_one": {"tc_ns3_min_cin": 1, "tc_ns3_mode": 2},
+    "ns3_one_mt2": {"tc_ns3_min_cin": 1, "tc_ns3_mode": 2, "tc_mt": 2},
+    "ns3_nores_one": {"tc_ns3_min_cin": 1, "tc_ns3_mode": 2, "tc_no_resident": 1},
+    "ns3_nores_two": {"tc_ns3_min_cin": 1, "tc_ns3_mode": 1, "tc_no_resident": 1},
 }
 import os
 SEL = [x.strip() for x in os.environ.get("KS_LAYERS", "").split(",") if x.strip()]
 VSEL = [x.strip() for x in os.environ.get("KS_VARIANTS", "").split(",") if x.strip()]
 REPS = int(os.environ.get("KS_REPS", "5"))
+ops.set_option("tc_debug", int(os.environ.get("KS_DEBUG", "0")))   # ablations: 1 no stores, 2 no TMEM loads, 4 no MMAs, 8 no epilogue, 16 no TMA
 if SEL:
     CONV = {k: v for k, v in CONV.items() if k in SEL}
     WGRAD = {k: v for k, v in WGRAD.items() if k in SEL}
@@ -101,7 +113,7 @@ out = {"conv": {}, "wgrad": {}}
 for name, (H, cins, couts, ks, stats) in CONV.items():
     row = {}
     for vn, opts in VARIANTS.items():
-        for o in ("tc_v1", "tc_mt", "tc_no_resident"):
+        for o in ("tc_v1", "tc_mt", "tc_no_resident", "tc_no_ns3", "tc_ns3_min_cin", "tc_ns3_mode"):
             ops.set_option(o, opts.get(o, 0))
         try:
             fn, fl = conv_case(H, cins, couts, ks, stats and vn != "v1")
@@ -112,7 +124,7 @@ for name, (H, cins, couts, ks, stats) in CONV.items():
         torch.cuda.empty_cache()
     out["conv"][name] = row
     print(f"{name:28s}", "  ".join(f"{k}={v}" for k, v in row.items()), flush=True)
-for o in ("tc_v1", "tc_mt", "tc_no_resident"):
+for o in ("tc_v1", "tc_mt", "tc_no_resident", "tc_no_ns3", "tc_ns3_min_cin", "tc_ns3_mode"):
     ops.set_option(o, 0)
 for name, (H, cins, couts) in WGRAD.items():
     fn, fl = wgrad_case(H, cins, couts)

@@ -306,6 +306,10 @@ class ShadowOps:
         p.addcdiv_(m, v.sqrt() / (bc2 ** 0.5) + eps, value=-lr / bc1)
         step += 1
 
+    def adamw_step(self, p, g, m, v, lr, b1, b2, eps, wd, grad_scale, step):
+        p.mul_(1 - lr * wd)                                   # torch.optim.AdamW: decoupled decay first
+        self.adam_step(p, g, m, v, lr, b1, b2, eps, 0.0, grad_scale, step)
+
     # -- Siamese U-Net passes ------------------------------------------------------------------
     def softmax_head_fwd(self, z, K, log_mode, out):
         zz = _t(z).float()[..., :K].permute(0, 3, 1, 2)
@@ -459,6 +463,16 @@ class ShadowOps:
         mat.view(-1).add_(torch.bincount(t[keep] * K + p[keep], minlength=K * K))
 
     # -- ChangeFormer passes ---------------------------------------------------------------------
+    def confusion_update_grouped(self, pred, labels, K, ignore_index, mat, key_a=None, mat_a=None, key_b=None, mat_b=None):
+        for s in range(labels.shape[0]):
+            one = torch.zeros(K, K, dtype=torch.int64)
+            self.confusion_update(pred[s].reshape(-1), labels[s].reshape(-1), K, ignore_index, one)
+            if mat is not None:
+                mat += one
+            for key, m in ((key_a, mat_a), (key_b, mat_b)):
+                if m is not None and 0 <= int(key[s]) < m.shape[0]:
+                    m[int(key[s])] += one
+
     @staticmethod
     def _w_oihw(weight, k, cout, cin):
         return weight.float().view(k * k, cout, cin).permute(1, 2, 0).reshape(cout, cin, k, k)

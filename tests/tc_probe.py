@@ -14,7 +14,8 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 sys.path.insert(0, str(Path(__file__).resolve().parent))
 from kurosiwo_b200.lib import IMPL_SIMT, IMPL_TC, CudaOps, KsError, View  # noqa: E402
-from gpu_util import rand_view, rel_l2  # noqa: E402
+from gpu_util import mirror, rand_view, rel_l2  # noqa: E402
+from shadow_ops import ShadowOps  # noqa: E402
 
 dev = "cuda:0"
 bf = torch.bfloat16
@@ -46,7 +47,16 @@ def conv_case(ops, name, N, H, W, ks, src_specs, dst_specs, bias, gen):
     w = (torch.randn(ks * ks * cout * cin, generator=gen) * (2.0 / (cin * ks * ks)) ** 0.5).to(bf).to(dev)
     b = (torch.randn(cout, generator=gen) * 0.1).to(dev) if bias else None
     init = [f.base.clone() for f in dst_fulls]
-    # reference: CUDA-core kernel
+    # reference 1: the torch-CPU shadow of the op (fp64 accumulate over the same bf16 inputs), independent of every CUDA kernel
+    sh = ShadowOps()
+    m_srcs = [mirror(v) for v in srcs]
+    m_fulls = [mirror(f) for f in dst_fulls]
+    m_dsts = []
+    for (C, ctot, c0, kind, acc), mf in zip(dst_specs, m_fulls):
+        m_dsts += [mf.phase(k // 2, k % 2) for k in range(4)] if kind == "phases" else [mf.ch(c0, C)]
+    sh.conv2d(N, H, W, ks, m_srcs, w.cpu(), b.cpu() if b is not None else None, m_dsts, accs, None)
+    shadow = [mf.base.clone() for mf in m_fulls]
+    # reference 2: CUDA-core kernel
     ops.conv2d(N, H, W, ks, srcs, w, b, dsts, accs, None, IMPL_SIMT)
     torch.cuda.synchronize()
     ref = [f.base.clone() for f in dst_fulls]
@@ -62,23 +72,32 @@ def conv_case(ops, name, N, H, W, ks, src_specs, dst_specs, bias, gen):
         "v2_nores_mt1": {"tc_no_resident": 1, "tc_mt": 1},
         "v2_nores_mt2": {"tc_no_resident": 1, "tc_mt": 2},
         "v2_nores_mt4": {"tc_no_resident": 1, "tc_mt": 4},
+        "v2_no_ns3": {"tc_no_ns3": 1},
+        "v2_no_ns3_nores": {"tc_no_ns3": 1, "tc_no_resident": 1},
+        # column taps stacked along N for every 3x3 case with N tile <= 80 (the library default applies it from Cin >= 96)
+        "v2_ns3": {"tc_ns3_min_cin": 1},
+        "v2_ns3_nores_one_cta": {"tc_ns3_min_cin": 1, "tc_no_resident": 1, "tc_ns3_mode": 2},
+        "v2_ns3_nores_two_cta": {"tc_ns3_min_cin": 1, "tc_no_resident": 1, "tc_ns3_mode": 1},
+        "v2_ns3_nores_mt2": {"tc_ns3_min_cin": 1, "tc_no_resident": 1, "tc_ns3_mode": 2, "tc_mt": 2},
     }
+    OPTS = ("tc_v1", "tc_mt", "tc_no_resident", "tc_no_ns3", "tc_ns3_min_cin", "tc_ns3_mode")
     for key, opts in variants.items():
         for f, i0 in zip(dst_fulls, init):
             f.base.copy_(i0)
-        for o in ("tc_v1", "tc_mt", "tc_no_resident"):
+        for o in OPTS:
             ops.set_option(o, opts.get(o, 0))
         try:
             st = torch.zeros(2 * cout, dtype=torch.float64, device=dev) if want_stats else None
             ops.conv2d(N, H, W, ks, srcs, w, b, dsts, accs, st, IMPL_TC)
             torch.cuda.synchronize()
             err = max(rel_l2(f.base.float(), r.float()) for f, r in zip(dst_fulls, ref))
+            err = max(err, max(rel_l2(f.base.float(), r.float()) for f, r in zip(dst_fulls, shadow)))
             if want_stats:
                 err = max(err, rel_l2(st, ref_stats))
             res[key] = err
         except KsError as e:
             res[key] = f"error: {e}"
-    for o in ("tc_v1", "tc_mt", "tc_no_resident"):
+    for o in OPTS:
         ops.set_option(o, 0)
     return res
 
@@ -98,13 +117,15 @@ def wgrad_case(ops, name, N, H, W, ks, x_specs, dy_specs, gen):
     got = torch.zeros_like(ref)
     ops.conv2d_wgrad(N, H, W, ks, xs, dys, ref, False, IMPL_SIMT)
     torch.cuda.synchronize()
-    res = {}
+    shadow = torch.zeros(ks * ks * cout * cin)
+    ShadowOps().conv2d_wgrad(N, H, W, ks, [mirror(v) for v in xs], [mirror(v) for v in dys], shadow, False)
+    res = {"simt_vs_shadow": rel_l2(ref, shadow)}
     for mode, tag in ((0, ""), (2, "_halo")):
         ops.set_option("wgrad_mode", mode)
         try:
             ops.conv2d_wgrad(N, H, W, ks, xs, dys, got, False, IMPL_TC)
             torch.cuda.synchronize()
-            res["assign" + tag] = rel_l2(got, ref)
+            res["assign" + tag] = max(rel_l2(got, ref), rel_l2(got, shadow))
             ops.conv2d_wgrad(N, H, W, ks, xs, dys, got, True, IMPL_TC)  # accumulate: 2x
             torch.cuda.synchronize()
             res["accumulate" + tag] = rel_l2(got, 2 * ref)
@@ -130,6 +151,14 @@ def main():
         "G_k3_dgrad_multidst": (2, 16, 28, 3, [(32, 32, 0, P)], [(64, 192, 0, P, True), (32, 192, 64, P, False), (64, 64, 0, P, False)], False),
         "H_k3_odd_hw": (1, 20, 20, 3, [(64, 64, 0, P)], [(64, 64, 0, P, False)], True),
         "I_k3_big": (4, 56, 56, 3, [(128, 256, 0, P), (128, 128, 0, P)], [(128, 128, 0, P, False)], True),
+        # column-tap-stacked N (narrow N tiles): resident (N = 32 / 16) and streamed (N = 64) weights, accumulate, ragged edges
+        "J_k3_c64_n64": (2, 28, 28, 3, [(64, 64, 0, P)], [(64, 64, 0, P, False)], True),
+        "K_k3_c320_n64": (2, 28, 28, 3, [(256, 256, 0, P), (64, 128, 64, P)], [(64, 128, 0, P, False)], True),
+        "L_k3_c32_n32_acc": (3, 16, 28, 3, [(32, 32, 0, P)], [(32, 96, 64, P, True)], False),
+        "M_k3_c224_n32_bk32": (2, 24, 42, 3, [(160, 160, 0, P), (64, 64, 0, P)], [(32, 32, 0, P, False)], True),
+        "N_k3_c64_n16": (2, 16, 14, 3, [(64, 64, 0, P)], [(16, 16, 0, P, False)], True),
+        "O_k3_c64_n64_ragged": (5, 21, 30, 3, [(64, 64, 0, P)], [(64, 64, 0, P, False)], True),
+        "P_k3_c128_n80": (2, 14, 14, 3, [(128, 128, 0, P)], [(80, 80, 0, P, False)], False),
     }
     for name, (N, H, W, ks, ss, ds, bias) in conv_cases.items():
         report["conv"][name] = conv_case(ops, name, N, H, W, ks, ss, ds, bias, gen)

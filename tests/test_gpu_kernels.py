@@ -345,6 +345,26 @@ def test_adam(ops, sh):
     assert max_rel(dp, ref.data) < 1e-6
 
 
+def test_adamw(ops, sh):
+    """Fused AdamW (change_detection_trainer.py:55-60: betas + decoupled weight decay) vs torch.optim.AdamW and the shadow."""
+    g = _gen(8)
+    n = 10007
+    p, gr = torch.randn(n, generator=g), torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref], lr=3e-3, betas=(0.8, 0.95), weight_decay=0.05)
+    dp, dg = p.clone().to(DEV), gr.clone().to(DEV)
+    dm, dv = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    sp, sm, sv, sstep = p.clone(), torch.zeros(n), torch.zeros(n), torch.zeros(1, dtype=torch.int32)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for it in range(4):
+        ref.grad = gr.clone() * (it + 1)
+        opt.step()
+        ops.adamw_step(dp, dg * (it + 1), dm, dv, 3e-3, 0.8, 0.95, 1e-8, 0.05, 1.0, step)
+        sh.adamw_step(sp, gr * (it + 1), sm, sv, 3e-3, 0.8, 0.95, 1e-8, 0.05, 1.0, sstep)
+    assert int(step.item()) == 4
+    assert max_rel(dp, ref.data) < 1e-6 and max_rel(sp, ref.data) < 1e-6
+
+
 def test_confusion_update(ops, sh):
     """Bit-exact integer work: the fused confusion-matrix kernel against torch.bincount, incl. accumulation over two calls."""
     g = _gen(9)

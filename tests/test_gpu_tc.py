@@ -22,10 +22,13 @@ def report():
     return json.loads(out.read_text())
 
 
-@pytest.mark.parametrize("variant", ["v2_auto", "v1_mt1", "v2_res_mt2", "v2_nores_mt1", "v2_nores_mt2", "v2_nores_mt4"])
+@pytest.mark.parametrize("variant", ["v2_auto", "v1_mt1", "v2_res_mt2", "v2_nores_mt1", "v2_nores_mt2", "v2_nores_mt4", "v2_no_ns3", "v2_no_ns3_nores",
+                                     "v2_ns3", "v2_ns3_nores_one_cta", "v2_ns3_nores_two_cta", "v2_ns3_nores_mt2"])
 def test_conv_tc(report, variant):
-    """v2_auto is what the library picks (persistent CTAs, resident weights when they fit, fused BN statistics);
-    the other variants pin the streaming / multi-window / non-persistent code paths."""
+    """v2_auto is what the library picks (persistent CTAs, resident weights when they fit, fused BN statistics, column taps
+    stacked along N for narrow N tiles); the other variants pin the streaming / multi-window / non-persistent / one-UMMA-per-tap
+    code paths.  Every variant is compared BOTH with the CUDA-core kernel and with the torch-CPU shadow of the op
+    (tests/shadow_ops.py), so the tcgen05 path is not only checked against this library's own kernels."""
     bad = {k: v[variant] for k, v in report["conv"].items() if not (isinstance(v[variant], float) and v[variant] < TOL)}
     assert not bad, bad
 
