@@ -38,7 +38,7 @@ WORKLOADS = {
                                     "inputs pre_event_1,post_event (BASELINE.json configs[0] shape)"),
     "changeformer": dict(metric="SAR patches/sec (224x224x6ch, bs=32) ChangeFormerV6 train step", batch=32, gflop=636.0, task="cd",
                          method="changeformer", lr=6e-4,
-                         desc="ChangeFormerV6 (embed 256, 41.0M params; stochastic layers p=0) train step: fwd + CE+Dice(+argmax) on the last "
+                         desc="ChangeFormerV6 (embed 256, 41.0M params; stochastic layers ON at the model defaults: Dropout / attention dropout / DropPath 0.1) train step: fwd + CE+Dice(+argmax) on the last "
                               "sigmoid output + bwd + allreduce + SGD(momentum 0.99); inputs pre_event_1,post_event (BASELINE.json configs[2] shape)"),
     "floodvit": dict(metric="SAR patches/sec (224x224x6ch, bs=64) FloodViT-B train step", batch=64, gflop=106.1, task="segmentation",
                      method="finetune", lr=1e-4,
@@ -162,6 +162,159 @@ def cpu_baseline_leg(seconds_budget: float = 25.0):
     med = times[len(times) // 2]
     return {"value": bs / med, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"oracle port of the reference SNUNet train step, fp32, bs={bs} (of 64), 1 warm-up + {len(times)} timed steps"}
+
+
+def library_snunet(base=32):
+    """Stock-torch SNUNet-ECAM (nn.Conv2d / BatchNorm2d / ConvTranspose2d -> cuDNN / cuBLAS) with the reference's wiring
+    (models/snunet.py:20-29, :41-46, :49-62, :118-153).  Used ONLY as the library comparator of SURVEY.md §8(d): the same step on the
+    same B200 through bf16 autocast + channels_last - the bar the hand-written kernels have to beat.  Never on the product path."""
+    import torch
+    import torch.nn as nn
+
+    class Block(nn.Module):
+        def __init__(self, cin, mid, cout):
+            super().__init__()
+            self.conv1, self.bn1 = nn.Conv2d(cin, mid, 3, padding=1), nn.BatchNorm2d(mid)
+            self.conv2, self.bn2 = nn.Conv2d(mid, cout, 3, padding=1), nn.BatchNorm2d(cout)
+
+        def forward(self, x):
+            y1 = self.conv1(x)
+            h = torch.relu(self.bn1(y1))
+            return torch.relu(self.bn2(self.conv2(h)) + y1)
+
+    class CA(nn.Module):
+        def __init__(self, c, ratio):
+            super().__init__()
+            self.fc1, self.fc2 = nn.Conv2d(c, c // ratio, 1, bias=False), nn.Conv2d(c // ratio, c, 1, bias=False)
+
+        def forward(self, x):
+            f = lambda t: self.fc2(torch.relu(self.fc1(t)))
+            return torch.sigmoid(f(torch.nn.functional.adaptive_avg_pool2d(x, 1)) + f(torch.nn.functional.adaptive_max_pool2d(x, 1)))
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            f = [base, base * 2, base * 4, base * 8, base * 16]
+            self.enc = nn.ModuleList([Block(2 if l == 0 else f[l - 1], f[l], f[l]) for l in range(5)])
+            self.dec = nn.ModuleDict({f"{l}_{j}": Block(f[l] * (j + 1) + f[l + 1], f[l], f[l]) for j in range(1, 5) for l in range(5 - j)})
+            self.up = nn.ModuleDict({f"{l}_{j}": nn.ConvTranspose2d(f[l + 1], f[l + 1], 2, stride=2) for j in range(1, 5) for l in range(5 - j)})
+            self.ca, self.ca1 = CA(f[0] * 4, 16), CA(f[0], 4)
+            self.final = nn.Conv2d(f[0] * 4, 3, 1)
+            self.pool = nn.MaxPool2d(2, 2)
+
+        def forward(self, xA, xB):
+            X = {}
+            for br, x in (("A", xA), ("B", xB)):
+                for l in range(5):
+                    if l == 4 and br == "A":
+                        continue
+                    X[(l, br)] = self.enc[l](x if l == 0 else self.pool(X[(l - 1, br)]))
+            for (l, j) in [(0, 1), (1, 1), (0, 2), (2, 1), (1, 2), (0, 3), (3, 1), (2, 2), (1, 3), (0, 4)]:
+                below = X[(l + 1, "B")] if j == 1 else X[(l + 1, j - 1)]
+                cat = [X[(l, "A")], X[(l, "B")]] + [X[(l, k)] for k in range(1, j)] + [self.up[f"{l}_{j}"](below)]
+                X[(l, j)] = self.dec[f"{l}_{j}"](torch.cat(cat, 1))
+            outs = [X[(0, j)] for j in range(1, 5)]
+            out = torch.cat(outs, 1)
+            intra = torch.sum(torch.stack(outs), dim=0)
+            out = self.ca(out) * (out + self.ca1(intra).repeat(1, 4, 1, 1))
+            return self.final(out)
+
+    return Net()
+
+
+def library_baseline_leg(dev, bs, steps=6, warmup=3):
+    """patches/s of the SAME training step (fwd + CE+Dice + bwd + Adam, same batch) on stock torch: cuDNN/cuBLAS under
+    torch.autocast(bfloat16), channels_last, fused Adam; eager and - when capture succeeds - as one CUDA graph (the better is reported)."""
+    import torch
+    import torch.nn.functional as F
+    from kurosiwo_b200 import synthetic
+    torch.manual_seed(999)
+    net = library_snunet().to(dev).to(memory_format=torch.channels_last).train()
+    b = synthetic.make_batch(999, bs, H, W, pin=False)
+    xA = b[6].to(dev).contiguous(memory_format=torch.channels_last)
+    xB = b[2].to(dev).contiguous(memory_format=torch.channels_last)
+    mask = b[3].to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, fused=True, capturable=True)
+
+    def loss_fn(logits):
+        logits = logits.float()
+        valid = mask != 3
+        t = torch.zeros_like(logits).scatter_(1, (mask * valid).unsqueeze(1), 1.0) + 1e-6
+        pr = F.softmax(logits, dim=1)
+        dice = torch.mean(1.0 - 2.0 * torch.sum(pr * t, (1, 2, 3)) / (torch.sum(pr + t, (1, 2, 3)) + 1e-6))
+        return dice + F.cross_entropy(logits, mask, ignore_index=3)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = net(xA, xB)
+        loss = loss_fn(out)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def timeit(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    res = {"unit": UNIT, "impl": f"torch {torch.__version__} eager nn.Module (cuDNN {torch.backends.cudnn.version()}), autocast bf16, channels_last, "
+                                 "fused Adam; same batch and step definition", "per_gpu_batch": bs}
+    torch.backends.cudnn.benchmark = True
+    ms_eager = timeit(step)
+    res["eager_ms_per_step"] = ms_eager
+    ms_best, mode = ms_eager, "eager"
+    try:
+        g = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=False)
+        s_ = torch.cuda.Stream()
+        s_.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s_):
+            step()
+        torch.cuda.current_stream().wait_stream(s_)
+        torch.cuda.synchronize()
+
+        def gstep():
+            opt.zero_grad(set_to_none=False)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = net(xA, xB)
+            loss = loss_fn(out)
+            loss.backward()
+            opt.step()
+        with torch.cuda.graph(g):
+            gstep()
+        ms_graph = timeit(g.replay)
+        res["graph_ms_per_step"] = ms_graph
+        if ms_graph < ms_best:
+            ms_best, mode = ms_graph, "cuda_graph"
+    except Exception as e:      # noqa: BLE001 - the comparator is best effort; eager stands
+        res["graph_error"] = str(e)[:120]
+    res.update(value=bs / (ms_best * 1e-3), ms_per_step=ms_best, mode=mode, peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)
+    del net, opt
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_library(args):
+    """`--impl torch-gpu`: the library comparator alone, as its own JSON line (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    torch.cuda.set_device(0)
+    wl = WORKLOADS["snunet"]
+    res = library_baseline_leg("cuda:0", args.batch or wl["batch"], steps=args.steps, warmup=max(args.warmup, 3))
+    print(json.dumps({"impl": "torch-gpu", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                      "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": wl["desc"], "per_gpu_batch": res["per_gpu_batch"], "library": res["impl"], "mode": res["mode"]},
+                      "library_baseline": res}))
 
 
 def conv_roofline(eng, dev_inputs, pk, pk_kind):
@@ -334,11 +487,19 @@ def run_ours(args):
     e2e_value = world * bs / (t.item() / args.steps * 1e-3)
     # ---- roofline + CPU baseline (rank 0, N==1 only) --------------------------------------------
     pk, pk_kind = peaks()
-    roof, layers, cpu = None, None, None
+    roof, layers, cpu, lib = None, None, None, None
     if rank == 0:
         roof, layers = conv_roofline(eng, dev_inputs, pk, pk_kind)
         if world == 1 and not args.no_cpu_baseline and args.workload == "snunet":
             cpu = cpu_baseline_leg()
+        if world == 1 and not args.no_library_baseline and args.workload == "snunet" and args.precision == "bf16":
+            try:
+                del step
+                eng.graph = None
+                torch.cuda.empty_cache()
+                lib = library_baseline_leg(dev, bs)
+            except Exception as e:      # noqa: BLE001
+                lib = {"unavailable": str(e)[:200]}
         out_dir = ROOT / "gpurun_out"
         try:
             out_dir.mkdir(exist_ok=True)
@@ -363,7 +524,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
         "gpu_launches": calls_per_step * args.steps,
         "gpu_launches_note": f"{calls_per_step} C-ABI calls per step (each >=1 kernel of libkurosiwo_b200.so)",
-        "roofline": roof, "cpu_baseline": cpu,
+        "roofline": roof, "cpu_baseline": cpu, "library_baseline": lib,
     }
     print(json.dumps(line))
 
@@ -373,7 +534,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"],
+                    help="reference = the CPU arm; torch-gpu = the stock-torch (cuDNN/cuBLAS) library comparator on the same GPU")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (0 = the workload's BASELINE.json batch)")
     ap.add_argument("--workload", default="snunet", choices=sorted(WORKLOADS), help="snunet = the headline (BASELINE.json configs[1])")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
@@ -381,9 +543,13 @@ def main():
     ap.add_argument("--tc-v1", type=int, default=0, help="1 = non-persistent v1 conv kernel (A/B comparisons)")
     ap.add_argument("--tc-mt", type=int, default=0, help="output windows per CTA of the tcgen05 conv (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.impl == "torch-gpu":
+        run_library(args)
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:

@@ -1,5 +1,5 @@
-// Fused softmax -> CE(weight, ignore_index) + Dice loss: forward, gradient and argmax
-// in ONE cooperative kernel (two phases separated by a grid barrier).
+// Fused softmax -> CE(weight, ignore_index) + Dice loss: forward, gradient and argmax in two streaming passes
+// (reduce | gradient) chained by a programmatic dependent launch.
 //
 // Reference semantics (parity target):
 //   utilities/bce_and_dice.py:18-24   loss = DiceLoss(preds, lbl) + CrossEntropyLoss(preds, lbl)
@@ -17,22 +17,6 @@ struct LossWs {
   // doubles: [N][2] (I_n, S_n), then [2] (ce_num, ce_den); then counters
   double *acc; double *ce; unsigned int *counter;
 };
-
-__device__ __forceinline__ void grid_barrier_arrive_wait(unsigned int *counter, unsigned int total, bool wait) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    if (wait) {
-      unsigned int v;
-      do {
-        asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-        if (v < total) __nanosleep(64);
-      } while (v < total);
-    }
-  }
-  __syncthreads();
-}
 
 // exp / log on the MUFU unit (ex2.approx / lg2.approx, relative error ~2^-22): with expf / logf the kernel issued 23 M warp
 // instructions at bs=64 (IPC 2.1 of 4 over its whole run); the loss and the gradient stay inside the 1e-5 bars of the tests.
@@ -61,12 +45,33 @@ __device__ __forceinline__ void softmax_px(const float (&z)[C], float (&p)[C], f
   lse = NEED_LSE ? fast_log(s) : 0.f;
 }
 
+// ---- pass 1: per-sample Dice sums, CE numerator / denominator, argmax.  Reads logits + labels once (20 B/pixel). ----
+template <int C, int VEC>
+__device__ __forceinline__ void load_px(const float *zb, const long long *lb, long long HW, long long px, float (&zz)[C][VEC], long long (&yy)[VEC]) {
+  if (VEC == 4) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float4 t = __ldcg(reinterpret_cast<const float4 *>(zb + c * HW + px));
+      zz[c][0] = t.x; zz[c][1] = t.y; zz[c][2] = t.z; zz[c][3] = t.w;
+    }
+    const longlong2 a = __ldcg(reinterpret_cast<const longlong2 *>(lb + px));
+    const longlong2 b = __ldcg(reinterpret_cast<const longlong2 *>(lb + px + 2));
+    yy[0] = a.x; yy[1] = a.y; yy[2] = b.x; yy[3] = b.y;
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) zz[c][0] = __ldcg(zb + c * HW + px);
+    yy[0] = __ldcg(lb + px);
+  }
+}
+
 template <int C, int VEC>
 __global__ void __launch_bounds__(256)
-ce_dice_kernel(const float *__restrict__ logits, const long long *__restrict__ labels,
-               int N, long long HW, const float *__restrict__ cw, int ignore_index,
-               float grad_scale, float *__restrict__ loss_out, float *__restrict__ dlogits,
-               unsigned char *__restrict__ pred, double *acc, double *ce, unsigned int *counter, float dice_weight) {
+ce_dice_reduce_kernel(const float *__restrict__ logits, const long long *__restrict__ labels,
+                      int N, long long HW, const float *__restrict__ cw, int ignore_index,
+                      float *__restrict__ loss_out, unsigned char *__restrict__ pred, double *acc, double *ce,
+                      unsigned int *counter, float dice_weight) {
+  // the gradient pass may be launched as a programmatic dependent: let it get resident (its prologue waits on griddepcontrol)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int n = blockIdx.y;
   const long long chunk = (((HW + gridDim.x - 1) / gridDim.x) + VEC - 1) / VEC * VEC;
   const long long p0 = (long long)blockIdx.x * chunk;
@@ -77,25 +82,10 @@ ce_dice_kernel(const float *__restrict__ logits, const long long *__restrict__ l
   float w[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) w[c] = cw[c];
-
-  // ---------------- phase 1: reductions (+argmax) ----------------
   float fI = 0.f, fS = 0.f, fnum = 0.f, fden = 0.f;
   for (long long px = p0 + (long long)threadIdx.x * VEC; px < p1; px += (long long)blockDim.x * VEC) {
     float zz[C][VEC]; long long yy[VEC];
-    if (VEC == 4) {
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        float4 t = __ldg(reinterpret_cast<const float4 *>(zb + c * HW + px));
-        zz[c][0] = t.x; zz[c][1] = t.y; zz[c][2] = t.z; zz[c][3] = t.w;
-      }
-      longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(lb + px));
-      longlong2 b = __ldg(reinterpret_cast<const longlong2 *>(lb + px + 2));
-      yy[0] = a.x; yy[1] = a.y; yy[2] = b.x; yy[3] = b.y;
-    } else {
-#pragma unroll
-      for (int c = 0; c < C; ++c) zz[c][0] = __ldg(zb + c * HW + px);
-      yy[0] = __ldg(lb + px);
-    }
+    load_px<C, VEC>(zb, lb, HW, px, zz, yy);
     unsigned char pr[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -124,35 +114,30 @@ ce_dice_kernel(const float *__restrict__ logits, const long long *__restrict__ l
       pr[i] = (unsigned char)am;
     }
     if (pred != nullptr) {
-      if (VEC == 4) {
-        uchar4 u = make_uchar4(pr[0], pr[1], pr[2], pr[3]);
-        *reinterpret_cast<uchar4 *>(pred + (long long)n * HW + px) = u;
-      } else {
-        pred[(long long)n * HW + px] = pr[0];
-      }
+      if (VEC == 4) *reinterpret_cast<uchar4 *>(pred + (long long)n * HW + px) = make_uchar4(pr[0], pr[1], pr[2], pr[3]);
+      else pred[(long long)n * HW + px] = pr[0];
     }
   }
-  {
-    __shared__ double red[4][8];
-    double d0 = warp_sum_d((double)fI), d1 = warp_sum_d((double)fS);
-    double d2 = warp_sum_d((double)fnum), d3 = warp_sum_d((double)fden);
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) { red[0][wid] = d0; red[1][wid] = d1; red[2][wid] = d2; red[3][wid] = d3; }
-    __syncthreads();
-    if (threadIdx.x < 4) {
-      double s = 0.0;
-      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[threadIdx.x][i];
-      double *dst = (threadIdx.x < 2) ? (acc + 2 * n + threadIdx.x) : (ce + (threadIdx.x - 2));
-      atomicAdd(dst, s);
-    }
+  __shared__ double red[4][8];
+  __shared__ unsigned int ticket;
+  const double d0 = warp_sum_d((double)fI), d1 = warp_sum_d((double)fS);
+  const double d2 = warp_sum_d((double)fnum), d3 = warp_sum_d((double)fden);
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][wid] = d0; red[1][wid] = d1; red[2][wid] = d2; red[3][wid] = d3; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[threadIdx.x][i];
+    double *dst = (threadIdx.x < 2) ? (acc + 2 * n + threadIdx.x) : (ce + (threadIdx.x - 2));
+    atomicAdd(dst, s);
+    __threadfence();
   }
-  const unsigned int total = gridDim.x * gridDim.y;
-  grid_barrier_arrive_wait(counter, total, /*wait=*/true);
-
-  // ---------------- loss value (one block) ----------------
-  // one WARP of the last block sums the per-sample Dice terms (a single thread walking N samples with two dependent L2 loads each
-  // sat on the critical path of block (0,0): its own gradient phase started ~20 us late at N = 64)
-  if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && threadIdx.x < 32) {
+  __syncthreads();
+  if (threadIdx.x == 0) ticket = atomicAdd(counter, 1u);
+  __syncthreads();
+  // ---- loss value: one warp of the LAST block to finish (every other block's sums are visible: fence + atomic ticket) ----
+  if (ticket == gridDim.x * gridDim.y - 1 && threadIdx.x < 32) {
+    __threadfence();
     double dice = 0.0;
     for (int i = threadIdx.x; i < N; i += 32) {
       const double I = __ldcg(acc + 2 * i), S = __ldcg(acc + 2 * i + 1);
@@ -165,30 +150,38 @@ ce_dice_kernel(const float *__restrict__ logits, const long long *__restrict__ l
       loss_out[0] = (float)((double)dice_weight * dice + cel); loss_out[1] = (float)dice; loss_out[2] = (float)cel;
     }
   }
-  if (dlogits == nullptr) return;
+}
 
-  // ---------------- phase 2: gradient ----------------
+// ---- pass 2: gradient.  Re-reads logits + labels (L2 hits: 64 MB at bs=64 against 126 MB of L2), writes 12 B/pixel. ----
+template <int C, int VEC>
+__global__ void __launch_bounds__(256)
+ce_dice_grad_kernel(const float *__restrict__ logits, const long long *__restrict__ labels, int N, long long HW,
+                    const float *__restrict__ cw, int ignore_index, float grad_scale, float *__restrict__ dlogits,
+                    const double *acc, const double *ce, float dice_weight) {
+  const int n = blockIdx.y;
+  const long long chunk = (((HW + gridDim.x - 1) / gridDim.x) + VEC - 1) / VEC * VEC;
+  const long long p0 = (long long)blockIdx.x * chunk;
+  const long long p1 = min(HW, p0 + chunk);
+  const float *zb = logits + (long long)n * C * HW;
+  const long long *lb = labels + (long long)n * HW;
+  const float T0 = 1e-6f, T1 = 1.0f + 1e-6f;
+  float w[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) w[c] = cw[c];
+  // first tile of inputs does not depend on pass 1: issue it before waiting for the sums
+  long long px = p0 + (long long)threadIdx.x * VEC;
+  float zz[C][VEC]; long long yy[VEC];
+  if (px < p1) load_px<C, VEC>(zb, lb, HW, px, zz, yy);
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // pass 1 complete and flushed (no-op without a programmatic dependency)
   const double In = __ldcg(acc + 2 * n), Sn = __ldcg(acc + 2 * n + 1) + 1e-6;
   const float a_n = (float)(-2.0 / ((double)N * Sn)) * grad_scale * dice_weight;      // dL/dp = a_n*t + b_n
   const float b_n = (float)(2.0 * In / ((double)N * Sn * Sn)) * grad_scale * dice_weight;
   const float inv_den = (float)(1.0 / __ldcg(ce + 1)) * grad_scale;
   float *gb = dlogits + (long long)n * C * HW;
-  for (long long px = p0 + (long long)threadIdx.x * VEC; px < p1; px += (long long)blockDim.x * VEC) {
-    float zz[C][VEC]; long long yy[VEC];
-    if (VEC == 4) {
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        float4 t = __ldcg(reinterpret_cast<const float4 *>(zb + c * HW + px));
-        zz[c][0] = t.x; zz[c][1] = t.y; zz[c][2] = t.z; zz[c][3] = t.w;
-      }
-      longlong2 a = __ldcg(reinterpret_cast<const longlong2 *>(lb + px));
-      longlong2 b = __ldcg(reinterpret_cast<const longlong2 *>(lb + px + 2));
-      yy[0] = a.x; yy[1] = a.y; yy[2] = b.x; yy[3] = b.y;
-    } else {
-#pragma unroll
-      for (int c = 0; c < C; ++c) zz[c][0] = __ldcg(zb + c * HW + px);
-      yy[0] = __ldcg(lb + px);
-    }
+  while (px < p1) {
+    const long long nx = px + (long long)blockDim.x * VEC;
+    float zn[C][VEC]; long long yn[VEC];
+    if (nx < p1) load_px<C, VEC>(zb, lb, HW, nx, zn, yn);   // software pipeline: next tile in flight while this one computes
     float gg[C][VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -227,6 +220,13 @@ ce_dice_kernel(const float *__restrict__ logits, const long long *__restrict__ l
 #pragma unroll
       for (int c = 0; c < C; ++c) gb[c * HW + px] = gg[c][0];
     }
+    px = nx;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) zz[c][i] = zn[c][i];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) yy[i] = yn[i];
   }
 }
 
@@ -234,32 +234,31 @@ template <int C, int VEC>
 static int launch_ce_dice(const float *logits, const int64_t *labels, int N, int64_t HW,
                           const float *cw, int ignore_index, float grad_scale, float *loss_out,
                           float *dlogits, uint8_t *pred, void *workspace, cudaStream_t st, float dice_weight) {
-  auto kern = ce_dice_kernel<C, VEC>;
-  static int max_blocks = 0;  // co-resident CTA capacity of this device for this kernel
-  if (max_blocks == 0) {
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return (int)e;
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return (int)e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0); if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) return KS_EUNSUPPORTED;
-    max_blocks = sms * per_sm;
-  }
-  if (N > max_blocks) return KS_EUNSUPPORTED;
-  // ~4 CTAs/SM of 256 threads, at least ~1024 px per CTA, never more than co-resident capacity.
-  int target = kNumSMs * 4; if (target > max_blocks) target = max_blocks;
-  int chunks = target / N; if (chunks < 1) chunks = 1;
+  // Two plain launches (no cooperative grid, no software grid barrier: the kernel boundary is the barrier, and with the
+  // programmatic-dependent-launch attribute the gradient pass is resident and has its first loads in flight when pass 1 drains).
+  // grid: ~8 CTAs of 256 threads per SM, at least 1024 pixels per CTA.
+  int chunks = (kNumSMs * 8 + N - 1) / N; if (chunks < 1) chunks = 1;
   long long maxchunks = (HW + 1023) / 1024; if (chunks > maxchunks) chunks = (int)maxchunks;
   if (chunks < 1) chunks = 1;
+  if (g_opt.loss_chunks > 0) chunks = g_opt.loss_chunks;
   const int64_t ws_bytes = ks_ce_dice_workspace_bytes(N);
   cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)ws_bytes, st);
   if (e != cudaSuccess) return (int)e;
   double *acc = (double *)workspace; double *ce = acc + 2 * (size_t)N;
   unsigned int *counter = (unsigned int *)(ce + 2);
-  const long long *lab = (const long long *)labels; long long hw = HW; unsigned char *pr = pred;
-  void *args[] = {(void *)&logits, (void *)&lab, (void *)&N, (void *)&hw, (void *)&cw, (void *)&ignore_index,
-                  (void *)&grad_scale, (void *)&loss_out, (void *)&dlogits, (void *)&pr,
-                  (void *)&acc, (void *)&ce, (void *)&counter, (void *)&dice_weight};
-  e = cudaLaunchCooperativeKernel((const void *)kern, dim3(chunks, N), dim3(256), args, 0, st);
+  const long long *lab = (const long long *)labels;
+  ce_dice_reduce_kernel<C, VEC><<<dim3(chunks, N), 256, 0, st>>>(logits, lab, N, (long long)HW, cw, ignore_index, loss_out, pred, acc, ce,
+                                                                  counter, dice_weight);
+  e = cudaGetLastError();
+  if (e != cudaSuccess || dlogits == nullptr) return (int)e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(chunks, N); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_opt.loss_no_pdl ? 0 : 1;
+  e = cudaLaunchKernelEx(&cfg, ce_dice_grad_kernel<C, VEC>, logits, lab, N, (long long)HW, cw, ignore_index, grad_scale, dlogits,
+                         (const double *)acc, (const double *)ce, dice_weight);
   return (int)e;
 }
 

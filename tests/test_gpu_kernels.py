@@ -405,3 +405,31 @@ def test_cross_entropy_mode_matches_torch(ops, weights):
     np.testing.assert_allclose(loss.item(), ref.item(), rtol=1e-5)
     assert rel_l2(zd.grad, z.grad) < 1e-5
     assert torch.equal(crit.last_pred.cpu().long(), z.detach().argmax(1))
+
+
+def test_confusion_update_grouped(ops, sh):
+    """Bit-exact: ONE launch fills the global, the per-activation and the per-climate-zone matrices (reference
+    change_detection_trainer.py:184-199, :445-480) - against the shadow (torch.bincount per sample and group)."""
+    g = _gen(10)
+    B, H, W = 7, 96, 112
+    pred = torch.randint(0, 3, (B, H, W), generator=g, dtype=torch.uint8)
+    lab = torch.randint(0, 4, (B, H, W), generator=g, dtype=torch.int64)
+    ka = torch.tensor([0, 2, 2, -1, 4, 0, 9], dtype=torch.int32)     # -1 and 9 (>= n_a) are skipped
+    kb = torch.tensor([0, 1, 2, 2, 1, 0, 0], dtype=torch.int32)
+    mats = [torch.zeros(4, 4, dtype=torch.int64), torch.zeros(5, 4, 4, dtype=torch.int64), torch.zeros(3, 4, 4, dtype=torch.int64)]
+    dmats = [m.clone().to(DEV) for m in mats]
+    for _ in range(2):
+        ops.confusion_update_grouped(pred.to(DEV), lab.to(DEV), 4, 3, dmats[0], ka.to(DEV), dmats[1], kb.to(DEV), dmats[2])
+        sh.confusion_update_grouped(pred, lab, 4, 3, mats[0], ka, mats[1], kb, mats[2])
+    for d, m in zip(dmats, mats):
+        assert torch.equal(d.cpu(), m)
+    assert int(mats[1].sum()) == 2 * int((lab[[0, 1, 2, 4, 5]] != 3).sum()) and int(mats[2].sum()) == int(mats[0].sum())
+    from kurosiwo_b200.utilities import GroupedConfusionMetrics
+    acts = [130, 470, 555]
+    m = GroupedConfusionMetrics(3, 3, DEV, activations=acts, zones=True)
+    activ = torch.tensor([470, 130, 470, 555, 130, 7, 555])
+    clz = torch.tensor([1, 2, 2, 3, 1, 2, 3])
+    m.update(pred.to(DEV), lab.to(DEV), activ=activ, clz=clz)
+    c = GroupedConfusionMetrics(3, 3, "cpu", activations=acts, zones=True)
+    c.update(pred, lab, activ=activ, clz=clz)
+    assert torch.equal(m.mat.cpu(), c.mat) and torch.equal(m.mat_aoi.cpu(), c.mat_aoi) and torch.equal(m.mat_zone.cpu(), c.mat_zone)

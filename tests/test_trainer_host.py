@@ -159,3 +159,155 @@ def test_lookahead_pairs():
     assert list(lookahead([])) == []
     assert list(lookahead([1])) == [(1, None)]
     assert list(lookahead("abc")) == [("a", "b"), ("b", "c"), ("c", None)]
+
+
+# ---- round 2: grouped metrics, AdamW, state hand-over, best-checkpoint reload, reference multi_scale_train ---------------------
+def test_grouped_confusion_metrics_match_per_group_definitions():
+    """Per-activation (AOI) and per-climate-zone metric sets (reference change_detection_trainer.py:184-199, :445-480) and the
+    water-only F-score (:408-413): the grouped matrices must equal the global definition applied to each group's samples."""
+    from kurosiwo_b200.utilities import GroupedConfusionMetrics, metrics_from_confusion, water_only_fscore
+    g = torch.Generator().manual_seed(1)
+    B = 6
+    pred = torch.randint(0, 3, (B, 12, 10), generator=g).to(torch.uint8)
+    tgt = torch.randint(0, 4, (B, 12, 10), generator=g)
+    acts = [130, 470, 555, 1111011]
+    activ = torch.tensor([470, 130, 470, 1111011, 999, 130])        # 999: not a known activation -> only the global set
+    clz = torch.tensor([1, 2, 2, 3, 1, 2])
+    m = GroupedConfusionMetrics(3, 3, "cpu", activations=acts, zones=True)
+    m.update(pred[:4], tgt[:4], activ=activ[:4], clz=clz[:4])
+    m.update(pred[4:], tgt[4:], activ=activ[4:], clz=clz[4:])
+    ref = ConfusionMetrics(3, 3, "cpu"); ref.update(pred, tgt)
+    assert torch.equal(m.mat, ref.mat)
+    aoi = m.compute_aoi()
+    assert sorted(aoi) == [130, 470, 1111011]
+    for a in aoi:
+        r = ConfusionMetrics(3, 3, "cpu"); r.update(pred[activ == a], tgt[activ == a])
+        for got, want in zip(aoi[a], r.compute()):
+            assert torch.allclose(got, want)
+    zones = m.compute_zones()
+    assert m.samples_per_zone == {1: 2, 2: 3, 3: 1}
+    for z in (1, 2, 3):
+        r = ConfusionMetrics(3, 3, "cpu"); r.update(pred[clz == z], tgt[clz == z])
+        assert torch.allclose(zones[z][4], r.compute()[4])
+    # water-only F1 = F1 of the relabelled 2-class problem (2 -> 1 in predictions and labels, ignore_index 3)
+    p2, t2 = pred.long().clone(), tgt.clone()
+    p2[p2 == 2] = 1; t2[t2 == 2] = 1
+    keep = t2 != 3
+    tp = ((p2 == 1) & (t2 == 1) & keep).sum().item(); fp = ((p2 == 1) & (t2 == 0) & keep).sum().item(); fn = ((p2 == 0) & (t2 == 1) & keep).sum().item()
+    assert abs(water_only_fscore(m.mat)[1].item() - 2 * tp / (2 * tp + fp + fn)) < 1e-12
+    assert torch.allclose(metrics_from_confusion(m.mat)[4], ref.compute()[4])
+
+
+def test_adamw_config_reaches_the_fused_optimizer():
+    """optimizer 'adamw' (reference change_detection_trainer.py:55-60: betas + weight_decay from the method config) against
+    torch.optim.AdamW driven with the oracle's gradients."""
+    seed, base, N, H, W = 3, 8, 2, 32, 32
+    configs, model_configs = _cfg()
+    model_configs.update(optimizer="adamw", betas=[0.8, 0.95], weight_decay=0.05, learning_rate=2e-3)
+    sd_np = weights.make_state(seed, 2, 3, base)
+    model = SNUNet_ECAM(2, 3, base_channel=base, precision="fp32")
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd_np.items()})
+    model.set_ops(ShadowOps())
+    stepper = cdt.FusedStepper(model, configs, model_configs)
+    batch = synthetic.make_batch(21, N, H, W, False)
+    xA, xB, mask = stepper._to_device(batch)
+    sd = snunet_oracle.to_torch_state(sd_np)
+    names = [n for n, _ in model.named_parameters()]
+    ref_params = [torch.nn.Parameter(sd[n].clone()) for n in names]
+    opt = torch.optim.AdamW(ref_params, lr=2e-3, betas=(0.8, 0.95), weight_decay=0.05)
+    for _ in range(2):
+        _, _, grads = snunet_oracle.train_step({**sd, **{n: p.detach() for n, p in zip(names, ref_params)}}, xA, xB, mask)
+        for n, p in zip(names, ref_params):
+            p.grad = grads[n].clone()
+        opt.step()
+        stepper.step_host(batch)
+    assert stepper.engine.optimizer == "adamw" and stepper.engine.hp["wd"] == 0.05 and stepper.engine.hp["b1"] == 0.8
+    for n, p in zip(names, ref_params):
+        got = dict(model.named_parameters())[n].detach()
+        assert (got - p.detach()).abs().max().item() < 3e-3, n     # Adam-type updates are lr-sized: 2 steps x 2e-3, rounding-level gradient noise
+
+
+def test_engine_swap_hands_over_moments_step_and_dropout_counter():
+    """assert the hand-over itself (not two runs that would lose the state identically)."""
+    from kurosiwo_b200.siam_unet import SiamUnet_conc
+    configs, model_configs = _cfg()
+    configs["method"] = "siam-conc"
+    model = SiamUnet_conc(input_nbr=2, label_nbr=3, precision="fp32")
+    model.set_ops(ShadowOps())
+    stepper = cdt.FusedStepper(model, configs, model_configs)
+    full, ragged = synthetic.make_batch(11, 2, 32, 32, False), synthetic.make_batch(12, 1, 32, 32, False)
+    stepper.step_host(full); stepper.step_host(full)
+    e1 = stepper.engine
+    m1, v1, s1, d1 = e1.adam_m.clone(), e1.adam_v.clone(), int(e1.adam_step.item()), int(e1.do_step.item())
+    assert s1 == 2 and d1 == 2 and float(m1.abs().sum()) > 0
+    xa = stepper._to_device(ragged)[0]
+    e2 = stepper._engine(xa)                       # the swap, before any step on the new engine
+    assert e2 is not e1
+    assert torch.equal(e2.adam_m, m1) and torch.equal(e2.adam_v, v1) and int(e2.adam_step.item()) == s1
+    assert int(e2.do_step.item()) == d1            # the dropout mask sequence continues instead of restarting
+
+
+def test_reference_multi_scale_train_raises():
+    """The reference's multi_scale_train branch (change_detection_trainer.py:155-164) resizes the [B,H,W] int64 mask with
+    F.interpolate(mask, size=int, mode="nearest"): torch has no nearest kernel for Long, so the branch raises before any loss is
+    computed (and a float mask would be resized along W only: [B,H,W] is read as (N, C, L)).  The drop-in raises the same type."""
+    import torch.nn.functional as F
+    mask = torch.randint(0, 4, (2, 64, 64))
+    with pytest.raises(NotImplementedError):
+        F.interpolate(mask, size=16, mode="nearest")
+    assert F.interpolate(mask.float(), size=16, mode="nearest").shape == (2, 64, 16)
+    from kurosiwo_b200.changeformer import ChangeFormerV6
+    configs, model_configs = _cfg()
+    model_configs["multi_scale_train"] = True
+    with pytest.raises(NotImplementedError):
+        cdt.FusedStepper(ChangeFormerV6(input_nc=2, output_nc=3, decoder_softmax=True, embed_dim=32), configs, model_configs)
+
+
+def test_main_reloads_best_checkpoint(tmp_path):
+    """the test set is evaluated on best_segmentation.pt (reference main.py:149-152, :172-185), not on the last epoch."""
+    import importlib.util
+    import sys
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("ks_main", Path(__file__).resolve().parent.parent / "main.py")
+    main = importlib.util.module_from_spec(spec); spec.loader.exec_module(main)
+    configs = {"checkpoint_path": str(tmp_path), "device": "cpu"}
+    best = SNUNet_ECAM(2, 3, base_channel=8, precision="fp32")
+    torch.save({"epoch": 0, "model_state_dict": best.state_dict(), "optimizer_state_dict": {}, "lr_scheduler_state_dict": {}, "loss": 0.0},
+               tmp_path / "best_segmentation.pt")
+    last = SNUNet_ECAM(2, 3, base_channel=8, precision="fp32")
+    assert not torch.equal(last.conv0_0.conv1.weight, best.conv0_0.conv1.weight)
+    out = main.load_best_checkpoint(last, configs, "cd")
+    assert out is last and torch.equal(last.conv0_0.conv1.weight, best.conv0_0.conv1.weight)
+    (tmp_path / "best_segmentation.pt").unlink()
+    torch.save(best, tmp_path / "best_segmentation.pt")               # the segmentation trainer pickles the module
+    out = main.load_best_checkpoint(last, configs, "segmentation")
+    assert isinstance(out, SNUNet_ECAM) and out is not last
+    (tmp_path / "best_segmentation.pt").unlink()
+    assert main.load_best_checkpoint(last, configs, "cd") is last      # no file: current weights
+
+
+def test_best_checkpoint_has_the_reference_keys(tmp_path):
+    configs, model_configs = _cfg()
+    configs["checkpoint_path"] = str(tmp_path)
+    configs["log_AOI_metrics"] = True
+    configs["log_zone_metrics"] = True
+    configs["evaluate_water"] = True
+    model = SNUNet_ECAM(2, 3, base_channel=8, precision="fp32")
+    model.set_ops(ShadowOps())
+    loader = synthetic.SyntheticLoader(2, 2, seed=5, H=32, W=32, pin=False)
+
+    class OracleCrit(torch.nn.Module):
+        def forward(self, out, mask):
+            return snunet_oracle.ce_dice_torch(out, mask, (1.0, 1.0, 1.0))
+    import kurosiwo_b200.change_detection_trainer as mod
+    orig = mod.create_loss
+    mod.create_loss = lambda c, mode="val": OracleCrit()
+    try:
+        cdt.train_change_detection(model, loader, loader, loader, configs, model_configs)
+    finally:
+        mod.create_loss = orig
+    ck = torch.load(tmp_path / "best_segmentation.pt", weights_only=False)
+    assert set(ck) >= {"epoch", "model_state_dict", "optimizer_state_dict", "lr_scheduler_state_dict", "loss"}   # reference :312-318
+    det = cdt.LAST_EVAL["Validation"]
+    assert det["zones"] and det["aoi"] and "water_fscore" in det
+    assert sum(det["samples_per_zone"].values()) == 4

@@ -248,3 +248,30 @@ def test_decoder_head_schedule_matches_oracle():
     for name, p in model.named_parameters():
         go = grads_o[name]
         assert (p.grad - go).abs().max().item() <= 2e-3 * go.abs().max().item() + 1e-8, name
+
+
+def test_linear_eval_freezes_the_encoder():
+    """configs['linear_eval'] (reference models/model_utilities.py:160-161: encoder.requires_grad = False): the fused step skips the
+    encoder backward; the head's gradients equal those of the full backward, the encoder's flat-gradient slices stay zero and
+    Adam leaves the encoder untouched."""
+    fx = np.load(GOLD / FIXTURES[0])
+    dim, depth, heads, mlp, sd_np, img, mask = _case(fx)
+    sd = vit_oracle.to_torch_state(sd_np)
+    _, _, grads_o = vit_oracle.train_step(sd, img, mask, heads)
+    model = _model(dim, depth, heads, mlp, sd_np)
+    model.set_ops(ShadowOps())
+    model.train()
+    eng = model.engine(img)
+    eng.init_training(lr=1e-3)
+    eng.freeze_encoder = True
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    eng.train_step(img, mask)
+    for n, p in model.named_parameters():
+        g = eng.params.g(n).view(p.shape)
+        if n.startswith("head."):
+            go = grads_o[n]
+            assert (g - go).abs().max().item() <= 2e-3 * go.abs().max().item() + 1e-7, n
+            assert not torch.equal(p.detach(), before[n]), n
+        else:
+            assert float(g.abs().max()) == 0.0, n
+            assert torch.equal(p.detach(), before[n]), n
