@@ -340,7 +340,8 @@ int ks_sigmoid_head_bwd(int dtype, int N, int H, int W, const float *out, const 
  * logits: NCHW fp32 [N][C][HW] (C==3); labels int64 [N][HW].
  * loss_out: fp32[3] = {total, dice, ce}; dlogits NCHW fp32 scaled by grad_scale
  * (may be NULL: forward only); pred: uint8 [N][HW] argmax (may be NULL).
- * workspace: ks_ce_dice_workspace_bytes(N) bytes, contents ignored. */
+ * workspace: ks_ce_dice_workspace_bytes(N) bytes, one per batch size N, ZERO-FILLED ONCE by the caller before its first use; every
+ * call leaves it ready for the next one (the kernels re-zero what they used: no memset launch per call). */
 int64_t ks_ce_dice_workspace_bytes(int N);
 int ks_ce_dice_fwd_bwd(const float *logits, const int64_t *labels, int N, int C, int64_t HW,
                        const float *class_weights, int ignore_index, float grad_scale,

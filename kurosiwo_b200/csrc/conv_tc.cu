@@ -826,6 +826,8 @@ extern "C" int ks_set_option(const char *name, int value) {
   else if (eq("tc_ns3_mode")) ks::g_opt.ns3_mode = value;         // streamed + stacked: 1 = two CTAs per SM (256 TMEM columns), 2 = one CTA per SM
   else if (eq("tc_nacc")) ks::g_opt.nacc = value;
   else if (eq("loss_chunks")) ks::g_opt.loss_chunks = value;   // perf experiments: CTAs per sample of the CE+Dice passes
+  else if (eq("loss_variant")) ks::g_opt.loss_variant = value;   // perf experiments: (stages, pixels per stage) of the bulk-staged passes
+  else if (eq("loss_no_bulk")) ks::g_opt.loss_no_bulk = value;   // 1 = register-staged CE+Dice passes (A/B comparisons)
   else if (eq("loss_no_pdl")) ks::g_opt.loss_no_pdl = value;   // 1 = plain stream order between the two CE+Dice passes
   else if (eq("tc_no_ns3")) ks::g_opt.no_ns3 = value;   // 1 = one UMMA per tap also for narrow N tiles (A/B comparisons)
   else if (eq("wgrad_mode")) ks::g_opt.wgrad_mode = value;   // 0 auto (tap stacking along N), 2 = halo kernel v2

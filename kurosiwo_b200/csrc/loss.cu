@@ -13,10 +13,23 @@
 
 namespace ks {
 
-struct LossWs {
-  // doubles: [N][2] (I_n, S_n), then [2] (ce_num, ce_den); then counters
-  double *acc; double *ce; unsigned int *counter;
-};
+// Workspace protocol (no memset launch per call - in a CUDA graph the memset node cost 6.7 us of a 34 us call): ctrl[0] is the
+// ticket counter, ctrl[1] a flip bit; the sums live in two halves of (4 N + 2) doubles.  Call k accumulates into half flip & 1;
+// the last block of pass 1 (which has seen every other block's ticket) zeroes the OTHER half (used by call k - 1, whose gradient
+// pass finished before this launch started), resets the ticket counter and toggles the flip; pass 2 reads half (flip ^ 1) & 1.
+// The caller zero-fills the workspace ONCE.
+__device__ __forceinline__ unsigned int ld_flip(const unsigned int *ctrl) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(v) : "l"(ctrl + 1) : "memory");
+  return v;
+}
+__device__ __forceinline__ void finish_workspace(double *ws, unsigned int *ctrl, int N) {   // one warp of the last block
+  const unsigned int flip = ld_flip(ctrl);
+  double *other = ws + (size_t)((flip ^ 1u) & 1u) * (4 * (size_t)N + 2);
+  for (int i = threadIdx.x; i < 4 * N + 2; i += 32) other[i] = 0.0;
+  __syncwarp();
+  if (threadIdx.x == 0) { ctrl[0] = 0u; __threadfence(); ctrl[1] = flip ^ 1u; }
+}
 
 // exp / log on the MUFU unit (ex2.approx / lg2.approx, relative error ~2^-22): with expf / logf the kernel issued 23 M warp
 // instructions at bs=64 (IPC 2.1 of 4 over its whole run); the loss and the gradient stay inside the 1e-5 bars of the tests.
@@ -68,8 +81,9 @@ template <int C, int VEC>
 __global__ void __launch_bounds__(256)
 ce_dice_reduce_kernel(const float *__restrict__ logits, const long long *__restrict__ labels,
                       int N, long long HW, const float *__restrict__ cw, int ignore_index,
-                      float *__restrict__ loss_out, unsigned char *__restrict__ pred, double *acc, double *ce,
-                      unsigned int *counter, float dice_weight) {
+                      float *__restrict__ loss_out, unsigned char *__restrict__ pred, double *ws,
+                      unsigned int *ctrl, float dice_weight) {
+  double *acc = ws + (size_t)(ld_flip(ctrl) & 1u) * (4 * (size_t)N + 2);
   // the gradient pass may be launched as a programmatic dependent: let it get resident (its prologue waits on griddepcontrol)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int n = blockIdx.y;
@@ -82,45 +96,62 @@ ce_dice_reduce_kernel(const float *__restrict__ logits, const long long *__restr
   float w[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) w[c] = cw[c];
-  float fI = 0.f, fS = 0.f, fnum = 0.f, fden = 0.f;
-  for (long long px = p0 + (long long)threadIdx.x * VEC; px < p1; px += (long long)blockDim.x * VEC) {
-    float zz[C][VEC]; long long yy[VEC];
-    load_px<C, VEC>(zb, lb, HW, px, zz, yy);
+  // Algebra (exact in real arithmetic, Sum_c p_c = 1): Sum_c p_c t_c = T0 + p_yd and Sum_c (p_c + t_c) = 1 + (C-1) T0 + T1, so the
+  // per-sample Dice sums need ONE probability per pixel, p_yd = exp(z_yd - m - lse); the CE term reuses the same log-probability.
+  // (The reference adds the C products in fp32; the difference is ~1e-7 relative, far inside the 1e-5 bars of the tests.)
+  float fI = 0.f, fnum = 0.f, fden = 0.f;
+  long long npx = 0;
+  const float L2E = 1.4426950408889634f;
+  long long px = p0 + (long long)threadIdx.x * VEC;
+  float zz[C][VEC]; long long yy[VEC];
+  if (px < p1) load_px<C, VEC>(zb, lb, HW, px, zz, yy);
+  while (px < p1) {
+    const long long nx = px + (long long)blockDim.x * VEC;
+    float zn[C][VEC]; long long yn[VEC];
+    if (nx < p1) load_px<C, VEC>(zb, lb, HW, nx, zn, yn);   // next tile in flight while this one computes
     unsigned char pr[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      float z[C], p[C], m, lse;
-#pragma unroll
-      for (int c = 0; c < C; ++c) z[c] = zz[c][i];
-      softmax_px<C>(z, p, m, lse);
       const int y = (int)yy[i];
       const bool valid = (y != ignore_index);
       const int yd = valid ? y : 0;  // dice.py:116-119: ignored pixels become class 0
-      int am = 0; float best = z[0];
+      float m = zz[0][i]; int am = 0;
+#pragma unroll
+      for (int c = 1; c < C; ++c) { if (zz[c][i] > m) { m = zz[c][i]; am = c; } }      // first maximum, as torch.argmax
+      float s = 0.f, zy = zz[0][i], wy = w[0];
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float t = (c == yd) ? T1 : T0;
-        fI += p[c] * t;
-        fS += p[c] + t;
-        if (c > 0 && z[c] > best) { best = z[c]; am = c; }
+        float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((zz[c][i] - m) * L2E));
+        s += e;
+        if (c > 0 && c == yd) { zy = zz[c][i]; wy = w[c]; }
       }
-      if (valid) {
-        float zy = z[0], wy = w[0];
-#pragma unroll
-        for (int c = 1; c < C; ++c) if (c == y) { zy = z[c]; wy = w[c]; }
-        fnum += -wy * (zy - m - lse);
-        fden += wy;
-      }
+      float l2s; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2s) : "f"(s));
+      const float logp2 = (zy - m) * L2E - l2s;                 // log2 p_yd
+      float pyd; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pyd) : "f"(logp2));
+      fI += pyd;
+      if (valid) { fnum -= wy * logp2; fden += wy; }
       pr[i] = (unsigned char)am;
     }
+    npx += VEC;
     if (pred != nullptr) {
       if (VEC == 4) *reinterpret_cast<uchar4 *>(pred + (long long)n * HW + px) = make_uchar4(pr[0], pr[1], pr[2], pr[3]);
       else pred[(long long)n * HW + px] = pr[0];
     }
+    px = nx;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) zz[c][i] = zn[c][i];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) yy[i] = yn[i];
   }
+  fnum *= 0.6931471805599453f;                                    // log2 -> ln
+  const float fS_unused = 0.f; (void)fS_unused;
   __shared__ double red[4][8];
   __shared__ unsigned int ticket;
-  const double d0 = warp_sum_d((double)fI), d1 = warp_sum_d((double)fS);
+  // I_n = Sum_px (T0 + p_yd), S_n = Sum_px (1 + (C-1) T0 + T1): the constants are added per pixel count in double
+  const double d0 = warp_sum_d((double)fI + (double)npx * (double)T0);
+  const double d1 = warp_sum_d((double)npx * (1.0 + (double)(C - 1) * (double)T0 + (double)T1));
   const double d2 = warp_sum_d((double)fnum), d3 = warp_sum_d((double)fden);
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) { red[0][wid] = d0; red[1][wid] = d1; red[2][wid] = d2; red[3][wid] = d3; }
@@ -128,27 +159,29 @@ ce_dice_reduce_kernel(const float *__restrict__ logits, const long long *__restr
   if (threadIdx.x < 4) {
     double s = 0.0;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[threadIdx.x][i];
-    double *dst = (threadIdx.x < 2) ? (acc + 2 * n + threadIdx.x) : (ce + (threadIdx.x - 2));
-    atomicAdd(dst, s);
+    atomicAdd(acc + 4 * n + threadIdx.x, s);          // per-sample slots {I, S, ce_num, ce_den}
     __threadfence();
   }
   __syncthreads();
-  if (threadIdx.x == 0) ticket = atomicAdd(counter, 1u);
+  if (threadIdx.x == 0) ticket = atomicAdd(ctrl, 1u);
   __syncthreads();
   // ---- loss value: one warp of the LAST block to finish (every other block's sums are visible: fence + atomic ticket) ----
   if (ticket == gridDim.x * gridDim.y - 1 && threadIdx.x < 32) {
     __threadfence();
-    double dice = 0.0;
+    double dice = 0.0, num = 0.0, den = 0.0;
     for (int i = threadIdx.x; i < N; i += 32) {
-      const double I = __ldcg(acc + 2 * i), S = __ldcg(acc + 2 * i + 1);
+      const double I = __ldcg(acc + 4 * i), S = __ldcg(acc + 4 * i + 1);
       dice += 1.0 - 2.0 * I / (S + 1e-6);
+      num += __ldcg(acc + 4 * i + 2); den += __ldcg(acc + 4 * i + 3);
     }
-    dice = warp_sum_d(dice);
+    dice = warp_sum_d(dice); num = warp_sum_d(num); den = warp_sum_d(den);
     if (threadIdx.x == 0) {
       dice /= (double)N;
-      const double cel = __ldcg(ce) / __ldcg(ce + 1);  // NaN when every pixel is ignored (as torch)
+      acc[4 * (size_t)N] = num; acc[4 * (size_t)N + 1] = den;     // totals for the gradient pass
+      const double cel = num / den;  // NaN when every pixel is ignored (as torch)
       loss_out[0] = (float)((double)dice_weight * dice + cel); loss_out[1] = (float)dice; loss_out[2] = (float)cel;
     }
+    finish_workspace(ws, ctrl, N);
   }
 }
 
@@ -157,7 +190,7 @@ template <int C, int VEC>
 __global__ void __launch_bounds__(256)
 ce_dice_grad_kernel(const float *__restrict__ logits, const long long *__restrict__ labels, int N, long long HW,
                     const float *__restrict__ cw, int ignore_index, float grad_scale, float *__restrict__ dlogits,
-                    const double *acc, const double *ce, float dice_weight) {
+                    const double *ws, const unsigned int *ctrl, float dice_weight) {
   const int n = blockIdx.y;
   const long long chunk = (((HW + gridDim.x - 1) / gridDim.x) + VEC - 1) / VEC * VEC;
   const long long p0 = (long long)blockIdx.x * chunk;
@@ -173,44 +206,46 @@ ce_dice_grad_kernel(const float *__restrict__ logits, const long long *__restric
   float zz[C][VEC]; long long yy[VEC];
   if (px < p1) load_px<C, VEC>(zb, lb, HW, px, zz, yy);
   asm volatile("griddepcontrol.wait;" ::: "memory");      // pass 1 complete and flushed (no-op without a programmatic dependency)
-  const double In = __ldcg(acc + 2 * n), Sn = __ldcg(acc + 2 * n + 1) + 1e-6;
-  const float a_n = (float)(-2.0 / ((double)N * Sn)) * grad_scale * dice_weight;      // dL/dp = a_n*t + b_n
-  const float b_n = (float)(2.0 * In / ((double)N * Sn * Sn)) * grad_scale * dice_weight;
-  const float inv_den = (float)(1.0 / __ldcg(ce + 1)) * grad_scale;
+  const double *acc = ws + (size_t)((ld_flip(ctrl) ^ 1u) & 1u) * (4 * (size_t)N + 2);   // pass 1 has already flipped
+  const double Sn = __ldcg(acc + 4 * n + 1) + 1e-6;
+  const float a_n = (float)(-2.0 / ((double)N * Sn)) * grad_scale * dice_weight;      // dL/dp = a_n*t + b_n (b_n cancels, see below)
+  const double den = __ldcg(acc + 4 * (size_t)N + 1);           // Sum over samples, written by pass 1's last block
+  const float inv_den = (float)(1.0 / den) * grad_scale;
   float *gb = dlogits + (long long)n * C * HW;
   while (px < p1) {
     const long long nx = px + (long long)blockDim.x * VEC;
     float zn[C][VEC]; long long yn[VEC];
     if (nx < p1) load_px<C, VEC>(zb, lb, HW, nx, zn, yn);   // software pipeline: next tile in flight while this one computes
+    // d_c = p_c (g_c - Sum_k g_k p_k) + wy (p_c - 1[c == y]) with g_c = a_n t_c + b_n.  Since Sum_k p_k = 1 the b_n terms cancel and
+    // g_c - dot = a_n (1[c == yd] - p_yd):  d_c = a_n p_c (1[c == yd] - p_yd) + wy (p_c - 1[c == y, valid]).
     float gg[C][VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      float z[C], p[C], m, lse;
-#pragma unroll
-      for (int c = 0; c < C; ++c) z[c] = zz[c][i];
-      softmax_px<C, false>(z, p, m, lse);
       const int y = (int)yy[i];
       const bool valid = (y != ignore_index);
       const int yd = valid ? y : 0;
-      float g[C], dot = 0.f;
+      float m = zz[0][i];
+#pragma unroll
+      for (int c = 1; c < C; ++c) m = fmaxf(m, zz[c][i]);
+      float e[C], ssum = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) { asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[c]) : "f"((zz[c][i] - m) * 1.4426950408889634f)); ssum += e[c]; }
+      const float inv = __fdividef(1.0f, ssum);
+      float pyd = e[0], wy = w[0];
+#pragma unroll
+      for (int c = 1; c < C; ++c) if (c == yd) { pyd = e[c]; wy = w[c]; }
+      pyd *= inv;
+      wy = valid ? wy * inv_den : 0.f;
+      const float k_all = wy - a_n * pyd;            // coefficient of p_c for every class
+      const float k_hot = a_n - wy;                  // extra term of the class yd: a_n p_c - wy  (valid: yd == y; ignored: wy = 0)
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        g[c] = a_n * ((c == yd) ? T1 : T0) + b_n;
-        dot += g[c] * p[c];
-      }
-      float wy = 0.f;
-      if (valid) {
-        wy = w[0];
-#pragma unroll
-        for (int c = 1; c < C; ++c) if (c == y) wy = w[c];
-        wy *= inv_den;
-      }
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        float d = p[c] * (g[c] - dot);
-        d += wy * (p[c] - ((valid && c == y) ? 1.0f : 0.0f));
+        const float pc = e[c] * inv;
+        float d = k_all * pc;
+        if (c == yd) d += a_n * pc - wy;
         gg[c][i] = d;
       }
+      (void)k_hot;
     }
     if (VEC == 4) {
 #pragma unroll
@@ -230,42 +265,267 @@ ce_dice_grad_kernel(const float *__restrict__ logits, const long long *__restric
   }
 }
 
+// =====================================================================================================================
+// Bulk-staged passes (the default whenever HW % 4 == 0): one elected thread per CTA issues cp.async.bulk copies of whole pixel
+// chunks (P pixels: C logit rows + the int64 label row = 20 KB at P = 1024) into a 3-stage shared-memory ring guarded by
+// mbarriers, so ~40 KB per CTA (120 KB per SM at 3 CTAs) are in flight regardless of register pressure or loop structure.
+// ncu on the register-staged kernels above: 2.8-3.1 TB/s of DRAM reads at 27-36 % SM throughput - latency-bound.
+// =====================================================================================================================
+
+__device__ __forceinline__ uint32_t ls_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ls_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+template <int C, int LS_P>
+__device__ __forceinline__ void ls_issue(uint32_t bar, uint32_t dst, const float *zb, const long long *lb, long long HW, long long p0, int npx) {
+  const uint32_t zbytes = (uint32_t)npx * 4u, lbytes = (uint32_t)npx * 8u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(zbytes * C + lbytes) : "memory");
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst + (uint32_t)c * LS_P * 4u), "l"(zb + c * HW + p0), "r"(zbytes), "r"(bar) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst + (uint32_t)C * LS_P * 4u), "l"(lb + p0), "r"(lbytes), "r"(bar) : "memory");
+}
+
+// GRAD = false: pass 1 (sums + argmax); GRAD = true: pass 2 (gradient).  grid (gx, N): CTA (x, n) walks chunks x, x + gx, ... of sample n.
+template <int C, bool GRAD, int LS_STAGES, int LS_P>
+__global__ void __launch_bounds__(LS_P / 4)
+ce_dice_bulk_kernel(const float *__restrict__ logits, const long long *__restrict__ labels, int N, long long HW,
+                    const float *__restrict__ cw, int ignore_index, float grad_scale, float *__restrict__ loss_out,
+                    float *__restrict__ dlogits, unsigned char *__restrict__ pred, double *ws, unsigned int *ctrl, float dice_weight) {
+  constexpr uint32_t STAGE_BYTES = (uint32_t)LS_P * (4u * C + 8u);
+  extern __shared__ __align__(128) unsigned char ls_smem[];
+  const uint32_t stage0 = ls_u32(ls_smem), bars = stage0 + LS_STAGES * STAGE_BYTES;
+  if (!GRAD) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  double *acc = nullptr;
+  if (!GRAD) acc = ws + (size_t)(ld_flip(ctrl) & 1u) * (4 * (size_t)N + 2);
+  const int n = blockIdx.y;
+  const float *zb = logits + (long long)n * C * HW;
+  const long long *lb = labels + (long long)n * HW;
+  const int nchunks = (int)((HW + LS_P - 1) / LS_P);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < LS_STAGES; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8u * i), "r"(1u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < LS_STAGES - 1; ++s) {
+      const int c = blockIdx.x + s * gridDim.x;
+      if (c < nchunks) ls_issue<C, LS_P>(bars + 8u * s, stage0 + s * STAGE_BYTES, zb, lb, HW, (long long)c * LS_P, (int)min((long long)LS_P, HW - (long long)c * LS_P));
+    }
+  }
+  const float T0 = 1e-6f, T1 = 1.0f + 1e-6f;  // one_hot(...)+eps in fp32 (dice.py:59)
+  const float L2E = 1.4426950408889634f;
+  float w[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) w[c] = cw[c];
+  float a_n = 0.f, inv_den = 0.f;
+  if (GRAD) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // pass 1 complete and flushed (the first stages are already in flight)
+    acc = ws + (size_t)((ld_flip(ctrl) ^ 1u) & 1u) * (4 * (size_t)N + 2);     // pass 1 has already flipped
+    const double Sn = __ldcg(acc + 4 * n + 1) + 1e-6;
+    const double den = __ldcg(acc + 4 * (size_t)N + 1);         // Sum over samples, written by pass 1's last block
+    a_n = (float)(-2.0 / ((double)N * Sn)) * grad_scale * dice_weight;      // dL/dp = a_n t + b_n; b_n cancels (Sum_c p_c = 1)
+    inv_den = (float)(1.0 / den) * grad_scale;
+  }
+  __syncthreads();
+  float fI = 0.f, fnum = 0.f, fden = 0.f;
+  long long npx_mine = 0;
+  int it = 0;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+    const int s = it % LS_STAGES;
+    if (threadIdx.x == 0) {
+      const int cn = c + (LS_STAGES - 1) * gridDim.x;
+      if (cn < nchunks) {
+        const int sn = (it + LS_STAGES - 1) % LS_STAGES;
+        ls_issue<C, LS_P>(bars + 8u * sn, stage0 + sn * STAGE_BYTES, zb, lb, HW, (long long)cn * LS_P, (int)min((long long)LS_P, HW - (long long)cn * LS_P));
+      }
+    }
+    ls_wait(bars + 8u * s, (uint32_t)((it / LS_STAGES) & 1));
+    const unsigned char *st = ls_smem + (size_t)s * STAGE_BYTES;
+    const long long p0 = (long long)c * LS_P;
+    const int npx = (int)min((long long)LS_P, HW - p0);
+    const int q = threadIdx.x * 4;
+    if (q < npx) {
+      float zz[C][4]; long long yy[4];
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc) {
+        const float4 t = *reinterpret_cast<const float4 *>(st + ((size_t)cc * LS_P + q) * 4);
+        zz[cc][0] = t.x; zz[cc][1] = t.y; zz[cc][2] = t.z; zz[cc][3] = t.w;
+      }
+      {
+        const longlong2 a = *reinterpret_cast<const longlong2 *>(st + (size_t)C * LS_P * 4 + (size_t)q * 8);
+        const longlong2 b = *reinterpret_cast<const longlong2 *>(st + (size_t)C * LS_P * 4 + (size_t)q * 8 + 16);
+        yy[0] = a.x; yy[1] = a.y; yy[2] = b.x; yy[3] = b.y;
+      }
+      unsigned char pr[4];
+      float gg[C][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int y = (int)yy[i];
+        const bool valid = (y != ignore_index);
+        const int yd = valid ? y : 0;  // dice.py:116-119: ignored pixels become class 0
+        float m = zz[0][i]; int am = 0;
+#pragma unroll
+        for (int cc = 1; cc < C; ++cc) { if (zz[cc][i] > m) { m = zz[cc][i]; am = cc; } }      // first maximum, as torch.argmax
+        float e[C], ssum = 0.f, zy = zz[0][i], ey = 0.f, wy = w[0];
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) {
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[cc]) : "f"((zz[cc][i] - m) * L2E));
+          ssum += e[cc];
+        }
+        ey = e[0];
+#pragma unroll
+        for (int cc = 1; cc < C; ++cc) if (cc == yd) { zy = zz[cc][i]; ey = e[cc]; wy = w[cc]; }
+        if (!GRAD) {
+          // Sum_c p_c t_c = T0 + p_yd and Sum_c (p_c + t_c) = 1 + (C-1) T0 + T1 (exact in real arithmetic: Sum_c p_c = 1), so the Dice
+          // sums need one probability per pixel; the CE term reuses its logarithm: log2 p_yd = (z_yd - m) log2 e - log2 Sum_c e_c.
+          float l2s; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2s) : "f"(ssum));
+          const float logp2 = (zy - m) * L2E - l2s;
+          float pyd; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pyd) : "f"(logp2));
+          fI += pyd;
+          if (valid) { fnum -= wy * logp2; fden += wy; }
+          pr[i] = (unsigned char)am;
+        } else {
+          // d_c = p_c (g_c - Sum_k g_k p_k) + wy (p_c - 1[c == y]), g_c = a_n t_c + b_n  ==>  (Sum_k p_k = 1: b_n cancels)
+          // d_c = p_c (wy - a_n p_yd) + 1[c == yd] (a_n p_c - wy),  wy = w[y] / Sum_valid w  (0 on ignored pixels)
+          const float inv = __fdividef(1.0f, ssum);
+          const float pyd = ey * inv;
+          wy = valid ? wy * inv_den : 0.f;
+          const float k_all = wy - a_n * pyd;
+#pragma unroll
+          for (int cc = 0; cc < C; ++cc) {
+            const float pc = e[cc] * inv;
+            float d = k_all * pc;
+            if (cc == yd) d += a_n * pc - wy;
+            gg[cc][i] = d;
+          }
+        }
+      }
+      if (!GRAD) {
+        npx_mine += 4;
+        if (pred != nullptr) *reinterpret_cast<uchar4 *>(pred + (long long)n * HW + p0 + q) = make_uchar4(pr[0], pr[1], pr[2], pr[3]);
+      } else {
+        float *gb = dlogits + (long long)n * C * HW + p0 + q;
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) __stcs(reinterpret_cast<float4 *>(gb + cc * HW), make_float4(gg[cc][0], gg[cc][1], gg[cc][2], gg[cc][3]));
+      }
+    }
+    __syncthreads();     // every thread is done with stage s before it is refilled in the next iteration
+  }
+  if (GRAD) return;
+  __shared__ double red[4][8];
+  __shared__ unsigned int ticket;
+  // I_n = Sum_px (T0 + p_yd), S_n = Sum_px (1 + (C-1) T0 + T1): the constants are added per pixel count in double
+  const double d0 = warp_sum_d((double)fI + (double)npx_mine * (double)T0);
+  const double d1 = warp_sum_d((double)npx_mine * (1.0 + (double)(C - 1) * (double)T0 + (double)T1));
+  const double d2 = warp_sum_d((double)fnum * 0.6931471805599453), d3 = warp_sum_d((double)fden);
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][wid] = d0; red[1][wid] = d1; red[2][wid] = d2; red[3][wid] = d3; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double sacc = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) sacc += red[threadIdx.x][i];
+    atomicAdd(acc + 4 * n + threadIdx.x, sacc);       // per-sample slots {I, S, ce_num, ce_den}: gridDim.x adds per address
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) ticket = atomicAdd(ctrl, 1u);
+  __syncthreads();
+  // ---- loss value: one warp of the LAST block to finish (every other block's sums are visible: fence + atomic ticket) ----
+  if (ticket == gridDim.x * gridDim.y - 1 && threadIdx.x < 32) {
+    __threadfence();
+    double dice = 0.0, num = 0.0, den = 0.0;
+    for (int i = threadIdx.x; i < N; i += 32) {
+      const double I = __ldcg(acc + 4 * i), S = __ldcg(acc + 4 * i + 1);
+      dice += 1.0 - 2.0 * I / (S + 1e-6);
+      num += __ldcg(acc + 4 * i + 2); den += __ldcg(acc + 4 * i + 3);
+    }
+    dice = warp_sum_d(dice); num = warp_sum_d(num); den = warp_sum_d(den);
+    if (threadIdx.x == 0) {
+      dice /= (double)N;
+      acc[4 * (size_t)N] = num; acc[4 * (size_t)N + 1] = den;     // totals for the gradient pass
+      const double cel = num / den;                    // NaN when every pixel is ignored (as torch)
+      loss_out[0] = (float)((double)dice_weight * dice + cel); loss_out[1] = (float)dice; loss_out[2] = (float)cel;
+    }
+    finish_workspace(ws, ctrl, N);
+  }
+}
+
+template <int C, int LS_STAGES, int LS_P>
+static int launch_bulk(cudaLaunchConfig_t &cfg, const float *logits, const long long *lab, int N, int64_t HW, const float *cw, int ignore_index,
+                       float grad_scale, float *loss_out, float *dlogits, uint8_t *pred, double *acc, unsigned int *counter, float dice_weight,
+                       cudaStream_t st) {   // acc = base of the two halves, counter = ctrl
+  constexpr size_t smem = (size_t)LS_STAGES * LS_P * (4 * C + 8) + 64;
+  constexpr int TH = LS_P / 4;
+  static bool attr_set = false;
+  cudaError_t e;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(ce_dice_bulk_kernel<C, false, LS_STAGES, LS_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(ce_dice_bulk_kernel<C, true, LS_STAGES, LS_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  int per_sm = (int)((227 * 1024) / (smem + 1024)); if (per_sm * TH > 2048) per_sm = 2048 / TH;
+  const int nchunks = (int)((HW + LS_P - 1) / LS_P);
+  int gx = (kNumSMs * per_sm) / N; if (gx < 1) gx = 1; if (gx > nchunks) gx = nchunks;
+  if (g_opt.loss_chunks > 0) gx = g_opt.loss_chunks;
+  ce_dice_bulk_kernel<C, false, LS_STAGES, LS_P><<<dim3(gx, N), TH, smem, st>>>(logits, lab, N, (long long)HW, cw, ignore_index, grad_scale, loss_out,
+                                                                                  dlogits, pred, acc, counter, dice_weight);
+  e = cudaGetLastError();
+  if (e != cudaSuccess || dlogits == nullptr) return (int)e;
+  cfg.gridDim = dim3(gx, N); cfg.blockDim = dim3(TH); cfg.dynamicSmemBytes = smem;
+  e = cudaLaunchKernelEx(&cfg, ce_dice_bulk_kernel<C, true, LS_STAGES, LS_P>, logits, lab, N, (long long)HW, cw, ignore_index, grad_scale, loss_out,
+                         dlogits, (unsigned char *)pred, acc, counter, dice_weight);
+  return (int)e;
+}
+
 template <int C, int VEC>
 static int launch_ce_dice(const float *logits, const int64_t *labels, int N, int64_t HW,
                           const float *cw, int ignore_index, float grad_scale, float *loss_out,
                           float *dlogits, uint8_t *pred, void *workspace, cudaStream_t st, float dice_weight) {
   // Two plain launches (no cooperative grid, no software grid barrier: the kernel boundary is the barrier, and with the
-  // programmatic-dependent-launch attribute the gradient pass is resident and has its first loads in flight when pass 1 drains).
-  // grid: ~8 CTAs of 256 threads per SM, at least 1024 pixels per CTA.
-  int chunks = (kNumSMs * 8 + N - 1) / N; if (chunks < 1) chunks = 1;
-  long long maxchunks = (HW + 1023) / 1024; if (chunks > maxchunks) chunks = (int)maxchunks;
-  if (chunks < 1) chunks = 1;
-  if (g_opt.loss_chunks > 0) chunks = g_opt.loss_chunks;
-  const int64_t ws_bytes = ks_ce_dice_workspace_bytes(N);
-  cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)ws_bytes, st);
-  if (e != cudaSuccess) return (int)e;
-  double *acc = (double *)workspace; double *ce = acc + 2 * (size_t)N;
-  unsigned int *counter = (unsigned int *)(ce + 2);
+  // programmatic-dependent-launch attribute the gradient pass is resident and has its first stages in flight when pass 1 drains).
+  cudaError_t e = cudaSuccess;
+  unsigned int *counter = (unsigned int *)workspace;                 // ctrl[0] ticket counter, ctrl[1] flip
+  double *acc = (double *)((char *)workspace + 16);                  // two halves of (4 N + 2) doubles
   const long long *lab = (const long long *)labels;
-  ce_dice_reduce_kernel<C, VEC><<<dim3(chunks, N), 256, 0, st>>>(logits, lab, N, (long long)HW, cw, ignore_index, loss_out, pred, acc, ce,
-                                                                  counter, dice_weight);
-  e = cudaGetLastError();
-  if (e != cudaSuccess || dlogits == nullptr) return (int)e;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(chunks, N); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cfg.blockDim = dim3(256); cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = g_opt.loss_no_pdl ? 0 : 1;
+  if (VEC == 4 && !g_opt.loss_no_bulk) {
+    const int rc = ((g_opt.loss_variant & 15) == 1) ? launch_bulk<C, 6, 512>(cfg, logits, lab, N, HW, cw, ignore_index, grad_scale, loss_out, dlogits, pred, acc, counter, dice_weight, st)
+                 : ((g_opt.loss_variant & 15) == 2) ? launch_bulk<C, 4, 1024>(cfg, logits, lab, N, HW, cw, ignore_index, grad_scale, loss_out, dlogits, pred, acc, counter, dice_weight, st)
+                 : ((g_opt.loss_variant & 15) == 3) ? launch_bulk<C, 8, 256>(cfg, logits, lab, N, HW, cw, ignore_index, grad_scale, loss_out, dlogits, pred, acc, counter, dice_weight, st)
+                 : launch_bulk<C, 3, 1024>(cfg, logits, lab, N, HW, cw, ignore_index, grad_scale, loss_out, dlogits, pred, acc, counter, dice_weight, st);
+    return rc;
+  }
+  // register-staged kernels: HW not a multiple of 4 (ragged shapes), or A/B comparisons
+  int chunks = (kNumSMs * 8 + N - 1) / N; if (chunks < 1) chunks = 1;
+  long long maxchunks = (HW + 1023) / 1024; if (chunks > maxchunks) chunks = (int)maxchunks;
+  if (chunks < 1) chunks = 1;
+  if (g_opt.loss_chunks > 0) chunks = g_opt.loss_chunks;
+  ce_dice_reduce_kernel<C, VEC><<<dim3(chunks, N), 256, 0, st>>>(logits, lab, N, (long long)HW, cw, ignore_index, loss_out, pred, acc,
+                                                                  counter, dice_weight);
+  e = cudaGetLastError();
+  if (e != cudaSuccess || dlogits == nullptr) return (int)e;
+  cfg.gridDim = dim3(chunks, N); cfg.dynamicSmemBytes = 0;
   e = cudaLaunchKernelEx(&cfg, ce_dice_grad_kernel<C, VEC>, logits, lab, N, (long long)HW, cw, ignore_index, grad_scale, dlogits,
-                         (const double *)acc, (const double *)ce, dice_weight);
+                         (const double *)acc, (const unsigned int *)counter, dice_weight);
   return (int)e;
 }
 
 }  // namespace ks
 
 extern "C" int64_t ks_ce_dice_workspace_bytes(int N) {
-  return (int64_t)((2 * (int64_t)N + 2) * 8 + 64);
+  return (int64_t)(16 + 2 * (4 * (int64_t)N + 2) * 8);   // ctrl[4] + two halves of [N][4] doubles {I_n, S_n, ce_num_n, ce_den_n} + 2 totals
 }
 
 extern "C" int ks_ce_dice_fwd_bwd_ex(const float *logits, const int64_t *labels, int N, int C, int64_t HW,

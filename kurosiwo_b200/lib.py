@@ -492,7 +492,7 @@ class CudaOps:
     # -- loss --------------------------------------------------------------------------------
     def ce_dice_workspace(self, N: int, device) -> torch.Tensor:
         nbytes = int(self.lib.ks_ce_dice_workspace_bytes(C.c_int(N)))
-        return torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
+        return torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=device)   # zero-filled ONCE; every call leaves it clean
 
     def ce_dice(self, logits, labels, class_weights, ignore_index, grad_scale, loss_out, dlogits, pred, workspace, dice_weight=1.0):
         N, K = logits.shape[0], logits.shape[1]
