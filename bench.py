@@ -342,12 +342,14 @@ def conv_roofline(eng, dev_inputs, pk, pk_kind):
         return wrapper
 
     ops.conv2d, ops.conv2d_wgrad = timed(orig_conv, "conv"), timed(orig_wgrad, "wgrad")
+    eng._skip_comm = True                  # this leg runs on rank 0 only: no collective may be issued (bucket hooks included)
     try:
-        eng._fwd_loss_bwd(*dev_inputs)     # no all-reduce here: this leg runs on rank 0 only
+        eng._fwd_loss_bwd(*dev_inputs)
         eng._optimizer()
         torch.cuda.synchronize()
     finally:
         ops.conv2d, ops.conv2d_wgrad = orig_conv, orig_wgrad
+        eng._skip_comm = False
     tot_fl = sum(r[5] for r in recs)
     tot_ms = sum(r[6].elapsed_time(r[7]) for r in recs)
     by_kind = {}
@@ -384,6 +386,8 @@ def run_ours(args):
     dev = f"cuda:{local}"
     pg = None
     if world > 1:
+        os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")      # gradient exchange over NVLink / NVSwitch peer access only
+        os.environ.setdefault("NCCL_IB_DISABLE", "1")
         dist.init_process_group("nccl", device_id=torch.device(dev))
         pg = dist.group.WORLD
     wl = WORKLOADS[args.workload]
@@ -427,8 +431,10 @@ def run_ours(args):
         eng.train_step(*dev_inputs)
     torch.cuda.synchronize()
     l0 = ops.launches
+    m0 = eng.comm_stats["messages"] if world > 1 else 0
     eng.train_step(*dev_inputs)
     calls_per_step = ops.launches - l0
+    msgs_per_step = (eng.comm_stats["messages"] - m0) if world > 1 else 0
     if use_graph:
         step = eng.capture(*dev_inputs)
     else:
@@ -457,6 +463,41 @@ def run_ours(args):
     ms_per_step = t.item() / args.steps
     value = world * bs / (ms_per_step * 1e-3)
     loss_val = float(eng.loss3[0].item())
+    # ---- gradient exchange: bytes, bus bandwidth of the isolated all-reduce, and the time it adds to the step -------------------
+    allreduce = None
+    if world > 1:
+        g = eng.params.grad
+        nbytes = 4 * g.numel()
+        for _ in range(2):
+            dist.all_reduce(g)
+        dist.barrier(); torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            dist.all_reduce(g)
+        a1.record(); torch.cuda.synchronize()
+        ta = torch.tensor([a0.elapsed_time(a1) / 5], device=dev)
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        ms_iso = ta.item()
+        # the same step WITHOUT its exchange (ranks run free): the difference is what the exchange costs the step (exposed time + skew)
+        eng._skip_comm = True
+        step_nc = eng.capture(*dev_inputs, warmup=0) if use_graph else (lambda: eng.train_step(*dev_inputs))
+        for _ in range(3):
+            step_nc()
+        dist.barrier(); torch.cuda.synchronize()
+        a0.record()
+        for _ in range(args.steps):
+            step_nc()
+        a1.record(); torch.cuda.synchronize()
+        tn = torch.tensor([a0.elapsed_time(a1) / args.steps], device=dev)
+        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+        eng._skip_comm = False
+        if use_graph:
+            step = eng.capture(*dev_inputs, warmup=0)       # back to the exchanging step for the legs below
+        allreduce = {"bytes": nbytes, "ms_isolated": ms_iso, "bus_gbs": nbytes * 2 * (world - 1) / world / (ms_iso * 1e-3) / 1e9,
+                     "ms_exposed": ms_per_step - tn.item(), "ms_per_step_without_exchange": tn.item(),
+                     "bucket_mb": eng.bucket_bytes / 2 ** 20, "overlapped_with_backward": bool(eng.overlap_comm),
+                     "messages_per_step": msgs_per_step, "transport": "NCCL all-reduce, NCCL_P2P_LEVEL=NVL (NVLink/NVSwitch only)"}
     # ---- end-to-end arm: public trainer step from pinned host buffers ---------------------------
     # stepper.step_host: two eager steps, then a CUDA-graph replay per step over static inputs; prefetch() puts the H2D copy of the
     # NEXT step's batch on a second stream.  Every step's inputs are copied from pinned host memory inside the timed region.
@@ -524,12 +565,15 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
         "gpu_launches": calls_per_step * args.steps,
         "gpu_launches_note": f"{calls_per_step} C-ABI calls per step (each >=1 kernel of libkurosiwo_b200.so)",
-        "roofline": roof, "cpu_baseline": cpu, "library_baseline": lib,
+        "roofline": roof, "cpu_baseline": cpu, "library_baseline": lib, "allreduce": allreduce,
     }
     print(json.dumps(line))
 
 
 def main():
+    if os.environ.get("KS_BENCH_WATCHDOG"):      # debugging aid: dump every thread's stack and exit if the run exceeds N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["KS_BENCH_WATCHDOG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -73,7 +73,8 @@ class TrainStepMixin:
     # ------------------------------------------------------------------------------------------
     def init_training(self, class_weights=(1.0, 1.0, 1.0), ignore_index: int = 3, lr: float = 1e-3,
                       betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, process_group=None,
-                      dice_weight: float = 1.0, optimizer: str = "adam", momentum: float = 0.0):
+                      dice_weight: float = 1.0, optimizer: str = "adam", momentum: float = 0.0,
+                      bucket_mb: float = 32.0, overlap_comm: bool = True):
         dev = self.device
         self.params.ensure(dev)
         self.cw = torch.tensor(class_weights, dtype=torch.float32, device=dev)
@@ -103,6 +104,12 @@ class TrainStepMixin:
                 if hasattr(self, attr) and not getattr(self, "_seed_rank_mixed", False):
                     setattr(self, attr, (int(getattr(self, attr)) + 0x9E3779B1 * rank) & 0x7FFFFFFF)
             self._seed_rank_mixed = True
+        # bucketed gradient all-reduce overlapped with the rest of the backward (see _grads_ready)
+        self.bucket_bytes = int(bucket_mb * 2 ** 20)
+        self.overlap_comm = bool(overlap_comm) and self.world > 1
+        self._ready, self._ready_bytes, self._reduced, self._comm_done, self._cap = [], 0, [], [], None
+        self.comm_stream = torch.cuda.Stream(device=dev) if (self.world > 1 and torch.device(dev).type == "cuda") else None
+        self.comm_stats = {"messages": 0, "bytes": 0}
         self.graph = None
 
     def adopt_training_state(self, old) -> bool:
@@ -125,10 +132,125 @@ class TrainStepMixin:
         self.ops.ce_dice(logits, mask, self.cw, self.ignore_index, 1.0, self.loss3, self.dlogits, self.pred, self.loss_ws, self.dice_weight)
         self.backward(self.dlogits)
 
+    # ------------------------------------------------------------------------------------------
+    # Data-parallel gradient exchange: NCCL all-reduce (sum; the optimizer applies 1/world) of the flat fp32
+    # gradient buffer, in BUCKETS issued on a side stream as soon as a range of the buffer is final, so that the transfer overlaps
+    # the rest of the backward.  Engines call _grads_ready(lo, hi) when flat-gradient elements [lo, hi) will not be written again
+    # in this step (ViT: after each transformer block's backward; the head first); whatever was never announced goes out in one last
+    # message after the backward.  Under CUDA-graph capture every bucket boundary ends one graph segment and starts the next: a
+    # replayed step is graph | all-reduce (side stream) | graph | ... and the GPU runs bucket k's all-reduce under segment k+1.
+    # ------------------------------------------------------------------------------------------
+    def _grads_ready(self, lo: int, hi: int):
+        if self.world == 1 or not self.overlap_comm or hi <= lo or getattr(self, "_skip_comm", False):
+            return
+        self._ready.append((int(lo), int(hi)))
+        self._ready_bytes += 4 * (hi - lo)
+        if self._ready_bytes >= self.bucket_bytes:
+            self._flush_ready()
+
+    @staticmethod
+    def _merge(ranges):
+        out = []
+        for lo, hi in sorted(ranges):
+            if out and lo <= out[-1][1]:
+                out[-1] = (out[-1][0], max(out[-1][1], hi))
+            else:
+                out.append((lo, hi))
+        return out
+
+    def _flush_ready(self):
+        if not self._ready:
+            return
+        ranges = self._merge(self._ready)
+        self._ready, self._ready_bytes = [], 0
+        self._reduced += ranges
+        if self._cap is not None:
+            self._segment_break(ranges)
+        else:
+            self._launch_allreduce(ranges)
+
+    def _launch_allreduce(self, ranges):
+        import torch.distributed as dist
+        g = self.params.grad
+        self.comm_stats["messages"] += len(ranges)
+        self.comm_stats["bytes"] += sum(4 * (hi - lo) for lo, hi in ranges)
+        if self.comm_stream is None:                       # CPU tensors (gloo, host-logic tests): synchronous
+            for lo, hi in ranges:
+                dist.all_reduce(g[lo:hi], group=self.pg)
+            return
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            for lo, hi in ranges:
+                dist.all_reduce(g[lo:hi], group=self.pg)   # NCCL over NVLink / NVSwitch
+            done = torch.cuda.Event()
+            done.record(self.comm_stream)
+        self._comm_done.append(done)
+
+    def _wait_comm(self):
+        main = torch.cuda.current_stream() if self.comm_stream is not None else None
+        for ev in self._comm_done:
+            main.wait_event(ev)
+        self._comm_done = []
+
     def _allreduce(self):
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.params.grad, group=self.pg)   # NCCL over NVLink: ONE message = all gradients
+        """After the backward: everything not yet announced goes out, then the compute stream waits for all buckets."""
+        if self.world == 1:
+            return
+        if getattr(self, "_skip_comm", False):             # bench.py: the step without its exchange (exposed-time measurement)
+            self._ready, self._ready_bytes, self._reduced = [], 0, []
+            return
+        done = self._merge(self._reduced + self._ready)
+        rest, pos = [], 0
+        for lo, hi in done:
+            if lo > pos:
+                rest.append((pos, lo))
+            pos = max(pos, hi)
+        if pos < self.params.numel:
+            rest.append((pos, self.params.numel))
+        self._ready += rest
+        self._flush_ready()
+        self._reduced = []
+        if self._cap is None:
+            self._wait_comm()
+
+    # -- segmented CUDA-graph capture (data parallel) -------------------------------------------------
+    def _segment_begin(self):
+        g = torch.cuda.CUDAGraph()
+        g.capture_begin(pool=self._cap["pool"], capture_error_mode="thread_local")
+        self._cap["g"] = g
+
+    def _segment_break(self, ranges):
+        self._cap["g"].capture_end()
+        self._cap["segs"].append(("graph", self._cap["g"]))
+        self._cap["segs"].append(("comm", ranges))
+        self._segment_begin()
+
+    def _capture_segments(self, fn):
+        """Capture fn() (forward + loss + backward + _allreduce) as graph segments separated by the bucket all-reduces."""
+        self._cap = {"pool": torch.cuda.graph_pool_handle(), "segs": [], "g": None}
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        try:
+            with torch.cuda.stream(s):
+                self._segment_begin()
+                fn()
+                self._cap["g"].capture_end()
+                self._cap["segs"].append(("graph", self._cap["g"]))
+        finally:
+            segs, self._cap = self._cap["segs"], None
+        torch.cuda.current_stream().wait_stream(s)
+        return segs
+
+    def _replay_segments(self, segs):
+        for kind, x in segs:
+            if kind == "graph":
+                x.replay()
+            else:
+                self._launch_allreduce(x)
+        self._wait_comm()
 
     def _optimizer(self):
         hp = self.hp
@@ -177,29 +299,24 @@ class TrainStepMixin:
                 ga.replay()
                 self._optimizer()
             self.replay = replay
-        elif not optimizer_in_graph:
-            ga = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ga, capture_error_mode="thread_local"):
-                self._fwd_loss_bwd(*args)
-            self.graph = ga
-
-            def replay():
-                ga.replay()
-                self._allreduce()
-                self._optimizer()
-            self.replay = replay
         else:
-            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            # thread_local: NCCL's watchdog thread may issue CUDA calls while this thread captures
-            with torch.cuda.graph(ga, capture_error_mode="thread_local"):
+            # data parallel: graph segments split at the bucket boundaries, NCCL launched between them on the side stream
+            def body():
                 self._fwd_loss_bwd(*args)
-            with torch.cuda.graph(gb, capture_error_mode="thread_local"):
-                self._optimizer()
-            self.graph = (ga, gb)
+                self._allreduce()
+            segs = self._capture_segments(body)
+            self.graph = segs
+            gb = None
+            if optimizer_in_graph:
+                gb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gb, capture_error_mode="thread_local"):
+                    self._optimizer()
 
             def replay():
-                ga.replay()
-                self._allreduce()
-                gb.replay()
+                self._replay_segments(segs)
+                if gb is not None:
+                    gb.replay()
+                else:
+                    self._optimizer()
             self.replay = replay
         return self.replay

@@ -206,12 +206,25 @@ class ViTSegEngine(TrainStepMixin):
     def backward(self, dlogits: torch.Tensor):
         self.ops.zero_(self.params.grad)        # LayerNorm / attention parameter gradients are accumulated with atomics
         self._head_backward(dlogits)            # leaves d(tokens) in self.dxn (all rows; 0 for the cls / padding rows)
+        self.ops.permute_cast_table(self._tables()[1])      # packed head gradients -> flat gradient: the head's slice is final now
+        self._grads_ready(self._head_lo(), self.params.numel)
         if getattr(self, "freeze_encoder", False):
             # linear_eval (models/model_utilities.py:160-161: encoder parameters have requires_grad=False): no encoder data- or
             # weight-gradient is computed at all; the encoder slices of the flat gradient stay zero, so Adam leaves them untouched
-            self.ops.permute_cast_table(self._tables()[1])
             return
         self._encoder_backward()
+
+    def _head_lo(self) -> int:
+        """First flat-gradient element that belongs to the head (parameters registered after the encoder's)."""
+        offs = self.params.offsets
+        head = min((off for n, (off, _) in offs.items() if not n.startswith(self.pre)), default=self.params.numel)
+        enc_end = max((off + shape.numel() for n, (off, shape) in offs.items() if n.startswith(self.pre)), default=0)
+        return head if enc_end <= head else self.params.numel       # head registered before the encoder: no early head bucket
+
+    def _block_range(self, bi: int):
+        lo = self.params.offsets[f"{self.blocks[bi].pa}.norm.weight"][0]
+        hi = self.params.offsets[f"{self.blocks[bi + 1].pa}.norm.weight"][0] if bi + 1 < self.depth else self._head_lo()
+        return lo, hi
 
     def _inject(self, bi: int):
         """Hook: add gradients that enter the residual stream AFTER block `bi` (multi-level heads); none for the linear head."""
@@ -240,12 +253,12 @@ class ViTSegEngine(TrainStepMixin):
             ops.attention_bwd(B, self.T, self.Tp, self.heads, self.dh, b.qkv, b.probs, self.datt, self.scale, self.dqkv, self.ds)
             self._linear_bwd(b.xn1, f"{b.pa}.to_qkv", self.dqkv, self.dxn, False)
             ops.layernorm_bwd(self.dxn, b.xa, b.m1, b.r1, P.p(f"{b.pa}.norm.weight"), self.dx, True, P.g(f"{b.pa}.norm.weight"), P.g(f"{b.pa}.norm.bias"))
+            self._grads_ready(*self._block_range(bi))       # this block's parameter gradients are final: its bucket may leave
         pe = f"{pre}to_patch_embedding"
         ops.vit_assemble_bwd(B, self.T, self.Tp, self.dx, self.dxn, P.g(f"{pre}cls_token"), P.g(f"{pre}pos_embedding"))
         ops.layernorm_bwd(self.dxn, self.e1, self.me, self.re, P.p(f"{pe}.3.weight"), self.de1, False, P.g(f"{pe}.3.weight"), P.g(f"{pe}.3.bias"))
         self._linear_bwd(self.a0, f"{pe}.2", self.de1, self.da0, True)
         ops.patchify_ln_bwd(self._img, self.Tp, self.mp, self.rp, self.da0, P.g(f"{pe}.1.weight"), P.g(f"{pe}.1.bias"))
-        ops.permute_cast_table(self._tables()[1])
 
     def grid_view(self, t: torch.Tensor) -> View:
         """The patch tokens (cls dropped) of a [R, C] token matrix as the NHWC map [B, G, G, C] - a strided view, no copy."""

@@ -311,3 +311,57 @@ def test_best_checkpoint_has_the_reference_keys(tmp_path):
     det = cdt.LAST_EVAL["Validation"]
     assert det["zones"] and det["aoi"] and "water_fscore" in det
     assert sum(det["samples_per_zone"].values()) == 4
+
+
+def _ddp_vit_worker(rank, world, port, ret, bucket_mb):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from kurosiwo_b200.vision_transformer import FinetunerSegmentation, ViT
+    from oracle import vit_oracle
+    dim, depth, heads, mlp = 64, 3, 2, 128
+    sd_np = vit_oracle.make_state(5, dim, depth, heads, mlp)
+    enc = ViT(image_size=224, patch_size=16, num_classes=3, dim=dim, depth=depth, heads=heads, mlp_dim=mlp, channels=6, precision="fp32")
+    model = FinetunerSegmentation(encoder=enc, configs={"mlp": False, "decoder": False, "num_classes": 3, "finetuning_patch_size": 16})
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd_np.items()})
+    model.set_ops(ShadowOps())
+    img, mask = (torch.from_numpy(a) for a in vit_oracle.make_batch(5 + rank, 1))
+    eng = model.engine(img)
+    eng.init_training(lr=1e-3, process_group=dist.group.WORLD, bucket_mb=bucket_mb)
+    eng._fwd_loss_bwd(img, mask)
+    local = eng.params.grad.clone()              # NOT yet complete: buckets announced during the backward are already reduced
+    eng._allreduce()
+    ret[rank] = (eng.params.grad.clone(), dict(eng.comm_stats), local)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bucket_mb", [0.05, 1e9])
+def test_bucketed_allreduce_gloo_world2(bucket_mb):
+    """The bucketed exchange (buckets announced block by block during the ViT backward; the rest after it) must give every rank the
+    SUM of the ranks' gradients, whatever the bucket size - against the oracle's per-rank gradients."""
+    from oracle import vit_oracle
+    world, port = 2, 29633 + (0 if bucket_mb < 1 else 1)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ddp_vit_worker, args=(world, port, ret, bucket_mb), nprocs=world, join=True)
+    g0, st0, _ = ret[0]
+    g1, st1, _ = ret[1]
+    assert torch.equal(g0, g1)
+    total_bytes = 4 * g0.numel()
+    assert st0["bytes"] == total_bytes                           # every element exactly once
+    assert (st0["messages"] > 2) == (bucket_mb < 1)              # small buckets: several messages; huge bucket: one (plus none)
+    dim, depth, heads, mlp = 64, 3, 2, 128
+    tot = None
+    for r in range(2):
+        sd = vit_oracle.to_torch_state(vit_oracle.make_state(5, dim, depth, heads, mlp))
+        img, mask = (torch.from_numpy(a) for a in vit_oracle.make_batch(5 + r, 1))
+        _, _, grads = vit_oracle.train_step(sd, img, mask, heads)
+        tot = grads if tot is None else {k: tot[k] + grads[k] for k in grads}
+    from kurosiwo_b200.engine_common import FlatParams
+    from kurosiwo_b200.vision_transformer import FinetunerSegmentation, ViT
+    enc = ViT(image_size=224, patch_size=16, num_classes=3, dim=dim, depth=depth, heads=heads, mlp_dim=mlp, channels=6, precision="fp32")
+    fp = FlatParams(FinetunerSegmentation(encoder=enc, configs={"mlp": False, "decoder": False, "num_classes": 3, "finetuning_patch_size": 16}))
+    for n in ("model.transformer.layers.0.0.to_qkv.weight", "model.transformer.layers.2.1.net.4.weight", "head.weight", "model.pos_embedding"):
+        off, shape = fp.offsets[n]
+        got = g0[off:off + shape.numel()].view(shape)
+        assert (got - tot[n]).abs().max().item() <= 2e-3 * tot[n].abs().max().item() + 1e-6, n
