@@ -370,6 +370,12 @@ int ks_confusion_update_grouped(const uint8_t *pred, const int64_t *labels, int 
                                 int num_classes_with_ignore, int ignore_index, const int32_t *key_a, int n_a,
                                 const int32_t *key_b, int n_b, int64_t *mat, int64_t *mat_a, int64_t *mat_b, void *stream);
 
+/* ---- input pipeline (dataset/Dataset.py:162-168 clamp + nan_to_num, :192-198 Normalize) on raw float32 SAR planes [B][C][HW];
+ * out may alias raw.  clamp_max > 0: v = NaN ? clamp_max : min(max(v, 0), clamp_max); clamp_max <= 0: NaN -> 200, +-inf -> +-FLT_MAX.
+ * Then (v - mean[c]) / std[c] with IEEE subtraction and division: bit-identical to the reference's torch ops. */
+int ks_sar_preprocess(const float *raw, float *out, int B, int C, int64_t HW, const float *mean, const float *stdv,
+                      float clamp_max, void *stream);
+
 /* ---- optimizer (torch.optim.Adam, change_detection_trainer.py:52-54) ---- */
 /* step_ptr: device int32 counter, incremented by the kernel (graph-capturable). */
 int ks_adam_step(float *p, const float *g, float *m, float *v, int64_t n,

@@ -39,11 +39,31 @@ def unpack_batch(batch, configs):
     return dict(post_event=post, mask=mask, pre_event_1=pre1, pre_event_2=pre2, dem=dem, clz=clz, activ=activ)
 
 
+_PRE = {}
+
+
+def preprocess_raw(x, configs):
+    """`raw_input: true` (additive key): the loader yields RAW float32 SAR tiles (what cv.imread returns, dataset/Dataset.py:720-760)
+    and the reference's per-sample CPU transform - clamp to [0, clamp_input], nan_to_num, Normalize(data_mean, data_std)
+    (dataset/Dataset.py:162-168, :192-198) - runs as ONE kernel on the device copy, in place."""
+    if not configs.get("raw_input") or not x.is_cuda:
+        return x
+    from .lib import default_ops
+    key = (str(x.device), tuple(configs.get("data_mean", ())), tuple(configs.get("data_std", ())))
+    if key not in _PRE:
+        _PRE[key] = (torch.tensor(configs["data_mean"], dtype=torch.float32, device=x.device),
+                     torch.tensor(configs["data_std"], dtype=torch.float32, device=x.device))
+    mean, std = _PRE[key]
+    x = x.contiguous()
+    default_ops().sar_preprocess(x, x, mean, std, configs.get("clamp_input") or 0.0)
+    return x
+
+
 def select_inputs(b, configs, device):
     """change_detection_trainer.py:117-133: the two images in `configs['inputs']` order (+DEM channel)."""
     outs = []
     for name in configs["inputs"]:
-        x = b[name].to(device, non_blocking=True)
+        x = preprocess_raw(b[name].to(device, non_blocking=True), configs)
         if configs.get("dem"):
             x = torch.cat((x, b["dem"].to(device, non_blocking=True)), dim=1)
         outs.append(x)

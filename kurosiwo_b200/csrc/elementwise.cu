@@ -862,3 +862,42 @@ extern "C" int ks_adamw_step(float *p, const float *g, float *m, float *v, int64
   ks::incr_kernel<<<1, 1, 0, st>>>(step_ptr);
   KS_LAUNCH_RET();
 }
+
+// ---- input pipeline on the GPU ------------------------------------------------------------
+// dataset/Dataset.py:162-168 (clamp to [0, clamp_input] and nan_to_num(nan = clamp_input); without clamp_input nan_to_num(nan = 200))
+// followed by :192-198 (torchvision Normalize(data_mean, data_std): (x - mean_c) / std_c), on the raw float32 SAR planes
+// [B][C][HW] AFTER the host->device copy - so the host loop only reads files, and the pinned copy carries raw tiles.
+namespace ks {
+__global__ void __launch_bounds__(256)
+sar_preprocess_kernel(const float *__restrict__ raw, float *__restrict__ out, long long HW, int C, long long total4, long long total,
+                      const float *__restrict__ mean, const float *__restrict__ stdv, float clamp_max) {
+  auto tr = [&](float v, float m, float s) {
+    if (clamp_max > 0.f) v = (v != v) ? clamp_max : fminf(fmaxf(v, 0.f), clamp_max);       // torch.clamp propagates NaN, nan_to_num maps it
+    else v = (v != v) ? 200.f : (isinf(v) ? (v > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f) : v);
+    return __fdiv_rn(__fsub_rn(v, m), s);                                                  // Normalize: sub then div, both IEEE (bit-exact)
+  };
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(((i * 4) / HW) % C);                                               // HW % 4 == 0 on this path: one channel per float4
+    const float m = __ldg(mean + c), s = __ldg(stdv + c);
+    float4 v = __ldcs(reinterpret_cast<const float4 *>(raw) + i);
+    v.x = tr(v.x, m, s); v.y = tr(v.y, m, s); v.z = tr(v.z, m, s); v.w = tr(v.w, m, s);
+    reinterpret_cast<float4 *>(out)[i] = v;
+  }
+  if (total4 == 0)
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const int c = (int)((i / HW) % C);
+      out[i] = tr(raw[i], __ldg(mean + c), __ldg(stdv + c));
+    }
+}
+}  // namespace ks
+
+extern "C" int ks_sar_preprocess(const float *raw, float *out, int B, int C, int64_t HW, const float *mean, const float *stdv,
+                                 float clamp_max, void *stream) {
+  KS_CHECK_ARG(raw && out && mean && stdv && B > 0 && C > 0 && HW > 0);
+  const long long total = (long long)B * C * HW;
+  const bool vec = (HW % 4 == 0) && (((uintptr_t)raw | (uintptr_t)out) % 16 == 0);
+  const long long total4 = vec ? total / 4 : 0;
+  const int grid = ks::ew_grid(vec ? total4 : total, 256);
+  ks::sar_preprocess_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(raw, out, (long long)HW, C, total4, total, mean, stdv, clamp_max);
+  KS_LAUNCH_RET();
+}

@@ -94,7 +94,7 @@ EXPORTED_SYMBOLS = [
     "ks_ecam_bwd_apply", "ks_ce_dice_workspace_bytes", "ks_ce_dice_fwd_bwd", "ks_ce_dice_fwd_bwd_ex", "ks_adam_step", "ks_adamw_step", "ks_sgd_step",
     "ks_softmax_head_fwd", "ks_softmax_head_bwd", "ks_dropout_mask", "ks_channel_scale", "ks_absdiff_fwd", "ks_absdiff_bwd",
     "ks_layernorm_fwd", "ks_layernorm_bwd", "ks_patchify_ln", "ks_patchify_ln_bwd", "ks_vit_assemble", "ks_vit_assemble_bwd",
-    "ks_confusion_update", "ks_confusion_update_grouped", "ks_attention_fwd", "ks_attention_bwd", "ks_conv2d_strided", "ks_conv2d_strided_dgrad", "ks_conv2d_strided_wgrad", "ks_im2col", "ks_col2im",
+    "ks_confusion_update", "ks_confusion_update_grouped", "ks_sar_preprocess", "ks_attention_fwd", "ks_attention_bwd", "ks_conv2d_strided", "ks_conv2d_strided_dgrad", "ks_conv2d_strided_wgrad", "ks_im2col", "ks_col2im",
     "ks_xattention_fwd", "ks_xattention_bwd", "ks_dwconv3x3_fwd", "ks_dwconv3x3_bwd", "ks_bilinear_nhwc_fwd", "ks_bilinear_nhwc_bwd",
     "ks_relu_fwd", "ks_relu_bwd", "ks_sigmoid_head_fwd", "ks_sigmoid_head_bwd", "ks_dropout_apply", "ks_branch_add", "ks_branch_scale", "ks_gelu_fwd", "ks_gelu_bwd", "ks_bilinear_up_fwd", "ks_bilinear_up_bwd", "ks_adaptive_avgpool_fwd", "ks_adaptive_avgpool_bwd",
 ]
@@ -515,6 +515,13 @@ class CudaOps:
                                                   _p(key_b), C.c_int(0 if mat_b is None else mat_b.shape[0]), _p(mat), _p(mat_a), _p(mat_b),
                                                   self._stream())
         self._check(rc, "ks_confusion_update_grouped")
+
+    def sar_preprocess(self, raw: torch.Tensor, out: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, clamp_max: float):
+        """raw / out: fp32 [B, C, H, W] contiguous (out may be raw); mean / std: fp32 [C] device tensors."""
+        B, Cn = raw.shape[0], raw.shape[1]
+        rc = self.lib.ks_sar_preprocess(_p(raw), _p(out), C.c_int(B), C.c_int(Cn), C.c_int64(raw.shape[2] * raw.shape[3]), _p(mean), _p(std),
+                                        C.c_float(clamp_max if clamp_max is not None else 0.0), self._stream())
+        self._check(rc, "ks_sar_preprocess")
 
     # -- optimizer ---------------------------------------------------------------------------
     def adam_step(self, p, g, m, v, lr, b1, b2, eps, wd, grad_scale, step):

@@ -12,7 +12,7 @@ from pathlib import Path
 
 import torch
 
-from .change_detection_trainer import CLASS_LABELS, LAST_EVAL, _rank, sync_buffers, unpack_batch
+from .change_detection_trainer import CLASS_LABELS, LAST_EVAL, _rank, preprocess_raw, sync_buffers, unpack_batch
 from .host_pipeline import HostPipelineMixin, lookahead
 from .utilities import GroupedConfusionMetrics, create_loss, init_lr_scheduler
 from .vision_transformer import FinetunerSegmentation, FloodViTUperNet
@@ -20,6 +20,10 @@ from .vision_transformer import FinetunerSegmentation, FloodViTUperNet
 
 def stack_inputs(b, configs, device):
     """segmentation_trainer.py:106-144: post_event first, then the pre-event dates named in configs['inputs'] (+ DEM)."""
+    b = dict(b)
+    for k in ("post_event", "pre_event_1", "pre_event_2"):      # raw_input: clamp / nan_to_num / Normalize on the device copy
+        if configs.get("raw_input") and b.get(k) is not None:
+            b[k] = preprocess_raw(b[k].to(device, non_blocking=True), configs)
     image = b["post_event"].to(device, non_blocking=True)
     if configs.get("dem"):
         image = torch.cat((image, b["dem"].to(device, non_blocking=True)), dim=1)

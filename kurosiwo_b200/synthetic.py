@@ -17,10 +17,15 @@ TRAIN_ACTS = (130, 470, 555, 118, 174, 324, 421, 554, 427, 518, 502, 498, 497, 4
               1111011, 1111004, 1111009, 1111010, 1111006, 1111005)
 
 
-def make_image(gen: torch.Generator, N: int, H: int, W: int, pin: bool = False) -> torch.Tensor:
+def make_image(gen: torch.Generator, N: int, H: int, W: int, pin: bool = False, raw_tiles: bool = False) -> torch.Tensor:
+    """raw_tiles: return the RAW backscatter planes (incl. a sprinkle of NaN no-data pixels, as in the GeoTIFFs) instead of the
+    clamped + normalised tensor - the input of the device-side pipeline (`raw_input: true`, ks_sar_preprocess)."""
     mean = torch.tensor(DATA_MEAN).view(1, 2, 1, 1)
     std = torch.tensor(DATA_STD).view(1, 2, 1, 1)
     raw = torch.empty(N, 2, H, W).exponential_(1.0, generator=gen) * mean
+    if raw_tiles:
+        raw[torch.rand(raw.shape, generator=gen) < 1e-3] = float("nan")
+        return raw.pin_memory() if pin else raw
     x = (raw.clamp_(0, 0.15) - mean) / std
     return x.pin_memory() if pin else x
 
@@ -30,10 +35,10 @@ def make_mask(gen: torch.Generator, N: int, H: int, W: int, pin: bool = False) -
     return m.pin_memory() if pin else m
 
 
-def make_batch(seed: int, N: int, H: int = 224, W: int = 224, pin: bool = False) -> List:
+def make_batch(seed: int, N: int, H: int = 224, W: int = 224, pin: bool = False, raw_tiles: bool = False) -> List:
     """The 12-tuple the reference trainers unpack (scale_input set, no DEM; change_detection_trainer.py:95-106)."""
     gen = torch.Generator().manual_seed(seed)
-    post, pre1, pre2 = (make_image(gen, N, H, W, pin) for _ in range(3))
+    post, pre1, pre2 = (make_image(gen, N, H, W, pin, raw_tiles) for _ in range(3))
     mask = make_mask(gen, N, H, W, pin)
     scale = [torch.full((N,), m) for m in DATA_MEAN], [torch.full((N,), s) for s in DATA_STD]
     clz = torch.randint(1, 4, (N,), generator=gen)

@@ -463,6 +463,15 @@ class ShadowOps:
         mat.view(-1).add_(torch.bincount(t[keep] * K + p[keep], minlength=K * K))
 
     # -- ChangeFormer passes ---------------------------------------------------------------------
+    def sar_preprocess(self, raw, out, mean, std, clamp_max):
+        """The reference's own ops (dataset/Dataset.py:162-168, :192-198)."""
+        img = raw.float()
+        if clamp_max:
+            img = torch.nan_to_num(torch.clamp(img, min=0.0, max=clamp_max), clamp_max)
+        else:
+            img = torch.nan_to_num(img, 200)
+        out.copy_((img - mean.view(1, -1, 1, 1)) / std.view(1, -1, 1, 1))
+
     def confusion_update_grouped(self, pred, labels, K, ignore_index, mat, key_a=None, mat_a=None, key_b=None, mat_b=None):
         for s in range(labels.shape[0]):
             one = torch.zeros(K, K, dtype=torch.int64)

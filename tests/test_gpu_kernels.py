@@ -433,3 +433,27 @@ def test_confusion_update_grouped(ops, sh):
     c = GroupedConfusionMetrics(3, 3, "cpu", activations=acts, zones=True)
     c.update(pred, lab, activ=activ, clz=clz)
     assert torch.equal(m.mat.cpu(), c.mat) and torch.equal(m.mat_aoi.cpu(), c.mat_aoi) and torch.equal(m.mat_zone.cpu(), c.mat_zone)
+
+
+def test_sar_preprocess_matches_reference_transform(ops, sh):
+    """Input pipeline on the GPU (reference dataset/Dataset.py:162-168 clamp + nan_to_num, :192-198 Normalize) - BIT-exact against
+    the reference's own torch ops on seeded raw tiles with NaN / +-inf / negative / over-range values, both clamp modes, in place."""
+    g = _gen(12)
+    mean, std = torch.tensor([0.0953, 0.0264]), torch.tensor([0.0427, 0.0215])
+    for (B, H, W) in ((3, 224, 224), (2, 7, 9)):
+        raw = torch.empty(B, 2, H, W).exponential_(1.0, generator=g) * mean.view(1, 2, 1, 1) * 2 - 0.01
+        flat = raw.view(-1)
+        idx = torch.randperm(flat.numel(), generator=g)[:64]
+        flat[idx[:24]] = float("nan"); flat[idx[24:40]] = float("inf"); flat[idx[40:56]] = float("-inf"); flat[idx[56:]] = 1e30
+        for clamp in (0.15, 0.0):
+            want = torch.empty_like(raw)
+            sh.sar_preprocess(raw, want, mean, std, clamp)
+            x = raw.clone().to(DEV)
+            ops.sar_preprocess(x, x, mean.to(DEV), std.to(DEV), clamp)
+            assert torch.equal(x.cpu(), want), (B, H, W, clamp, float((x.cpu() - want).abs().max()))
+    # through the trainer surface: raw tiles in, the same tensors the normalised loader would have produced
+    from kurosiwo_b200.change_detection_trainer import preprocess_raw
+    cfg = {"raw_input": True, "data_mean": [0.0953, 0.0264], "data_std": [0.0427, 0.0215], "clamp_input": 0.15}
+    raw = torch.empty(2, 2, 32, 32).exponential_(1.0, generator=g) * mean.view(1, 2, 1, 1)
+    want = (raw.clamp(0, 0.15) - mean.view(1, 2, 1, 1)) / std.view(1, 2, 1, 1)
+    assert torch.equal(preprocess_raw(raw.to(DEV), cfg).cpu(), want)
