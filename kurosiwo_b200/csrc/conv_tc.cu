@@ -286,8 +286,10 @@ __device__ __forceinline__ void issue_taps(uint32_t a_lo_row, uint32_t a_tile_st
   }
 }
 
-template <int BK, int KS, bool NS3>
-__global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant__ ConvTcParams p) {
+// EW = epilogue warps: 8 (320 threads, up to 2 CTAs per SM) or 16 (576 threads, ONE CTA per SM: configurations whose weights or
+// TMEM columns already pin the CTA count to one and whose epilogue - 4 sequential 32-column items per warp - paced the kernel).
+template <int BK, int KS, bool NS3, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, EW == 8 ? 2 : 1) conv_tc2_kernel(const __grid_constant__ ConvTcParams p) {
 #define MBW(bar, par) do { if (p.debug & 32) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int TW = (KS == 3) ? 14 : 16;
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
     prefetch_tmap(&p.wmap);
     for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), EW); }
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
@@ -460,7 +462,7 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
     // (window, 32-column chunk) work items.  Per item: one 32-column TMEM load, the optional += loads are
     // issued before the TMEM wait, then bias, bf16 pack, four 16-byte stores and the BN-statistics butterfly.
     const int lg = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;      // 0 .. EW/4-1: the warps of a lane group split the work items
     const int row = lg * 32 + lane;
     const int ty = row >> 4, tx = row & 15;
     const int nchunk = (BN + 31) >> 5;
@@ -472,7 +474,7 @@ __global__ void __launch_bounds__(320, 2) conv_tc2_kernel(const __grid_constant_
       tc_fence_after();
       int cur_mt = -1, n = 0, h = 0, w = 0;
       bool ok = false;
-      for (int item = half; item < ((p.debug & 8) ? 0 : nvalid * nchunk); item += 2) {
+      for (int item = half; item < ((p.debug & 8) ? 0 : nvalid * nchunk); item += EW / 4) {
         const int mt = item / nchunk, cc = (item % nchunk) << 5;
         if (mt != cur_mt) {            // window coordinates change once per MT accumulator, not per 32-column item
           cur_mt = mt;
@@ -628,15 +630,15 @@ static int launch_conv_tc(const ConvTcParams &p, dim3 grid, size_t smem, cudaStr
 
 extern "C" int ks_bn_stats(int dtype, int N, int H, int W, const ks_view_t *x, double *sums, void *stream);
 
-template <int BK, int KS, bool NS3>
+template <int BK, int KS, bool NS3, int EW>
 static int launch_conv_tc2(const ConvTcParams &p, dim3 grid, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BK, KS, NS3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BK, KS, NS3, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  conv_tc2_kernel<BK, KS, NS3><<<grid, 320, smem, st>>>(p);
+  conv_tc2_kernel<BK, KS, NS3, EW><<<grid, 64 + 32 * EW, smem, st>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -801,10 +803,16 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
   if (per_sm > (int)(512 / cols)) per_sm = (int)(512 / cols);   // tcgen05.alloc of a further CTA would block until TMEM columns free up
   int gx = (kNumSMs * per_sm) / nt; if (gx < 1) gx = 1; if (gx > p.n_super) gx = p.n_super;
   dim3 grid((unsigned)gx, (unsigned)nt);
-  if (BK == 64 && ksize == 3) rc = ns3 ? launch_conv_tc2<64, 3, true>(p, grid, smem, st) : launch_conv_tc2<64, 3, false>(p, grid, smem, st);
-  else if (BK == 64 && ksize == 1) rc = launch_conv_tc2<64, 1, false>(p, grid, smem, st);
-  else if (BK == 32 && ksize == 3) rc = ns3 ? launch_conv_tc2<32, 3, true>(p, grid, smem, st) : launch_conv_tc2<32, 3, false>(p, grid, smem, st);
-  else rc = launch_conv_tc2<32, 1, false>(p, grid, smem, st);
+  // 16 epilogue warps when only one CTA fits per SM anyway and every lane group has >= 4 work items per super-tile
+  const int items = MT * ((p.BN + 31) / 32);
+  // measured (scripts/bench_layers.py, ew8 / ew16): 32->224 dgrad 0.532 -> 0.465 ms, 32->64 0.121 -> 0.102; with two N tiles (64->384) 4 % slower
+  const bool ew16 = g_opt.ew ? (g_opt.ew == 16) : (per_sm == 1 && items >= 4 && nt == 1);
+#define KS_LAUNCH(BKv, KSv, NS3v) (ew16 ? launch_conv_tc2<BKv, KSv, NS3v, 16>(p, grid, smem, st) : launch_conv_tc2<BKv, KSv, NS3v, 8>(p, grid, smem, st))
+  if (BK == 64 && ksize == 3) rc = ns3 ? KS_LAUNCH(64, 3, true) : KS_LAUNCH(64, 3, false);
+  else if (BK == 64 && ksize == 1) rc = KS_LAUNCH(64, 1, false);
+  else if (BK == 32 && ksize == 3) rc = ns3 ? KS_LAUNCH(32, 3, true) : KS_LAUNCH(32, 3, false);
+  else rc = KS_LAUNCH(32, 1, false);
+#undef KS_LAUNCH
   return rc;
 }
 
@@ -825,6 +833,7 @@ extern "C" int ks_set_option(const char *name, int value) {
   else if (eq("tc_ns3_min_cin")) ks::g_opt.ns3_min_cin = value;   // > 0: stack column taps from this many input channels (default 96) and for N tiles up to 80
   else if (eq("tc_ns3_mode")) ks::g_opt.ns3_mode = value;         // streamed + stacked: 1 = two CTAs per SM (256 TMEM columns), 2 = one CTA per SM
   else if (eq("tc_nacc")) ks::g_opt.nacc = value;
+  else if (eq("tc_ew")) ks::g_opt.ew = value;             // epilogue warps: 0 auto, 8, 16
   else if (eq("loss_chunks")) ks::g_opt.loss_chunks = value;   // perf experiments: CTAs per sample of the CE+Dice passes
   else if (eq("loss_variant")) ks::g_opt.loss_variant = value;   // perf experiments: (stages, pixels per stage) of the bulk-staged passes
   else if (eq("loss_no_bulk")) ks::g_opt.loss_no_bulk = value;   // 1 = register-staged CE+Dice passes (A/B comparisons)

@@ -92,6 +92,8 @@ VARIANTS = {
     "nores_mt4": {"tc_no_resident": 1, "tc_mt": 4},
     "res_mt2": {"tc_mt": 2},
     "no_ns3": {"tc_no_ns3": 1},
+    "ew8": {"tc_ew": 8},
+    "ew16": {"tc_ew": 16},
     "ns3_all": {"tc_ns3_min_cin": 1},
     "ns3_two": {"tc_ns3_min_cin": 1, "tc_ns3_mode": 1},
     "ns3_one": {"tc_ns3_min_cin": 1, "tc_ns3_mode": 2},
@@ -113,7 +115,7 @@ out = {"conv": {}, "wgrad": {}}
 for name, (H, cins, couts, ks, stats) in CONV.items():
     row = {}
     for vn, opts in VARIANTS.items():
-        for o in ("tc_v1", "tc_mt", "tc_no_resident", "tc_no_ns3", "tc_ns3_min_cin", "tc_ns3_mode"):
+        for o in ("tc_v1", "tc_mt", "tc_no_resident", "tc_no_ns3", "tc_ns3_min_cin", "tc_ns3_mode", "tc_ew"):
             ops.set_option(o, opts.get(o, 0))
         try:
             fn, fl = conv_case(H, cins, couts, ks, stats and vn != "v1")
@@ -124,7 +126,7 @@ for name, (H, cins, couts, ks, stats) in CONV.items():
         torch.cuda.empty_cache()
     out["conv"][name] = row
     print(f"{name:28s}", "  ".join(f"{k}={v}" for k, v in row.items()), flush=True)
-for o in ("tc_v1", "tc_mt", "tc_no_resident", "tc_no_ns3", "tc_ns3_min_cin", "tc_ns3_mode"):
+for o in ("tc_v1", "tc_mt", "tc_no_resident", "tc_no_ns3", "tc_ns3_min_cin", "tc_ns3_mode", "tc_ew"):
     ops.set_option(o, 0)
 for name, (H, cins, couts) in WGRAD.items():
     fn, fl = wgrad_case(H, cins, couts)

@@ -79,8 +79,12 @@ def conv_case(ops, name, N, H, W, ks, src_specs, dst_specs, bias, gen):
         "v2_ns3_nores_one_cta": {"tc_ns3_min_cin": 1, "tc_no_resident": 1, "tc_ns3_mode": 2},
         "v2_ns3_nores_two_cta": {"tc_ns3_min_cin": 1, "tc_no_resident": 1, "tc_ns3_mode": 1},
         "v2_ns3_nores_mt2": {"tc_ns3_min_cin": 1, "tc_no_resident": 1, "tc_ns3_mode": 2, "tc_mt": 2},
+        # 16 epilogue warps (576 threads, one CTA per SM)
+        "v2_ew16": {"tc_ew": 16},
+        "v2_ew16_ns3": {"tc_ew": 16, "tc_ns3_min_cin": 1},
+        "v2_ew16_nores_mt4": {"tc_ew": 16, "tc_no_resident": 1, "tc_mt": 4},
     }
-    OPTS = ("tc_v1", "tc_mt", "tc_no_resident", "tc_no_ns3", "tc_ns3_min_cin", "tc_ns3_mode")
+    OPTS = ("tc_v1", "tc_mt", "tc_no_resident", "tc_no_ns3", "tc_ns3_min_cin", "tc_ns3_mode", "tc_ew")
     for key, opts in variants.items():
         for f, i0 in zip(dst_fulls, init):
             f.base.copy_(i0)

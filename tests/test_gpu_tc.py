@@ -23,7 +23,8 @@ def report():
 
 
 @pytest.mark.parametrize("variant", ["v2_auto", "v1_mt1", "v2_res_mt2", "v2_nores_mt1", "v2_nores_mt2", "v2_nores_mt4", "v2_no_ns3", "v2_no_ns3_nores",
-                                     "v2_ns3", "v2_ns3_nores_one_cta", "v2_ns3_nores_two_cta", "v2_ns3_nores_mt2"])
+                                     "v2_ns3", "v2_ns3_nores_one_cta", "v2_ns3_nores_two_cta", "v2_ns3_nores_mt2",
+                                     "v2_ew16", "v2_ew16_ns3", "v2_ew16_nores_mt4"])
 def test_conv_tc(report, variant):
     """v2_auto is what the library picks (persistent CTAs, resident weights when they fit, fused BN statistics, column taps
     stacked along N for narrow N tiles); the other variants pin the streaming / multi-window / non-persistent / one-UMMA-per-tap
