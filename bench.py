@@ -362,7 +362,7 @@ def conv_roofline(eng, dev_inputs, pk, pk_kind):
     layers = [{"kind": r[0], "cin": r[1], "cout": r[2], "h": r[3], "k": r[4], "ms": r[6].elapsed_time(r[7]),
                "tflops": r[5] / (r[6].elapsed_time(r[7]) * 1e-3) / 1e12} for r in recs]
     traffic = None      # DRAM bytes per launch of this kernel family from the committed ncu launch list (SNUNet bs=64 only)
-    tp = ROOT / "profiles" / "r1_conv_traffic.json"
+    tp = ROOT / "profiles" / "r2_conv_traffic.json"
     if tp.exists() and getattr(eng, "f", None) is not None and getattr(eng, "N", 0) == 64:
         try:
             traffic = json.loads(tp.read_text())["dram_bytes_per_launch"]

@@ -835,7 +835,6 @@ extern "C" int ks_set_option(const char *name, int value) {
   else if (eq("tc_nacc")) ks::g_opt.nacc = value;
   else if (eq("tc_ew")) ks::g_opt.ew = value;             // epilogue warps: 0 auto, 8, 16
   else if (eq("loss_chunks")) ks::g_opt.loss_chunks = value;   // perf experiments: CTAs per sample of the CE+Dice passes
-  else if (eq("loss_variant")) ks::g_opt.loss_variant = value;   // perf experiments: (stages, pixels per stage) of the bulk-staged passes
   else if (eq("loss_no_bulk")) ks::g_opt.loss_no_bulk = value;   // 1 = register-staged CE+Dice passes (A/B comparisons)
   else if (eq("loss_no_pdl")) ks::g_opt.loss_no_pdl = value;   // 1 = plain stream order between the two CE+Dice passes
   else if (eq("tc_no_ns3")) ks::g_opt.no_ns3 = value;   // 1 = one UMMA per tap also for narrow N tiles (A/B comparisons)
