@@ -42,7 +42,8 @@ def initialize_segmentation_model(config, model_configs):
     precision = "bf16" if config.get("mixed_precision", True) else "fp32"
     precision = config.get("precision", precision)
     if config.get("encoder"):
-        encoder = torch.load(config["encoder"], map_location="cpu", weights_only=False)
+        from .checkpoint_compat import from_reference_module     # a ViT pickled by the reference (its classes on PYTHONPATH) or by us
+        encoder = from_reference_module(torch.load(config["encoder"], map_location="cpu", weights_only=False), precision)
         encoder.precision = precision
     else:
         ec = dict(model_configs.get("encoder_config") or config["encoder_config"])

@@ -92,11 +92,8 @@ def load_best_checkpoint(model, configs, task):
         print(f"No best checkpoint at {path}: evaluating the current weights")
         return model
     print("Loading model from: ", str(path))
-    ckpt = torch.load(path, map_location=configs["device"], weights_only=False)
-    if isinstance(ckpt, torch.nn.Module):
-        return ckpt.to(configs["device"])
-    model.load_state_dict(ckpt["model_state_dict"] if isinstance(ckpt, dict) and "model_state_dict" in ckpt else ckpt)
-    return model
+    from kurosiwo_b200.checkpoint_compat import load_reference_checkpoint   # also accepts files written by the reference itself
+    return load_reference_checkpoint(path, model, configs["device"], getattr(model, "precision", "bf16"), configs)
 
 
 if __name__ == "__main__":

@@ -367,7 +367,94 @@ def upernet_goldens():
     print("floodvit+upernet loss", float(loss.detach()))
 
 
+def bf16_drift_goldens():
+    """How far the UNMODIFIED reference moves when it runs under torch.autocast(bfloat16) instead of fp32 - per gradient tensor, on
+    exactly the cases the bf16 GPU tests use.  The tests bound the CUDA bf16 path's gradient error by a multiple of THIS drift
+    (tests/golden/bf16_drift.npz) instead of by a free constant: the bf16 bar is pinned to the reference's own behaviour."""
+    from oracle.ref_import import install_stubs
+    install_stubs()
+    sys.path.insert(0, REF)
+    from models.changeformer import ChangeFormerV6 as RefCF
+    from models.siam_conc import SiamUnet_conc as RefConc
+    from models.snunet import SNUNet_ECAM as RefSNUNet
+    from utilities.bce_and_dice import BCEandDiceLoss as RefLoss
+    from oracle import changeformer_oracle as co
+    from oracle import siam_oracle
+    from oracle.weights import make_batch, make_state
+    torch.set_num_threads(8)
+    out = {}
+
+    def run(tag, build, sd, batch, pick_last=False):
+        grads = {}
+        for mode in ("fp32", "bf16"):
+            model = build()
+            model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+            for mod in model.modules():
+                if isinstance(mod, (torch.nn.Dropout, torch.nn.Dropout2d)):
+                    mod.p = 0.0
+                if type(mod).__name__ == "DropPath":
+                    mod.drop_prob = 0.0
+            if hasattr(model, "do11"):                       # FC-Siam: functional dropout2d objects
+                for k_, v_ in vars(model)["_modules"].items():
+                    if k_.startswith("do"):
+                        v_.p = 0.0
+            model.train()
+            crit = RefLoss(weights=torch.tensor([1.0, 1.0, 1.0]), ignore_index=3, use_softmax=True)
+            x1, x2, mask = (torch.from_numpy(a) for a in batch)
+            with torch.autocast("cpu", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+                o = model(x1, x2)
+                o = o[-1] if pick_last else o
+            loss = crit(o.float(), mask)
+            loss.backward()
+            grads[mode] = {k: p.grad.detach().double().clone() for k, p in model.named_parameters() if p.grad is not None}
+            out[f"{tag}.loss.{mode}"] = float(loss.detach())
+            out[f"{tag}.out_rel_l2"] = 0.0
+            if mode == "fp32":
+                ref_out = o.detach().double()
+            else:
+                out[f"{tag}.out_rel_l2"] = float((o.detach().double() - ref_out).norm() / ref_out.norm())
+        names, drift = [], []
+        for k, g in grads["fp32"].items():
+            names.append(k)
+            drift.append(float((grads["bf16"][k] - g).norm() / (g.norm() + 1e-300)))
+        out[f"{tag}.names"] = np.array(names)
+        out[f"{tag}.drift"] = np.array(drift, np.float64)
+        print(tag, "out rel-L2", out[f"{tag}.out_rel_l2"], "max drift", max(drift), "median", float(np.median(drift)))
+
+    run("snunet_b32_n2_s64_seed21", lambda: RefSNUNet(2, 3, base_channel=32), make_state(21, 2, 3, 32), make_batch(21, 2, 64, 64))
+    from models.siam_diff import SiamUnet_diff as RefDiff
+    run("siam_conc_n2_s64_seed33", lambda: RefConc(2, 3), siam_oracle.make_state(33, 2, 3, "conc"), make_batch(33, 2, 64, 64))
+    run("siam_diff_n2_s64_seed33", lambda: RefDiff(2, 3), siam_oracle.make_state(33, 2, 3, "diff"), make_batch(33, 2, 64, 64))
+    run("changeformer_n2_s224_seed91", lambda: RefCF(embed_dim=256, input_nc=2, output_nc=3, decoder_softmax=True), co.make_state(91),
+        make_batch(91, 2, 224, 224), pick_last=True)
+    # ViT-B/16 (768 / 12 / 12 / 3072, 6 channels: the BASELINE.json encoder), N = 2: single-input model
+    from models.model_utilities import FinetunerSegmentation as RefFinetuner
+    from models.vision_transformer import ViT as RefViT
+    from oracle import vit_oracle
+
+    class _Seg(torch.nn.Module):                              # adapter: run(...) feeds (x1, x2); the ViT takes one stacked image
+        def __init__(self):
+            super().__init__()
+            enc = RefViT(image_size=224, patch_size=16, num_classes=3, dim=768, depth=12, heads=12, mlp_dim=3072, channels=6)
+            self.m = RefFinetuner(encoder=enc, configs={"mlp": False, "decoder": False, "num_classes": 3, "finetuning_patch_size": 16})
+
+        def forward(self, img, _unused):
+            return self.m(img)
+
+        def load_state_dict(self, sd, **kw):
+            return self.m.load_state_dict(sd, **kw)
+
+        def named_parameters(self, *a, **k):
+            return self.m.named_parameters(*a, **k)
+    img, mask = vit_oracle.make_batch(71, 2)
+    run("floodvit_b_n2_seed71", _Seg, vit_oracle.make_state(71, 768, 12, 12, 3072), (img, img[:, :1], mask))
+    np.savez_compressed(OUT / "bf16_drift.npz", **out)
+
+
 if __name__ == "__main__":
+    if "--bf16-drift-only" in sys.argv:
+        bf16_drift_goldens()
+        sys.exit(0)
     if "--upernet-only" in sys.argv:
         upernet_goldens()
         sys.exit(0)

@@ -16,6 +16,19 @@ def rand_view(N, H, W, C, dtype, device, ctot=None, c0=0, scale=1.0, gen=None):
     return full.ch(c0, C), full
 
 
+def bf16_drift(case: str) -> dict:
+    """{parameter name: rel-L2 distance between the UNMODIFIED reference's gradient under torch.autocast(bfloat16) and its fp32
+    gradient} for one of the cases of tests/golden/bf16_drift.npz (oracle/make_golden.py --bf16-drift-only).  The bf16 tests
+    bound the CUDA path's gradient error by DRIFT_FACTOR x this drift + DRIFT_FLOOR: the bar is the reference's own bf16 behaviour."""
+    import numpy as np
+    from pathlib import Path
+    d = np.load(Path(__file__).parent / "golden" / "bf16_drift.npz")
+    return dict(zip([str(s) for s in d[f"{case}.names"]], [float(v) for v in d[f"{case}.drift"]]))
+
+
+DRIFT_FACTOR, DRIFT_FLOOR = 1.5, 0.02
+
+
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a, b = a.double().cpu(), b.double().cpu()
     return float((a - b).norm() / (b.norm() + 1e-30))

@@ -127,12 +127,15 @@ def test_bf16_close_to_oracle(impl):
     assert rel < 5e-2 and agree > 0.97
     assert abs(loss3[0].item() - float(loss_o)) < 3e-2 * abs(float(loss_o))
     # gradients of the largest tensors (before the Adam update they sit in the flat gradient buffer)
+    # bar = 1.5 x the REFERENCE's own fp32 -> autocast(bf16) gradient drift on this very case (tests/golden/bf16_drift.npz) + 0.02
+    from gpu_util import DRIFT_FACTOR, DRIFT_FLOOR, bf16_drift
+    drift = bf16_drift("snunet_b32_n2_s64_seed21")
     for n in ("conv0_4.conv1.weight", "conv1_3.conv1.weight", "conv3_1.conv1.weight", "conv4_0.conv2.weight", "Up1_3.up.weight", "conv0_0.conv1.weight"):
         off, shape = eng.params.offsets[n]
         g = eng.params.grad[off:off + shape.numel()].view(shape).cpu()
         r = float((g - grads_o[n]).norm() / grads_o[n].norm())
-        print(f"   grad {n}: rel-L2 {r:.4f}")
-        assert r < 0.3, (n, r)   # bf16 storage of dy/dx through ~30 layers; deep 8x8 levels see only 128 px/channel
+        print(f"   grad {n}: rel-L2 {r:.4f} (reference bf16 drift {drift[n]:.4f})")
+        assert r < DRIFT_FACTOR * drift[n] + DRIFT_FLOOR, (n, r, drift[n])
 
 
 def test_fp32_three_adam_steps_match_oracle():
