@@ -1246,10 +1246,17 @@ static int att_cfg(int T, int Tp, int dh, int extra_rows, size_t &smem, int &row
   return KS_OK;
 }
 
+namespace ks { int attention_fwd_umma(int B, int T, int Tp, int heads, const void *qkv, float scale, void *out, void *probs, cudaStream_t st); }
+
 extern "C" int ks_attention_fwd(int dtype, int B, int T, int Tp, int heads, int dh, const void *qkv, float scale, void *out, void *probs,
                                 void *stream) {
   KS_CHECK_ARG(B > 0 && T > 0 && heads > 0 && qkv && out && probs);
   if (!al16(qkv) || !al16(out) || !al16(probs)) return KS_EUNSUPPORTED;
+  if (atc_ok(dtype, T, Tp, dh, heads) && !g_opt.att_no_umma) {
+    // tcgen05 path (csrc/attention_tc.cu): TMA -> smem -> UMMA -> TMEM, softmax out of TMEM; falls through when the shape does not fit
+    const int rc = attention_fwd_umma(B, T, Tp, heads, qkv, scale, out, probs, (cudaStream_t)stream);
+    if (rc != KS_EUNSUPPORTED) return rc;
+  }
   if (atc_ok(dtype, T, Tp, dh, heads)) {
     static bool attr = false;
     if (!attr) { cudaError_t e = cudaFuncSetAttribute(attention_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);

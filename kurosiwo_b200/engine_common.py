@@ -141,7 +141,7 @@ class TrainStepMixin:
     # replayed step is graph | all-reduce (side stream) | graph | ... and the GPU runs bucket k's all-reduce under segment k+1.
     # ------------------------------------------------------------------------------------------
     def _grads_ready(self, lo: int, hi: int):
-        if self.world == 1 or not self.overlap_comm or hi <= lo or getattr(self, "_skip_comm", False):
+        if getattr(self, "world", 1) == 1 or not self.overlap_comm or hi <= lo or getattr(self, "_skip_comm", False):   # world: set by init_training
             return
         self._ready.append((int(lo), int(hi)))
         self._ready_bytes += 4 * (hi - lo)
