@@ -1246,6 +1246,8 @@ static int att_cfg(int T, int Tp, int dh, int extra_rows, size_t &smem, int &row
   return KS_OK;
 }
 
+namespace ks { int attention_bwd_umma(int B, int T, int Tp, int heads, const void *qkv, const void *probs, const void *dout, float scale, void *dqkv,
+                                      void *ds, cudaStream_t st); }
 namespace ks { int attention_fwd_umma(int B, int T, int Tp, int heads, const void *qkv, float scale, void *out, void *probs, cudaStream_t st); }
 
 extern "C" int ks_attention_fwd(int dtype, int B, int T, int Tp, int heads, int dh, const void *qkv, float scale, void *out, void *probs,
@@ -1281,6 +1283,10 @@ extern "C" int ks_attention_bwd(int dtype, int B, int T, int Tp, int heads, int 
                                 float scale, void *dqkv, void *ds_scratch, void *stream) {
   KS_CHECK_ARG(B > 0 && T > 0 && heads > 0 && qkv && probs && dout && dqkv && ds_scratch);
   if (!al16(qkv) || !al16(dout) || !al16(probs) || !al16(dqkv) || !al16(ds_scratch)) return KS_EUNSUPPORTED;
+  if (atc_ok(dtype, T, Tp, dh, heads) && !g_opt.att_no_umma) {
+    const int rc = attention_bwd_umma(B, T, Tp, heads, qkv, probs, dout, scale, dqkv, ds_scratch, (cudaStream_t)stream);
+    if (rc != KS_EUNSUPPORTED) return rc;
+  }
   if (atc_ok(dtype, T, Tp, dh, heads)) {
     static bool attr = false;
     if (!attr) {
