@@ -296,60 +296,68 @@ __global__ void __launch_bounds__(160, 2) attention_bwd_rows_umma_kernel(const _
     const bool row_ok = row < T;                        // P rows >= T are zero: dS = 0 there
     const long long poff = (((long long)b * p.heads + h) * Tp + min(row, Tp - 1)) * Tp;
     const __nv_bfloat16 *prow = p.probs + poff;
+    // this row of P (bf16, Tp <= 256 values = up to 32 x 16 bytes) is read ONCE, into registers, before UMMA 1 has even finished:
+    // the loads overlap the TMA / MMA latency and both passes below run out of registers
+    uint4 pq[8][4];
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        pq[ch][q] = (ch < nch && row_ok && (ch * 32 + q * 8) < Tp) ? __ldg(reinterpret_cast<const uint4 *>(prow + ch * 32) + q) : make_uint4(0u, 0u, 0u, 0u);
     mbar_wait(s_full, 0);
     tc_fence_after();
     // pass 1: d = sum_j dP_j P_j
     float d = 0.f;
-    for (int ch = 0; ch < nch; ++ch) {
-      uint32_t v[32];
-      const int c0 = ch << 5;
-      const bool wide = (Tp - c0) >= 32;
-      if (wide) tmem_ld32(trow + c0, v);
-      else { uint32_t v16[16]; tmem_ld16(trow + c0, v16);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { v[i] = v16[i]; v[16 + i] = 0u; } }
-      uint4 pq[4];
+    for (int ch = 0; ch < 8; ++ch) {
+      if (ch < nch) {
+        uint32_t v[32];
+        const int c0 = ch << 5;
+        const bool wide = (Tp - c0) >= 32;
+        if (wide) tmem_ld32(trow + c0, v);
+        else { uint32_t v16[16]; tmem_ld16(trow + c0, v16);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) pq[q] = (row_ok && (wide || q < 2)) ? __ldg(reinterpret_cast<const uint4 *>(prow + c0) + q) : make_uint4(0u, 0u, 0u, 0u);
-      tmem_ld_wait();
-      const uint32_t *pw = reinterpret_cast<const uint32_t *>(pq);
+          for (int i = 0; i < 16; ++i) { v[i] = v16[i]; v[16 + i] = 0u; } }
+        tmem_ld_wait();
+        const uint32_t *pw = reinterpret_cast<const uint32_t *>(pq[ch]);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&pw[i]));
-        d = fmaf(__uint_as_float(v[2 * i]), pf.x, d);
-        d = fmaf(__uint_as_float(v[2 * i + 1]), pf.y, d);
+        for (int i = 0; i < 16; ++i) {
+          const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&pw[i]));
+          d = fmaf(__uint_as_float(v[2 * i]), pf.x, d);
+          d = fmaf(__uint_as_float(v[2 * i + 1]), pf.y, d);
+        }
       }
     }
     // pass 2: dS = P (dP - d) -> bf16 -> global scratch + shared memory (A operand of UMMA 2)
     __nv_bfloat16 *dsrow = p.ds + poff;
-    for (int ch = 0; ch < nch; ++ch) {
-      uint32_t v[32];
-      const int c0 = ch << 5;
-      const bool wide = (Tp - c0) >= 32;
-      if (wide) tmem_ld32(trow + c0, v);
-      else { uint32_t v16[16]; tmem_ld16(trow + c0, v16);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { v[i] = v16[i]; v[16 + i] = 0u; } }
-      uint4 pq[4];
+    for (int ch = 0; ch < 8; ++ch) {
+      if (ch < nch) {
+        uint32_t v[32];
+        const int c0 = ch << 5;
+        const bool wide = (Tp - c0) >= 32;
+        if (wide) tmem_ld32(trow + c0, v);
+        else { uint32_t v16[16]; tmem_ld16(trow + c0, v16);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) pq[q] = (row_ok && (wide || q < 2)) ? __ldg(reinterpret_cast<const uint4 *>(prow + c0) + q) : make_uint4(0u, 0u, 0u, 0u);
-      tmem_ld_wait();
-      const uint32_t *pw = reinterpret_cast<const uint32_t *>(pq);
-      uint32_t pk[16];
+          for (int i = 0; i < 16; ++i) { v[i] = v16[i]; v[16 + i] = 0u; } }
+        tmem_ld_wait();
+        const uint32_t *pw = reinterpret_cast<const uint32_t *>(pq[ch]);
+        uint32_t pk[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&pw[i]));
-        const __nv_bfloat162 h2 = __floats2bfloat162_rn(pf.x * (__uint_as_float(v[2 * i]) - d), pf.y * (__uint_as_float(v[2 * i + 1]) - d));
-        pk[i] = *reinterpret_cast<const uint32_t *>(&h2);
-      }
-      const int nv = wide ? 4 : 2;
+        for (int i = 0; i < 16; ++i) {
+          const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&pw[i]));
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(pf.x * (__uint_as_float(v[2 * i]) - d), pf.y * (__uint_as_float(v[2 * i + 1]) - d));
+          pk[i] = *reinterpret_cast<const uint32_t *>(&h2);
+        }
+        const int nv = wide ? 4 : 2;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (q < nv) {
-          const uint4 u = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          const int j = (c0 >> 3) + q;
-          *reinterpret_cast<uint4 *>(sm + AT_Q + (uint32_t)(j >> 3) * 16384u + (uint32_t)r * 128u + (uint32_t)(((j & 7) ^ (r & 7)) << 4)) = u;
-          if (row < Tp) *reinterpret_cast<uint4 *>(dsrow + c0 + 8 * q) = u;
+        for (int q = 0; q < 4; ++q) {
+          if (q < nv) {
+            const uint4 u = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            const int j = (c0 >> 3) + q;
+            *reinterpret_cast<uint4 *>(sm + AT_Q + (uint32_t)(j >> 3) * 16384u + (uint32_t)r * 128u + (uint32_t)(((j & 7) ^ (r & 7)) << 4)) = u;
+            if (row < Tp) *reinterpret_cast<uint4 *>(dsrow + c0 + 8 * q) = u;
+          }
         }
       }
     }
