@@ -158,7 +158,7 @@ class ViTSegEngine(TrainStepMixin):
         v = tok_view(m)
         for c0 in range(0, v.C, 1024):
             c = min(1024, v.C - c0)
-            self.ops.channel_sum(v.ch(c0, c), out[c0:c0 + c], False)
+            self.ops.channel_sum(v.ch(c0, c), out[c0:c0 + c], True)     # accumulate into the flat gradient, zeroed at the start of backward: no memset launch per bias
 
     # ------------------------------------------------------------------------------------------
     def forward(self, img: torch.Tensor, training: bool = True) -> torch.Tensor:
