@@ -44,6 +44,10 @@ class FlatParams:
                     break
         if ok:
             return False
+        if self.flat is not None:
+            import warnings
+            warnings.warn("module parameters no longer alias the flat parameter buffer (e.g. after .to() or load of new Parameter objects): "
+                          "re-flattening; the flat layout is deterministic, so existing optimizer moments stay aligned", RuntimeWarning, stacklevel=2)
         flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
         grad = torch.zeros(self.numel, dtype=torch.float32, device=device)
         for name in self.names:
@@ -84,6 +88,10 @@ class TrainStepMixin:
         if optimizer not in ("adam", "adamw", "sgd"):
             raise NotImplementedError(f"fused optimizer '{optimizer}' (adam: change_detection_trainer.py:52-54, adamw: :55-60, sgd: :61-66)")
         self.optimizer = optimizer
+        if getattr(self, "adam_m", None) is not None and int(self.adam_step.item()) > 0:
+            import warnings
+            warnings.warn("init_training() called on an engine that has already stepped: the optimizer moments and the step counter are "
+                          "reset (use adopt_training_state(old_engine) to carry them over)", RuntimeWarning, stacklevel=2)
         self.adam_m = torch.zeros_like(self.params.flat)
         self.adam_v = torch.zeros_like(self.params.flat)
         self.adam_step = torch.zeros(1, dtype=torch.int32, device=dev)
