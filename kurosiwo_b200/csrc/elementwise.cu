@@ -811,7 +811,12 @@ extern "C" int ks_channel_sum(int dtype, int N, int H, int W, const ks_view_t *x
   const long long npix = (long long)N * H * W;
   cudaStream_t st = (cudaStream_t)stream;
   if (!accumulate) { cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * x->C, st); if (e != cudaSuccess) return (int)e; }
+  // every CTA ends with C atomic adds on the same C addresses: few, long-running CTAs (>= 32 rows per row lane) instead of many short
+  // ones - on the [13312 x 768] ViT bias gradients 832 CTAs x 768 atomics were the cost, not the 20 MB read
+  const int per_lane = g_opt.cs_rows > 0 ? g_opt.cs_rows : 32;
 #define CALL(T, V) { int grid; size_t smem; int rc = launch_reduce_cfg<T, V>(x->C, npix, grid, smem, 1); if (rc) return rc; \
+    { const int CVv = x->C / V, rowsv = 256 / CVv; long long g2 = (npix + (long long)rowsv * per_lane - 1) / ((long long)rowsv * per_lane); \
+      if (g2 < 1) g2 = 1; if (g2 < grid) grid = (int)g2; } \
     channel_sum_kernel<T, V><<<grid, 256, smem, st>>>(to_view(*x), N, H, W, out, view_flat(*x, H, W)); }
   KS_DISPATCH_TV(dtype, vec, CALL);
 #undef CALL
