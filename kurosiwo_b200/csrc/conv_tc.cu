@@ -839,6 +839,7 @@ extern "C" int ks_set_option(const char *name, int value) {
   else if (eq("loss_no_pdl")) ks::g_opt.loss_no_pdl = value;   // 1 = plain stream order between the two CE+Dice passes
   else if (eq("tc_no_ns3")) ks::g_opt.no_ns3 = value;   // 1 = one UMMA per tap also for narrow N tiles (A/B comparisons)
   else if (eq("wgrad_mode")) ks::g_opt.wgrad_mode = value;   // 0 auto (tap stacking along N), 2 = halo kernel v2
+  else if (eq("ln_rows")) ks::g_opt.ln_rows = value;     // perf experiments: rows per thread of the LayerNorm-backward column pass
   else if (eq("cs_rows")) ks::g_opt.cs_rows = value;     // perf experiments: rows per row lane and CTA of ks_channel_sum (default 32)
   else if (eq("ew_cap")) ks::g_opt.ew_cap = value;       // perf experiments: CTAs per SM of the BatchNorm passes' grids (0 = default 8)
   else if (eq("att_no_umma")) ks::g_opt.att_no_umma = value;   // 1 = mma.sync attention forward instead of the tcgen05 kernel (A/B comparisons)

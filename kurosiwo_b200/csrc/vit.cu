@@ -1181,7 +1181,8 @@ extern "C" int ks_layernorm_bwd(int dtype, int64_t rows, int C, const void *dy, 
   }
   if (dgamma || dbeta) {
     const int cvb = (C / 8) < 256 ? (C / 8) : 256, rl = 256 / cvb;
-    const int grid = grid_for(rows, rl * 16, 4);        // >= 16 rows per thread so that the per-CTA column atomics amortise
+    // >= 16 rows per thread so that the per-CTA column atomics amortise; measured (scripts/bench_lnbwd.py): C = 768 18.3 -> 14.3 us with 32, C = 128 better with 16
+    const int grid = grid_for(rows, rl * (g_opt.ln_rows > 0 ? g_opt.ln_rows : (C >= 512 ? 32 : 16)), 4);
     const size_t smem = (size_t)2 * C * sizeof(float);
 #define CALL(T) layernorm_bwd_cols_kernel<T><<<grid, 256, smem, st>>>(rows, C, (const T *)dy, lddy, (const T *)x, ldx, mean, rstd, dgamma, dbeta)
     KS_DISPATCH_T(dtype, CALL);
