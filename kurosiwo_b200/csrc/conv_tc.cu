@@ -836,12 +836,15 @@ extern "C" int ks_set_option(const char *name, int value) {
   else if (eq("tc_ew")) ks::g_opt.ew = value;             // epilogue warps: 0 auto, 8, 16
   else if (eq("loss_chunks")) ks::g_opt.loss_chunks = value;   // perf experiments: CTAs per sample of the CE+Dice passes
   else if (eq("loss_no_bulk")) ks::g_opt.loss_no_bulk = value;   // 1 = register-staged CE+Dice passes (A/B comparisons)
+  else if (eq("loss_variant")) ks::g_opt.loss_variant = value;   // 1 = two-pass CE+Dice kernels also when the resident single pass fits (A/B comparisons)
   else if (eq("loss_no_pdl")) ks::g_opt.loss_no_pdl = value;   // 1 = plain stream order between the two CE+Dice passes
   else if (eq("tc_no_ns3")) ks::g_opt.no_ns3 = value;   // 1 = one UMMA per tap also for narrow N tiles (A/B comparisons)
   else if (eq("wgrad_mode")) ks::g_opt.wgrad_mode = value;   // 0 auto (tap stacking along N), 2 = halo kernel v2
   else if (eq("ln_rows")) ks::g_opt.ln_rows = value;     // perf experiments: rows per thread of the LayerNorm-backward column pass
   else if (eq("cs_rows")) ks::g_opt.cs_rows = value;     // perf experiments: rows per row lane and CTA of ks_channel_sum (default 32)
   else if (eq("ew_cap")) ks::g_opt.ew_cap = value;       // perf experiments: CTAs per SM of the BatchNorm passes' grids (0 = default 8)
+  else if (eq("stem_simt")) ks::g_opt.stem_simt = value;   // 1 = CUDA-core stem kernels also for bf16 / Cin == 2 (A/B comparisons)
+  else if (eq("ecam_simt")) ks::g_opt.ecam_simt = value;   // 1 = CUDA-core ECAM final pass also for bf16 (A/B comparisons)
   else if (eq("att_no_umma")) ks::g_opt.att_no_umma = value;   // 1 = mma.sync attention forward instead of the tcgen05 kernel (A/B comparisons)
   else if (eq("att_simt")) ks::g_opt.att_simt = value;   // 1 = CUDA-core attention kernels also for bf16 (A/B comparisons)
   else if (eq("tc_debug")) ks::g_opt.debug = value;   // perf experiments only: bit0 skip epilogue stores, bit1 skip TMEM loads, bit2 skip MMAs

@@ -695,6 +695,172 @@ ecam_final_bulk_kernel(ViewList xs, int J, int Cb, int HW, int P, const float *_
   }
 }
 
+// Tensor-core variant of the final pass (bf16 storage, Cb == 32): the CUDA-core kernel above spends ~330 issue slots per
+// (pixel, 8-channel) item - 96 FMAs behind 24 LDS.128 of weights, 32 bf16->fp32 conversions, 40 compares - and ran at 1.7 TB/s.
+// Here the 1x1 classifier is a warp-level MMA per 16 pixels: the A fragments ARE the raw 16-byte loads (thread (g, t) holds channels
+// 8t..8t+7 of pixels g and g+8 of every view; the K index is a free permutation, the B fragments use the same one), the effective
+// weights ca*wf are split into bf16 hi + lo parts that sit in neighbouring accumulator columns (n = 2 class + part), so the products
+// are exact and thread t < 3 ends up with logit t = c0 + c1 without a shuffle; the arg-max discovery compares packed bf16 pairs.
+__device__ __forceinline__ void ecam_mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t ecam_pack2(float lo, float hi) {
+  const __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t *>(&h2);
+}
+__device__ __forceinline__ float2 ecam_unpack2(uint32_t u) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u));
+}
+
+template <int K>
+__global__ void __launch_bounds__(256, 2)
+ecam_final_mma_kernel(ViewList xs, int J, int HW, int P, const float *__restrict__ gates, const float *__restrict__ wf,
+                      const float *__restrict__ bf, const float *__restrict__ pooled, int *argmax, float *logits) {
+  typedef __nv_bfloat16 T;
+  constexpr int Cb = 32;
+  static_assert(K == 3, "hi/lo columns of 3 classes fill 6 of the 8 accumulator columns");
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int n = blockIdx.y, CC = J * Cb, CT = (J + 1) * Cb;
+  const uint32_t stage_bytes = (uint32_t)J * P * Cb * sizeof(T);
+  unsigned char *stages = smraw;
+  unsigned char *barmem = smraw + BULK_STAGES * stage_bytes;
+  float *weff = reinterpret_cast<float *>(barmem + 64);   // [J][K][Cb]
+  float *cst = weff + K * CC;                              // [K] (+1 pad)
+  float *smx = cst + 4;                                    // [CT]
+  float *slog = smx + CT;                                  // [K][P] logits of the chunk (coalesced plane stores)
+  BulkPipe bp; bp.init(barmem, stages, stage_bytes);
+  const float *gt = gates + (size_t)n * CT;
+  for (int i = threadIdx.x; i < K * CC; i += blockDim.x) {
+    const int j = i / (K * Cb), k = (i / Cb) % K, cb = i % Cb;
+    weff[i] = wf[k * CC + j * Cb + cb] * gt[j * Cb + cb];
+  }
+  for (int i = threadIdx.x; i < CT; i += blockDim.x) smx[i] = pooled ? pooled[((size_t)n * 2 + 1) * CT + i] : 0.f;
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float sacc = bf[threadIdx.x];
+    for (int j = 0; j < J; ++j)
+      for (int cb = 0; cb < Cb; ++cb) sacc += weff[(j * K + threadIdx.x) * Cb + cb] * gt[CC + cb];
+    cst[threadIdx.x] = sacc;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  int *am = argmax ? argmax + (size_t)n * CT : nullptr;
+  // B fragments: column n = g -> class g >> 1, part g & 1 (0 = hi, 1 = lo); k-step s of view j covers channels 8t + 4s .. 8t + 4s + 3
+  uint32_t bfr[kMaxJ][2][2];
+#pragma unroll
+  for (int j = 0; j < kMaxJ; ++j)
+#pragma unroll
+    for (int sst = 0; sst < 2; ++sst)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float v[2] = {0.f, 0.f};
+        if (j < J && g < 2 * K) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float wv = weff[(j * K + (g >> 1)) * Cb + 8 * t + 4 * sst + 2 * r + e];
+            const float hi = __bfloat162float(__float2bfloat16_rn(wv));
+            v[e] = (g & 1) ? (wv - hi) : hi;
+          }
+        }
+        bfr[j][sst][r] = ecam_pack2(v[0], v[1]);
+      }
+  uint32_t mxp[kMaxJ][4];      // pooled maxima of this thread's channels as packed bf16 pairs (exact: they ARE bf16 values)
+  float mxi[8];                // intra maxima (fp32 sums)
+#pragma unroll
+  for (int j = 0; j < kMaxJ; ++j)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) mxp[j][r] = (j < J) ? ecam_pack2(smx[j * Cb + t * 8 + 2 * r], smx[j * Cb + t * 8 + 2 * r + 1]) : 0u;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) mxi[i] = smx[CC + t * 8 + i];
+  const float my_cst = (t < K) ? cst[t] : 0.f;
+  const int nchunks = (HW + P - 1) / P;
+  if (threadIdx.x == 0)
+    for (int s = 0; s < BULK_STAGES - 1; ++s) {
+      const int c = blockIdx.x + s * gridDim.x;
+      if (c < nchunks) bulk_issue<T>(bp, s, xs, J, Cb, n, P, c * P, min(P, HW - c * P), nullptr, 0, HW);
+    }
+  int it = 0;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+    const int s = it % BULK_STAGES;
+    if (threadIdx.x == 0) {
+      const int cn = c + (BULK_STAGES - 1) * gridDim.x;
+      if (cn < nchunks) bulk_issue<T>(bp, (it + BULK_STAGES - 1) % BULK_STAGES, xs, J, Cb, n, P, cn * P, min(P, HW - cn * P), nullptr, 0, HW);
+    }
+    bk_wait(bp.bars + 8u * s, (uint32_t)((it / BULK_STAGES) & 1));
+    const T *st = reinterpret_cast<const T *>(stages + (size_t)s * stage_bytes);
+    const int p0 = c * P, npx = min(P, HW - p0);
+    for (int base = warp * 16; base < npx; base += 128) {          // warp-uniform
+      const int px[2] = {base + g, base + g + 8};
+      const bool ok[2] = {px[0] < npx, px[1] < npx};
+      uint4 d[2][kMaxJ];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < kMaxJ; ++j)
+          d[h][j] = (j < J && ok[h]) ? *reinterpret_cast<const uint4 *>(st + ((size_t)j * P + px[h]) * Cb + t * 8) : make_uint4(0u, 0u, 0u, 0u);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < kMaxJ; ++j)
+        if (j < J) {
+          ecam_mma_16816(acc, d[0][j].x, d[1][j].x, d[0][j].y, d[1][j].y, bfr[j][0][0], bfr[j][0][1]);
+          ecam_mma_16816(acc, d[0][j].z, d[1][j].z, d[0][j].w, d[1][j].w, bfr[j][1][0], bfr[j][1][1]);
+        }
+      if (t < K) {
+        if (ok[0]) slog[t * P + px[0]] = acc[0] + acc[1] + my_cst;
+        if (ok[1]) slog[t * P + px[1]] = acc[2] + acc[3] + my_cst;
+      }
+      if (am) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (!ok[h]) continue;
+          float itv[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) itv[q] = 0.f;
+          unsigned int hit = 0u;
+#pragma unroll
+          for (int j = 0; j < kMaxJ; ++j)
+            if (j < J) {
+              const uint32_t dw[4] = {d[h][j].x, d[h][j].y, d[h][j].z, d[h][j].w};
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                hit |= __heq2_mask(*reinterpret_cast<const __nv_bfloat162 *>(&dw[r]), *reinterpret_cast<const __nv_bfloat162 *>(&mxp[j][r]));
+                const float2 f2 = ecam_unpack2(dw[r]);
+                itv[2 * r] += f2.x; itv[2 * r + 1] += f2.y;
+              }
+            }
+          bool hit_i = false;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) hit_i |= (itv[q] == mxi[q]);
+          if (hit != 0u || hit_i) {      // rare: some element equals its channel's pooled maximum -> record the FIRST such pixel
+            const int p = p0 + px[h];
+#pragma unroll
+            for (int j = 0; j < kMaxJ; ++j)
+              if (j < J) {
+                const uint32_t dw[4] = {d[h][j].x, d[h][j].y, d[h][j].z, d[h][j].w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  const float2 f2 = ecam_unpack2(dw[r]), m2 = ecam_unpack2(mxp[j][r]);
+                  if (f2.x == m2.x) atomicMin(am + j * Cb + t * 8 + 2 * r, p);
+                  if (f2.y == m2.y) atomicMin(am + j * Cb + t * 8 + 2 * r + 1, p);
+                }
+              }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (itv[q] == mxi[q]) atomicMin(am + CC + t * 8 + q, p);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * npx; i += blockDim.x) {
+      const int k = i / npx, pxl = i % npx;
+      logits[((size_t)n * K + k) * HW + p0 + pxl] = slog[k * P + pxl];
+    }
+    __syncthreads();
+  }
+}
+
 template <typename T, int K>
 __global__ void __launch_bounds__(256, 2)
 ecam_bwd_reduce_bulk_kernel(ViewList xs, int J, int Cb, int HW, int P, const float *__restrict__ dlogits, double *red) {
@@ -859,7 +1025,10 @@ extern "C" int ks_ecam_final(int dtype, int N, int H, int W, const ks_view_t *xs
     const int nch = (H * W + P - 1) / P;
     int gx = (kNumSMs * 2) / N; if (gx > nch) gx = nch; if (gx < 1) gx = 1;
     const size_t smem = (size_t)BULK_STAGES * J * P * Cb * es + 64 + sizeof(float) * (size_t)(K * CC + 4 + CT + K * P);
-    if (dtype == KS_F32) {
+    if (dtype == KS_BF16 && Cb == 32 && !g_opt.ecam_simt) {
+      static bool a = false; if (!a) { cudaFuncSetAttribute(ecam_final_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); a = true; }
+      ecam_final_mma_kernel<3><<<dim3(gx, N), 256, smem, st>>>(vl, J, H * W, P, gates, wf, bf, pooled, argmax, logits);
+    } else if (dtype == KS_F32) {
       static bool a = false; if (!a) { cudaFuncSetAttribute(ecam_final_bulk_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024); a = true; }
       ecam_final_bulk_kernel<float, 3><<<dim3(gx, N), 256, smem, st>>>(vl, J, Cb, H * W, P, gates, wf, bf, pooled, argmax, logits);
     } else {

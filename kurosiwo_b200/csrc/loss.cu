@@ -457,6 +457,298 @@ ce_dice_bulk_kernel(const float *__restrict__ logits, const long long *__restric
   }
 }
 
+// =====================================================================================================================
+// Resident single pass (the default whenever the problem fits on the chip: N * ceil(HW / 2048) <= 148 * 11 chunks, i.e. up to
+// bs=64 at 224x224): logits and labels are read from HBM ONCE and stay on the SMs across the one global dependency of the
+// gradient.  That dependency is a single scalar: with Sum_c p_c = 1 the Dice term of dL/dz needs only S_n = HW (1 + (C-1) T0 + T1)
+// (a constant of the shape - I_n enters the loss VALUE only, its b_n term cancels in the gradient) and the CE term needs
+// den = Sum_valid w_y.  One CTA per SM (512 threads) owns up to 11 chunks of 2048 pixels: logit planes 0 and 1 are bulk-copied
+// (cp.async.bulk, one mbarrier per chunk, all 176 KB in flight at once) into shared memory and stay there; plane 2 is loaded into
+// registers (11 x float4 per thread, all in flight at once); the int64 labels stream through a 3-deep register prefetch and are kept
+// as one byte per pixel.  Phase 1: argmax, per-chunk Sum p_yd, CE numerator / denominator -> atomics; grid barrier on ctrl[2] (all
+// CTAs are co-resident: grid <= #SMs, launched alone in stream order; the spin is bounded and poisons the loss with NaN instead
+// of hanging); phase 2: gradient from the resident logits, 12 B/pixel written with streaming stores.
+// Algorithmic traffic 33 B/pixel = DRAM traffic (the two-pass kernels above re-read 20 B/pixel through L2).
+// =====================================================================================================================
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// chunk cursor: chunk k = blockIdx.x + j * gridDim.x lives in sample n at chunk c; advanced incrementally (no division per chunk)
+struct ResCur {
+  int k, n, c;
+  __device__ __forceinline__ void init(int k0, int cps) { k = k0; n = k0 / cps; c = k0 - n * cps; }
+  __device__ __forceinline__ void advance(int G, int gd, int gq, int cps) {
+    k += G; n += gd; c += gq;
+    if (c >= cps) { c -= cps; ++n; }
+  }
+};
+
+template <int C, int MAXC, int TH>
+__global__ void __launch_bounds__(TH, 1)
+ce_dice_resident_kernel(const float *__restrict__ logits, const long long *__restrict__ labels, int N, int HW,
+                        const float *__restrict__ cw, int ignore_index, float grad_scale, float *__restrict__ loss_out,
+                        float *__restrict__ dlogits, unsigned char *__restrict__ pred, double *ws, unsigned int *ctrl,
+                        float dice_weight, int cps, int total) {
+  static_assert(C == 3, "planes 0/1 in shared memory, plane 2 in registers");
+  constexpr int P = 4 * TH;                       // pixels per chunk: 4 per thread
+  constexpr int LD = 3;                           // chunks in flight (issue order == consumption order: a request issued late
+                                                  // would queue behind everything issued before it)
+  extern __shared__ __align__(128) unsigned char rs_smem[];
+  float *zs = reinterpret_cast<float *>(rs_smem);                           // [MAXC][2][P]
+  const uint32_t zs_u = ls_u32(rs_smem), bars = zs_u + (uint32_t)MAXC * 2u * P * 4u;
+  float *sI = reinterpret_cast<float *>(rs_smem + (size_t)MAXC * 2 * P * 4 + 8 * 16);     // [16] per-chunk Sum p_yd (MAXC <= 16)
+  double *red = reinterpret_cast<double *>(rs_smem + (size_t)MAXC * 2 * P * 4 + 8 * 16 + 64);   // [2][TH / 32]
+  __shared__ unsigned int s_ticket;
+  const int tid = threadIdx.x, G = gridDim.x, q = tid * 4;
+  const int gd = G / cps, gq = G - gd * cps;
+  double *acc = ws + (size_t)(ld_flip(ctrl) & 1u) * (4 * (size_t)N + 2);
+  // all element offsets fit 32 bits: the resident path takes at most 148 * MAXC * P pixels (x C logits)
+  auto issue_planes = [&](int j, const ResCur &cu) {                 // thread 0: logit planes 0 and 1 of chunk j -> their resident slot
+    const int p0 = cu.c * P;
+    const uint32_t bytes = (uint32_t)min(P, HW - p0) * 4u;
+    const float *zb = logits + (cu.n * C * HW + p0);
+    const uint32_t bar = bars + 8u * j, dst = zs_u + (uint32_t)j * 2u * P * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(zb), "r"(bytes), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst + (uint32_t)P * 4u), "l"(zb + HW), "r"(bytes), "r"(bar) : "memory");
+  };
+  float4 z2r[MAXC];        // plane 2 (phase 1: logits, afterwards: probabilities), resident in registers
+  longlong2 ya[LD], yb[LD];
+  auto load_regs = [&](const ResCur &cu, float4 &z2, longlong2 &a, longlong2 &b) {      // plane 2 + labels of a chunk
+    const int pq = cu.c * P + q;
+    z2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    a = make_longlong2(0, 0); b = make_longlong2(0, 0);
+    if (pq < HW) {
+      z2 = __ldcs(reinterpret_cast<const float4 *>(logits + ((cu.n * C + 2) * HW + pq)));
+      const long long *lb = labels + (cu.n * HW + pq);
+      a = __ldcs(reinterpret_cast<const longlong2 *>(lb));
+      b = __ldcs(reinterpret_cast<const longlong2 *>(lb + 2));
+    }
+  };
+  ResCur pre; pre.init(blockIdx.x, cps);        // prefetch cursor: LD - 1 chunks ahead of the compute cursor
+  if (tid == 0) {
+    for (int j = 0; j < MAXC; ++j) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8u * j), "r"(1u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (tid < 16) sI[tid] = 0.f;
+#pragma unroll
+  for (int j = 0; j < LD - 1; ++j) {
+    if (j < MAXC) {
+      z2r[j] = make_float4(0.f, 0.f, 0.f, 0.f); ya[j] = make_longlong2(0, 0); yb[j] = make_longlong2(0, 0);
+      if (pre.k < total) {
+        if (tid == 0) issue_planes(j, pre);
+        load_regs(pre, z2r[j], ya[j], yb[j]);
+      }
+      pre.advance(G, gd, gq, cps);
+    }
+  }
+  float w[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) w[c] = cw[c];
+  const float T0 = 1e-6f, T1 = 1.0f + 1e-6f;  // one_hot(...)+eps in fp32 (dice.py:59)
+  const float L2E = 1.4426950408889634f;
+  __syncthreads();       // barrier initialisation visible to every waiter
+  // ---- phase 1: argmax, sums; the logits are replaced IN PLACE by the probabilities (phase 2 needs no transcendental) ----
+  uint32_t lab8[MAXC];   // per pixel: yd | valid << 2
+  float fnum = 0.f, fden = 0.f;
+  ResCur cur; cur.init(blockIdx.x, cps);
+#pragma unroll
+  for (int j = 0; j < MAXC; ++j) {
+    lab8[j] = 0u;
+    if (j + LD - 1 < MAXC) {
+      z2r[j + LD - 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ya[(j + LD - 1) % LD] = make_longlong2(0, 0); yb[(j + LD - 1) % LD] = make_longlong2(0, 0);
+      if (pre.k < total) {
+        if (tid == 0) issue_planes(j + LD - 1, pre);
+        load_regs(pre, z2r[j + LD - 1], ya[(j + LD - 1) % LD], yb[(j + LD - 1) % LD]);
+      }
+      pre.advance(G, gd, gq, cps);
+    }
+    if (cur.k < total) {                                   // uniform per CTA
+      const int pq = cur.c * P + q;
+      ls_wait(bars + 8u * j, 0u);
+      float fI = 0.f;
+      if (pq < HW) {
+        float4 *s0 = reinterpret_cast<float4 *>(zs + (j * 2 + 0) * P + q);
+        float4 *s1 = reinterpret_cast<float4 *>(zs + (j * 2 + 1) * P + q);
+        const float4 a0 = *s0, a1 = *s1;
+        const float zz[C][4] = {{a0.x, a0.y, a0.z, a0.w}, {a1.x, a1.y, a1.z, a1.w}, {z2r[j].x, z2r[j].y, z2r[j].z, z2r[j].w}};
+        const int yv[4] = {(int)ya[j % LD].x, (int)ya[j % LD].y, (int)yb[j % LD].x, (int)yb[j % LD].y};
+        float pp[C][4];
+        uint32_t lb8 = 0u, prw = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int y = yv[i];
+          const bool valid = (y != ignore_index);
+          const int yd = valid ? y : 0;  // dice.py:116-119: ignored pixels become class 0
+          float m = zz[0][i]; uint32_t am = 0u;
+#pragma unroll
+          for (int cc = 1; cc < C; ++cc) { if (zz[cc][i] > m) { m = zz[cc][i]; am = (uint32_t)cc; } }      // first maximum, as torch.argmax
+          float ar[C], e[C], ssum = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < C; ++cc) {
+            ar[cc] = (zz[cc][i] - m) * L2E;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[cc]) : "f"(ar[cc]));
+            ssum += e[cc];
+          }
+          float ay = ar[0], ey = e[0], wy = w[0];
+#pragma unroll
+          for (int cc = 1; cc < C; ++cc) if (cc == yd) { ay = ar[cc]; ey = e[cc]; wy = w[cc]; }
+          float l2s; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2s) : "f"(ssum));
+          const float logp2 = ay - l2s;                             // log2 p_yd
+          const float inv = __fdividef(1.0f, ssum);
+#pragma unroll
+          for (int cc = 0; cc < C; ++cc) pp[cc][i] = e[cc] * inv;
+          fI = fmaf(ey, inv, fI);                                   // Sum_c p_c t_c = T0 + p_yd (Sum_c p_c = 1)
+          const float wv = valid ? wy : 0.f;
+          fnum = fmaf(-wv, logp2, fnum); fden += wv;
+          prw |= am << (8 * i);
+          lb8 |= ((uint32_t)yd | (valid ? 4u : 0u)) << (8 * i);
+        }
+        lab8[j] = lb8;
+        *s0 = make_float4(pp[0][0], pp[0][1], pp[0][2], pp[0][3]);
+        *s1 = make_float4(pp[1][0], pp[1][1], pp[1][2], pp[1][3]);
+        z2r[j] = make_float4(pp[2][0], pp[2][1], pp[2][2], pp[2][3]);
+        if (pred != nullptr) *reinterpret_cast<uint32_t *>(pred + (cur.n * HW + pq)) = prw;
+      }
+      fI = warp_sum(fI);
+      if ((tid & 31) == 0) atomicAdd(&sI[j], fI);
+    }
+    cur.advance(G, gd, gq, cps);
+  }
+  {
+    const double d2 = warp_sum_d((double)fnum * 0.6931471805599453), d3 = warp_sum_d((double)fden);
+    if ((tid & 31) == 0) { red[tid >> 5] = d2; red[(TH / 32) + (tid >> 5)] = d3; }
+  }
+  __syncthreads();
+  if (tid < MAXC) {
+    const int k = blockIdx.x + tid * G;
+    if (k < total) {
+      const int n = k / cps;
+      const int p0 = (k - n * cps) * P;
+      const double npx = (double)min(P, HW - p0);
+      // I_n = Sum_px (T0 + p_yd), S_n = Sum_px (1 + (C-1) T0 + T1): the constants are added per pixel count in double
+      atomicAdd(acc + 4 * n, (double)sI[tid] + npx * (double)T0);
+      atomicAdd(acc + 4 * n + 1, npx * (1.0 + (double)(C - 1) * (double)T0 + (double)T1));
+      __threadfence();
+    }
+  } else if (tid == 32 || tid == 33) {
+    const int o = (tid - 32) * (TH / 32);
+    double sred = 0.0;
+    for (int i = 0; i < TH / 32; ++i) sred += red[o + i];
+    atomicAdd(acc + 4 * (size_t)N + (tid - 32), sred);       // totals {ce_num, ce_den}
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- grid barrier: every CTA's ce_den contribution is in ----
+  if (tid == 0) {
+    __threadfence();
+    atomicAdd(ctrl + 2, 1u);
+    unsigned int spins = 0;
+    while (ld_acquire_u32(ctrl + 2) < (unsigned int)G) {
+      if (++spins > (1u << 24)) { atomicExch(ctrl + 3, 1u); break; }     // never hang the device: poison the loss instead
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: gradient from the resident probabilities ----
+  {
+    const double Sn = (double)HW * (1.0 + (double)(C - 1) * (double)T0 + (double)T1) + 1e-6;
+    const double den = __ldcg(acc + 4 * (size_t)N + 1);
+    const float a_n = (float)(-2.0 / ((double)N * Sn)) * grad_scale * dice_weight;      // dL/dp = a_n t + b_n; b_n cancels (Sum_c p_c = 1)
+    const float inv_den = (float)(1.0 / den) * grad_scale;
+    float wsc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) wsc[c] = w[c] * inv_den;
+    cur.init(blockIdx.x, cps);
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) {
+      if (cur.k < total) {
+        const int pq = cur.c * P + q;
+        if (pq < HW) {
+          const float4 a0 = *reinterpret_cast<const float4 *>(zs + (j * 2 + 0) * P + q);
+          const float4 a1 = *reinterpret_cast<const float4 *>(zs + (j * 2 + 1) * P + q);
+          const float pp[C][4] = {{a0.x, a0.y, a0.z, a0.w}, {a1.x, a1.y, a1.z, a1.w}, {z2r[j].x, z2r[j].y, z2r[j].z, z2r[j].w}};
+          float gg[C][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t b = lab8[j] >> (8 * i);
+            const int yd = (int)(b & 3u);
+            float pyd = pp[0][i], wy = wsc[0];
+#pragma unroll
+            for (int cc = 1; cc < C; ++cc) if (cc == yd) { pyd = pp[cc][i]; wy = wsc[cc]; }
+            // d_c = p_c (wy - a_n p_yd) + 1[c == yd] (a_n p_c - wy),  wy = w[y] / Sum_valid w  (0 on ignored pixels)
+            wy = (b & 4u) ? wy : 0.f;
+            const float k_all = fmaf(-a_n, pyd, wy);
+            const float hot = fmaf(a_n, pyd, -wy);
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) gg[cc][i] = fmaf(k_all, pp[cc][i], (cc == yd) ? hot : 0.f);
+          }
+          float *gb = dlogits + (cur.n * C * HW + pq);
+#pragma unroll
+          for (int cc = 0; cc < C; ++cc) __stcs(reinterpret_cast<float4 *>(gb + cc * HW), make_float4(gg[cc][0], gg[cc][1], gg[cc][2], gg[cc][3]));
+        }
+      }
+      cur.advance(G, gd, gq, cps);
+    }
+  }
+  // ---- loss value + workspace clean-up: one warp of the LAST CTA to finish ----
+  if (tid == 0) s_ticket = atomicAdd(ctrl, 1u);
+  __syncthreads();
+  if (s_ticket == (unsigned int)G - 1 && tid < 32) {
+    __threadfence();
+    double dice = 0.0;
+    for (int i = tid; i < N; i += 32) {
+      const double I = __ldcg(acc + 4 * i), S = __ldcg(acc + 4 * i + 1);
+      dice += 1.0 - 2.0 * I / (S + 1e-6);
+    }
+    dice = warp_sum_d(dice);
+    if (tid == 0) {
+      dice /= (double)N;
+      const double num = __ldcg(acc + 4 * (size_t)N), den = __ldcg(acc + 4 * (size_t)N + 1);
+      const double cel = num / den;                    // NaN when every pixel is ignored (as torch)
+      const bool poisoned = ld_acquire_u32(ctrl + 3) != 0u;
+      const float nanv = __int_as_float(0x7fc00000);
+      loss_out[0] = poisoned ? nanv : (float)((double)dice_weight * dice + cel);
+      loss_out[1] = poisoned ? nanv : (float)dice; loss_out[2] = poisoned ? nanv : (float)cel;
+      ctrl[2] = 0u;
+    }
+    __syncwarp();
+    finish_workspace(ws, ctrl, N);
+  }
+}
+
+constexpr int kResMaxC = 11, kResTH = 512;
+constexpr size_t kResSmem = (size_t)kResMaxC * 2 * (4 * kResTH) * 4 + 8 * 16 + 64 + 2 * (kResTH / 32) * 8;
+
+// returns -1 when the problem does not fit on the chip (the caller falls back to the two-pass kernels)
+static int launch_resident(const float *logits, const long long *lab, int N, int64_t HW, const float *cw, int ignore_index, float grad_scale,
+                           float *loss_out, float *dlogits, uint8_t *pred, double *acc, unsigned int *ctrl, float dice_weight, cudaStream_t st) {
+  constexpr int P = 4 * kResTH;
+  const long long cps = (HW + P - 1) / P, total = cps * N;
+  if (total > (long long)kNumSMs * kResMaxC) return -1;
+  static int ok = 0;     // 0 unknown, 1 usable, -1 not usable on this device
+  if (ok == 0) {
+    cudaError_t e = cudaFuncSetAttribute(ce_dice_resident_kernel<3, kResMaxC, kResTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResSmem);
+    int nsm = 0, per = 0, devi = 0;
+    if (e == cudaSuccess) e = cudaGetDevice(&devi);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, devi);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, ce_dice_resident_kernel<3, kResMaxC, kResTH>, kResTH, kResSmem);
+    ok = (e == cudaSuccess && per >= 1 && nsm >= kNumSMs) ? 1 : -1;      // the grid barrier needs every CTA resident
+    if (e != cudaSuccess) (void)cudaGetLastError();
+  }
+  if (ok < 0) return -1;
+  const int G = (int)(total < kNumSMs ? total : kNumSMs);
+  ce_dice_resident_kernel<3, kResMaxC, kResTH><<<G, kResTH, kResSmem, st>>>(logits, lab, N, (int)HW, cw, ignore_index, grad_scale, loss_out,
+                                                                           dlogits, pred, acc, ctrl, dice_weight, (int)cps, (int)total);
+  return (int)cudaGetLastError();
+}
+
 template <int C, int LS_STAGES, int LS_P>
 static int launch_bulk(cudaLaunchConfig_t &cfg, const float *logits, const long long *lab, int N, int64_t HW, const float *cw, int ignore_index,
                        float grad_scale, float *loss_out, float *dlogits, uint8_t *pred, double *acc, unsigned int *counter, float dice_weight,
@@ -500,6 +792,10 @@ static int launch_ce_dice(const float *logits, const int64_t *labels, int N, int
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = g_opt.loss_no_pdl ? 0 : 1;
+  if (VEC == 4 && dlogits != nullptr && !g_opt.loss_no_bulk && !g_opt.loss_variant) {     // loss_variant = 1: two-pass kernels (A/B comparisons)
+    const int rc = launch_resident(logits, lab, N, HW, cw, ignore_index, grad_scale, loss_out, dlogits, pred, acc, counter, dice_weight, st);
+    if (rc >= 0) return rc;
+  }
   if (VEC == 4 && !g_opt.loss_no_bulk) {
     // measured (scripts/bench_loss.py): 3 x 1024-pixel stages = 31.5 us; 6 x 512: 32.3; 4 x 1024: 31.7; 8 x 256: 37.1
     const int rc = launch_bulk<C, 3, 1024>(cfg, logits, lab, N, HW, cw, ignore_index, grad_scale, loss_out, dlogits, pred, acc, counter, dice_weight, st);

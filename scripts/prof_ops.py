@@ -1,4 +1,4 @@
-"""Per-op CUDA-event timing of one eager training step of a bench workload:  python scripts/prof_ops.py <workload> [batch]"""
+"""Per-op CUDA-event timing of one eager training step of a bench workload:  python scripts/prof_ops.py <workload> [batch] [opt=value,...]"""
 import collections, sys
 from pathlib import Path
 import torch
@@ -32,6 +32,8 @@ else:
     stepper = FusedSegStepper(model, configs, mc)
     inputs = (torch.cat((b[2], b[6], b[9]), 1).to(dev), b[3].to(dev))
 eng = stepper._engine(inputs[0]); ops = eng.ops
+for kv in (sys.argv[3].split(',') if len(sys.argv) > 3 else []):
+    ops.set_option(kv.split('=')[0], int(kv.split('=')[1]))
 for _ in range(2): eng.train_step(*inputs)
 torch.cuda.synchronize()
 times = collections.OrderedDict(); orig = {}

@@ -79,7 +79,7 @@ def test_wgrad_simt(ops, sh, dtype, ks):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("cin,H,W", [(2, 24, 40), (3, 17, 33)])
+@pytest.mark.parametrize("cin,H,W", [(2, 24, 40), (3, 17, 33), (2, 50, 70)])
 def test_stem_kernels(ops, sh, dtype, cin, H, W):
     g = _gen(8)
     N = 3
@@ -326,6 +326,43 @@ def test_loss_kernel_full_size_vs_oracle_and_properties(ops):
     r = ce_dice(logits[sub].cpu().numpy(), labels[sub].cpu().numpy(), [1.0, 1.0, 1.0], 3)
     np.testing.assert_allclose(loss3b[0].item(), r["loss"], rtol=1e-5)
     np.testing.assert_allclose(dl2[sub].cpu().numpy(), r["dlogits"], rtol=2e-3, atol=1e-10)
+
+
+@pytest.mark.parametrize("N,H,W", [(3, 64, 64), (5, 224, 224), (64, 224, 224), (2, 36, 100), (150, 64, 64), (70, 224, 224)])
+def test_loss_resident_single_pass_matches_two_pass_and_oracle(ops, N, H, W):
+    """The resident single-pass CE+Dice kernel (logits kept on the SMs across the grid barrier) against the two-pass kernels on the same
+    workspace (alternating calls exercise the self-cleaning flip protocol) and, on a 2-sample slice, the numpy oracle.  Shapes: whole and
+    ragged 2048-pixel chunks, more chunks than CTAs, fewer chunks than CTAs, and (70 x 224 x 224) beyond the on-chip capacity (falls back)."""
+    from oracle.loss_oracle import ce_dice
+    g = _gen(60 + N)
+    logits = (2.0 * torch.randn(N, 3, H, W, generator=g)).to(DEV)
+    labels = torch.randint(0, 4, (N, H, W), generator=g).to(DEV)
+    w = torch.tensor([0.5, 2.0, 1.25], device=DEV)
+    ws = ops.ce_dice_workspace(N, DEV)
+    outs = []
+    try:
+        for variant in (0, 1, 0, 0, 1):
+            ops.set_option("loss_variant", variant)
+            loss3, dl = torch.zeros(3, device=DEV), torch.full_like(logits, 7.0)
+            pred = torch.full((N, H, W), 9, dtype=torch.uint8, device=DEV)
+            ops.ce_dice(logits, labels, w, 3, 1.0, loss3, dl, pred, ws, dice_weight=0.7)
+            torch.cuda.synchronize()
+            outs.append((loss3.clone(), dl, pred))
+    finally:
+        ops.set_option("loss_variant", 0)
+    l0, d0, p0 = outs[0]
+    assert torch.equal(p0.long(), logits.argmax(1))
+    for l, d, pr in outs[1:]:
+        assert torch.equal(pr, p0)
+        assert torch.allclose(l, l0, rtol=5e-6), (l, l0)
+        assert torch.allclose(d, d0, rtol=1e-4, atol=1e-12)
+    assert torch.equal(outs[2][1], d0) and torch.equal(outs[3][1], d0)          # same kernel, same workspace state -> bit-identical
+    sub = slice(0, 2)
+    loss3b, dl2 = torch.zeros(3, device=DEV), torch.zeros_like(logits[sub])
+    ops.ce_dice(logits[sub].contiguous(), labels[sub].contiguous(), w, 3, 1.0, loss3b, dl2, None, ops.ce_dice_workspace(2, DEV))
+    r = ce_dice(logits[sub].cpu().numpy(), labels[sub].cpu().numpy(), [0.5, 2.0, 1.25], 3)
+    np.testing.assert_allclose(loss3b[0].item(), r["loss"], rtol=1e-5)
+    np.testing.assert_allclose(dl2.cpu().numpy(), r["dlogits"], rtol=2e-3, atol=1e-10)
 
 
 def test_adam(ops, sh):
