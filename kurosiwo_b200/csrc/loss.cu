@@ -591,9 +591,10 @@ ce_dice_resident_kernel(const float *__restrict__ logits, const long long *__res
 #pragma unroll
           for (int cc = 1; cc < C; ++cc) { if (zz[cc][i] > m) { m = zz[cc][i]; am = (uint32_t)cc; } }      // first maximum, as torch.argmax
           float ar[C], e[C], ssum = 0.f;
+          const float mL = -m * L2E;
 #pragma unroll
           for (int cc = 0; cc < C; ++cc) {
-            ar[cc] = (zz[cc][i] - m) * L2E;
+            ar[cc] = fmaf(zz[cc][i], L2E, mL);
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[cc]) : "f"(ar[cc]));
             ssum += e[cc];
           }
@@ -627,35 +628,63 @@ ce_dice_resident_kernel(const float *__restrict__ logits, const long long *__res
     if ((tid & 31) == 0) { red[tid >> 5] = d2; red[(TH / 32) + (tid >> 5)] = d3; }
   }
   __syncthreads();
-  if (tid < MAXC) {
-    const int k = blockIdx.x + tid * G;
+  // ---- grid barrier: the gradient needs ONE global scalar, ce_den.  Thread 0 publishes this CTA's share and arrives; the other
+  // sums (I_n, S_n, ce_num: loss value only) are added off the critical path - the last CTA reads them after the end-of-kernel ticket.
+  if (tid == 0) {
+    double sden = 0.0;
+    for (int i = 0; i < TH / 32; ++i) sden += red[(TH / 32) + i];
+    atomicAdd(acc + 4 * (size_t)N + 1, sden);
+    __threadfence();
+    atomicAdd(ctrl + 2, 1u);
+  } else if (tid >= 32 && tid < 32 + MAXC) {
+    const int jj = tid - 32, k = blockIdx.x + jj * G;
     if (k < total) {
       const int n = k / cps;
       const int p0 = (k - n * cps) * P;
       const double npx = (double)min(P, HW - p0);
       // I_n = Sum_px (T0 + p_yd), S_n = Sum_px (1 + (C-1) T0 + T1): the constants are added per pixel count in double
-      atomicAdd(acc + 4 * n, (double)sI[tid] + npx * (double)T0);
+      atomicAdd(acc + 4 * n, (double)sI[jj] + npx * (double)T0);
       atomicAdd(acc + 4 * n + 1, npx * (1.0 + (double)(C - 1) * (double)T0 + (double)T1));
       __threadfence();
     }
-  } else if (tid == 32 || tid == 33) {
-    const int o = (tid - 32) * (TH / 32);
-    double sred = 0.0;
-    for (int i = 0; i < TH / 32; ++i) sred += red[o + i];
-    atomicAdd(acc + 4 * (size_t)N + (tid - 32), sred);       // totals {ce_num, ce_den}
+  } else if (tid == 64) {
+    double snum = 0.0;
+    for (int i = 0; i < TH / 32; ++i) snum += red[i];
+    atomicAdd(acc + 4 * (size_t)N, snum);
     __threadfence();
   }
-  __syncthreads();
-  // ---- grid barrier: every CTA's ce_den contribution is in ----
   if (tid == 0) {
-    __threadfence();
-    atomicAdd(ctrl + 2, 1u);
     unsigned int spins = 0;
     while (ld_acquire_u32(ctrl + 2) < (unsigned int)G) {
       if (++spins > (1u << 24)) { atomicExch(ctrl + 3, 1u); break; }     // never hang the device: poison the loss instead
     }
   }
   __syncthreads();
+  // ---- loss value + workspace clean-up: one warp of the LAST CTA to post its sums (every CTA has passed the grid barrier by then;
+  // the other half / the counters are not touched by anyone else in this call), so the kernel ends with the last gradient store ----
+  if (tid == 0) s_ticket = atomicAdd(ctrl, 1u);
+  __syncthreads();
+  if (s_ticket == (unsigned int)G - 1 && tid < 32) {
+    __threadfence();
+    double dice = 0.0;
+    for (int i = tid; i < N; i += 32) {
+      const double I = __ldcg(acc + 4 * i), S = __ldcg(acc + 4 * i + 1);
+      dice += 1.0 - 2.0 * I / (S + 1e-6);
+    }
+    dice = warp_sum_d(dice);
+    if (tid == 0) {
+      dice /= (double)N;
+      const double num = __ldcg(acc + 4 * (size_t)N), den = __ldcg(acc + 4 * (size_t)N + 1);
+      const double cel = num / den;                    // NaN when every pixel is ignored (as torch)
+      const bool poisoned = ld_acquire_u32(ctrl + 3) != 0u;
+      const float nanv = __int_as_float(0x7fc00000);
+      loss_out[0] = poisoned ? nanv : (float)((double)dice_weight * dice + cel);
+      loss_out[1] = poisoned ? nanv : (float)dice; loss_out[2] = poisoned ? nanv : (float)cel;
+      ctrl[2] = 0u;
+    }
+    __syncwarp();
+    finish_workspace(ws, ctrl, N);
+  }
   // ---- phase 2: gradient from the resident probabilities ----
   {
     const double Sn = (double)HW * (1.0 + (double)(C - 1) * (double)T0 + (double)T1) + 1e-6;
@@ -696,30 +725,6 @@ ce_dice_resident_kernel(const float *__restrict__ logits, const long long *__res
       }
       cur.advance(G, gd, gq, cps);
     }
-  }
-  // ---- loss value + workspace clean-up: one warp of the LAST CTA to finish ----
-  if (tid == 0) s_ticket = atomicAdd(ctrl, 1u);
-  __syncthreads();
-  if (s_ticket == (unsigned int)G - 1 && tid < 32) {
-    __threadfence();
-    double dice = 0.0;
-    for (int i = tid; i < N; i += 32) {
-      const double I = __ldcg(acc + 4 * i), S = __ldcg(acc + 4 * i + 1);
-      dice += 1.0 - 2.0 * I / (S + 1e-6);
-    }
-    dice = warp_sum_d(dice);
-    if (tid == 0) {
-      dice /= (double)N;
-      const double num = __ldcg(acc + 4 * (size_t)N), den = __ldcg(acc + 4 * (size_t)N + 1);
-      const double cel = num / den;                    // NaN when every pixel is ignored (as torch)
-      const bool poisoned = ld_acquire_u32(ctrl + 3) != 0u;
-      const float nanv = __int_as_float(0x7fc00000);
-      loss_out[0] = poisoned ? nanv : (float)((double)dice_weight * dice + cel);
-      loss_out[1] = poisoned ? nanv : (float)dice; loss_out[2] = poisoned ? nanv : (float)cel;
-      ctrl[2] = 0u;
-    }
-    __syncwarp();
-    finish_workspace(ws, ctrl, N);
   }
 }
 

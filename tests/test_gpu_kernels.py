@@ -355,7 +355,7 @@ def test_loss_resident_single_pass_matches_two_pass_and_oracle(ops, N, H, W):
     for l, d, pr in outs[1:]:
         assert torch.equal(pr, p0)
         assert torch.allclose(l, l0, rtol=5e-6), (l, l0)
-        assert torch.allclose(d, d0, rtol=1e-4, atol=1e-12)
+        assert torch.allclose(d, d0, rtol=1e-4, atol=1e-10)      # |d| ~ 1 / (N H W) = 1e-4 .. 1e-6; cancellation in w_y (p_y - 1)
     assert torch.equal(outs[2][1], d0) and torch.equal(outs[3][1], d0)          # same kernel, same workspace state -> bit-identical
     sub = slice(0, 2)
     loss3b, dl2 = torch.zeros(3, device=DEV), torch.zeros_like(logits[sub])
