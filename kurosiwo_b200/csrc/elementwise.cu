@@ -244,10 +244,13 @@ __global__ void bn_finalize_kernel(int C, double count, const double *__restrict
 // ------------------------------------------------------------------------------------------
 
 // out = relu(y*scale+shift (+res)), optional fused 2x2 max-pool output
-template <typename T, int V, bool POOL>
+// Bytes in flight decide these passes (B200: ~32 KB per SM in flight measured 4.4 TB/s, ~96 KB 6.2 TB/s): the pixel unroll is chosen
+// per instantiation so that every thread keeps 8-12 independent 16-byte loads outstanding whatever the number of input tensors.
+template <typename T, int V, bool POOL, bool HAS_RES>
 __global__ void __launch_bounds__(256, 2)
-bn_act_kernel(View y, View res, bool has_res, View out, View pool, int N, int H, int W,
+bn_act_kernel(View y, View res, View out, View pool, int N, int H, int W,
               const float *__restrict__ scale, const float *__restrict__ shift, int relu, bool flat) {
+  constexpr bool has_res = HAS_RES;
   const int CV = y.C / V, rows = blockDim.x / CV;
   const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
   if (ty >= rows) return;
@@ -295,23 +298,23 @@ bn_act_kernel(View y, View res, bool has_res, View out, View pool, int N, int H,
       VecIO<T, V>::st(pp + (n * pool.sn + (long long)hp * pool.sh + (long long)wp * pool.sw), mx);
     }
   } else {
-    constexpr int U = Unr<T>::value;
+    constexpr int U = HAS_RES ? (Unr<T>::value * 3) / 2 : Unr<T>::value * 2;
     const long long npix = (long long)N * H * W, stride = (long long)gridDim.x * rows;
     for (long long p0 = (long long)blockIdx.x * rows + ty; p0 < npix; p0 += stride * U) {
-      Raw<T, V> ry[U], rr[U];
+      Raw<T, V> ry[U], rr[HAS_RES ? U : 1];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long p = p0 + u * stride;
         if (p < npix) {
           ry[u].ld(yp + pix_off(y, p, H, W, flat));
-          if (has_res) rr[u].ld(rp + pix_off(res, p, H, W, flat));
+          if (has_res) rr[HAS_RES ? u : 0].ld(rp + pix_off(res, p, H, W, flat));
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long p = p0 + u * stride;
         float o[V];
-        if (p < npix) finish(ry[u], rr[u], p, o);
+        if (p < npix) finish(ry[u], rr[HAS_RES ? u : 0], p, o);
       }
     }
   }
@@ -345,17 +348,17 @@ bn_bwd_reduce_kernel(View dout, View out, View y, int N, int H, int W, const flo
     T *gp = reinterpret_cast<T *>(dout.ptr) + c;
     const T *op = reinterpret_cast<const T *>(out.ptr) + c;
     const T *yp = reinterpret_cast<const T *>(y.ptr) + c;
-    constexpr int U = Unr<T>::value;
+    constexpr int U = MASK_OUT ? Unr<T>::value : (Unr<T>::value * 3) / 2;     // 12 loads in flight per thread either way
     const long long stride = (long long)gridDim.x * rows;
     for (long long p0 = (long long)blockIdx.x * rows + ty; p0 < npix; p0 += stride * U) {
-      Raw<T, V> rg[U], ro[U], rf[U];
+      Raw<T, V> rg[U], ro[MASK_OUT ? U : 1], rf[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long p = p0 + u * stride;
         if (p < npix) {
           rg[u].ld(gp + pix_off(dout, p, H, W, flat));
           rf[u].ld(yp + pix_off(y, p, H, W, flat));
-          if (MASK_OUT) ro[u].ld(op + pix_off(out, p, H, W, flat));
+          if (MASK_OUT) ro[MASK_OUT ? u : 0].ld(op + pix_off(out, p, H, W, flat));
         }
       }
 #pragma unroll
@@ -364,7 +367,7 @@ bn_bwd_reduce_kernel(View dout, View out, View y, int N, int H, int W, const flo
         if (p < npix) {
           float g[V], o[V], f[V];
           rg[u].get(g); rf[u].get(f);
-          if (MASK_OUT) ro[u].get(o);
+          if (MASK_OUT) ro[MASK_OUT ? u : 0].get(o);
 #pragma unroll
           for (int k = 0; k < V; ++k) {
             const bool on = MASK_OUT ? (o[k] > 0.f) : (fmaf(f[k], sc[k], sh[k]) > 0.f);
@@ -384,7 +387,7 @@ bn_bwd_reduce_kernel(View dout, View out, View y, int N, int H, int W, const flo
 // pass 1 for encoder outputs: as MASK_OUT above, with the 2x2 max-pool backward folded in.  Each thread owns whole
 // pooling windows: g = (dout + [pixel is the window's first maximum] * dpool) * (out > 0), written back over dout.
 template <typename T, int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce_pool_kernel(View dout, View out, View y, View dpool, int N, int H, int W,
                           const float *__restrict__ mean, const float *__restrict__ rstd, double *sums, bool flat) {
   extern __shared__ float smem[];
@@ -448,9 +451,9 @@ bn_bwd_reduce_pool_kernel(View dout, View out, View y, View dpool, int N, int H,
 }
 
 // pass 2: dy = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M) (+ add) = a*g + (k1*y + k0) (+ add);  `premasked`: g already masked by pass 1
-template <typename T, int V>
+template <typename T, int V, bool HAS_ADD>
 __global__ void __launch_bounds__(256, 2)
-bn_bwd_apply_kernel(View gin, View y, View add, bool has_add, View dy, int N, int H, int W, int premasked,
+bn_bwd_apply_kernel(View gin, View y, View add, View dy, int N, int H, int W, int premasked,
                     const float *__restrict__ scale, const float *__restrict__ shift,
                     const float *__restrict__ mean, const float *__restrict__ rstd, const float *__restrict__ gamma,
                     const double *__restrict__ sums, double count, float *dgamma, float *dbeta, float *dsum_out,
@@ -482,16 +485,17 @@ bn_bwd_apply_kernel(View gin, View y, View add, bool has_add, View dy, int N, in
   const T *ap = reinterpret_cast<const T *>(add.ptr) + c;
   T *dp = reinterpret_cast<T *>(dy.ptr) + c;
   const long long npix = (long long)N * H * W, stride = (long long)gridDim.x * rows;
-  constexpr int U = Unr<T>::value;
+  constexpr bool has_add = HAS_ADD;
+  constexpr int U = HAS_ADD ? Unr<T>::value : (Unr<T>::value * 3) / 2;
   for (long long p0 = (long long)blockIdx.x * rows + ty; p0 < npix; p0 += stride * U) {
-    Raw<T, V> rg[U], rf[U], ra[U];
+    Raw<T, V> rg[U], rf[U], ra[HAS_ADD ? U : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long p = p0 + u * stride;
       if (p < npix) {
         rg[u].ld(gp + pix_off(gin, p, H, W, flat));
         rf[u].ld(yp + pix_off(y, p, H, W, flat));
-        if (has_add) ra[u].ld(ap + pix_off(add, p, H, W, flat));
+        if (has_add) ra[HAS_ADD ? u : 0].ld(ap + pix_off(add, p, H, W, flat));
       }
     }
 #pragma unroll
@@ -500,7 +504,7 @@ bn_bwd_apply_kernel(View gin, View y, View add, bool has_add, View dy, int N, in
       if (p < npix) {
         float g[V], f[V], ad[V], d[V];
         rg[u].get(g); rf[u].get(f);
-        if (has_add) ra[u].get(ad);
+        if (has_add) ra[HAS_ADD ? u : 0].get(ad);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
           const bool on = premasked ? true : (fmaf(f[k], sc[k], sh[k]) > 0.f);
@@ -741,8 +745,10 @@ extern "C" int ks_bn_act(int dtype, int N, int H, int W, const ks_view_t *y, con
   const View vy = to_view(*y), vo = to_view(*out), vr = res ? to_view(*res) : vy, vp = pool ? to_view(*pool) : vo;
 #define CALL(T, V) { const long long np = (long long)N * (pool ? H / 2 : H) * (pool ? W / 2 : W); \
     const int grid = pl_grid(y->C, V, np, pool ? 2 : 8); \
-    if (pool) bn_act_kernel<T, V, true><<<grid, 256, 0, st>>>(vy, vr, res != nullptr, vo, vp, N, H, W, scale, shift, relu, flat); \
-    else bn_act_kernel<T, V, false><<<grid, 256, 0, st>>>(vy, vr, res != nullptr, vo, vp, N, H, W, scale, shift, relu, flat); }
+    if (pool && res) bn_act_kernel<T, V, true, true><<<grid, 256, 0, st>>>(vy, vr, vo, vp, N, H, W, scale, shift, relu, flat); \
+    else if (pool) bn_act_kernel<T, V, true, false><<<grid, 256, 0, st>>>(vy, vr, vo, vp, N, H, W, scale, shift, relu, flat); \
+    else if (res) bn_act_kernel<T, V, false, true><<<grid, 256, 0, st>>>(vy, vr, vo, vp, N, H, W, scale, shift, relu, flat); \
+    else bn_act_kernel<T, V, false, false><<<grid, 256, 0, st>>>(vy, vr, vo, vp, N, H, W, scale, shift, relu, flat); }
   KS_DISPATCH_TV(dtype, vec, CALL);
 #undef CALL
   KS_LAUNCH_RET();
@@ -785,7 +791,9 @@ extern "C" int ks_bn_bwd_apply(int dtype, int N, int H, int W, const ks_view_t *
   cudaStream_t st = (cudaStream_t)stream;
   const View vg = to_view(*g), vy = to_view(*y), vdy = to_view(*dy), va = has_add ? to_view(*add) : vg;
 #define CALL(T, V) { const int grid = pl_grid(y->C, V, (long long)N * H * W, 8); \
-    bn_bwd_apply_kernel<T, V><<<grid, 256, 0, st>>>(vg, vy, va, has_add, vdy, N, H, W, premasked, scale, shift, mean, rstd, gamma, sums, count, \
+    if (has_add) bn_bwd_apply_kernel<T, V, true><<<grid, 256, 0, st>>>(vg, vy, va, vdy, N, H, W, premasked, scale, shift, mean, rstd, gamma, sums, count, \
+                                                 dgamma, dbeta, dsum_out, accumulate_param_grads, flat); \
+    else bn_bwd_apply_kernel<T, V, false><<<grid, 256, 0, st>>>(vg, vy, va, vdy, N, H, W, premasked, scale, shift, mean, rstd, gamma, sums, count, \
                                                  dgamma, dbeta, dsum_out, accumulate_param_grads, flat); }
   KS_DISPATCH_TV(dtype, vec, CALL);
 #undef CALL
