@@ -17,7 +17,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 BUILD = HERE.parent / "build" / "ks_obj"
 LIB = HERE / "libkurosiwo_b200.so"
-SOURCES = ["loss.cu", "siam.cu", "vit.cu", "cformer.cu", "elementwise.cu", "ecam.cu", "conv_simt.cu", "stem.cu", "conv_api.cu", "conv_tc.cu", "wgrad_tc.cu", "attention_tc.cu"]
+SOURCES = ["loss.cu", "siam.cu", "vit.cu", "cformer.cu", "elementwise.cu", "ecam.cu", "conv_simt.cu", "stem.cu", "conv_api.cu", "conv_tc.cu", "wgrad_tc.cu", "attention_tc.cu", "xattention_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

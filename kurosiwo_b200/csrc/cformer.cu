@@ -1122,11 +1122,25 @@ static int xa_cfg(int B, int Nq, int Nk, int heads, int dh, int nbuf, size_t &sm
   return KS_OK;
 }
 
+namespace ks {
+int xattention_fwd_umma(int B, int Nq, int Nk, int heads, const void *q, long long ldq, const void *kv, long long ldkv, float scale,
+                        void *out, long long ldo, void *probs, float pdrop, unsigned long long seed, const int *step_ptr, int site,
+                        cudaStream_t st);
+}
+
 extern "C" int ks_xattention_fwd(int dtype, int B, int Nq, int Nk, int heads, int dh, const void *q, int64_t ldq, const void *kv, int64_t ldkv,
                                  float scale, void *out, int64_t ldo, void *probs, float pdrop, uint64_t seed, const int *step_ptr, int site,
                                  void *stream) {
   KS_CHECK_ARG(pdrop >= 0.f && pdrop < 1.f);
   KS_CHECK_ARG(B > 0 && Nq > 0 && heads > 0 && q && kv && out && probs);
+  // tcgen05 variant (xattention_tc.cu): opt-in.  Measured on B200 (ChangeFormer bs=32, 13 calls per step): 0.915 vs 0.975 ms for the mma.sync
+  // kernel below - a tile is 8 UMMAs next to a 49-wide softmax + dropout RNG per row, so the tensor-core path buys 6 % - and the two are
+  // numerically equivalent (same error against an fp32 reference), but every rounding-level change of the attention output moves the
+  // random-init bf16 gradients the end-to-end drift test pins (64 one-ulp flips: 3 % of the gradient norm), so the default stays put.
+  if (dtype == KS_BF16 && dh == 64 && Nk >= 1 && Nk <= 64 && !g_opt.att_simt && g_opt.xatt_umma) {
+    const int rc = xattention_fwd_umma(B, Nq, Nk, heads, q, ldq, kv, ldkv, scale, out, ldo, probs, pdrop, seed, step_ptr, site, (cudaStream_t)stream);
+    if (rc != KS_EUNSUPPORTED) return rc;
+  }
   if (dtype == KS_BF16 && dh == 64 && Nk >= 1 && Nk <= 64 && !g_opt.att_simt && a16(kv) && (ldkv * 2) % 16 == 0 && ((uintptr_t)q % 4) == 0 &&
       (ldq % 2) == 0 && ((uintptr_t)out % 4) == 0 && (ldo % 2) == 0) {
     int nb = 1;

@@ -193,19 +193,23 @@ class SNUNetEngine(TrainStepMixin):
         return jobs
 
     def _unpack_jobs(self):
-        P, jobs = self.params, []
+        """Three groups by the point of the backward at which the packed gradients are final (data-parallel overlap, see backward()):
+        "dec" = nested-decoder blocks + every ConvTranspose (after the decoder loop), "l4" = conv4_0 (executed for one date only: final
+        after its own backward), "enc" = the shared encoder blocks conv0_0..conv3_0 (final after the second date, i.e. at the end)."""
+        P, jobs = self.params, {"dec": [], "l4": [], "enc": []}
         for bn_ in self.block_names:
             l = int(bn_[4])
             cin, fl = self.block_cin[bn_], self.f[l]
+            grp = "dec" if int(bn_[6:]) >= 1 else ("l4" if l == 4 else "enc")
             for tag, (co, ci) in (("conv1", (fl, cin)), ("conv2", (fl, fl))):
                 if self.use_stem and bn_ == "conv0_0" and tag == "conv1":
                     continue
                 # grad[o][i][t] = gp[t][o][i]
-                jobs.append((self.gp[f"{bn_}.{tag}"], P.g(f"{bn_}.{tag}.weight"), (co, ci, 9), (ci, 1, co * ci), 0))
+                jobs[grp].append((self.gp[f"{bn_}.{tag}"], P.g(f"{bn_}.{tag}.weight"), (co, ci, 9), (ci, 1, co * ci), 0))
         for (l, j), nm in self.up_names.items():
             c = self.f[l + 1]
             # grad[ci][co][k] = gp[k][co][ci]
-            jobs.append((self.gp[nm], P.g(f"{nm}.up.weight"), (c, c, 4), (1, c, c * c), 0))
+            jobs["dec"].append((self.gp[nm], P.g(f"{nm}.up.weight"), (c, c, 4), (1, c, c * c), 0))
         return jobs
 
     def _tables(self):
@@ -213,15 +217,17 @@ class SNUNetEngine(TrainStepMixin):
         key = (self.params.flat.data_ptr(), self.params.grad.data_ptr())
         if getattr(self, "_table_key", None) != key:
             self._pack_table = self.ops.make_permute_table(self._pack_jobs(), self.device)
-            self._unpack_table = self.ops.make_permute_table(self._unpack_jobs(), self.device)
+            self._unpack_table = {g: self.ops.make_permute_table(j, self.device) for g, j in self._unpack_jobs().items() if j}
             self._table_key = key
         return self._pack_table, self._unpack_table
 
     def _pack_weights(self):
         self.ops.permute_cast_table(self._tables()[0])
 
-    def _unpack_grads(self):
-        self.ops.permute_cast_table(self._tables()[1])
+    def _unpack_grads(self, group: str):
+        t = self._tables()[1].get(group)
+        if t is not None:
+            self.ops.permute_cast_table(t)
 
     def _ensure_nbt(self):
         """num_batches_tracked of every BatchNorm as views into one int64 buffer (re-pointed after .to()/load)."""
@@ -390,6 +396,13 @@ class SNUNetEngine(TrainStepMixin):
             written.add(tgt)
             ops.conv2d_wgrad(N, h1, w1, 1, [self.slot(self.X, l + 1, j)], phases, self.gp[nm], False, self.conv_impl)
             ops.channel_sum(dup, P.g(f"{nm}.up.bias"), False)
+        # Data-parallel overlap: everything registered from conv0_1 on (decoder blocks, their ConvTransposes, ECAM, classifier) is final
+        # here, conv4_0 + Up4_0 (registered right before conv0_1) after the first encoder block below: the flat gradient range
+        # [conv4_0 .., end) = 83 % of the bytes goes out under the rest of the encoder backward, the shared encoder blocks at the end.
+        self._unpack_grads("dec")
+        off = P.offsets
+        if "conv0_1.conv1.weight" in off:
+            self._grads_ready(off["conv0_1.conv1.weight"][0], P.numel)
         for br in (1, 0):
             for l in (4, 3, 2, 1, 0):
                 if l == 4 and br == 0:
@@ -406,4 +419,8 @@ class SNUNetEngine(TrainStepMixin):
                 gd = None if l == 0 else [self.dP[(l, br)]]
                 self._block_backward(e, gd, None if gd is None else [False], e.name not in seen_blocks, dpool)
                 seen_blocks.add(e.name)
-        self._unpack_grads()
+                if l == 4:
+                    self._unpack_grads("l4")
+                    if "conv4_0.conv1.weight" in off and "conv0_1.conv1.weight" in off:
+                        self._grads_ready(off["conv4_0.conv1.weight"][0], off["conv0_1.conv1.weight"][0])
+        self._unpack_grads("enc")

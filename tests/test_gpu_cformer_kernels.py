@@ -61,7 +61,7 @@ def test_strided_conv_family(ops, sh, dtype, k, s, p, cin, cout, H):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("B,Nq,Nk,heads,dh", [(2, 64, 49, 1, 64), (3, 196, 49, 4, 80), (2, 49, 49, 8, 64), (1, 100, 17, 2, 32)])
+@pytest.mark.parametrize("B,Nq,Nk,heads,dh", [(2, 64, 49, 1, 64), (3, 196, 49, 4, 80), (2, 49, 49, 8, 64), (1, 100, 17, 2, 32), (2, 784, 49, 2, 64), (3, 196, 49, 5, 64), (4, 3136, 49, 1, 64)])
 def test_xattention_fwd_bwd(ops, sh, dtype, B, Nq, Nk, heads, dh):
     g = torch.Generator().manual_seed(2)
     inner = heads * dh
@@ -73,6 +73,24 @@ def test_xattention_fwd_bwd(ops, sh, dtype, B, Nq, Nk, heads, dh):
     ops.xattention_fwd(B, Nq, Nk, heads, dh, q.to(DEV), kv.to(DEV), scale, outd, probsd)
     assert rel_l2(probsd.float(), probs.float()) < _tol(dtype)
     assert rel_l2(outd.float(), out.float()) < _tol(dtype)
+    if dtype == torch.bfloat16 and dh == 64:
+        # the tcgen05 variant (TMA -> UMMA -> TMEM softmax -> UMMA; opt-in, csrc/xattention_tc.cu) against the same shadow and, within
+        # one bf16 ulp of the probabilities, against the mma.sync kernel; with dropout both draw the same stateless masks
+        try:
+            ops.set_option("xatt_umma", 1)
+            outu, probsu = torch.ones_like(outd), torch.ones_like(probsd)
+            ops.xattention_fwd(B, Nq, Nk, heads, dh, q.to(DEV), kv.to(DEV), scale, outu, probsu)
+            assert rel_l2(probsu.float(), probs.float()) < _tol(dtype) and rel_l2(outu.float(), out.float()) < _tol(dtype)
+            assert (probsu.float() - probsd.float()).abs().max().item() <= 2.0 ** -8
+            step = torch.zeros(1, dtype=torch.int32, device=DEV)
+            od, ou = torch.zeros_like(outd), torch.zeros_like(outd)
+            ops.set_option("xatt_umma", 0)
+            ops.xattention_fwd(B, Nq, Nk, heads, dh, q.to(DEV), kv.to(DEV), scale, od, probsd, 0.25, 777, step, 5)
+            ops.set_option("xatt_umma", 1)
+            ops.xattention_fwd(B, Nq, Nk, heads, dh, q.to(DEV), kv.to(DEV), scale, ou, probsu, 0.25, 777, step, 5)
+            assert rel_l2(ou.float(), od.float()) < 2e-2
+        finally:
+            ops.set_option("xatt_umma", 0)
     dout = _r((B * Nq, inner), dtype, g)
     dq, dkv = torch.zeros_like(q), torch.zeros(B * Nk * 2 * inner)
     sh.xattention_bwd(B, Nq, Nk, heads, dh, q, kv, probs, dout, scale, dq, dkv)
