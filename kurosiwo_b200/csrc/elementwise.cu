@@ -84,6 +84,23 @@ permute_cast_batched_kernel(const ks_permute_job_t *__restrict__ jobs, const int
     }
     return;
   }
+  if (j.total < (1ll << 31) && !j.dst_strided && !j.accumulate && j.src_dtype == KS_F32 && j.d3 == 1) {
+    // the conv-weight packs / gradient unpacks of a step ([t][o][i] <-> OIHW): 32-bit index arithmetic (the 64-bit divisions of the
+    // generic loop below were ~100 instructions per element: 0.21 ms per SNUNet step for 36 M elements)
+    const float *sp = reinterpret_cast<const float *>(j.src);
+    const unsigned int d1 = (unsigned int)j.d1, d2 = (unsigned int)j.d2;
+    const int s0 = (int)j.s0, s1 = (int)j.s1, s2 = (int)j.s2;
+    for (unsigned int i = (unsigned int)ch.y + threadIdx.x; i < (unsigned int)end; i += blockDim.x) {
+      unsigned int r = i;
+      const unsigned int i2 = r % d2; r /= d2;
+      const unsigned int i1 = r % d1; r /= d1;
+      float v = sp[(long long)((int)r * s0 + (int)i1 * s1 + (int)i2 * s2)];
+      if (j.scale != 0.f) v *= j.scale;
+      if (j.dst_dtype == KS_F32) reinterpret_cast<float *>(j.dst)[i] = v;
+      else reinterpret_cast<__nv_bfloat16 *>(j.dst)[i] = __float2bfloat16_rn(v);
+    }
+    return;
+  }
   for (long long i = ch.y + threadIdx.x; i < end; i += blockDim.x) {
     long long r = i;
     const int i3 = (int)(r % j.d3); r /= j.d3;
