@@ -288,8 +288,9 @@ __device__ __forceinline__ void issue_taps(uint32_t a_lo_row, uint32_t a_tile_st
 
 // EW = epilogue warps: 8 (320 threads, up to 2 CTAs per SM) or 16 (576 threads, ONE CTA per SM: configurations whose weights or
 // TMEM columns already pin the CTA count to one and whose epilogue - 4 sequential 32-column items per warp - paced the kernel).
-template <int BK, int KS, bool NS3, int EW>
-__global__ void __launch_bounds__(64 + 32 * EW, EW == 8 ? 2 : 1) conv_tc2_kernel(const __grid_constant__ ConvTcParams p) {
+// STATR: BatchNorm statistics in per-thread registers over the CTA's tiles (2 x 32 floats; one CTA per SM), reduced once at CTA exit.
+template <int BK, int KS, bool NS3, int EW, bool STATR>
+__global__ void __launch_bounds__(64 + 32 * EW, (EW == 8 && !STATR) ? 2 : 1) conv_tc2_kernel(const __grid_constant__ ConvTcParams p) {
 #define MBW(bar, par) do { if (p.debug & 32) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int TW = (KS == 3) ? 14 : 16;
@@ -466,6 +467,12 @@ __global__ void __launch_bounds__(64 + 32 * EW, EW == 8 ? 2 : 1) conv_tc2_kernel
     const int row = lg * 32 + lane;
     const int ty = row >> 4, tx = row & 15;
     const int nchunk = (BN + 31) >> 5;
+    float ra[STATR ? 32 : 1], rq[STATR ? 32 : 1];
+    int r_cc = 0;
+    if constexpr (STATR) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { ra[i] = 0.f; rq[i] = 0.f; }
+    }
     int as = 0, pacc = 0;
     for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
       const int t0 = st * MT;
@@ -564,7 +571,16 @@ __global__ void __launch_bounds__(64 + 32 * EW, EW == 8 ? 2 : 1) conv_tc2_kernel
             if (!(p.debug & 1)) st_global_v8(op[hh], pk);
           }
         }
-        if (p.stats) {
+        if constexpr (STATR) {
+          if (p.stats) {                 // the host guarantees one fixed 32-channel chunk per warp (nchunk divides EW / 4)
+            r_cc = cc;
+            if (ok) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) { const float q = round_as<__nv_bfloat16>(v[i]); ra[i] += q; rq[i] = fmaf(q, q, rq[i]); }
+            }
+          }
+        } else
+        if (p.stats && !(p.debug & 128)) {      // tc_debug bit 7: skip the statistics work (ablation only)
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             if (hh < nh) {
@@ -586,6 +602,22 @@ __global__ void __launch_bounds__(64 + 32 * EW, EW == 8 ? 2 : 1) conv_tc2_kernel
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(as));
       if (++as == NACC) { as = 0; pacc ^= 1; }
+    }
+    if constexpr (STATR) {
+      if (p.stats) {                   // one butterfly per warp and CTA instead of one per item
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          float s1[16], s2[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { s1[i] = ra[16 * hh + i]; s2[i] = rq[16 * hh + i]; }
+          warp_reduce_scatter16(s1, lane);
+          warp_reduce_scatter16(s2, lane);
+          if ((lane & 1) == 0) {
+            const int c = r_cc + 16 * hh + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            if (c < BN) { atomicAdd(&sstat[c], s1[0]); atomicAdd(&sstat[BN + c], s2[0]); }
+          }
+        }
+      }
     }
   }
   __syncthreads();
@@ -630,15 +662,15 @@ static int launch_conv_tc(const ConvTcParams &p, dim3 grid, size_t smem, cudaStr
 
 extern "C" int ks_bn_stats(int dtype, int N, int H, int W, const ks_view_t *x, double *sums, void *stream);
 
-template <int BK, int KS, bool NS3, int EW>
+template <int BK, int KS, bool NS3, int EW, bool STATR>
 static int launch_conv_tc2(const ConvTcParams &p, dim3 grid, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BK, KS, NS3, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BK, KS, NS3, EW, STATR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  conv_tc2_kernel<BK, KS, NS3, EW><<<grid, 64 + 32 * EW, smem, st>>>(p);
+  conv_tc2_kernel<BK, KS, NS3, EW, STATR><<<grid, 64 + 32 * EW, smem, st>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -708,6 +740,12 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
   // ---- resident weights? (all [BN x BK] tiles of this N tile stay in smem for the CTA's lifetime)
   const size_t w_bytes = (size_t)p.n_wtiles * p.b_tile_bytes;
   int MT, SA, SB;
+  // BatchNorm statistics in per-thread registers over the CTA's tiles (conv_tc2_kernel<.., STATR>): for N tiles of <= 32 channels every
+  // epilogue warp owns ONE 32-channel chunk, so 64 accumulators replace the per-item shuffle butterfly + shared atomics, which stall on the
+  // same MIO pipe that feeds the UMMA operands (ncu: short-scoreboard stalls on the shuffles).  168 registers -> one CTA per SM, made up
+  // for by four output windows per super-tile.  Measured (scripts/bench_layers.py): 32->32 @ 224 0.174 -> 0.151 ms, 128->32 0.298 -> 0.244,
+  // 224->32 0.462 -> 0.443, 32->64 @ 112 0.107 -> 0.081; N tiles of 64 lose (384->64: 0.374 -> 0.469) and keep the butterfly.
+  const bool statr = !v1 && stats != nullptr && p.BN <= 32 && g_opt.stat_mode != 1;
   p.resident = 0;
   // Measured on B200 (scripts/bench_layers.py): keeping the weights resident pays when the MMAs are short
   // (BN <= 32: one [BN x BK] tile is only 2-4 KB, so per-tap barrier round trips dominate) or when K is tiny
@@ -715,7 +753,7 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
   const bool want_res = g_opt.no_resident ? false : (g_opt.mt < 0 ? true : (p.BN <= 32 || Cin <= 32 || ksize == 1));
   if (!v1 && want_res && w_bytes + 2 * p.a_tile_bytes + fixed <= budget) {
     p.resident = 1;
-    MT = g_opt.mt > 0 ? g_opt.mt : 2;
+    MT = g_opt.mt > 0 ? g_opt.mt : (statr ? 4 : 2);
     while (MT > 1 && (2 * MT * p.BNA > 512 || w_bytes + 2 * (size_t)MT * p.a_tile_bytes + fixed > budget)) MT >>= 1;
     SA = g_opt.sa > 0 ? g_opt.sa : 4;
     while (SA > 2 && w_bytes + (size_t)SA * MT * p.a_tile_bytes + fixed > budget) --SA;
@@ -806,8 +844,10 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
   // 16 epilogue warps when only one CTA fits per SM anyway and every lane group has >= 4 work items per super-tile
   const int items = MT * ((p.BN + 31) / 32);
   // measured (scripts/bench_layers.py, ew8 / ew16): 32->224 dgrad 0.532 -> 0.465 ms, 32->64 0.121 -> 0.102; with two N tiles (64->384) 4 % slower
-  const bool ew16 = g_opt.ew ? (g_opt.ew == 16) : (per_sm == 1 && items >= 4 && nt == 1);
-#define KS_LAUNCH(BKv, KSv, NS3v) (ew16 ? launch_conv_tc2<BKv, KSv, NS3v, 16>(p, grid, smem, st) : launch_conv_tc2<BKv, KSv, NS3v, 8>(p, grid, smem, st))
+  if (statr) { per_sm = 1; gx = kNumSMs / nt; if (gx < 1) gx = 1; if (gx > p.n_super) gx = p.n_super; grid = dim3((unsigned)gx, (unsigned)nt); }
+  const bool ew16 = statr ? false : (g_opt.ew ? (g_opt.ew == 16) : (per_sm == 1 && items >= 4 && nt == 1));
+#define KS_LAUNCH(BKv, KSv, NS3v) (statr ? launch_conv_tc2<BKv, KSv, NS3v, 8, true>(p, grid, smem, st) : \
+    (ew16 ? launch_conv_tc2<BKv, KSv, NS3v, 16, false>(p, grid, smem, st) : launch_conv_tc2<BKv, KSv, NS3v, 8, false>(p, grid, smem, st)))
   if (BK == 64 && ksize == 3) rc = ns3 ? KS_LAUNCH(64, 3, true) : KS_LAUNCH(64, 3, false);
   else if (BK == 64 && ksize == 1) rc = KS_LAUNCH(64, 1, false);
   else if (BK == 32 && ksize == 3) rc = ns3 ? KS_LAUNCH(32, 3, true) : KS_LAUNCH(32, 3, false);
@@ -846,6 +886,7 @@ extern "C" int ks_set_option(const char *name, int value) {
   else if (eq("stem_simt")) ks::g_opt.stem_simt = value;   // 1 = CUDA-core stem kernels also for bf16 / Cin == 2 (A/B comparisons)
   else if (eq("ecam_simt")) ks::g_opt.ecam_simt = value;   // 1 = CUDA-core ECAM final pass also for bf16 (A/B comparisons)
   else if (eq("xatt_umma")) ks::g_opt.xatt_umma = value;   // 1 = tcgen05 forward of the ChangeFormer spatial-reduction attention (default: mma.sync)
+  else if (eq("tc_stat_mode")) ks::g_opt.stat_mode = value;   // 1 = shuffle butterfly for every BatchNorm-statistics epilogue (A/B comparisons)
   else if (eq("att_no_umma")) ks::g_opt.att_no_umma = value;   // 1 = mma.sync attention forward instead of the tcgen05 kernel (A/B comparisons)
   else if (eq("att_simt")) ks::g_opt.att_simt = value;   // 1 = CUDA-core attention kernels also for bf16 (A/B comparisons)
   else if (eq("tc_debug")) ks::g_opt.debug = value;   // perf experiments only: bit0 skip epilogue stores, bit1 skip TMEM loads, bit2 skip MMAs

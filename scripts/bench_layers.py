@@ -94,6 +94,7 @@ VARIANTS = {
     "no_ns3": {"tc_no_ns3": 1},
     "ew8": {"tc_ew": 8},
     "ew16": {"tc_ew": 16},
+    "stat_butterfly": {"tc_stat_mode": 1},
     "ns3_all": {"tc_ns3_min_cin": 1},
     "ns3_two": {"tc_ns3_min_cin": 1, "tc_ns3_mode": 1},
     "ns3_one": {"tc_ns3_min_cin": 1, "tc_ns3_mode": 2},
@@ -115,7 +116,7 @@ out = {"conv": {}, "wgrad": {}}
 for name, (H, cins, couts, ks, stats) in CONV.items():
     row = {}
     for vn, opts in VARIANTS.items():
-        for o in ("tc_v1", "tc_mt", "tc_no_resident", "tc_no_ns3", "tc_ns3_min_cin", "tc_ns3_mode", "tc_ew"):
+        for o in ("tc_v1", "tc_mt", "tc_no_resident", "tc_no_ns3", "tc_ns3_min_cin", "tc_ns3_mode", "tc_ew", "tc_stat_mode"):
             ops.set_option(o, opts.get(o, 0))
         try:
             fn, fl = conv_case(H, cins, couts, ks, stats and vn != "v1")
@@ -126,7 +127,7 @@ for name, (H, cins, couts, ks, stats) in CONV.items():
         torch.cuda.empty_cache()
     out["conv"][name] = row
     print(f"{name:28s}", "  ".join(f"{k}={v}" for k, v in row.items()), flush=True)
-for o in ("tc_v1", "tc_mt", "tc_no_resident", "tc_no_ns3", "tc_ns3_min_cin", "tc_ns3_mode", "tc_ew"):
+for o in ("tc_v1", "tc_mt", "tc_no_resident", "tc_no_ns3", "tc_ns3_min_cin", "tc_ns3_mode", "tc_ew", "tc_stat_mode"):
     ops.set_option(o, 0)
 for name, (H, cins, couts) in WGRAD.items():
     fn, fl = wgrad_case(H, cins, couts)
