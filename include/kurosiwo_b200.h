@@ -56,7 +56,10 @@ typedef struct ks_view {
 int ks_version(void);
 const char *ks_error_string(int code);
 /* Tuning/debug knobs: "tc_mt" (output windows per CTA), "tc_bo_mode", "tc_disable",
- * "wgrad_tc_disable", "tc_sa", "tc_sb" (pipeline depths). Returns KS_EINVAL for unknown names. */
+ * "wgrad_tc_disable", "tc_sa", "tc_sb" (pipeline depths); A/B switches that select the OLDER kernel of a pair (never needed for
+ * correctness, every pair is parity-tested): "loss_variant" = 1 two-pass CE+Dice, "stem_simt" = 1 CUDA-core stem, "ecam_simt" = 1
+ * CUDA-core ECAM classifier pass, "tc_stat_mode" = 1 shuffle-butterfly BatchNorm statistics everywhere, "att_no_umma" = 1 mma.sync ViT
+ * attention; "xatt_umma" = 1 turns the tcgen05 forward of the ChangeFormer attention ON.  Returns KS_EINVAL for unknown names. */
 int ks_set_option(const char *name, int value);
 
 /* ---- layout / precision plumbing --------------------------------------- */
@@ -341,7 +344,10 @@ int ks_sigmoid_head_bwd(int dtype, int N, int H, int W, const float *out, const 
  * loss_out: fp32[3] = {total, dice, ce}; dlogits NCHW fp32 scaled by grad_scale
  * (may be NULL: forward only); pred: uint8 [N][HW] argmax (may be NULL).
  * workspace: ks_ce_dice_workspace_bytes(N) bytes, one per batch size N, ZERO-FILLED ONCE by the caller before its first use; every
- * call leaves it ready for the next one (the kernels re-zero what they used: no memset launch per call). */
+ * call leaves it ready for the next one (the kernels re-zero what they used: no memset launch per call).
+ * Up to 148 x 11 chunks of 2048 pixels (bs = 64 at 224 x 224) with HW % 4 == 0 and dlogits != NULL run as ONE resident pass: one CTA per SM
+ * keeps its logits on the chip across a single grid barrier (bounded spin; on a time-out loss_out becomes NaN instead of a hang), so the
+ * call must not share the GPU with a kernel that waits on it.  Other shapes / forward-only calls take two streaming passes. */
 int64_t ks_ce_dice_workspace_bytes(int N);
 int ks_ce_dice_fwd_bwd(const float *logits, const int64_t *labels, int N, int C, int64_t HW,
                        const float *class_weights, int ignore_index, float grad_scale,

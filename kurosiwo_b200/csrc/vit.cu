@@ -139,6 +139,74 @@ layernorm_bwd_rows_kernel(long long rows, int C, int L, const T *__restrict__ dy
     if (c < C) ld8(gamma + c, gm[k]);
   }
   const float invC = 1.f / (float)C;
+  if constexpr (sizeof(T) == 2) {
+    // bf16 storage: two-deep software pipeline.  The raw 16-byte vectors of the NEXT row are in flight while this one is reduced
+    // (one row per warp iteration left every lane with 2 K loads outstanding: the pass ran at ~1.6 TB/s out of L2); the row is
+    // converted twice (sums, then output) so that only the raw registers live across the shuffle reduction.
+    const long long stride = (long long)gridDim.x * wpb * rpw;
+    uint4 nd[K], nx[K];
+    float nmu = 0.f, nrs = 0.f;
+    auto fetch = [&](long long r0_) {
+      const long long r = r0_ + sub;
+      const bool live = r < rows;
+      nmu = live ? mean[r] : 0.f; nrs = live ? rstd[r] : 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int c = (k * L + sl) * 8;
+        nd[k] = make_uint4(0u, 0u, 0u, 0u); nx[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (live && c < C) {
+          nd[k] = *reinterpret_cast<const uint4 *>(dy + r * lddy + c);
+          nx[k] = *reinterpret_cast<const uint4 *>(x + r * ldx + c);
+        }
+      }
+    };
+    auto cvt = [](const uint4 &u, float (&f)[8]) {
+      const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    };
+    long long r0 = ((long long)blockIdx.x * wpb + wib) * rpw;
+    if (r0 < rows) fetch(r0);
+    for (; r0 < rows; r0 += stride) {
+      uint4 cd[K], cx[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) { cd[k] = nd[k]; cx[k] = nx[k]; }
+      const float mu = nmu, rs = nrs;
+      const long long r = r0 + sub;
+      const bool live = r < rows;
+      if (r0 + stride < rows) fetch(r0 + stride);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        float d[8], xv[8];
+        cvt(cd[k], d); cvt(cx[k], xv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (xv[i] - mu) * rs, g = d[i] * gm[k][i];
+          s1 += g; s2 = fmaf(g, xh, s2);
+        }
+      }
+      for (int o = L >> 1; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+      const float m1 = s1 * invC, m2 = s2 * invC;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int c = (k * L + sl) * 8;
+        if (live && c < C) {
+          float d[8], xv[8], o[8];
+          cvt(cd[k], d); cvt(cx[k], xv);
+          if (acc_dx) ldv8(dx + r * lddx + c, o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float xh = (xv[i] - mu) * rs, g = d[i] * gm[k][i];
+            const float t = rs * (g - m1 - xh * m2);
+            o[i] = acc_dx ? o[i] + t : t;
+          }
+          stv8(dx + r * lddx + c, o);
+        }
+      }
+    }
+    return;
+  }
   for (long long r0 = ((long long)blockIdx.x * wpb + wib) * rpw; r0 < rows; r0 += (long long)gridDim.x * wpb * rpw) {
     const long long r = r0 + sub;
     const bool live = r < rows;
