@@ -406,6 +406,7 @@ ecam_bwd_apply_kernel(ViewList dxs, int J, int Cb, int H, int W, const float *__
   }
   const View &dv = dxs.v[j];
   T *dp = reinterpret_cast<T *>(dv.ptr) + (long long)n * dv.sn + cb0;
+  const bool flat = dv.sh == (long long)W * dv.sw;      // pixel-dense view (the planar slots): no h / w decomposition per pixel
   constexpr int UNR = 4;
   const int stride = gridDim.x * rows;
   for (int p0 = blockIdx.x * rows + ty; p0 < HW; p0 += stride * UNR) {
@@ -430,7 +431,7 @@ ecam_bwd_apply_kernel(ViewList dxs, int J, int Cb, int H, int W, const float *__
           if (ami[i] == p) v += dmi[i];
           o[i] = v;
         }
-        st8(dp + (long long)(p / W) * dv.sh + (long long)(p % W) * dv.sw, o);
+        st8(dp + (flat ? (long long)p * dv.sw : (long long)(p / W) * dv.sh + (long long)(p % W) * dv.sw), o);
       }
     }
   }
