@@ -83,8 +83,11 @@ def conv_case(ops, name, N, H, W, ks, src_specs, dst_specs, bias, gen):
         "v2_ew16": {"tc_ew": 16},
         "v2_ew16_ns3": {"tc_ew": 16, "tc_ns3_min_cin": 1},
         "v2_ew16_nores_mt4": {"tc_ew": 16, "tc_no_resident": 1, "tc_mt": 4},
+        # BatchNorm statistics: the shuffle butterfly everywhere (the default keeps them in registers for N tiles <= 32), also stacked
+        "v2_stat_butterfly": {"tc_stat_mode": 1},
+        "v2_stat_butterfly_ns3": {"tc_stat_mode": 1, "tc_ns3_min_cin": 1},
     }
-    OPTS = ("tc_v1", "tc_mt", "tc_no_resident", "tc_no_ns3", "tc_ns3_min_cin", "tc_ns3_mode", "tc_ew")
+    OPTS = ("tc_v1", "tc_mt", "tc_no_resident", "tc_no_ns3", "tc_ns3_min_cin", "tc_ns3_mode", "tc_ew", "tc_stat_mode")
     for key, opts in variants.items():
         for f, i0 in zip(dst_fulls, init):
             f.base.copy_(i0)
