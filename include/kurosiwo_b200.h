@@ -61,6 +61,8 @@ const char *ks_error_string(int code);
  * CUDA-core ECAM classifier pass, "tc_stat_mode" = 1 shuffle-butterfly BatchNorm statistics everywhere, "att_no_umma" = 1 mma.sync ViT
  * attention; "xatt_umma" = 1 turns the tcgen05 forward of the ChangeFormer attention ON.  Returns KS_EINVAL for unknown names. */
 int ks_set_option(const char *name, int value);
+/* Every knob back to its default (0).  The knobs are process-global: harnesses that toggle them call this when they are done. */
+int ks_reset_options(void);
 
 /* ---- layout / precision plumbing --------------------------------------- */
 /* dst[i0][i1][i2][i3] (contiguous, dtype dst_dtype) = src[i0*s0+i1*s1+i2*s2+i3*s3]

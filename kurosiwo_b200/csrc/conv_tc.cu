@@ -858,6 +858,11 @@ int conv2d_tc(int N, int H, int W, int ksize, const ViewList &srcs, const void *
 
 }  // namespace ks
 
+extern "C" int ks_reset_options(void) {
+  ks::g_opt = ks::Options{};
+  return KS_OK;
+}
+
 extern "C" int ks_set_option(const char *name, int value) {
   if (!name) return KS_EINVAL;
   auto eq = [&](const char *s) { const char *a = name; while (*a && *a == *s) { ++a; ++s; } return *a == 0 && *s == 0; };

@@ -88,7 +88,7 @@ def load() -> C.CDLL:
 
 
 EXPORTED_SYMBOLS = [
-    "ks_version", "ks_error_string", "ks_set_option", "ks_permute_cast", "ks_permute_cast_batched", "ks_conv2d", "ks_conv2d_wgrad", "ks_stem_conv3x3", "ks_stem_wgrad3x3",
+    "ks_version", "ks_error_string", "ks_set_option", "ks_reset_options", "ks_permute_cast", "ks_permute_cast_batched", "ks_conv2d", "ks_conv2d_wgrad", "ks_stem_conv3x3", "ks_stem_wgrad3x3",
     "ks_bn_stats", "ks_bn_finalize", "ks_bn_act", "ks_bn_bwd_reduce", "ks_bn_bwd_apply", "ks_maxpool2x2_bwd",
     "ks_channel_sum", "ks_ecam_pool", "ks_ecam_gates", "ks_ecam_final", "ks_ecam_bwd_reduce", "ks_ecam_gates_bwd",
     "ks_ecam_bwd_apply", "ks_ce_dice_workspace_bytes", "ks_ce_dice_fwd_bwd", "ks_ce_dice_fwd_bwd_ex", "ks_adam_step", "ks_adamw_step", "ks_sgd_step",
@@ -132,6 +132,10 @@ class CudaOps:
         self.launches += 1
         if rc != 0:
             raise KsError(f"{what} failed: {self.lib.ks_error_string(C.c_int(rc)).decode()} (code {rc})")
+
+    def reset_options(self):
+        """All perf-experiment / A-B switches back to their defaults (they are process-global state of the library)."""
+        self._check(self.lib.ks_reset_options(), "ks_reset_options")
 
     def set_option(self, name: str, value: int):
         rc = self.lib.ks_set_option(name.encode(), C.c_int(value))

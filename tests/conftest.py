@@ -17,3 +17,17 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return ROOT / "tests" / "golden"
+
+
+@pytest.fixture(autouse=True)
+def _library_options_are_per_test(request):
+    """The perf / A-B switches of the library (ks_set_option) are process-global: every GPU test starts and ends with the defaults,
+    so a test that toggles a kernel variant cannot leak it into the next one."""
+    if request.node.get_closest_marker("gpu") is None:
+        yield
+        return
+    from kurosiwo_b200.lib import default_ops
+    ops = default_ops()
+    ops.reset_options()
+    yield
+    ops.reset_options()
