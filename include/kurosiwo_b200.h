@@ -114,6 +114,16 @@ int ks_conv2d_wgrad(int dtype, int N, int H, int W, int ksize,
                     const ks_view_t *dys, int n_dy,
                     float *dw, int accumulate, int impl, void *stream);
 
+/* The same plus the bias gradient of the layer: dbias[(channel offset of the dy view + c) % bias_mod] (+)= sum_pixels dy[p][c]
+ * (bias_mod = 0: no folding; the four 1x1 phase views of a ConvTranspose2d(k2, s2), snunet.py:41, share one bias: bias_mod = C).
+ * On the tcgen05 path the sum rides along in the weight-gradient UMMAs when the last 128-row tile of Cin has a free channel-group
+ * slot (a tile of ones as one more X group); otherwise the call runs ks_channel_sum per view.  Replaces: the bias branch of
+ * cuDNN's ConvolutionBackward. */
+int ks_conv2d_wgrad_bias(int dtype, int N, int H, int W, int ksize, const ks_view_t *xs, int n_x,
+                         const ks_view_t *dys, int n_dy, float *dw, int accumulate, float *dbias, int bias_mod,
+                         int accumulate_bias, int impl, void *stream);
+
+
 /* Stem conv (models/snunet.py:75, conv0_0.conv1: Cin = 2 or 3, Cout = 32): reads the NCHW fp32 network
  * input and the OIHW fp32 master weight directly; NHWC output in `dtype`; optional BN statistics. */
 int ks_stem_conv3x3(int dtype, int N, int Cin, int H, int W, const float *x_nchw, const float *w_oihw,

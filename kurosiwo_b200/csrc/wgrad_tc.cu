@@ -30,6 +30,10 @@ struct alignas(64) WgradTcParams {
   int Cin, Cout, SX, SY;
   uint32_t x_stage_bytes, y_stage_bytes, tmem_cols, idesc;
   float *dw;
+  // optional per-channel sum of dy (the bias gradient of the layer), fused: when the last M tile has a free channel-group slot it is
+  // filled with ONES once per stage buffer, so the rows of that group accumulate sum_pixels dy[p][co] in the same UMMAs
+  float *dsum;
+  int dsum_mod;
 };
 
 using namespace tc;
@@ -63,6 +67,15 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   const int tile_begin = blockIdx.y * per, tile_end = min(p.total_tiles, tile_begin + per);
   const int pad = p.ksize / 2;
   const uint32_t xg_bytes = 128u * p.GX * 2u, yg_bytes = 128u * p.GY * 2u;
+  const bool fuse_sum = p.dsum != nullptr && mtile == p.m_tiles - 1 && nxg < p.MG && tg == 0;
+  if (fuse_sum) {
+    // a tile of ones is the same in every layout; TMA only ever writes the first nxg group slots of a stage
+    for (int sg = 0; sg < SX; ++sg) {
+      uint32_t *ones = reinterpret_cast<uint32_t *>(sm + (x_base - base) + (size_t)sg * p.x_stage_bytes + (size_t)nxg * xg_bytes);
+      for (uint32_t i = threadIdx.x; i < xg_bytes / 4u; i += blockDim.x) ones[i] = 0x3F803F80u;      // bf16 1.0 | 1.0
+    }
+    fence_proxy_async();
+  }
 
   if (warp == 0 && elect_one()) {
     for (int i = 0; i < SX; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 1); }
@@ -146,6 +159,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     tc_fence_after();
     if (tile_end > tile_begin) {
       const bool row_ok = g < nxg;
+      const bool sum_row = fuse_sum && row == nxg * p.GX;       // first row of the ones group: sum over this CTA's pixels of dy[.][co]
       int ci = 0;
       if (row_ok) ci = p.x_cstart[p.xg_view[xg0 + g]] + p.xg_c0[xg0 + g] + (row % p.GX);
       for (int tp = 0; tp < ntap; ++tp) {
@@ -154,6 +168,12 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
           uint32_t r[16];
           tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(tp * p.BN + cc), r);
           tmem_ld_wait();
+          if (sum_row && tp == 0) {
+            const int yg = cc / p.GY;
+            const int co = p.y_cstart[p.yg_view[yg0 + yg]] + p.yg_c0[yg0 + yg] + (cc % p.GY);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(p.dsum + (p.dsum_mod > 0 ? (co + i) % p.dsum_mod : co + i), __uint_as_float(r[i]));
+          }
           if (row_ok) {
             const int yg = cc / p.GY;
             const int co = p.y_cstart[p.yg_view[yg0 + yg]] + p.yg_c0[yg0 + yg] + (cc % p.GY);
@@ -657,7 +677,9 @@ static int wgrad_tc3(int N, int H, int W, const ViewList &xs, const ViewList &dy
   return (int)cudaGetLastError();
 }
 
-int wgrad_tc(int N, int H, int W, int ksize, const ViewList &xs, const ViewList &dys, float *dw, cudaStream_t st) {
+int wgrad_tc(int N, int H, int W, int ksize, const ViewList &xs, const ViewList &dys, float *dw, cudaStream_t st, float *dsum, int dsum_mod,
+             bool *dsum_done) {
+  if (dsum_done) *dsum_done = false;
   if (g_opt.tc_disable || g_opt.wgrad_tc_disable) return KS_EUNSUPPORTED;
   // Cin == 32 (one 32-channel group): the halo kernel stacks the three taps of a kernel row along M instead (v2, stack3)
   const bool single32 = (xs.n == 1 && xs.v[0].C == 32);
@@ -722,6 +744,10 @@ int wgrad_tc(int N, int H, int W, int ksize, const ViewList &xs, const ViewList 
   if (bytes(SX, SY) > budget) return KS_EUNSUPPORTED;
   p.SX = SX; p.SY = SY;
   p.dw = dw;
+  // the bias gradient rides along when the last M tile has a free group slot (1x1 layers: one tap, the dy tile is not shifted)
+  p.dsum = (dsum != nullptr && ksize == 1 && (p.n_xg % p.MG) != 0) ? dsum : nullptr;
+  p.dsum_mod = dsum_mod;
+  if (dsum_done) *dsum_done = p.dsum != nullptr;
   for (int i = 0; i < xs.n; ++i) {
     int rc = encode_act_map(&p.x[i], xs.v[i], N, H, W, p.GX, 16, 8, p.GX == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;

@@ -88,7 +88,7 @@ def load() -> C.CDLL:
 
 
 EXPORTED_SYMBOLS = [
-    "ks_version", "ks_error_string", "ks_set_option", "ks_reset_options", "ks_permute_cast", "ks_permute_cast_batched", "ks_conv2d", "ks_conv2d_wgrad", "ks_stem_conv3x3", "ks_stem_wgrad3x3",
+    "ks_version", "ks_error_string", "ks_set_option", "ks_reset_options", "ks_permute_cast", "ks_permute_cast_batched", "ks_conv2d", "ks_conv2d_wgrad", "ks_conv2d_wgrad_bias", "ks_stem_conv3x3", "ks_stem_wgrad3x3",
     "ks_bn_stats", "ks_bn_finalize", "ks_bn_act", "ks_bn_bwd_reduce", "ks_bn_bwd_apply", "ks_maxpool2x2_bwd",
     "ks_channel_sum", "ks_ecam_pool", "ks_ecam_gates", "ks_ecam_final", "ks_ecam_bwd_reduce", "ks_ecam_gates_bwd",
     "ks_ecam_bwd_apply", "ks_ce_dice_workspace_bytes", "ks_ce_dice_fwd_bwd", "ks_ce_dice_fwd_bwd_ex", "ks_adam_step", "ks_adamw_step", "ks_sgd_step",
@@ -206,6 +206,12 @@ class CudaOps:
                                       _views(xs), C.c_int(len(xs)), _views(dys), C.c_int(len(dys)), _p(dw),
                                       C.c_int(int(accumulate)), C.c_int(impl), self._stream())
         self._check(rc, "ks_conv2d_wgrad")
+
+    def conv2d_wgrad_bias(self, N, H, W, ksize, xs, dys, dw, dbias, bias_mod=0, accumulate=False, accumulate_bias=False, impl=IMPL_AUTO):
+        rc = self.lib.ks_conv2d_wgrad_bias(dtype_code(xs[0].dtype), C.c_int(N), C.c_int(H), C.c_int(W), C.c_int(ksize),
+                                           _views(xs), C.c_int(len(xs)), _views(dys), C.c_int(len(dys)), _p(dw), C.c_int(int(accumulate)),
+                                           _p(dbias), C.c_int(bias_mod), C.c_int(int(accumulate_bias)), C.c_int(impl), self._stream())
+        self._check(rc, "ks_conv2d_wgrad_bias")
 
     def stem_conv3x3(self, x_nchw: torch.Tensor, w_oihw, bias, dst: View, stats=None):
         N, Cin, H, W = x_nchw.shape

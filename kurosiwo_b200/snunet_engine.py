@@ -394,8 +394,15 @@ class SNUNetEngine(TrainStepMixin):
             ops.conv2d(N, h1, w1, 1, phases, self.wp[f"{nm}.dgrad"], None, [self.slot(self.dX, l + 1, j)],
                        [tgt in written], None, self.conv_impl)
             written.add(tgt)
-            ops.conv2d_wgrad(N, h1, w1, 1, [self.slot(self.X, l + 1, j)], phases, self.gp[nm], False, self.conv_impl)
-            ops.channel_sum(dup, P.g(f"{nm}.up.bias"), False)
+            # weight gradient of the four phases + the bias gradient (one bias per channel for all four phases: folded modulo C).  With
+            # 64 input channels (the full-resolution level: 4 x 411 MB of dUP) the last 128-row tile of the weight-gradient GEMM has a free
+            # group slot and the per-channel sums ride along in its UMMAs; wider layers keep the one dense pass over dUP.
+            if f[l + 1] % 128 != 0 and self.dtype == torch.bfloat16:
+                ops.conv2d_wgrad_bias(N, h1, w1, 1, [self.slot(self.X, l + 1, j)], phases, self.gp[nm], P.g(f"{nm}.up.bias"), f[l + 1],
+                                      False, False, self.conv_impl)
+            else:
+                ops.conv2d_wgrad(N, h1, w1, 1, [self.slot(self.X, l + 1, j)], phases, self.gp[nm], False, self.conv_impl)
+                ops.channel_sum(dup, P.g(f"{nm}.up.bias"), False)
         # Data-parallel overlap: everything registered from conv0_1 on (decoder blocks, their ConvTransposes, ECAM, classifier) is final
         # here, conv4_0 + Up4_0 (registered right before conv0_1) after the first encoder block below: the flat gradient range
         # [conv4_0 .., end) = 83 % of the bytes goes out under the rest of the encoder backward, the shared encoder blocks at the end.

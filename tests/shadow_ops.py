@@ -92,6 +92,19 @@ class ShadowOps:
         out = dw.reshape(-1)[: g.numel()]
         out.copy_(g + out if accumulate else g)
 
+    def conv2d_wgrad_bias(self, N, H, W, ksize, xs, dys, dw, dbias, bias_mod=0, accumulate=False, accumulate_bias=False, impl=0):
+        self.conv2d_wgrad(N, H, W, ksize, xs, dys, dw, accumulate, impl)
+        cout = sum(v.C for v in dys)
+        blen = bias_mod if bias_mod > 0 else cout
+        out = dbias.reshape(-1)[:blen]
+        if not accumulate_bias:
+            out.zero_()
+        c0 = 0
+        for v in dys:
+            o = c0 % bias_mod if bias_mod > 0 else c0
+            out[o:o + v.C] += _t(v).float().reshape(-1, v.C).sum(0)
+            c0 += v.C
+
     def stem_conv3x3(self, x_nchw, w_oihw, bias, dst, stats=None):
         t = _t(dst)
         q = (lambda a: a.to(t.dtype).float())

@@ -78,6 +78,37 @@ def test_wgrad_simt(ops, sh, dtype, ks):
     assert rel_l2(dw, cdw) < 1e-4
 
 
+@pytest.mark.parametrize("cins,couts,phases,mod", [([64], [64], True, 64), ([128], [128], True, 128), ([32], [32], False, 0),
+                                                  ([64, 32], [64, 32], False, 0), ([64], [256], False, 0), ([320], [64], False, 0)])
+def test_wgrad_with_fused_bias_gradient(ops, sh, cins, couts, phases, mod):
+    """ks_conv2d_wgrad_bias (1x1, bf16, tcgen05): the per-channel sum of dy rides along in the weight-gradient UMMAs when the last M tile of
+    Cin has a free group slot (Cin = 64, 32, 96, 320), else falls back to ks_channel_sum (Cin = 128); four ConvTranspose phase views fold
+    onto one bias (mod = C).  Against the shadow, incl. accumulation over two calls."""
+    from kurosiwo_b200.lib import IMPL_TC
+    g = _gen(77)
+    N, H, W = 3, 24, 32
+    dt = torch.bfloat16
+    xs = [rand_view(N, H, W, c, dt, DEV, gen=g)[0] for c in cins]
+    if phases:
+        _, full = rand_view(N, 2 * H, 2 * W, couts[0], dt, DEV, gen=g)
+        dys = [full.phase(k // 2, k % 2) for k in range(4)]
+        cfull = mirror(full)
+        cdys = [cfull.phase(k // 2, k % 2) for k in range(4)]
+    else:
+        dys = [rand_view(N, H, W, c, dt, DEV, gen=g)[0] for c in couts]
+        cdys = [mirror(v) for v in dys]
+    cxs = [mirror(v) for v in xs]
+    cin, cout = sum(cins), sum(v.C for v in dys)
+    blen = mod if mod else cout
+    dw, cdw = torch.full((cout * cin,), 3.0, device=DEV), torch.full((cout * cin,), 3.0)
+    db, cdb = torch.full((blen,), 5.0, device=DEV), torch.full((blen,), 5.0)
+    for acc in (False, True):
+        ops.conv2d_wgrad_bias(N, H, W, 1, xs, dys, dw, db, mod, acc, acc, IMPL_TC)
+        sh.conv2d_wgrad_bias(N, H, W, 1, cxs, cdys, cdw, cdb, mod, acc, acc)
+        assert rel_l2(dw, cdw) < 1e-4
+        assert rel_l2(db, cdb) < 1e-4, (db[:8], cdb[:8])
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("cin,H,W", [(2, 24, 40), (3, 17, 33), (2, 50, 70)])
 def test_stem_kernels(ops, sh, dtype, cin, H, W):
