@@ -493,6 +493,7 @@ ce_dice_resident_kernel(const float *__restrict__ logits, const long long *__res
                         float *__restrict__ dlogits, unsigned char *__restrict__ pred, double *ws, unsigned int *ctrl,
                         float dice_weight, int cps, int total) {
   static_assert(C == 3, "planes 0/1 in shared memory, plane 2 in registers");
+  static_assert(MAXC <= 16, "sI[16] holds one partial sum per chunk");
   constexpr int P = 4 * TH;                       // pixels per chunk: 4 per thread
   constexpr int LD = 3;                           // chunks in flight (issue order == consumption order: a request issued late
                                                   // would queue behind everything issued before it)
