@@ -823,6 +823,152 @@ dwconv_wgrad_kernel(int N, int H, int W, int C, const T *__restrict__ x, const T
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// 2x2-block variants (round 2b).  The kernels above spend 27 loads per output vector (9 taps x (16 B of x + 32 B of weights)) and
+// four integer divisions: 3.2 + 1.1 ms per ChangeFormer step against an HBM floor of ~0.6 ms.  Here a warp owns 32 channel vectors
+// (512 contiguous bytes per pixel) and walks 2x2 output blocks: the 4x4 input window is loaded ONCE (16 loads for 4 outputs instead of
+// 36), every input vector feeds the up-to-four outputs it belongs to, and the 9 x 8 weights of the thread's channels (forward / data
+// gradient) or its 9 x 8 partial weight gradients stay in registers for the thread's lifetime (the channel vector of a thread is fixed).
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, bool FLIP>
+__global__ void __launch_bounds__(256, 2)
+dwconv_block_kernel(int N, int H, int W, int C, const T *__restrict__ x, const float *__restrict__ w9, const float *__restrict__ bias, T *__restrict__ y) {
+  const int CV = C / 8, cv = blockIdx.y * 32 + (threadIdx.x & 31);
+  if (cv >= CV) return;                                     // no barriers below
+  const int c = cv * 8;
+  float wr[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) ld8(w9 + (long long)(FLIP ? 8 - t : t) * C + c, wr[t]);      // data gradient = correlation with the flipped taps
+  float bs[8];
+  if (bias) ld8(bias + c, bs); else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bs[k] = 0.f;
+  }
+  const int HB = (H + 1) >> 1, WB = (W + 1) >> 1;
+  const unsigned nblk = (unsigned)N * HB * WB;
+  for (unsigned q = blockIdx.x * 8 + (threadIdx.x >> 5); q < nblk; q += gridDim.x * 8) {
+    const int wb = (int)(q % WB), hb = (int)((q / WB) % HB); const long long n = q / ((unsigned)WB * HB);
+    const int h0 = 2 * hb, w0 = 2 * wb;
+    // every output starts from the bias and adds its taps in the order of dwconv_kernel (t = 0..8 of the UNflipped weights): the results
+    // are bit-identical to the one-output-per-thread kernel, so the end-to-end drift pins do not move with the kernel choice
+    float acc[2][2][8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[a][b][k] = bs[k];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int r = FLIP ? 3 - rr : rr;
+      const int hh = h0 - 1 + r;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int ss = 0; ss < 4; ++ss) {
+        const int sx = FLIP ? 3 - ss : ss;
+        const int ww = w0 - 1 + sx;
+        if (ww < 0 || ww >= W) continue;
+        float f[8];
+        ld8(x + ((n * H + hh) * W + ww) * C + c, f);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          if (r - a < 0 || r - a > 2) continue;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            if (sx - b < 0 || sx - b > 2) continue;
+            const int t = (r - a) * 3 + (sx - b);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[a][b][k] = fmaf(f[k], wr[t][k], acc[a][b][k]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+        if (h0 + a < H && w0 + b < W) st8(y + ((n * H + h0 + a) * W + w0 + b) * C + c, acc[a][b]);
+  }
+}
+
+// dw9[t][c] += sum_px dy[px][c] * x[px+t][c];  dbias[c] += sum_px dy[px][c]: the same 2x2 blocks, 4 dy vectors + the 4x4 x window per block
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+dwconv_wgrad_block_kernel(int N, int H, int W, int C, const T *__restrict__ x, const T *__restrict__ dy, float *__restrict__ dw9,
+                          float *__restrict__ dbias) {
+  __shared__ float red[10][256];
+  for (int i = threadIdx.x; i < 10 * 256; i += blockDim.x) (&red[0][0])[i] = 0.f;
+  __syncthreads();
+  const int CV = C / 8, lane = threadIdx.x & 31, cv = blockIdx.y * 32 + lane;
+  const bool live = cv < CV;
+  const int c = cv * 8;
+  float acc[9][8], ab[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ab[k] = 0.f;
+  const int HB = (H + 1) >> 1, WB = (W + 1) >> 1;
+  const unsigned nblk = (unsigned)N * HB * WB;
+  if (live) {
+    for (unsigned q = blockIdx.x * 8 + (threadIdx.x >> 5); q < nblk; q += gridDim.x * 8) {
+      const int wb = (int)(q % WB), hb = (int)((q / WB) % HB); const long long n = q / ((unsigned)WB * HB);
+      const int h0 = 2 * hb, w0 = 2 * wb;
+      float g[2][2][8];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          if (h0 + a < H && w0 + b < W) {
+            ld8(dy + ((n * H + h0 + a) * W + w0 + b) * C + c, g[a][b]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ab[k] += g[a][b][k];
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[a][b][k] = 0.f;
+          }
+        }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int hh = h0 - 1 + r;
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int sx = 0; sx < 4; ++sx) {
+          const int ww = w0 - 1 + sx;
+          if (ww < 0 || ww >= W) continue;
+          float f[8];
+          ld8(x + ((n * H + hh) * W + ww) * C + c, f);
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            if (r - a < 0 || r - a > 2) continue;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              if (sx - b < 0 || sx - b > 2) continue;
+              const int t = (r - a) * 3 + (sx - b);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(g[a][b][k], f[k], acc[t][k]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&red[t][lane * 8 + k], acc[t][k]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&red[9][lane * 8 + k], ab[k]);
+  }
+  __syncthreads();
+  const int cbase = blockIdx.y * 256, cw = min(256, C - cbase);
+  for (int i = threadIdx.x; i < 10 * cw; i += blockDim.x) {
+    const int t = i / cw, cc = i % cw;
+    if (t < 9) atomicAdd(dw9 + (long long)t * C + cbase + cc, red[t][cc]);
+    else if (dbias) atomicAdd(dbias + cbase + cc, red[9][cc]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Bilinear resize of dense NHWC maps, align_corners=False (aten upsample_bilinear2d).
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bl_src(int d, float ratio, int in, int &i0, int &i1, float &l1) {
@@ -1246,7 +1392,11 @@ extern "C" int ks_dwconv3x3_fwd(int dtype, int N, int H, int W, int C, const voi
   if (C % 8 || !a16(x) || !a16(y) || !a16(w9) || (bias && !a16(bias))) return KS_EUNSUPPORTED;
   if ((long long)N * H * W * (C / 8) >= (1LL << 31)) return KS_EUNSUPPORTED;
   const int grid = cgrid((long long)N * H * W * (C / 8), 256);
-#define CALL(T) dwconv_kernel<T, false><<<grid, 256, 0, (cudaStream_t)stream>>>(N, H, W, C, (const T *)x, w9, bias, (T *)y)
+  const long long nblk = (long long)N * ((H + 1) / 2) * ((W + 1) / 2);
+  const int gyb = (C / 8 + 31) / 32;
+  int gxb = (kNumSMs * 2 + gyb - 1) / gyb; if (gxb > (nblk + 7) / 8) gxb = (int)((nblk + 7) / 8); if (gxb < 1) gxb = 1;
+#define CALL(T) { if (g_opt.dwconv_simple) dwconv_kernel<T, false><<<grid, 256, 0, (cudaStream_t)stream>>>(N, H, W, C, (const T *)x, w9, bias, (T *)y); \
+    else dwconv_block_kernel<T, false><<<dim3(gxb, gyb), 256, 0, (cudaStream_t)stream>>>(N, H, W, C, (const T *)x, w9, bias, (T *)y); }
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();
@@ -1263,8 +1413,13 @@ extern "C" int ks_dwconv3x3_bwd(int dtype, int N, int H, int W, int C, const voi
   int gx = (kNumSMs * 4) / gy; if (gx < 1) gx = 1;
   const long long npix = (long long)N * H * W;
   if (gx > (npix + 7) / 8) gx = (int)((npix + 7) / 8);
-#define CALL(T) { dwconv_kernel<T, true><<<grid, 256, 0, st>>>(N, H, W, C, (const T *)dy, w9, nullptr, (T *)dx); \
-    dwconv_wgrad_kernel<T><<<dim3(gx, gy), 256, 0, st>>>(N, H, W, C, (const T *)x, (const T *)dy, dw9, dbias); }
+  const long long nblk = (long long)N * ((H + 1) / 2) * ((W + 1) / 2);
+  const int gyb = (C / 8 + 31) / 32;
+  int gxb = (kNumSMs * 2 + gyb - 1) / gyb; if (gxb > (nblk + 7) / 8) gxb = (int)((nblk + 7) / 8); if (gxb < 1) gxb = 1;
+#define CALL(T) { if (g_opt.dwconv_simple) { dwconv_kernel<T, true><<<grid, 256, 0, st>>>(N, H, W, C, (const T *)dy, w9, nullptr, (T *)dx); \
+      dwconv_wgrad_kernel<T><<<dim3(gx, gy), 256, 0, st>>>(N, H, W, C, (const T *)x, (const T *)dy, dw9, dbias); } \
+    else { dwconv_block_kernel<T, true><<<dim3(gxb, gyb), 256, 0, st>>>(N, H, W, C, (const T *)dy, w9, nullptr, (T *)dx); \
+      dwconv_wgrad_block_kernel<T><<<dim3(gxb, gyb), 256, 0, st>>>(N, H, W, C, (const T *)x, (const T *)dy, dw9, dbias); } }
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();
