@@ -969,6 +969,178 @@ dwconv_wgrad_block_kernel(int N, int H, int W, int C, const T *__restrict__ x, c
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Shared-memory tile variants for bf16 (round 2c, the default).  The register-window kernels above keep one 4x4 window per warp in flight:
+// the loads of the next block are issued only after the previous block's arithmetic, so a launch is bound by memory latency (1.3 TB/s of
+// algorithmic traffic).  Here a CTA owns a 256-channel group (lane = 8 channels, 512 contiguous bytes per pixel) and walks 7x7 output
+// tiles (56 / 28 / 14 / 7 are multiples of 7): the 9x9 input halo tile (41.5 KB) of the NEXT tile streams into the second shared-memory
+// buffer with cp.async (16 bytes per request, zero fill outside the image = the padding) while the warps compute the current one, i.e. up to
+// 2 x 41.5 KB per SM are in flight without holding registers.  Every output starts from the bias and adds its nine taps with fmaf in the
+// order of dwconv_kernel (out-of-image taps add 0 * w): results are bit-identical to the one-output-per-thread kernel.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int DWT = 7, DWI = DWT + 2;
+constexpr int DW_PIX_BYTES = 512;                                   // 32 lanes x 8 bf16
+constexpr int DW_IN_BYTES = DWI * DWI * DW_PIX_BYTES;               // 41 472
+constexpr int DW_OUT_BYTES = DWT * DWT * DW_PIX_BYTES;              // 25 088
+
+// 8 bf16 of a staged pixel -> 8 floats, one ALU instruction per value (the low half shifts up, the high half is masked in place)
+__device__ __forceinline__ void dw_ld8s(const unsigned char *p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4 *>(p);
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+
+// a RH x RW pixel rectangle whose top-left pixel is (hs, ws) of image n -> shared memory, pixel-major; warps take whole pixels
+template <int RH, int RW>
+__device__ __forceinline__ void dw_stage_rect(uint32_t sdst, const __nv_bfloat16 *__restrict__ src, long long n, int hs, int ws, int H, int W, int C, int c,
+                                              bool cok) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int p = wid; p < RH * RW; p += nw) {
+    const int hh = hs + p / RW, ww = ws + p % RW;
+    const bool ok = cok && hh >= 0 && hh < H && ww >= 0 && ww < W;
+    const __nv_bfloat16 *g = ok ? src + ((n * H + hh) * W + ww) * C + c : src;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst + (uint32_t)(p * DW_PIX_BYTES + lane * 16)), "l"(g), "r"(ok ? 16u : 0u) : "memory");
+  }
+}
+
+template <bool FLIP>
+__global__ void __launch_bounds__(256, 2)
+dwconv_tile_kernel(int N, int H, int W, int C, const __nv_bfloat16 *__restrict__ x, const float *__restrict__ w9, const float *__restrict__ bias,
+                   __nv_bfloat16 *__restrict__ y) {
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(dw_smem);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.y * 256 + lane * 8;
+  const bool cok = c < C;
+  float wr[9][8], bs[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    if (cok) ld8(w9 + (long long)t * C + c, wr[t]); else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) wr[t][k] = 0.f;
+    }
+  }
+  if (cok && bias) ld8(bias + c, bs); else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bs[k] = 0.f;
+  }
+  const int TH = (H + DWT - 1) / DWT, TW = (W + DWT - 1) / DWT;
+  const int ntile = N * TH * TW;
+  auto stage = [&](int tile, int buf) {
+    const int tw = tile % TW, th = (tile / TW) % TH, n = tile / (TW * TH);
+    dw_stage_rect<DWI, DWI>(sbase + (uint32_t)buf * DW_IN_BYTES, x, n, th * DWT - 1, tw * DWT - 1, H, W, C, c, cok);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if ((int)blockIdx.x < ntile) stage(blockIdx.x, 0);
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x, buf ^= 1) {
+    const bool more = tile + (int)gridDim.x < ntile;
+    if (more) stage(tile + gridDim.x, buf ^ 1);                  // buffer buf^1 was released by the barrier that ended the previous iteration
+    if (more) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const int tw = tile % TW, th = (tile / TW) % TH; const long long n = tile / (TW * TH);
+    const int h0 = th * DWT, w0 = tw * DWT;
+    const unsigned char *sb = dw_smem + buf * DW_IN_BYTES + lane * 16;
+    if (cok) {
+      // pixel p = a * 7 + b of the tile; a warp takes p = wid, wid + 8, ...: (a, b) advance by (1, 1) with a carry out of b
+      for (int a = wid / DWT, b = wid % DWT; a < DWT; ++a, ++b) {
+        if (b >= DWT) { b -= DWT; if (++a >= DWT) break; }
+        if (h0 + a >= H || w0 + b >= W) continue;
+        const unsigned char *sp = sb + ((a + 1) * DWI + b + 1) * DW_PIX_BYTES;      // the centre tap
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = bs[k];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int dy = t / 3 - 1, dx = t % 3 - 1;
+          float f[8];
+          dw_ld8s(sp + ((FLIP ? -dy : dy) * DWI + (FLIP ? -dx : dx)) * DW_PIX_BYTES, f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[k], wr[t][k], acc[k]);
+        }
+        st8(y + ((n * H + h0 + a) * W + w0 + b) * C + c, acc);
+      }
+    }
+    __syncthreads();                                             // every warp is done with buffer buf before the next iteration refills it
+  }
+}
+
+// dw9[t][c] += sum_px dy[px][c] * x[px+t][c];  dbias[c] += sum_px dy[px][c]: the x halo tile and the dy tile of the next 7x7 tile stream in
+// (2 x 65 KB, one CTA of 16 warps per SM) while the warps accumulate the current one; zero-filled dy pixels / x halos contribute nothing
+__global__ void __launch_bounds__(512, 1)
+dwconv_wgrad_tile_kernel(int N, int H, int W, int C, const __nv_bfloat16 *__restrict__ x, const __nv_bfloat16 *__restrict__ dy, float *__restrict__ dw9,
+                         float *__restrict__ dbias) {
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  __shared__ float red[10][256];
+  for (int i = threadIdx.x; i < 10 * 256; i += blockDim.x) (&red[0][0])[i] = 0.f;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(dw_smem);
+  constexpr int STAGE = DW_IN_BYTES + DW_OUT_BYTES;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.y * 256 + lane * 8;
+  const bool cok = c < C;
+  float acc[9][8], ab[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ab[k] = 0.f;
+  const int TH = (H + DWT - 1) / DWT, TW = (W + DWT - 1) / DWT;
+  const int ntile = N * TH * TW;
+  auto stage = [&](int tile, int buf) {
+    const int tw = tile % TW, th = (tile / TW) % TH, n = tile / (TW * TH);
+    dw_stage_rect<DWI, DWI>(sbase + (uint32_t)buf * STAGE, x, n, th * DWT - 1, tw * DWT - 1, H, W, C, c, cok);
+    dw_stage_rect<DWT, DWT>(sbase + (uint32_t)buf * STAGE + DW_IN_BYTES, dy, n, th * DWT, tw * DWT, H, W, C, c, cok);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if ((int)blockIdx.x < ntile) stage(blockIdx.x, 0);
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x, buf ^= 1) {
+    const bool more = tile + (int)gridDim.x < ntile;
+    if (more) stage(tile + gridDim.x, buf ^ 1);
+    if (more) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const unsigned char *sx = dw_smem + buf * STAGE + lane * 16, *sg = sx + DW_IN_BYTES;
+    if (cok) {
+      // pixel p = a * 7 + b; a warp takes p = wid, wid + 16, ...: (a, b) advance by (2, 2) with a carry out of b
+      for (int a = wid / DWT, b = wid % DWT; a < DWT; a += 2, b += 2) {
+        if (b >= DWT) { b -= DWT; if (++a >= DWT) break; }
+        float g[8];
+        dw_ld8s(sg + (a * DWT + b) * DW_PIX_BYTES, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ab[k] += g[k];
+        const unsigned char *sp = sx + (a * DWI + b) * DW_PIX_BYTES;                 // tap (0, 0) of output pixel (a, b)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          float f[8];
+          dw_ld8s(sp + ((t / 3) * DWI + t % 3) * DW_PIX_BYTES, f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(g[k], f[k], acc[t][k]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();                                               // also orders the zeroing of red[] for a CTA that had no tile
+  if (cok) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&red[t][lane * 8 + k], acc[t][k]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&red[9][lane * 8 + k], ab[k]);
+  }
+  __syncthreads();
+  const int cbase = blockIdx.y * 256, cw = min(256, C - cbase);
+  for (int i = threadIdx.x; i < 10 * cw; i += blockDim.x) {
+    const int t = i / cw, cc = i % cw;
+    if (t < 9) atomicAdd(dw9 + (long long)t * C + cbase + cc, red[t][cc]);
+    else if (dbias) atomicAdd(dbias + cbase + cc, red[9][cc]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Bilinear resize of dense NHWC maps, align_corners=False (aten upsample_bilinear2d).
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bl_src(int d, float ratio, int in, int &i0, int &i1, float &l1) {
@@ -1395,7 +1567,16 @@ extern "C" int ks_dwconv3x3_fwd(int dtype, int N, int H, int W, int C, const voi
   const long long nblk = (long long)N * ((H + 1) / 2) * ((W + 1) / 2);
   const int gyb = (C / 8 + 31) / 32;
   int gxb = (kNumSMs * 2 + gyb - 1) / gyb; if (gxb > (nblk + 7) / 8) gxb = (int)((nblk + 7) / 8); if (gxb < 1) gxb = 1;
-#define CALL(T) { if (g_opt.dwconv_simple) dwconv_kernel<T, false><<<grid, 256, 0, (cudaStream_t)stream>>>(N, H, W, C, (const T *)x, w9, bias, (T *)y); \
+  if (dtype == KS_BF16 && (g_opt.dwconv_simple == 0 || g_opt.dwconv_simple == 3)) {            // shared-memory tile kernel (the default for bf16)
+    static bool attr = false;
+    if (!attr) { cudaError_t e = cudaFuncSetAttribute(dwconv_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * DW_IN_BYTES);
+                 if (e != cudaSuccess) return (int)e; attr = true; }
+    const long long ntile = (long long)N * ((H + DWT - 1) / DWT) * ((W + DWT - 1) / DWT);
+    int gxt = (kNumSMs * 2 + gyb - 1) / gyb; if (gxt > ntile) gxt = (int)ntile;
+    dwconv_tile_kernel<false><<<dim3(gxt, gyb), 256, 2 * DW_IN_BYTES, (cudaStream_t)stream>>>(N, H, W, C, (const __nv_bfloat16 *)x, w9, bias, (__nv_bfloat16 *)y);
+    KS_LAUNCH_RET();
+  }
+#define CALL(T) { if (g_opt.dwconv_simple == 1) dwconv_kernel<T, false><<<grid, 256, 0, (cudaStream_t)stream>>>(N, H, W, C, (const T *)x, w9, bias, (T *)y); \
     else dwconv_block_kernel<T, false><<<dim3(gxb, gyb), 256, 0, (cudaStream_t)stream>>>(N, H, W, C, (const T *)x, w9, bias, (T *)y); }
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
@@ -1416,7 +1597,24 @@ extern "C" int ks_dwconv3x3_bwd(int dtype, int N, int H, int W, int C, const voi
   const long long nblk = (long long)N * ((H + 1) / 2) * ((W + 1) / 2);
   const int gyb = (C / 8 + 31) / 32;
   int gxb = (kNumSMs * 2 + gyb - 1) / gyb; if (gxb > (nblk + 7) / 8) gxb = (int)((nblk + 7) / 8); if (gxb < 1) gxb = 1;
-#define CALL(T) { if (g_opt.dwconv_simple) { dwconv_kernel<T, true><<<grid, 256, 0, st>>>(N, H, W, C, (const T *)dy, w9, nullptr, (T *)dx); \
+  if (dtype == KS_BF16 && (g_opt.dwconv_simple == 0 || g_opt.dwconv_simple == 3)) {            // shared-memory tile kernels (the default for bf16)
+    static bool attr = false;
+    if (!attr) { cudaError_t e = cudaFuncSetAttribute(dwconv_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * DW_IN_BYTES);
+                 if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv_wgrad_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (DW_IN_BYTES + DW_OUT_BYTES));
+                 if (e != cudaSuccess) return (int)e; attr = true; }
+    const long long ntile = (long long)N * ((H + DWT - 1) / DWT) * ((W + DWT - 1) / DWT);
+    int gxt = (kNumSMs * 2 + gyb - 1) / gyb; if (gxt > ntile) gxt = (int)ntile;
+    int gxw = (kNumSMs + gyb - 1) / gyb; if (gxw > ntile) gxw = (int)ntile;
+    dwconv_tile_kernel<true><<<dim3(gxt, gyb), 256, 2 * DW_IN_BYTES, st>>>(N, H, W, C, (const __nv_bfloat16 *)dy, w9, nullptr, (__nv_bfloat16 *)dx);
+    // one-tile images (7x7, the last encoder stage) pay the whole halo for nothing and give a CTA 3-4 tiles: measured 63 us vs 41 us for the
+    // register-block kernel at 64 x 7x7 x 2048 (14x14 x 1280: 100 vs 97); option 3 keeps the tile kernel everywhere (tests)
+    if (H * W >= 100 || g_opt.dwconv_simple == 3)
+      dwconv_wgrad_tile_kernel<<<dim3(gxw, gyb), 512, 2 * (DW_IN_BYTES + DW_OUT_BYTES), st>>>(N, H, W, C, (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)dy, dw9, dbias);
+    else
+      dwconv_wgrad_block_kernel<__nv_bfloat16><<<dim3(gxb, gyb), 256, 0, st>>>(N, H, W, C, (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)dy, dw9, dbias);
+    KS_LAUNCH_RET();
+  }
+#define CALL(T) { if (g_opt.dwconv_simple == 1) { dwconv_kernel<T, true><<<grid, 256, 0, st>>>(N, H, W, C, (const T *)dy, w9, nullptr, (T *)dx); \
       dwconv_wgrad_kernel<T><<<dim3(gx, gy), 256, 0, st>>>(N, H, W, C, (const T *)x, (const T *)dy, dw9, dbias); } \
     else { dwconv_block_kernel<T, true><<<dim3(gxb, gyb), 256, 0, st>>>(N, H, W, C, (const T *)dy, w9, nullptr, (T *)dx); \
       dwconv_wgrad_block_kernel<T><<<dim3(gxb, gyb), 256, 0, st>>>(N, H, W, C, (const T *)x, (const T *)dy, dw9, dbias); } }

@@ -103,10 +103,13 @@ def test_xattention_fwd_bwd(ops, sh, dtype, B, Nq, Nk, heads, dh):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("simple", [0, 1])
-@pytest.mark.parametrize("N,H,W,C", [(2, 9, 7, 40), (2, 14, 14, 256), (1, 7, 7, 2048), (3, 1, 1, 8), (1, 2, 5, 520)])
+@pytest.mark.parametrize("simple", [0, 1, 2, 3])
+@pytest.mark.parametrize("N,H,W,C", [(2, 9, 7, 40), (2, 14, 14, 256), (1, 7, 7, 2048), (3, 1, 1, 8), (1, 2, 5, 520),
+                                     (8, 56, 56, 64), (20, 30, 23, 264)])      # the last two: several tiles per CTA (double-buffered pipeline), ragged tiles
 def test_dwconv_fwd_bwd(ops, sh, dtype, N, H, W, C, simple):
-    ops.set_option("dwconv_simple", simple)      # 0 = 2x2-block kernels (default), 1 = one output per thread; reset by the autouse fixture
+    # 0 = shared-memory tile kernels for bf16 (default; fp32 storage runs the 2x2-block kernels), 1 = one output per thread, 2 = 2x2 blocks,
+    # 3 = the tile kernels also for the weight gradient of images under 100 pixels (default: 2x2 blocks there)
+    ops.set_option("dwconv_simple", simple)      # reset by the autouse fixture
     g = torch.Generator().manual_seed(3)
     x, dy = _r((N * H * W, C), dtype, g), _r((N * H * W, C), dtype, g)
     w9, b = _r((9, C), torch.float32, g, 0.3), _r(C, torch.float32, g)
