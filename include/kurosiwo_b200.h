@@ -59,7 +59,8 @@ const char *ks_error_string(int code);
  * "wgrad_tc_disable", "tc_sa", "tc_sb" (pipeline depths); A/B switches that select the OLDER kernel of a pair (never needed for
  * correctness, every pair is parity-tested): "loss_variant" = 1 two-pass CE+Dice, "stem_simt" = 1 CUDA-core stem, "ecam_simt" = 1
  * CUDA-core ECAM classifier pass, "tc_stat_mode" = 1 shuffle-butterfly BatchNorm statistics everywhere, "att_no_umma" = 1 mma.sync ViT
- * attention; "xatt_umma" = 1 turns the tcgen05 forward of the ChangeFormer attention ON.  Returns KS_EINVAL for unknown names. */
+ * attention, "dwconv_simple" = 1 / 2 one-output-per-thread / 2x2-register-block depth-wise conv kernels (default 0: shared-memory tiles
+ * for bf16); "xatt_umma" = 1 turns the tcgen05 forward of the ChangeFormer attention ON.  Returns KS_EINVAL for unknown names. */
 int ks_set_option(const char *name, int value);
 /* Every knob back to its default (0).  The knobs are process-global: harnesses that toggle them call this when they are done. */
 int ks_reset_options(void);
@@ -333,7 +334,8 @@ int ks_im2col(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int ksize, int s
 int ks_col2im(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int ksize, int stride, int pad, const void *dcol, int Kp, const ks_view_t *dx,
               int accumulate, void *stream);
 /* Depth-wise 3x3 conv, padding 1 (DWConv, changeformer.py:84-96) on dense NHWC; w9: fp32 [9][C] (tap-major), bias fp32 [C].
- * _bwd: dx = data gradient; dw9 += weight gradient, dbias += bias gradient (fp32 atomics, caller zeroes). */
+ * _bwd: dx = data gradient; dw9 += weight gradient, dbias += bias gradient (fp32 atomics, caller zeroes).  y / dx are bit-identical
+ * across the kernel selections of "dwconv_simple" (bias, then nine fmaf in tap order). */
 int ks_dwconv3x3_fwd(int dtype, int N, int H, int W, int C, const void *x, const float *w9, const float *bias, void *y, void *stream);
 int ks_dwconv3x3_bwd(int dtype, int N, int H, int W, int C, const void *x, const void *dy, const float *w9, void *dx, float *dw9,
                      float *dbias, void *stream);
