@@ -60,7 +60,8 @@ const char *ks_error_string(int code);
  * correctness, every pair is parity-tested): "loss_variant" = 1 two-pass CE+Dice, "stem_simt" = 1 CUDA-core stem, "ecam_simt" = 1
  * CUDA-core ECAM classifier pass, "tc_stat_mode" = 1 shuffle-butterfly BatchNorm statistics everywhere, "att_no_umma" = 1 mma.sync ViT
  * attention, "dwconv_simple" = 1 / 2 one-output-per-thread / 2x2-register-block depth-wise conv kernels (default 0: shared-memory tiles
- * for bf16); "xatt_umma" = 1 turns the tcgen05 forward of the ChangeFormer attention ON.  Returns KS_EINVAL for unknown names. */
+ * for bf16), "cf_scalar" = 1 scalar Dropout / DropPath kernels and 64-bit index arithmetic in im2col / col2im / the sigmoid head;
+ * "xatt_umma" = 1 turns the tcgen05 forward of the ChangeFormer attention ON.  Returns KS_EINVAL for unknown names. */
 int ks_set_option(const char *name, int value);
 /* Every knob back to its default (0).  The knobs are process-global: harnesses that toggle them call this when they are done. */
 int ks_reset_options(void);

@@ -1243,32 +1243,47 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(long long n8, const T *__
   }
 }
 
-template <typename T>
-__device__ __forceinline__ T *cvp(const View &v, long long p, int H, int W, int c) {
-  const int w = (int)(p % W); const long long r = p / W; const int h = (int)(r % H); const long long n = r / H;
+// I = unsigned (pixel count < 2^31, the launcher's default) or long long: 64-bit div / mod made these per-pixel kernels issue-bound
+template <typename T, typename I>
+__device__ __forceinline__ T *cvp(const View &v, I p, int H, int W, int c) {
+  const int w = (int)(p % (I)W); const I r = p / (I)W; const int h = (int)(r % (I)H); const long long n = (long long)(r / (I)H);
   return reinterpret_cast<T *>(v.ptr) + (n * v.sn + (long long)h * v.sh + (long long)w * v.sw + c);
 }
-template <typename T>
+template <typename T, typename I>
 __global__ void __launch_bounds__(256)
 sigmoid_head_fwd_kernel(View z, int H, int W, long long NP, int K, float *__restrict__ out) {
-  const long long HW = (long long)H * W;
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < NP; p += (long long)gridDim.x * blockDim.x) {
-    const T *zp = cvp<T>(z, p, H, W, 0);
-    const long long n = p / HW, q = p % HW;
-    for (int k = 0; k < K; ++k) out[(n * K + k) * HW + q] = 1.f / (1.f + expf(-Cvt<T>::ld(zp + k)));
+  const I HW = (I)H * (I)W;
+  for (I p = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; p < (I)NP; p += (I)gridDim.x * (I)blockDim.x) {
+    const T *zp = cvp<T, I>(z, p, H, W, 0);
+    const long long n = (long long)(p / HW), q = (long long)(p % HW);
+    for (int k = 0; k < K; ++k) out[(n * K + k) * (long long)HW + q] = 1.f / (1.f + expf(-Cvt<T>::ld(zp + k)));
   }
 }
-template <typename T>
+// VEC: dz.C is a multiple of 8 and every pixel's channel vector is 16-byte aligned - one st8 per 8 channels instead of 8 scalar stores
+template <typename T, typename I, bool VEC>
 __global__ void __launch_bounds__(256)
 sigmoid_head_bwd_kernel(View dz, int H, int W, long long NP, int K, const float *__restrict__ out, const float *__restrict__ dout) {
-  const long long HW = (long long)H * W;
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < NP; p += (long long)gridDim.x * blockDim.x) {
-    T *dp = cvp<T>(dz, p, H, W, 0);
-    const long long n = p / HW, q = p % HW;
-    for (int c = 0; c < dz.C; ++c) {
-      float v = 0.f;
-      if (c < K) { const float y = out[(n * K + c) * HW + q]; v = dout[(n * K + c) * HW + q] * y * (1.f - y); }
-      Cvt<T>::st(dp + c, v);
+  const I HW = (I)H * (I)W;
+  for (I p = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; p < (I)NP; p += (I)gridDim.x * (I)blockDim.x) {
+    T *dp = cvp<T, I>(dz, p, H, W, 0);
+    const long long n = (long long)(p / HW), q = (long long)(p % HW);
+    if (VEC) {
+      for (int c0 = 0; c0 < dz.C; c0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = c0 + j;
+          v[j] = 0.f;
+          if (c < K) { const float y = out[(n * K + c) * (long long)HW + q]; v[j] = dout[(n * K + c) * (long long)HW + q] * y * (1.f - y); }
+        }
+        st8(dp + c0, v);
+      }
+    } else {
+      for (int c = 0; c < dz.C; ++c) {
+        float v = 0.f;
+        if (c < K) { const float y = out[(n * K + c) * (long long)HW + q]; v = dout[(n * K + c) * (long long)HW + q] * y * (1.f - y); }
+        Cvt<T>::st(dp + c, v);
+      }
     }
   }
 }
@@ -1304,6 +1319,47 @@ branch_kernel(long long n, long long per_sample, T *__restrict__ x, T *__restric
   }
 }
 
+// 16-byte variants (n, per_sample multiples of 8, n < 2^31): eight elements per thread, the same per-element RNG draw and the same
+// arithmetic expressions as the scalar kernels above (bit-identical results), one sample lookup per vector instead of a 64-bit division per
+// element.  The scalar kernels moved 2 bytes per thread and iteration and were issue-bound: 2.6 ms of the ChangeFormer bs=32 step.
+template <typename T>
+__global__ void __launch_bounds__(256)
+dropout_apply_vec_kernel(unsigned nv, const T *x, T *y, float p, unsigned long long seed, const int *step_ptr, int site) {
+  const unsigned long long key = cf_key(seed, step_ptr, site);
+  const float ik = 1.f / (1.f - p);
+  for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+    const unsigned long long i0 = (unsigned long long)v * 8;
+    float f[8];
+    ld8(x + i0, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = f[k] * cf_keep(key, i0 + k, p, ik);
+    st8(y + i0, f);
+  }
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+branch_vec_kernel(unsigned nv, unsigned per_sample_v, T *x, T *t, float p, const float *__restrict__ dp, unsigned long long seed, const int *step_ptr,
+                  int site) {
+  const unsigned long long key = cf_key(seed, step_ptr, site);
+  const float ik = 1.f / (1.f - p);
+  for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+    const unsigned long long i0 = (unsigned long long)v * 8;
+    const float d = dp ? dp[v / per_sample_v] : 1.f;
+    float xv[8], tv[8];
+    ld8(x + i0, xv);
+    if (MODE == 0) ld8(t + i0, tv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float f = (p > 0.f) ? cf_keep(key, i0 + k, p, ik) : 1.f;
+      if (dp) f *= d;
+      if (MODE == 0) xv[k] = xv[k] + f * tv[k];
+      else tv[k] = f * xv[k];
+    }
+    if (MODE == 0) st8(x + i0, xv); else st8(t + i0, tv);
+  }
+}
+
 static inline int cgrid(long long work, int per_block, int cap_mult = 8) {
   long long g = (work + per_block - 1) / per_block;
   const long long cap = (long long)kNumSMs * cap_mult;
@@ -1317,19 +1373,21 @@ static inline int cgrid(long long work, int per_block, int cap_mult = 8) {
 // forward = col x W^T (1x1 ks_conv2d), weight gradient = 1x1 ks_conv2d_wgrad(col, dy), data gradient = col2im(dy x W).
 // Pure data movement (HBM-bound): one 16-byte (bf16) / 32-byte (fp32) vector per thread.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int VEC>
+// I = unsigned (the launcher's choice whenever the item count is < 2^31) or long long: the six div / mod of the index decomposition in
+// 64-bit arithmetic are ~400 instructions per 16-byte vector - the kernel was issue-bound, not HBM-bound
+template <typename T, int VEC, typename I>
 __global__ void __launch_bounds__(256)
 im2col_kernel(int N, int Hi, int Wi, int Ho, int Wo, int k, int s, int p, View x, T *__restrict__ col, int Kp) {
   const int C = x.C, CV = C / VEC, taps = k * k;
-  const long long total = (long long)N * Ho * Wo * taps * CV;
+  const I total = (I)N * (I)Ho * (I)Wo * (I)taps * (I)CV;
   const T *xp = reinterpret_cast<const T *>(x.ptr);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % CV); const int t = (int)((i / CV) % taps); const long long row = i / ((long long)CV * taps);
-    const int wo = (int)(row % Wo), ho = (int)((row / Wo) % Ho); const long long n = row / ((long long)Wo * Ho);
+  for (I i = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; i < total; i += (I)gridDim.x * (I)blockDim.x) {
+    const int cv = (int)(i % (I)CV); const int t = (int)((i / (I)CV) % (I)taps); const I row = i / ((I)CV * (I)taps);
+    const int wo = (int)(row % (I)Wo), ho = (int)((row / (I)Wo) % (I)Ho); const long long n = (long long)(row / ((I)Wo * (I)Ho));
     const int h = ho * s - p + t / k, w = wo * s - p + t % k;
     const bool in = h >= 0 && h < Hi && w >= 0 && w < Wi;
     const T *src = xp + n * x.sn + (long long)h * x.sh + (long long)w * x.sw + cv * VEC;
-    T *dst = col + row * Kp + (long long)t * C + cv * VEC;
+    T *dst = col + (long long)row * Kp + (long long)t * C + cv * VEC;
     if (VEC == 1) dst[0] = in ? src[0] : T(0.f);
     else {
       constexpr int NV = (VEC * (int)sizeof(T)) / 16;
@@ -1341,15 +1399,15 @@ im2col_kernel(int N, int Hi, int Wi, int Ho, int Wo, int k, int s, int p, View x
 }
 
 // dx[n,h,w,c] (+)= sum over the windows (ho,wo) that contain (h,w) of dcol[(n,ho,wo)][(u*k+v)*C + c], u = h+p-ho*s, v = w+p-wo*s
-template <typename T>
+template <typename T, typename I>
 __global__ void __launch_bounds__(256)
 col2im_kernel(int N, int Hi, int Wi, int Ho, int Wo, int k, int s, int p, const T *__restrict__ dcol, int Kp, View dx, int accumulate) {
   const int C = dx.C, CV = C / 8;
-  const long long total = (long long)N * Hi * Wi * CV;
+  const I total = (I)N * (I)Hi * (I)Wi * (I)CV;
   T *dp = reinterpret_cast<T *>(dx.ptr);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % CV) * 8; const long long px = i / CV;
-    const int w = (int)(px % Wi), h = (int)((px / Wi) % Hi); const long long n = px / ((long long)Wi * Hi);
+  for (I i = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; i < total; i += (I)gridDim.x * (I)blockDim.x) {
+    const int c = (int)(i % (I)CV) * 8; const I px = i / (I)CV;
+    const int w = (int)(px % (I)Wi), h = (int)((px / (I)Wi) % (I)Hi); const long long n = (long long)(px / ((I)Wi * (I)Hi));
     float acc[8];
     T *out = dp + n * dx.sn + (long long)h * dx.sh + (long long)w * dx.sw + c;
     if (accumulate) ld8(out, acc); else {
@@ -1537,8 +1595,11 @@ extern "C" int ks_im2col(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int k
                    ((long long)Kp * es) % 16 == 0;
   const long long items = (long long)N * Ho * Wo * ksize * ksize * (vec ? xv.C / 8 : xv.C);
   const int grid = cgrid(items, 256);
-#define CALL(T) { if (vec) im2col_kernel<T, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, ksize, stride, pad, xv, (T *)col, Kp); \
-                  else im2col_kernel<T, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, ksize, stride, pad, xv, (T *)col, Kp); }
+  const bool i32 = items < (1LL << 31) && !g_opt.cf_scalar;
+#define CALL(T) { if (vec && i32) im2col_kernel<T, 8, unsigned><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, ksize, stride, pad, xv, (T *)col, Kp); \
+                  else if (vec) im2col_kernel<T, 8, long long><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, ksize, stride, pad, xv, (T *)col, Kp); \
+                  else if (i32) im2col_kernel<T, 1, unsigned><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, ksize, stride, pad, xv, (T *)col, Kp); \
+                  else im2col_kernel<T, 1, long long><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, ksize, stride, pad, xv, (T *)col, Kp); }
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();
@@ -1552,8 +1613,11 @@ extern "C" int ks_col2im(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int k
   const int es = (dtype == KS_F32) ? 4 : 2;
   if (dv.C % 8 || !a16(dv.ptr) || !a16(dcol) || (dv.sn * es) % 16 || (dv.sh * es) % 16 || (dv.sw * es) % 16 || ((long long)Kp * es) % 16)
     return KS_EUNSUPPORTED;
-  const int grid = cgrid((long long)N * Hi * Wi * (dv.C / 8), 256);
-#define CALL(T) col2im_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, ksize, stride, pad, (const T *)dcol, Kp, dv, accumulate)
+  const long long items = (long long)N * Hi * Wi * (dv.C / 8);
+  const int grid = cgrid(items, 256);
+  const bool i32 = items < (1LL << 31) && !g_opt.cf_scalar;
+#define CALL(T) { if (i32) col2im_kernel<T, unsigned><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, ksize, stride, pad, (const T *)dcol, Kp, dv, accumulate); \
+                  else col2im_kernel<T, long long><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, ksize, stride, pad, (const T *)dcol, Kp, dv, accumulate); }
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();
@@ -1667,7 +1731,9 @@ extern "C" int ks_sigmoid_head_fwd(int dtype, int N, int H, int W, const ks_view
   KS_CHECK_ARG(N > 0 && H > 0 && W > 0 && z && z->ptr && out && K > 0 && K <= z->C);
   const long long NP = (long long)N * H * W;
   const int grid = cgrid(NP, 256);
-#define CALL(T) sigmoid_head_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(to_view(*z), H, W, NP, K, out)
+  const bool i32 = NP < (1LL << 31) && !g_opt.cf_scalar;
+#define CALL(T) { if (i32) sigmoid_head_fwd_kernel<T, unsigned><<<grid, 256, 0, (cudaStream_t)stream>>>(to_view(*z), H, W, NP, K, out); \
+                  else sigmoid_head_fwd_kernel<T, long long><<<grid, 256, 0, (cudaStream_t)stream>>>(to_view(*z), H, W, NP, K, out); }
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();
@@ -1677,7 +1743,13 @@ extern "C" int ks_sigmoid_head_bwd(int dtype, int N, int H, int W, const float *
   KS_CHECK_ARG(N > 0 && H > 0 && W > 0 && dz && dz->ptr && out && dout && K > 0 && K <= dz->C);
   const long long NP = (long long)N * H * W;
   const int grid = cgrid(NP, 256);
-#define CALL(T) sigmoid_head_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(to_view(*dz), H, W, NP, K, out, dout)
+  const View dv = to_view(*dz);
+  const int es = (dtype == KS_F32) ? 4 : 2;
+  const bool i32 = NP < (1LL << 31) && !g_opt.cf_scalar;
+  const bool vec = i32 && dv.C % 8 == 0 && a16(dv.ptr) && (dv.sn * es) % 16 == 0 && (dv.sh * es) % 16 == 0 && (dv.sw * es) % 16 == 0;
+#define CALL(T) { if (vec) sigmoid_head_bwd_kernel<T, unsigned, true><<<grid, 256, 0, (cudaStream_t)stream>>>(dv, H, W, NP, K, out, dout); \
+                  else if (i32) sigmoid_head_bwd_kernel<T, unsigned, false><<<grid, 256, 0, (cudaStream_t)stream>>>(dv, H, W, NP, K, out, dout); \
+                  else sigmoid_head_bwd_kernel<T, long long, false><<<grid, 256, 0, (cudaStream_t)stream>>>(dv, H, W, NP, K, out, dout); }
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();
@@ -1686,7 +1758,9 @@ extern "C" int ks_sigmoid_head_bwd(int dtype, int N, int H, int W, const float *
 extern "C" int ks_dropout_apply(int dtype, int64_t n, const void *x, void *y, float p, uint64_t seed, const int *step_ptr, int site, void *stream) {
   KS_CHECK_ARG(n > 0 && x && y && p >= 0.f && p < 1.f);
   const int grid = cgrid(n, 256 * 8);
-#define CALL(T) dropout_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(n, (const T *)x, (T *)y, p, seed, step_ptr, site)
+  const bool vec = n % 8 == 0 && n < (1LL << 31) && a16(x) && a16(y) && !g_opt.cf_scalar;
+#define CALL(T) { if (vec) dropout_apply_vec_kernel<T><<<cgrid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((unsigned)(n / 8), (const T *)x, (T *)y, p, seed, step_ptr, site); \
+                  else dropout_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(n, (const T *)x, (T *)y, p, seed, step_ptr, site); }
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();
@@ -1696,7 +1770,9 @@ extern "C" int ks_branch_add(int dtype, int64_t n, int64_t per_sample, void *x, 
                              const int *step_ptr, int site, void *stream) {
   KS_CHECK_ARG(n > 0 && per_sample > 0 && x && t && p >= 0.f && p < 1.f);
   const int grid = cgrid(n, 256 * 8);
-#define CALL(T) branch_kernel<T, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(n, per_sample, (T *)x, (T *)t, p, droppath, seed, step_ptr, site)
+  const bool vec = n % 8 == 0 && per_sample % 8 == 0 && n < (1LL << 31) && a16(x) && a16(t) && !g_opt.cf_scalar;
+#define CALL(T) { if (vec) branch_vec_kernel<T, 0><<<cgrid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((unsigned)(n / 8), (unsigned)(per_sample / 8), (T *)x, (T *)t, p, droppath, seed, step_ptr, site); \
+                  else branch_kernel<T, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(n, per_sample, (T *)x, (T *)t, p, droppath, seed, step_ptr, site); }
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();
@@ -1706,7 +1782,9 @@ extern "C" int ks_branch_scale(int dtype, int64_t n, int64_t per_sample, const v
                                const int *step_ptr, int site, void *stream) {
   KS_CHECK_ARG(n > 0 && per_sample > 0 && dx && dt && p >= 0.f && p < 1.f);
   const int grid = cgrid(n, 256 * 8);
-#define CALL(T) branch_kernel<T, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(n, per_sample, (T *)dx, (T *)dt, p, droppath, seed, step_ptr, site)
+  const bool vec = n % 8 == 0 && per_sample % 8 == 0 && n < (1LL << 31) && a16(dx) && a16(dt) && !g_opt.cf_scalar;
+#define CALL(T) { if (vec) branch_vec_kernel<T, 1><<<cgrid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((unsigned)(n / 8), (unsigned)(per_sample / 8), (T *)dx, (T *)dt, p, droppath, seed, step_ptr, site); \
+                  else branch_kernel<T, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(n, per_sample, (T *)dx, (T *)dt, p, droppath, seed, step_ptr, site); }
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();

@@ -12,7 +12,7 @@ namespace ks {
 
 constexpr int kNumSMs = 148;
 
-struct Options { int mt, bo_mode, tc_disable, wgrad_tc_disable, sa, sb, v1, no_resident, debug, tb, wgrad_mode, att_simt, ew_cap, no_ns3, ns3_min_cin, ns3_mode, nacc, loss_chunks, loss_no_pdl, loss_no_bulk, loss_variant, ew, att_no_umma, cs_rows, ln_rows, stem_simt, ecam_simt, xatt_umma, stat_mode, dwconv_simple; };
+struct Options { int mt, bo_mode, tc_disable, wgrad_tc_disable, sa, sb, v1, no_resident, debug, tb, wgrad_mode, att_simt, ew_cap, no_ns3, ns3_min_cin, ns3_mode, nacc, loss_chunks, loss_no_pdl, loss_no_bulk, loss_variant, ew, att_no_umma, cs_rows, ln_rows, stem_simt, ecam_simt, xatt_umma, stat_mode, dwconv_simple, cf_scalar; };
 extern Options g_opt;
 
 template <typename T> struct Cvt;

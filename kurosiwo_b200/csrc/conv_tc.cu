@@ -892,6 +892,7 @@ extern "C" int ks_set_option(const char *name, int value) {
   else if (eq("ecam_simt")) ks::g_opt.ecam_simt = value;   // 1 = CUDA-core ECAM final pass also for bf16 (A/B comparisons)
   else if (eq("xatt_umma")) ks::g_opt.xatt_umma = value;   // 1 = tcgen05 forward of the ChangeFormer spatial-reduction attention (default: mma.sync)
   else if (eq("tc_stat_mode")) ks::g_opt.stat_mode = value;   // 1 = shuffle butterfly for every BatchNorm-statistics epilogue (A/B comparisons)
+  else if (eq("cf_scalar")) ks::g_opt.cf_scalar = value;   // 1 = scalar Dropout / DropPath kernels and 64-bit index arithmetic in im2col / col2im (A/B comparisons)
   else if (eq("dwconv_simple")) ks::g_opt.dwconv_simple = value;   // depth-wise conv kernels: 0 = shared-memory tiles (bf16) / 2x2 blocks (fp32), 1 = one output per thread, 2 = 2x2 register blocks, 3 = tiles also for the weight gradient of tiny images (A/B, tests)
   else if (eq("att_no_umma")) ks::g_opt.att_no_umma = value;   // 1 = mma.sync attention forward instead of the tcgen05 kernel (A/B comparisons)
   else if (eq("att_simt")) ks::g_opt.att_simt = value;   // 1 = CUDA-core attention kernels also for bf16 (A/B comparisons)

@@ -155,16 +155,21 @@ def test_relu_and_sigmoid_head(ops, sh, dtype):
     sh.relu_bwd(y, gg, dx); ops.relu_bwd(yd, gg.to(DEV), dxd)
     assert torch.equal(dxd.cpu(), dx)
     N, H, W, K = 2, 6, 10, 3
-    z, _ = rand_view(N, H, W, 16, dtype, DEV, gen=g)
-    cz = mirror(z)
-    out, outd = torch.zeros(N, K, H, W), torch.zeros(N, K, H, W, device=DEV)
-    sh.sigmoid_head_fwd(cz, K, out); ops.sigmoid_head_fwd(z, K, outd)
-    assert rel_l2(outd, out) < 1e-6
-    dout = torch.randn(N, K, H, W, generator=g)
-    dz, _ = rand_view(N, H, W, 16, dtype, DEV, gen=g)
-    cdz = mirror(dz)
-    sh.sigmoid_head_bwd(out, dout, K, cdz); ops.sigmoid_head_bwd(outd, dout.to(DEV), K, dz)
-    assert rel_l2(dz.base.float(), cdz.base.float()) < _tol(dtype)
+    # (C, ctot, c0): dense 16 channels and an aligned 8-channel slice (16-byte stores), a 12-channel slice at channel 4 (scalar stores);
+    # wide = 1: the 64-bit index arithmetic (`cf_scalar`)
+    for C, ctot, c0 in ((16, 16, 0), (8, 24, 8), (12, 16, 4)):
+        for wide in (0, 1):
+            ops.set_option("cf_scalar", wide)
+            z, _ = rand_view(N, H, W, C, dtype, DEV, ctot=ctot, c0=c0, gen=g)
+            cz = mirror(z)
+            out, outd = torch.zeros(N, K, H, W), torch.zeros(N, K, H, W, device=DEV)
+            sh.sigmoid_head_fwd(cz, K, out); ops.sigmoid_head_fwd(z, K, outd)
+            assert rel_l2(outd, out) < 1e-6
+            dout = torch.randn(N, K, H, W, generator=g)
+            dz, _ = rand_view(N, H, W, C, dtype, DEV, ctot=ctot, c0=c0, gen=g)
+            cdz = mirror(dz)
+            sh.sigmoid_head_bwd(out, dout, K, cdz); ops.sigmoid_head_bwd(outd, dout.to(DEV), K, dz)
+            assert rel_l2(dz.base.float(), cdz.base.float()) < _tol(dtype)     # the whole buffer: channels outside the slice untouched
 
 
 def test_permute_table_scale(ops):
@@ -177,9 +182,12 @@ def test_permute_table_scale(ops):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("wide", [0, 1])
 @pytest.mark.parametrize("k,s,p,cin,H", [(7, 4, 3, 2, 32), (7, 2, 3, 64, 16), (8, 8, 0, 64, 16), (2, 2, 0, 40, 14), (3, 1, 1, 16, 9)])
-def test_im2col_col2im(ops, sh, dtype, k, s, p, cin, H):
-    """ks_im2col is pure data movement (bit-exact, also on a strided source view); ks_col2im is its adjoint in gather form."""
+def test_im2col_col2im(ops, sh, dtype, k, s, p, cin, H, wide):
+    """ks_im2col is pure data movement (bit-exact, also on a strided source view); ks_col2im is its adjoint in gather form.
+    wide = 1: the 64-bit index decomposition (`cf_scalar`; the default takes 32-bit arithmetic whenever the item count is < 2^31)."""
+    ops.set_option("cf_scalar", wide)           # reset by the autouse fixture
     g = torch.Generator().manual_seed(4)
     N, W = 2, H + 4
     Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
@@ -199,3 +207,38 @@ def test_im2col_col2im(ops, sh, dtype, k, s, p, cin, H):
             ops.col2im(N, H, W, Ho, Wo, k, s, p, dcol.to(DEV), Kp, dx, acc)
             sh.col2im(N, H, W, Ho, Wo, k, s, p, dcol, Kp, cdx, acc)
             assert rel_l2(dx.base.float(), cdx.base.float()) < _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dropout_branch_vector_kernels_equal_scalar(ops, sh, dtype):
+    """The 16-byte Dropout / DropPath kernels (default) draw the same per-element masks and evaluate the same expressions as the scalar
+    kernels (`cf_scalar` = 1): bit-identical results; both against the numpy restatement of the RNG (tests/shadow_ops.py)."""
+    g = torch.Generator().manual_seed(12)
+    B, per = 5, 40 * 24                                              # per_sample % 8 == 0: a 16-byte vector never straddles two samples
+    n = B * per
+    step = torch.tensor([7], dtype=torch.int32)
+    x, t = _r(n, dtype, g), _r(n, dtype, g)
+    dp = torch.tensor([1.25, 0.0, 1.25, 1.25, 0.0])
+    res = {}
+    for scalar in (0, 1):
+        ops.set_option("cf_scalar", scalar)
+        out = []
+        for p, dpv in ((0.1, dp), (0.1, None), (0.0, dp)):
+            y = torch.zeros(n, dtype=dtype, device=DEV)
+            ops.dropout_apply(x.to(DEV), y, max(p, 0.05), 99, step.to(DEV), 5)
+            xa = x.to(DEV)
+            ops.branch_add(xa, t.to(DEV), per, p, None if dpv is None else dpv.to(DEV), 99, step.to(DEV), 6)
+            dt = torch.zeros(n, dtype=dtype, device=DEV)
+            ops.branch_scale(x.to(DEV), dt, per, p, None if dpv is None else dpv.to(DEV), 99, step.to(DEV), 6)
+            xin = x.to(DEV)
+            ops.dropout_apply(xin, xin, 0.1, 99, step.to(DEV), 7)     # in place, as the engine calls it
+            out += [y.cpu(), xa.cpu(), dt.cpu(), xin.cpu()]
+        res[scalar] = out
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b)
+    ys = torch.zeros_like(x)
+    sh.dropout_apply(x, ys, 0.1, 99, step, 5)
+    assert torch.equal(res[0][0], ys)
+    xs = x.clone()
+    sh.branch_add(xs, t, per, 0.1, dp, 99, step, 6)
+    assert torch.allclose(res[0][1].float(), xs.float(), rtol=1e-2 if dtype == torch.bfloat16 else 1e-6, atol=1e-2 if dtype == torch.bfloat16 else 1e-6)
