@@ -1151,15 +1151,17 @@ __device__ __forceinline__ void bl_src(int d, float ratio, int in, int &i0, int 
   l1 = s - (float)i0;
 }
 
-template <typename T>
+// I = unsigned (item count < 2^31, the launcher's default) or long long for the index decomposition (see im2col_kernel)
+template <typename T, typename I>
 __global__ void __launch_bounds__(256)
 bilinear_nhwc_fwd_kernel(int N, int Hi, int Wi, int Ho, int Wo, int C, const T *__restrict__ src, T *__restrict__ dst, int accumulate) {
   const int CV = C / 8;
-  const long long total = (long long)N * Ho * Wo * CV;
+  const I total = (I)N * (I)Ho * (I)Wo * (I)CV;
   const float ry = (float)Hi / (float)Ho, rx = (float)Wi / (float)Wo;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % CV) * 8; const long long p = i / CV;
-    const int x = (int)(p % Wo), y = (int)((p / Wo) % Ho); const long long n = p / ((long long)Wo * Ho);
+  for (I i = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; i < total; i += (I)gridDim.x * (I)blockDim.x) {
+    const int c = (int)(i % (I)CV) * 8; const long long p = (long long)(i / (I)CV);
+    const I pi = i / (I)CV;
+    const int x = (int)(pi % (I)Wo), y = (int)((pi / (I)Wo) % (I)Ho); const long long n = (long long)(pi / ((I)Wo * (I)Ho));
     int y0, y1, x0, x1; float ly, lx;
     bl_src(y, ry, Hi, y0, y1, ly); bl_src(x, rx, Wi, x0, x1, lx);
     float a[8], b[8], cc[8], d[8], o[8];
@@ -1176,15 +1178,16 @@ bilinear_nhwc_fwd_kernel(int N, int Hi, int Wi, int Ho, int Wo, int C, const T *
   }
 }
 
-template <typename T>
+template <typename T, typename I>
 __global__ void __launch_bounds__(256)
 bilinear_nhwc_bwd_kernel(int N, int Hi, int Wi, int Ho, int Wo, int C, const T *__restrict__ ddst, T *__restrict__ dsrc, int accumulate) {
   const int CV = C / 8;
-  const long long total = (long long)N * Hi * Wi * CV;
+  const I total = (I)N * (I)Hi * (I)Wi * (I)CV;
   const float ry = (float)Hi / (float)Ho, rx = (float)Wi / (float)Wo;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % CV) * 8; const long long p = i / CV;
-    const int gx = (int)(p % Wi), gy = (int)((p / Wi) % Hi); const long long n = p / ((long long)Wi * Hi);
+  for (I i = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; i < total; i += (I)gridDim.x * (I)blockDim.x) {
+    const int c = (int)(i % (I)CV) * 8; const long long p = (long long)(i / (I)CV);
+    const I pi = i / (I)CV;
+    const int gx = (int)(pi % (I)Wi), gy = (int)((pi / (I)Wi) % (I)Hi); const long long n = (long long)(pi / ((I)Wi * (I)Hi));
     int ylo = (int)floorf(((float)gy - 0.5f) / ry - 0.5f) - 1, yhi = (int)ceilf(((float)gy + 1.5f) / ry - 0.5f) + 1;
     int xlo = (int)floorf(((float)gx - 0.5f) / rx - 0.5f) - 1, xhi = (int)ceilf(((float)gx + 1.5f) / rx - 0.5f) + 1;
     if (gy == 0) ylo = 0;
@@ -1690,8 +1693,11 @@ extern "C" int ks_dwconv3x3_bwd(int dtype, int N, int H, int W, int C, const voi
 extern "C" int ks_bilinear_nhwc_fwd(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int C, const void *src, void *dst, int accumulate, void *stream) {
   KS_CHECK_ARG(N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && src && dst);
   if (C % 8 || !a16(src) || !a16(dst)) return KS_EUNSUPPORTED;
-  const int grid = cgrid((long long)N * Ho * Wo * (C / 8), 256);
-#define CALL(T) bilinear_nhwc_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, C, (const T *)src, (T *)dst, accumulate)
+  const long long items = (long long)N * Ho * Wo * (C / 8);
+  const int grid = cgrid(items, 256);
+  const bool i32 = items < (1LL << 31) && (long long)N * Hi * Wi * (C / 8) < (1LL << 31) && !g_opt.cf_scalar;
+#define CALL(T) { if (i32) bilinear_nhwc_fwd_kernel<T, unsigned><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, C, (const T *)src, (T *)dst, accumulate); \
+                  else bilinear_nhwc_fwd_kernel<T, long long><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, C, (const T *)src, (T *)dst, accumulate); }
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();
@@ -1700,8 +1706,11 @@ extern "C" int ks_bilinear_nhwc_fwd(int dtype, int N, int Hi, int Wi, int Ho, in
 extern "C" int ks_bilinear_nhwc_bwd(int dtype, int N, int Hi, int Wi, int Ho, int Wo, int C, const void *ddst, void *dsrc, int accumulate, void *stream) {
   KS_CHECK_ARG(N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && ddst && dsrc);
   if (C % 8 || !a16(ddst) || !a16(dsrc)) return KS_EUNSUPPORTED;
-  const int grid = cgrid((long long)N * Hi * Wi * (C / 8), 256, 16);
-#define CALL(T) bilinear_nhwc_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, C, (const T *)ddst, (T *)dsrc, accumulate)
+  const long long items = (long long)N * Hi * Wi * (C / 8);
+  const int grid = cgrid(items, 256, 16);
+  const bool i32 = items < (1LL << 31) && !g_opt.cf_scalar;
+#define CALL(T) { if (i32) bilinear_nhwc_bwd_kernel<T, unsigned><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, C, (const T *)ddst, (T *)dsrc, accumulate); \
+                  else bilinear_nhwc_bwd_kernel<T, long long><<<grid, 256, 0, (cudaStream_t)stream>>>(N, Hi, Wi, Ho, Wo, C, (const T *)ddst, (T *)dsrc, accumulate); }
   KS_DISPATCH_T(dtype, CALL);
 #undef CALL
   KS_LAUNCH_RET();

@@ -127,8 +127,10 @@ def test_dwconv_fwd_bwd(ops, sh, dtype, N, H, W, C, simple):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("wide", [0, 1])
 @pytest.mark.parametrize("Hi,Ho", [(7, 14), (7, 56), (14, 56), (5, 12)])
-def test_bilinear_nhwc_fwd_bwd(ops, sh, dtype, Hi, Ho):
+def test_bilinear_nhwc_fwd_bwd(ops, sh, dtype, Hi, Ho, wide):
+    ops.set_option("cf_scalar", wide)           # 1 = 64-bit index decomposition; reset by the autouse fixture
     g = torch.Generator().manual_seed(4)
     N, C = 2, 24
     Wi, Wo = Hi + 1, (Hi + 1) * Ho // Hi
